@@ -1,0 +1,108 @@
+"""In-tree build of the native pieces (explicit nvcc / g++; no JIT cache, the .so files travel with the repo).
+
+    libmirogpu.so          the product: C ABI (include/mirogpu.h) + sm_100a kernels + host BVH builder
+    libmiro_host.so        the host API layer (reference Object/BVH/Scene/Camera interfaces) over that C ABI
+    tests/cpu_emu/libmiro_emu.so   test-only host emulation of the traversal cores (never shipped)
+"""
+import os
+import shutil
+import subprocess
+import sys
+
+PKG = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(PKG)
+CSRC = os.path.join(PKG, "csrc")
+LIB = os.path.join(PKG, "libmirogpu.so")
+HOST_LIB = os.path.join(PKG, "libmiro_host.so")
+EMU_LIB = os.path.join(ROOT, "tests", "cpu_emu", "libmiro_emu.so")
+HOSTTEST = os.path.join(ROOT, "tests", "cpp", "miro_host_test")
+
+NVCC = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
+GXX = "/usr/bin/g++" if os.path.exists("/usr/bin/g++") else "g++"
+ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
+NVCC_FLAGS = ARCH + ["-lineinfo", "-O3", "-std=c++17", "-ccbin", GXX, "-Xcompiler", "-fPIC,-fopenmp,-ffp-contract=off"]
+GXX_FLAGS = ["-O3", "-std=c++17", "-fPIC", "-fopenmp", "-ffp-contract=off", "-Wall"]
+
+
+def _run(cmd, verbose):
+    if verbose:
+        print(" ".join(cmd), flush=True)
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    if r.returncode != 0:
+        sys.stderr.write(r.stdout + r.stderr)
+        raise RuntimeError("build step failed: " + " ".join(cmd))
+    return r.stdout + r.stderr
+
+
+def _newer(target, sources):
+    if not os.path.exists(target):
+        return False
+    t = os.path.getmtime(target)
+    return all(os.path.getmtime(s) <= t for s in sources)
+
+
+def _sources(*dirs):
+    out = []
+    for d in dirs:
+        for base, _, files in os.walk(d):
+            for f in files:
+                if f.endswith((".cu", ".cuh", ".cpp", ".h")):
+                    out.append(os.path.join(base, f))
+    return out
+
+
+def build_product(force=False, verbose=False, ptxas_v=False):
+    srcs = _sources(CSRC, os.path.join(ROOT, "include"))
+    if not force and _newer(LIB, srcs):
+        return LIB
+    bdir = os.path.join(ROOT, "build")
+    os.makedirs(bdir, exist_ok=True)
+    _run([GXX] + GXX_FLAGS + ["-c", os.path.join(CSRC, "bvh_build.cpp"), "-o", os.path.join(bdir, "bvh_build.o")], verbose)
+    flags = list(NVCC_FLAGS) + (["-Xptxas", "-v"] if ptxas_v else [])
+    log = _run([NVCC] + flags + ["-c", os.path.join(CSRC, "mirogpu.cu"), "-o", os.path.join(bdir, "mirogpu.o")], verbose)
+    if ptxas_v:
+        print(log)
+    _run([NVCC] + ARCH + ["-ccbin", GXX, "-shared", "-o", LIB, os.path.join(bdir, "mirogpu.o"), os.path.join(bdir, "bvh_build.o"),
+                          "-Xcompiler", "-fopenmp", "-lgomp"], verbose)
+    return LIB
+
+
+def build_host(force=False, verbose=False):
+    mdir = os.path.join(CSRC, "miro")
+    srcs = _sources(mdir, os.path.join(ROOT, "include"))
+    if not force and _newer(HOST_LIB, srcs + [LIB]):
+        return HOST_LIB
+    _run([GXX] + GXX_FLAGS + ["-shared", "-o", HOST_LIB, os.path.join(mdir, "miro_host.cpp"), os.path.join(mdir, "miro_host_capi.cpp"),
+                              "-L" + PKG, "-lmirogpu", "-Wl,-rpath,$ORIGIN"], verbose)
+    return HOST_LIB
+
+
+def build_emulation(force=False, verbose=False):
+    src = os.path.join(ROOT, "tests", "cpu_emu", "emu.cu")
+    srcs = [src] + _sources(CSRC)
+    if not force and _newer(EMU_LIB, srcs):
+        return EMU_LIB
+    bdir = os.path.join(ROOT, "build")
+    os.makedirs(bdir, exist_ok=True)
+    _run([GXX] + GXX_FLAGS + ["-c", os.path.join(CSRC, "bvh_build.cpp"), "-o", os.path.join(bdir, "bvh_build.o")], verbose)
+    _run([NVCC] + NVCC_FLAGS + ["-shared", "-o", EMU_LIB, src, os.path.join(bdir, "bvh_build.o"), "-lgomp"], verbose)
+    return EMU_LIB
+
+
+def build_oracle(verbose=False):
+    """Builds the checkers: the CPU restatement always, oracle/_ref only where /root/reference exists."""
+    odir = os.path.join(ROOT, "oracle")
+    _run(["make", "-C", odir, "oracle"], verbose)
+    if os.path.isdir("/root/reference"):
+        _run(["make", "-C", odir, "ref"], verbose)
+
+
+def build_all(force=False, verbose=False):
+    build_product(force, verbose)
+    build_host(force, verbose)
+    build_emulation(force, verbose)
+    build_oracle(verbose)
+
+
+if __name__ == "__main__":
+    build_all(force="--force" in sys.argv, verbose=True)

@@ -1,0 +1,94 @@
+// bvh_build.h -- host-side acceleration-structure construction for the B200 engine.
+//
+// Replaces BVH::build (reference BVH.cpp:60-339) on the product path.  The reference grows a pointer
+// tree by a 32-step binary search on the split plane per axis; here a binned-SAH binary tree is built
+// over conservative triangle bounds and then flattened into one of two GPU layouts:
+//   * BVH2  -- 64-byte nodes holding both children's boxes (two children per fetch), and
+//   * CWBVH8 -- 80-byte 8-wide nodes with child boxes quantised to 8 bits on a per-node grid
+//     (compressed wide BVH), children slotted for octant-ordered traversal.
+// Triangles are re-ordered into leaf (spatial) order so a leaf's triangles are one contiguous 48-byte-
+// strided run in HBM.
+//
+// Box contract (what makes the flat tree a drop-in for the reference's): every box contains, with
+// margin, every point at which Triangle::intersect (Triangle.cpp:136-169) can accept a hit on the
+// triangles below it -- i.e. the triangle grown by the reference's epsilon slop in barycentric space
+// (beta, gamma >= -eps, beta+gamma <= 1+eps) plus an absolute pad >= the reference's own epsilon pad
+// (BVH.cpp:75-79).  tests/test_flat_bvh.py checks this for every node of both layouts.
+#ifndef MIROGPU_BVH_BUILD_H
+#define MIROGPU_BVH_BUILD_H
+
+#include <cstdint>
+#include <vector>
+
+namespace mirogpu {
+
+struct Aabb {
+    float lo[3], hi[3];
+};
+
+struct BinaryNode {
+    Aabb box;
+    int32_t left, right;    // children (internal) or -1 (leaf)
+    uint32_t first, count;  // leaf: range in BinaryBvh::order
+};
+
+struct BinaryBvh {
+    std::vector<BinaryNode> nodes;  // nodes[0] is the root
+    std::vector<uint32_t> order;    // primitive ids in leaf order
+    uint32_t num_leaves = 0;
+    uint32_t max_depth = 0;
+};
+
+// Conservative bounds of one triangle (9 floats A,B,C): slop-grown triangle + absolute pad.
+void triangle_bounds(const float* v9, Aabb& out);
+
+BinaryBvh build_binary_sah(const float* tri_vertices, uint32_t ntris, int max_leaf, int bins);
+
+// ---- BVH2 flat layout (64 B / node) -----------------------------------------------------------------
+// f[0..3]  = child0 lo.x, hi.x, lo.y, hi.y      f[4..7] = child1 lo.x, hi.x, lo.y, hi.y
+// f[8..11] = child0 lo.z, hi.z, child1 lo.z, hi.z
+// link[0], link[1] = child references: >= 0 internal node index; < 0 leaf: ~((first << 3) | (count-1))
+struct Bvh2Node {
+    float f[12];
+    int32_t link[4];
+};
+static_assert(sizeof(Bvh2Node) == 64, "Bvh2Node must be 64 bytes");
+
+// ---- CWBVH8 flat layout (80 B / node) ----------------------------------------------------------------
+struct Cwbvh8Node {
+    float p[3];          // quantisation grid origin (node box min)
+    uint8_t e[3];        // per-axis biased exponent: cell size = 2^(e-127)
+    uint8_t imask;       // bit s set: slot s holds an internal child
+    uint32_t child_base; // index of the first internal child; child of slot s = base + popc(imask & ((1<<s)-1))
+    uint32_t tri_base;   // first triangle of this node's leaf children
+    uint8_t meta[8];     // 0 empty | internal: 0x20 | (24+s) | leaf: (unary count)<<5 | triangle offset
+    uint8_t qlox[8], qloy[8], qloz[8];
+    uint8_t qhix[8], qhiy[8], qhiz[8];
+};
+static_assert(sizeof(Cwbvh8Node) == 80, "Cwbvh8Node must be 80 bytes");
+
+// 48-byte triangle record in leaf order: A.xyz + prim id bits, B-A, C-A (the two edge vectors exactly as
+// Triangle.cpp:150 forms them in binary32).
+struct TriRecord {
+    float ax, ay, az;
+    uint32_t prim_id;
+    float e1x, e1y, e1z, pad0;
+    float e2x, e2y, e2z, pad1;
+};
+static_assert(sizeof(TriRecord) == 48, "TriRecord must be 48 bytes");
+
+struct FlatBvh {
+    int layout = 0;
+    std::vector<Bvh2Node> nodes2;
+    std::vector<Cwbvh8Node> nodes8;
+    std::vector<uint32_t> order;  // flat triangle slot -> prim id
+    Aabb root;
+    uint32_t max_depth = 0;
+};
+
+void flatten_bvh2(const BinaryBvh& b, FlatBvh& out);
+void flatten_cwbvh8(const BinaryBvh& b, FlatBvh& out);
+void make_tri_records(const float* tri_vertices, const std::vector<uint32_t>& order, std::vector<TriRecord>& out);
+
+}  // namespace mirogpu
+#endif

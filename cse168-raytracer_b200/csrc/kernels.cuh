@@ -1,0 +1,228 @@
+// kernels.cuh -- sm_100a kernels of the ray-intersection engine (included once by mirogpu.cu).
+//
+//   k_trace_simple      one thread per ray, grid covers the batch (bring-up / comparison variant)
+//   k_trace_persistent  persistent warps: grid = SMs x resident CTAs, every warp pulls 32-ray packets from
+//                       a global ticket counter until the batch is drained
+//   k_gen_primary       Camera::eyeRay for a block of rows (Camera.cpp:104-161)
+//   k_gen_bounce        Ray::diffuse at every hit (Ray.h:109-122, Utility.h:34-50)
+//   k_resolve_hits      P, N, material from (prim, beta, gamma) (Triangle.cpp:160-166, Scene.cpp:262)
+#ifndef MIROGPU_KERNELS_CUH
+#define MIROGPU_KERNELS_CUH
+
+#include "traverse.cuh"
+#include "rng.cuh"
+
+namespace mirogpu {
+
+struct DeviceScene {
+    const float4* nodes;   // BVH2: 4 float4 per node; CWBVH8: 5 uint4 per node
+    const float4* tris;    // 3 float4 per triangle, leaf order
+    const float4* shade;   // 6 float4 per primitive, prim-id order: (A,mat) e1 e2 nA nB nC
+    uint32_t num_tris;
+};
+
+struct CameraBasis {       // what Camera::eyeRay caches in its statics (Camera.cpp:106-125)
+    float eye[3], w[3], u[3], v[3];
+    float top, left, bottom, right;
+};
+
+#define MIRO_PI 3.1415926535897932384626433832795028841972f /* Miro.h:10 */
+
+template <int LAYOUT, bool ANY, bool COUNT>
+__device__ __forceinline__ void trace_one(const DeviceScene& s, const mirogpu_ray& r, BestHit& best, TraceCounters* c)
+{
+    if (LAYOUT == MIROGPU_LAYOUT_BVH2) trace_bvh2<ANY, COUNT>(s.nodes, s.tris, r, best, c);
+    else trace_cwbvh8<ANY, COUNT>(reinterpret_cast<const uint4*>(s.nodes), s.tris, r, best, c);
+}
+
+__device__ __forceinline__ mirogpu_ray load_ray(const mirogpu_ray* rays, size_t i)
+{
+    const float4* p = reinterpret_cast<const float4*>(rays + i);
+    const float4 a = __ldg(p), b = __ldg(p + 1);
+    mirogpu_ray r;
+    r.ox = a.x; r.oy = a.y; r.oz = a.z; r.tmin = a.w; r.dx = b.x; r.dy = b.y; r.dz = b.z; r.tmax = b.w;
+    return r;
+}
+__device__ __forceinline__ void store_hit(mirogpu_hit* hits, size_t i, const BestHit& b)
+{
+    float4 h; h.x = b.t; h.y = __uint_as_float(b.prim); h.z = b.beta; h.w = b.gamma;
+    *reinterpret_cast<float4*>(hits + i) = h;
+}
+
+template <int LAYOUT, bool ANY, bool COUNT>
+__global__ void __launch_bounds__(128) k_trace_simple(DeviceScene s, const mirogpu_ray* __restrict__ rays, size_t n,
+                                                      mirogpu_hit* __restrict__ hits, unsigned long long* __restrict__ counters)
+{
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    TraceCounters c = {0, 0, 0};
+    uint32_t hit = 0;
+    if (i < n) {
+        const mirogpu_ray r = load_ray(rays, i);
+        BestHit best;
+        trace_one<LAYOUT, ANY, COUNT>(s, r, best, &c);
+        store_hit(hits, i, best);
+        hit = best.prim != MIROGPU_MISS;
+    }
+    if (COUNT) {
+        // warp-aggregate, then one atomic per warp per counter
+        for (int o = 16; o > 0; o >>= 1) {
+            c.nodes += __shfl_down_sync(0xffffffffu, c.nodes, o);
+            c.boxes += __shfl_down_sync(0xffffffffu, c.boxes, o);
+            c.tris += __shfl_down_sync(0xffffffffu, c.tris, o);
+            hit += __shfl_down_sync(0xffffffffu, hit, o);
+        }
+        if ((threadIdx.x & 31) == 0) {
+            atomicAdd(counters + 0, (unsigned long long)c.nodes);
+            atomicAdd(counters + 1, (unsigned long long)c.boxes);
+            atomicAdd(counters + 2, (unsigned long long)c.tris);
+            atomicAdd(counters + 3, (unsigned long long)hit);
+        }
+    }
+}
+
+// Persistent warps.  The grid is sized to the machine (SM count x resident CTAs), not to the batch; each
+// warp takes a ticket for the next 32 consecutive rays.  Consecutive tickets keep primary rays of one
+// warp coherent; for incoherent batches the packet order is irrelevant and the ticket loop removes the
+// tail effect of uneven ray costs across CTAs.
+template <int LAYOUT, bool ANY>
+__global__ void __launch_bounds__(128) k_trace_persistent(DeviceScene s, const mirogpu_ray* __restrict__ rays, size_t n,
+                                                          mirogpu_hit* __restrict__ hits, unsigned long long* __restrict__ ticket)
+{
+    const unsigned lane = threadIdx.x & 31u;
+    for (;;) {
+        unsigned long long base = 0;
+        if (lane == 0) base = atomicAdd(ticket, 32ull);
+        base = __shfl_sync(0xffffffffu, base, 0);
+        if (base >= n) return;
+        const size_t i = (size_t)base + lane;
+        if (i < n) {
+            const mirogpu_ray r = load_ray(rays, i);
+            BestHit best;
+            trace_one<LAYOUT, ANY, false>(s, r, best, nullptr);
+            store_hit(hits, i, best);
+        }
+        __syncwarp();
+    }
+}
+
+// ---- Camera::eyeRay, Camera.cpp:127-160 (no DOF).  Same operand order, no FMA: bit-exact with the oracle. ----
+__global__ void __launch_bounds__(256) k_gen_primary(CameraBasis cb, int width, int height, int row_begin, int row_end,
+                                                      int jitter, uint32_t seed, uint32_t sample, mirogpu_ray* __restrict__ rays)
+{
+    const size_t npix = (size_t)(row_end - row_begin) * width;
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= npix) return;
+    const int x = (int)(i % width), y = row_begin + (int)(i / width);
+    float dx = 0.5f, dy = 0.5f;
+    if (jitter) uniform2(seed, (uint32_t)((size_t)y * width + x), sample, RNG_DIM_PIXEL, dx, dy);
+    const float U = xadd(cb.left, xmul(xsub(cb.right, cb.left), xdiv(xadd((float)x, dx), (float)width)));
+    const float V = xadd(cb.bottom, xmul(xsub(cb.top, cb.bottom), xdiv(xadd((float)y, dy), (float)height)));
+    float d[3];
+#pragma unroll
+    for (int k = 0; k < 3; ++k) d[k] = xsub(xadd(xmul(cb.u[k], U), xmul(cb.v[k], V)), cb.w[k]);
+    const float inv = xdiv(1.0f, xsqrt(xdot(d[0], d[1], d[2], d[0], d[1], d[2])));
+    float4 a, b;
+    a.x = cb.eye[0]; a.y = cb.eye[1]; a.z = cb.eye[2]; a.w = 0.0f;
+    b.x = xmul(d[0], inv); b.y = xmul(d[1], inv); b.z = xmul(d[2], inv); b.w = MIROGPU_TMAX;
+    float4* o = reinterpret_cast<float4*>(rays + i);
+    o[0] = a; o[1] = b;
+}
+
+struct SurfacePoint {
+    float P[3], N[3];
+    uint32_t material;
+};
+
+// Triangle.cpp:160-162 then Scene::trace's normalisation (Scene.cpp:262; all materials are UV-lookup Phong
+// with zero bump height, so the perturbation term is exactly zero).
+__device__ __forceinline__ SurfacePoint resolve_hit(const DeviceScene& s, const mirogpu_hit& h)
+{
+    const float4* q = s.shade + 6 * (size_t)h.prim_id;
+    const float4 A = __ldg(q), e1 = __ldg(q + 1), e2 = __ldg(q + 2), nA = __ldg(q + 3), nB = __ldg(q + 4), nC = __ldg(q + 5);
+    SurfacePoint sp;
+    sp.P[0] = xadd(xadd(A.x, xmul(e1.x, h.beta)), xmul(e2.x, h.gamma));
+    sp.P[1] = xadd(xadd(A.y, xmul(e1.y, h.beta)), xmul(e2.y, h.gamma));
+    sp.P[2] = xadd(xadd(A.z, xmul(e1.z, h.beta)), xmul(e2.z, h.gamma));
+    const float alpha = xsub(xsub(1.0f, h.beta), h.gamma);
+    float n[3];
+    n[0] = xadd(xadd(xmul(nA.x, alpha), xmul(nB.x, h.beta)), xmul(nC.x, h.gamma));
+    n[1] = xadd(xadd(xmul(nA.y, alpha), xmul(nB.y, h.beta)), xmul(nC.y, h.gamma));
+    n[2] = xadd(xadd(xmul(nA.z, alpha), xmul(nB.z, h.beta)), xmul(nC.z, h.gamma));
+    const float inv = xdiv(1.0f, xsqrt(xdot(n[0], n[1], n[2], n[0], n[1], n[2])));
+    sp.N[0] = xmul(n[0], inv); sp.N[1] = xmul(n[1], inv); sp.N[2] = xmul(n[2], inv);
+    sp.material = __float_as_uint(A.w);
+    return sp;
+}
+
+__global__ void __launch_bounds__(256) k_resolve_hits(DeviceScene s, const mirogpu_hit* __restrict__ hits, size_t n,
+                                                       float* __restrict__ P, float* __restrict__ N, uint32_t* __restrict__ mat)
+{
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const float4 hv = __ldg(reinterpret_cast<const float4*>(hits + i));
+    mirogpu_hit h; h.t = hv.x; h.prim_id = __float_as_uint(hv.y); h.beta = hv.z; h.gamma = hv.w;
+    SurfacePoint sp;
+    if (h.prim_id == MIROGPU_MISS) {
+        sp.P[0] = sp.P[1] = sp.P[2] = 0.f; sp.N[0] = sp.N[1] = sp.N[2] = 0.f; sp.material = MIROGPU_MISS;
+    } else sp = resolve_hit(s, h);
+    if (P) { P[3 * i] = sp.P[0]; P[3 * i + 1] = sp.P[1]; P[3 * i + 2] = sp.P[2]; }
+    if (N) { N[3 * i] = sp.N[0]; N[3 * i + 1] = sp.N[1]; N[3 * i + 2] = sp.N[2]; }
+    if (mat) mat[i] = sp.material;
+}
+
+// alignHemisphereToVector, Utility.h:34-50.  Everything except sinf/cosf is evaluated in the reference's
+// operand order without FMA; CUDA's sinf/cosf/asinf differ from glibc's in the last ulp, which is why
+// generated bounce rays are compared with a tolerance and hit parity is checked on the dumped rays.
+__device__ __forceinline__ void align_hemisphere(const float v[3], float theta, float phi, float out[3])
+{
+    const float sp = sinf(phi), cp = cosf(phi), st = sinf(theta), ct = cosf(theta);
+    const float u1 = xmul(sp, ct), u2 = xmul(sp, st), u3 = cp;
+    // t1 = cross((0,0,1), v)
+    float t1[3] = {xsub(xmul(0.f, v[2]), xmul(1.f, v[1])), xsub(xmul(1.f, v[0]), xmul(0.f, v[2])), xsub(xmul(0.f, v[1]), xmul(0.f, v[0]))};
+    if ((double)xdot(t1[0], t1[1], t1[2], t1[0], t1[1], t1[2]) < 1e-6) {
+        // t1 = cross((0,1,0), v)
+        t1[0] = xsub(xmul(1.f, v[2]), xmul(0.f, v[1]));
+        t1[1] = xsub(xmul(0.f, v[0]), xmul(0.f, v[2]));
+        t1[2] = xsub(xmul(0.f, v[1]), xmul(1.f, v[0]));
+    }
+    // cross(t1, v)
+    const float c[3] = {xsub(xmul(t1[1], v[2]), xmul(t1[2], v[1])), xsub(xmul(t1[2], v[0]), xmul(t1[0], v[2])),
+                        xsub(xmul(t1[0], v[1]), xmul(t1[1], v[0]))};
+    float a[3];
+#pragma unroll
+    for (int k = 0; k < 3; ++k) a[k] = xadd(xadd(xmul(t1[k], u1), xmul(c[k], u2)), xmul(v[k], u3));
+    const float inv = xdiv(1.0f, xsqrt(xdot(a[0], a[1], a[2], a[0], a[1], a[2])));
+#pragma unroll
+    for (int k = 0; k < 3; ++k) out[k] = xmul(a[k], inv);
+}
+
+// Ray::diffuse, Ray.h:109-122, with (u1,u2) from the counter RNG in place of rand().
+__global__ void __launch_bounds__(256) k_gen_bounce(DeviceScene s, const mirogpu_ray* __restrict__ rays,
+                                                     const mirogpu_hit* __restrict__ hits, size_t n, uint32_t seed, uint32_t sample,
+                                                     mirogpu_ray* __restrict__ out)
+{
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const float4 hv = __ldg(reinterpret_cast<const float4*>(hits + i));
+    mirogpu_hit h; h.t = hv.x; h.prim_id = __float_as_uint(hv.y); h.beta = hv.z; h.gamma = hv.w;
+    float4 a, b;
+    if (h.prim_id == MIROGPU_MISS) {
+        a = make_float4(0.f, 0.f, 0.f, 0.f); b = make_float4(0.f, 0.f, 1.f, -1.0f);  // tmax < tmin: never hits
+    } else {
+        const SurfacePoint sp = resolve_hit(s, h);
+        float u1, u2;
+        uniform2(seed, (uint32_t)i, sample, RNG_DIM_BOUNCE, u1, u2);
+        const float phi = asinf(sqrtf(u1));
+        const float theta = xmul(xmul(2.0f, MIRO_PI), u2);
+        float d[3];
+        align_hemisphere(sp.N, theta, phi, d);
+        a.x = xadd(sp.P[0], xmul(d[0], MIRO_EPS)); a.y = xadd(sp.P[1], xmul(d[1], MIRO_EPS)); a.z = xadd(sp.P[2], xmul(d[2], MIRO_EPS));
+        a.w = 0.0f;
+        b.x = d[0]; b.y = d[1]; b.z = d[2]; b.w = MIROGPU_TMAX;
+    }
+    float4* o = reinterpret_cast<float4*>(out + i);
+    o[0] = a; o[1] = b;
+}
+
+}  // namespace mirogpu
+#endif

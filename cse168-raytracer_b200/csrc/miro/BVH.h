@@ -1,0 +1,34 @@
+// BVH.h -- the reference's BVH interface (BVH.h:29-62) backed by the device engine.
+//   build()      gathers the Triangle objects of the list, hands per-triangle arrays to
+//                mirogpu_scene_create (host SAH build -> flat GPU layout -> HBM) and keeps the handle.
+//   intersect()  single-ray convenience over the batched device query; same result contract as the
+//                reference (minHit.t = tMax on a miss, t/P/N/material/object on a hit).
+//   intersectBatch()  the throughput path: n rays per call, host buffers in and out.
+#ifndef MIROHOST_BVH_H
+#define MIROHOST_BVH_H
+#include <vector>
+#include "Miro.h"
+#include "Object.h"
+#include "../../../include/mirogpu.h"
+
+class BVH {
+public:
+    BVH() : m_handle(0), m_objects(0), m_layout(MIROGPU_LAYOUT_CWBVH8) {}
+    ~BVH();
+    void build(Objects* objs, int depth = 0);
+    bool intersect(HitInfo& result, const Ray& ray, float tMin = 0.0f, float tMax = MIRO_TMAX) const;
+    bool intersectChildren(HitInfo& result, const Ray& ray, float tMin, float tMax) const { return intersect(result, ray, tMin, tMax); }
+    // results[i] is filled like intersect() would; returns the number of hits.
+    size_t intersectBatch(const Ray* rays, size_t n, HitInfo* results, bool* hitFlags, float tMin = 0.0f, float tMax = MIRO_TMAX) const;
+    void setLayout(int layout) { m_layout = layout; }
+    mirogpu_handle handle() const { return m_handle; }
+    const std::vector<Object*>& fallbackObjects() const { return m_other; }
+protected:
+    bool finish(HitInfo& result, const mirogpu_hit& h, const Ray& ray, float tMin, float tMax) const;
+    mirogpu_handle m_handle;
+    Objects* m_objects;               // borrowed, as in the reference (BVH.cpp:84)
+    std::vector<Triangle*> m_tris;    // device prim id -> Triangle
+    std::vector<Object*> m_other;     // bounded non-triangle objects: tested on the host after the device query
+    int m_layout;
+};
+#endif

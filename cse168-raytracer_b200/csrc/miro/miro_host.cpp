@@ -1,0 +1,572 @@
+// miro_host.cpp -- host API layer: the reference's Object / BVH / Scene / Camera / Image / Photon_map
+// interfaces implemented over the C ABI in include/mirogpu.h.  Host code keeps the reference's binary32
+// operand order wherever a value feeds the device (geometry ingest, camera basis, hit reconstruction), so
+// this file is compiled with -ffp-contract=off and no -march flag.
+#include <chrono>
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <map>
+#include <vector>
+
+#include "Miro.h"
+#include "Vector3.h"
+#include "Matrix4x4.h"
+#include "Ray.h"
+#include "Material.h"
+#include "Object.h"
+#include "TriangleMesh.h"
+#include "Triangle.h"
+#include "PointLight.h"
+#include "BVH.h"
+#include "Camera.h"
+#include "Image.h"
+#include "PhotonMap.h"
+#include "Scene.h"
+
+Camera* g_camera = 0;
+Scene* g_scene = 0;
+Image* g_image = 0;
+
+namespace {
+[[noreturn]] void fatal(const char* what)
+{
+    // the reference's fatal() prints and exits (Console.cpp:119-129); the device layer has no CPU fallback
+    fprintf(stderr, "fatal: %s: %s\n", what, mirogpu_last_error());
+    exit(-1);
+}
+double wall()
+{
+    return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count();
+}
+}  // namespace
+
+// ================================= TriangleMesh ===========================================================
+TriangleMesh::TriangleMesh() : m_normals(0), m_vertices(0), m_normalIndices(0), m_vertexIndices(0), m_numVertices(0), m_numTris(0) {}
+
+TriangleMesh::~TriangleMesh()
+{
+    delete[] m_normals; delete[] m_vertices; delete[] m_normalIndices; delete[] m_vertexIndices;
+}
+
+void TriangleMesh::createSingleTriangle()
+{
+    m_normals = new Vector3[3];
+    m_vertices = new Vector3[3];
+    m_normalIndices = new TupleI3[1];
+    m_vertexIndices = new TupleI3[1];
+    for (unsigned k = 0; k < 3; ++k) m_vertexIndices[0].v[k] = m_normalIndices[0].v[k] = k;
+    m_numVertices = 3;
+    m_numTris = 1;
+}
+
+bool TriangleMesh::load(const char* file, const Matrix4x4& ctm)
+{
+    FILE* fp = fopen(file, "rb");
+    if (!fp) { fprintf(stderr, "error: Cannot open \"%s\" for reading\n", file); return false; }
+    loadObj(fp, ctm);
+    fclose(fp);
+    return true;
+}
+
+namespace {
+// "v", "v/t", "v//n", "v/t/n" -> (v, t, n), missing parts 0
+void splitFaceToken(char* tok, int& v, int& t, int& n)
+{
+    char* second = 0; char* third = 0;
+    for (char* p = tok; *p; ++p)
+        if (*p == '/') { *p = 0; if (!second) second = p + 1; else third = p + 1; }
+    v = atoi(tok); t = second ? atoi(second) : 0; n = third ? atoi(third) : 0;
+}
+}  // namespace
+
+void TriangleMesh::loadObj(FILE* fp, const Matrix4x4& ctm)
+{
+    char line[81];
+    int nv = 0, nf = 0;
+    while (fgets(line, 80, fp)) {               // 80-byte reads: longer lines split, exactly like the reference
+        if (line[0] == 'v') { if (line[1] != 'n' && line[1] != 't') nv++; }
+        else if (line[0] == 'f') nf++;
+    }
+    fseek(fp, 0, SEEK_SET);
+    const int ncap = std::max(nv, nf * 3);
+    m_normals = new Vector3[ncap];
+    m_vertices = new Vector3[nv];
+    m_numVertices = nv;
+    m_normalIndices = new TupleI3[nf];
+    m_vertexIndices = new TupleI3[nf];
+    std::vector<std::vector<int> > around(nv);   // normal slots touching each vertex
+    std::vector<char> synthesised(ncap, 0);
+    Matrix4x4 nctm = ctm;
+    nctm.invert();
+    nctm.transpose();
+    int nverts = 0, nnormals = 0;
+    m_numTris = 0;
+    while (fgets(line, 80, fp)) {
+        if (line[0] == 'v' && line[1] == 'n') {
+            float x, y, z; sscanf(&line[2], "%f %f %f\n", &x, &y, &z);
+            m_normals[nnormals] = nctm * Vector3(x, y, z);
+            m_normals[nnormals].normalize();
+            nnormals++;
+        } else if (line[0] == 'v' && line[1] == 't') {
+            // texture coordinates are not used on this path
+        } else if (line[0] == 'v') {
+            float x, y, z; sscanf(&line[1], "%f %f %f\n", &x, &y, &z);
+            m_vertices[nverts++] = ctm * Vector3(x, y, z);
+        } else if (line[0] == 'f') {
+            char tok[3][32];
+            sscanf(&line[1], "%s %s %s\n", tok[0], tok[1], tok[2]);
+            TupleI3& vi = m_vertexIndices[m_numTris];
+            TupleI3& ni = m_normalIndices[m_numTris];
+            int v = 0, t = 0, n = 0;
+            for (int k = 0; k < 3; ++k) {
+                splitFaceToken(tok[k], v, t, n);
+                vi.v[k] = v - 1;
+                if (n) { ni.v[k] = n - 1; around[v - 1].push_back(n - 1); }
+            }
+            if (!n) {   // the LAST token decides, as in the reference
+                const Vector3 e1 = m_vertices[vi.v[1]] - m_vertices[vi.v[0]];
+                const Vector3 e2 = m_vertices[vi.v[2]] - m_vertices[vi.v[0]];
+                for (int k = 0; k < 3; ++k) {
+                    m_normals[nnormals] = cross(e1, e2);
+                    m_normals[nnormals].normalize();
+                    synthesised[nnormals] = 1;
+                    ni.v[k] = nnormals;
+                    around[vi.v[k]].push_back(nnormals);
+                    nnormals++;
+                }
+            }
+            m_numTris++;
+        }
+    }
+    for (int i = 0; i < nverts; ++i) {
+        const std::vector<int>& a = around[i];
+        if (a.empty()) continue;
+        Vector3 avg;                             // default-constructed: (0,1,2), as the reference accumulates from
+        for (size_t j = 0; j < a.size(); ++j) avg += m_normals[a[j]];
+        avg /= (float)a.size();
+        avg.normalize();
+        for (size_t j = 0; j < a.size(); ++j) if (synthesised[a[j]]) m_normals[a[j]] = avg;
+    }
+}
+
+// ================================= Triangle ================================================================
+Vector3 Triangle::center() const
+{
+    const TriangleMesh::TupleI3 ti = m_mesh->vIndices()[m_index];
+    const Vector3 A = m_mesh->vertices()[ti.v[0]], B = m_mesh->vertices()[ti.v[1]], C = m_mesh->vertices()[ti.v[2]];
+    return A + (B - A) / 3 + (C - A) / 3;
+}
+
+void Triangle::preCalc()
+{
+    const TriangleMesh::TupleI3 ti = m_mesh->vIndices()[m_index];
+    m_cachedMin = m_cachedMax = m_mesh->vertices()[ti.v[0]];
+    for (int k = 1; k < 3; ++k) {
+        const Vector3& p = m_mesh->vertices()[ti.v[k]];
+        for (int a = 0; a < 3; ++a) {
+            if (p[a] < m_cachedMin[a]) m_cachedMin[a] = p[a];
+            if (p[a] > m_cachedMax[a]) m_cachedMax[a] = p[a];
+        }
+    }
+}
+
+void Triangle::fillHit(HitInfo& result, float t, float beta, float gamma) const
+{
+    const TriangleMesh::TupleI3 ti = m_mesh->vIndices()[m_index];
+    const TriangleMesh::TupleI3 ni = m_mesh->nIndices()[m_index];
+    const Vector3& A = m_mesh->vertices()[ti.v[0]];
+    const Vector3 BmA = m_mesh->vertices()[ti.v[1]] - A, CmA = m_mesh->vertices()[ti.v[2]] - A;
+    result.P = A + beta * BmA + gamma * CmA;
+    result.t = t;
+    result.N = (1 - beta - gamma) * m_mesh->normals()[ni.v[0]] + beta * m_mesh->normals()[ni.v[1]] + gamma * m_mesh->normals()[ni.v[2]];
+    result.material = m_material;
+}
+
+// Single triangle, single ray on the host: plane / barycentric form with the epsilon slop of the reference.
+bool Triangle::intersect(HitInfo& result, const Ray& r, float tMin, float tMax)
+{
+    const TriangleMesh::TupleI3 ti = m_mesh->vIndices()[m_index];
+    const Vector3& A = m_mesh->vertices()[ti.v[0]];
+    const Vector3 BmA = m_mesh->vertices()[ti.v[1]] - A, CmA = m_mesh->vertices()[ti.v[2]] - A;
+    const Vector3 n = cross(BmA, CmA);
+    const Vector3 nd = -r.d, oa = r.o - A;
+    const float den = dot(nd, n);
+    const float t = dot(oa, n) / den;
+    const float beta = dot(nd, cross(oa, CmA)) / den;
+    const float gamma = dot(nd, cross(BmA, oa)) / den;
+    if (beta < -epsilon || gamma < -epsilon || beta + gamma > 1 + epsilon || t < tMin || t > tMax) return false;
+    fillHit(result, t, beta, gamma);
+    return true;
+}
+
+// ================================= BVH =======================================================================
+BVH::~BVH() { if (m_handle) mirogpu_scene_destroy(m_handle); }
+
+void BVH::build(Objects* objs, int)
+{
+    if (m_handle) { mirogpu_scene_destroy(m_handle); m_handle = 0; }
+    m_objects = objs;
+    m_tris.clear(); m_other.clear();
+    std::map<const Material*, uint32_t> matIndex;
+    std::vector<mirogpu_material> mats;
+    std::vector<float> verts, norms;
+    std::vector<uint32_t> matIds;
+    for (size_t i = 0; i < objs->size(); ++i) {
+        Object* o = (*objs)[i];
+        if (!o->isBounded()) continue;
+        Triangle* t = dynamic_cast<Triangle*>(o);
+        if (!t) { m_other.push_back(o); continue; }
+        TriangleMesh* m = t->getMesh();
+        const TriangleMesh::TupleI3 vi = m->vIndices()[t->getIndex()], ni = m->nIndices()[t->getIndex()];
+        for (int k = 0; k < 3; ++k) {
+            const Vector3& p = m->vertices()[vi.v[k]];
+            verts.push_back(p.x); verts.push_back(p.y); verts.push_back(p.z);
+        }
+        for (int k = 0; k < 3; ++k) {
+            const Vector3& q = m->normals()[ni.v[k]];
+            norms.push_back(q.x); norms.push_back(q.y); norms.push_back(q.z);
+        }
+        const Material* mat = t->getMaterial();
+        std::map<const Material*, uint32_t>::iterator it = matIndex.find(mat);
+        if (it == matIndex.end()) {
+            mirogpu_material mm; memset(&mm, 0, sizeof mm);
+            const Vector3 kd = mat ? mat->getDiffuse() : Vector3(1.f), ks = mat ? mat->getReflection() : Vector3(0.f),
+                          kt = mat ? mat->getRefraction() : Vector3(0.f);
+            for (int k = 0; k < 3; ++k) { mm.kd[k] = kd[k]; mm.ks[k] = ks[k]; mm.kt[k] = kt[k]; }
+            mm.shininess = mat ? mat->getShininess() : 1.f;
+            mm.refract_index = mat ? mat->getRefractionIndex() : 1.f;
+            it = matIndex.insert(std::make_pair(mat, (uint32_t)mats.size())).first;
+            mats.push_back(mm);
+        }
+        matIds.push_back(it->second);
+        m_tris.push_back(t);
+    }
+    mirogpu_build_options opt; opt.layout = m_layout; opt.max_leaf = 0; opt.sah_bins = 32; opt.device = -1;
+    const int rc = mirogpu_scene_create(verts.data(), norms.data(), matIds.data(), (uint32_t)m_tris.size(),
+                                        mats.empty() ? 0 : mats.data(), (uint32_t)mats.size(), &opt, &m_handle);
+    if (rc != MIROGPU_OK) fatal("BVH::build");
+}
+
+bool BVH::finish(HitInfo& result, const mirogpu_hit& h, const Ray& ray, float tMin, float tMax) const
+{
+    bool hit = false;
+    result.t = tMax;                                  // miss contract of the reference (BVH.cpp:444)
+    if (h.prim_id != MIROGPU_MISS) {
+        const Triangle* t = m_tris[h.prim_id];
+        t->fillHit(result, h.t, h.beta, h.gamma);
+        result.object = t;
+        hit = true;
+    }
+    for (size_t i = 0; i < m_other.size(); ++i) {     // spheres etc.: outside the device path
+        HitInfo tmp;
+        if (m_other[i]->intersect(tmp, ray, tMin, result.t) && tmp.t < result.t) { result = tmp; result.object = m_other[i]; hit = true; }
+    }
+    return hit;
+}
+
+bool BVH::intersect(HitInfo& result, const Ray& ray, float tMin, float tMax) const
+{
+    if (!m_handle) fatal("BVH::intersect before build");
+    mirogpu_ray r = {ray.o.x, ray.o.y, ray.o.z, tMin, ray.d.x, ray.d.y, ray.d.z, tMax};
+    mirogpu_hit h;
+    if (mirogpu_intersect_batch(m_handle, &r, 1, &h, MIROGPU_CLOSEST_HIT) != MIROGPU_OK) fatal("BVH::intersect");
+    return finish(result, h, ray, tMin, tMax);
+}
+
+size_t BVH::intersectBatch(const Ray* rays, size_t n, HitInfo* results, bool* hitFlags, float tMin, float tMax) const
+{
+    if (!m_handle) fatal("BVH::intersectBatch before build");
+    std::vector<mirogpu_ray> rr(n);
+    std::vector<mirogpu_hit> hh(n);
+    for (size_t i = 0; i < n; ++i) {
+        const Ray& q = rays[i];
+        mirogpu_ray r = {q.o.x, q.o.y, q.o.z, tMin, q.d.x, q.d.y, q.d.z, tMax};
+        rr[i] = r;
+    }
+    if (mirogpu_intersect_batch(m_handle, rr.data(), n, hh.data(), MIROGPU_CLOSEST_HIT) != MIROGPU_OK) fatal("BVH::intersectBatch");
+    size_t nh = 0;
+    for (size_t i = 0; i < n; ++i) {
+        const bool h = finish(results[i], hh[i], rays[i], tMin, tMax);
+        if (hitFlags) hitFlags[i] = h;
+        nh += h;
+    }
+    return nh;
+}
+
+// ================================= Camera / Image ============================================================
+mirogpu_camera Camera::abi() const
+{
+    mirogpu_camera c;
+    for (int k = 0; k < 3; ++k) { c.eye[k] = m_eye[k]; c.up[k] = m_up[k]; c.view_dir[k] = m_viewDir[k]; }
+    c.fov_degrees = m_fov;
+    return c;
+}
+
+Ray Camera::eyeRay(int x, int y, int imageWidth, int imageHeight, bool randomize)
+{
+    const float HalfDegToRad = DegToRad / 2.0f;
+    Vector3 w = -m_viewDir; w.normalize();
+    Vector3 u = cross(m_up, w); u.normalize();
+    const Vector3 v = cross(w, u);
+    const float aspect = (float)imageWidth / (float)imageHeight;
+    const float top = tanf(m_fov * HalfDegToRad), right = aspect * top, bottom = -top, left = -right;
+    float dx = 0.5f, dy = 0.5f;
+    if (randomize) { dx = (float)rand() / (float)RAND_MAX; dy = (float)rand() / (float)RAND_MAX; }
+    const float U = left + (right - left) * (((float)x + dx) / (float)imageWidth);
+    const float V = bottom + (top - bottom) * (((float)y + dy) / (float)imageHeight);
+    Vector3 d = U * u + V * v - w;
+    d.normalize();
+    return Ray(m_eye, d);
+}
+
+void Camera::click(Scene* pScene, Image* pImage)
+{
+    pImage->clear(bgColor());
+    pScene->raytraceImage(this, pImage);
+}
+
+void Image::resize(int width, int height)
+{
+    delete[] m_pixels;
+    m_pixels = new Pixel[(size_t)width * height];
+    m_width = width; m_height = height;
+}
+namespace {
+unsigned char mapByte(float r) { const float m = 255 * r; return m > 255 ? 255 : (unsigned char)m; }
+}
+void Image::setPixel(int x, int y, const Vector3& p)
+{
+    if (x >= 0 && x < m_width && y >= 0 && y < m_height) m_pixels[(size_t)y * m_width + x] = Pixel(mapByte(p.x), mapByte(p.y), mapByte(p.z));
+}
+void Image::setPixel(int x, int y, const Pixel& p)
+{
+    if (x >= 0 && x < m_width && y >= 0 && y < m_height) m_pixels[(size_t)y * m_width + x] = p;
+}
+void Image::clear(const Vector3& c)
+{
+    for (int y = 0; y < m_height; ++y) for (int x = 0; x < m_width; ++x) setPixel(x, y, c);
+}
+void Image::writePPM(const char* pcFile)
+{
+    FILE* fp = fopen(pcFile, "wb");
+    if (!fp) return;
+    fprintf(fp, "P6\n%d %d\n255\n", m_width, m_height);
+    for (int y = m_height - 1; y >= 0; --y) fwrite(m_pixels + (size_t)y * m_width, 3, m_width, fp);   // row 0 is the bottom scanline
+    fclose(fp);
+}
+
+// ================================= Scene =====================================================================
+Scene::Scene()
+    : renderSpp(1), renderJitter(0), renderMode(MIROGPU_RENDER_WHITTED), renderShadows(1), renderSeed(168), lastRenderSeconds(0),
+      m_bgColor(0.f), m_usePhotonMaps(false)
+{
+    // the reference reserves 20.1 M photons per map up front (Scene.h:18); maps here grow on store()
+    m_photonMap = new Photon_map(0);
+    m_causticMap = new Photon_map(0);
+}
+
+Scene::~Scene() { delete m_photonMap; delete m_causticMap; }
+
+void Scene::preCalc()
+{
+    for (Objects::iterator it = m_objects.begin(); it != m_objects.end(); ++it) (*it)->preCalc();
+    for (Lights::iterator it = m_lights.begin(); it != m_lights.end(); ++it) (*it)->preCalc();
+    m_bvh.build(&m_objects);
+    std::vector<mirogpu_light> ls;
+    for (size_t i = 0; i < m_lights.size(); ++i) {
+        mirogpu_light l; memset(&l, 0, sizeof l);
+        const PointLight* p = m_lights[i];
+        for (int k = 0; k < 3; ++k) { l.position[k] = p->position()[k]; l.color[k] = p->color()[k]; }
+        l.wattage = p->wattage();
+        if (DirectionalAreaLight* d = dynamic_cast<DirectionalAreaLight*>(m_lights[i])) {
+            l.kind = 1; l.radius = d->getRadius();
+            const Vector3 n = d->getNormal();
+            for (int k = 0; k < 3; ++k) l.normal[k] = n[k];
+        }
+        ls.push_back(l);
+    }
+    if (mirogpu_scene_set_lights(m_bvh.handle(), ls.empty() ? 0 : ls.data(), (uint32_t)ls.size()) != MIROGPU_OK) fatal("Scene::preCalc lights");
+    if (m_photonMap->stored() > 0) m_photonMap->attach(m_bvh.handle(), 0);
+    if (m_causticMap->stored() > 0) m_causticMap->attach(m_bvh.handle(), 1);
+}
+
+// Scene.cpp:232-266 for UV-lookup materials with zero bump height: the perturbation vanishes, N is normalised.
+void Scene::postProcess(HitInfo& minHit) const { minHit.N.normalize(); }
+
+bool Scene::trace(HitInfo& minHit, const Ray& ray, float tMin, float tMax) const
+{
+    bool result = m_bvh.intersect(minHit, ray, tMin, tMax);
+    for (size_t i = 0; i < m_unboundedObjects.size(); ++i) {
+        HitInfo tmp;
+        if (m_unboundedObjects[i]->intersect(tmp, ray, tMin, tMax) && (!result || tmp.t < minHit.t)) {
+            result = true; minHit = tmp; minHit.object = m_unboundedObjects[i];
+        }
+    }
+    if (result) postProcess(minHit);
+    return result;
+}
+
+size_t Scene::traceBatch(const Ray* rays, size_t n, HitInfo* results, bool* hitFlags, float tMin, float tMax) const
+{
+    std::vector<char> flags(n);
+    m_bvh.intersectBatch(rays, n, results, reinterpret_cast<bool*>(flags.data()), tMin, tMax);
+    size_t nh = 0;
+    for (size_t r = 0; r < n; ++r) {
+        bool result = flags[r] != 0;
+        for (size_t i = 0; i < m_unboundedObjects.size(); ++i) {
+            HitInfo tmp;
+            if (m_unboundedObjects[i]->intersect(tmp, rays[r], tMin, tMax) && (!result || tmp.t < results[r].t)) {
+                result = true; results[r] = tmp; results[r].object = m_unboundedObjects[i];
+            }
+        }
+        if (result) postProcess(results[r]);
+        if (hitFlags) hitFlags[r] = result;
+        nh += result;
+    }
+    return nh;
+}
+
+void Scene::raytraceImage(Camera* cam, Image* img)
+{
+    const int w = img->width(), h = img->height();
+    mirogpu_render_params p; memset(&p, 0, sizeof p);
+    p.width = w; p.height = h; p.spp = renderSpp; p.jitter = renderJitter; p.max_depth = (int)TRACE_DEPTH; p.mode = renderMode;
+    p.seed = renderSeed; p.tonemap = 1; p.row_begin = 0; p.row_end = h; p.row_stride = 1; p.row_phase = 0;
+    for (int k = 0; k < 3; ++k) p.bg_color[k] = m_bgColor[k];
+    p.use_photon_maps = m_usePhotonMaps ? 1 : 0;
+    p.shadows = renderShadows;
+    std::vector<float> rgb((size_t)w * h * 3);
+    const mirogpu_camera c = cam->abi();
+    const double t0 = wall();
+    if (mirogpu_render(m_bvh.handle(), &c, &p, rgb.data()) != MIROGPU_OK) fatal("Scene::raytraceImage");
+    lastRenderSeconds = wall() - t0;
+    for (int y = 0; y < h; ++y)
+        for (int x = 0; x < w; ++x) {
+            const float* q = &rgb[3 * ((size_t)y * w + x)];
+            img->setPixel(x, y, Vector3(q[0], q[1], q[2]));
+        }
+    printf("Time spent raytracing image: %lf seconds.\n", lastRenderSeconds);
+}
+
+// ================================= Photon_map ================================================================
+Photon_map::Photon_map(int max_phot)
+    : photons(0), stored_photons(0), half_stored_photons(0), max_photons(max_phot), prev_scale(1), m_handle(0), m_which(0)
+{
+    photons = (Photon*)malloc(sizeof(Photon) * ((size_t)std::max(max_photons, 0) + 1));
+    bbox_min[0] = bbox_min[1] = bbox_min[2] = 1e8f;
+    bbox_max[0] = bbox_max[1] = bbox_max[2] = -1e8f;
+}
+
+Photon_map::~Photon_map() { free(photons); }
+
+void Photon_map::store(const float power[3], const float pos[3], const float dir[3])
+{
+    if (stored_photons >= max_photons) {        // grow instead of the reference's silent drop at capacity
+        max_photons = max_photons ? 2 * max_photons : 1024;
+        photons = (Photon*)realloc(photons, sizeof(Photon) * ((size_t)max_photons + 1));
+    }
+    Photon* const node = &photons[++stored_photons];
+    for (int i = 0; i < 3; ++i) {
+        node->pos[i] = pos[i];
+        bbox_min[i] = std::min(bbox_min[i], node->pos[i]);
+        bbox_max[i] = std::max(bbox_max[i], node->pos[i]);
+        node->power[i] = power[i];
+    }
+    // direction quantised to two bytes (PhotonMap.cpp:275-287)
+    const int theta = int(acos(dir[2]) * (256.0 / M_PI));
+    node->theta = theta > 255 ? 255 : (unsigned char)theta;
+    const int phi = int(atan2(dir[1], dir[0]) * (256.0 / (2.0 * M_PI)));
+    node->phi = phi > 255 ? 255 : (phi < 0 ? (unsigned char)(phi + 256) : (unsigned char)phi);
+}
+
+void Photon_map::scale_photon_power(const float scale)
+{
+    for (int i = prev_scale; i <= stored_photons; ++i)
+        for (int k = 0; k < 3; ++k) photons[i].power[k] *= scale;
+    prev_scale = stored_photons;
+}
+
+// Quickselect partition about `median` on one axis (PhotonMap.cpp:371-402); the pivot / scan order decides
+// which photon lands where among equal keys, so it follows Jensen's routine step for step.
+void Photon_map::median_split(Photon** p, const int start, const int end, const int median, const int axis)
+{
+    int left = start, right = end;
+    while (right > left) {
+        const float v = p[right]->pos[axis];
+        int i = left - 1, j = right;
+        for (;;) {
+            while (p[++i]->pos[axis] < v) {}
+            while (p[--j]->pos[axis] > v && j > left) {}
+            if (i >= j) break;
+            std::swap(p[i], p[j]);
+        }
+        std::swap(p[i], p[right]);
+        if (i >= median) right = i - 1;
+        if (i <= median) left = i + 1;
+    }
+}
+
+void Photon_map::balance_segment(Photon** pbal, Photon** porg, const int index, const int start, const int end)
+{
+    // left-balanced median (Jensen, "Realistic Image Synthesis using Photon Mapping", ch. 6)
+    const int count = end - start + 1;
+    int median = 1;
+    while (4 * median <= count) median += median;
+    if (3 * median <= count) median = 2 * median + start - 1; else median = end - median + 1;
+    int axis = 2;
+    const float ex = bbox_max[0] - bbox_min[0], ey = bbox_max[1] - bbox_min[1], ez = bbox_max[2] - bbox_min[2];
+    if (ex > ey && ex > ez) axis = 0; else if (ey > ez) axis = 1;
+    median_split(porg, start, end, median, axis);
+    pbal[index] = porg[median];
+    pbal[index]->plane = (short)axis;
+    if (median > start) {
+        if (start < median - 1) {
+            const float keep = bbox_max[axis];
+            bbox_max[axis] = pbal[index]->pos[axis];
+            balance_segment(pbal, porg, 2 * index, start, median - 1);
+            bbox_max[axis] = keep;
+        } else pbal[2 * index] = porg[start];
+    }
+    if (median < end) {
+        if (median + 1 < end) {
+            const float keep = bbox_min[axis];
+            bbox_min[axis] = pbal[index]->pos[axis];
+            balance_segment(pbal, porg, 2 * index + 1, median + 1, end);
+            bbox_min[axis] = keep;
+        } else pbal[2 * index + 1] = porg[end];
+    }
+}
+
+void Photon_map::balance(void)
+{
+    if (stored_photons > 1) {
+        std::vector<Photon*> pa1((size_t)2 * stored_photons + 4, (Photon*)0), pa2((size_t)stored_photons + 1);
+        for (int i = 0; i <= stored_photons; ++i) pa2[i] = &photons[i];
+        balance_segment(pa1.data(), pa2.data(), 1, 1, stored_photons);
+        // permute the records in place into heap order by following cycles
+        std::vector<Photon> ordered((size_t)stored_photons + 1);
+        ordered[0] = photons[0];
+        for (int i = 1; i <= stored_photons; ++i) ordered[i] = *pa1[i];
+        memcpy(photons, ordered.data(), sizeof(Photon) * ((size_t)stored_photons + 1));
+    }
+    half_stored_photons = stored_photons / 2 - 1;
+}
+
+void Photon_map::attach(mirogpu_handle h, int which)
+{
+    m_handle = h; m_which = which;
+    if (mirogpu_photon_upload(h, which, photons, stored_photons) != MIROGPU_OK) fatal("Photon_map::attach");
+}
+
+void Photon_map::irradiance_estimate_batch(float* irrad3, const float* pos3, const float* normal3, size_t n, float max_dist, int nphotons) const
+{
+    if (!m_handle) fatal("Photon_map::irradiance_estimate before attach");
+    if (mirogpu_photon_gather(m_handle, m_which, pos3, normal3, n, max_dist, nphotons, irrad3) != MIROGPU_OK) fatal("Photon_map::irradiance_estimate");
+}
+
+void Photon_map::irradiance_estimate(float irrad[3], const float pos[3], const float normal[3], const float max_dist, const int nphotons) const
+{
+    irradiance_estimate_batch(irrad, pos, normal, 1, max_dist, nphotons);
+}

@@ -1,0 +1,531 @@
+// mirogpu.cu -- the C ABI of include/mirogpu.h: scene construction (host SAH build -> flat layout -> HBM),
+// batched intersection, device-side ray generation, render and photon gather entry points.
+// No CPU fallback: every compute entry point needs a CUDA device and says so loudly when there is none.
+#include <algorithm>
+#include <chrono>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include <cuda_runtime.h>
+
+#include "../../include/mirogpu.h"
+#include "bvh_build.h"
+#include "kernels.cuh"
+#include "render.cuh"
+#include "photon.cuh"
+
+using namespace mirogpu;
+
+namespace {
+
+thread_local std::string g_last_error;
+
+int fail(int code, const std::string& msg)
+{
+    g_last_error = msg;
+    return code;
+}
+
+#define CUDA_TRY(expr)                                                                                          \
+    do {                                                                                                        \
+        cudaError_t _e = (expr);                                                                                \
+        if (_e != cudaSuccess) {                                                                                \
+            const int code = (_e == cudaErrorNoDevice || _e == cudaErrorInsufficientDriver) ? MIROGPU_ERR_NO_DEVICE \
+                             : (_e == cudaErrorMemoryAllocation ? MIROGPU_ERR_OOM : MIROGPU_ERR_CUDA);          \
+            return fail(code, std::string(#expr) + ": " + cudaGetErrorString(_e));                              \
+        }                                                                                                       \
+    } while (0)
+
+double now_s()
+{
+    return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count();
+}
+
+}  // namespace
+
+struct mirogpu_scene {
+    int device = 0;
+    int layout = MIROGPU_LAYOUT_CWBVH8;
+    int variant = 0;
+    int sm_count = 148;
+    DeviceScene ds{};
+    void* d_nodes = nullptr;
+    void* d_tris = nullptr;
+    void* d_shade = nullptr;
+    mirogpu_material* d_materials = nullptr;
+    uint32_t nmaterials = 0;
+    mirogpu_light* d_lights = nullptr;
+    uint32_t nlights = 0;
+    unsigned long long* d_ticket = nullptr;  // persistent-kernel ticket counters (ring of 64)
+    uint32_t ticket_slot = 0;
+    mirogpu_scene_info info{};
+    std::vector<uint8_t> h_nodes;     // host copies kept for mirogpu_debug_copy_*
+    std::vector<TriRecord> h_tris;
+    PhotonMapDevice pm[2];
+    RenderScratch scratch;
+    std::mutex mtx;                   // guards scratch, ticket_slot and the last-call stats
+    uint64_t last_rays = 0, last_launches = 0;
+};
+
+namespace {
+
+template <int LAYOUT, bool ANY>
+cudaError_t launch_trace(mirogpu_scene* h, const mirogpu_ray* d_rays, size_t n, mirogpu_hit* d_hits, cudaStream_t st)
+{
+    if (n == 0) return cudaSuccess;
+    if (h->variant == 1) {
+        const unsigned grid = (unsigned)((n + 127) / 128);
+        k_trace_simple<LAYOUT, ANY, false><<<grid, 128, 0, st>>>(h->ds, d_rays, n, d_hits, nullptr);
+        return cudaGetLastError();
+    }
+    unsigned long long* ticket;
+    {
+        std::lock_guard<std::mutex> lk(h->mtx);
+        ticket = h->d_ticket + (h->ticket_slot++ & 63u);
+    }
+    cudaError_t e = cudaMemsetAsync(ticket, 0, sizeof(unsigned long long), st);
+    if (e != cudaSuccess) return e;
+    int occ = 0;
+    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_trace_persistent<LAYOUT, ANY>, 128, 0);
+    if (e != cudaSuccess) return e;
+    if (occ < 1) occ = 1;
+    size_t grid = (size_t)h->sm_count * occ;
+    const size_t need = (n + 127) / 128;
+    if (grid > need) grid = need;
+    k_trace_persistent<LAYOUT, ANY><<<(unsigned)grid, 128, 0, st>>>(h->ds, d_rays, n, d_hits, ticket);
+    return cudaGetLastError();
+}
+
+cudaError_t dispatch_trace(mirogpu_scene* h, const mirogpu_ray* d_rays, size_t n, mirogpu_hit* d_hits, int mode, cudaStream_t st)
+{
+    const bool any = mode == MIROGPU_ANY_HIT;
+    if (h->layout == MIROGPU_LAYOUT_BVH2)
+        return any ? launch_trace<MIROGPU_LAYOUT_BVH2, true>(h, d_rays, n, d_hits, st)
+                   : launch_trace<MIROGPU_LAYOUT_BVH2, false>(h, d_rays, n, d_hits, st);
+    return any ? launch_trace<MIROGPU_LAYOUT_CWBVH8, true>(h, d_rays, n, d_hits, st)
+               : launch_trace<MIROGPU_LAYOUT_CWBVH8, false>(h, d_rays, n, d_hits, st);
+}
+
+// Camera::eyeRay's cached basis (Camera.cpp:113-124), computed on the host in the reference's operand order.
+void camera_basis(const mirogpu_camera& c, int W, int H, CameraBasis& b)
+{
+    auto norm3 = [](float* v) {
+        const float len = sqrtf(v[0] * v[0] + v[1] * v[1] + v[2] * v[2]);
+        const float inv = float(1) / len;
+        v[0] *= inv; v[1] *= inv; v[2] *= inv;
+    };
+    auto cross3 = [](const float* a, const float* bb, float* o) {
+        o[0] = a[1] * bb[2] - a[2] * bb[1]; o[1] = a[2] * bb[0] - a[0] * bb[2]; o[2] = a[0] * bb[1] - a[1] * bb[0];
+    };
+    for (int k = 0; k < 3; ++k) { b.eye[k] = c.eye[k]; b.w[k] = -c.view_dir[k]; }
+    norm3(b.w);
+    cross3(c.up, b.w, b.u); norm3(b.u);
+    cross3(b.w, b.u, b.v);
+    const float PI = MIRO_PI, DegToRad = PI / 180.0f, HalfDegToRad = DegToRad / 2.0f;  // Miro.h:10-11, Camera.cpp:15
+    const float aspect = (float)W / (float)H;
+    b.top = tanf(c.fov_degrees * HalfDegToRad);
+    b.right = aspect * b.top; b.bottom = -b.top; b.left = -b.right;
+}
+
+}  // namespace
+
+// RenderScratch / render + photon implementations need the pieces above.
+#include "render_impl.cuh"
+
+extern "C" {
+
+int mirogpu_version(void) { return MIROGPU_VERSION; }
+
+const char* mirogpu_last_error(void) { return g_last_error.c_str(); }
+
+int mirogpu_device_count(int* count)
+{
+    if (!count) return fail(MIROGPU_ERR_INVALID_ARG, "count is NULL");
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess) { *count = 0; (void)cudaGetLastError(); return fail(MIROGPU_ERR_NO_DEVICE, cudaGetErrorString(e)); }
+    *count = n;
+    return MIROGPU_OK;
+}
+
+int mirogpu_scene_create(const float* tri_vertices, const float* tri_normals, const uint32_t* material_ids, uint32_t ntris,
+                         const mirogpu_material* materials, uint32_t nmaterials, const mirogpu_build_options* opt,
+                         mirogpu_handle* out)
+{
+    if (!out) return fail(MIROGPU_ERR_INVALID_ARG, "out handle is NULL");
+    *out = nullptr;
+    if (ntris && !tri_vertices) return fail(MIROGPU_ERR_INVALID_ARG, "tri_vertices is NULL");
+    if (ntris >= (1u << 28)) return fail(MIROGPU_ERR_INVALID_ARG, "too many triangles (limit 2^28)");
+    mirogpu_build_options o;
+    o.layout = MIROGPU_LAYOUT_CWBVH8; o.max_leaf = 0; o.sah_bins = 32; o.device = -1;
+    if (opt) o = *opt;
+    if (o.layout != MIROGPU_LAYOUT_BVH2 && o.layout != MIROGPU_LAYOUT_CWBVH8) return fail(MIROGPU_ERR_INVALID_ARG, "unknown layout");
+    if (o.max_leaf <= 0) o.max_leaf = (o.layout == MIROGPU_LAYOUT_CWBVH8) ? 3 : 4;
+    if (o.layout == MIROGPU_LAYOUT_CWBVH8 && o.max_leaf > 3) o.max_leaf = 3;
+    if (o.layout == MIROGPU_LAYOUT_BVH2 && o.max_leaf > 8) o.max_leaf = 8;
+    if (o.sah_bins <= 0) o.sah_bins = 32;
+
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
+        (void)cudaGetLastError();
+        return fail(MIROGPU_ERR_NO_DEVICE, "no CUDA device: mirogpu has no CPU path");
+    }
+    int dev = o.device;
+    if (dev < 0) CUDA_TRY(cudaGetDevice(&dev));
+    if (dev >= ndev) return fail(MIROGPU_ERR_INVALID_ARG, "device ordinal out of range");
+    CUDA_TRY(cudaSetDevice(dev));
+
+    mirogpu_scene* h = new (std::nothrow) mirogpu_scene;
+    if (!h) return fail(MIROGPU_ERR_OOM, "host allocation failed");
+    h->device = dev; h->layout = o.layout;
+    cudaDeviceProp prop;
+    CUDA_TRY(cudaGetDeviceProperties(&prop, dev));
+    h->sm_count = prop.multiProcessorCount;
+
+    // ---- host build ------------------------------------------------------------------------------
+    double t0 = now_s();
+    BinaryBvh bin = build_binary_sah(tri_vertices, ntris, o.max_leaf, o.sah_bins);
+    double t1 = now_s();
+    FlatBvh flat;
+    if (o.layout == MIROGPU_LAYOUT_BVH2) flatten_bvh2(bin, flat); else flatten_cwbvh8(bin, flat);
+    make_tri_records(tri_vertices, flat.order, h->h_tris);
+    double t2 = now_s();
+
+    const void* node_src; size_t node_bytes;
+    if (o.layout == MIROGPU_LAYOUT_BVH2) { node_src = flat.nodes2.data(); node_bytes = flat.nodes2.size() * sizeof(Bvh2Node); }
+    else { node_src = flat.nodes8.data(); node_bytes = flat.nodes8.size() * sizeof(Cwbvh8Node); }
+    h->h_nodes.assign((const uint8_t*)node_src, (const uint8_t*)node_src + node_bytes);
+
+    // shading records in prim-id order: (A, material) e1 e2 nA nB nC
+    std::vector<float4> shade((size_t)ntris * 6);
+    for (size_t i = 0; i < ntris; ++i) {
+        const float* v = tri_vertices + 9 * i;
+        uint32_t m = material_ids ? material_ids[i] : 0u;
+        if (nmaterials && m >= nmaterials) { delete h; return fail(MIROGPU_ERR_INVALID_ARG, "material id out of range"); }
+        float4 A = make_float4(v[0], v[1], v[2], 0.f);
+        memcpy(&A.w, &m, 4);
+        shade[6 * i + 0] = A;
+        shade[6 * i + 1] = make_float4(v[3] - v[0], v[4] - v[1], v[5] - v[2], 0.f);
+        shade[6 * i + 2] = make_float4(v[6] - v[0], v[7] - v[1], v[8] - v[2], 0.f);
+        for (int k = 0; k < 3; ++k) {
+            if (tri_normals) shade[6 * i + 3 + k] = make_float4(tri_normals[9 * i + 3 * k], tri_normals[9 * i + 3 * k + 1], tri_normals[9 * i + 3 * k + 2], 0.f);
+            else shade[6 * i + 3 + k] = make_float4(0.f, 1.f, 0.f, 0.f);
+        }
+    }
+    std::vector<mirogpu_material> mats;
+    if (materials && nmaterials) mats.assign(materials, materials + nmaterials);
+    else {
+        mirogpu_material m; memset(&m, 0, sizeof m);
+        m.kd[0] = m.kd[1] = m.kd[2] = 1.f; m.shininess = 1.f; m.refract_index = 1.f;  // Lambert(Vector3(1)) = Phong defaults
+        mats.push_back(m);
+    }
+
+    // ---- upload ------------------------------------------------------------------------------------
+    const size_t tri_bytes = h->h_tris.size() * sizeof(TriRecord), shade_bytes = shade.size() * sizeof(float4);
+    auto bail = [&](cudaError_t e, const char* what) {
+        std::string msg = std::string(what) + ": " + cudaGetErrorString(e);
+        mirogpu_scene_destroy(h);
+        return fail(e == cudaErrorMemoryAllocation ? MIROGPU_ERR_OOM : MIROGPU_ERR_CUDA, msg);
+    };
+    cudaError_t e;
+    if ((e = cudaMalloc(&h->d_nodes, std::max<size_t>(node_bytes, 16))) != cudaSuccess) return bail(e, "cudaMalloc nodes");
+    if ((e = cudaMalloc(&h->d_tris, std::max<size_t>(tri_bytes, 16))) != cudaSuccess) return bail(e, "cudaMalloc triangles");
+    if ((e = cudaMalloc(&h->d_shade, std::max<size_t>(shade_bytes, 16))) != cudaSuccess) return bail(e, "cudaMalloc shading records");
+    if ((e = cudaMalloc(&h->d_materials, mats.size() * sizeof(mirogpu_material))) != cudaSuccess) return bail(e, "cudaMalloc materials");
+    if ((e = cudaMalloc(&h->d_ticket, 64 * sizeof(unsigned long long))) != cudaSuccess) return bail(e, "cudaMalloc tickets");
+    if (node_bytes && (e = cudaMemcpy(h->d_nodes, node_src, node_bytes, cudaMemcpyHostToDevice)) != cudaSuccess) return bail(e, "upload nodes");
+    if (tri_bytes && (e = cudaMemcpy(h->d_tris, h->h_tris.data(), tri_bytes, cudaMemcpyHostToDevice)) != cudaSuccess) return bail(e, "upload triangles");
+    if (shade_bytes && (e = cudaMemcpy(h->d_shade, shade.data(), shade_bytes, cudaMemcpyHostToDevice)) != cudaSuccess) return bail(e, "upload shading records");
+    if ((e = cudaMemcpy(h->d_materials, mats.data(), mats.size() * sizeof(mirogpu_material), cudaMemcpyHostToDevice)) != cudaSuccess) return bail(e, "upload materials");
+    if ((e = cudaMemset(h->d_ticket, 0, 64 * sizeof(unsigned long long))) != cudaSuccess) return bail(e, "memset tickets");
+    h->nmaterials = (uint32_t)mats.size();
+    double t3 = now_s();
+
+    h->ds.nodes = reinterpret_cast<const float4*>(h->d_nodes);
+    h->ds.tris = reinterpret_cast<const float4*>(h->d_tris);
+    h->ds.shade = reinterpret_cast<const float4*>(h->d_shade);
+    h->ds.num_tris = ntris;
+
+    mirogpu_scene_info& in = h->info;
+    in.num_triangles = ntris;
+    in.num_nodes = (uint32_t)(o.layout == MIROGPU_LAYOUT_BVH2 ? flat.nodes2.size() : flat.nodes8.size());
+    in.num_binary_nodes = (uint32_t)bin.nodes.size();
+    in.num_binary_leaves = bin.num_leaves;
+    in.max_depth = o.layout == MIROGPU_LAYOUT_BVH2 ? bin.max_depth : flat.max_depth;
+    in.layout = o.layout;
+    in.node_bytes = node_bytes; in.triangle_bytes = tri_bytes; in.shading_bytes = shade_bytes;
+    in.build_seconds = t1 - t0; in.flatten_seconds = t2 - t1; in.upload_seconds = t3 - t2;
+    for (int k = 0; k < 3; ++k) { in.bounds_min[k] = flat.root.lo[k]; in.bounds_max[k] = flat.root.hi[k]; }
+    *out = h;
+    return MIROGPU_OK;
+}
+
+int mirogpu_scene_destroy(mirogpu_handle h)
+{
+    if (!h) return MIROGPU_OK;
+    cudaSetDevice(h->device);
+    cudaFree(h->d_nodes); cudaFree(h->d_tris); cudaFree(h->d_shade); cudaFree(h->d_materials);
+    cudaFree(h->d_lights); cudaFree(h->d_ticket);
+    for (int i = 0; i < 2; ++i) h->pm[i].release();
+    h->scratch.release();
+    (void)cudaGetLastError();
+    delete h;
+    return MIROGPU_OK;
+}
+
+int mirogpu_scene_info_get(mirogpu_handle h, mirogpu_scene_info* info)
+{
+    if (!h || !info) return fail(MIROGPU_ERR_INVALID_ARG, "NULL argument");
+    *info = h->info;
+    return MIROGPU_OK;
+}
+
+int mirogpu_scene_set_lights(mirogpu_handle h, const mirogpu_light* lights, uint32_t nlights)
+{
+    if (!h || (nlights && !lights)) return fail(MIROGPU_ERR_INVALID_ARG, "NULL argument");
+    CUDA_TRY(cudaSetDevice(h->device));
+    std::lock_guard<std::mutex> lk(h->mtx);
+    cudaFree(h->d_lights); h->d_lights = nullptr; h->nlights = 0;
+    if (nlights) {
+        CUDA_TRY(cudaMalloc(&h->d_lights, nlights * sizeof(mirogpu_light)));
+        CUDA_TRY(cudaMemcpy(h->d_lights, lights, nlights * sizeof(mirogpu_light), cudaMemcpyHostToDevice));
+        h->nlights = nlights;
+    }
+    return MIROGPU_OK;
+}
+
+int mirogpu_debug_copy_nodes(mirogpu_handle h, void* out, uint64_t* bytes)
+{
+    if (!h || !bytes) return fail(MIROGPU_ERR_INVALID_ARG, "NULL argument");
+    const uint64_t need = h->h_nodes.size();
+    if (out && *bytes >= need) memcpy(out, h->h_nodes.data(), need);
+    *bytes = need;
+    return MIROGPU_OK;
+}
+
+int mirogpu_debug_copy_triangles(mirogpu_handle h, void* out, uint64_t* bytes)
+{
+    if (!h || !bytes) return fail(MIROGPU_ERR_INVALID_ARG, "NULL argument");
+    const uint64_t need = h->h_tris.size() * sizeof(TriRecord);
+    if (out && *bytes >= need) memcpy(out, h->h_tris.data(), need);
+    *bytes = need;
+    return MIROGPU_OK;
+}
+
+int mirogpu_set_kernel_variant(mirogpu_handle h, int variant)
+{
+    if (!h) return fail(MIROGPU_ERR_INVALID_ARG, "NULL handle");
+    if (variant < 0 || variant > 1) return fail(MIROGPU_ERR_INVALID_ARG, "variant must be 0 (persistent) or 1 (one thread per ray)");
+    h->variant = variant;
+    return MIROGPU_OK;
+}
+
+int mirogpu_intersect_batch_device(mirogpu_handle h, const mirogpu_ray* d_rays, size_t n, mirogpu_hit* d_hits, int mode,
+                                   void* cuda_stream)
+{
+    if (!h || (n && (!d_rays || !d_hits))) return fail(MIROGPU_ERR_INVALID_ARG, "NULL argument");
+    if (mode != MIROGPU_CLOSEST_HIT && mode != MIROGPU_ANY_HIT) return fail(MIROGPU_ERR_INVALID_ARG, "unknown mode");
+    CUDA_TRY(cudaSetDevice(h->device));
+    CUDA_TRY(dispatch_trace(h, d_rays, n, d_hits, mode, (cudaStream_t)cuda_stream));
+    {
+        std::lock_guard<std::mutex> lk(h->mtx);
+        h->last_rays = n; h->last_launches = n ? 1 : 0;
+    }
+    return MIROGPU_OK;
+}
+
+// Host-buffer query: chunks of up to 4 Mi rays are double-buffered over two streams so the H2D copy of
+// chunk k+1 and the D2H copy of chunk k-1 overlap the traversal of chunk k.
+int mirogpu_intersect_batch(mirogpu_handle h, const mirogpu_ray* rays, size_t n, mirogpu_hit* hits, int mode)
+{
+    if (!h || (n && (!rays || !hits))) return fail(MIROGPU_ERR_INVALID_ARG, "NULL argument");
+    if (mode != MIROGPU_CLOSEST_HIT && mode != MIROGPU_ANY_HIT) return fail(MIROGPU_ERR_INVALID_ARG, "unknown mode");
+    if (n == 0) return MIROGPU_OK;
+    CUDA_TRY(cudaSetDevice(h->device));
+    const size_t chunk = std::min<size_t>(n, (size_t)4 << 20);
+    cudaStream_t st[2];
+    mirogpu_ray* d_r[2] = {nullptr, nullptr};
+    mirogpu_hit* d_h[2] = {nullptr, nullptr};
+    const int nbuf = n > chunk ? 2 : 1;
+    int rc = MIROGPU_OK;
+    for (int b = 0; b < nbuf; ++b) {
+        CUDA_TRY(cudaStreamCreateWithFlags(&st[b], cudaStreamNonBlocking));
+        CUDA_TRY(cudaMalloc(&d_r[b], chunk * sizeof(mirogpu_ray)));
+        CUDA_TRY(cudaMalloc(&d_h[b], chunk * sizeof(mirogpu_hit)));
+    }
+    uint64_t launches = 0;
+    size_t k = 0;
+    for (size_t off = 0; off < n && rc == MIROGPU_OK; off += chunk, ++k) {
+        const int b = (int)(k % nbuf);
+        const size_t m = std::min(chunk, n - off);
+        cudaError_t e = cudaMemcpyAsync(d_r[b], rays + off, m * sizeof(mirogpu_ray), cudaMemcpyHostToDevice, st[b]);
+        if (e == cudaSuccess) e = dispatch_trace(h, d_r[b], m, d_h[b], mode, st[b]);
+        if (e == cudaSuccess) e = cudaMemcpyAsync(hits + off, d_h[b], m * sizeof(mirogpu_hit), cudaMemcpyDeviceToHost, st[b]);
+        if (e != cudaSuccess) rc = fail(MIROGPU_ERR_CUDA, std::string("intersect_batch: ") + cudaGetErrorString(e));
+        launches++;
+    }
+    for (int b = 0; b < nbuf; ++b) {
+        cudaError_t e = cudaStreamSynchronize(st[b]);
+        if (e != cudaSuccess && rc == MIROGPU_OK) rc = fail(MIROGPU_ERR_CUDA, std::string("intersect_batch sync: ") + cudaGetErrorString(e));
+        cudaFree(d_r[b]); cudaFree(d_h[b]); cudaStreamDestroy(st[b]);
+    }
+    {
+        std::lock_guard<std::mutex> lk(h->mtx);
+        h->last_rays = n; h->last_launches = launches;
+    }
+    return rc;
+}
+
+int mirogpu_intersect_batch_counted(mirogpu_handle h, const mirogpu_ray* rays, size_t n, mirogpu_hit* hits, int mode,
+                                    mirogpu_counters* c)
+{
+    if (!h || !c || (n && (!rays || !hits))) return fail(MIROGPU_ERR_INVALID_ARG, "NULL argument");
+    if (mode != MIROGPU_CLOSEST_HIT && mode != MIROGPU_ANY_HIT) return fail(MIROGPU_ERR_INVALID_ARG, "unknown mode");
+    if (n == 0) return MIROGPU_OK;
+    CUDA_TRY(cudaSetDevice(h->device));
+    mirogpu_ray* d_r = nullptr; mirogpu_hit* d_h = nullptr; unsigned long long* d_c = nullptr;
+    CUDA_TRY(cudaMalloc(&d_r, n * sizeof(mirogpu_ray)));
+    CUDA_TRY(cudaMalloc(&d_h, n * sizeof(mirogpu_hit)));
+    CUDA_TRY(cudaMalloc(&d_c, 4 * sizeof(unsigned long long)));
+    CUDA_TRY(cudaMemset(d_c, 0, 4 * sizeof(unsigned long long)));
+    CUDA_TRY(cudaMemcpy(d_r, rays, n * sizeof(mirogpu_ray), cudaMemcpyHostToDevice));
+    const unsigned grid = (unsigned)((n + 127) / 128);
+    const bool any = mode == MIROGPU_ANY_HIT;
+    if (h->layout == MIROGPU_LAYOUT_BVH2) {
+        if (any) k_trace_simple<MIROGPU_LAYOUT_BVH2, true, true><<<grid, 128>>>(h->ds, d_r, n, d_h, d_c);
+        else k_trace_simple<MIROGPU_LAYOUT_BVH2, false, true><<<grid, 128>>>(h->ds, d_r, n, d_h, d_c);
+    } else {
+        if (any) k_trace_simple<MIROGPU_LAYOUT_CWBVH8, true, true><<<grid, 128>>>(h->ds, d_r, n, d_h, d_c);
+        else k_trace_simple<MIROGPU_LAYOUT_CWBVH8, false, true><<<grid, 128>>>(h->ds, d_r, n, d_h, d_c);
+    }
+    CUDA_TRY(cudaGetLastError());
+    unsigned long long hc[4];
+    CUDA_TRY(cudaMemcpy(hc, d_c, sizeof hc, cudaMemcpyDeviceToHost));
+    CUDA_TRY(cudaMemcpy(hits, d_h, n * sizeof(mirogpu_hit), cudaMemcpyDeviceToHost));
+    cudaFree(d_r); cudaFree(d_h); cudaFree(d_c);
+    const uint64_t node_size = h->layout == MIROGPU_LAYOUT_BVH2 ? 64 : 80;
+    c->rays += n; c->node_visits += hc[0]; c->box_tests += hc[1]; c->triangle_tests += hc[2]; c->hits += hc[3];
+    c->bytes_fetched += hc[0] * node_size + hc[2] * 48;
+    return MIROGPU_OK;
+}
+
+int mirogpu_resolve_hits_device(mirogpu_handle h, const mirogpu_hit* d_hits, size_t n, float* d_P, float* d_N,
+                                uint32_t* d_material, void* cuda_stream)
+{
+    if (!h || (n && !d_hits)) return fail(MIROGPU_ERR_INVALID_ARG, "NULL argument");
+    if (n == 0) return MIROGPU_OK;
+    CUDA_TRY(cudaSetDevice(h->device));
+    k_resolve_hits<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)cuda_stream>>>(h->ds, d_hits, n, d_P, d_N, d_material);
+    CUDA_TRY(cudaGetLastError());
+    return MIROGPU_OK;
+}
+
+int mirogpu_generate_primary_device(mirogpu_handle h, const mirogpu_camera* cam, int width, int height, int row_begin,
+                                    int row_end, int jitter, uint32_t seed, uint32_t sample, mirogpu_ray* d_rays,
+                                    void* cuda_stream)
+{
+    if (!h || !cam || !d_rays) return fail(MIROGPU_ERR_INVALID_ARG, "NULL argument");
+    if (width <= 0 || height <= 0 || row_begin < 0 || row_end > height || row_begin > row_end)
+        return fail(MIROGPU_ERR_INVALID_ARG, "bad image or row range");
+    const size_t npix = (size_t)(row_end - row_begin) * width;
+    if (npix == 0) return MIROGPU_OK;
+    CUDA_TRY(cudaSetDevice(h->device));
+    CameraBasis cb;
+    camera_basis(*cam, width, height, cb);
+    k_gen_primary<<<(unsigned)((npix + 255) / 256), 256, 0, (cudaStream_t)cuda_stream>>>(cb, width, height, row_begin, row_end,
+                                                                                           jitter, seed, sample, d_rays);
+    CUDA_TRY(cudaGetLastError());
+    return MIROGPU_OK;
+}
+
+int mirogpu_generate_bounce_device(mirogpu_handle h, const mirogpu_ray* d_rays, const mirogpu_hit* d_hits, size_t n,
+                                   uint32_t seed, uint32_t sample, mirogpu_ray* d_out, void* cuda_stream)
+{
+    if (!h || (n && (!d_rays || !d_hits || !d_out))) return fail(MIROGPU_ERR_INVALID_ARG, "NULL argument");
+    if (n == 0) return MIROGPU_OK;
+    CUDA_TRY(cudaSetDevice(h->device));
+    k_gen_bounce<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)cuda_stream>>>(h->ds, d_rays, d_hits, n, seed, sample, d_out);
+    CUDA_TRY(cudaGetLastError());
+    return MIROGPU_OK;
+}
+
+int mirogpu_rng_uniforms(uint32_t seed, uint32_t sample, uint32_t dimension, size_t first, size_t n, float* out)
+{
+    if (n && !out) return fail(MIROGPU_ERR_INVALID_ARG, "NULL argument");
+    for (size_t i = 0; i < n; ++i) uniform2(seed, (uint32_t)(first + i), sample, dimension, out[2 * i], out[2 * i + 1]);
+    return MIROGPU_OK;
+}
+
+int mirogpu_last_call_stats(mirogpu_handle h, uint64_t* rays_traced, uint64_t* kernel_launches)
+{
+    if (!h) return fail(MIROGPU_ERR_INVALID_ARG, "NULL handle");
+    std::lock_guard<std::mutex> lk(h->mtx);
+    if (rays_traced) *rays_traced = h->last_rays;
+    if (kernel_launches) *kernel_launches = h->last_launches;
+    return MIROGPU_OK;
+}
+
+int mirogpu_render(mirogpu_handle h, const mirogpu_camera* cam, const mirogpu_render_params* p, float* rgb_out)
+{
+    if (!h || !cam || !p || !rgb_out) return fail(MIROGPU_ERR_INVALID_ARG, "NULL argument");
+    CUDA_TRY(cudaSetDevice(h->device));
+    std::string err;
+    const int rc = render_host(h, *cam, *p, rgb_out, err);
+    return rc == MIROGPU_OK ? rc : fail(rc, err);
+}
+
+int mirogpu_render_device(mirogpu_handle h, const mirogpu_camera* cam, const mirogpu_render_params* p, float* d_rgb,
+                          void* cuda_stream)
+{
+    if (!h || !cam || !p || !d_rgb) return fail(MIROGPU_ERR_INVALID_ARG, "NULL argument");
+    CUDA_TRY(cudaSetDevice(h->device));
+    std::string err;
+    const int rc = render_device(h, *cam, *p, d_rgb, (cudaStream_t)cuda_stream, err);
+    return rc == MIROGPU_OK ? rc : fail(rc, err);
+}
+
+int mirogpu_photon_upload(mirogpu_handle h, int which, const void* photons, int stored)
+{
+    if (!h || which < 0 || which > 1 || stored < 0 || (stored && !photons)) return fail(MIROGPU_ERR_INVALID_ARG, "bad argument");
+    CUDA_TRY(cudaSetDevice(h->device));
+    std::lock_guard<std::mutex> lk(h->mtx);
+    std::string err;
+    const int rc = h->pm[which].upload(photons, stored, err);
+    return rc == MIROGPU_OK ? rc : fail(rc, err);
+}
+
+int mirogpu_photon_gather_device(mirogpu_handle h, int which, const float* d_pos3, const float* d_normal3, size_t n,
+                                 float max_dist, int k, float* d_irrad3, void* cuda_stream)
+{
+    if (!h || which < 0 || which > 1 || (n && (!d_pos3 || !d_normal3 || !d_irrad3))) return fail(MIROGPU_ERR_INVALID_ARG, "bad argument");
+    if (k < 1 || k > MIRO_PHOTON_KMAX) return fail(MIROGPU_ERR_INVALID_ARG, "k out of range (1..512)");
+    if (n == 0) return MIROGPU_OK;
+    CUDA_TRY(cudaSetDevice(h->device));
+    CUDA_TRY(photon_gather_launch(h->pm[which], d_pos3, d_normal3, n, max_dist, k, d_irrad3, (cudaStream_t)cuda_stream));
+    return MIROGPU_OK;
+}
+
+int mirogpu_photon_gather(mirogpu_handle h, int which, const float* pos3, const float* normal3, size_t n, float max_dist,
+                          int k, float* irrad3)
+{
+    if (!h || which < 0 || which > 1 || (n && (!pos3 || !normal3 || !irrad3))) return fail(MIROGPU_ERR_INVALID_ARG, "bad argument");
+    if (k < 1 || k > MIRO_PHOTON_KMAX) return fail(MIROGPU_ERR_INVALID_ARG, "k out of range (1..512)");
+    if (n == 0) return MIROGPU_OK;
+    CUDA_TRY(cudaSetDevice(h->device));
+    float *d_p = nullptr, *d_n = nullptr, *d_i = nullptr;
+    CUDA_TRY(cudaMalloc(&d_p, n * 12)); CUDA_TRY(cudaMalloc(&d_n, n * 12)); CUDA_TRY(cudaMalloc(&d_i, n * 12));
+    CUDA_TRY(cudaMemcpy(d_p, pos3, n * 12, cudaMemcpyHostToDevice));
+    CUDA_TRY(cudaMemcpy(d_n, normal3, n * 12, cudaMemcpyHostToDevice));
+    cudaError_t e = photon_gather_launch(h->pm[which], d_p, d_n, n, max_dist, k, d_i, cudaStreamPerThread);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(cudaStreamPerThread);
+    if (e == cudaSuccess) e = cudaMemcpy(irrad3, d_i, n * 12, cudaMemcpyDeviceToHost);
+    cudaFree(d_p); cudaFree(d_n); cudaFree(d_i);
+    if (e != cudaSuccess) return fail(MIROGPU_ERR_CUDA, std::string("photon_gather: ") + cudaGetErrorString(e));
+    return MIROGPU_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,31 @@
+// photon.cuh -- photon-map kNN gather on the device (Photon_map::irradiance_estimate / locate_photons,
+// reference PhotonMap.cpp:81-243) against the reference's own heap-ordered left-balanced kd-tree.
+#ifndef MIROGPU_PHOTON_CUH
+#define MIROGPU_PHOTON_CUH
+#include <cuda_runtime.h>
+#include <cstdint>
+#include <cstddef>
+#include <string>
+#include "../../include/mirogpu.h"
+
+#define MIRO_PHOTON_KMAX 512
+
+namespace mirogpu {
+
+struct PhotonMapDevice {
+    float4* d_photons = nullptr;  // 2 float4 per photon: (pos.xyz, plane|theta<<8|phi<<16 bits) (power.xyz, 0)
+    float* d_tables = nullptr;    // costheta[256] sintheta[256] cosphi[256] sinphi[256]  (PhotonMap.cpp:47-53)
+    int stored = 0, half_stored = 0;
+    int upload(const void* photons28, int stored, std::string& err);
+    void release()
+    {
+        cudaFree(d_photons); cudaFree(d_tables);
+        d_photons = nullptr; d_tables = nullptr; stored = half_stored = 0;
+    }
+};
+
+cudaError_t photon_gather_launch(const PhotonMapDevice& pm, const float* d_pos3, const float* d_normal3, size_t n,
+                                 float max_dist, int k, float* d_irrad3, cudaStream_t st);
+
+}  // namespace mirogpu
+#endif

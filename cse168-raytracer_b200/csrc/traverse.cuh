@@ -1,0 +1,323 @@
+// traverse.cuh -- per-ray traversal cores and the reference's ray-triangle test, written once as
+// host/device inline functions: the CUDA kernels in kernels.cu call them per thread on sm_100a, and the
+// test-only emulation harness (tests/cpu_emu/emu.cu, never linked into the product) calls the very same
+// code on the host so traversal logic can be checked against the oracle without a GPU.
+//
+// Arithmetic contract.  The triangle test reproduces Triangle::intersect (reference Triangle.cpp:136-169)
+// operation for operation in IEEE binary32 with round-to-nearest and NO fused multiply-add: the device
+// build uses __fmul_rn/__fadd_rn/__fsub_rn/__fdiv_rn, which nvcc never contracts, so t, beta and gamma
+// are bit-identical to the reference's scalar CPU build.  Box tests are free to use FMA: any conservative
+// slab test yields the same closest hit.
+#ifndef MIROGPU_TRAVERSE_CUH
+#define MIROGPU_TRAVERSE_CUH
+
+#include <cstdint>
+#include <cuda_runtime.h>
+
+#include "../../include/mirogpu.h"
+
+#define MIRO_HD __host__ __device__ __forceinline__
+
+namespace mirogpu {
+
+#define MIRO_EPS 1e-4f /* epsilon, Miro.h:9 */
+
+// ---- exactly-rounded, never-contracted binary32 ops ----------------------------------------------------
+MIRO_HD float xmul(float a, float b)
+{
+#ifdef __CUDA_ARCH__
+    return __fmul_rn(a, b);
+#else
+    return a * b;
+#endif
+}
+MIRO_HD float xadd(float a, float b)
+{
+#ifdef __CUDA_ARCH__
+    return __fadd_rn(a, b);
+#else
+    return a + b;
+#endif
+}
+MIRO_HD float xsub(float a, float b)
+{
+#ifdef __CUDA_ARCH__
+    return __fsub_rn(a, b);
+#else
+    return a - b;
+#endif
+}
+MIRO_HD float xdiv(float a, float b)
+{
+#ifdef __CUDA_ARCH__
+    return __fdiv_rn(a, b);
+#else
+    return a / b;
+#endif
+}
+MIRO_HD float xsqrt(float a)
+{
+#ifdef __CUDA_ARCH__
+    return __fsqrt_rn(a);
+#else
+    return sqrtf(a);
+#endif
+}
+// dot(a, b) = a.x*b.x + a.y*b.y + a.z*b.z, left to right (Vector3.h:243-246)
+MIRO_HD float xdot(float ax, float ay, float az, float bx, float by, float bz)
+{
+    return xadd(xadd(xmul(ax, bx), xmul(ay, by)), xmul(az, bz));
+}
+
+template <typename T>
+MIRO_HD T ldg(const T* p)
+{
+#ifdef __CUDA_ARCH__
+    return __ldg(p);
+#else
+    return *p;
+#endif
+}
+MIRO_HD int popc32(uint32_t x)
+{
+#ifdef __CUDA_ARCH__
+    return __popc(x);
+#else
+    return __builtin_popcount(x);
+#endif
+}
+MIRO_HD int bfind32(uint32_t x)  // index of the highest set bit; x != 0
+{
+#ifdef __CUDA_ARCH__
+    return 31 - __clz((int)x);
+#else
+    return 31 - __builtin_clz(x);
+#endif
+}
+MIRO_HD float u2f(uint32_t u)
+{
+#ifdef __CUDA_ARCH__
+    return __uint_as_float(u);
+#else
+    union { uint32_t u; float f; } c; c.u = u; return c.f;
+#endif
+}
+MIRO_HD uint32_t f2u(float f)
+{
+#ifdef __CUDA_ARCH__
+    return __float_as_uint(f);
+#else
+    union { uint32_t u; float f; } c; c.f = f; return c.u;
+#endif
+}
+
+struct TraceCounters {
+    uint32_t nodes, boxes, tris;
+};
+
+struct BestHit {
+    float t;
+    uint32_t prim;  // MIROGPU_MISS until something is accepted
+    float beta, gamma;
+};
+
+// Triangle::intersect, Triangle.cpp:150-158.  v0 = (A, prim id bits), v1 = (B-A, -), v2 = (C-A, -).
+// Acceptance on top of the reference's own reject line: the leaf keeps a hit only if it is strictly closer
+// than the best so far (BVH.cpp:498-500); equal t goes to the smaller primitive id so the result does not
+// depend on traversal order.  NaN t fails every comparison and is dropped, as in the reference.
+MIRO_HD bool tri_test(const float4 v0, const float4 v1, const float4 v2, const mirogpu_ray& r, BestHit& best)
+{
+    // normal = cross(BmA, CmA)
+    const float nx = xsub(xmul(v1.y, v2.z), xmul(v1.z, v2.y));
+    const float ny = xsub(xmul(v1.z, v2.x), xmul(v1.x, v2.z));
+    const float nz = xsub(xmul(v1.x, v2.y), xmul(v1.y, v2.x));
+    const float ndx = -r.dx, ndy = -r.dy, ndz = -r.dz;
+    const float ddotn = xdot(ndx, ndy, ndz, nx, ny, nz);
+    const float oax = xsub(r.ox, v0.x), oay = xsub(r.oy, v0.y), oaz = xsub(r.oz, v0.z);
+    const float t = xdiv(xdot(oax, oay, oaz, nx, ny, nz), ddotn);
+    // cross(o-A, CmA)
+    const float c1x = xsub(xmul(oay, v2.z), xmul(oaz, v2.y));
+    const float c1y = xsub(xmul(oaz, v2.x), xmul(oax, v2.z));
+    const float c1z = xsub(xmul(oax, v2.y), xmul(oay, v2.x));
+    const float beta = xdiv(xdot(ndx, ndy, ndz, c1x, c1y, c1z), ddotn);
+    // cross(BmA, o-A)
+    const float c2x = xsub(xmul(v1.y, oaz), xmul(v1.z, oay));
+    const float c2y = xsub(xmul(v1.z, oax), xmul(v1.x, oaz));
+    const float c2z = xsub(xmul(v1.x, oay), xmul(v1.y, oax));
+    const float gamma = xdiv(xdot(ndx, ndy, ndz, c2x, c2y, c2z), ddotn);
+    if (beta < -MIRO_EPS || gamma < -MIRO_EPS || xadd(beta, gamma) > 1 + MIRO_EPS || t < r.tmin || t > best.t) return false;
+    const uint32_t prim = f2u(v0.w);
+    if (t < best.t || (t == best.t && prim < best.prim)) {
+        best.t = t; best.prim = prim; best.beta = beta; best.gamma = gamma;
+        return true;
+    }
+    return false;
+}
+
+MIRO_HD float safe_rcp(float d)
+{
+    // 1/d with |d| clamped away from zero so that 0 * inf never produces a NaN in the slab test
+    const float a = fabsf(d) < 1e-30f ? copysignf(1e-30f, d) : d;
+    return 1.0f / a;
+}
+
+#define MIRO_STACK 64
+
+// ---- BVH2 (64-byte nodes, two child boxes per fetch) ---------------------------------------------------
+template <bool ANY, bool COUNT>
+MIRO_HD void trace_bvh2(const float4* __restrict__ nodes, const float4* __restrict__ tris, const mirogpu_ray& r,
+                        BestHit& best, TraceCounters* cnt)
+{
+    const float idx = safe_rcp(r.dx), idy = safe_rcp(r.dy), idz = safe_rcp(r.dz);
+    const float oodx = r.ox * idx, oody = r.oy * idy, oodz = r.oz * idz;
+    int32_t stack[MIRO_STACK];
+    int sp = 0;
+    int32_t node = 0;
+    best.t = r.tmax; best.prim = MIROGPU_MISS; best.beta = 0.f; best.gamma = 0.f;
+    if (!(r.tmax >= r.tmin)) return;
+    for (;;) {
+        while (node >= 0) {
+            const float4 n0 = ldg(nodes + 4 * node + 0);
+            const float4 n1 = ldg(nodes + 4 * node + 1);
+            const float4 nz = ldg(nodes + 4 * node + 2);
+            const float4 lk = ldg(nodes + 4 * node + 3);
+            if (COUNT) { cnt->nodes++; cnt->boxes += 2; }
+            const float c0lox = n0.x * idx - oodx, c0hix = n0.y * idx - oodx;
+            const float c0loy = n0.z * idy - oody, c0hiy = n0.w * idy - oody;
+            const float c0loz = nz.x * idz - oodz, c0hiz = nz.y * idz - oodz;
+            const float c1lox = n1.x * idx - oodx, c1hix = n1.y * idx - oodx;
+            const float c1loy = n1.z * idy - oody, c1hiy = n1.w * idy - oody;
+            const float c1loz = nz.z * idz - oodz, c1hiz = nz.w * idz - oodz;
+            const float t0n = fmaxf(fmaxf(fminf(c0lox, c0hix), fminf(c0loy, c0hiy)), fmaxf(fminf(c0loz, c0hiz), r.tmin));
+            const float t0f = fminf(fminf(fmaxf(c0lox, c0hix), fmaxf(c0loy, c0hiy)), fminf(fmaxf(c0loz, c0hiz), best.t));
+            const float t1n = fmaxf(fmaxf(fminf(c1lox, c1hix), fminf(c1loy, c1hiy)), fmaxf(fminf(c1loz, c1hiz), r.tmin));
+            const float t1f = fminf(fminf(fmaxf(c1lox, c1hix), fmaxf(c1loy, c1hiy)), fminf(fmaxf(c1loz, c1hiz), best.t));
+            const bool h0 = t0n <= t0f, h1 = t1n <= t1f;
+            const int32_t l0 = (int32_t)f2u(lk.x), l1 = (int32_t)f2u(lk.y);
+            if (!h0 && !h1) {
+                if (sp == 0) return;
+                node = stack[--sp];
+            } else {
+                node = h0 ? l0 : l1;
+                if (h0 && h1) {
+                    int32_t other = l1;
+                    if (t1n < t0n) { node = l1; other = l0; }
+                    stack[sp++] = other;
+                }
+            }
+        }
+        // leaf: ~node = (first << 3) | (count - 1)
+        {
+            const uint32_t ref = (uint32_t)~node;
+            const uint32_t first = ref >> 3, count = (ref & 7u) + 1u;
+            for (uint32_t i = 0; i < count; ++i) {
+                const float4 v0 = ldg(tris + 3 * (first + i) + 0);
+                const float4 v1 = ldg(tris + 3 * (first + i) + 1);
+                const float4 v2 = ldg(tris + 3 * (first + i) + 2);
+                if (COUNT) cnt->tris++;
+                const bool acc = tri_test(v0, v1, v2, r, best);
+                if (ANY && acc) return;
+            }
+            if (sp == 0) return;
+            node = stack[--sp];
+        }
+    }
+}
+
+// ---- CWBVH8 (80-byte nodes, eight 8-bit-quantised child boxes per fetch) --------------------------------
+// Node words (5 x uint4), see Cwbvh8Node in bvh_build.h:
+//   w0 = px, py, pz, (ex | ey<<8 | ez<<16 | imask<<24)
+//   w1 = child_base, tri_base, meta[0..3], meta[4..7]
+//   w2 = qlox[0..3], qlox[4..7], qloy[0..3], qloy[4..7]
+//   w3 = qloz[0..3], qloz[4..7], qhix[0..3], qhix[4..7]
+//   w4 = qhiy[0..3], qhiy[4..7], qhiz[0..3], qhiz[4..7]
+// Traversal state: a node group G = (child_base, hits<<24 | imask) whose bits 24..31 mark internal children
+// still to visit, ordered so that the highest bit is the child nearest along the ray's octant; a triangle
+// group T = (tri_base, 24-bit mask).  Slot s of a node gets bit 24 + (s ^ octinv).
+MIRO_HD uint32_t byte_of(uint32_t w, int i) { return (w >> (8 * i)) & 0xffu; }
+
+template <bool ANY, bool COUNT>
+MIRO_HD void trace_cwbvh8(const uint4* __restrict__ nodes, const float4* __restrict__ tris, const mirogpu_ray& r,
+                          BestHit& best, TraceCounters* cnt)
+{
+    const float idx = safe_rcp(r.dx), idy = safe_rcp(r.dy), idz = safe_rcp(r.dz);
+    const uint32_t octinv = (r.dx >= 0.f ? 4u : 0u) | (r.dy >= 0.f ? 2u : 0u) | (r.dz >= 0.f ? 1u : 0u);
+    uint2 stack[MIRO_STACK];
+    int sp = 0;
+    best.t = r.tmax; best.prim = MIROGPU_MISS; best.beta = 0.f; best.gamma = 0.f;
+    if (!(r.tmax >= r.tmin)) return;
+    uint2 G = make_uint2(0u, 0x80000000u);  // the root: base 0, one pending "child" whose relative index is 0
+    for (;;) {
+        uint2 T = make_uint2(0u, 0u);
+        if (G.y & 0xff000000u) {
+            const uint32_t hits_imask = G.y;
+            const int bit = bfind32(hits_imask);
+            G.y &= ~(1u << bit);
+            if (G.y & 0xff000000u) stack[sp++] = G;
+            const uint32_t slot = ((uint32_t)(bit - 24)) ^ octinv;
+            const uint32_t rel = (uint32_t)popc32(hits_imask & ((1u << slot) - 1u) & 0xffu);
+            const uint32_t ni = G.x + rel;
+            const uint4 w0 = ldg(nodes + 5 * (size_t)ni + 0);
+            const uint4 w1 = ldg(nodes + 5 * (size_t)ni + 1);
+            const uint4 w2 = ldg(nodes + 5 * (size_t)ni + 2);
+            const uint4 w3 = ldg(nodes + 5 * (size_t)ni + 3);
+            const uint4 w4 = ldg(nodes + 5 * (size_t)ni + 4);
+            if (COUNT) { cnt->nodes++; cnt->boxes += 8; }
+            const uint32_t imask = w0.w >> 24;
+            // cell size per axis * 1/d, and the node origin relative to the ray, in ray-parameter units
+            const float ax = u2f((w0.w & 0xffu) << 23) * idx;
+            const float ay = u2f(((w0.w >> 8) & 0xffu) << 23) * idy;
+            const float az = u2f(((w0.w >> 16) & 0xffu) << 23) * idz;
+            const float bx = (u2f(w0.x) - r.ox) * idx;
+            const float by = (u2f(w0.y) - r.oy) * idy;
+            const float bz = (u2f(w0.z) - r.oz) * idz;
+            uint32_t hitmask = 0;
+#pragma unroll
+            for (int half = 0; half < 2; ++half) {
+                const uint32_t meta4 = half ? w1.w : w1.z;
+                const uint32_t qlx = half ? w2.y : w2.x, qly = half ? w2.w : w2.z, qlz = half ? w3.y : w3.x;
+                const uint32_t qhx = half ? w3.w : w3.z, qhy = half ? w4.y : w4.x, qhz = half ? w4.w : w4.z;
+                // near / far plane per axis by the sign of the direction
+                const uint32_t nxq = r.dx >= 0.f ? qlx : qhx, fxq = r.dx >= 0.f ? qhx : qlx;
+                const uint32_t nyq = r.dy >= 0.f ? qly : qhy, fyq = r.dy >= 0.f ? qhy : qly;
+                const uint32_t nzq = r.dz >= 0.f ? qlz : qhz, fzq = r.dz >= 0.f ? qhz : qlz;
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    const float tnx = (float)byte_of(nxq, i) * ax + bx, tfx = (float)byte_of(fxq, i) * ax + bx;
+                    const float tny = (float)byte_of(nyq, i) * ay + by, tfy = (float)byte_of(fyq, i) * ay + by;
+                    const float tnz = (float)byte_of(nzq, i) * az + bz, tfz = (float)byte_of(fzq, i) * az + bz;
+                    const float tn = fmaxf(fmaxf(tnx, tny), fmaxf(tnz, r.tmin));
+                    const float tf = fminf(fminf(tfx, tfy), fminf(tfz, best.t));
+                    const uint32_t meta = byte_of(meta4, i);
+                    if (tn <= tf && meta != 0u) {
+                        const uint32_t s = (uint32_t)(half * 4 + i);
+                        const uint32_t internal = (imask >> s) & 1u;
+                        const uint32_t bits = meta >> 5;
+                        const uint32_t pos = (meta & 31u) ^ (internal ? octinv : 0u);
+                        hitmask |= bits << pos;
+                    }
+                }
+            }
+            G = make_uint2(w1.x, (hitmask & 0xff000000u) | imask);
+            T = make_uint2(w1.y, hitmask & 0x00ffffffu);
+        }
+        while (T.y) {
+            const int bit = bfind32(T.y);
+            T.y &= ~(1u << bit);
+            const uint32_t ti = T.x + (uint32_t)bit;
+            const float4 v0 = ldg(tris + 3 * (size_t)ti + 0);
+            const float4 v1 = ldg(tris + 3 * (size_t)ti + 1);
+            const float4 v2 = ldg(tris + 3 * (size_t)ti + 2);
+            if (COUNT) cnt->tris++;
+            const bool acc = tri_test(v0, v1, v2, r, best);
+            if (ANY && acc) return;
+        }
+        if ((G.y & 0xff000000u) == 0u) {
+            if (sp == 0) return;
+            G = stack[--sp];
+        }
+    }
+}
+
+}  // namespace mirogpu
+#endif

@@ -1,0 +1,230 @@
+/* mirogpu.h -- C ABI of the B200-native ray-intersection engine for the Miro ray tracer.
+ *
+ * This is the drop-in boundary for the reference's hot path.  The reference has no FFI: the path sits
+ * behind C++ member functions.  Each entry point below names the reference interface it replaces; the
+ * host-side C++ mirror in cse168-raytracer_b200/csrc/miro/ keeps those signatures and forwards here.
+ *
+ *   mirogpu_scene_create        <- BVH::build(Objects*, int)                         BVH.h:33, BVH.cpp:60-339
+ *                                  (called from Scene::preCalc, Scene.cpp:72)
+ *   mirogpu_intersect_batch     <- BVH::intersect / BVH::intersectChildren            BVH.h:35-38, BVH.cpp:438-658
+ *                                  + Triangle::intersect                              Triangle.cpp:136-169
+ *                                  (= Scene::trace with no unbounded objects,         Scene.cpp:214-268)
+ *   mirogpu_generate_primary    <- Camera::eyeRay                                     Camera.cpp:104-161
+ *   mirogpu_generate_bounce     <- Ray::diffuse / Ray::random                         Ray.h:109-140, Utility.h:34-50
+ *   mirogpu_render              <- Scene::raytraceImage + Scene::traceScene           Scene.cpp:93-212, 270-346
+ *                                  + Phong::shade's light loop and shadow query       Phong.cpp:44-161
+ *   mirogpu_photon_upload       <- the balanced Photon array Photon_map::balance leaves   PhotonMap.cpp:314-359
+ *   mirogpu_photon_gather       <- Photon_map::irradiance_estimate / locate_photons   PhotonMap.cpp:81-243
+ *
+ * Conventions: every function returns an int status (MIROGPU_OK = 0), never throws, keeps no global
+ * state besides the per-thread last-error string, and works on an opaque scene handle.  The caller owns
+ * all host buffers.  Queries on one handle may be issued from several host threads.  Functions named
+ * *_device take DEVICE pointers and a cudaStream_t (passed as void*) and are asynchronous on that stream;
+ * the others take HOST pointers, copy in and out, and return when the result is in the caller's buffer.
+ * There is no CPU fallback: without a CUDA device every call fails with MIROGPU_ERR_NO_DEVICE.
+ *
+ * Primitive identity: prim_id is the index of the triangle in the arrays given to mirogpu_scene_create,
+ * which the host mirror fills in Scene::objects() insertion order (Scene.h:20-26).
+ */
+#ifndef MIROGPU_H_INCLUDED
+#define MIROGPU_H_INCLUDED
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MIROGPU_VERSION 1
+
+enum {
+    MIROGPU_OK = 0,
+    MIROGPU_ERR_INVALID_ARG = 1,
+    MIROGPU_ERR_NO_DEVICE = 2,
+    MIROGPU_ERR_CUDA = 3,
+    MIROGPU_ERR_OOM = 4,
+    MIROGPU_ERR_UNSUPPORTED = 5
+};
+
+#define MIROGPU_MISS 0xFFFFFFFFu
+#define MIROGPU_TMAX 1e12f /* MIRO_TMAX, Miro.h:8 */
+
+/* Ray {o, d} of Ray.h:40-46 plus the [tMin, tMax] arguments of BVH::intersect.  32 bytes. */
+typedef struct mirogpu_ray {
+    float ox, oy, oz, tmin;
+    float dx, dy, dz, tmax;
+} mirogpu_ray;
+
+/* What Triangle::intersect computes before it derives P and N (Triangle.cpp:154-156).  16 bytes.
+ * Miss: prim_id = MIROGPU_MISS and t = the ray's tmax (the reference leaves minHit.t = tMax, BVH.cpp:444).
+ * The host reconstructs P = A + beta(B-A) + gamma(C-A), N = (1-beta-gamma)nA + beta nB + gamma nC. */
+typedef struct mirogpu_hit {
+    float t;
+    uint32_t prim_id;
+    float beta, gamma;
+} mirogpu_hit;
+
+/* Phong(kd, ks, kt, shininess, refractIndex) AFTER the constructor's energy clamp (Phong.cpp:13-32). */
+typedef struct mirogpu_material {
+    float kd[3];
+    float ks[3];
+    float kt[3];
+    float shininess; /* +inf disables the highlight (Phong.cpp:149) */
+    float refract_index;
+    float _pad;
+} mirogpu_material;
+
+/* PointLight (kind 0, PointLight.h) or DirectionalAreaLight (kind 1, DirectionalAreaLight.h). */
+typedef struct mirogpu_light {
+    int32_t kind;
+    float position[3];
+    float color[3];
+    float wattage;
+    float normal[3]; /* kind 1 only */
+    float radius;    /* kind 1 only */
+} mirogpu_light;
+
+/* Camera state of Camera.h:56-61 (eye, up, viewDir already normalised as the setters do; fov in degrees). */
+typedef struct mirogpu_camera {
+    float eye[3];
+    float up[3];
+    float view_dir[3];
+    float fov_degrees;
+} mirogpu_camera;
+
+enum { MIROGPU_LAYOUT_BVH2 = 0, MIROGPU_LAYOUT_CWBVH8 = 1 };
+
+typedef struct mirogpu_build_options {
+    int32_t layout;       /* MIROGPU_LAYOUT_*; default CWBVH8 */
+    int32_t max_leaf;     /* triangles per leaf (BVH2: <= 4 like the reference's OBJECTS_PER_LEAF; CWBVH8: <= 3) */
+    int32_t sah_bins;     /* binned SAH resolution, default 32 */
+    int32_t device;       /* CUDA device ordinal, -1 = current device */
+} mirogpu_build_options;
+
+typedef struct mirogpu_scene_info {
+    uint32_t num_triangles;
+    uint32_t num_nodes;        /* nodes of the flat layout in HBM */
+    uint32_t num_binary_nodes; /* nodes of the intermediate binary SAH tree */
+    uint32_t num_binary_leaves;
+    uint32_t max_depth;
+    int32_t layout;
+    uint64_t node_bytes;
+    uint64_t triangle_bytes;
+    uint64_t shading_bytes;
+    double build_seconds;   /* host SAH build */
+    double flatten_seconds; /* wide collapse + encode */
+    double upload_seconds;
+    float bounds_min[3];
+    float bounds_max[3];
+} mirogpu_scene_info;
+
+enum { MIROGPU_CLOSEST_HIT = 0, MIROGPU_ANY_HIT = 1 };
+
+/* mode bits for mirogpu_render */
+enum {
+    MIROGPU_RENDER_WHITTED = 0,        /* the reference's default build: direct light + shadow + reflect/refract recursion */
+    MIROGPU_RENDER_DIFFUSE_BOUNCE = 1, /* BASELINE config 3: jittered primary + one cosine-weighted Ray::diffuse bounce */
+    MIROGPU_RENDER_PRIMARY_ONLY = 2    /* direct light, no shadow rays (reference -DDISABLE_SHADOWS) */
+};
+
+typedef struct mirogpu_render_params {
+    int32_t width, height;
+    int32_t spp;       /* samples per pixel; 1 with jitter = 0 reproduces the reference's pixel-centre ray */
+    int32_t jitter;    /* 1: Camera::eyeRay(randomize = true) with the counter-based RNG */
+    int32_t max_depth; /* TRACE_DEPTH, Miro.h:13 */
+    int32_t mode;      /* MIROGPU_RENDER_* */
+    uint32_t seed;
+    int32_t tonemap;   /* 1: apply Scene.cpp:177-202 (NaN -> max, sigmoid(6v-3)); output still float */
+    /* Screen-space shard for multi-GPU: this call renders rows [row_begin, row_end) interleaved
+     * as row % row_stride == row_phase.  Full frame: 0, height, 1, 0. */
+    int32_t row_begin, row_end, row_stride, row_phase;
+    float bg_color[3];
+    int32_t use_photon_maps; /* 1: add irradiance_estimate of both maps at diffuse hits (Scene.cpp:286-299) */
+    int32_t shadows;         /* 0: the reference's -DDISABLE_SHADOWS build (Phong.cpp:91): no shadow rays */
+} mirogpu_render_params;
+
+/* Per-call work counters of the instrumented kernels (reference: -DSTATS, Stats.h). */
+typedef struct mirogpu_counters {
+    uint64_t rays;
+    uint64_t node_visits;    /* flat-layout nodes fetched */
+    uint64_t box_tests;      /* child boxes tested */
+    uint64_t triangle_tests; /* reference: Stats::Ray_Tri_Intersect, BVH.cpp:496 */
+    uint64_t hits;
+    uint64_t bytes_fetched;  /* node + triangle bytes requested by the traversal */
+} mirogpu_counters;
+
+typedef struct mirogpu_scene* mirogpu_handle;
+
+/* ---- lifetime ------------------------------------------------------------------------------------------ */
+int mirogpu_version(void);
+const char* mirogpu_last_error(void);
+int mirogpu_device_count(int* count);
+
+/* Builds the acceleration structure on the host from per-triangle arrays, flattens it to the GPU layout
+ * and uploads it to the selected device.  tri_vertices: ntris x 9 floats (A, B, C); tri_normals: ntris x 9
+ * floats (nA, nB, nC) or NULL; material_ids: ntris entries or NULL (all 0); materials may be NULL (one
+ * white Lambert).  opt may be NULL. */
+int mirogpu_scene_create(const float* tri_vertices, const float* tri_normals, const uint32_t* material_ids,
+                         uint32_t ntris, const mirogpu_material* materials, uint32_t nmaterials,
+                         const mirogpu_build_options* opt, mirogpu_handle* out);
+int mirogpu_scene_destroy(mirogpu_handle h);
+int mirogpu_scene_info_get(mirogpu_handle h, mirogpu_scene_info* info);
+int mirogpu_scene_set_lights(mirogpu_handle h, const mirogpu_light* lights, uint32_t nlights);
+
+/* Copies the flat node array / the reordered triangle array back to the host for inspection (tests check
+ * every flat box against the triangles below it).  *bytes in: capacity, out: size needed/written. */
+int mirogpu_debug_copy_nodes(mirogpu_handle h, void* out, uint64_t* bytes);
+int mirogpu_debug_copy_triangles(mirogpu_handle h, void* out, uint64_t* bytes);
+
+/* ---- batched intersection (BVH::intersect over n rays) ---------------------------------------------- */
+int mirogpu_intersect_batch(mirogpu_handle h, const mirogpu_ray* rays, size_t n, mirogpu_hit* hits, int mode);
+int mirogpu_intersect_batch_device(mirogpu_handle h, const mirogpu_ray* d_rays, size_t n, mirogpu_hit* d_hits,
+                                   int mode, void* cuda_stream);
+/* Same query through the instrumented kernel; counters are accumulated into *c (host struct). */
+int mirogpu_intersect_batch_counted(mirogpu_handle h, const mirogpu_ray* rays, size_t n, mirogpu_hit* hits,
+                                    int mode, mirogpu_counters* c);
+/* Kernel variant selection for measurement (0 = default persistent kernel). */
+int mirogpu_set_kernel_variant(mirogpu_handle h, int variant);
+
+/* Reconstructs P, N (normalised as Scene::trace does for UV materials, Scene.cpp:262) and material id
+ * from hits.  Outputs are n x 3 floats / n uint32; any may be NULL. */
+int mirogpu_resolve_hits_device(mirogpu_handle h, const mirogpu_hit* d_hits, size_t n, float* d_P, float* d_N,
+                                uint32_t* d_material, void* cuda_stream);
+
+/* ---- device-side ray generation ------------------------------------------------------------------------ */
+/* Camera::eyeRay for every pixel of rows [row_begin,row_end) (row 0 = bottom), sample index `sample`.
+ * Writes (row_end-row_begin)*width rays in row-major order.  jitter = 0: pixel centre (dx = dy = 0.5). */
+int mirogpu_generate_primary_device(mirogpu_handle h, const mirogpu_camera* cam, int width, int height,
+                                    int row_begin, int row_end, int jitter, uint32_t seed, uint32_t sample,
+                                    mirogpu_ray* d_rays, void* cuda_stream);
+/* Ray::diffuse at every hit of (d_rays, d_hits): phi = asin(sqrt(u1)), theta = 2 pi u2, direction aligned to
+ * the normalised shading normal, origin P + eps*dir.  Misses yield a ray with tmax < tmin (never hits). */
+int mirogpu_generate_bounce_device(mirogpu_handle h, const mirogpu_ray* d_rays, const mirogpu_hit* d_hits, size_t n,
+                                   uint32_t seed, uint32_t sample, mirogpu_ray* d_out, void* cuda_stream);
+/* The uniform numbers the generators draw, for feeding the oracle the same samples: out = n x 2 floats. */
+int mirogpu_rng_uniforms(uint32_t seed, uint32_t sample, uint32_t dimension, size_t first, size_t n, float* out);
+
+/* ---- whole-frame render (Scene::raytraceImage) -------------------------------------------------------- */
+/* rgb_out: HOST buffer, width*height*3 floats, row 0 = bottom.  Only the rows of this call's shard are written. */
+int mirogpu_render(mirogpu_handle h, const mirogpu_camera* cam, const mirogpu_render_params* p, float* rgb_out);
+/* d_rgb: DEVICE buffer of the same shape.  rays_traced (host, may be NULL) receives the ray count after
+ * the stream is synchronised by the caller only if sync != 0. */
+int mirogpu_render_device(mirogpu_handle h, const mirogpu_camera* cam, const mirogpu_render_params* p, float* d_rgb,
+                          void* cuda_stream);
+/* Rays traced (all kinds) and kernels launched by the last render / intersect call on this handle. */
+int mirogpu_last_call_stats(mirogpu_handle h, uint64_t* rays_traced, uint64_t* kernel_launches);
+
+/* ---- photon map ------------------------------------------------------------------------------------------ */
+/* which: 0 = global map, 1 = caustic map (Scene.h:58-59).  photons: (stored+1) records of the reference's
+ * 28-byte Photon (PhotonMap.h:16-22) in the heap order Photon_map::balance produces; entry 0 is unused. */
+int mirogpu_photon_upload(mirogpu_handle h, int which, const void* photons, int stored);
+int mirogpu_photon_gather(mirogpu_handle h, int which, const float* pos3, const float* normal3, size_t n,
+                          float max_dist, int k, float* irrad3);
+int mirogpu_photon_gather_device(mirogpu_handle h, int which, const float* d_pos3, const float* d_normal3, size_t n,
+                                 float max_dist, int k, float* d_irrad3, void* cuda_stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MIROGPU_H_INCLUDED */

@@ -574,8 +574,9 @@ inline Ray refractRay(const Ray& in, const Hit& h)
     float n1, n2; V3 n;
     const float ri = g->materials[h.material].refr;
     if (dot(in.d, h.N) < 0) { n1 = 1.0f; n2 = ri; n = h.N; } else { n1 = ri; n2 = 1.0f; n = -h.N; }
-    // pow(float,int) promotes to double in the reference (Ray.h:221)
-    float energy = 1 - (std::pow(n1, 2) * (1 - std::pow(dot(in.d, n), 2)) / std::pow(n2, 2));
+    // The reference is built as gnu++98, where pow(float, int) is libstdc++'s __builtin_powif overload
+    // (Ray.h:221); calling the builtin here makes the same compiler emit the same multiply chain.
+    float energy = 1 - (__builtin_powif(n1, 2) * (1 - __builtin_powif(dot(in.d, n), 2)) / __builtin_powif(n2, 2));
     if (energy < 0) return reflectRay(in, h);
     V3 d_r = n1 * (in.d - n * dot(in.d, n)) / n2 - n * std::sqrt(energy);
     Ray r; r.o = h.P + d_r * kEps; r.d = d_r; return r;
@@ -623,7 +624,7 @@ V3 phongShade(const Ray& ray, const Hit& hit, Counters& cn, long long* shadow_ra
         L = L + result * (std::max(0.0f, nDotL * falloff * lt.wattage / ((float)samples)) * diffuseColor * mat.kd) * intensity;
         if (mat.shininess < kInf) {
             V3 r = -l + 2 * dot(l, hit.N) * hit.N;
-            float eDotr = std::pow(std::max(0.0f, std::min(1.f, dot(-ray.d, r))), 500);
+            float eDotr = __builtin_powif(std::max(0.0f, std::min(1.f, dot(-ray.d, r))), 500);   // pow(float,int), gnu++98
             float highlights = std::max(0.0f, eDotr * falloff * lt.wattage / (float)samples);
             L = L + V3(highlights);
         }

@@ -90,6 +90,9 @@ void ref_new_scene()
     g_image = new Image;
     g_materials.clear();
     g_prim_id.clear();
+#ifdef STATS
+    Stats::BVH_Nodes = Stats::BVH_LeafNodes = 0;   // the reference only ever increments these (BVH.cpp:64,88)
+#endif
 }
 
 // Phong(kd, ks, kt, shininess, refractIndex), Phong.cpp:13.  shininess < 0 means "infinity" (the ctor default).

@@ -1,0 +1,288 @@
+"""GPU tier: the CUDA kernels, called through the C ABI (include/mirogpu.h), against the oracle.
+
+Bars (BASELINE.json north_star):
+  * closest-hit prim ids equal the oracle's exhaustive search exactly and t is bit-identical (the device
+    triangle test uses the reference's operand order without FMA);
+  * against the reference's own traversal order (oracle BVH / golden vectors from the real reference) ids may
+    differ only in the documented classes (equal-t ties resolved by visit order, reference false culls):
+    <= 1e-5 of rays, and |t_gpu - t_ref| <= 1e-5 |t_ref| on every ray whose id matches;
+  * generated primary rays are bit-identical to Camera::eyeRay; bounce rays agree to 1e-5 (CUDA's
+    sinf/cosf/asinf differ from glibc's in the last ulp -- hit parity on bounce rays is therefore checked by
+    feeding the oracle the rays the GPU generated).
+Nothing here reads /root/reference.
+"""
+import os
+
+import numpy as np
+import pytest
+
+import objio
+from conftest import bits, random_rays, subsample_rays
+
+pytestmark = pytest.mark.gpu
+torch = pytest.importorskip("torch")
+
+LAYOUTS = [0, 1]
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "ref_hits.npz")
+
+
+def ids_of(hits):
+    i = hits["prim_id"].astype(np.int64)
+    i[i == 0xFFFFFFFF] = -1
+    return i
+
+
+@pytest.fixture(scope="module")
+def host_scenes(pkg, scenes):
+    """name, layout -> (HostScene already preCalc'ed on the GPU, MiroScene view).  One global host scene at a
+    time (like the reference's g_scene), so entries are rebuilt on demand."""
+    state = {"key": None, "H": None}
+
+    def get(name, layout):
+        if state["key"] != (name, layout):
+            H = pkg.HostScene(layout)
+            scenes.realise(H, name, objio.obj_path)
+            H.precalc()
+            state.update(key=(name, layout), H=H)
+        return state["H"], state["H"].scene()
+    return get
+
+
+@pytest.fixture(scope="module")
+def oracle_scene(oracle, scenes):
+    state = {"name": None}
+
+    def get(name):
+        if state["name"] != name:
+            scenes.realise(oracle, name, objio.obj_path)
+            oracle.precalc()
+            state["name"] = name
+        return oracle
+    return get
+
+
+@pytest.mark.parametrize("layout", LAYOUTS)
+@pytest.mark.parametrize("name", ["testobj", "cornell", "teapot"])
+def test_closest_hit_equals_exhaustive_search(host_scenes, oracle_scene, name, layout):
+    H, S = host_scenes(name, layout)
+    O = oracle_scene(name)
+    V = O.dump_triangles()[:, :9].reshape(-1, 3)
+    rays = np.concatenate([O.eye_rays(128, 128), random_rays(20000, V.min(0), V.max(0), 42)])
+    bt, bid, bP, bN = O.trace_brute(rays)
+    for variant in (0, 1):
+        S.set_kernel_variant(variant)
+        hits = S.intersect(rays)
+        assert np.array_equal(ids_of(hits), bid)
+        assert np.array_equal(bits(hits["t"]), bits(bt))
+    S.set_kernel_variant(0)
+
+
+@pytest.mark.parametrize("layout", LAYOUTS)
+def test_bunny_teapot_config2(host_scenes, oracle_scene, layout):
+    """BASELINE config 2 geometry: sampled primary rays + incoherent rays vs exhaustive search, and the full
+    1024^2 primary image vs the reference's traversal semantics."""
+    H, S = host_scenes("bunny_teapot", layout)
+    O = oracle_scene("bunny_teapot")
+    full = O.eye_rays(1024, 1024)
+    sample = np.concatenate([subsample_rays(full, 1024, 1024, 16), random_rays(4000, [-6, 0, -3], [3, 4, 4], 5)])
+    bt, bid, _, _ = O.trace_brute(sample)
+    hits = S.intersect(sample)
+    assert np.array_equal(ids_of(hits), bid)
+    assert np.array_equal(bits(hits["t"]), bits(bt))
+    rt, rid, rP, rN = O.trace(full)
+    hits = S.intersect(full)
+    gid = ids_of(hits)
+    mism = int((gid != rid).sum())
+    assert mism <= max(1, int(1e-5 * full.shape[0])), f"{mism} id mismatches of {full.shape[0]}"
+    same = (gid == rid) & (rid >= 0)
+    assert np.all(np.abs(hits["t"][same] - rt[same]) <= 1e-5 * np.abs(rt[same]))
+    assert np.array_equal(bits(hits["t"][same]), bits(rt[same]))      # in fact bit-identical
+    # the host layer reconstructs P, N, object exactly like Triangle::intersect + Scene::trace
+    ht, hid, hP, hN = H.trace(full[:50000])
+    m = (hid == rid[:50000])
+    assert m.mean() > 0.9999
+    assert np.array_equal(hP[m], rP[:50000][m]) and np.array_equal(hN[m], rN[:50000][m])
+
+
+@pytest.mark.parametrize("layout", LAYOUTS)
+@pytest.mark.parametrize("name", ["testobj", "cornell", "teapot", "bunny_teapot"])
+def test_against_golden_vectors_from_the_real_reference(host_scenes, name, layout):
+    gold = np.load(GOLD)
+    H, S = host_scenes(name, layout)
+    for kind in ("primary", "bounce"):
+        rays = gold[f"{name}__{kind}_rays"]
+        hits = S.intersect(rays)
+        gid, rid, rt = ids_of(hits), gold[f"{name}__{kind}_id"], gold[f"{name}__{kind}_t"]
+        mism = int((gid != rid).sum())
+        assert mism <= max(1, int(1e-4 * rays.shape[0])), f"{kind}: {mism} id mismatches of {rays.shape[0]}"
+        same = gid == rid
+        assert np.array_equal(bits(hits["t"][same]), bits(rt[same]))
+
+
+@pytest.mark.parametrize("layout", LAYOUTS)
+def test_any_hit(host_scenes, pkg, layout):
+    H, S = host_scenes("teapot", layout)
+    rays = random_rays(50000, [-4, 0, -3], [4, 3, 3], 23)
+    rays[:, 7] = np.random.default_rng(1).random(50000, dtype=np.float32) * 6
+    closest = S.intersect(rays)
+    anyh = S.intersect(rays, mode=pkg.ANY_HIT)
+    assert np.array_equal(ids_of(closest) >= 0, ids_of(anyh) >= 0)
+
+
+@pytest.mark.parametrize("layout", LAYOUTS)
+def test_edge_cases(pkg, layout):
+    empty = pkg.MiroScene(np.zeros((0, 9), np.float32), layout=layout)
+    rays = random_rays(1000, [-1, -1, -1], [1, 1, 1], 3)
+    hits = empty.intersect(rays)
+    assert (ids_of(hits) == -1).all() and np.array_equal(hits["t"], rays[:, 7])
+    assert empty.intersect(np.zeros((0, 8), np.float32)).shape == (0,)
+    V = np.array([[0, 0, 0, 1, 0, 0, 0, 1, 0], [5, 5, 5, 5, 5, 5, 5, 5, 5]], np.float32)
+    S = pkg.MiroScene(V, layout=layout)
+    r = np.zeros((7, 8), np.float32)
+    r[:, 0:3] = [0.25, 0.25, 1.0]; r[:, 4:7] = [0, 0, -1]; r[:, 7] = 1e12
+    r[1, 7] = 0.5; r[2, 3] = 1.5; r[3, 4:7] = [0, 0, 1]; r[4, 7] = 1.0
+    r[5, 0:3] = [-5e-5, 0.3, 1.0]; r[6, 0:3] = [-2e-4, 0.3, 1.0]
+    hits = S.intersect(r)
+    assert list(ids_of(hits)) == [0, -1, -1, -1, 0, 0, -1]
+    assert hits["t"][0] == 1.0 and hits["t"][1] == 0.5 and hits["t"][4] == 1.0
+    # ragged batch sizes around the 32-ray packet and 128-thread block boundaries
+    base = random_rays(300, [-1, -1, 0.5], [2, 2, 2], 8); base[:, 4:7] = [0, 0, -1]
+    ref = S.intersect(base)
+    for n in (1, 31, 32, 33, 127, 128, 129, 255, 300):
+        assert np.array_equal(S.intersect(base[:n]), ref[:n])
+    # duplicate geometry: equal t goes to the smaller primitive id
+    D = pkg.MiroScene(np.stack([V[0]] * 9), layout=layout)
+    h = D.intersect(r[:1])
+    assert ids_of(h)[0] == 0 and h["t"][0] == 1.0
+
+
+@pytest.mark.parametrize("layout", LAYOUTS)
+def test_primary_ray_generation_is_bit_exact(host_scenes, oracle_scene, pkg, layout):
+    H, S = host_scenes("bunny_teapot", layout)
+    O = oracle_scene("bunny_teapot")
+    cam = H.camera()
+    for (w, h) in ((64, 64), (1920, 1080), (333, 77)):
+        d = torch.empty((w * h, 8), dtype=torch.float32, device="cuda")
+        S.generate_primary(cam, w, h, d)
+        assert np.array_equal(bits(d.cpu().numpy()), bits(O.eye_rays(w, h)))
+    # a row shard equals the same rows of the full frame
+    w, h = 320, 200
+    full = torch.empty((w * h, 8), dtype=torch.float32, device="cuda")
+    S.generate_primary(cam, w, h, full, jitter=1, seed=7, sample=3)
+    part = torch.empty((50 * w, 8), dtype=torch.float32, device="cuda")
+    S.generate_primary(cam, w, h, part, row_begin=100, row_end=150, jitter=1, seed=7, sample=3)
+    assert torch.equal(part, full[100 * w:150 * w])
+    # jittered rays equal the oracle's eyeRay fed the same uniforms
+    import ctypes
+    import miro_driver as md
+    u = pkg.rng_uniforms(7, 3, 0, 0, w * h)
+    assert u.min() >= 0 and u.max() < 1
+    rays = np.zeros((w * h, 8), np.float32)
+    O.lib.orc_eye_rays_jitter(w, h, md._fp(u), md._fp(rays))
+    assert np.array_equal(bits(full.cpu().numpy()), bits(rays))
+
+
+@pytest.mark.parametrize("layout", LAYOUTS)
+def test_bounce_generation_and_hit_resolution(host_scenes, oracle_scene, pkg, layout):
+    import ctypes
+    import miro_driver as md
+    H, S = host_scenes("bunny_teapot", layout)
+    O = oracle_scene("bunny_teapot")
+    cam = H.camera()
+    w, h = 256, 256
+    n = w * h
+    d_rays = torch.empty((n, 8), dtype=torch.float32, device="cuda")
+    d_hits = torch.empty((n, 4), dtype=torch.float32, device="cuda")
+    d_b = torch.empty((n, 8), dtype=torch.float32, device="cuda")
+    d_P = torch.empty((n, 3), dtype=torch.float32, device="cuda")
+    d_N = torch.empty((n, 3), dtype=torch.float32, device="cuda")
+    S.generate_primary(cam, w, h, d_rays)
+    S.intersect_device(d_rays, d_hits)
+    S.resolve_hits_device(d_hits, d_P, d_N)
+    S.generate_bounce(d_rays, d_hits, d_b, seed=168, sample=0)
+    torch.cuda.synchronize()
+    rays = d_rays.cpu().numpy()
+    hits = d_hits.cpu().numpy().view(pkg.HIT_DTYPE).reshape(-1)
+    ot, oid, oP, oN = O.trace(rays)
+    gid = ids_of(hits)
+    assert (gid != oid).sum() <= 1
+    m = (gid == oid) & (oid >= 0)
+    assert np.array_equal(d_P.cpu().numpy()[m], oP[m]) and np.array_equal(d_N.cpu().numpy()[m], oN[m])
+    # bounce rays: same uniforms through the oracle's Ray::diffuse
+    u = pkg.rng_uniforms(168, 0, 1, 0, n)
+    orays = np.zeros((n, 8), np.float32)
+    O.lib.orc_diffuse_rays(md._fp(oP), md._fp(oN), md._fp(oid.astype(np.int32)), md._fp(u), ctypes.c_long(n), md._fp(orays))
+    b = d_b.cpu().numpy()
+    assert np.allclose(b[m][:, 0:7], orays[m][:, 0:7], rtol=0, atol=2e-5)
+    assert np.all(b[gid < 0][:, 7] < b[gid < 0][:, 3])              # misses produce rays that cannot hit
+    nrm = np.linalg.norm(b[m][:, 4:7], axis=1)
+    assert np.allclose(nrm, 1.0, atol=1e-6)
+    # hit parity on the rays the GPU generated (incoherent second generation)
+    d_h2 = torch.empty((n, 4), dtype=torch.float32, device="cuda")
+    S.intersect_device(d_b, d_h2)
+    h2 = d_h2.cpu().numpy().view(pkg.HIT_DTYPE).reshape(-1)
+    o2t, o2id, _, _ = O.trace(b)
+    g2 = ids_of(h2)
+    assert (g2 != o2id).sum() <= 1
+    mm = (g2 == o2id)
+    assert np.array_equal(bits(h2["t"][mm]), bits(o2t[mm]))
+
+
+@pytest.mark.parametrize("layout", LAYOUTS)
+def test_counters(host_scenes, pkg, layout):
+    H, S = host_scenes("teapot", layout)
+    rays = H.eye_rays(128, 128)
+    hits, c = S.intersect_counted(rays)
+    assert np.array_equal(hits, S.intersect(rays))
+    assert c.rays == rays.shape[0] and c.hits == int((ids_of(hits) >= 0).sum())
+    assert c.node_visits > 0 and c.triangle_tests > 0
+    assert c.bytes_fetched == c.node_visits * (64 if layout == 0 else 80) + c.triangle_tests * 48
+
+
+def test_full_size_properties_bunny20(host_scenes, pkg):
+    """BASELINE config 3 stand-in at full size (1 389 021 triangles, 1920x1080 jittered primaries + bounce):
+    size-independent properties instead of an exhaustive oracle run."""
+    H, S = host_scenes("bunny20", 1)
+    info = S.info
+    assert info.num_triangles == 1389021
+    cam = H.camera()
+    w, h = 1920, 1080
+    n = w * h
+    d_rays = torch.empty((n, 8), dtype=torch.float32, device="cuda")
+    d_hits = torch.empty((n, 4), dtype=torch.float32, device="cuda")
+    d_b = torch.empty((n, 8), dtype=torch.float32, device="cuda")
+    d_h2 = torch.empty((n, 4), dtype=torch.float32, device="cuda")
+    S.generate_primary(cam, w, h, d_rays, jitter=1)
+    S.intersect_device(d_rays, d_hits)
+    S.generate_bounce(d_rays, d_hits, d_b)
+    S.intersect_device(d_b, d_h2)
+    torch.cuda.synchronize()
+    for dr, dh in ((d_rays, d_hits), (d_b, d_h2)):
+        rays = dr.cpu().numpy(); hits = dh.cpu().numpy().view(pkg.HIT_DTYPE).reshape(-1).copy()
+        ids = ids_of(hits)
+        valid = rays[:, 7] >= rays[:, 3]
+        assert (ids[~valid] == -1).all()
+        hit = ids >= 0
+        assert hit.sum() > 1000
+        # (1) idempotence under tmax clipping: with tmax = t_hit the same triangle is found at the same t
+        r2 = rays[hit].copy(); r2[:, 7] = hits["t"][hit]
+        again = S.intersect(r2)
+        assert np.array_equal(again["prim_id"], hits["prim_id"][hit]) and np.array_equal(bits(again["t"]), bits(hits["t"][hit]))
+        # (2) nothing closer: with tmax just below t_hit every ray misses
+        r3 = rays[hit].copy(); r3[:, 7] = np.nextafter(hits["t"][hit], np.float32(0))
+        assert (ids_of(S.intersect(r3)) == -1).all()
+        # (3) any-hit agrees with closest-hit on occlusion
+        anyh = S.intersect(rays, mode=pkg.ANY_HIT)
+        assert np.array_equal(ids_of(anyh) >= 0, hit)
+        # (4) both layouts and both kernel variants give the same answer
+        S.set_kernel_variant(1)
+        assert np.array_equal(S.intersect(rays), hits)
+        S.set_kernel_variant(0)
+        # (5) barycentrics of accepted hits respect the reference's epsilon slop
+        assert (hits["beta"][hit] >= -1e-4).all() and (hits["gamma"][hit] >= -1e-4).all()
+        assert (hits["beta"][hit] + hits["gamma"][hit] <= 1 + 1e-4 + 1e-7).all()
+    # layout independence on a sample, and the sample against the reference's traversal semantics
+    sample = np.concatenate([d_rays.cpu().numpy()[::97], d_b.cpu().numpy()[::97]])
+    h8 = S.intersect(sample)
+    H2, S2 = host_scenes("bunny20", 0)
+    assert np.array_equal(S2.intersect(sample), h8)
