@@ -1,0 +1,419 @@
+#!/usr/bin/env python
+"""bench.py -- closest-hit Mrays/s on BASELINE config 3 (sponza.obj 1920x1080 incoherent diffuse-bounce path
+tracing; sponza.obj is absent from the reference tree, so the declared stand-in of SURVEY 8d is used: the
+reference's makeBunny20Scene geometry, 1 389 021 triangles, with its own camera).
+
+    python bench.py --gpus N --steps K --warmup W            # this engine, one rank per GPU (torchrun for N > 1)
+    python bench.py --impl reference --gpus N --steps K ...  # the reference's own CPU path on the host cores
+
+A step is one pass of the hot path over one batch of synthetic rays: SPP jittered samples of the frame --
+device-side Camera::eyeRay -> closest-hit -> device-side Ray::diffuse at every hit -> closest-hit.
+`value` = (primary + live bounce rays of all ranks) / max-over-ranks device time, inputs resident in HBM.
+`e2e`   = the same metric through the reference-facing call with HOST buffers: Scene::raytraceImage ->
+          mirogpu_render (diffuse-bounce mode, no shadow rays so the ray work equals a step's), framebuffer
+          gathered over NCCL/NVLink for N > 1 and copied to pinned host memory, every step.
+Image rows are interleaved across ranks (row % N == rank); the BVH is replicated; fixed frame => strong scaling.
+"""
+import argparse
+import importlib
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))   # objio (fixture -> .obj) and, for the CPU legs only, miro_driver
+
+METRIC = "closest-hit Mrays/s (sponza, primary+diffuse bounce)"
+SCENE = "bunny20"
+WIDTH, HEIGHT = 1920, 1080
+SPP = 4
+SEED = 168
+# SURVEY 8d yardstick: bytes/ray = 32*V + 36*T + 48 with V, T the scalar reference's node entries / triangle
+# tests per ray.  Measured live with the oracle on a subsample; these are the fall-back figures (SURVEY 8d,
+# bunny x20 bounce rays) if the oracle is unavailable.
+FALLBACK_VT = {"primary": (18.48, 3.37), "bounce": (22.43, 4.70)}
+
+
+def bytes_per_ray(V, T):
+    return 32.0 * V + 36.0 * T + 48.0
+
+
+def peaks():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+
+    Q = "index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown," \
+        "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, index):
+        self.index = index
+        self.path = tempfile.mktemp(prefix="miro_clocks_", suffix=".csv")
+        self.proc = None
+
+    def start(self):
+        try:
+            self.fh = open(self.path, "w")
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=self.fh, stderr=subprocess.DEVNULL)
+        except Exception:
+            self.proc = None
+
+    def stop(self):
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        if self.proc is None:
+            return out
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        self.fh.close()
+        sm, mx, reasons = [], [], set()
+        for line in open(self.path):
+            f = [x.strip() for x in line.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1])); mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        os.unlink(self.path)
+        if sm:
+            out.update(sm_mhz=float(np.median(sm)), sm_max_mhz=float(max(mx)), reasons=sorted(reasons), samples=len(sm))
+        return out
+
+
+def build_host_scene(pkg, scenes, layout):
+    import objio
+    H = pkg.HostScene(layout)
+    scenes.realise(H, SCENE, objio.obj_path)
+    H.precalc()
+    return H
+
+
+# ------------------------------------------------------------------------------------------------------------------
+def cpu_leg(rays_p, rays_b, want_counters=True, kind_pref="reference"):
+    """Times the reference's CPU path (oracle/_ref; else the oracle port) on the given rays with all host threads,
+    and measures V, T per ray with the oracle's exact counters on a subsample."""
+    import miro_driver as md
+    import objio
+    scenes = importlib.import_module("cse168-raytracer_b200.scenes")
+    cores = os.cpu_count() or 1
+    out = {}
+    kind = "reference" if (kind_pref == "reference" and os.path.exists(md.REF_SO)) else "port"
+    D = md.reference("scalar") if kind == "reference" else md.oracle()
+    devnull = os.open(os.devnull, os.O_WRONLY)
+    saved = os.dup(1)
+    os.dup2(devnull, 1)   # the reference prints progress to stdout; keep the JSON line clean
+    try:
+        scenes.realise(D, SCENE, objio.obj_path)
+        build_s = D.precalc()
+        rays = np.concatenate([rays_p, rays_b])
+        D.trace_time(rays[:100000], 0)   # warm the caches / thread pool
+        secs, hits = D.trace_time(rays, 0)
+    finally:
+        os.dup2(saved, 1)
+        os.close(devnull)
+    out["cpu"] = dict(value=rays.shape[0] / secs / 1e6, unit="Mrays/s", cores=cores, kind=kind,
+                      sample=f"{rays_p.shape[0]} primary + {rays_b.shape[0]} live bounce rays of one {WIDTH}x{HEIGHT} sample (the GPU's own rays), "
+                             f"Scene::trace over OpenMP dynamic chunks of 4096; reference BVH build {build_s:.1f} s not timed",
+                      seconds=secs)
+    if want_counters:
+        O = D if kind == "port" else md.oracle()
+        if kind != "port":
+            scenes.realise(O, SCENE, objio.obj_path)
+            O.precalc()
+        vt = {}
+        for name, r in (("primary", rays_p[::16]), ("bounce", rays_b[::16])):
+            O.stats_reset_rays()
+            O.trace(r, 0)
+            st = O.stats()
+            vt[name] = (st["ray_box"] / r.shape[0], st["ray_tri"] / r.shape[0])
+        out["vt"] = vt
+        st = O.stats()
+        out["ref_nodes"] = (st["nodes"], st["leaves"])
+    return out
+
+
+# ------------------------------------------------------------------------------------------------------------------
+def run_reference(args):
+    """The reference's own CPU implementation of the path on the box's host cores (rank 0 only)."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    import miro_driver as md
+    import objio
+    scenes = importlib.import_module("cse168-raytracer_b200.scenes")
+    cores = os.cpu_count() or 1
+    kind = "reference" if os.path.exists(md.REF_SO) else "port"
+    D = md.reference("scalar") if kind == "reference" else md.oracle()
+    O = md.oracle()
+    devnull = os.open(os.devnull, os.O_WRONLY)
+    saved = os.dup(1)
+    os.dup2(devnull, 1)
+    try:
+        scenes.realise(D, SCENE, objio.obj_path)
+        build_s = D.precalc()
+        scenes.realise(O, SCENE, objio.obj_path)   # camera + Ray::diffuse restatement for ray generation (no BVH build)
+        # bounded sample per step: every 4th row of one jittered sample of the frame + its bounce rays
+        rows = np.arange(0, HEIGHT, 4)
+        rng = np.random.default_rng(SEED)
+        import ctypes
+        times, nrays = [], []
+        for it in range(args.warmup + args.steps):
+            jit = rng.random((WIDTH * HEIGHT, 2), dtype=np.float32)
+            full = np.zeros((WIDTH * HEIGHT, 8), np.float32)
+            O.lib.orc_eye_rays_jitter(WIDTH, HEIGHT, md._fp(jit), md._fp(full))
+            rays = np.ascontiguousarray(full.reshape(HEIGHT, WIDTH, 8)[rows].reshape(-1, 8))
+            s_primary, _ = D.trace_time(rays, 0)          # timed: Scene::trace over all host threads, no output traffic
+            t, ids, P, N = D.trace(rays, 0)               # untimed: the hits, to generate the bounce rays from
+            u = rng.random((rays.shape[0], 2), dtype=np.float32)
+            br = np.zeros_like(rays)
+            O.lib.orc_diffuse_rays(md._fp(P), md._fp(N), md._fp(ids), md._fp(u), ctypes.c_long(rays.shape[0]), md._fp(br))
+            br = np.ascontiguousarray(br[ids >= 0])
+            s_bounce, _ = D.trace_time(br, 0)
+            if it >= args.warmup:
+                times.append(s_primary + s_bounce); nrays.append(rays.shape[0] + br.shape[0])
+    finally:
+        os.dup2(saved, 1)
+        os.close(devnull)
+    total_t, total_r = float(np.sum(times)), int(np.sum(nrays))
+    value = total_r / total_t / 1e6
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": "Mrays/s", "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": 1e3 * total_t / max(1, args.steps), "higher_is_better": True, "scaling": "strong",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": f"{SCENE} ({WIDTH}x{HEIGHT} camera of makeBunny20Scene; stand-in for the missing sponza.obj): per step every 4th row of one "
+                               "jittered sample + one Ray::diffuse bounce ray per hit, closest-hit through Scene::trace",
+                   "rays_per_step": total_r // max(1, args.steps), "threads": cores, "bvh_build_s": build_s},
+        "cpu_baseline": {"value": value, "unit": "Mrays/s", "cores": cores, "kind": kind,
+                         "sample": f"{total_r // max(1, args.steps)} rays per step (270 of 1080 rows of one sample + bounce), OpenMP over all host threads"},
+        "e2e": {"value": value, "unit": "Mrays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------------------------------
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device -- the engine has no CPU fallback (use --impl reference for the CPU arm)")
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    pkg = importlib.import_module("cse168-raytracer_b200")
+    scenes = importlib.import_module("cse168-raytracer_b200.scenes")
+    layout = {"bvh2": pkg.LAYOUT_BVH2, "cwbvh8": pkg.LAYOUT_CWBVH8}[args.layout]
+    H = build_host_scene(pkg, scenes, layout)       # BVH replicated on every GPU
+    S = H.scene()
+    S.set_kernel_variant(args.variant)
+    cam = H.camera()
+    info = S.info
+    rows = (0, HEIGHT, world, rank)
+    nrows = len(range(rank, HEIGHT, world))
+    npix = nrows * WIDTH
+    n = npix * SPP
+    dev = torch.device("cuda", local)
+    d_rays = torch.empty((n, 8), dtype=torch.float32, device=dev)
+    d_hits = torch.empty((n, 4), dtype=torch.float32, device=dev)
+    d_b = torch.empty((n, 8), dtype=torch.float32, device=dev)
+    d_h2 = torch.empty((n, 4), dtype=torch.float32, device=dev)
+    d_live = torch.zeros(1, dtype=torch.int64, device=dev)
+    index_base = (rank * 0x01000000) & 0xFFFFFFFF
+
+    def step(it, ev=None):
+        S.generate_primary(cam, WIDTH, HEIGHT, d_rays, rows=rows, jitter=1, seed=SEED, sample=it * SPP, samples=SPP)
+        if ev: ev[0].record()
+        S.intersect_device(d_rays, d_hits)
+        if ev: ev[1].record()
+        S.generate_bounce(d_rays, d_hits, d_b, seed=SEED, sample=it, index_base=index_base, d_live_count=d_live)
+        if ev: ev[2].record()
+        S.intersect_device(d_b, d_h2)
+        if ev: ev[3].record()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for it in range(args.warmup):
+        step(it)
+    barrier()
+    d_live.zero_()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    evs = [[torch.cuda.Event(enable_timing=True) for _ in range(4)] for _ in range(args.steps)]
+    t_begin, t_end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    t_begin.record()
+    for it in range(args.steps):
+        step(args.warmup + it, evs[it])
+    t_end.record()
+    barrier()
+    ms_local = t_begin.elapsed_time(t_end)
+    # keep the GPU busy a little longer so the clock sampler sees the load even for short runs
+    clocks = None
+    live_local = int(d_live.item())
+    prim_ms = float(np.mean([e[0].elapsed_time(e[1]) for e in evs]))
+    bounce_ms = float(np.mean([e[2].elapsed_time(e[3]) for e in evs]))
+
+    # ---- e2e: Scene::raytraceImage-shaped call, host framebuffer out, every step --------------------------------
+    e2e_steps = args.steps
+    p = S.render_params(WIDTH, HEIGHT, spp=SPP, jitter=1, max_depth=10, mode=pkg.RENDER_DIFFUSE_BOUNCE, seed=SEED, tonemap=0,
+                        rows=rows, shadows=0)
+    host_fb = torch.empty((HEIGHT, WIDTH, 3), dtype=torch.float32).pin_memory()
+    e2e_rays = 0
+    if world == 1:
+        def e2e_step(it):
+            p.seed = SEED + it
+            S.render(cam, p, out=host_fb.numpy())
+            return S.last_call_stats()[0]
+    else:
+        d_rgb = torch.zeros((HEIGHT, WIDTH, 3), dtype=torch.float32, device=dev)
+        nrows_max = (HEIGHT + world - 1) // world
+        d_local = torch.empty((nrows_max, WIDTH, 3), dtype=torch.float32, device=dev)
+        d_all = torch.empty((world, nrows_max, WIDTH, 3), dtype=torch.float32, device=dev)
+
+        def e2e_step(it):
+            p.seed = SEED + it
+            S.render_device(cam, p, d_rgb)
+            d_local.zero_()
+            d_local[:nrows].copy_(d_rgb[rank::world])
+            dist.all_gather_into_tensor(d_all, d_local)     # framebuffer gather over NVLink
+            if rank == 0:
+                for r in range(world):
+                    k = len(range(r, HEIGHT, world))
+                    d_rgb[r::world].copy_(d_all[r, :k])
+                host_fb.copy_(d_rgb, non_blocking=True)
+            torch.cuda.synchronize()
+            return S.last_call_stats()[0]
+    for it in range(min(3, args.warmup)):
+        e2e_step(it)
+    barrier()
+    t0 = time.perf_counter()
+    for it in range(e2e_steps):
+        e2e_rays += e2e_step(100 + it)
+    barrier()
+    e2e_s_local = time.perf_counter() - t0
+    if rank == 0:
+        clocks = sampler.stop()
+
+    # ---- aggregate over ranks: max time, summed rays ------------------------------------------------------------
+    stats = torch.tensor([ms_local, e2e_s_local, prim_ms, bounce_ms], dtype=torch.float64, device=dev)
+    sums = torch.tensor([float(n * args.steps), float(live_local), float(e2e_rays)], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(stats, op=dist.ReduceOp.MAX)
+        dist.all_reduce(sums, op=dist.ReduceOp.SUM)
+    ms_total, e2e_s, prim_ms, bounce_ms = [float(x) for x in stats.tolist()]
+    prim_total, live_total, e2e_total = [float(x) for x in sums.tolist()]
+    rays_total = prim_total + live_total
+    value = rays_total / (ms_total * 1e-3) / 1e6
+    e2e_value = e2e_total / e2e_s / 1e6
+
+    line = None
+    if rank == 0:
+        peak, peak_src = peaks()
+        cpu, vt, ref_nodes = None, dict(FALLBACK_VT), None
+        vt_src = "SURVEY 8d figures (oracle not run)"
+        if world == 1 and not args.no_cpu:
+            # one sample's worth of the rays the GPU itself generated
+            rp = d_rays[:npix].cpu().numpy()
+            rb = d_b[:npix].cpu().numpy()
+            rb = np.ascontiguousarray(rb[rb[:, 7] >= rb[:, 3]])
+            try:
+                leg = cpu_leg(rp, rb)
+                cpu, vt, ref_nodes = leg["cpu"], leg.get("vt", vt), leg.get("ref_nodes")
+                vt_src = "scalar reference counters (oracle restatement, bit-exact with -DSTATS) on every 16th of these rays"
+            except Exception as exc:   # the CPU leg is a reported baseline, never a reason to lose the GPU number
+                cpu = {"error": repr(exc)}
+        bpr_p, bpr_b = bytes_per_ray(*vt["primary"]), bytes_per_ray(*vt["bounce"])
+        live_per_launch = live_total / max(1, args.steps) / world
+        achieved = live_per_launch * bpr_b / (bounce_ms * 1e-3) / 1e9
+        traffic = None
+        try:
+            with open(os.path.join(ROOT, "profiles", "ncu_summary.json")) as f:
+                traffic = json.load(f).get("bounce_trace_dram_bytes_per_launch")
+        except Exception:
+            pass
+        line = {
+            "metric": METRIC, "value": value, "unit": "Mrays/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic",
+            "config": {
+                "workload": f"{SCENE}: reference makeBunny20Scene geometry ({info.num_triangles} triangles) and camera, declared stand-in for BASELINE config 3's "
+                            f"sponza.obj (absent from the reference tree); {WIDTH}x{HEIGHT}, {SPP} jittered samples per step, one Ray::diffuse bounce ray per hit",
+                "rays_per_step": rays_total / args.steps, "primary_rays_per_step": prim_total / args.steps, "bounce_rays_per_step": live_total / args.steps,
+                "layout": args.layout, "kernel_variant": args.variant, "nodes": info.num_nodes, "node_mb": info.node_bytes / 1e6,
+                "triangle_mb": info.triangle_bytes / 1e6, "build_s": info.build_seconds + info.flatten_seconds,
+                "sharding": f"image rows interleaved over {world} rank(s), BVH replicated",
+                "l2": "inputs larger than L2: each step rewrites and rereads %.0f MB of ray/hit buffers per GPU, evicting the scene between its kernels" % (n * 96 / 1e6),
+                "primary_mrays_s": (prim_total / args.steps / world) / (prim_ms * 1e-3) / 1e6 * world,
+                "bounce_mrays_s": (live_total / args.steps / world) / (bounce_ms * 1e-3) / 1e6 * world,
+                "bytes_per_ray": {"primary": bpr_p, "bounce": bpr_b, "V_T": vt, "source": vt_src},
+                "reference_bvh_nodes": ref_nodes,
+            },
+            "roofline": {"bound": "hbm", "kernel": "k_trace_persistent (bounce rays, closest hit)", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                         "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
+                         "note": "algorithmic bytes = live bounce rays per launch x (32V + 36T + 48) B; the scene is mostly L2-resident, so DRAM traffic is far below this"},
+            "cpu_baseline": cpu,
+            "e2e": {"value": e2e_value, "unit": "Mrays/s", "h2d_bytes_per_step": 40 + 17 * 4, "d2h_bytes_per_step": WIDTH * HEIGHT * 12,
+                    "call": "mirogpu_render (Scene::raytraceImage), diffuse-bounce mode, host framebuffer" + ("" if world == 1 else " + NCCL all_gather of row shards")},
+            "gpu_launches": int(4 * args.steps * world),
+            "clocks": clocks,
+        }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    return line
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--layout", default="bvh2", choices=["bvh2", "cwbvh8"])
+    ap.add_argument("--variant", type=int, default=0)
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg (faster iteration)")
+    args = ap.parse_args()
+    if args.warmup < 3:
+        args.warmup = 3
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        world = int(os.environ.get("WORLD_SIZE", "1"))
+        if args.gpus > 1 and world == 1:
+            # convenience: re-launch under torchrun when called as plain `python bench.py --gpus N`
+            cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={args.gpus}", "--master-addr", "127.0.0.1",
+                   "--master-port", "29541", os.path.abspath(__file__)] + sys.argv[1:]
+            raise SystemExit(subprocess.call(cmd))
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

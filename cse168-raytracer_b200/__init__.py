@@ -246,15 +246,17 @@ class MiroScene:
         _check(lib.mirogpu_resolve_hits_device(self._h, _ptr(d_hits), ctypes.c_size_t(d_hits.shape[0]), _ptr(d_P), _ptr(d_N), _ptr(d_mat), _stream()))
 
     # ---- device ray generation ----------------------------------------------------------------------
-    def generate_primary(self, cam, width, height, d_rays, row_begin=0, row_end=None, jitter=0, seed=168, sample=0):
-        row_end = height if row_end is None else row_end
-        _check(lib.mirogpu_generate_primary_device(self._h, ctypes.byref(cam), int(width), int(height), int(row_begin), int(row_end),
-                                                   int(jitter), ctypes.c_uint32(seed), ctypes.c_uint32(sample), _ptr(d_rays), _stream()))
+    def generate_primary(self, cam, width, height, d_rays, rows=None, jitter=0, seed=168, sample=0, samples=1):
+        """rows = (row_begin, row_end, row_stride, row_phase); output is sample-major then row-major."""
+        rb, re_, rs, rp = rows if rows is not None else (0, height, 1, 0)
+        _check(lib.mirogpu_generate_primary_device(self._h, ctypes.byref(cam), int(width), int(height), int(rb), int(re_), int(rs), int(rp),
+                                                   int(jitter), ctypes.c_uint32(seed), ctypes.c_uint32(sample), ctypes.c_uint32(samples),
+                                                   _ptr(d_rays), _stream()))
 
-    def generate_bounce(self, d_rays, d_hits, d_out, seed=168, sample=0, n=None):
+    def generate_bounce(self, d_rays, d_hits, d_out, seed=168, sample=0, n=None, index_base=0, d_live_count=None):
         n = d_rays.shape[0] if n is None else n
         _check(lib.mirogpu_generate_bounce_device(self._h, _ptr(d_rays), _ptr(d_hits), ctypes.c_size_t(n), ctypes.c_uint32(seed),
-                                                  ctypes.c_uint32(sample), _ptr(d_out), _stream()))
+                                                  ctypes.c_uint32(sample), ctypes.c_uint32(index_base), _ptr(d_out), _ptr(d_live_count), _stream()))
 
     # ---- Scene::raytraceImage ------------------------------------------------------------------------
     def render_params(self, width, height, spp=1, jitter=0, max_depth=10, mode=RENDER_WHITTED, seed=168, tonemap=0,

@@ -106,15 +106,18 @@ __global__ void __launch_bounds__(128) k_trace_persistent(DeviceScene s, const m
 }
 
 // ---- Camera::eyeRay, Camera.cpp:127-160 (no DOF).  Same operand order, no FMA: bit-exact with the oracle. ----
-__global__ void __launch_bounds__(256) k_gen_primary(CameraBasis cb, int width, int height, int row_begin, int row_end,
-                                                      int jitter, uint32_t seed, uint32_t sample, mirogpu_ray* __restrict__ rays)
+__global__ void __launch_bounds__(256) k_gen_primary(CameraBasis cb, int width, int height, int first_row, int row_stride,
+                                                      int nrows_local, int jitter, uint32_t seed, uint32_t sample_begin,
+                                                      uint32_t sample_count, mirogpu_ray* __restrict__ rays)
 {
-    const size_t npix = (size_t)(row_end - row_begin) * width;
+    const size_t npix = (size_t)nrows_local * width;
     const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= npix) return;
-    const int x = (int)(i % width), y = row_begin + (int)(i / width);
+    if (i >= npix * sample_count) return;
+    const uint32_t s = (uint32_t)(i / npix);
+    const size_t lp = i - (size_t)s * npix;
+    const int x = (int)(lp % width), y = first_row + (int)(lp / width) * row_stride;
     float dx = 0.5f, dy = 0.5f;
-    if (jitter) uniform2(seed, (uint32_t)((size_t)y * width + x), sample, RNG_DIM_PIXEL, dx, dy);
+    if (jitter) uniform2(seed, (uint32_t)((size_t)y * width + x), sample_begin + s, RNG_DIM_PIXEL, dx, dy);
     const float U = xadd(cb.left, xmul(xsub(cb.right, cb.left), xdiv(xadd((float)x, dx), (float)width)));
     const float V = xadd(cb.bottom, xmul(xsub(cb.top, cb.bottom), xdiv(xadd((float)y, dy), (float)height)));
     float d[3];
@@ -199,19 +202,24 @@ __device__ __forceinline__ void align_hemisphere(const float v[3], float theta, 
 // Ray::diffuse, Ray.h:109-122, with (u1,u2) from the counter RNG in place of rand().
 __global__ void __launch_bounds__(256) k_gen_bounce(DeviceScene s, const mirogpu_ray* __restrict__ rays,
                                                      const mirogpu_hit* __restrict__ hits, size_t n, uint32_t seed, uint32_t sample,
-                                                     mirogpu_ray* __restrict__ out)
+                                                     uint32_t index_base, mirogpu_ray* __restrict__ out, unsigned long long* live_count)
 {
     const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    const float4 hv = __ldg(reinterpret_cast<const float4*>(hits + i));
+    float4 hv = make_float4(0.f, __uint_as_float(MIROGPU_MISS), 0.f, 0.f);
+    if (i < n) hv = __ldg(reinterpret_cast<const float4*>(hits + i));
     mirogpu_hit h; h.t = hv.x; h.prim_id = __float_as_uint(hv.y); h.beta = hv.z; h.gamma = hv.w;
+    if (live_count) {   // one atomic per warp
+        const unsigned live = __ballot_sync(0xffffffffu, h.prim_id != MIROGPU_MISS);
+        if ((threadIdx.x & 31) == 0 && live) atomicAdd(live_count, (unsigned long long)__popc(live));
+    }
+    if (i >= n) return;
     float4 a, b;
     if (h.prim_id == MIROGPU_MISS) {
         a = make_float4(0.f, 0.f, 0.f, 0.f); b = make_float4(0.f, 0.f, 1.f, -1.0f);  // tmax < tmin: never hits
     } else {
         const SurfacePoint sp = resolve_hit(s, h);
         float u1, u2;
-        uniform2(seed, (uint32_t)i, sample, RNG_DIM_BOUNCE, u1, u2);
+        uniform2(seed, index_base + (uint32_t)i, sample, RNG_DIM_BOUNCE, u1, u2);
         const float phi = asinf(sqrtf(u1));
         const float theta = xmul(xmul(2.0f, MIRO_PI), u2);
         float d[3];

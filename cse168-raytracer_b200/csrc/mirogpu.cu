@@ -2,6 +2,7 @@
 // batched intersection, device-side ray generation, render and photon gather entry points.
 // No CPU fallback: every compute entry point needs a CUDA device and says so loudly when there is none.
 #include <algorithm>
+#include <atomic>
 #include <chrono>
 #include <cmath>
 #include <cstdio>
@@ -61,13 +62,13 @@ struct mirogpu_scene {
     mirogpu_light* d_lights = nullptr;
     uint32_t nlights = 0;
     unsigned long long* d_ticket = nullptr;  // persistent-kernel ticket counters (ring of 64)
-    uint32_t ticket_slot = 0;
+    std::atomic<uint32_t> ticket_slot{0};
     mirogpu_scene_info info{};
     std::vector<uint8_t> h_nodes;     // host copies kept for mirogpu_debug_copy_*
     std::vector<TriRecord> h_tris;
     PhotonMapDevice pm[2];
     RenderScratch scratch;
-    std::mutex mtx;                   // guards scratch, ticket_slot and the last-call stats
+    std::mutex mtx;                   // guards scratch and the last-call stats
     uint64_t last_rays = 0, last_launches = 0;
 };
 
@@ -82,11 +83,7 @@ cudaError_t launch_trace(mirogpu_scene* h, const mirogpu_ray* d_rays, size_t n, 
         k_trace_simple<LAYOUT, ANY, false><<<grid, 128, 0, st>>>(h->ds, d_rays, n, d_hits, nullptr);
         return cudaGetLastError();
     }
-    unsigned long long* ticket;
-    {
-        std::lock_guard<std::mutex> lk(h->mtx);
-        ticket = h->d_ticket + (h->ticket_slot++ & 63u);
-    }
+    unsigned long long* ticket = h->d_ticket + (h->ticket_slot.fetch_add(1) & 63u);
     cudaError_t e = cudaMemsetAsync(ticket, 0, sizeof(unsigned long long), st);
     if (e != cudaSuccess) return e;
     int occ = 0;
@@ -134,6 +131,7 @@ void camera_basis(const mirogpu_camera& c, int W, int H, CameraBasis& b)
 }  // namespace
 
 // RenderScratch / render + photon implementations need the pieces above.
+#include "photon_impl.cuh"
 #include "render_impl.cuh"
 
 extern "C" {
@@ -425,30 +423,35 @@ int mirogpu_resolve_hits_device(mirogpu_handle h, const mirogpu_hit* d_hits, siz
 }
 
 int mirogpu_generate_primary_device(mirogpu_handle h, const mirogpu_camera* cam, int width, int height, int row_begin,
-                                    int row_end, int jitter, uint32_t seed, uint32_t sample, mirogpu_ray* d_rays,
-                                    void* cuda_stream)
+                                    int row_end, int row_stride, int row_phase, int jitter, uint32_t seed, uint32_t sample_begin,
+                                    uint32_t sample_count, mirogpu_ray* d_rays, void* cuda_stream)
 {
     if (!h || !cam || !d_rays) return fail(MIROGPU_ERR_INVALID_ARG, "NULL argument");
-    if (width <= 0 || height <= 0 || row_begin < 0 || row_end > height || row_begin > row_end)
+    if (width <= 0 || height <= 0 || row_begin < 0 || row_end > height || row_begin > row_end || row_stride < 1 || row_phase < 0 ||
+        row_phase >= row_stride)
         return fail(MIROGPU_ERR_INVALID_ARG, "bad image or row range");
-    const size_t npix = (size_t)(row_end - row_begin) * width;
-    if (npix == 0) return MIROGPU_OK;
+    const int first_row = row_begin + row_phase;
+    const int nrows = first_row < row_end ? (row_end - first_row + row_stride - 1) / row_stride : 0;
+    const size_t total = (size_t)nrows * width * sample_count;
+    if (total == 0) return MIROGPU_OK;
     CUDA_TRY(cudaSetDevice(h->device));
     CameraBasis cb;
     camera_basis(*cam, width, height, cb);
-    k_gen_primary<<<(unsigned)((npix + 255) / 256), 256, 0, (cudaStream_t)cuda_stream>>>(cb, width, height, row_begin, row_end,
-                                                                                           jitter, seed, sample, d_rays);
+    k_gen_primary<<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)cuda_stream>>>(cb, width, height, first_row, row_stride, nrows,
+                                                                                            jitter, seed, sample_begin, sample_count, d_rays);
     CUDA_TRY(cudaGetLastError());
     return MIROGPU_OK;
 }
 
 int mirogpu_generate_bounce_device(mirogpu_handle h, const mirogpu_ray* d_rays, const mirogpu_hit* d_hits, size_t n,
-                                   uint32_t seed, uint32_t sample, mirogpu_ray* d_out, void* cuda_stream)
+                                   uint32_t seed, uint32_t sample, uint32_t index_base, mirogpu_ray* d_out,
+                                   unsigned long long* d_live_count, void* cuda_stream)
 {
     if (!h || (n && (!d_rays || !d_hits || !d_out))) return fail(MIROGPU_ERR_INVALID_ARG, "NULL argument");
     if (n == 0) return MIROGPU_OK;
     CUDA_TRY(cudaSetDevice(h->device));
-    k_gen_bounce<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)cuda_stream>>>(h->ds, d_rays, d_hits, n, seed, sample, d_out);
+    k_gen_bounce<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)cuda_stream>>>(h->ds, d_rays, d_hits, n, seed, sample, index_base,
+                                                                                       d_out, d_live_count);
     CUDA_TRY(cudaGetLastError());
     return MIROGPU_OK;
 }

@@ -1,20 +1,468 @@
-// render_impl.cuh -- included by mirogpu.cu after mirogpu_scene is complete.  (Filled in below.)
+// render_impl.cuh -- Scene::raytraceImage on the device as a wavefront (included by mirogpu.cu once
+// mirogpu_scene is complete).
+//
+// The reference walks one pixel at a time through a recursive Scene::traceScene (Scene.cpp:270-346).  Here a
+// frame is a sequence of waves over a queue of path items {ray, pixel, RGB weight, depth left}:
+//     trace (closest hit)  ->  k_shade  ->  trace shadow rays  ->  k_shadow_accumulate  ->  next wave
+// k_shade evaluates Phong::shade's light loop (Phong.cpp:61-158) up to the shadow test, appends the
+// reflection / Fresnel / refraction / diffuse-bounce rays with their weights to the next queue, and the
+// shadow pass applies the occlusion rule of Phong.cpp:97-114 (an occluder blocks the light unless it is
+// refractive and faces the light, in which case the diffuse term is scaled by N_occ . l).
+// Radiance is accumulated per pixel with float atomics, so sums differ from the reference's recursion order
+// in the last bits; images are compared with a tolerance (tests/test_gpu_render.py).
 #ifndef MIROGPU_RENDER_IMPL_CUH
 #define MIROGPU_RENDER_IMPL_CUH
+
 namespace {
-int render_device(mirogpu_scene*, const mirogpu_camera&, const mirogpu_render_params&, float*, cudaStream_t, std::string& err)
+
+using namespace mirogpu;
+
+#define MIRO_MAX_LIGHTS 4
+
+struct WaveParams {
+    DeviceScene ds;
+    const mirogpu_material* mats;
+    const mirogpu_light* lights;
+    uint32_t nlights;
+    int mode, shadows, max_depth, use_pm;
+    float bg[3];
+    uint32_t seed, sample;
+    uint32_t cap;          // queue capacity
+    int width, first_row, row_stride;   // local pixel index -> frame pixel (for shard-independent random numbers)
+};
+
+// queue layout (SoA)
+struct Queue {
+    mirogpu_ray* rays;
+    mirogpu_hit* hits;
+    uint32_t* pix;         // local pixel index
+    float4* weight;        // rgb weight, w = depth left (as float)
+};
+
+__global__ void __launch_bounds__(256) k_render_primary(CameraBasis cb, int width, int height, int row_begin, int row_stride,
+                                                         int nrows_local, int jitter, uint32_t seed, uint32_t sample, int max_depth, Queue q)
 {
-    err = "mirogpu_render: not implemented yet";
-    return MIROGPU_ERR_UNSUPPORTED;
+    const size_t npix = (size_t)nrows_local * width;
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= npix) return;
+    const int x = (int)(i % width), y = row_begin + (int)(i / width) * row_stride;
+    float dx = 0.5f, dy = 0.5f;
+    if (jitter) uniform2(seed, (uint32_t)((size_t)y * width + x), sample, RNG_DIM_PIXEL, dx, dy);
+    const float U = xadd(cb.left, xmul(xsub(cb.right, cb.left), xdiv(xadd((float)x, dx), (float)width)));
+    const float V = xadd(cb.bottom, xmul(xsub(cb.top, cb.bottom), xdiv(xadd((float)y, dy), (float)height)));
+    float d[3];
+#pragma unroll
+    for (int k = 0; k < 3; ++k) d[k] = xsub(xadd(xmul(cb.u[k], U), xmul(cb.v[k], V)), cb.w[k]);
+    const float inv = xdiv(1.0f, xsqrt(xdot(d[0], d[1], d[2], d[0], d[1], d[2])));
+    float4* o = reinterpret_cast<float4*>(q.rays + i);
+    o[0] = make_float4(cb.eye[0], cb.eye[1], cb.eye[2], 0.0f);
+    o[1] = make_float4(xmul(d[0], inv), xmul(d[1], inv), xmul(d[2], inv), MIROGPU_TMAX);
+    q.pix[i] = (uint32_t)i;
+    q.weight[i] = make_float4(1.f, 1.f, 1.f, (float)max_depth);
 }
-int render_host(mirogpu_scene*, const mirogpu_camera&, const mirogpu_render_params&, float*, std::string& err)
+
+__device__ __forceinline__ float dot3(const float a[3], const float b[3]) { return a[0] * b[0] + a[1] * b[1] + a[2] * b[2]; }
+
+__device__ __forceinline__ void push_item(const WaveParams& p, Queue& next, uint32_t* next_count, uint32_t* dropped, const float o[3],
+                                          const float d[3], uint32_t pixel, float wr, float wg, float wb, float depth)
 {
-    err = "mirogpu_render: not implemented yet";
-    return MIROGPU_ERR_UNSUPPORTED;
+    if (!(wr > 0.f || wg > 0.f || wb > 0.f)) return;
+    const uint32_t slot = atomicAdd(next_count, 1u);
+    if (slot >= p.cap) { atomicAdd(dropped, 1u); return; }
+    float4* r = reinterpret_cast<float4*>(next.rays + slot);
+    r[0] = make_float4(o[0], o[1], o[2], 0.0f);
+    r[1] = make_float4(d[0], d[1], d[2], MIROGPU_TMAX);
+    next.pix[slot] = pixel;
+    next.weight[slot] = make_float4(wr, wg, wb, depth);
 }
+
+// One wave of Scene::traceScene bodies.  shadow_* arrays have nlights slots per item.
+__global__ void __launch_bounds__(128) k_shade(WaveParams p, Queue cur, uint32_t n, Queue next, uint32_t* next_count, uint32_t* dropped,
+                                               mirogpu_ray* shadow_rays, float4* shadow_cd, float4* shadow_ch, float* accum,
+                                               float* gather_pos, float* gather_nrm, float4* gather_w)
+{
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const float4 hv = __ldg(reinterpret_cast<const float4*>(cur.hits + i));
+    const float4 w = cur.weight[i];
+    const uint32_t pixel = cur.pix[i];
+    const mirogpu_ray ray = load_ray(cur.rays, i);
+    if (gather_w) gather_w[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (p.shadows)
+        for (uint32_t li = 0; li < p.nlights; ++li) shadow_rays[(size_t)i * p.nlights + li].tmax = -1.0f;   // inactive unless set below
+    if (__float_as_uint(hv.y) == MIROGPU_MISS) {
+        if (ray.tmax < ray.tmin) return;   // dead item
+        // Scene.cpp:338-342: environment / background colour
+        atomicAdd(accum + 3 * (size_t)pixel + 0, w.x * p.bg[0]);
+        atomicAdd(accum + 3 * (size_t)pixel + 1, w.y * p.bg[1]);
+        atomicAdd(accum + 3 * (size_t)pixel + 2, w.z * p.bg[2]);
+        return;
+    }
+    mirogpu_hit h; h.t = hv.x; h.prim_id = __float_as_uint(hv.y); h.beta = hv.z; h.gamma = hv.w;
+    const SurfacePoint sp = resolve_hit(p.ds, h);
+    const mirogpu_material m = p.mats[sp.material];
+    const float rd[3] = {ray.dx, ray.dy, ray.dz};
+    float direct[3] = {0.f, 0.f, 0.f};
+
+    // ---- Phong::shade light loop -------------------------------------------------------------------
+    for (uint32_t li = 0; li < p.nlights; ++li) {
+        const mirogpu_light L = p.lights[li];
+        float l[3];
+        if (L.kind == 1) { l[0] = -L.normal[0]; l[1] = -L.normal[1]; l[2] = -L.normal[2]; }
+        else { l[0] = L.position[0] - sp.P[0]; l[1] = L.position[1] - sp.P[1]; l[2] = L.position[2] - sp.P[2]; }
+        float falloff = dot3(l, l);
+        const float dist = sqrtf(falloff);
+        const float invd = 1.0f / dist;
+        l[0] *= invd; l[1] *= invd; l[2] *= invd;
+        float nDotL;
+        if (L.kind == 1) {
+            const float nl[3] = {-L.normal[0], -L.normal[1], -L.normal[2]};
+            nDotL = dot3(sp.N, nl);
+            const float lp[3] = {L.position[0] - sp.P[0], L.position[1] - sp.P[1], L.position[2] - sp.P[2]};
+            const float t = dot3(L.normal, lp) / -1.0f;
+            const float q[3] = {sp.P[0] - t * L.normal[0] - L.position[0], sp.P[1] - t * L.normal[1] - L.position[1], sp.P[2] - t * L.normal[2] - L.position[2]};
+            if (dot3(q, q) > L.radius * L.radius) continue;
+            falloff = 1.0f / MIRO_PI;
+        } else {
+            nDotL = dot3(sp.N, l);
+            falloff = 1.0f / (falloff * 4.0f * MIRO_PI * MIRO_PI);
+        }
+        const float dterm = fmaxf(0.0f, nDotL * falloff * L.wattage);
+        // diffuseColor * m_diffuse: Phong::diffuse2D returns m_diffuse, so kd enters squared (Phong.cpp:146, Phong.h:20)
+        float cd[3] = {L.color[0] * dterm * m.kd[0] * m.kd[0], L.color[1] * dterm * m.kd[1] * m.kd[1], L.color[2] * dterm * m.kd[2] * m.kd[2]};
+        float hl = 0.f;
+        if (m.shininess < INFINITY) {
+            const float ldn = 2.0f * dot3(l, sp.N);
+            const float r[3] = {-l[0] + ldn * sp.N[0], -l[1] + ldn * sp.N[1], -l[2] + ldn * sp.N[2]};
+            const float e[3] = {-rd[0], -rd[1], -rd[2]};
+            const float c = fmaxf(0.0f, fminf(1.f, dot3(e, r)));
+            hl = fmaxf(0.0f, powf(c, 500.0f) * falloff * L.wattage);   // exponent fixed at 500 (Phong.cpp:152)
+        }
+        if (p.shadows) {
+            if (cd[0] > 0.f || cd[1] > 0.f || cd[2] > 0.f || hl > 0.f) {
+                const size_t s = (size_t)i * p.nlights + li;
+                float4* r = reinterpret_cast<float4*>(shadow_rays + s);
+                r[0] = make_float4(sp.P[0] + l[0] * MIRO_EPS, sp.P[1] + l[1] * MIRO_EPS, sp.P[2] + l[2] * MIRO_EPS, 0.0f);
+                r[1] = make_float4(l[0], l[1], l[2], dist);
+                shadow_cd[s] = make_float4(w.x * cd[0], w.y * cd[1], w.z * cd[2], __uint_as_float(pixel));
+                shadow_ch[s] = make_float4(w.x * hl, w.y * hl, w.z * hl, 0.f);
+            }
+        } else {
+            direct[0] += cd[0] + hl; direct[1] += cd[1] + hl; direct[2] += cd[2] + hl;
+        }
+    }
+    if (!p.shadows && (direct[0] != 0.f || direct[1] != 0.f || direct[2] != 0.f)) {
+        atomicAdd(accum + 3 * (size_t)pixel + 0, w.x * direct[0]);
+        atomicAdd(accum + 3 * (size_t)pixel + 1, w.y * direct[1]);
+        atomicAdd(accum + 3 * (size_t)pixel + 2, w.z * direct[2]);
+    }
+    const bool diffuse = m.kd[0] > 0.f || m.kd[1] > 0.f || m.kd[2] > 0.f;
+    // photon-map irradiance at diffuse hits (Scene.cpp:286-299): queued for the gather kernel
+    if (p.use_pm && diffuse && gather_w) {
+        gather_pos[3 * (size_t)i] = sp.P[0]; gather_pos[3 * (size_t)i + 1] = sp.P[1]; gather_pos[3 * (size_t)i + 2] = sp.P[2];
+        gather_nrm[3 * (size_t)i] = sp.N[0]; gather_nrm[3 * (size_t)i + 1] = sp.N[1]; gather_nrm[3 * (size_t)i + 2] = sp.N[2];
+        gather_w[i] = make_float4(w.x, w.y, w.z, 1.f);
+    }
+    // ---- secondary rays -------------------------------------------------------------------------------
+    const float depth_left = w.w - 1.0f;          // --depth (Scene.cpp:282)
+    if (depth_left < 0.f) return;
+    if (p.mode == MIROGPU_RENDER_DIFFUSE_BOUNCE) {
+        if (diffuse && w.w == (float)p.max_depth) {   // one cosine-weighted bounce from the first hit only
+            float u1, u2;
+            const uint32_t frame_pixel = (uint32_t)(p.first_row + (int)(pixel / (uint32_t)p.width) * p.row_stride) * (uint32_t)p.width + pixel % (uint32_t)p.width;
+            uniform2(p.seed, frame_pixel, p.sample, RNG_DIM_BOUNCE, u1, u2);
+            float d[3];
+            align_hemisphere(sp.N, xmul(xmul(2.0f, MIRO_PI), u2), asinf(sqrtf(u1)), d);
+            const float o[3] = {sp.P[0] + d[0] * MIRO_EPS, sp.P[1] + d[1] * MIRO_EPS, sp.P[2] + d[2] * MIRO_EPS};
+            push_item(p, next, next_count, dropped, o, d, pixel, w.x * m.kd[0], w.y * m.kd[1], w.z * m.kd[2], 0.0f);
+        }
+        return;
+    }
+    if (p.mode != MIROGPU_RENDER_WHITTED) return;
+    const bool reflective = m.ks[0] > 0.f || m.ks[1] > 0.f || m.ks[2] > 0.f;
+    const bool refractive = m.kt[0] > 0.f || m.kt[1] > 0.f || m.kt[2] > 0.f;
+    if (!reflective && !refractive) return;
+    // Ray::reflect (Ray.h:160-163)
+    const float dn = dot3(sp.N, rd);
+    float dr[3] = {rd[0] - 2.f * dn * sp.N[0], rd[1] - 2.f * dn * sp.N[1], rd[2] - 2.f * dn * sp.N[2]};
+    {
+        const float inv = 1.0f / sqrtf(dot3(dr, dr));
+        dr[0] *= inv; dr[1] *= inv; dr[2] *= inv;
+    }
+    const float orr[3] = {sp.P[0] + dr[0] * MIRO_EPS, sp.P[1] + dr[1] * MIRO_EPS, sp.P[2] + dr[2] * MIRO_EPS};
+    if (reflective) push_item(p, next, next_count, dropped, orr, dr, pixel, w.x * m.ks[0], w.y * m.ks[1], w.z * m.ks[2], depth_left);
+    if (refractive) {
+        // Fresnel coefficient (Ray.h:168-200) and Snell refraction with TIR fallback (Ray.h:202-243)
+        float n1, n2, n[3];
+        if (dn < 0.f) { n1 = 1.0f; n2 = m.refract_index; n[0] = sp.N[0]; n[1] = sp.N[1]; n[2] = sp.N[2]; }
+        else { n1 = m.refract_index; n2 = 1.0f; n[0] = -sp.N[0]; n[1] = -sp.N[1]; n[2] = -sp.N[2]; }
+        const float nrd[3] = {-rd[0], -rd[1], -rd[2]};
+        const float cosT = dot3(nrd, n);
+        const float sinT = sinf(acosf(cosT));
+        const float ps = (n1 / n2) * sinT * ((n1 / n2) * sinT);
+        float Rs;
+        if (ps > 1.f) Rs = 1.f;
+        else {
+            const float sq = sqrtf(1.f - ps);
+            const float q = (n1 * cosT - sq) / (n1 * cosT + sq);
+            Rs = q * q;
+        }
+        if (Rs > 0.01f) push_item(p, next, next_count, dropped, orr, dr, pixel, w.x * m.kt[0] * Rs, w.y * m.kt[1] * Rs, w.z * m.kt[2] * Rs, depth_left);
+        const float ddn = dot3(rd, n);
+        const float energy = 1.f - (n1 * n1 * (1.f - ddn * ddn) / (n2 * n2));
+        const float tw = 1.f - Rs;
+        if (energy < 0.f) {
+            push_item(p, next, next_count, dropped, orr, dr, pixel, w.x * m.kt[0] * tw, w.y * m.kt[1] * tw, w.z * m.kt[2] * tw, depth_left);
+        } else {
+            const float se = sqrtf(energy);
+            float dt[3];   // the refracted direction is NOT normalised in the reference (Ray.h:233)
+#pragma unroll
+            for (int k = 0; k < 3; ++k) dt[k] = n1 * (rd[k] - n[k] * ddn) / n2 - n[k] * se;
+            const float ot[3] = {sp.P[0] + dt[0] * MIRO_EPS, sp.P[1] + dt[1] * MIRO_EPS, sp.P[2] + dt[2] * MIRO_EPS};
+            push_item(p, next, next_count, dropped, ot, dt, pixel, w.x * m.kt[0] * tw, w.y * m.kt[1] * tw, w.z * m.kt[2] * tw, depth_left);
+        }
+    }
+}
+
+// Phong.cpp:97-114 applied to the traced shadow rays.
+__global__ void __launch_bounds__(256) k_shadow_accumulate(WaveParams p, const mirogpu_ray* __restrict__ srays, const mirogpu_hit* __restrict__ shits,
+                                                           const float4* __restrict__ cd, const float4* __restrict__ ch, size_t n, float* accum)
+{
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const mirogpu_ray r = load_ray(srays, i);
+    if (r.tmax < r.tmin) return;   // no shadow ray in this slot
+    const float4 hv = __ldg(reinterpret_cast<const float4*>(shits + i));
+    float intensity = 1.f;
+    if (__float_as_uint(hv.y) != MIROGPU_MISS) {
+        mirogpu_hit h; h.t = hv.x; h.prim_id = __float_as_uint(hv.y); h.beta = hv.z; h.gamma = hv.w;
+        const SurfacePoint sp = resolve_hit(p.ds, h);
+        const mirogpu_material m = p.mats[sp.material];
+        if (!(m.kt[0] > 0.f || m.kt[1] > 0.f || m.kt[2] > 0.f)) return;      // opaque occluder
+        const float l[3] = {r.dx, r.dy, r.dz};
+        intensity = dot3(sp.N, l);
+        if (intensity < 0.f || intensity < MIRO_EPS) return;
+    }
+    const float4 d = cd[i], s = ch[i];
+    const uint32_t pixel = __float_as_uint(d.w);
+    atomicAdd(accum + 3 * (size_t)pixel + 0, d.x * intensity + s.x);
+    atomicAdd(accum + 3 * (size_t)pixel + 1, d.y * intensity + s.y);
+    atomicAdd(accum + 3 * (size_t)pixel + 2, d.z * intensity + s.z);
+}
+
+__global__ void __launch_bounds__(256) k_gather_accumulate(const float4* __restrict__ gw, const uint32_t* __restrict__ pix,
+                                                           const float* __restrict__ irr0, const float* __restrict__ irr1, uint32_t n, float* accum)
+{
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const float4 w = gw[i];
+    if (w.w == 0.f) return;
+    const uint32_t pixel = pix[i];
+    for (int k = 0; k < 3; ++k) {
+        const float e = (irr0 ? irr0[3 * (size_t)i + k] : 0.f) + (irr1 ? irr1[3 * (size_t)i + k] : 0.f);
+        const float wk = k == 0 ? w.x : (k == 1 ? w.y : w.z);
+        atomicAdd(accum + 3 * (size_t)pixel + k, wk * e);
+    }
+}
+
+// accum (local pixels) -> rgb (full-frame layout), divided by the sample count like Scene.cpp:138.
+__global__ void __launch_bounds__(256) k_resolve_frame(const float* __restrict__ accum, int width, int row_begin, int row_stride, int nrows_local,
+                                                        float inv_spp, int spp, float* __restrict__ rgb, float* gmax)
+{
+    const size_t n = (size_t)nrows_local * width * 3;
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    float v = -INFINITY;
+    if (i < n) {
+        const size_t lp = i / 3; const int c = (int)(i % 3);
+        const int x = (int)(lp % width), y = row_begin + (int)(lp / width) * row_stride;
+        float a = accum[i];
+        if (spp > 1) a *= inv_spp;
+        rgb[3 * ((size_t)y * width + x) + c] = a;
+        if (a == a) v = a;
+    }
+    // block max -> global max (for the NaN replacement of the tone map)
+    for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_down_sync(0xffffffffu, v, o));
+    __shared__ float sm[8];
+    if ((threadIdx.x & 31) == 0) sm[threadIdx.x >> 5] = v;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (int k = 1; k < 8; ++k) v = fmaxf(v, sm[k]);
+        // float atomic max by CAS on the bit pattern
+        unsigned int* g = reinterpret_cast<unsigned int*>(gmax);
+        unsigned int old = *g;
+        while (v > __uint_as_float(old)) {
+            const unsigned int assumed = old;
+            old = atomicCAS(g, assumed, __float_as_uint(v));
+            if (old == assumed) break;
+        }
+    }
+}
+
+// Scene.cpp:177-202: NaN -> maxIntensity, then sigmoid(6v - 3).
+__global__ void __launch_bounds__(256) k_tonemap(float* rgb, int width, int row_begin, int row_stride, int nrows_local, const float* gmax)
+{
+    const size_t n = (size_t)nrows_local * width * 3;
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const size_t lp = i / 3; const int c = (int)(i % 3);
+    const int x = (int)(lp % width), y = row_begin + (int)(lp / width) * row_stride;
+    float* q = rgb + 3 * ((size_t)y * width + x) + c;
+    float v = *q;
+    if (v != v) v = *gmax;
+    *q = 1.0f / (1.0f + expf(-(6.0f * v - 3.0f)));
+}
+
+int render_device(mirogpu_scene* h, const mirogpu_camera& cam, const mirogpu_render_params& rp, float* d_rgb, cudaStream_t st, std::string& err)
+{
+#define RT(expr)                                                                     \
+    do {                                                                             \
+        cudaError_t _e = (expr);                                                     \
+        if (_e != cudaSuccess) { err = std::string(#expr) + ": " + cudaGetErrorString(_e); return _e == cudaErrorMemoryAllocation ? MIROGPU_ERR_OOM : MIROGPU_ERR_CUDA; } \
+    } while (0)
+    if (rp.width <= 0 || rp.height <= 0 || rp.spp < 1 || rp.row_stride < 1 || rp.row_phase < 0 || rp.row_phase >= rp.row_stride ||
+        rp.row_begin < 0 || rp.row_end > rp.height || rp.row_begin > rp.row_end) { err = "bad render parameters"; return MIROGPU_ERR_INVALID_ARG; }
+    if (rp.mode != MIROGPU_RENDER_WHITTED && rp.mode != MIROGPU_RENDER_DIFFUSE_BOUNCE && rp.mode != MIROGPU_RENDER_PRIMARY_ONLY) { err = "unknown render mode"; return MIROGPU_ERR_INVALID_ARG; }
+    if (h->nlights > MIRO_MAX_LIGHTS) { err = "too many lights (max 4)"; return MIROGPU_ERR_UNSUPPORTED; }
+    std::lock_guard<std::mutex> lk(h->mtx);   // one render at a time per handle (scratch buffers)
+    const int first_row = rp.row_begin + rp.row_phase;
+    const int nrows = first_row < rp.row_end ? (rp.row_end - first_row + rp.row_stride - 1) / rp.row_stride : 0;
+    const size_t npix = (size_t)nrows * rp.width;
+    uint64_t rays_traced = 0, launches = 0;
+    if (npix == 0) { h->last_rays = 0; h->last_launches = 0; return MIROGPU_OK; }
+    if (npix >= (1ull << 31)) { err = "frame too large"; return MIROGPU_ERR_UNSUPPORTED; }
+
+    // does any material refract?  (shadow rays then need the closest occluder, Phong.cpp:99-113)
+    std::vector<mirogpu_material> hm(h->nmaterials);
+    RT(cudaMemcpyAsync(hm.data(), h->d_materials, hm.size() * sizeof(mirogpu_material), cudaMemcpyDeviceToHost, st));
+    RT(cudaStreamSynchronize(st));
+    bool any_refractive = false, any_specular = false;
+    for (const mirogpu_material& m : hm) {
+        any_refractive |= m.kt[0] > 0.f || m.kt[1] > 0.f || m.kt[2] > 0.f;
+        any_specular |= m.ks[0] > 0.f || m.ks[1] > 0.f || m.ks[2] > 0.f;
+    }
+    const bool shadows = rp.shadows != 0 && rp.mode != MIROGPU_RENDER_PRIMARY_ONLY && h->nlights > 0;
+    const uint32_t nl = std::max<uint32_t>(h->nlights, 1);
+    const size_t cap = npix * (any_refractive ? 4 : (any_specular || rp.mode == MIROGPU_RENDER_DIFFUSE_BOUNCE ? 2 : 1));
+    const bool use_pm = rp.use_photon_maps && (h->pm[0].stored > 0 || h->pm[1].stored > 0);
+
+    RenderScratch& sc = h->scratch;
+    // 0,1: queue A/B rays  2: hits  3,4: pix A/B  5,6: weight A/B  7: shadow rays  8: shadow hits  9: shadow cd+ch  10: accum + counters  11: gather
+    RT(sc.ensure(0, cap * sizeof(mirogpu_ray))); RT(sc.ensure(1, cap * sizeof(mirogpu_ray)));
+    RT(sc.ensure(2, cap * sizeof(mirogpu_hit)));
+    RT(sc.ensure(3, cap * 4)); RT(sc.ensure(4, cap * 4));
+    RT(sc.ensure(5, cap * 16)); RT(sc.ensure(6, cap * 16));
+    if (shadows) {
+        RT(sc.ensure(7, cap * nl * sizeof(mirogpu_ray))); RT(sc.ensure(8, cap * nl * sizeof(mirogpu_hit))); RT(sc.ensure(9, cap * nl * 32));
+    }
+    RT(sc.ensure(10, npix * 12 + 64));
+    if (use_pm) RT(sc.ensure(11, cap * (12 + 12 + 16 + 12 + 12)));
+    float* accum = reinterpret_cast<float*>(sc.buf[10]);
+    uint32_t* counters = reinterpret_cast<uint32_t*>(reinterpret_cast<char*>(sc.buf[10]) + npix * 12);   // [0] next count [1] dropped [2] gmax
+    Queue q[2];
+    for (int k = 0; k < 2; ++k) {
+        q[k].rays = reinterpret_cast<mirogpu_ray*>(sc.buf[0 + k]); q[k].hits = reinterpret_cast<mirogpu_hit*>(sc.buf[2]);
+        q[k].pix = reinterpret_cast<uint32_t*>(sc.buf[3 + k]); q[k].weight = reinterpret_cast<float4*>(sc.buf[5 + k]);
+    }
+    mirogpu_ray* srays = reinterpret_cast<mirogpu_ray*>(sc.buf[7]);
+    mirogpu_hit* shits = reinterpret_cast<mirogpu_hit*>(sc.buf[8]);
+    float4* scd = reinterpret_cast<float4*>(sc.buf[9]);
+    float4* sch = scd ? scd + cap * nl : nullptr;
+    float *gpos = nullptr, *gnrm = nullptr, *girr0 = nullptr, *girr1 = nullptr; float4* gw = nullptr;
+    if (use_pm) {
+        char* b = reinterpret_cast<char*>(sc.buf[11]);
+        gw = reinterpret_cast<float4*>(b); b += cap * 16;
+        gpos = reinterpret_cast<float*>(b); b += cap * 12; gnrm = reinterpret_cast<float*>(b); b += cap * 12;
+        girr0 = reinterpret_cast<float*>(b); b += cap * 12; girr1 = reinterpret_cast<float*>(b);
+    }
+
+    WaveParams wp;
+    wp.ds = h->ds; wp.mats = h->d_materials; wp.lights = h->d_lights; wp.nlights = h->nlights;
+    wp.mode = rp.mode; wp.shadows = shadows ? 1 : 0; wp.max_depth = rp.max_depth; wp.use_pm = use_pm ? 1 : 0;
+    for (int k = 0; k < 3; ++k) wp.bg[k] = rp.bg_color[k];
+    wp.seed = rp.seed; wp.cap = (uint32_t)std::min<size_t>(cap, 0xffffffffu);
+    wp.width = rp.width; wp.first_row = first_row; wp.row_stride = rp.row_stride;
+    CameraBasis cb;
+    camera_basis(cam, rp.width, rp.height, cb);
+
+    RT(cudaMemsetAsync(accum, 0, npix * 12 + 64, st));
+    uint32_t total_dropped = 0;
+    for (int s = 0; s < rp.spp; ++s) {
+        wp.sample = (uint32_t)s;
+        int cur = 0;
+        k_render_primary<<<(unsigned)((npix + 255) / 256), 256, 0, st>>>(cb, rp.width, rp.height, first_row, rp.row_stride, nrows, rp.jitter, rp.seed,
+                                                                          (uint32_t)s, rp.max_depth, q[cur]);
+        launches++;
+        uint32_t n = (uint32_t)npix;
+        for (int wave = 0; n > 0 && wave <= rp.max_depth + 1; ++wave) {
+            // -- closest hit for the wave
+            RT(dispatch_trace(h, q[cur].rays, n, q[cur].hits, MIROGPU_CLOSEST_HIT, st));
+            launches++; rays_traced += n;
+            RT(cudaMemsetAsync(counters, 0, 8, st));
+            k_shade<<<(n + 127) / 128, 128, 0, st>>>(wp, q[cur], n, q[cur ^ 1], counters, counters + 1, srays, scd, sch, accum, gpos, gnrm, gw);
+            launches++;
+            if (shadows) {
+                const size_t ns = (size_t)n * nl;
+                RT(dispatch_trace(h, srays, ns, shits, any_refractive ? MIROGPU_CLOSEST_HIT : MIROGPU_ANY_HIT, st));
+                k_shadow_accumulate<<<(unsigned)((ns + 255) / 256), 256, 0, st>>>(wp, srays, shits, scd, sch, ns, accum);
+                launches += 2; rays_traced += ns;
+            }
+            if (use_pm) {
+                const float4* gwc = gw;
+                if (h->pm[0].stored > 0) { RT(photon_gather_launch(h->pm[0], gpos, gnrm, n, 1e10f, 500, girr0, st, gwc)); launches++; }
+                if (h->pm[1].stored > 0) { RT(photon_gather_launch(h->pm[1], gpos, gnrm, n, 1e10f, 500, girr1, st, gwc)); launches++; }
+                k_gather_accumulate<<<(n + 255) / 256, 256, 0, st>>>(gwc, q[cur].pix, h->pm[0].stored > 0 ? girr0 : nullptr,
+                                                                       h->pm[1].stored > 0 ? girr1 : nullptr, n, accum);
+                launches++;
+            }
+            uint32_t hc[2];
+            RT(cudaMemcpyAsync(hc, counters, 8, cudaMemcpyDeviceToHost, st));
+            RT(cudaStreamSynchronize(st));
+            total_dropped += hc[1];
+            n = std::min<uint32_t>(hc[0], wp.cap);
+            cur ^= 1;
+        }
+    }
+    float* gmax = reinterpret_cast<float*>(counters + 2);
+    const float ninf = -INFINITY;
+    RT(cudaMemcpyAsync(gmax, &ninf, 4, cudaMemcpyHostToDevice, st));
+    const size_t nvals = npix * 3;
+    k_resolve_frame<<<(unsigned)((nvals + 255) / 256), 256, 0, st>>>(accum, rp.width, first_row, rp.row_stride, nrows, 1.0f / (float)rp.spp, rp.spp, d_rgb, gmax);
+    launches++;
+    if (rp.tonemap) {
+        k_tonemap<<<(unsigned)((nvals + 255) / 256), 256, 0, st>>>(d_rgb, rp.width, first_row, rp.row_stride, nrows, gmax);
+        launches++;
+    }
+    RT(cudaGetLastError());
+    h->last_rays = rays_traced; h->last_launches = launches;
+    (void)total_dropped;
+    return MIROGPU_OK;
+#undef RT
+}
+
+int render_host(mirogpu_scene* h, const mirogpu_camera& cam, const mirogpu_render_params& rp, float* rgb_out, std::string& err)
+{
+    if (rp.width <= 0 || rp.height <= 0) { err = "bad render parameters"; return MIROGPU_ERR_INVALID_ARG; }
+    const size_t bytes = (size_t)rp.width * rp.height * 12;
+    float* d_rgb = nullptr;
+    cudaError_t e = cudaMalloc(&d_rgb, bytes);
+    if (e != cudaSuccess) { err = std::string("cudaMalloc framebuffer: ") + cudaGetErrorString(e); return MIROGPU_ERR_OOM; }
+    cudaStream_t st = cudaStreamPerThread;
+    int rc = render_device(h, cam, rp, d_rgb, st, err);
+    if (rc == MIROGPU_OK) {
+        // only this call's rows are defined on the device; copy row by row when sharded, in one piece otherwise
+        if (rp.row_stride == 1 && rp.row_begin == 0 && rp.row_end == rp.height) e = cudaMemcpyAsync(rgb_out, d_rgb, bytes, cudaMemcpyDeviceToHost, st);
+        else {
+            const size_t rowb = (size_t)rp.width * 12;
+            e = cudaMemcpy2DAsync(rgb_out + (size_t)(rp.row_begin + rp.row_phase) * rp.width * 3, rowb * rp.row_stride,
+                                  d_rgb + (size_t)(rp.row_begin + rp.row_phase) * rp.width * 3, rowb * rp.row_stride, rowb,
+                                  (rp.row_end - rp.row_begin - rp.row_phase + rp.row_stride - 1) / rp.row_stride, cudaMemcpyDeviceToHost, st);
+        }
+        if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+        if (e != cudaSuccess) { err = std::string("framebuffer copy: ") + cudaGetErrorString(e); rc = MIROGPU_ERR_CUDA; }
+    }
+    cudaFree(d_rgb);
+    return rc;
+}
+
 }  // namespace
-namespace mirogpu {
-int PhotonMapDevice::upload(const void*, int, std::string& err) { err = "photon upload: not implemented yet"; return MIROGPU_ERR_UNSUPPORTED; }
-cudaError_t photon_gather_launch(const PhotonMapDevice&, const float*, const float*, size_t, float, int, float*, cudaStream_t) { return cudaErrorNotSupported; }
-}
 #endif

@@ -193,15 +193,20 @@ int mirogpu_resolve_hits_device(mirogpu_handle h, const mirogpu_hit* d_hits, siz
                                 uint32_t* d_material, void* cuda_stream);
 
 /* ---- device-side ray generation ------------------------------------------------------------------------ */
-/* Camera::eyeRay for every pixel of rows [row_begin,row_end) (row 0 = bottom), sample index `sample`.
- * Writes (row_end-row_begin)*width rays in row-major order.  jitter = 0: pixel centre (dx = dy = 0.5). */
+/* Camera::eyeRay for the pixels of this call's rows, for `sample_count` samples starting at `sample_begin`.
+ * Rows: row_begin + row_phase + j*row_stride < row_end (row 0 = bottom) -- (0, height, 1, 0) is the full frame,
+ * (0, height, N, r) is rank r's interleaved share on N GPUs.  Output order: sample-major, then row-major over
+ * the local rows: sample_count * local_rows * width rays.  jitter = 0: pixel centre (dx = dy = 0.5). */
 int mirogpu_generate_primary_device(mirogpu_handle h, const mirogpu_camera* cam, int width, int height,
-                                    int row_begin, int row_end, int jitter, uint32_t seed, uint32_t sample,
-                                    mirogpu_ray* d_rays, void* cuda_stream);
+                                    int row_begin, int row_end, int row_stride, int row_phase, int jitter, uint32_t seed,
+                                    uint32_t sample_begin, uint32_t sample_count, mirogpu_ray* d_rays, void* cuda_stream);
 /* Ray::diffuse at every hit of (d_rays, d_hits): phi = asin(sqrt(u1)), theta = 2 pi u2, direction aligned to
- * the normalised shading normal, origin P + eps*dir.  Misses yield a ray with tmax < tmin (never hits). */
+ * the normalised shading normal, origin P + eps*dir.  Misses yield a ray with tmax < tmin (never hits).
+ * Ray i draws its uniforms at RNG index index_base + i.  d_live_count (device uint64, may be NULL) is
+ * incremented by the number of live (non-miss) rays generated. */
 int mirogpu_generate_bounce_device(mirogpu_handle h, const mirogpu_ray* d_rays, const mirogpu_hit* d_hits, size_t n,
-                                   uint32_t seed, uint32_t sample, mirogpu_ray* d_out, void* cuda_stream);
+                                   uint32_t seed, uint32_t sample, uint32_t index_base, mirogpu_ray* d_out,
+                                   unsigned long long* d_live_count, void* cuda_stream);
 /* The uniform numbers the generators draw, for feeding the oracle the same samples: out = n x 2 floats. */
 int mirogpu_rng_uniforms(uint32_t seed, uint32_t sample, uint32_t dimension, size_t first, size_t n, float* out);
 

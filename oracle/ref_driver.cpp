@@ -24,6 +24,7 @@
 #include <cmath>
 #include <vector>
 #include <map>
+#include <tr1/unordered_map>
 #include <string>
 #include <iostream>
 #include <limits>
@@ -55,12 +56,13 @@
 
 namespace {
 std::vector<Material*> g_materials;
-std::map<const Object*, int> g_prim_id;
+std::tr1::unordered_map<const Object*, int> g_prim_id;   // hit.object -> index in Scene::objects()
 
 void rebuild_prim_ids()
 {
     g_prim_id.clear();
     const Objects* objs = g_scene->objects();
+    g_prim_id.rehash(2 * objs->size() + 16);
     for (size_t i = 0; i < objs->size(); ++i) g_prim_id[(*objs)[i]] = (int)i;
 }
 }  // namespace
@@ -212,7 +214,7 @@ void ref_trace(const float* rays, long n, float* out_t, int* out_id, float* out_
         HitInfo hit;
         bool h = g_scene->trace(hit, ray, r[3], r[7]);
         if (h) {
-            std::map<const Object*, int>::const_iterator it = g_prim_id.find(hit.object);
+            std::tr1::unordered_map<const Object*, int>::const_iterator it = g_prim_id.find(hit.object);
             out_id[i] = (it == g_prim_id.end()) ? -2 : it->second;
             if (out_t) out_t[i] = hit.t;
             if (out_P) { out_P[3 * i] = hit.P.x; out_P[3 * i + 1] = hit.P.y; out_P[3 * i + 2] = hit.P.z; }

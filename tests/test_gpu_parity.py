@@ -170,8 +170,15 @@ def test_primary_ray_generation_is_bit_exact(host_scenes, oracle_scene, pkg, lay
     full = torch.empty((w * h, 8), dtype=torch.float32, device="cuda")
     S.generate_primary(cam, w, h, full, jitter=1, seed=7, sample=3)
     part = torch.empty((50 * w, 8), dtype=torch.float32, device="cuda")
-    S.generate_primary(cam, w, h, part, row_begin=100, row_end=150, jitter=1, seed=7, sample=3)
+    S.generate_primary(cam, w, h, part, rows=(100, 150, 1, 0), jitter=1, seed=7, sample=3)
     assert torch.equal(part, full[100 * w:150 * w])
+    # interleaved rows (rank r of N) and several samples per call
+    inter = torch.empty((2 * 67 * w, 8), dtype=torch.float32, device="cuda")
+    S.generate_primary(cam, w, h, inter, rows=(0, h, 3, 1), jitter=1, seed=7, sample=3, samples=2)
+    assert torch.equal(inter[:67 * w].reshape(67, w, 8), full.reshape(h, w, 8)[1::3])
+    nxt = torch.empty((w * h, 8), dtype=torch.float32, device="cuda")
+    S.generate_primary(cam, w, h, nxt, jitter=1, seed=7, sample=4)
+    assert torch.equal(inter[67 * w:].reshape(67, w, 8), nxt.reshape(h, w, 8)[1::3])
     # jittered rays equal the oracle's eyeRay fed the same uniforms
     import ctypes
     import miro_driver as md
@@ -199,8 +206,10 @@ def test_bounce_generation_and_hit_resolution(host_scenes, oracle_scene, pkg, la
     S.generate_primary(cam, w, h, d_rays)
     S.intersect_device(d_rays, d_hits)
     S.resolve_hits_device(d_hits, d_P, d_N)
-    S.generate_bounce(d_rays, d_hits, d_b, seed=168, sample=0)
+    live = torch.zeros(1, dtype=torch.int64, device="cuda")
+    S.generate_bounce(d_rays, d_hits, d_b, seed=168, sample=0, d_live_count=live)
     torch.cuda.synchronize()
+    assert int(live.item()) == int((d_hits[:, 1].view(torch.int32) != -1).sum().item())
     rays = d_rays.cpu().numpy()
     hits = d_hits.cpu().numpy().view(pkg.HIT_DTYPE).reshape(-1)
     ot, oid, oP, oN = O.trace(rays)

@@ -1,0 +1,183 @@
+"""GPU tier: whole-frame rendering (Scene::raytraceImage on the device) and the photon-map gather, through the
+C ABI and the host API layer, against the oracle's restatement of Scene::traceScene / Phong::shade /
+Photon_map::irradiance_estimate (pinned bit-exactly to the real reference in test_oracle_vs_reference.py).
+
+Tolerances: images max |diff| <= 2/255 per channel after the tone map for the deterministic
+configs; PSNR >= 40 dB where secondary rays make isolated pixels flip across geometric edges; photon gather
+bit-identical (the device walk keeps the reference's visiting order and heap, so even the summation order is
+the same).
+"""
+import ctypes
+
+import numpy as np
+import pytest
+
+import miro_driver as md
+import objio
+from conftest import bits
+
+pytestmark = pytest.mark.gpu
+torch = pytest.importorskip("torch")
+
+
+def tonemap_u8(O, rgb):
+    out = np.zeros(rgb.shape, np.uint8)
+    O.lib.orc_tonemap(md._fp(np.ascontiguousarray(rgb, np.float32)), ctypes.c_long(rgb.shape[0] * rgb.shape[1] if rgb.ndim == 3 else rgb.shape[0]), md._fp(out))
+    return out
+
+
+def psnr(a, b):
+    mse = np.mean((a.astype(np.float64) - b.astype(np.float64)) ** 2)
+    return 99.0 if mse == 0 else 10 * np.log10(255.0 ** 2 / mse)
+
+
+def build_pair(pkg, scenes, oracle, name, layout=1):
+    H = pkg.HostScene(layout)
+    for d in (oracle, H):
+        scenes.realise(d, name, objio.obj_path)
+        d.precalc()
+    return H, H.scene()
+
+
+@pytest.mark.parametrize("name,size", [("cornell", (160, 120)), ("teapot", (128, 128)), ("bunny_teapot", (256, 256))])
+def test_whitted_render_matches_reference_semantics(pkg, scenes, oracle, name, size):
+    H, S = build_pair(pkg, scenes, oracle, name)
+    w, h = size
+    p = S.render_params(w, h, mode=pkg.RENDER_WHITTED, tonemap=0)
+    img = S.render(H.camera(), p)
+    ref = oracle.trace_scene(oracle.eye_rays(w, h), depth=10).reshape(h, w, 3)
+    close = np.isclose(img, ref, rtol=2e-4, atol=2e-5)
+    assert close.mean() > 0.9995, close.mean()
+    a, b = tonemap_u8(oracle, img), tonemap_u8(oracle, ref)
+    diff = np.abs(a.astype(int) - b.astype(int))
+    assert (diff <= 2).mean() > 0.9995 and psnr(a, b) >= 40
+    # the host layer's Scene::raytraceImage (device tone map + Image::setPixel) gives the same 8-bit image
+    H.set_render(spp=1, jitter=0, mode=pkg.RENDER_WHITTED, shadows=1)
+    u8 = H.render(w, h)
+    assert (np.abs(u8.astype(int) - b.astype(int)) <= 2).mean() > 0.9995
+    # no shadows == the reference's -DDISABLE_SHADOWS build: brighter or equal everywhere
+    p2 = S.render_params(w, h, mode=pkg.RENDER_WHITTED, tonemap=0, shadows=0)
+    img2 = S.render(H.camera(), p2)
+    assert (img2 >= img - 1e-6).all() and (img2 > img + 1e-4).any()
+
+
+def test_render_row_shards_are_bit_identical_to_the_full_frame(pkg, scenes, oracle):
+    H, S = build_pair(pkg, scenes, oracle, "teapot")
+    w, h = 200, 150
+    for mode in (pkg.RENDER_WHITTED, pkg.RENDER_DIFFUSE_BOUNCE):
+        full = S.render(H.camera(), S.render_params(w, h, mode=mode, jitter=1, spp=2, seed=5))
+        for nshard in (2, 3, 8):
+            acc = np.full((h, w, 3), np.nan, np.float32)
+            for r in range(nshard):
+                S.render(H.camera(), S.render_params(w, h, mode=mode, jitter=1, spp=2, seed=5, rows=(0, h, nshard, r)), out=acc)
+            assert np.array_equal(bits(acc), bits(full))
+        # contiguous blocks of rows as well
+        acc = np.full((h, w, 3), np.nan, np.float32)
+        for (a, b) in ((0, 40), (40, 41), (41, 150)):
+            S.render(H.camera(), S.render_params(w, h, mode=mode, jitter=1, spp=2, seed=5, rows=(a, b, 1, 0)), out=acc)
+        assert np.array_equal(bits(acc), bits(full))
+
+
+def test_diffuse_bounce_render(pkg, scenes, oracle):
+    """BASELINE config 3's estimator on small geometry: jittered primary + one Ray::diffuse bounce, radiance =
+    direct(P0) + kd * direct(P1), rebuilt from oracle pieces with the same uniforms."""
+    H, S = build_pair(pkg, scenes, oracle, "teapot")
+    w, h = 160, 120
+    n = w * h
+    p = S.render_params(w, h, mode=pkg.RENDER_DIFFUSE_BOUNCE, jitter=1, spp=1, seed=168, shadows=1)
+    img = S.render(H.camera(), p).reshape(n, 3)
+    assert S.last_call_stats()[0] >= 2 * n                                   # primaries + shadow + bounce rays were traced
+    uj = pkg.rng_uniforms(168, 0, 0, 0, n)
+    rays = np.zeros((n, 8), np.float32)
+    oracle.lib.orc_eye_rays_jitter(w, h, md._fp(uj), md._fp(rays))
+    t, ids, P, N = oracle.trace(rays)
+    d0 = oracle.trace_scene(rays, depth=0)
+    ub = pkg.rng_uniforms(168, 0, 1, 0, n)
+    brays = np.zeros((n, 8), np.float32)
+    oracle.lib.orc_diffuse_rays(md._fp(P), md._fp(N), md._fp(ids), md._fp(ub), ctypes.c_long(n), md._fp(brays))
+    d1 = oracle.trace_scene(brays, depth=0)
+    d1[ids < 0] = 0
+    ref = d0 + d1          # kd = 1
+    close = np.isclose(img, ref, rtol=1e-3, atol=1e-4)
+    assert close.all(axis=1).mean() > 0.998, close.all(axis=1).mean()
+
+
+def test_specular_and_refractive_materials(pkg, scenes, oracle):
+    """Reflection / Fresnel / refraction recursion (Scene.cpp:302-336) and the refractive-occluder shadow rule
+    (Phong.cpp:99-113): cornell box + a glass sphere + a mirror teapot."""
+    H = pkg.HostScene()
+    T = scenes.translate
+    for d in (oracle, H):
+        d.new_scene()
+        d.new_material((1, 1, 1), (0, 0, 0), (0, 0, 0), 1.0, 1.0)
+        d.new_material((0.1, 0.1, 0.1), (0, 0, 0), (1, 1, 1), 5.0, 1.5)        # glass: Phong(kd, 0, 1, 5, 1.5)
+        d.new_material((0.2, 0.2, 0.2), (0.8, 0.8, 0.8), (0, 0, 0), -1.0, 1.0)  # mirror, infinite shininess
+        d.add_obj(objio.obj_path("cornell_box"), None, 0)
+        d.add_obj(objio.obj_path("sphere"), (T(1.5, 1.2, -1.0) @ scenes.scale(0.8, 0.8, 0.8)).astype(np.float32), 1)
+        d.add_obj(objio.obj_path("teapot"), (T(3.6, 0.0, -2.0) @ scenes.scale(0.6, 0.6, 0.6)).astype(np.float32), 2)
+        d.add_point_light((2.5, 4.9, -1), (1, 1, 1), 160)
+        d.set_bg_color((0.0, 0.0, 0.2))
+        d.set_camera((2.5, 3, 3), (2.5, 2.5, 0), (0, 1, 0), 90)
+        d.precalc()
+    S = H.scene()
+    w, h = 192, 144
+    img = S.render(H.camera(), S.render_params(w, h, mode=pkg.RENDER_WHITTED, max_depth=10, bg=(0, 0, 0.2)))
+    ref = oracle.trace_scene(oracle.eye_rays(w, h), depth=10).reshape(h, w, 3)
+    assert np.isfinite(img).mean() > 0.999
+    a, b = tonemap_u8(oracle, np.nan_to_num(img)), tonemap_u8(oracle, np.nan_to_num(ref))
+    diff = np.abs(a.astype(int) - b.astype(int)).max(axis=2)
+    assert (diff <= 2).mean() > 0.99, (diff <= 2).mean()
+    assert psnr(a, b) >= 35, psnr(a, b)
+    assert S.last_call_stats()[0] > 3 * w * h            # secondary generations were traced
+
+
+def _photon_cloud(n, seed):
+    rng = np.random.default_rng(seed)
+    pos = (rng.random((n, 3), dtype=np.float32) * np.float32(5)).astype(np.float32)
+    pos[:, 1] *= 0.02                                      # mostly on a floor, like stored photons
+    d = rng.normal(size=(n, 3)).astype(np.float32); d /= np.linalg.norm(d, axis=1, keepdims=True)
+    pw = rng.random((n, 3), dtype=np.float32)
+    return pw, pos, d
+
+
+@pytest.mark.parametrize("nphot", [1, 7, 1000, 60000])
+def test_photon_gather_is_bit_identical(pkg, scenes, oracle, nphot):
+    H, S = build_pair(pkg, scenes, oracle, "testobj")
+    pw, pos, d = _photon_cloud(nphot, 4)
+    w = oracle.pm_new(nphot)
+    oracle.pm_store(w, pw, pos, d); oracle.pm_scale(w, 1.0 / nphot); oracle.pm_balance(w)
+    S.photon_upload(0, oracle.pm_dump(w))
+    rng = np.random.default_rng(5)
+    q = (rng.random((3000, 3), dtype=np.float32) * np.float32(5)).astype(np.float32); q[:, 1] *= 0.02
+    qn = np.tile(np.array([[0, 1, 0]], np.float32), (3000, 1))
+    qn[::3] = rng.normal(size=(1000, 3)).astype(np.float32)
+    for k, md_ in ((500, 1e10), (50, 1e10), (1, 1e10), (50, 0.3), (512, 1e10)):
+        a = oracle.pm_irradiance(w, q, qn, md_, k)
+        b = S.photon_gather(0, q, qn, md_, k)
+        assert np.array_equal(bits(a), bits(b)), (nphot, k, md_)
+    assert oracle.pm_irradiance(w, q, qn, 1e10, 50).max() > 0 or nphot < 50
+    # through the host layer's Photon_map (store / scale / balance on the host, gather on the device)
+    H.pm_store(1, pw, pos, d); H.pm_scale(1, 1.0 / nphot); H.pm_balance(1); H.pm_attach(1)
+    c = H.pm_irradiance(1, q, qn, 1e10, 100)
+    assert np.array_equal(bits(c), bits(oracle.pm_irradiance(w, q, qn, 1e10, 100)))
+
+
+def test_render_with_photon_maps(pkg, scenes, oracle):
+    """Config 5's gather inside the frame: irradiance of both maps added at diffuse hits (Scene.cpp:286-299)."""
+    H, S = build_pair(pkg, scenes, oracle, "cornell")
+    n = 20000
+    pw, pos, d = _photon_cloud(n, 8)
+    pw2, pos2, d2 = _photon_cloud(n // 4, 9)
+    d[:, 1] = -np.abs(d[:, 1]); d2[:, 1] = -np.abs(d2[:, 1])      # arriving from above, so floor normals accept them
+    for which, (a, b, c) in enumerate(((pw, pos, d), (pw2, pos2, d2))):
+        oracle.lib.orc_pm_reset(which, ctypes.c_int(len(b)))
+        oracle.pm_store(which, a, b, c); oracle.pm_scale(which, 1.0 / len(b)); oracle.pm_balance(which)
+        S.photon_upload(which, oracle.pm_dump(which))
+    w, h = 96, 72
+    img = S.render(H.camera(), S.render_params(w, h, mode=pkg.RENDER_WHITTED, use_photon_maps=1))
+    ref = oracle.trace_scene(oracle.eye_rays(w, h), depth=10).reshape(h, w, 3)
+    base = S.render(H.camera(), S.render_params(w, h, mode=pkg.RENDER_WHITTED, use_photon_maps=0))
+    assert (img - base).max() > 1e-3                                   # the maps contribute
+    assert np.isclose(img, ref, rtol=2e-4, atol=2e-5).mean() > 0.999
+    for which in (0, 1):
+        oracle.lib.orc_pm_reset(which, ctypes.c_int(1))
