@@ -284,30 +284,26 @@ def run_ours(args):
     e2e_steps = args.steps
     p = S.render_params(WIDTH, HEIGHT, spp=SPP, jitter=1, max_depth=10, mode=pkg.RENDER_DIFFUSE_BOUNCE, seed=SEED, tonemap=0,
                         rows=rows, shadows=0)
-    host_fb = torch.empty((HEIGHT, WIDTH, 3), dtype=torch.float32).pin_memory()
+    host_fb = torch.empty((HEIGHT, WIDTH, 3), dtype=torch.uint8).pin_memory()   # the reference's Image: 3 bytes per pixel
     e2e_rays = 0
     if world == 1:
         def e2e_step(it):
             p.seed = SEED + it
-            S.render(cam, p, out=host_fb.numpy())
+            S.render_rgb8(cam, p, out=host_fb.numpy())
             return S.last_call_stats()[0]
     else:
+        sharding = importlib.import_module("cse168-raytracer_b200.sharding")
         d_rgb = torch.zeros((HEIGHT, WIDTH, 3), dtype=torch.float32, device=dev)
-        nrows_max = (HEIGHT + world - 1) // world
-        d_local = torch.empty((nrows_max, WIDTH, 3), dtype=torch.float32, device=dev)
-        d_all = torch.empty((world, nrows_max, WIDTH, 3), dtype=torch.float32, device=dev)
+        d_full = torch.empty((HEIGHT, WIDTH, 3), dtype=torch.float32, device=dev)
+        d_u8 = torch.empty((HEIGHT, WIDTH, 3), dtype=torch.uint8, device=dev)
 
         def e2e_step(it):
             p.seed = SEED + it
-            S.render_device(cam, p, d_rgb)
-            d_local.zero_()
-            d_local[:nrows].copy_(d_rgb[rank::world])
-            dist.all_gather_into_tensor(d_all, d_local)     # framebuffer gather over NVLink
+            S.render_device(cam, p, d_rgb)                                   # this rank's rows, float radiance
+            sharding.gather_rows(d_rgb[rank::world], HEIGHT, world, rank, out=d_full)   # framebuffer gather over NVLink (NCCL)
             if rank == 0:
-                for r in range(world):
-                    k = len(range(r, HEIGHT, world))
-                    d_rgb[r::world].copy_(d_all[r, :k])
-                host_fb.copy_(d_rgb, non_blocking=True)
+                S.tonemap_rgb8_device(d_full, d_u8)                          # Scene.cpp:177-202 + Image::Map on the gathered frame
+                host_fb.copy_(d_u8, non_blocking=True)
             torch.cuda.synchronize()
             return S.last_call_stats()[0]
     for it in range(min(3, args.warmup)):
@@ -379,8 +375,8 @@ def run_ours(args):
                          "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
                          "note": "algorithmic bytes = live bounce rays per launch x (32V + 36T + 48) B; the scene is mostly L2-resident, so DRAM traffic is far below this"},
             "cpu_baseline": cpu,
-            "e2e": {"value": e2e_value, "unit": "Mrays/s", "h2d_bytes_per_step": 40 + 17 * 4, "d2h_bytes_per_step": WIDTH * HEIGHT * 12,
-                    "call": "mirogpu_render (Scene::raytraceImage), diffuse-bounce mode, host framebuffer" + ("" if world == 1 else " + NCCL all_gather of row shards")},
+            "e2e": {"value": e2e_value, "unit": "Mrays/s", "h2d_bytes_per_step": 40 + 17 * 4, "d2h_bytes_per_step": WIDTH * HEIGHT * 3,
+                    "call": "mirogpu_render_rgb8 (Scene::raytraceImage -> 8-bit Image), diffuse-bounce mode, pinned host framebuffer" + ("" if world == 1 else " + NCCL all_gather of row shards")},
             "gpu_launches": int(4 * args.steps * world),
             "clocks": clocks,
         }

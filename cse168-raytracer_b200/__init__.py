@@ -80,7 +80,7 @@ EXPORTS = [
     "mirogpu_scene_info_get", "mirogpu_scene_set_lights", "mirogpu_debug_copy_nodes", "mirogpu_debug_copy_triangles",
     "mirogpu_intersect_batch", "mirogpu_intersect_batch_device", "mirogpu_intersect_batch_counted", "mirogpu_set_kernel_variant",
     "mirogpu_resolve_hits_device", "mirogpu_generate_primary_device", "mirogpu_generate_bounce_device", "mirogpu_rng_uniforms",
-    "mirogpu_render", "mirogpu_render_device", "mirogpu_last_call_stats", "mirogpu_photon_upload", "mirogpu_photon_gather",
+    "mirogpu_render", "mirogpu_render_rgb8", "mirogpu_tonemap_rgb8_device", "mirogpu_render_device", "mirogpu_last_call_stats", "mirogpu_photon_upload", "mirogpu_photon_gather",
     "mirogpu_photon_gather_device",
 ]
 
@@ -277,6 +277,17 @@ class MiroScene:
             out = np.zeros((params.height, params.width, 3), np.float32)
         _check(lib.mirogpu_render(self._h, ctypes.byref(cam), ctypes.byref(params), _ptr(out)))
         return out
+
+    def render_rgb8(self, cam, params, out=None):
+        """HOST 8-bit framebuffer (height, width, 3), tone-mapped like the reference's Image; row 0 = bottom."""
+        if out is None:
+            out = np.zeros((params.height, params.width, 3), np.uint8)
+        _check(lib.mirogpu_render_rgb8(self._h, ctypes.byref(cam), ctypes.byref(params), _ptr(out)))
+        return out
+
+    def tonemap_rgb8_device(self, d_rgb, d_rgb8):
+        h, w = d_rgb.shape[0], d_rgb.shape[1]
+        _check(lib.mirogpu_tonemap_rgb8_device(self._h, _ptr(d_rgb), int(w), int(h), _ptr(d_rgb8), _stream()))
 
     def render_device(self, cam, params, d_rgb):
         _check(lib.mirogpu_render_device(self._h, ctypes.byref(cam), ctypes.byref(params), _ptr(d_rgb), _stream()))

@@ -51,8 +51,10 @@ __device__ __forceinline__ void store_hit(mirogpu_hit* hits, size_t i, const Bes
 
 template <int LAYOUT, bool ANY, bool COUNT>
 __global__ void __launch_bounds__(128) k_trace_simple(DeviceScene s, const mirogpu_ray* __restrict__ rays, size_t n,
-                                                      mirogpu_hit* __restrict__ hits, unsigned long long* __restrict__ counters)
+                                                      mirogpu_hit* __restrict__ hits, unsigned long long* __restrict__ counters,
+                                                      const uint32_t* __restrict__ d_n, uint32_t mult)
 {
+    if (d_n) n = min(n, (size_t)*d_n * mult);
     const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     TraceCounters c = {0, 0, 0};
     uint32_t hit = 0;
@@ -86,8 +88,10 @@ __global__ void __launch_bounds__(128) k_trace_simple(DeviceScene s, const mirog
 // tail effect of uneven ray costs across CTAs.
 template <int LAYOUT, bool ANY>
 __global__ void __launch_bounds__(128) k_trace_persistent(DeviceScene s, const mirogpu_ray* __restrict__ rays, size_t n,
-                                                          mirogpu_hit* __restrict__ hits, unsigned long long* __restrict__ ticket)
+                                                          mirogpu_hit* __restrict__ hits, unsigned long long* __restrict__ ticket,
+                                                          const uint32_t* __restrict__ d_n, uint32_t mult)
 {
+    if (d_n) n = min(n, (size_t)*d_n * mult);
     const unsigned lane = threadIdx.x & 31u;
     for (;;) {
         unsigned long long base = 0;
@@ -100,6 +104,64 @@ __global__ void __launch_bounds__(128) k_trace_persistent(DeviceScene s, const m
             BestHit best;
             trace_one<LAYOUT, ANY, false>(s, r, best, nullptr);
             store_hit(hits, i, best);
+        }
+        __syncwarp();
+    }
+}
+
+// Persistent warps with ray replacement (BVH2).  Every lane owns one ray's resumable traversal state and runs
+// it for a quantum of node visits; at each quantum boundary a ballot finds the lanes whose ray has finished,
+// ONE atomic claims that many new rays for the warp, a popc-prefix hands each idle lane its ray, and the busy
+// lanes resume where they stopped.  Incoherent rays differ wildly in cost (sky rays end after 2-3 nodes,
+// interior rays take 50+; rays generated at misses are dead on arrival), so a fixed 32-ray packet runs at the
+// length of its slowest ray with most lanes idle (ncu: 7.4 of 32 threads active per instruction on bounce rays).
+#define MIRO_REFILL_BELOW 12   /* default quantum: node visits per lane between refill points */
+
+template <bool ANY>
+__global__ void __launch_bounds__(128) k_trace_bvh2_dynamic(DeviceScene s, const mirogpu_ray* __restrict__ rays, size_t n,
+                                                            mirogpu_hit* __restrict__ hits, unsigned long long* __restrict__ ticket,
+                                                            int quantum, const uint32_t* __restrict__ d_n, uint32_t mult)
+{
+    if (d_n) n = min(n, (size_t)*d_n * mult);
+    const unsigned lane = threadIdx.x & 31u;
+    const unsigned lt_mask = (1u << lane) - 1u;
+    bool active = false, drained = false;
+    size_t my = 0;
+    mirogpu_ray r;
+    Bvh2State st;
+    BestHit best;
+    int32_t stack[MIRO_STACK];
+    r.ox = r.oy = r.oz = r.tmin = r.dx = r.dy = r.dz = r.tmax = 0.f;
+    st.node = MIRO_BVH2_DONE; st.sp = 0;
+    st.idx = st.idy = st.idz = st.oodx = st.oody = st.oodz = 0.f;
+    best.t = 0.f; best.prim = MIROGPU_MISS; best.beta = best.gamma = 0.f;
+    for (;;) {
+        // ---- hand new rays to idle lanes (two rounds, so a lane that drew a dead ray gets another) ----
+        for (int round = 0; round < 2 && !drained; ++round) {
+            const unsigned idle = __ballot_sync(0xffffffffu, !active);
+            if (!idle) break;
+            const int leader = __ffs(idle) - 1;
+            unsigned long long base = 0;
+            if ((int)lane == leader) base = atomicAdd(ticket, (unsigned long long)__popc(idle));
+            base = __shfl_sync(0xffffffffu, base, leader);
+            if (base >= n) { drained = true; break; }
+            if (!active) {
+                const size_t i = (size_t)base + __popc(idle & lt_mask);
+                if (i < n) {
+                    r = load_ray(rays, i);
+                    bvh2_begin(r, st, best);
+                    if (st.node == MIRO_BVH2_DONE) store_hit(hits, i, best);   // empty interval: answered without traversal
+                    else { active = true; my = i; }
+                }
+            }
+        }
+        if (!__any_sync(0xffffffffu, active)) {
+            if (drained) return;
+            continue;
+        }
+        if (active) {
+            const bool done = bvh2_run<ANY>(s.nodes, s.tris, r, st, stack, best, drained ? 0x7fffffff : quantum);
+            if (done) { store_hit(hits, my, best); active = false; }
         }
         __syncwarp();
     }

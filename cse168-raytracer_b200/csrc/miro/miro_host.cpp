@@ -437,16 +437,11 @@ void Scene::raytraceImage(Camera* cam, Image* img)
     for (int k = 0; k < 3; ++k) p.bg_color[k] = m_bgColor[k];
     p.use_photon_maps = m_usePhotonMaps ? 1 : 0;
     p.shadows = renderShadows;
-    std::vector<float> rgb((size_t)w * h * 3);
     const mirogpu_camera c = cam->abi();
     const double t0 = wall();
-    if (mirogpu_render(m_bvh.handle(), &c, &p, rgb.data()) != MIROGPU_OK) fatal("Scene::raytraceImage");
+    // the device applies the tone map and Image::setPixel's 8-bit mapping; Image::Pixel is 3 bytes, row 0 = bottom
+    if (mirogpu_render_rgb8(m_bvh.handle(), &c, &p, img->getCharPixels()) != MIROGPU_OK) fatal("Scene::raytraceImage");
     lastRenderSeconds = wall() - t0;
-    for (int y = 0; y < h; ++y)
-        for (int x = 0; x < w; ++x) {
-            const float* q = &rgb[3 * ((size_t)y * w + x)];
-            img->setPixel(x, y, Vector3(q[0], q[1], q[2]));
-        }
     printf("Time spent raytracing image: %lf seconds.\n", lastRenderSeconds);
 }
 

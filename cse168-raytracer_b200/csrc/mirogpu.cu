@@ -6,6 +6,7 @@
 #include <chrono>
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <mutex>
 #include <string>
@@ -53,6 +54,7 @@ struct mirogpu_scene {
     int layout = MIROGPU_LAYOUT_CWBVH8;
     int variant = 0;
     int sm_count = 148;
+    int refill_below = MIRO_REFILL_BELOW;   // ray-replacement quantum in node visits (env MIROGPU_QUANTUM overrides, for tuning)
     DeviceScene ds{};
     void* d_nodes = nullptr;
     void* d_tris = nullptr;
@@ -70,41 +72,51 @@ struct mirogpu_scene {
     RenderScratch scratch;
     std::mutex mtx;                   // guards scratch and the last-call stats
     uint64_t last_rays = 0, last_launches = 0;
+    bool any_refractive = false, any_specular = false;
+    uint32_t* h_stats = nullptr;      // pinned: device wave counters of the last render land here
+    uint32_t stats_batches = 0, stats_mult = 1;
 };
 
 namespace {
 
+// n is the number of rays, or -- when d_n is given -- an upper bound on it: the kernels then read the real count
+// *d_n * mult from device memory (wavefront queues whose size the host never sees).
 template <int LAYOUT, bool ANY>
-cudaError_t launch_trace(mirogpu_scene* h, const mirogpu_ray* d_rays, size_t n, mirogpu_hit* d_hits, cudaStream_t st)
+cudaError_t launch_trace(mirogpu_scene* h, const mirogpu_ray* d_rays, size_t n, mirogpu_hit* d_hits, cudaStream_t st,
+                         const uint32_t* d_n, uint32_t mult)
 {
     if (n == 0) return cudaSuccess;
     if (h->variant == 1) {
         const unsigned grid = (unsigned)((n + 127) / 128);
-        k_trace_simple<LAYOUT, ANY, false><<<grid, 128, 0, st>>>(h->ds, d_rays, n, d_hits, nullptr);
+        k_trace_simple<LAYOUT, ANY, false><<<grid, 128, 0, st>>>(h->ds, d_rays, n, d_hits, nullptr, d_n, mult);
         return cudaGetLastError();
     }
     unsigned long long* ticket = h->d_ticket + (h->ticket_slot.fetch_add(1) & 63u);
     cudaError_t e = cudaMemsetAsync(ticket, 0, sizeof(unsigned long long), st);
     if (e != cudaSuccess) return e;
+    const bool dynamic = LAYOUT == MIROGPU_LAYOUT_BVH2 && h->variant == 2;   // variant 0: 32-ray tickets (fastest measured)
     int occ = 0;
-    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_trace_persistent<LAYOUT, ANY>, 128, 0);
+    if (dynamic) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_trace_bvh2_dynamic<ANY>, 128, 0);
+    else e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_trace_persistent<LAYOUT, ANY>, 128, 0);
     if (e != cudaSuccess) return e;
     if (occ < 1) occ = 1;
     size_t grid = (size_t)h->sm_count * occ;
     const size_t need = (n + 127) / 128;
     if (grid > need) grid = need;
-    k_trace_persistent<LAYOUT, ANY><<<(unsigned)grid, 128, 0, st>>>(h->ds, d_rays, n, d_hits, ticket);
+    if (dynamic) k_trace_bvh2_dynamic<ANY><<<(unsigned)grid, 128, 0, st>>>(h->ds, d_rays, n, d_hits, ticket, h->refill_below, d_n, mult);
+    else k_trace_persistent<LAYOUT, ANY><<<(unsigned)grid, 128, 0, st>>>(h->ds, d_rays, n, d_hits, ticket, d_n, mult);
     return cudaGetLastError();
 }
 
-cudaError_t dispatch_trace(mirogpu_scene* h, const mirogpu_ray* d_rays, size_t n, mirogpu_hit* d_hits, int mode, cudaStream_t st)
+cudaError_t dispatch_trace(mirogpu_scene* h, const mirogpu_ray* d_rays, size_t n, mirogpu_hit* d_hits, int mode, cudaStream_t st,
+                           const uint32_t* d_n = nullptr, uint32_t mult = 1)
 {
     const bool any = mode == MIROGPU_ANY_HIT;
     if (h->layout == MIROGPU_LAYOUT_BVH2)
-        return any ? launch_trace<MIROGPU_LAYOUT_BVH2, true>(h, d_rays, n, d_hits, st)
-                   : launch_trace<MIROGPU_LAYOUT_BVH2, false>(h, d_rays, n, d_hits, st);
-    return any ? launch_trace<MIROGPU_LAYOUT_CWBVH8, true>(h, d_rays, n, d_hits, st)
-               : launch_trace<MIROGPU_LAYOUT_CWBVH8, false>(h, d_rays, n, d_hits, st);
+        return any ? launch_trace<MIROGPU_LAYOUT_BVH2, true>(h, d_rays, n, d_hits, st, d_n, mult)
+                   : launch_trace<MIROGPU_LAYOUT_BVH2, false>(h, d_rays, n, d_hits, st, d_n, mult);
+    return any ? launch_trace<MIROGPU_LAYOUT_CWBVH8, true>(h, d_rays, n, d_hits, st, d_n, mult)
+               : launch_trace<MIROGPU_LAYOUT_CWBVH8, false>(h, d_rays, n, d_hits, st, d_n, mult);
 }
 
 // Camera::eyeRay's cached basis (Camera.cpp:113-124), computed on the host in the reference's operand order.
@@ -157,7 +169,7 @@ int mirogpu_scene_create(const float* tri_vertices, const float* tri_normals, co
     if (!out) return fail(MIROGPU_ERR_INVALID_ARG, "out handle is NULL");
     *out = nullptr;
     if (ntris && !tri_vertices) return fail(MIROGPU_ERR_INVALID_ARG, "tri_vertices is NULL");
-    if (ntris >= (1u << 28)) return fail(MIROGPU_ERR_INVALID_ARG, "too many triangles (limit 2^28)");
+    if (ntris >= (1u << 28) - 16u) return fail(MIROGPU_ERR_INVALID_ARG, "too many triangles (limit 2^28 - 16)");
     mirogpu_build_options o;
     o.layout = MIROGPU_LAYOUT_CWBVH8; o.max_leaf = 0; o.sah_bins = 32; o.device = -1;
     if (opt) o = *opt;
@@ -183,6 +195,7 @@ int mirogpu_scene_create(const float* tri_vertices, const float* tri_normals, co
     cudaDeviceProp prop;
     CUDA_TRY(cudaGetDeviceProperties(&prop, dev));
     h->sm_count = prop.multiProcessorCount;
+    if (const char* e = getenv("MIROGPU_QUANTUM")) { const int v = atoi(e); if (v >= 1 && v <= 100000) h->refill_below = v; }
 
     // ---- host build ------------------------------------------------------------------------------
     double t0 = now_s();
@@ -241,6 +254,12 @@ int mirogpu_scene_create(const float* tri_vertices, const float* tri_normals, co
     if ((e = cudaMemcpy(h->d_materials, mats.data(), mats.size() * sizeof(mirogpu_material), cudaMemcpyHostToDevice)) != cudaSuccess) return bail(e, "upload materials");
     if ((e = cudaMemset(h->d_ticket, 0, 64 * sizeof(unsigned long long))) != cudaSuccess) return bail(e, "memset tickets");
     h->nmaterials = (uint32_t)mats.size();
+    for (const mirogpu_material& m : mats) {
+        h->any_refractive |= m.kt[0] > 0.f || m.kt[1] > 0.f || m.kt[2] > 0.f;
+        h->any_specular |= m.ks[0] > 0.f || m.ks[1] > 0.f || m.ks[2] > 0.f;
+    }
+    if ((e = cudaHostAlloc(&h->h_stats, 64 * sizeof(uint32_t), cudaHostAllocDefault)) != cudaSuccess) return bail(e, "cudaHostAlloc stats");
+    memset(h->h_stats, 0, 64 * sizeof(uint32_t));
     double t3 = now_s();
 
     h->ds.nodes = reinterpret_cast<const float4*>(h->d_nodes);
@@ -268,6 +287,7 @@ int mirogpu_scene_destroy(mirogpu_handle h)
     cudaSetDevice(h->device);
     cudaFree(h->d_nodes); cudaFree(h->d_tris); cudaFree(h->d_shade); cudaFree(h->d_materials);
     cudaFree(h->d_lights); cudaFree(h->d_ticket);
+    if (h->h_stats) cudaFreeHost(h->h_stats);
     for (int i = 0; i < 2; ++i) h->pm[i].release();
     h->scratch.release();
     (void)cudaGetLastError();
@@ -317,7 +337,8 @@ int mirogpu_debug_copy_triangles(mirogpu_handle h, void* out, uint64_t* bytes)
 int mirogpu_set_kernel_variant(mirogpu_handle h, int variant)
 {
     if (!h) return fail(MIROGPU_ERR_INVALID_ARG, "NULL handle");
-    if (variant < 0 || variant > 1) return fail(MIROGPU_ERR_INVALID_ARG, "variant must be 0 (persistent) or 1 (one thread per ray)");
+    if (variant < 0 || variant > 2)
+        return fail(MIROGPU_ERR_INVALID_ARG, "variant must be 0 (persistent warps, 32-ray tickets), 1 (one thread per ray) or 2 (persistent warps with ray replacement, BVH2)");
     h->variant = variant;
     return MIROGPU_OK;
 }
@@ -331,7 +352,7 @@ int mirogpu_intersect_batch_device(mirogpu_handle h, const mirogpu_ray* d_rays, 
     CUDA_TRY(dispatch_trace(h, d_rays, n, d_hits, mode, (cudaStream_t)cuda_stream));
     {
         std::lock_guard<std::mutex> lk(h->mtx);
-        h->last_rays = n; h->last_launches = n ? 1 : 0;
+        h->last_rays = n; h->last_launches = n ? 1 : 0; h->stats_batches = 0;
     }
     return MIROGPU_OK;
 }
@@ -373,7 +394,7 @@ int mirogpu_intersect_batch(mirogpu_handle h, const mirogpu_ray* rays, size_t n,
     }
     {
         std::lock_guard<std::mutex> lk(h->mtx);
-        h->last_rays = n; h->last_launches = launches;
+        h->last_rays = n; h->last_launches = launches; h->stats_batches = 0;
     }
     return rc;
 }
@@ -394,11 +415,11 @@ int mirogpu_intersect_batch_counted(mirogpu_handle h, const mirogpu_ray* rays, s
     const unsigned grid = (unsigned)((n + 127) / 128);
     const bool any = mode == MIROGPU_ANY_HIT;
     if (h->layout == MIROGPU_LAYOUT_BVH2) {
-        if (any) k_trace_simple<MIROGPU_LAYOUT_BVH2, true, true><<<grid, 128>>>(h->ds, d_r, n, d_h, d_c);
-        else k_trace_simple<MIROGPU_LAYOUT_BVH2, false, true><<<grid, 128>>>(h->ds, d_r, n, d_h, d_c);
+        if (any) k_trace_simple<MIROGPU_LAYOUT_BVH2, true, true><<<grid, 128>>>(h->ds, d_r, n, d_h, d_c, nullptr, 1);
+        else k_trace_simple<MIROGPU_LAYOUT_BVH2, false, true><<<grid, 128>>>(h->ds, d_r, n, d_h, d_c, nullptr, 1);
     } else {
-        if (any) k_trace_simple<MIROGPU_LAYOUT_CWBVH8, true, true><<<grid, 128>>>(h->ds, d_r, n, d_h, d_c);
-        else k_trace_simple<MIROGPU_LAYOUT_CWBVH8, false, true><<<grid, 128>>>(h->ds, d_r, n, d_h, d_c);
+        if (any) k_trace_simple<MIROGPU_LAYOUT_CWBVH8, true, true><<<grid, 128>>>(h->ds, d_r, n, d_h, d_c, nullptr, 1);
+        else k_trace_simple<MIROGPU_LAYOUT_CWBVH8, false, true><<<grid, 128>>>(h->ds, d_r, n, d_h, d_c, nullptr, 1);
     }
     CUDA_TRY(cudaGetLastError());
     unsigned long long hc[4];
@@ -467,7 +488,10 @@ int mirogpu_last_call_stats(mirogpu_handle h, uint64_t* rays_traced, uint64_t* k
 {
     if (!h) return fail(MIROGPU_ERR_INVALID_ARG, "NULL handle");
     std::lock_guard<std::mutex> lk(h->mtx);
-    if (rays_traced) *rays_traced = h->last_rays;
+    uint64_t rays = h->last_rays;
+    // secondary waves of the last render batches were counted on the device (valid after the stream was synchronised)
+    if (h->stats_batches) { uint64_t secondary; memcpy(&secondary, h->h_stats, 8); rays += secondary * h->stats_mult; }
+    if (rays_traced) *rays_traced = rays;
     if (kernel_launches) *kernel_launches = h->last_launches;
     return MIROGPU_OK;
 }
@@ -477,7 +501,16 @@ int mirogpu_render(mirogpu_handle h, const mirogpu_camera* cam, const mirogpu_re
     if (!h || !cam || !p || !rgb_out) return fail(MIROGPU_ERR_INVALID_ARG, "NULL argument");
     CUDA_TRY(cudaSetDevice(h->device));
     std::string err;
-    const int rc = render_host(h, *cam, *p, rgb_out, err);
+    const int rc = render_host(h, *cam, *p, rgb_out, nullptr, err);
+    return rc == MIROGPU_OK ? rc : fail(rc, err);
+}
+
+int mirogpu_render_rgb8(mirogpu_handle h, const mirogpu_camera* cam, const mirogpu_render_params* p, uint8_t* rgb8_out)
+{
+    if (!h || !cam || !p || !rgb8_out) return fail(MIROGPU_ERR_INVALID_ARG, "NULL argument");
+    CUDA_TRY(cudaSetDevice(h->device));
+    std::string err;
+    const int rc = render_host(h, *cam, *p, nullptr, rgb8_out, err);
     return rc == MIROGPU_OK ? rc : fail(rc, err);
 }
 
@@ -487,8 +520,25 @@ int mirogpu_render_device(mirogpu_handle h, const mirogpu_camera* cam, const mir
     if (!h || !cam || !p || !d_rgb) return fail(MIROGPU_ERR_INVALID_ARG, "NULL argument");
     CUDA_TRY(cudaSetDevice(h->device));
     std::string err;
-    const int rc = render_device(h, *cam, *p, d_rgb, (cudaStream_t)cuda_stream, err);
+    const int rc = render_device(h, *cam, *p, d_rgb, nullptr, (cudaStream_t)cuda_stream, err);
     return rc == MIROGPU_OK ? rc : fail(rc, err);
+}
+
+int mirogpu_tonemap_rgb8_device(mirogpu_handle h, const float* d_rgb, int width, int height, uint8_t* d_rgb8, void* cuda_stream)
+{
+    if (!h || !d_rgb || !d_rgb8 || width <= 0 || height <= 0) return fail(MIROGPU_ERR_INVALID_ARG, "bad argument");
+    CUDA_TRY(cudaSetDevice(h->device));
+    cudaStream_t st = (cudaStream_t)cuda_stream;
+    std::lock_guard<std::mutex> lk(h->mtx);
+    CUDA_TRY(h->scratch.ensure(15, 64));
+    float* gmax = reinterpret_cast<float*>(h->scratch.buf[15]);
+    const float ninf = -INFINITY;
+    CUDA_TRY(cudaMemcpyAsync(gmax, &ninf, 4, cudaMemcpyHostToDevice, st));
+    const size_t nvals = (size_t)width * height * 3;
+    k_frame_max<<<(unsigned)((nvals + 255) / 256), 256, 0, st>>>(d_rgb, nvals, gmax);
+    k_tonemap<<<(unsigned)((nvals + 255) / 256), 256, 0, st>>>(const_cast<float*>(d_rgb), d_rgb8, width, 0, 1, height, gmax);
+    CUDA_TRY(cudaGetLastError());
+    return MIROGPU_OK;
 }
 
 int mirogpu_photon_upload(mirogpu_handle h, int which, const void* photons, int stored)

@@ -26,7 +26,8 @@ struct PhotonMapDevice {
 
 // active (may be NULL): per-query float4 whose .w == 0 marks a query to skip (its irradiance is written as 0).
 cudaError_t photon_gather_launch(const PhotonMapDevice& pm, const float* d_pos3, const float* d_normal3, size_t n,
-                                 float max_dist, int k, float* d_irrad3, cudaStream_t st, const float4* active = nullptr);
+                                 float max_dist, int k, float* d_irrad3, cudaStream_t st, const float4* active = nullptr,
+                                 const uint32_t* d_n = nullptr);
 
 }  // namespace mirogpu
 #endif

@@ -48,10 +48,11 @@ int PhotonMapDevice::upload(const void* photons28, int n, std::string& err)
 
 __global__ void __launch_bounds__(128) k_photon_gather(const float4* __restrict__ photons, const float* __restrict__ tables, int stored,
                                                        int half_stored, const float* __restrict__ pos3, const float* __restrict__ nrm3,
-                                                       const float4* __restrict__ active, size_t n, float max_dist, int kmax,
-                                                       float* __restrict__ irr3)
+                                                       const float4* __restrict__ active, size_t n, const uint32_t* __restrict__ d_n,
+                                                       float max_dist, int kmax, float* __restrict__ irr3)
 {
     const size_t q = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (d_n) n = min(n, (size_t)*d_n);
     if (q >= n) return;
     if (active && active[q].w == 0.f) { irr3[3 * q] = irr3[3 * q + 1] = irr3[3 * q + 2] = 0.f; return; }
     const float px = pos3[3 * q], py = pos3[3 * q + 1], pz = pos3[3 * q + 2];
@@ -143,12 +144,12 @@ __global__ void __launch_bounds__(128) k_photon_gather(const float4* __restrict_
 }
 
 cudaError_t photon_gather_launch(const PhotonMapDevice& pm, const float* d_pos3, const float* d_normal3, size_t n, float max_dist,
-                                 int k, float* d_irrad3, cudaStream_t st, const float4* active)
+                                 int k, float* d_irrad3, cudaStream_t st, const float4* active, const uint32_t* d_n)
 {
     if (n == 0) return cudaSuccess;
     if (!pm.d_photons) return cudaMemsetAsync(d_irrad3, 0, n * 12, st);   // empty map: zero irradiance, like a map with no photons
     k_photon_gather<<<(unsigned)((n + 127) / 128), 128, 0, st>>>(pm.d_photons, pm.d_tables, pm.stored, pm.half_stored, d_pos3, d_normal3,
-                                                                  active, n, max_dist, k, d_irrad3);
+                                                                  active, n, d_n, max_dist, k, d_irrad3);
     return cudaGetLastError();
 }
 

@@ -9,8 +9,8 @@ namespace mirogpu {
 
 // Device buffers reused across render calls on one handle (grown on demand, never shrunk).
 struct RenderScratch {
-    void* buf[12] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
-    size_t cap[12] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
+    void* buf[16] = {};
+    size_t cap[16] = {};
     cudaError_t ensure(int i, size_t bytes)
     {
         if (cap[i] >= bytes) return cudaSuccess;
@@ -21,7 +21,7 @@ struct RenderScratch {
     }
     void release()
     {
-        for (int i = 0; i < 12; ++i) { cudaFree(buf[i]); buf[i] = nullptr; cap[i] = 0; }
+        for (int i = 0; i < 16; ++i) { cudaFree(buf[i]); buf[i] = nullptr; cap[i] = 0; }
     }
 };
 

@@ -29,7 +29,14 @@ struct WaveParams {
     uint32_t seed, sample;
     uint32_t cap;          // queue capacity
     int width, first_row, row_stride;   // local pixel index -> frame pixel (for shard-independent random numbers)
+    uint32_t npix;                      // local pixels; accumulation planes are [sample in batch][pixel][rgb]
+    uint32_t sample_base;               // first sample of this batch
 };
+
+// weight.w carries (depth left | sample-in-batch << 8) as integer bits
+__device__ __forceinline__ float pack_ds(int depth, uint32_t sample) { return __uint_as_float(((uint32_t)depth & 0xffu) | (sample << 8)); }
+__device__ __forceinline__ int unpack_depth(float w) { return (int)(__float_as_uint(w) & 0xffu); }
+__device__ __forceinline__ uint32_t unpack_sample(float w) { return __float_as_uint(w) >> 8; }
 
 // queue layout (SoA)
 struct Queue {
@@ -40,14 +47,17 @@ struct Queue {
 };
 
 __global__ void __launch_bounds__(256) k_render_primary(CameraBasis cb, int width, int height, int row_begin, int row_stride,
-                                                         int nrows_local, int jitter, uint32_t seed, uint32_t sample, int max_depth, Queue q)
+                                                         int nrows_local, int jitter, uint32_t seed, uint32_t sample_base, uint32_t nsamples,
+                                                         int max_depth, Queue q)
 {
     const size_t npix = (size_t)nrows_local * width;
     const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= npix) return;
-    const int x = (int)(i % width), y = row_begin + (int)(i / width) * row_stride;
+    if (i >= npix * nsamples) return;
+    const uint32_t sb = (uint32_t)(i / npix);
+    const size_t lp = i - (size_t)sb * npix;
+    const int x = (int)(lp % width), y = row_begin + (int)(lp / width) * row_stride;
     float dx = 0.5f, dy = 0.5f;
-    if (jitter) uniform2(seed, (uint32_t)((size_t)y * width + x), sample, RNG_DIM_PIXEL, dx, dy);
+    if (jitter) uniform2(seed, (uint32_t)((size_t)y * width + x), sample_base + sb, RNG_DIM_PIXEL, dx, dy);
     const float U = xadd(cb.left, xmul(xsub(cb.right, cb.left), xdiv(xadd((float)x, dx), (float)width)));
     const float V = xadd(cb.bottom, xmul(xsub(cb.top, cb.bottom), xdiv(xadd((float)y, dy), (float)height)));
     float d[3];
@@ -57,14 +67,14 @@ __global__ void __launch_bounds__(256) k_render_primary(CameraBasis cb, int widt
     float4* o = reinterpret_cast<float4*>(q.rays + i);
     o[0] = make_float4(cb.eye[0], cb.eye[1], cb.eye[2], 0.0f);
     o[1] = make_float4(xmul(d[0], inv), xmul(d[1], inv), xmul(d[2], inv), MIROGPU_TMAX);
-    q.pix[i] = (uint32_t)i;
-    q.weight[i] = make_float4(1.f, 1.f, 1.f, (float)max_depth);
+    q.pix[i] = (uint32_t)lp;
+    q.weight[i] = make_float4(1.f, 1.f, 1.f, pack_ds(max_depth, sb));
 }
 
 __device__ __forceinline__ float dot3(const float a[3], const float b[3]) { return a[0] * b[0] + a[1] * b[1] + a[2] * b[2]; }
 
 __device__ __forceinline__ void push_item(const WaveParams& p, Queue& next, uint32_t* next_count, uint32_t* dropped, const float o[3],
-                                          const float d[3], uint32_t pixel, float wr, float wg, float wb, float depth)
+                                          const float d[3], uint32_t pixel, float wr, float wg, float wb, float packed_depth_sample)
 {
     if (!(wr > 0.f || wg > 0.f || wb > 0.f)) return;
     const uint32_t slot = atomicAdd(next_count, 1u);
@@ -73,19 +83,22 @@ __device__ __forceinline__ void push_item(const WaveParams& p, Queue& next, uint
     r[0] = make_float4(o[0], o[1], o[2], 0.0f);
     r[1] = make_float4(d[0], d[1], d[2], MIROGPU_TMAX);
     next.pix[slot] = pixel;
-    next.weight[slot] = make_float4(wr, wg, wb, depth);
+    next.weight[slot] = make_float4(wr, wg, wb, packed_depth_sample);
 }
 
 // One wave of Scene::traceScene bodies.  shadow_* arrays have nlights slots per item.
-__global__ void __launch_bounds__(128) k_shade(WaveParams p, Queue cur, uint32_t n, Queue next, uint32_t* next_count, uint32_t* dropped,
-                                               mirogpu_ray* shadow_rays, float4* shadow_cd, float4* shadow_ch, float* accum,
-                                               float* gather_pos, float* gather_nrm, float4* gather_w)
+__global__ void __launch_bounds__(128) k_shade(WaveParams p, Queue cur, uint32_t n, const uint32_t* __restrict__ d_n, Queue next,
+                                               uint32_t* next_count, uint32_t* dropped, mirogpu_ray* shadow_rays, float4* shadow_cd,
+                                               float4* shadow_ch, float* accum, float* gather_pos, float* gather_nrm, float4* gather_w)
 {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (d_n) n = min(n, *d_n);
     if (i >= n) return;
     const float4 hv = __ldg(reinterpret_cast<const float4*>(cur.hits + i));
     const float4 w = cur.weight[i];
-    const uint32_t pixel = cur.pix[i];
+    const uint32_t lpix = cur.pix[i];
+    const uint32_t sb = unpack_sample(w.w);
+    const uint32_t pixel = sb * p.npix + lpix;     // accumulation plane of this item's sample
     const mirogpu_ray ray = load_ray(cur.rays, i);
     if (gather_w) gather_w[i] = make_float4(0.f, 0.f, 0.f, 0.f);
     if (p.shadows)
@@ -164,17 +177,19 @@ __global__ void __launch_bounds__(128) k_shade(WaveParams p, Queue cur, uint32_t
         gather_w[i] = make_float4(w.x, w.y, w.z, 1.f);
     }
     // ---- secondary rays -------------------------------------------------------------------------------
-    const float depth_left = w.w - 1.0f;          // --depth (Scene.cpp:282)
-    if (depth_left < 0.f) return;
+    const int depth_now = unpack_depth(w.w);
+    const int depth_next = depth_now - 1;          // --depth (Scene.cpp:282)
+    if (depth_next < 0) return;
+    const float depth_left = pack_ds(depth_next, sb);
     if (p.mode == MIROGPU_RENDER_DIFFUSE_BOUNCE) {
-        if (diffuse && w.w == (float)p.max_depth) {   // one cosine-weighted bounce from the first hit only
+        if (diffuse && depth_now == p.max_depth) {   // one cosine-weighted bounce from the first hit only
             float u1, u2;
-            const uint32_t frame_pixel = (uint32_t)(p.first_row + (int)(pixel / (uint32_t)p.width) * p.row_stride) * (uint32_t)p.width + pixel % (uint32_t)p.width;
-            uniform2(p.seed, frame_pixel, p.sample, RNG_DIM_BOUNCE, u1, u2);
+            const uint32_t frame_pixel = (uint32_t)(p.first_row + (int)(lpix / (uint32_t)p.width) * p.row_stride) * (uint32_t)p.width + lpix % (uint32_t)p.width;
+            uniform2(p.seed, frame_pixel, p.sample_base + sb, RNG_DIM_BOUNCE, u1, u2);
             float d[3];
             align_hemisphere(sp.N, xmul(xmul(2.0f, MIRO_PI), u2), asinf(sqrtf(u1)), d);
             const float o[3] = {sp.P[0] + d[0] * MIRO_EPS, sp.P[1] + d[1] * MIRO_EPS, sp.P[2] + d[2] * MIRO_EPS};
-            push_item(p, next, next_count, dropped, o, d, pixel, w.x * m.kd[0], w.y * m.kd[1], w.z * m.kd[2], 0.0f);
+            push_item(p, next, next_count, dropped, o, d, lpix, w.x * m.kd[0], w.y * m.kd[1], w.z * m.kd[2], pack_ds(0, sb));
         }
         return;
     }
@@ -190,7 +205,7 @@ __global__ void __launch_bounds__(128) k_shade(WaveParams p, Queue cur, uint32_t
         dr[0] *= inv; dr[1] *= inv; dr[2] *= inv;
     }
     const float orr[3] = {sp.P[0] + dr[0] * MIRO_EPS, sp.P[1] + dr[1] * MIRO_EPS, sp.P[2] + dr[2] * MIRO_EPS};
-    if (reflective) push_item(p, next, next_count, dropped, orr, dr, pixel, w.x * m.ks[0], w.y * m.ks[1], w.z * m.ks[2], depth_left);
+    if (reflective) push_item(p, next, next_count, dropped, orr, dr, lpix, w.x * m.ks[0], w.y * m.ks[1], w.z * m.ks[2], depth_left);
     if (refractive) {
         // Fresnel coefficient (Ray.h:168-200) and Snell refraction with TIR fallback (Ray.h:202-243)
         float n1, n2, n[3];
@@ -207,28 +222,30 @@ __global__ void __launch_bounds__(128) k_shade(WaveParams p, Queue cur, uint32_t
             const float q = (n1 * cosT - sq) / (n1 * cosT + sq);
             Rs = q * q;
         }
-        if (Rs > 0.01f) push_item(p, next, next_count, dropped, orr, dr, pixel, w.x * m.kt[0] * Rs, w.y * m.kt[1] * Rs, w.z * m.kt[2] * Rs, depth_left);
+        if (Rs > 0.01f) push_item(p, next, next_count, dropped, orr, dr, lpix, w.x * m.kt[0] * Rs, w.y * m.kt[1] * Rs, w.z * m.kt[2] * Rs, depth_left);
         const float ddn = dot3(rd, n);
         const float energy = 1.f - (n1 * n1 * (1.f - ddn * ddn) / (n2 * n2));
         const float tw = 1.f - Rs;
         if (energy < 0.f) {
-            push_item(p, next, next_count, dropped, orr, dr, pixel, w.x * m.kt[0] * tw, w.y * m.kt[1] * tw, w.z * m.kt[2] * tw, depth_left);
+            push_item(p, next, next_count, dropped, orr, dr, lpix, w.x * m.kt[0] * tw, w.y * m.kt[1] * tw, w.z * m.kt[2] * tw, depth_left);
         } else {
             const float se = sqrtf(energy);
             float dt[3];   // the refracted direction is NOT normalised in the reference (Ray.h:233)
 #pragma unroll
             for (int k = 0; k < 3; ++k) dt[k] = n1 * (rd[k] - n[k] * ddn) / n2 - n[k] * se;
             const float ot[3] = {sp.P[0] + dt[0] * MIRO_EPS, sp.P[1] + dt[1] * MIRO_EPS, sp.P[2] + dt[2] * MIRO_EPS};
-            push_item(p, next, next_count, dropped, ot, dt, pixel, w.x * m.kt[0] * tw, w.y * m.kt[1] * tw, w.z * m.kt[2] * tw, depth_left);
+            push_item(p, next, next_count, dropped, ot, dt, lpix, w.x * m.kt[0] * tw, w.y * m.kt[1] * tw, w.z * m.kt[2] * tw, depth_left);
         }
     }
 }
 
 // Phong.cpp:97-114 applied to the traced shadow rays.
 __global__ void __launch_bounds__(256) k_shadow_accumulate(WaveParams p, const mirogpu_ray* __restrict__ srays, const mirogpu_hit* __restrict__ shits,
-                                                           const float4* __restrict__ cd, const float4* __restrict__ ch, size_t n, float* accum)
+                                                           const float4* __restrict__ cd, const float4* __restrict__ ch, size_t n,
+                                                           const uint32_t* __restrict__ d_n, uint32_t mult, float* accum)
 {
     const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (d_n) n = min(n, (size_t)*d_n * mult);
     if (i >= n) return;
     const mirogpu_ray r = load_ray(srays, i);
     if (r.tmax < r.tmin) return;   // no shadow ray in this slot
@@ -251,13 +268,15 @@ __global__ void __launch_bounds__(256) k_shadow_accumulate(WaveParams p, const m
 }
 
 __global__ void __launch_bounds__(256) k_gather_accumulate(const float4* __restrict__ gw, const uint32_t* __restrict__ pix,
-                                                           const float* __restrict__ irr0, const float* __restrict__ irr1, uint32_t n, float* accum)
+                                                           const float* __restrict__ irr0, const float* __restrict__ irr1, uint32_t n,
+                                                           const uint32_t* __restrict__ d_n, const float4* __restrict__ weight, uint32_t npix, float* accum)
 {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (d_n) n = min(n, *d_n);
     if (i >= n) return;
     const float4 w = gw[i];
     if (w.w == 0.f) return;
-    const uint32_t pixel = pix[i];
+    const uint32_t pixel = unpack_sample(weight[i].w) * npix + pix[i];
     for (int k = 0; k < 3; ++k) {
         const float e = (irr0 ? irr0[3 * (size_t)i + k] : 0.f) + (irr1 ? irr1[3 * (size_t)i + k] : 0.f);
         const float wk = k == 0 ? w.x : (k == 1 ? w.y : w.z);
@@ -265,7 +284,17 @@ __global__ void __launch_bounds__(256) k_gather_accumulate(const float4* __restr
     }
 }
 
-// accum (local pixels) -> rgb (full-frame layout), divided by the sample count like Scene.cpp:138.
+// Adds the per-sample planes of one batch, in sample order, into the frame accumulator (deterministic sums).
+__global__ void __launch_bounds__(256) k_fold_planes(const float* __restrict__ planes, uint32_t nsamples, size_t nvals, float* __restrict__ frame)
+{
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= nvals) return;
+    float a = frame[i];
+    for (uint32_t s = 0; s < nsamples; ++s) a += planes[(size_t)s * nvals + i];
+    frame[i] = a;
+}
+
+// frame accumulator (local pixels) -> rgb (full-frame layout), divided by the sample count like Scene.cpp:138.
 __global__ void __launch_bounds__(256) k_resolve_frame(const float* __restrict__ accum, int width, int row_begin, int row_stride, int nrows_local,
                                                         float inv_spp, int spp, float* __restrict__ rgb, float* gmax)
 {
@@ -287,7 +316,45 @@ __global__ void __launch_bounds__(256) k_resolve_frame(const float* __restrict__
     __syncthreads();
     if (threadIdx.x == 0) {
         for (int k = 1; k < 8; ++k) v = fmaxf(v, sm[k]);
-        // float atomic max by CAS on the bit pattern
+        unsigned int* g = reinterpret_cast<unsigned int*>(gmax);   // float atomic max by CAS on the bit pattern
+        unsigned int old = *g;
+        while (v > __uint_as_float(old)) {
+            const unsigned int assumed = old;
+            old = atomicCAS(g, assumed, __float_as_uint(v));
+            if (old == assumed) break;
+        }
+    }
+}
+
+// Scene.cpp:177-202: NaN -> maxIntensity, then sigmoid(6v - 3); optionally Image::Map()'s 8-bit truncation
+// (Image.cpp:47-52).  Works on rows row_begin + j*row_stride of a full-frame float buffer.
+__global__ void __launch_bounds__(256) k_tonemap(float* rgb, unsigned char* rgb8, int width, int row_begin, int row_stride, int nrows_local,
+                                                  const float* gmax)
+{
+    const size_t n = (size_t)nrows_local * width * 3;
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const size_t lp = i / 3; const int c = (int)(i % 3);
+    const int x = (int)(lp % width), y = row_begin + (int)(lp / width) * row_stride;
+    const size_t o = 3 * ((size_t)y * width + x) + c;
+    float v = rgb[o];
+    if (v != v) v = *gmax;
+    v = 1.0f / (1.0f + expf(-(6.0f * v - 3.0f)));
+    if (rgb8) { const float m = 255.0f * v; rgb8[o] = m > 255.0f ? 255 : (unsigned char)m; }
+    else rgb[o] = v;
+}
+
+__global__ void __launch_bounds__(256) k_frame_max(const float* __restrict__ rgb, size_t n, float* gmax)
+{
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    float v = -INFINITY;
+    if (i < n) { const float a = rgb[i]; if (a == a) v = a; }
+    for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_down_sync(0xffffffffu, v, o));
+    __shared__ float sm[8];
+    if ((threadIdx.x & 31) == 0) sm[threadIdx.x >> 5] = v;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (int k = 1; k < 8; ++k) v = fmaxf(v, sm[k]);
         unsigned int* g = reinterpret_cast<unsigned int*>(gmax);
         unsigned int old = *g;
         while (v > __uint_as_float(old)) {
@@ -298,21 +365,21 @@ __global__ void __launch_bounds__(256) k_resolve_frame(const float* __restrict__
     }
 }
 
-// Scene.cpp:177-202: NaN -> maxIntensity, then sigmoid(6v - 3).
-__global__ void __launch_bounds__(256) k_tonemap(float* rgb, int width, int row_begin, int row_stride, int nrows_local, const float* gmax)
+#define MIRO_MAX_WAVES 16
+#define MIRO_SAMPLE_BATCH 8
+
+// Adds this batch's secondary wave sizes (counters[1..16]) to the frame's running 64-bit total.
+__global__ void k_sum_wave_counters(const uint32_t* __restrict__ counters, unsigned long long* total)
 {
-    const size_t n = (size_t)nrows_local * width * 3;
-    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    const size_t lp = i / 3; const int c = (int)(i % 3);
-    const int x = (int)(lp % width), y = row_begin + (int)(lp / width) * row_stride;
-    float* q = rgb + 3 * ((size_t)y * width + x) + c;
-    float v = *q;
-    if (v != v) v = *gmax;
-    *q = 1.0f / (1.0f + expf(-(6.0f * v - 3.0f)));
+    unsigned long long s = 0;
+    for (int w = 1; w <= MIRO_MAX_WAVES; ++w) s += counters[w];
+    *total += s;
 }
 
-int render_device(mirogpu_scene* h, const mirogpu_camera& cam, const mirogpu_render_params& rp, float* d_rgb, cudaStream_t st, std::string& err)
+// d_rgb: full-frame float buffer (rows of this shard are written).  d_rgb8 (may be NULL): full-frame 8-bit
+// tone-mapped output (requires rp.tonemap semantics; used by mirogpu_render_rgb8).
+int render_device(mirogpu_scene* h, const mirogpu_camera& cam, const mirogpu_render_params& rp, float* d_rgb, unsigned char* d_rgb8,
+                  cudaStream_t st, std::string& err)
 {
 #define RT(expr)                                                                     \
     do {                                                                             \
@@ -320,33 +387,33 @@ int render_device(mirogpu_scene* h, const mirogpu_camera& cam, const mirogpu_ren
         if (_e != cudaSuccess) { err = std::string(#expr) + ": " + cudaGetErrorString(_e); return _e == cudaErrorMemoryAllocation ? MIROGPU_ERR_OOM : MIROGPU_ERR_CUDA; } \
     } while (0)
     if (rp.width <= 0 || rp.height <= 0 || rp.spp < 1 || rp.row_stride < 1 || rp.row_phase < 0 || rp.row_phase >= rp.row_stride ||
-        rp.row_begin < 0 || rp.row_end > rp.height || rp.row_begin > rp.row_end) { err = "bad render parameters"; return MIROGPU_ERR_INVALID_ARG; }
+        rp.row_begin < 0 || rp.row_end > rp.height || rp.row_begin > rp.row_end || rp.max_depth < 0 || rp.max_depth > 200) { err = "bad render parameters"; return MIROGPU_ERR_INVALID_ARG; }
     if (rp.mode != MIROGPU_RENDER_WHITTED && rp.mode != MIROGPU_RENDER_DIFFUSE_BOUNCE && rp.mode != MIROGPU_RENDER_PRIMARY_ONLY) { err = "unknown render mode"; return MIROGPU_ERR_INVALID_ARG; }
     if (h->nlights > MIRO_MAX_LIGHTS) { err = "too many lights (max 4)"; return MIROGPU_ERR_UNSUPPORTED; }
     std::lock_guard<std::mutex> lk(h->mtx);   // one render at a time per handle (scratch buffers)
     const int first_row = rp.row_begin + rp.row_phase;
     const int nrows = first_row < rp.row_end ? (rp.row_end - first_row + rp.row_stride - 1) / rp.row_stride : 0;
     const size_t npix = (size_t)nrows * rp.width;
-    uint64_t rays_traced = 0, launches = 0;
-    if (npix == 0) { h->last_rays = 0; h->last_launches = 0; return MIROGPU_OK; }
-    if (npix >= (1ull << 31)) { err = "frame too large"; return MIROGPU_ERR_UNSUPPORTED; }
+    h->last_rays = 0; h->last_launches = 0;
+    for (int k = 0; k < 64; ++k) h->h_stats[k] = 0;
+    if (npix == 0) return MIROGPU_OK;
+    const uint32_t batch = (uint32_t)std::min(rp.spp, MIRO_SAMPLE_BATCH);
+    const size_t items0 = npix * batch;
+    if (items0 >= (1ull << 30)) { err = "frame too large"; return MIROGPU_ERR_UNSUPPORTED; }
 
-    // does any material refract?  (shadow rays then need the closest occluder, Phong.cpp:99-113)
-    std::vector<mirogpu_material> hm(h->nmaterials);
-    RT(cudaMemcpyAsync(hm.data(), h->d_materials, hm.size() * sizeof(mirogpu_material), cudaMemcpyDeviceToHost, st));
-    RT(cudaStreamSynchronize(st));
-    bool any_refractive = false, any_specular = false;
-    for (const mirogpu_material& m : hm) {
-        any_refractive |= m.kt[0] > 0.f || m.kt[1] > 0.f || m.kt[2] > 0.f;
-        any_specular |= m.ks[0] > 0.f || m.ks[1] > 0.f || m.ks[2] > 0.f;
-    }
+    const bool any_refractive = h->any_refractive, any_specular = h->any_specular;
     const bool shadows = rp.shadows != 0 && rp.mode != MIROGPU_RENDER_PRIMARY_ONLY && h->nlights > 0;
     const uint32_t nl = std::max<uint32_t>(h->nlights, 1);
-    const size_t cap = npix * (any_refractive ? 4 : (any_specular || rp.mode == MIROGPU_RENDER_DIFFUSE_BOUNCE ? 2 : 1));
+    const bool whitted_secondary = rp.mode == MIROGPU_RENDER_WHITTED && (any_specular || any_refractive);
+    // Wave plan: diffuse-only Whitted frames have exactly one wave, diffuse-bounce frames exactly two (no host
+    // round trip between waves: counts stay on the device); specular scenes read the queue size back each wave.
+    const int static_waves = rp.mode == MIROGPU_RENDER_DIFFUSE_BOUNCE ? 2 : (whitted_secondary ? -1 : 1);
+    const size_t cap = items0 * (any_refractive && whitted_secondary ? 4 : 1);
     const bool use_pm = rp.use_photon_maps && (h->pm[0].stored > 0 || h->pm[1].stored > 0);
 
     RenderScratch& sc = h->scratch;
-    // 0,1: queue A/B rays  2: hits  3,4: pix A/B  5,6: weight A/B  7: shadow rays  8: shadow hits  9: shadow cd+ch  10: accum + counters  11: gather
+    // 0,1: queue A/B rays  2: hits  3,4: pix A/B  5,6: weight A/B  7: shadow rays  8: shadow hits  9: shadow cd+ch
+    // 10: frame accumulator + counters  11: gather  12: per-sample planes
     RT(sc.ensure(0, cap * sizeof(mirogpu_ray))); RT(sc.ensure(1, cap * sizeof(mirogpu_ray)));
     RT(sc.ensure(2, cap * sizeof(mirogpu_hit)));
     RT(sc.ensure(3, cap * 4)); RT(sc.ensure(4, cap * 4));
@@ -354,10 +421,14 @@ int render_device(mirogpu_scene* h, const mirogpu_camera& cam, const mirogpu_ren
     if (shadows) {
         RT(sc.ensure(7, cap * nl * sizeof(mirogpu_ray))); RT(sc.ensure(8, cap * nl * sizeof(mirogpu_hit))); RT(sc.ensure(9, cap * nl * 32));
     }
-    RT(sc.ensure(10, npix * 12 + 64));
+    const size_t frame_bytes = (npix * 12 + 15) / 16 * 16;
+    RT(sc.ensure(10, frame_bytes + 256));
+    RT(sc.ensure(12, items0 * 12));
     if (use_pm) RT(sc.ensure(11, cap * (12 + 12 + 16 + 12 + 12)));
-    float* accum = reinterpret_cast<float*>(sc.buf[10]);
-    uint32_t* counters = reinterpret_cast<uint32_t*>(reinterpret_cast<char*>(sc.buf[10]) + npix * 12);   // [0] next count [1] dropped [2] gmax
+    float* frame = reinterpret_cast<float*>(sc.buf[10]);
+    uint32_t* counters = reinterpret_cast<uint32_t*>(reinterpret_cast<char*>(sc.buf[10]) + frame_bytes);   // [0..16] wave sizes, [17] dropped, [18] gmax
+    unsigned long long* d_total = reinterpret_cast<unsigned long long*>(counters + 20);                     // secondary items of the whole frame
+    float* planes = reinterpret_cast<float*>(sc.buf[12]);
     Queue q[2];
     for (int k = 0; k < 2; ++k) {
         q[k].rays = reinterpret_cast<mirogpu_ray*>(sc.buf[0 + k]); q[k].hits = reinterpret_cast<mirogpu_hit*>(sc.buf[2]);
@@ -379,89 +450,120 @@ int render_device(mirogpu_scene* h, const mirogpu_camera& cam, const mirogpu_ren
     wp.ds = h->ds; wp.mats = h->d_materials; wp.lights = h->d_lights; wp.nlights = h->nlights;
     wp.mode = rp.mode; wp.shadows = shadows ? 1 : 0; wp.max_depth = rp.max_depth; wp.use_pm = use_pm ? 1 : 0;
     for (int k = 0; k < 3; ++k) wp.bg[k] = rp.bg_color[k];
-    wp.seed = rp.seed; wp.cap = (uint32_t)std::min<size_t>(cap, 0xffffffffu);
-    wp.width = rp.width; wp.first_row = first_row; wp.row_stride = rp.row_stride;
+    wp.seed = rp.seed; wp.sample = 0; wp.cap = (uint32_t)cap;
+    wp.width = rp.width; wp.first_row = first_row; wp.row_stride = rp.row_stride; wp.npix = (uint32_t)npix;
     CameraBasis cb;
     camera_basis(cam, rp.width, rp.height, cb);
 
-    RT(cudaMemsetAsync(accum, 0, npix * 12 + 64, st));
-    uint32_t total_dropped = 0;
-    for (int s = 0; s < rp.spp; ++s) {
-        wp.sample = (uint32_t)s;
+    uint64_t launches = 0;
+    uint32_t* hs = h->h_stats;          // pinned: [0] rays traced (filled at the end), [1] launches
+    uint64_t host_rays = 0;             // exact when counts are known on the host, else completed from device counters
+    RT(cudaMemsetAsync(frame, 0, frame_bytes + 256, st));
+    for (uint32_t s0 = 0; s0 < (uint32_t)rp.spp; s0 += batch) {
+        const uint32_t nb = std::min<uint32_t>(batch, (uint32_t)rp.spp - s0);
+        const size_t items = npix * nb;
+        wp.sample_base = s0;
+        RT(cudaMemsetAsync(planes, 0, items * 12, st));
+        RT(cudaMemsetAsync(counters, 0, 18 * 4, st));
         int cur = 0;
-        k_render_primary<<<(unsigned)((npix + 255) / 256), 256, 0, st>>>(cb, rp.width, rp.height, first_row, rp.row_stride, nrows, rp.jitter, rp.seed,
-                                                                          (uint32_t)s, rp.max_depth, q[cur]);
+        k_render_primary<<<(unsigned)((items + 255) / 256), 256, 0, st>>>(cb, rp.width, rp.height, first_row, rp.row_stride, nrows, rp.jitter, rp.seed,
+                                                                           s0, nb, rp.max_depth, q[cur]);
         launches++;
-        uint32_t n = (uint32_t)npix;
-        for (int wave = 0; n > 0 && wave <= rp.max_depth + 1; ++wave) {
-            // -- closest hit for the wave
-            RT(dispatch_trace(h, q[cur].rays, n, q[cur].hits, MIROGPU_CLOSEST_HIT, st));
-            launches++; rays_traced += n;
-            RT(cudaMemsetAsync(counters, 0, 8, st));
-            k_shade<<<(n + 127) / 128, 128, 0, st>>>(wp, q[cur], n, q[cur ^ 1], counters, counters + 1, srays, scd, sch, accum, gpos, gnrm, gw);
-            launches++;
+        size_t bound = items;
+        for (int wave = 0; wave < MIRO_MAX_WAVES && wave <= rp.max_depth; ++wave) {
+            const uint32_t* d_n = wave == 0 ? nullptr : counters + wave;
+            RT(dispatch_trace(h, q[cur].rays, bound, q[cur].hits, MIROGPU_CLOSEST_HIT, st, d_n, 1));
+            k_shade<<<(unsigned)((bound + 127) / 128), 128, 0, st>>>(wp, q[cur], (uint32_t)bound, d_n, q[cur ^ 1], counters + wave + 1, counters + 17,
+                                                                      srays, scd, sch, planes, gpos, gnrm, gw);
+            launches += 2;
             if (shadows) {
-                const size_t ns = (size_t)n * nl;
-                RT(dispatch_trace(h, srays, ns, shits, any_refractive ? MIROGPU_CLOSEST_HIT : MIROGPU_ANY_HIT, st));
-                k_shadow_accumulate<<<(unsigned)((ns + 255) / 256), 256, 0, st>>>(wp, srays, shits, scd, sch, ns, accum);
-                launches += 2; rays_traced += ns;
+                const size_t ns = bound * nl;
+                RT(dispatch_trace(h, srays, ns, shits, any_refractive ? MIROGPU_CLOSEST_HIT : MIROGPU_ANY_HIT, st, d_n, nl));
+                k_shadow_accumulate<<<(unsigned)((ns + 255) / 256), 256, 0, st>>>(wp, srays, shits, scd, sch, ns, d_n, nl, planes);
+                launches += 2;
             }
             if (use_pm) {
-                const float4* gwc = gw;
-                if (h->pm[0].stored > 0) { RT(photon_gather_launch(h->pm[0], gpos, gnrm, n, 1e10f, 500, girr0, st, gwc)); launches++; }
-                if (h->pm[1].stored > 0) { RT(photon_gather_launch(h->pm[1], gpos, gnrm, n, 1e10f, 500, girr1, st, gwc)); launches++; }
-                k_gather_accumulate<<<(n + 255) / 256, 256, 0, st>>>(gwc, q[cur].pix, h->pm[0].stored > 0 ? girr0 : nullptr,
-                                                                       h->pm[1].stored > 0 ? girr1 : nullptr, n, accum);
+                if (h->pm[0].stored > 0) { RT(photon_gather_launch(h->pm[0], gpos, gnrm, bound, 1e10f, 500, girr0, st, gw, d_n)); launches++; }
+                if (h->pm[1].stored > 0) { RT(photon_gather_launch(h->pm[1], gpos, gnrm, bound, 1e10f, 500, girr1, st, gw, d_n)); launches++; }
+                k_gather_accumulate<<<(unsigned)((bound + 255) / 256), 256, 0, st>>>(gw, q[cur].pix, h->pm[0].stored > 0 ? girr0 : nullptr,
+                                                                                      h->pm[1].stored > 0 ? girr1 : nullptr, (uint32_t)bound, d_n,
+                                                                                      q[cur].weight, (uint32_t)npix, planes);
                 launches++;
             }
-            uint32_t hc[2];
-            RT(cudaMemcpyAsync(hc, counters, 8, cudaMemcpyDeviceToHost, st));
-            RT(cudaStreamSynchronize(st));
-            total_dropped += hc[1];
-            n = std::min<uint32_t>(hc[0], wp.cap);
             cur ^= 1;
+            if (static_waves > 0) {
+                if (wave + 1 >= static_waves) break;
+                bound = std::min(cap, bound);            // the next wave holds at most one item per item of this one
+            } else {
+                uint32_t next_n = 0;
+                RT(cudaMemcpyAsync(&next_n, counters + wave + 1, 4, cudaMemcpyDeviceToHost, st));
+                RT(cudaStreamSynchronize(st));
+                if (next_n == 0) break;
+                bound = std::min<size_t>(cap, next_n);
+            }
         }
+        k_fold_planes<<<(unsigned)((npix * 3 + 255) / 256), 256, 0, st>>>(planes, nb, npix * 3, frame);
+        launches++;
+        k_sum_wave_counters<<<1, 1, 0, st>>>(counters, d_total);
+        launches++;
+        host_rays += items * (shadows ? 1 + nl : 1);
     }
-    float* gmax = reinterpret_cast<float*>(counters + 2);
+    float* gmax = reinterpret_cast<float*>(counters + 18);
     const float ninf = -INFINITY;
     RT(cudaMemcpyAsync(gmax, &ninf, 4, cudaMemcpyHostToDevice, st));
     const size_t nvals = npix * 3;
-    k_resolve_frame<<<(unsigned)((nvals + 255) / 256), 256, 0, st>>>(accum, rp.width, first_row, rp.row_stride, nrows, 1.0f / (float)rp.spp, rp.spp, d_rgb, gmax);
+    k_resolve_frame<<<(unsigned)((nvals + 255) / 256), 256, 0, st>>>(frame, rp.width, first_row, rp.row_stride, nrows, 1.0f / (float)rp.spp, rp.spp, d_rgb, gmax);
     launches++;
-    if (rp.tonemap) {
-        k_tonemap<<<(unsigned)((nvals + 255) / 256), 256, 0, st>>>(d_rgb, rp.width, first_row, rp.row_stride, nrows, gmax);
+    if (rp.tonemap || d_rgb8) {
+        k_tonemap<<<(unsigned)((nvals + 255) / 256), 256, 0, st>>>(d_rgb, d_rgb8, rp.width, first_row, rp.row_stride, nrows, gmax);
         launches++;
     }
     RT(cudaGetLastError());
-    h->last_rays = rays_traced; h->last_launches = launches;
-    (void)total_dropped;
+    // rays: the primary wave is known here; the secondary waves were counted on the device and land in pinned
+    // host memory (valid once the caller has synchronised the stream) for mirogpu_last_call_stats
+    RT(cudaMemcpyAsync(hs, d_total, 8, cudaMemcpyDeviceToHost, st));
+    h->last_rays = host_rays; h->last_launches = launches;
+    h->stats_batches = 1;
+    h->stats_mult = shadows ? 1 + nl : 1;
     return MIROGPU_OK;
 #undef RT
 }
 
-int render_host(mirogpu_scene* h, const mirogpu_camera& cam, const mirogpu_render_params& rp, float* rgb_out, std::string& err)
+int render_host(mirogpu_scene* h, const mirogpu_camera& cam, const mirogpu_render_params& rp, float* rgb_out, unsigned char* rgb8_out,
+                std::string& err)
 {
     if (rp.width <= 0 || rp.height <= 0) { err = "bad render parameters"; return MIROGPU_ERR_INVALID_ARG; }
-    const size_t bytes = (size_t)rp.width * rp.height * 12;
-    float* d_rgb = nullptr;
-    cudaError_t e = cudaMalloc(&d_rgb, bytes);
-    if (e != cudaSuccess) { err = std::string("cudaMalloc framebuffer: ") + cudaGetErrorString(e); return MIROGPU_ERR_OOM; }
-    cudaStream_t st = cudaStreamPerThread;
-    int rc = render_device(h, cam, rp, d_rgb, st, err);
-    if (rc == MIROGPU_OK) {
-        // only this call's rows are defined on the device; copy row by row when sharded, in one piece otherwise
-        if (rp.row_stride == 1 && rp.row_begin == 0 && rp.row_end == rp.height) e = cudaMemcpyAsync(rgb_out, d_rgb, bytes, cudaMemcpyDeviceToHost, st);
-        else {
-            const size_t rowb = (size_t)rp.width * 12;
-            e = cudaMemcpy2DAsync(rgb_out + (size_t)(rp.row_begin + rp.row_phase) * rp.width * 3, rowb * rp.row_stride,
-                                  d_rgb + (size_t)(rp.row_begin + rp.row_phase) * rp.width * 3, rowb * rp.row_stride, rowb,
-                                  (rp.row_end - rp.row_begin - rp.row_phase + rp.row_stride - 1) / rp.row_stride, cudaMemcpyDeviceToHost, st);
-        }
-        if (e == cudaSuccess) e = cudaStreamSynchronize(st);
-        if (e != cudaSuccess) { err = std::string("framebuffer copy: ") + cudaGetErrorString(e); rc = MIROGPU_ERR_CUDA; }
+    const size_t npx = (size_t)rp.width * rp.height;
+    cudaError_t e;
+    {
+        std::lock_guard<std::mutex> lk(h->mtx);
+        e = h->scratch.ensure(13, npx * 12);
+        if (e == cudaSuccess && rgb8_out) e = h->scratch.ensure(14, npx * 3);
     }
-    cudaFree(d_rgb);
-    return rc;
+    if (e != cudaSuccess) { err = std::string("cudaMalloc framebuffer: ") + cudaGetErrorString(e); return MIROGPU_ERR_OOM; }
+    float* d_rgb = reinterpret_cast<float*>(h->scratch.buf[13]);
+    unsigned char* d_rgb8 = rgb8_out ? reinterpret_cast<unsigned char*>(h->scratch.buf[14]) : nullptr;
+    cudaStream_t st = cudaStreamPerThread;
+    int rc = render_device(h, cam, rp, d_rgb, d_rgb8, st, err);
+    if (rc != MIROGPU_OK) return rc;
+    // only this call's rows are defined on the device; copy them (one piece for a full frame)
+    const bool full = rp.row_stride == 1 && rp.row_begin == 0 && rp.row_end == rp.height;
+    const int first_row = rp.row_begin + rp.row_phase;
+    const int nrows = first_row < rp.row_end ? (rp.row_end - first_row + rp.row_stride - 1) / rp.row_stride : 0;
+    if (rgb8_out) {
+        const size_t rowb = (size_t)rp.width * 3;
+        if (full) e = cudaMemcpyAsync(rgb8_out, d_rgb8, npx * 3, cudaMemcpyDeviceToHost, st);
+        else e = cudaMemcpy2DAsync(rgb8_out + (size_t)first_row * rowb, rowb * rp.row_stride, d_rgb8 + (size_t)first_row * rowb, rowb * rp.row_stride, rowb,
+                                   nrows, cudaMemcpyDeviceToHost, st);
+    } else {
+        const size_t rowb = (size_t)rp.width * 12;
+        if (full) e = cudaMemcpyAsync(rgb_out, d_rgb, npx * 12, cudaMemcpyDeviceToHost, st);
+        else e = cudaMemcpy2DAsync(reinterpret_cast<char*>(rgb_out) + (size_t)first_row * rowb, rowb * rp.row_stride,
+                                   reinterpret_cast<char*>(d_rgb) + (size_t)first_row * rowb, rowb * rp.row_stride, rowb, nrows, cudaMemcpyDeviceToHost, st);
+    }
+    if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+    if (e != cudaSuccess) { err = std::string("framebuffer copy: ") + cudaGetErrorString(e); return MIROGPU_ERR_CUDA; }
+    return MIROGPU_OK;
 }
 
 }  // namespace

@@ -224,6 +224,83 @@ MIRO_HD void trace_bvh2(const float4* __restrict__ nodes, const float4* __restri
     }
 }
 
+// ---- BVH2, resumable form -----------------------------------------------------------------------------------
+// Same walk as trace_bvh2, but all per-ray state lives in Bvh2State and bvh2_run() returns after a budget of
+// node visits (checked at leaf boundaries).  The persistent kernel with ray replacement runs every lane for one
+// such quantum, then refills the lanes whose ray finished and resumes the others where they stopped.
+#define MIRO_BVH2_DONE ((int32_t)0x80000000)
+
+struct Bvh2State {
+    float idx, idy, idz, oodx, oody, oodz;
+    int32_t node;
+    int sp;
+};
+
+MIRO_HD void bvh2_begin(const mirogpu_ray& r, Bvh2State& st, BestHit& best)
+{
+    st.idx = safe_rcp(r.dx); st.idy = safe_rcp(r.dy); st.idz = safe_rcp(r.dz);
+    st.oodx = r.ox * st.idx; st.oody = r.oy * st.idy; st.oodz = r.oz * st.idz;
+    st.sp = 0;
+    st.node = (r.tmax >= r.tmin) ? 0 : MIRO_BVH2_DONE;   // an empty interval (or NaN bounds) never hits
+    best.t = r.tmax; best.prim = MIROGPU_MISS; best.beta = 0.f; best.gamma = 0.f;
+}
+
+// Returns true when the ray is finished, false when the budget ran out (state saved for the next call).
+template <bool ANY>
+MIRO_HD bool bvh2_run(const float4* __restrict__ nodes, const float4* __restrict__ tris, const mirogpu_ray& r, Bvh2State& st,
+                      int32_t* __restrict__ stack, BestHit& best, int budget)
+{
+    int32_t node = st.node;
+    int sp = st.sp;
+    const float idx = st.idx, idy = st.idy, idz = st.idz, oodx = st.oodx, oody = st.oody, oodz = st.oodz;
+    for (;;) {
+        while (node >= 0) {
+            const float4 n0 = ldg(nodes + 4 * node + 0);
+            const float4 n1 = ldg(nodes + 4 * node + 1);
+            const float4 nz = ldg(nodes + 4 * node + 2);
+            const float4 lk = ldg(nodes + 4 * node + 3);
+            --budget;
+            const float c0lox = n0.x * idx - oodx, c0hix = n0.y * idx - oodx;
+            const float c0loy = n0.z * idy - oody, c0hiy = n0.w * idy - oody;
+            const float c0loz = nz.x * idz - oodz, c0hiz = nz.y * idz - oodz;
+            const float c1lox = n1.x * idx - oodx, c1hix = n1.y * idx - oodx;
+            const float c1loy = n1.z * idy - oody, c1hiy = n1.w * idy - oody;
+            const float c1loz = nz.z * idz - oodz, c1hiz = nz.w * idz - oodz;
+            const float t0n = fmaxf(fmaxf(fminf(c0lox, c0hix), fminf(c0loy, c0hiy)), fmaxf(fminf(c0loz, c0hiz), r.tmin));
+            const float t0f = fminf(fminf(fmaxf(c0lox, c0hix), fmaxf(c0loy, c0hiy)), fminf(fmaxf(c0loz, c0hiz), best.t));
+            const float t1n = fmaxf(fmaxf(fminf(c1lox, c1hix), fminf(c1loy, c1hiy)), fmaxf(fminf(c1loz, c1hiz), r.tmin));
+            const float t1f = fminf(fminf(fmaxf(c1lox, c1hix), fmaxf(c1loy, c1hiy)), fminf(fmaxf(c1loz, c1hiz), best.t));
+            const bool h0 = t0n <= t0f, h1 = t1n <= t1f;
+            const int32_t l0 = (int32_t)f2u(lk.x), l1 = (int32_t)f2u(lk.y);
+            if (!h0 && !h1) {
+                if (sp == 0) { st.node = MIRO_BVH2_DONE; return true; }
+                node = stack[--sp];
+            } else {
+                node = h0 ? l0 : l1;
+                if (h0 && h1) {
+                    int32_t other = l1;
+                    if (t1n < t0n) { node = l1; other = l0; }
+                    stack[sp++] = other;
+                }
+            }
+        }
+        {
+            const uint32_t ref = (uint32_t)~node;
+            const uint32_t first = ref >> 3, count = (ref & 7u) + 1u;
+            for (uint32_t i = 0; i < count; ++i) {
+                const float4 v0 = ldg(tris + 3 * (first + i) + 0);
+                const float4 v1 = ldg(tris + 3 * (first + i) + 1);
+                const float4 v2 = ldg(tris + 3 * (first + i) + 2);
+                const bool acc = tri_test(v0, v1, v2, r, best);
+                if (ANY && acc) { st.node = MIRO_BVH2_DONE; return true; }
+            }
+            if (sp == 0) { st.node = MIRO_BVH2_DONE; return true; }
+            node = stack[--sp];
+            if (budget <= 0) { st.node = node; st.sp = sp; return false; }
+        }
+    }
+}
+
 // ---- CWBVH8 (80-byte nodes, eight 8-bit-quantised child boxes per fetch) --------------------------------
 // Node words (5 x uint4), see Cwbvh8Node in bvh_build.h:
 //   w0 = px, py, pz, (ex | ey<<8 | ez<<16 | imask<<24)

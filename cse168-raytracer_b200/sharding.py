@@ -1,0 +1,50 @@
+"""Screen-space sharding across ranks (one process per GPU) and the framebuffer gather.
+
+The reference parallelises Scene::raytraceImage over image rows with OpenMP dynamic chunks (Scene.cpp:113); here
+rank r of N owns the rows with row % N == r (perfect balance, every row stays a coherent run of pixels), the
+scene is replicated, and the only exchange is one all-gather of the row shards -- NCCL over NVLink on GPUs, gloo
+in the CPU tests.  No torch type crosses the C ABI: the render call gets (row_begin, row_end, row_stride,
+row_phase) = rows_of_rank(...).
+"""
+import torch
+import torch.distributed as dist
+
+
+def rows_of_rank(height, world, rank):
+    """Render-parameter row tuple for rank `rank` of `world`, and how many rows that is."""
+    return (0, height, world, rank), len(range(rank, height, world))
+
+
+def max_rows(height, world):
+    return (height + world - 1) // world
+
+
+def gather_rows(local_rows, height, world, rank, out=None, group=None):
+    """local_rows: (rows_of_this_rank, width, C) tensor.  Returns the full (height, width, C) frame on every rank.
+    Shards are padded to the same row count so a single all_gather_into_tensor moves everything."""
+    if world == 1:
+        if out is None:
+            return local_rows
+        out.copy_(local_rows)
+        return out
+    nmax = max_rows(height, world)
+    width, ch = local_rows.shape[1], local_rows.shape[2]
+    send = torch.zeros((nmax, width, ch), dtype=local_rows.dtype, device=local_rows.device)
+    send[: local_rows.shape[0]].copy_(local_rows)
+    recv = torch.empty((world * nmax, width, ch), dtype=local_rows.dtype, device=local_rows.device)   # concatenated along dim 0
+    dist.all_gather_into_tensor(recv, send, group=group)
+    recv = recv.view(world, nmax, width, ch)
+    if out is None:
+        out = torch.empty((height, width, ch), dtype=local_rows.dtype, device=local_rows.device)
+    for r in range(world):
+        k = len(range(r, height, world))
+        out[r::world].copy_(recv[r, :k])
+    return out
+
+
+def reduce_max(value, group=None):
+    """Max over ranks of one float (the NaN-replacement intensity of the tone map, Scene.cpp:157-164)."""
+    if not dist.is_initialized() or dist.get_world_size(group) == 1:
+        return value
+    dist.all_reduce(value, op=dist.ReduceOp.MAX, group=group)
+    return value

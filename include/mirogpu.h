@@ -11,7 +11,7 @@
  *                                  (= Scene::trace with no unbounded objects,         Scene.cpp:214-268)
  *   mirogpu_generate_primary    <- Camera::eyeRay                                     Camera.cpp:104-161
  *   mirogpu_generate_bounce     <- Ray::diffuse / Ray::random                         Ray.h:109-140, Utility.h:34-50
- *   mirogpu_render              <- Scene::raytraceImage + Scene::traceScene           Scene.cpp:93-212, 270-346
+ *   mirogpu_render(_rgb8)       <- Scene::raytraceImage + Scene::traceScene           Scene.cpp:93-212, 270-346
  *                                  + Phong::shade's light loop and shadow query       Phong.cpp:44-161
  *   mirogpu_photon_upload       <- the balanced Photon array Photon_map::balance leaves   PhotonMap.cpp:314-359
  *   mirogpu_photon_gather       <- Photon_map::irradiance_estimate / locate_photons   PhotonMap.cpp:81-243
@@ -184,7 +184,8 @@ int mirogpu_intersect_batch_device(mirogpu_handle h, const mirogpu_ray* d_rays, 
 /* Same query through the instrumented kernel; counters are accumulated into *c (host struct). */
 int mirogpu_intersect_batch_counted(mirogpu_handle h, const mirogpu_ray* rays, size_t n, mirogpu_hit* hits,
                                     int mode, mirogpu_counters* c);
-/* Kernel variant selection for measurement (0 = default persistent kernel). */
+/* Kernel variant selection for measurement: 0 = persistent warps with ray replacement (default; BVH2) /
+ * 32-ray tickets (CWBVH8), 1 = one thread per ray, 2 = persistent warps with plain 32-ray tickets. */
 int mirogpu_set_kernel_variant(mirogpu_handle h, int variant);
 
 /* Reconstructs P, N (normalised as Scene::trace does for UV materials, Scene.cpp:262) and material id
@@ -213,6 +214,12 @@ int mirogpu_rng_uniforms(uint32_t seed, uint32_t sample, uint32_t dimension, siz
 /* ---- whole-frame render (Scene::raytraceImage) -------------------------------------------------------- */
 /* rgb_out: HOST buffer, width*height*3 floats, row 0 = bottom.  Only the rows of this call's shard are written. */
 int mirogpu_render(mirogpu_handle h, const mirogpu_camera* cam, const mirogpu_render_params* p, float* rgb_out);
+/* Same frame as the reference's Image holds it (Image.h: 3 bytes per pixel): tone-mapped on the device
+ * (Scene.cpp:177-202) and truncated to 8 bits like Image::setPixel's Map() (Image.cpp:47-52).
+ * rgb8_out: HOST buffer, width*height*3 bytes, row 0 = bottom. */
+int mirogpu_render_rgb8(mirogpu_handle h, const mirogpu_camera* cam, const mirogpu_render_params* p, uint8_t* rgb8_out);
+/* Tone map + 8-bit conversion of a complete DEVICE float frame (after a multi-GPU gather). */
+int mirogpu_tonemap_rgb8_device(mirogpu_handle h, const float* d_rgb, int width, int height, uint8_t* d_rgb8, void* cuda_stream);
 /* d_rgb: DEVICE buffer of the same shape.  rays_traced (host, may be NULL) receives the ray count after
  * the stream is synchronised by the caller only if sync != 0. */
 int mirogpu_render_device(mirogpu_handle h, const mirogpu_camera* cam, const mirogpu_render_params* p, float* d_rgb,

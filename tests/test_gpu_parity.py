@@ -69,7 +69,7 @@ def test_closest_hit_equals_exhaustive_search(host_scenes, oracle_scene, name, l
     V = O.dump_triangles()[:, :9].reshape(-1, 3)
     rays = np.concatenate([O.eye_rays(128, 128), random_rays(20000, V.min(0), V.max(0), 42)])
     bt, bid, bP, bN = O.trace_brute(rays)
-    for variant in (0, 1):
+    for variant in (0, 1, 2):
         S.set_kernel_variant(variant)
         hits = S.intersect(rays)
         assert np.array_equal(ids_of(hits), bid)
@@ -284,8 +284,9 @@ def test_full_size_properties_bunny20(host_scenes, pkg):
         anyh = S.intersect(rays, mode=pkg.ANY_HIT)
         assert np.array_equal(ids_of(anyh) >= 0, hit)
         # (4) both layouts and both kernel variants give the same answer
-        S.set_kernel_variant(1)
-        assert np.array_equal(S.intersect(rays), hits)
+        for variant in (1, 2):
+            S.set_kernel_variant(variant)
+            assert np.array_equal(S.intersect(rays), hits)
         S.set_kernel_variant(0)
         # (5) barycentrics of accepted hits respect the reference's epsilon slop
         assert (hits["beta"][hit] >= -1e-4).all() and (hits["gamma"][hit] >= -1e-4).all()

@@ -55,6 +55,13 @@ def test_whitted_render_matches_reference_semantics(pkg, scenes, oracle, name, s
     H.set_render(spp=1, jitter=0, mode=pkg.RENDER_WHITTED, shadows=1)
     u8 = H.render(w, h)
     assert (np.abs(u8.astype(int) - b.astype(int)) <= 2).mean() > 0.9995
+    # the same 8-bit frame straight from the C ABI, and the device tone map of a float frame
+    u8b = S.render_rgb8(H.camera(), S.render_params(w, h, mode=pkg.RENDER_WHITTED, tonemap=1))
+    assert np.array_equal(u8, u8b)
+    d_rgb = torch.from_numpy(img).cuda(); d_u8 = torch.empty((h, w, 3), dtype=torch.uint8, device="cuda")
+    S.tonemap_rgb8_device(d_rgb, d_u8)
+    torch.cuda.synchronize()
+    assert np.array_equal(d_u8.cpu().numpy(), u8b)
     # no shadows == the reference's -DDISABLE_SHADOWS build: brighter or equal everywhere
     p2 = S.render_params(w, h, mode=pkg.RENDER_WHITTED, tonemap=0, shadows=0)
     img2 = S.render(H.camera(), p2)

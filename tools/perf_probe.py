@@ -33,7 +33,7 @@ def main(scene="bunny20", w=1920, h=1080, iters=10):
         d_hits = torch.empty((n, 4), dtype=torch.float32, device="cuda")
         d_b = torch.empty((n, 8), dtype=torch.float32, device="cuda")
         d_h2 = torch.empty((n, 4), dtype=torch.float32, device="cuda")
-        for variant in (0, 1):
+        for variant in (0, 2, 1):
             S.set_kernel_variant(variant)
             ev = [torch.cuda.Event(enable_timing=True) for _ in range(5)]
             acc = np.zeros(4)
