@@ -6,6 +6,7 @@
 #include <algorithm>
 #include <atomic>
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 #include <limits>
 
@@ -44,6 +45,7 @@ struct Builder {
     std::atomic<uint32_t> num_leaves{0};
     std::atomic<uint32_t> max_depth{0};
     int max_leaf, bins;
+    float trav_cost = 1.0f;     // cost of one node visit relative to one triangle test
 
     void note_depth(uint32_t d)
     {
@@ -108,9 +110,9 @@ struct Builder {
         }
         const float parent_area = box_half_area(box);
         if ((int)n <= max_leaf) {
-            // leaf cost n*Ct vs split cost Ctrav + (sum A_i n_i)/A * Ct, with Ctrav = 1, Ct = 1
+            // leaf cost n*Ct vs split cost Ctrav + (sum A_i n_i)/A * Ct, with Ct = 1
             const float leaf_cost = (float)n;
-            const float split_cost = (best_axis >= 0 && parent_area > 0.f) ? 1.0f + best_cost / parent_area : kInf;
+            const float split_cost = (best_axis >= 0 && parent_area > 0.f) ? trav_cost + best_cost / parent_area : kInf;
             if (leaf_cost <= split_cost) { make_leaf(ni, begin, end, depth); return; }
         }
         uint32_t mid;
@@ -205,6 +207,7 @@ BinaryBvh build_binary_sah(const float* tri_vertices, uint32_t ntris, int max_le
     Builder b;
     b.pb = pb.data(); b.pc = pc.data(); b.idx = out.order.data(); b.nodes = out.nodes.data();
     b.max_leaf = max_leaf; b.bins = bins;
+    if (const char* e = getenv("MIROGPU_CTRAV")) { const float v = (float)atof(e); if (v > 0.f && v < 100.f) b.trav_cost = v; }   // tuning knob
 #pragma omp parallel
 #pragma omp single nowait
     b.build(0, 0, ntris, 0);

@@ -109,24 +109,25 @@ __global__ void __launch_bounds__(128) k_trace_persistent(DeviceScene s, const m
     }
 }
 
-// Persistent warps with ray replacement (BVH2).  Every lane owns one ray's resumable traversal state and runs
-// it for a quantum of node visits; at each quantum boundary a ballot finds the lanes whose ray has finished,
-// ONE atomic claims that many new rays for the warp, a popc-prefix hands each idle lane its ray, and the busy
+// Persistent warps with ray replacement (BVH2).  Every lane owns one ray's resumable traversal state.  All lanes
+// run `rounds` while-while rounds, then a ballot finds the lanes whose ray has finished; they take the next rays
+// of the warp's private pool (256 consecutive rays claimed with ONE global atomic) by popc-prefix, and the busy
 // lanes resume where they stopped.  Incoherent rays differ wildly in cost (sky rays end after 2-3 nodes,
 // interior rays take 50+; rays generated at misses are dead on arrival), so a fixed 32-ray packet runs at the
 // length of its slowest ray with most lanes idle (ncu: 7.4 of 32 threads active per instruction on bounce rays).
-#define MIRO_REFILL_BELOW 12   /* default quantum: node visits per lane between refill points */
+#define MIRO_REFILL_BELOW 2    /* default: while-while rounds per lane between refill points */
+#define MIRO_POOL 256          /* rays claimed per global atomic */
 
 template <bool ANY>
 __global__ void __launch_bounds__(128) k_trace_bvh2_dynamic(DeviceScene s, const mirogpu_ray* __restrict__ rays, size_t n,
                                                             mirogpu_hit* __restrict__ hits, unsigned long long* __restrict__ ticket,
-                                                            int quantum, const uint32_t* __restrict__ d_n, uint32_t mult)
+                                                            int rounds, const uint32_t* __restrict__ d_n, uint32_t mult)
 {
     if (d_n) n = min(n, (size_t)*d_n * mult);
     const unsigned lane = threadIdx.x & 31u;
     const unsigned lt_mask = (1u << lane) - 1u;
     bool active = false, drained = false;
-    size_t my = 0;
+    size_t my = 0, pool_next = 0, pool_end = 0;   // pool_* are warp-uniform
     mirogpu_ray r;
     Bvh2State st;
     BestHit best;
@@ -136,31 +137,36 @@ __global__ void __launch_bounds__(128) k_trace_bvh2_dynamic(DeviceScene s, const
     st.idx = st.idy = st.idz = st.oodx = st.oody = st.oodz = 0.f;
     best.t = 0.f; best.prim = MIROGPU_MISS; best.beta = best.gamma = 0.f;
     for (;;) {
-        // ---- hand new rays to idle lanes (two rounds, so a lane that drew a dead ray gets another) ----
-        for (int round = 0; round < 2 && !drained; ++round) {
+        // ---- hand new rays to idle lanes (two passes, so a lane that drew a dead ray gets another) ----
+        for (int pass = 0; pass < 2; ++pass) {
             const unsigned idle = __ballot_sync(0xffffffffu, !active);
             if (!idle) break;
-            const int leader = __ffs(idle) - 1;
-            unsigned long long base = 0;
-            if ((int)lane == leader) base = atomicAdd(ticket, (unsigned long long)__popc(idle));
-            base = __shfl_sync(0xffffffffu, base, leader);
-            if (base >= n) { drained = true; break; }
+            if (pool_next >= pool_end) {
+                if (drained) break;
+                unsigned long long base = 0;
+                if (lane == 0) base = atomicAdd(ticket, (unsigned long long)MIRO_POOL);
+                base = __shfl_sync(0xffffffffu, base, 0);
+                if (base >= n) { drained = true; break; }
+                pool_next = (size_t)base;
+                pool_end = min((size_t)base + MIRO_POOL, n);
+            }
             if (!active) {
-                const size_t i = (size_t)base + __popc(idle & lt_mask);
-                if (i < n) {
+                const size_t i = pool_next + __popc(idle & lt_mask);
+                if (i < pool_end) {
                     r = load_ray(rays, i);
                     bvh2_begin(r, st, best);
                     if (st.node == MIRO_BVH2_DONE) store_hit(hits, i, best);   // empty interval: answered without traversal
                     else { active = true; my = i; }
                 }
             }
+            pool_next = min(pool_next + (size_t)__popc(idle), pool_end);
         }
         if (!__any_sync(0xffffffffu, active)) {
-            if (drained) return;
+            if (drained && pool_next >= pool_end) return;
             continue;
         }
         if (active) {
-            const bool done = bvh2_run<ANY>(s.nodes, s.tris, r, st, stack, best, drained ? 0x7fffffff : quantum);
+            const bool done = bvh2_run<ANY>(s.nodes, s.tris, r, st, stack, best, rounds);
             if (done) { store_hit(hits, my, best); active = false; }
         }
         __syncwarp();

@@ -174,6 +174,7 @@ int mirogpu_scene_create(const float* tri_vertices, const float* tri_normals, co
     o.layout = MIROGPU_LAYOUT_CWBVH8; o.max_leaf = 0; o.sah_bins = 32; o.device = -1;
     if (opt) o = *opt;
     if (o.layout != MIROGPU_LAYOUT_BVH2 && o.layout != MIROGPU_LAYOUT_CWBVH8) return fail(MIROGPU_ERR_INVALID_ARG, "unknown layout");
+    if (o.max_leaf <= 0) if (const char* e = getenv("MIROGPU_MAX_LEAF")) o.max_leaf = atoi(e);   // tuning knob
     if (o.max_leaf <= 0) o.max_leaf = (o.layout == MIROGPU_LAYOUT_CWBVH8) ? 3 : 4;
     if (o.layout == MIROGPU_LAYOUT_CWBVH8 && o.max_leaf > 3) o.max_leaf = 3;
     if (o.layout == MIROGPU_LAYOUT_BVH2 && o.max_leaf > 8) o.max_leaf = 8;

@@ -226,8 +226,9 @@ MIRO_HD void trace_bvh2(const float4* __restrict__ nodes, const float4* __restri
 
 // ---- BVH2, resumable form -----------------------------------------------------------------------------------
 // Same walk as trace_bvh2, but all per-ray state lives in Bvh2State and bvh2_run() returns after a budget of
-// node visits (checked at leaf boundaries).  The persistent kernel with ray replacement runs every lane for one
-// such quantum, then refills the lanes whose ray finished and resumes the others where they stopped.
+// while-while rounds (one round = descend to the next leaf, test its triangles).  Lanes of a warp move through
+// rounds in lockstep, so with a common budget they all return together; the persistent kernel with ray
+// replacement then refills the lanes whose ray finished and resumes the others where they stopped.
 #define MIRO_BVH2_DONE ((int32_t)0x80000000)
 
 struct Bvh2State {
@@ -259,7 +260,6 @@ MIRO_HD bool bvh2_run(const float4* __restrict__ nodes, const float4* __restrict
             const float4 n1 = ldg(nodes + 4 * node + 1);
             const float4 nz = ldg(nodes + 4 * node + 2);
             const float4 lk = ldg(nodes + 4 * node + 3);
-            --budget;
             const float c0lox = n0.x * idx - oodx, c0hix = n0.y * idx - oodx;
             const float c0loy = n0.z * idy - oody, c0hiy = n0.w * idy - oody;
             const float c0loz = nz.x * idz - oodz, c0hiz = nz.y * idz - oodz;
@@ -296,7 +296,7 @@ MIRO_HD bool bvh2_run(const float4* __restrict__ nodes, const float4* __restrict
             }
             if (sp == 0) { st.node = MIRO_BVH2_DONE; return true; }
             node = stack[--sp];
-            if (budget <= 0) { st.node = node; st.sp = sp; return false; }
+            if (--budget <= 0) { st.node = node; st.sp = sp; return false; }
         }
     }
 }
