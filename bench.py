@@ -132,7 +132,7 @@ def cpu_leg(rays_p, rays_b, want_counters=True, kind_pref="reference"):
         os.dup2(saved, 1)
         os.close(devnull)
     out["cpu"] = dict(value=rays.shape[0] / secs / 1e6, unit="Mrays/s", cores=cores, kind=kind,
-                      sample=f"{rays_p.shape[0]} primary + {rays_b.shape[0]} live bounce rays of one {WIDTH}x{HEIGHT} sample (the GPU's own rays), "
+                      sample=f"{rays_p.shape[0]} primary + {rays_b.shape[0]} live bounce rays = one whole step ({SPP} samples of {WIDTH}x{HEIGHT}, the GPU's own rays), "
                              f"Scene::trace over OpenMP dynamic chunks of 4096; reference BVH build {build_s:.1f} s not timed",
                       seconds=secs)
     if want_counters:
@@ -246,7 +246,7 @@ def run_ours(args):
     def step(it, ev=None):
         S.generate_primary(cam, WIDTH, HEIGHT, d_rays, rows=rows, jitter=1, seed=SEED, sample=it * SPP, samples=SPP)
         if ev: ev[0].record()
-        S.intersect_device(d_rays, d_hits)
+        S.intersect_device(d_rays, d_hits, mode=pkg.CLOSEST_HIT | pkg.HINT_COHERENT)
         if ev: ev[1].record()
         S.generate_bounce(d_rays, d_hits, d_b, seed=SEED, sample=it, index_base=index_base, d_live_count=d_live)
         if ev: ev[2].record()
@@ -335,9 +335,9 @@ def run_ours(args):
         cpu, vt, ref_nodes = None, dict(FALLBACK_VT), None
         vt_src = "SURVEY 8d figures (oracle not run)"
         if world == 1 and not args.no_cpu:
-            # one sample's worth of the rays the GPU itself generated
-            rp = d_rays[:npix].cpu().numpy()
-            rb = d_b[:npix].cpu().numpy()
+            # the rays of the last timed step, exactly as the GPU generated them (all SPP samples)
+            rp = d_rays.cpu().numpy()
+            rb = d_b.cpu().numpy()
             rb = np.ascontiguousarray(rb[rb[:, 7] >= rb[:, 3]])
             try:
                 leg = cpu_leg(rp, rb)
@@ -371,7 +371,8 @@ def run_ours(args):
                 "bytes_per_ray": {"primary": bpr_p, "bounce": bpr_b, "V_T": vt, "source": vt_src},
                 "reference_bvh_nodes": ref_nodes,
             },
-            "roofline": {"bound": "hbm", "kernel": "k_trace_persistent (bounce rays, closest hit)", "achieved": achieved, "peak": peak, "unit": "GB/s",
+            "roofline": {"bound": "hbm", "kernel": ("k_trace_bvh2_hybrid" if (args.layout == "bvh2" and args.variant in (-1, 2)) else
+                                                    "k_trace_simple" if args.variant == 1 else "k_trace_persistent") + " (bounce rays, closest hit)", "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
                          "note": "algorithmic bytes = live bounce rays per launch x (32V + 36T + 48) B; the scene is mostly L2-resident, so DRAM traffic is far below this"},
             "cpu_baseline": cpu,
@@ -394,7 +395,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--layout", default="bvh2", choices=["bvh2", "cwbvh8"])
-    ap.add_argument("--variant", type=int, default=0)
+    ap.add_argument("--variant", type=int, default=int(os.environ.get("MIROGPU_VARIANT", "-1")))
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg (faster iteration)")
     args = ap.parse_args()
     if args.warmup < 3:

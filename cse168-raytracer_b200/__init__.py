@@ -25,6 +25,7 @@ MISS = 0xFFFFFFFF
 TMAX = np.float32(1e12)
 LAYOUT_BVH2, LAYOUT_CWBVH8 = 0, 1
 CLOSEST_HIT, ANY_HIT = 0, 1
+HINT_COHERENT = 0x100   # or-ed into a query mode: camera-like batch -> packet kernel
 RENDER_WHITTED, RENDER_DIFFUSE_BOUNCE, RENDER_PRIMARY_ONLY = 0, 1, 2
 
 RAY_DTYPE = np.dtype([("o", np.float32, 3), ("tmin", np.float32), ("d", np.float32, 3), ("tmax", np.float32)])

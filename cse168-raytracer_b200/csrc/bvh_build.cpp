@@ -429,8 +429,13 @@ void make_tri_records(const float* v, const std::vector<uint32_t>& order, std::v
         TriRecord r;
         r.ax = a[0]; r.ay = a[1]; r.az = a[2]; r.prim_id = p;
         // B - A and C - A in binary32, exactly the BmA / CmA of Triangle.cpp:150
-        r.e1x = a[3] - a[0]; r.e1y = a[4] - a[1]; r.e1z = a[5] - a[2]; r.pad0 = 0.f;
-        r.e2x = a[6] - a[0]; r.e2y = a[7] - a[1]; r.e2z = a[8] - a[2]; r.pad1 = 0.f;
+        r.e1x = a[3] - a[0]; r.e1y = a[4] - a[1]; r.e1z = a[5] - a[2];
+        r.e2x = a[6] - a[0]; r.e2y = a[7] - a[1]; r.e2z = a[8] - a[2];
+        // normal = cross(BmA, CmA), Triangle.cpp:151 (Vector3.h cross: y*v.z - z*v.y, ...), each product and the
+        // difference rounded to binary32 separately (this file is compiled with -ffp-contract=off)
+        const float p0 = r.e1y * r.e2z, p1 = r.e1z * r.e2y, p2 = r.e1z * r.e2x, p3 = r.e1x * r.e2z, p4 = r.e1x * r.e2y, p5 = r.e1y * r.e2x;
+        r.nx = p0 - p1; r.ny = p2 - p3; r.nz = p4 - p5;
+        r.pad[0] = r.pad[1] = r.pad[2] = 0.f;
         out[i] = r;
     }
 }

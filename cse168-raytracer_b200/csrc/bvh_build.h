@@ -67,15 +67,17 @@ struct Cwbvh8Node {
 };
 static_assert(sizeof(Cwbvh8Node) == 80, "Cwbvh8Node must be 80 bytes");
 
-// 48-byte triangle record in leaf order: A.xyz + prim id bits, B-A, C-A (the two edge vectors exactly as
-// Triangle.cpp:150 forms them in binary32).
+// 64-byte triangle record in leaf order (two 32-byte sectors, fetched with two 256-bit loads): A.xyz + prim id
+// bits, B-A, C-A (the two edge vectors exactly as Triangle.cpp:150 forms them in binary32) and their cross product
+// (the plane normal Triangle.cpp:151 recomputes on every call; same operations, so the same bits).
 struct TriRecord {
     float ax, ay, az;
     uint32_t prim_id;
-    float e1x, e1y, e1z, pad0;
-    float e2x, e2y, e2z, pad1;
+    float e1x, e1y, e1z, nx;
+    float e2x, e2y, e2z, ny;
+    float nz, pad[3];
 };
-static_assert(sizeof(TriRecord) == 48, "TriRecord must be 48 bytes");
+static_assert(sizeof(TriRecord) == 64, "TriRecord must be 64 bytes");
 
 struct FlatBvh {
     int layout = 0;

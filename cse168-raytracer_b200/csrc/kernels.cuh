@@ -35,10 +35,12 @@ __device__ __forceinline__ void trace_one(const DeviceScene& s, const mirogpu_ra
     else trace_cwbvh8<ANY, COUNT>(reinterpret_cast<const uint4*>(s.nodes), s.tris, r, best, c);
 }
 
+// Rays and hits are streamed once per launch: loads/stores carry the evict-first hint so the batch does not push
+// the scene (nodes + triangles, which every ray re-reads) out of L2.
 __device__ __forceinline__ mirogpu_ray load_ray(const mirogpu_ray* rays, size_t i)
 {
     const float4* p = reinterpret_cast<const float4*>(rays + i);
-    const float4 a = __ldg(p), b = __ldg(p + 1);
+    const float4 a = __ldcs(p), b = __ldcs(p + 1);
     mirogpu_ray r;
     r.ox = a.x; r.oy = a.y; r.oz = a.z; r.tmin = a.w; r.dx = b.x; r.dy = b.y; r.dz = b.z; r.tmax = b.w;
     return r;
@@ -46,7 +48,7 @@ __device__ __forceinline__ mirogpu_ray load_ray(const mirogpu_ray* rays, size_t 
 __device__ __forceinline__ void store_hit(mirogpu_hit* hits, size_t i, const BestHit& b)
 {
     float4 h; h.x = b.t; h.y = __uint_as_float(b.prim); h.z = b.beta; h.w = b.gamma;
-    *reinterpret_cast<float4*>(hits + i) = h;
+    __stcs(reinterpret_cast<float4*>(hits + i), h);
 }
 
 template <int LAYOUT, bool ANY, bool COUNT>
@@ -109,67 +111,87 @@ __global__ void __launch_bounds__(128) k_trace_persistent(DeviceScene s, const m
     }
 }
 
-// Persistent warps with ray replacement (BVH2).  Every lane owns one ray's resumable traversal state.  All lanes
-// run `rounds` while-while rounds, then a ballot finds the lanes whose ray has finished; they take the next rays
-// of the warp's private pool (256 consecutive rays claimed with ONE global atomic) by popc-prefix, and the busy
-// lanes resume where they stopped.  Incoherent rays differ wildly in cost (sky rays end after 2-3 nodes,
-// interior rays take 50+; rays generated at misses are dead on arrival), so a fixed 32-ray packet runs at the
-// length of its slowest ray with most lanes idle (ncu: 7.4 of 32 threads active per instruction on bounce rays).
-#define MIRO_REFILL_BELOW 2    /* default: while-while rounds per lane between refill points */
-#define MIRO_POOL 256          /* rays claimed per global atomic */
-
-template <bool ANY>
-__global__ void __launch_bounds__(128) k_trace_bvh2_dynamic(DeviceScene s, const mirogpu_ray* __restrict__ rays, size_t n,
-                                                            mirogpu_hit* __restrict__ hits, unsigned long long* __restrict__ ticket,
-                                                            int rounds, const uint32_t* __restrict__ d_n, uint32_t mult)
+// Persistent warps, hybrid step scheduling + ray replacement (BVH2).  In the while-while kernel a round costs the
+// warp max-over-lanes(descent length) node steps plus max-over-lanes(leaf size) triangle tests, and on incoherent
+// rays the descent lengths differ so much that 7 of 32 lanes are busy on average (ncu; tools/simt_sim.cu replays
+// the same rays and predicts the same figure).  Here every iteration the warp votes: it takes node steps while at
+// least `nmin` lanes want one (or nobody waits at a leaf), otherwise the lanes waiting at leaves test their
+// triangles.  Every `period` iterations, if at least `min_idle` lanes have finished their ray, those lanes pull the
+// next rays of the warp's pool by ballot + popc-prefix (warp-level ray compaction); pools of `pool` consecutive rays
+// are claimed from a global ticket one ahead of use and prefetched into L2 while the warp works on the current one.
+//   PF    prefetch flags of bvh2_node_step; bit 3: prefetch the pool claimed ahead         MINB  resident CTAs per SM asked of the compiler
+//   NREP  node steps per vote (a lane that leaves the inner nodes sits the rest out)
+template <bool ANY, int PF, int MINB, int NREP>
+__global__ void __launch_bounds__(128, MINB) k_trace_bvh2_hybrid(DeviceScene s, const mirogpu_ray* __restrict__ rays, size_t n,
+                                                                 mirogpu_hit* __restrict__ hits, unsigned long long* __restrict__ ticket,
+                                                                 int nmin, int period, int min_idle, uint32_t pool,
+                                                                 const uint32_t* __restrict__ d_n, uint32_t mult)
 {
     if (d_n) n = min(n, (size_t)*d_n * mult);
     const unsigned lane = threadIdx.x & 31u;
     const unsigned lt_mask = (1u << lane) - 1u;
-    bool active = false, drained = false;
-    size_t my = 0, pool_next = 0, pool_end = 0;   // pool_* are warp-uniform
+    // 32-bit ray indices (the launcher splits batches of 2^32 rays or more)
+    const uint32_t n32 = (uint32_t)n;
+    uint32_t my = 0;
+    uint32_t cur = 0, cur_end = 0, nxt;   // warp-uniform: the pool in use [cur, cur_end) and the base of the pool claimed ahead
     mirogpu_ray r;
-    Bvh2State st;
+    Bvh2Walk w;
     BestHit best;
-    int32_t stack[MIRO_STACK];
+    int32_t stack[MIRO_STACK + 1];
     r.ox = r.oy = r.oz = r.tmin = r.dx = r.dy = r.dz = r.tmax = 0.f;
-    st.node = MIRO_BVH2_DONE; st.sp = 0;
-    st.idx = st.idy = st.idz = st.oodx = st.oody = st.oodz = 0.f;
+    w.node = w.tos = MIRO_BVH2_DONE; w.sp = 0;
+    w.idx = w.idy = w.idz = w.oodx = w.oody = w.oodz = 0.f;
     best.t = 0.f; best.prim = MIROGPU_MISS; best.beta = best.gamma = 0.f;
+    auto claim = [&]() -> uint32_t {
+        unsigned long long base64 = 0;
+        if (lane == 0) base64 = atomicAdd(ticket, (unsigned long long)pool);
+        const uint32_t base = (uint32_t)min(base64, (unsigned long long)n32);
+        const uint32_t b = __shfl_sync(0xffffffffu, base, 0);
+        // one 128-byte line holds four rays
+        if (PF & 8) for (uint32_t k = 4 * lane; k < pool && k < n32 - b; k += 128) prefetch_l2(rays + b + k);
+        return b;
+    };
+    nxt = claim();
     for (;;) {
         // ---- hand new rays to idle lanes (two passes, so a lane that drew a dead ray gets another) ----
-        for (int pass = 0; pass < 2; ++pass) {
-            const unsigned idle = __ballot_sync(0xffffffffu, !active);
-            if (!idle) break;
-            if (pool_next >= pool_end) {
-                if (drained) break;
-                unsigned long long base = 0;
-                if (lane == 0) base = atomicAdd(ticket, (unsigned long long)MIRO_POOL);
-                base = __shfl_sync(0xffffffffu, base, 0);
-                if (base >= n) { drained = true; break; }
-                pool_next = (size_t)base;
-                pool_end = min((size_t)base + MIRO_POOL, n);
-            }
-            if (!active) {
-                const size_t i = pool_next + __popc(idle & lt_mask);
-                if (i < pool_end) {
-                    r = load_ray(rays, i);
-                    bvh2_begin(r, st, best);
-                    if (st.node == MIRO_BVH2_DONE) store_hit(hits, i, best);   // empty interval: answered without traversal
-                    else { active = true; my = i; }
+        unsigned idle = __ballot_sync(0xffffffffu, w.node == MIRO_BVH2_DONE);
+        if (__popc(idle) >= min_idle) {
+            for (int pass = 0; pass < 2 && idle; ++pass) {
+                if (cur >= cur_end) {
+                    if (nxt >= n32) break;   // drained
+                    cur = nxt; cur_end = nxt + min(pool, n32 - nxt);
+                    nxt = claim();
                 }
+                if (w.node == MIRO_BVH2_DONE) {
+                    const uint32_t i = cur + __popc(idle & lt_mask);
+                    if (i < cur_end) {
+                        r = load_ray(rays, i);
+                        bvh2_begin(r, w, best);
+                        if (w.node == MIRO_BVH2_DONE) store_hit(hits, i, best);   // empty interval: answered without traversal
+                        else my = i;
+                    }
+                }
+                cur = min(cur + (uint32_t)__popc(idle), cur_end);
+                idle = __ballot_sync(0xffffffffu, w.node == MIRO_BVH2_DONE);
             }
-            pool_next = min(pool_next + (size_t)__popc(idle), pool_end);
+            if (idle == 0xffffffffu) {
+                if (cur >= cur_end && nxt >= n32) return;
+                continue;
+            }
         }
-        if (!__any_sync(0xffffffffu, active)) {
-            if (drained && pool_next >= pool_end) return;
-            continue;
+        for (int it = 0; it < period; ++it) {
+            const unsigned mn = __ballot_sync(0xffffffffu, w.node >= 0);
+            const unsigned ml = __ballot_sync(0xffffffffu, w.node < 0 && w.node != MIRO_BVH2_DONE);
+            if ((mn | ml) == 0u) break;
+            if (mn != 0u && (__popc(mn) >= nmin || ml == 0u)) {
+#pragma unroll
+                for (int rep = 0; rep < NREP; ++rep)
+                    if (w.node >= 0) bvh2_node_step<PF>(s.nodes, s.tris, r, w, stack, best);
+            } else if (w.node < 0 && w.node != MIRO_BVH2_DONE) {
+                bvh2_leaf_step<ANY>(s.tris, r, w, stack, best);
+            }
+            if (w.node == MIRO_BVH2_DONE && ((mn | ml) >> lane & 1u)) store_hit(hits, my, best);
         }
-        if (active) {
-            const bool done = bvh2_run<ANY>(s.nodes, s.tris, r, st, stack, best, rounds);
-            if (done) { store_hit(hits, my, best); active = false; }
-        }
-        __syncwarp();
     }
 }
 

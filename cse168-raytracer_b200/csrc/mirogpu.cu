@@ -52,9 +52,11 @@ double now_s()
 struct mirogpu_scene {
     int device = 0;
     int layout = MIROGPU_LAYOUT_CWBVH8;
-    int variant = 0;
+    int variant = -1;   // mirogpu_set_kernel_variant
     int sm_count = 148;
-    int refill_below = MIRO_REFILL_BELOW;   // ray-replacement quantum in node visits (env MIROGPU_QUANTUM overrides, for tuning)
+    // hybrid kernel (variant 2) knobs; env MIROGPU_NMIN / _PERIOD / _MINIDLE / _POOL / _PF / _MINB / _NREP override (tuning)
+    int hyb_nmin = 16, hyb_period = 4, hyb_min_idle = 8, hyb_pool = 64, hyb_nrep = 2;
+    int hyb_pf = 0, hyb_minb = 9;                          // prefetch flags (traverse.cuh), min resident CTAs
     DeviceScene ds{};
     void* d_nodes = nullptr;
     void* d_tris = nullptr;
@@ -81,9 +83,35 @@ namespace {
 
 // n is the number of rays, or -- when d_n is given -- an upper bound on it: the kernels then read the real count
 // *d_n * mult from device memory (wavefront queues whose size the host never sees).
+template <bool ANY, int PF, int MINB, int NREP>
+cudaError_t launch_hybrid_inst(mirogpu_scene* h, const mirogpu_ray* d_rays, size_t n, mirogpu_hit* d_hits, unsigned long long* ticket,
+                               cudaStream_t st, const uint32_t* d_n, uint32_t mult)
+{
+    int occ = 0;
+    cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_trace_bvh2_hybrid<ANY, PF, MINB, NREP>, 128, 0);
+    if (e != cudaSuccess) return e;
+    if (occ < 1) occ = 1;
+    size_t grid = (size_t)h->sm_count * occ;
+    const size_t need = (n + 127) / 128;
+    if (grid > need) grid = need;
+    k_trace_bvh2_hybrid<ANY, PF, MINB, NREP><<<(unsigned)grid, 128, 0, st>>>(h->ds, d_rays, n, d_hits, ticket, h->hyb_nmin, h->hyb_period,
+                                                                            h->hyb_min_idle, (uint32_t)h->hyb_pool, d_n, mult);
+    return cudaGetLastError();
+}
+
+template <bool ANY>
+cudaError_t launch_hybrid(mirogpu_scene* h, const mirogpu_ray* d_rays, size_t n, mirogpu_hit* d_hits, unsigned long long* ticket,
+                          cudaStream_t st, const uint32_t* d_n, uint32_t mult)
+{
+#define MIRO_HYB(PF, MINB, NREP) if (h->hyb_pf == PF && h->hyb_minb == MINB && h->hyb_nrep == NREP) return launch_hybrid_inst<ANY, PF, MINB, NREP>(h, d_rays, n, d_hits, ticket, st, d_n, mult);
+    MIRO_HYB(0, 9, 2) MIRO_HYB(4, 9, 2) MIRO_HYB(0, 8, 2) MIRO_HYB(0, 9, 1) MIRO_HYB(0, 9, 3)
+#undef MIRO_HYB
+    return launch_hybrid_inst<ANY, 0, 9, 2>(h, d_rays, n, d_hits, ticket, st, d_n, mult);
+}
+
 template <int LAYOUT, bool ANY>
 cudaError_t launch_trace(mirogpu_scene* h, const mirogpu_ray* d_rays, size_t n, mirogpu_hit* d_hits, cudaStream_t st,
-                         const uint32_t* d_n, uint32_t mult)
+                         const uint32_t* d_n, uint32_t mult, bool coherent)
 {
     if (n == 0) return cudaSuccess;
     if (h->variant == 1) {
@@ -94,29 +122,28 @@ cudaError_t launch_trace(mirogpu_scene* h, const mirogpu_ray* d_rays, size_t n, 
     unsigned long long* ticket = h->d_ticket + (h->ticket_slot.fetch_add(1) & 63u);
     cudaError_t e = cudaMemsetAsync(ticket, 0, sizeof(unsigned long long), st);
     if (e != cudaSuccess) return e;
-    const bool dynamic = LAYOUT == MIROGPU_LAYOUT_BVH2 && h->variant == 2;   // variant 0: 32-ray tickets (fastest measured)
+    if (LAYOUT == MIROGPU_LAYOUT_BVH2 && (h->variant == 2 || (h->variant < 0 && !coherent)) && n < 0xFF000000ull) return launch_hybrid<ANY>(h, d_rays, n, d_hits, ticket, st, d_n, mult);
     int occ = 0;
-    if (dynamic) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_trace_bvh2_dynamic<ANY>, 128, 0);
-    else e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_trace_persistent<LAYOUT, ANY>, 128, 0);
+    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_trace_persistent<LAYOUT, ANY>, 128, 0);
     if (e != cudaSuccess) return e;
     if (occ < 1) occ = 1;
     size_t grid = (size_t)h->sm_count * occ;
     const size_t need = (n + 127) / 128;
     if (grid > need) grid = need;
-    if (dynamic) k_trace_bvh2_dynamic<ANY><<<(unsigned)grid, 128, 0, st>>>(h->ds, d_rays, n, d_hits, ticket, h->refill_below, d_n, mult);
-    else k_trace_persistent<LAYOUT, ANY><<<(unsigned)grid, 128, 0, st>>>(h->ds, d_rays, n, d_hits, ticket, d_n, mult);
+    k_trace_persistent<LAYOUT, ANY><<<(unsigned)grid, 128, 0, st>>>(h->ds, d_rays, n, d_hits, ticket, d_n, mult);
     return cudaGetLastError();
 }
 
 cudaError_t dispatch_trace(mirogpu_scene* h, const mirogpu_ray* d_rays, size_t n, mirogpu_hit* d_hits, int mode, cudaStream_t st,
                            const uint32_t* d_n = nullptr, uint32_t mult = 1)
 {
-    const bool any = mode == MIROGPU_ANY_HIT;
+    const bool any = (mode & 0xff) == MIROGPU_ANY_HIT;
+    const bool coherent = (mode & MIROGPU_HINT_COHERENT) != 0;
     if (h->layout == MIROGPU_LAYOUT_BVH2)
-        return any ? launch_trace<MIROGPU_LAYOUT_BVH2, true>(h, d_rays, n, d_hits, st, d_n, mult)
-                   : launch_trace<MIROGPU_LAYOUT_BVH2, false>(h, d_rays, n, d_hits, st, d_n, mult);
-    return any ? launch_trace<MIROGPU_LAYOUT_CWBVH8, true>(h, d_rays, n, d_hits, st, d_n, mult)
-               : launch_trace<MIROGPU_LAYOUT_CWBVH8, false>(h, d_rays, n, d_hits, st, d_n, mult);
+        return any ? launch_trace<MIROGPU_LAYOUT_BVH2, true>(h, d_rays, n, d_hits, st, d_n, mult, coherent)
+                   : launch_trace<MIROGPU_LAYOUT_BVH2, false>(h, d_rays, n, d_hits, st, d_n, mult, coherent);
+    return any ? launch_trace<MIROGPU_LAYOUT_CWBVH8, true>(h, d_rays, n, d_hits, st, d_n, mult, coherent)
+               : launch_trace<MIROGPU_LAYOUT_CWBVH8, false>(h, d_rays, n, d_hits, st, d_n, mult, coherent);
 }
 
 // Camera::eyeRay's cached basis (Camera.cpp:113-124), computed on the host in the reference's operand order.
@@ -196,7 +223,13 @@ int mirogpu_scene_create(const float* tri_vertices, const float* tri_normals, co
     cudaDeviceProp prop;
     CUDA_TRY(cudaGetDeviceProperties(&prop, dev));
     h->sm_count = prop.multiProcessorCount;
-    if (const char* e = getenv("MIROGPU_QUANTUM")) { const int v = atoi(e); if (v >= 1 && v <= 100000) h->refill_below = v; }
+    if (const char* e = getenv("MIROGPU_POOL")) { const int v = atoi(e); if (v >= 32 && v <= 65536) h->hyb_pool = v; }
+    if (const char* e = getenv("MIROGPU_NREP")) h->hyb_nrep = atoi(e);
+    if (const char* e = getenv("MIROGPU_NMIN")) { const int v = atoi(e); if (v >= 1 && v <= 32) h->hyb_nmin = v; }
+    if (const char* e = getenv("MIROGPU_PERIOD")) { const int v = atoi(e); if (v >= 1 && v <= 100000) h->hyb_period = v; }
+    if (const char* e = getenv("MIROGPU_PF")) h->hyb_pf = atoi(e);
+    if (const char* e = getenv("MIROGPU_MINB")) h->hyb_minb = atoi(e);
+    if (const char* e = getenv("MIROGPU_MINIDLE")) { const int v = atoi(e); if (v >= 1 && v <= 32) h->hyb_min_idle = v; }
 
     // ---- host build ------------------------------------------------------------------------------
     double t0 = now_s();
@@ -244,8 +277,10 @@ int mirogpu_scene_create(const float* tri_vertices, const float* tri_normals, co
         return fail(e == cudaErrorMemoryAllocation ? MIROGPU_ERR_OOM : MIROGPU_ERR_CUDA, msg);
     };
     cudaError_t e;
-    if ((e = cudaMalloc(&h->d_nodes, std::max<size_t>(node_bytes, 16))) != cudaSuccess) return bail(e, "cudaMalloc nodes");
-    if ((e = cudaMalloc(&h->d_tris, std::max<size_t>(tri_bytes, 16))) != cudaSuccess) return bail(e, "cudaMalloc triangles");
+    // nodes and triangles share one allocation (the traversal working set is one address range)
+    const size_t node_span = (std::max<size_t>(node_bytes, 16) + 255) & ~(size_t)255;
+    if ((e = cudaMalloc(&h->d_nodes, node_span + std::max<size_t>(tri_bytes, 16))) != cudaSuccess) return bail(e, "cudaMalloc nodes + triangles");
+    h->d_tris = static_cast<char*>(h->d_nodes) + node_span;
     if ((e = cudaMalloc(&h->d_shade, std::max<size_t>(shade_bytes, 16))) != cudaSuccess) return bail(e, "cudaMalloc shading records");
     if ((e = cudaMalloc(&h->d_materials, mats.size() * sizeof(mirogpu_material))) != cudaSuccess) return bail(e, "cudaMalloc materials");
     if ((e = cudaMalloc(&h->d_ticket, 64 * sizeof(unsigned long long))) != cudaSuccess) return bail(e, "cudaMalloc tickets");
@@ -286,7 +321,7 @@ int mirogpu_scene_destroy(mirogpu_handle h)
 {
     if (!h) return MIROGPU_OK;
     cudaSetDevice(h->device);
-    cudaFree(h->d_nodes); cudaFree(h->d_tris); cudaFree(h->d_shade); cudaFree(h->d_materials);
+    cudaFree(h->d_nodes); cudaFree(h->d_shade); cudaFree(h->d_materials);   // d_tris lives inside d_nodes's allocation
     cudaFree(h->d_lights); cudaFree(h->d_ticket);
     if (h->h_stats) cudaFreeHost(h->h_stats);
     for (int i = 0; i < 2; ++i) h->pm[i].release();
@@ -338,8 +373,8 @@ int mirogpu_debug_copy_triangles(mirogpu_handle h, void* out, uint64_t* bytes)
 int mirogpu_set_kernel_variant(mirogpu_handle h, int variant)
 {
     if (!h) return fail(MIROGPU_ERR_INVALID_ARG, "NULL handle");
-    if (variant < 0 || variant > 2)
-        return fail(MIROGPU_ERR_INVALID_ARG, "variant must be 0 (persistent warps, 32-ray tickets), 1 (one thread per ray) or 2 (persistent warps with ray replacement, BVH2)");
+    if (variant < -1 || variant > 2)
+        return fail(MIROGPU_ERR_INVALID_ARG, "variant must be -1 (automatic), 0 (persistent warps, 32-ray tickets, while-while), 1 (one thread per ray) or 2 (persistent warps, hybrid step scheduling + ray replacement; BVH2 only)");
     h->variant = variant;
     return MIROGPU_OK;
 }
@@ -348,7 +383,8 @@ int mirogpu_intersect_batch_device(mirogpu_handle h, const mirogpu_ray* d_rays, 
                                    void* cuda_stream)
 {
     if (!h || (n && (!d_rays || !d_hits))) return fail(MIROGPU_ERR_INVALID_ARG, "NULL argument");
-    if (mode != MIROGPU_CLOSEST_HIT && mode != MIROGPU_ANY_HIT) return fail(MIROGPU_ERR_INVALID_ARG, "unknown mode");
+    if ((mode & ~MIROGPU_HINT_COHERENT) != MIROGPU_CLOSEST_HIT && (mode & ~MIROGPU_HINT_COHERENT) != MIROGPU_ANY_HIT)
+        return fail(MIROGPU_ERR_INVALID_ARG, "unknown mode");
     CUDA_TRY(cudaSetDevice(h->device));
     CUDA_TRY(dispatch_trace(h, d_rays, n, d_hits, mode, (cudaStream_t)cuda_stream));
     {
@@ -363,7 +399,8 @@ int mirogpu_intersect_batch_device(mirogpu_handle h, const mirogpu_ray* d_rays, 
 int mirogpu_intersect_batch(mirogpu_handle h, const mirogpu_ray* rays, size_t n, mirogpu_hit* hits, int mode)
 {
     if (!h || (n && (!rays || !hits))) return fail(MIROGPU_ERR_INVALID_ARG, "NULL argument");
-    if (mode != MIROGPU_CLOSEST_HIT && mode != MIROGPU_ANY_HIT) return fail(MIROGPU_ERR_INVALID_ARG, "unknown mode");
+    if ((mode & ~MIROGPU_HINT_COHERENT) != MIROGPU_CLOSEST_HIT && (mode & ~MIROGPU_HINT_COHERENT) != MIROGPU_ANY_HIT)
+        return fail(MIROGPU_ERR_INVALID_ARG, "unknown mode");
     if (n == 0) return MIROGPU_OK;
     CUDA_TRY(cudaSetDevice(h->device));
     const size_t chunk = std::min<size_t>(n, (size_t)4 << 20);
@@ -404,7 +441,8 @@ int mirogpu_intersect_batch_counted(mirogpu_handle h, const mirogpu_ray* rays, s
                                     mirogpu_counters* c)
 {
     if (!h || !c || (n && (!rays || !hits))) return fail(MIROGPU_ERR_INVALID_ARG, "NULL argument");
-    if (mode != MIROGPU_CLOSEST_HIT && mode != MIROGPU_ANY_HIT) return fail(MIROGPU_ERR_INVALID_ARG, "unknown mode");
+    if ((mode & ~MIROGPU_HINT_COHERENT) != MIROGPU_CLOSEST_HIT && (mode & ~MIROGPU_HINT_COHERENT) != MIROGPU_ANY_HIT)
+        return fail(MIROGPU_ERR_INVALID_ARG, "unknown mode");
     if (n == 0) return MIROGPU_OK;
     CUDA_TRY(cudaSetDevice(h->device));
     mirogpu_ray* d_r = nullptr; mirogpu_hit* d_h = nullptr; unsigned long long* d_c = nullptr;
@@ -429,7 +467,7 @@ int mirogpu_intersect_batch_counted(mirogpu_handle h, const mirogpu_ray* rays, s
     cudaFree(d_r); cudaFree(d_h); cudaFree(d_c);
     const uint64_t node_size = h->layout == MIROGPU_LAYOUT_BVH2 ? 64 : 80;
     c->rays += n; c->node_visits += hc[0]; c->box_tests += hc[1]; c->triangle_tests += hc[2]; c->hits += hc[3];
-    c->bytes_fetched += hc[0] * node_size + hc[2] * 48;
+    c->bytes_fetched += hc[0] * node_size + hc[2] * sizeof(TriRecord);
     return MIROGPU_OK;
 }
 

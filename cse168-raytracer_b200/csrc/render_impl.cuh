@@ -472,13 +472,13 @@ int render_device(mirogpu_scene* h, const mirogpu_camera& cam, const mirogpu_ren
         size_t bound = items;
         for (int wave = 0; wave < MIRO_MAX_WAVES && wave <= rp.max_depth; ++wave) {
             const uint32_t* d_n = wave == 0 ? nullptr : counters + wave;
-            RT(dispatch_trace(h, q[cur].rays, bound, q[cur].hits, MIROGPU_CLOSEST_HIT, st, d_n, 1));
+            RT(dispatch_trace(h, q[cur].rays, bound, q[cur].hits, MIROGPU_CLOSEST_HIT | (wave == 0 ? MIROGPU_HINT_COHERENT : 0), st, d_n, 1));
             k_shade<<<(unsigned)((bound + 127) / 128), 128, 0, st>>>(wp, q[cur], (uint32_t)bound, d_n, q[cur ^ 1], counters + wave + 1, counters + 17,
                                                                       srays, scd, sch, planes, gpos, gnrm, gw);
             launches += 2;
             if (shadows) {
                 const size_t ns = bound * nl;
-                RT(dispatch_trace(h, srays, ns, shits, any_refractive ? MIROGPU_CLOSEST_HIT : MIROGPU_ANY_HIT, st, d_n, nl));
+                RT(dispatch_trace(h, srays, ns, shits, (any_refractive ? MIROGPU_CLOSEST_HIT : MIROGPU_ANY_HIT) | (wave == 0 ? MIROGPU_HINT_COHERENT : 0), st, d_n, nl));
                 k_shadow_accumulate<<<(unsigned)((ns + 255) / 256), 256, 0, st>>>(wp, srays, shits, scd, sch, ns, d_n, nl, planes);
                 launches += 2;
             }

@@ -78,6 +78,42 @@ MIRO_HD T ldg(const T* p)
     return *p;
 #endif
 }
+// 256-bit read-only load (LDG.E.ENL2.256.CONSTANT on sm_100a): one 32-byte sector per lane per instruction.  The
+// traversal kernels are bound by L1 data-pipe wavefronts (one sector per wavefront for divergent lanes), so a 64-byte
+// node or triangle record costs two of these instead of four 128-bit loads.  p must be 32-byte aligned.
+struct F8 {
+    float4 lo, hi;
+};
+MIRO_HD F8 ld256(const float4* p)
+{
+    F8 r;
+#ifdef __CUDA_ARCH__
+    asm("ld.global.nc.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+        : "=f"(r.lo.x), "=f"(r.lo.y), "=f"(r.lo.z), "=f"(r.lo.w), "=f"(r.hi.x), "=f"(r.hi.y), "=f"(r.hi.z), "=f"(r.hi.w)
+        : "l"(p));
+#else
+    r.lo = p[0]; r.hi = p[1];
+#endif
+    return r;
+}
+// L2 prefetch of the 128-byte line holding p: issued when a far child is pushed on the stack (or a leaf is reached
+// before the warp's leaf phase), so the DRAM/L2 latency of that fetch overlaps the walk of the near subtree.
+MIRO_HD void prefetch_l2(const void* p)
+{
+#ifdef __CUDA_ARCH__
+    asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
+#else
+    (void)p;
+#endif
+}
+MIRO_HD void prefetch_l1(const void* p)
+{
+#ifdef __CUDA_ARCH__
+    asm volatile("prefetch.global.L1 [%0];" ::"l"(p));
+#else
+    (void)p;
+#endif
+}
 MIRO_HD int popc32(uint32_t x)
 {
 #ifdef __CUDA_ARCH__
@@ -121,16 +157,15 @@ struct BestHit {
     float beta, gamma;
 };
 
-// Triangle::intersect, Triangle.cpp:150-158.  v0 = (A, prim id bits), v1 = (B-A, -), v2 = (C-A, -).
+// Triangle::intersect, Triangle.cpp:150-158.  v0 = (A, prim id bits), v1 = (B-A, n.x), v2 = (C-A, n.y), v3 = (n.z, -, -, -)
+// with n = cross(B-A, C-A) formed once on the host in the same binary32 operations the reference performs per call
+// (make_tri_records), so the value is the one the reference computes.
 // Acceptance on top of the reference's own reject line: the leaf keeps a hit only if it is strictly closer
 // than the best so far (BVH.cpp:498-500); equal t goes to the smaller primitive id so the result does not
 // depend on traversal order.  NaN t fails every comparison and is dropped, as in the reference.
-MIRO_HD bool tri_test(const float4 v0, const float4 v1, const float4 v2, const mirogpu_ray& r, BestHit& best)
+MIRO_HD bool tri_test(const float4 v0, const float4 v1, const float4 v2, const float4 v3, const mirogpu_ray& r, BestHit& best)
 {
-    // normal = cross(BmA, CmA)
-    const float nx = xsub(xmul(v1.y, v2.z), xmul(v1.z, v2.y));
-    const float ny = xsub(xmul(v1.z, v2.x), xmul(v1.x, v2.z));
-    const float nz = xsub(xmul(v1.x, v2.y), xmul(v1.y, v2.x));
+    const float nx = v1.w, ny = v2.w, nz = v3.x;   // normal = cross(BmA, CmA)
     const float ndx = -r.dx, ndy = -r.dy, ndz = -r.dz;
     const float ddotn = xdot(ndx, ndy, ndz, nx, ny, nz);
     const float oax = xsub(r.ox, v0.x), oay = xsub(r.oy, v0.y), oaz = xsub(r.oz, v0.z);
@@ -177,10 +212,8 @@ MIRO_HD void trace_bvh2(const float4* __restrict__ nodes, const float4* __restri
     if (!(r.tmax >= r.tmin)) return;
     for (;;) {
         while (node >= 0) {
-            const float4 n0 = ldg(nodes + 4 * node + 0);
-            const float4 n1 = ldg(nodes + 4 * node + 1);
-            const float4 nz = ldg(nodes + 4 * node + 2);
-            const float4 lk = ldg(nodes + 4 * node + 3);
+            const F8 na = ld256(nodes + 4 * (size_t)node), nb = ld256(nodes + 4 * (size_t)node + 2);
+            const float4 n0 = na.lo, n1 = na.hi, nz = nb.lo, lk = nb.hi;
             if (COUNT) { cnt->nodes++; cnt->boxes += 2; }
             const float c0lox = n0.x * idx - oodx, c0hix = n0.y * idx - oodx;
             const float c0loy = n0.z * idy - oody, c0hiy = n0.w * idy - oody;
@@ -211,11 +244,9 @@ MIRO_HD void trace_bvh2(const float4* __restrict__ nodes, const float4* __restri
             const uint32_t ref = (uint32_t)~node;
             const uint32_t first = ref >> 3, count = (ref & 7u) + 1u;
             for (uint32_t i = 0; i < count; ++i) {
-                const float4 v0 = ldg(tris + 3 * (first + i) + 0);
-                const float4 v1 = ldg(tris + 3 * (first + i) + 1);
-                const float4 v2 = ldg(tris + 3 * (first + i) + 2);
+                const F8 ta = ld256(tris + 4 * (size_t)(first + i)), tb = ld256(tris + 4 * (size_t)(first + i) + 2);
                 if (COUNT) cnt->tris++;
-                const bool acc = tri_test(v0, v1, v2, r, best);
+                const bool acc = tri_test(ta.lo, ta.hi, tb.lo, tb.hi, r, best);
                 if (ANY && acc) return;
             }
             if (sp == 0) return;
@@ -224,81 +255,105 @@ MIRO_HD void trace_bvh2(const float4* __restrict__ nodes, const float4* __restri
     }
 }
 
-// ---- BVH2, resumable form -----------------------------------------------------------------------------------
-// Same walk as trace_bvh2, but all per-ray state lives in Bvh2State and bvh2_run() returns after a budget of
-// while-while rounds (one round = descend to the next leaf, test its triangles).  Lanes of a warp move through
-// rounds in lockstep, so with a common budget they all return together; the persistent kernel with ray
-// replacement then refills the lanes whose ray finished and resumes the others where they stopped.
+// ---- BVH2, single-step form (hybrid-scheduled kernel) ---------------------------------------------------------
+// The same walk as trace_bvh2, cut into its two kinds of step so that a warp can decide per iteration which kind to
+// run, with all per-ray state in Bvh2Walk:
+//   bvh2_node_step  -- w.node >= 0: fetch the node, test both child boxes, descend / push / pop
+//   bvh2_leaf_step  -- w.node < 0 and != MIRO_BVH2_DONE: test the leaf's triangles, then pop
+// Either leaves w.node = next inner node, next leaf, or MIRO_BVH2_DONE when the walk is over.
+// The top of the stack is cached in a register (w.tos): a pop hands out the register at once and the reload of the
+// new top from local memory completes in the shadow of the next step.  The bottom-of-stack marker is an ordinary
+// entry (MIRO_BVH2_DONE), so there is no emptiness test.
 #define MIRO_BVH2_DONE ((int32_t)0x80000000)
 
-struct Bvh2State {
+struct Bvh2Walk {
     float idx, idy, idz, oodx, oody, oodz;
-    int32_t node;
+    int32_t node, tos;
     int sp;
 };
 
-MIRO_HD void bvh2_begin(const mirogpu_ray& r, Bvh2State& st, BestHit& best)
+MIRO_HD float fast_safe_rcp(float d)
 {
-    st.idx = safe_rcp(r.dx); st.idy = safe_rcp(r.dy); st.idz = safe_rcp(r.dz);
-    st.oodx = r.ox * st.idx; st.oody = r.oy * st.idy; st.oodz = r.oz * st.idz;
-    st.sp = 0;
-    st.node = (r.tmax >= r.tmin) ? 0 : MIRO_BVH2_DONE;   // an empty interval (or NaN bounds) never hits
+    const float a = fabsf(d) < 1e-30f ? copysignf(1e-30f, d) : d;
+#ifdef __CUDA_ARCH__
+    float r;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(a));   // 1 ulp; box tests only (conservative boxes absorb it)
+    return r;
+#else
+    return 1.0f / a;
+#endif
+}
+
+MIRO_HD void bvh2_begin(const mirogpu_ray& r, Bvh2Walk& w, BestHit& best)
+{
+    w.idx = fast_safe_rcp(r.dx); w.idy = fast_safe_rcp(r.dy); w.idz = fast_safe_rcp(r.dz);
+    w.oodx = r.ox * w.idx; w.oody = r.oy * w.idy; w.oodz = r.oz * w.idz;
+    w.sp = 0;
+    w.tos = MIRO_BVH2_DONE;
+    w.node = (r.tmax >= r.tmin) ? 0 : MIRO_BVH2_DONE;   // an empty interval (or NaN bounds) never hits
     best.t = r.tmax; best.prim = MIROGPU_MISS; best.beta = 0.f; best.gamma = 0.f;
 }
 
-// Returns true when the ray is finished, false when the budget ran out (state saved for the next call).
-template <bool ANY>
-MIRO_HD bool bvh2_run(const float4* __restrict__ nodes, const float4* __restrict__ tris, const mirogpu_ray& r, Bvh2State& st,
-                      int32_t* __restrict__ stack, BestHit& best, int budget)
+MIRO_HD void bvh2_pop(Bvh2Walk& w, const int32_t* __restrict__ stack)
 {
-    int32_t node = st.node;
-    int sp = st.sp;
-    const float idx = st.idx, idy = st.idy, idz = st.idz, oodx = st.oodx, oody = st.oody, oodz = st.oodz;
-    for (;;) {
-        while (node >= 0) {
-            const float4 n0 = ldg(nodes + 4 * node + 0);
-            const float4 n1 = ldg(nodes + 4 * node + 1);
-            const float4 nz = ldg(nodes + 4 * node + 2);
-            const float4 lk = ldg(nodes + 4 * node + 3);
-            const float c0lox = n0.x * idx - oodx, c0hix = n0.y * idx - oodx;
-            const float c0loy = n0.z * idy - oody, c0hiy = n0.w * idy - oody;
-            const float c0loz = nz.x * idz - oodz, c0hiz = nz.y * idz - oodz;
-            const float c1lox = n1.x * idx - oodx, c1hix = n1.y * idx - oodx;
-            const float c1loy = n1.z * idy - oody, c1hiy = n1.w * idy - oody;
-            const float c1loz = nz.z * idz - oodz, c1hiz = nz.w * idz - oodz;
-            const float t0n = fmaxf(fmaxf(fminf(c0lox, c0hix), fminf(c0loy, c0hiy)), fmaxf(fminf(c0loz, c0hiz), r.tmin));
-            const float t0f = fminf(fminf(fmaxf(c0lox, c0hix), fmaxf(c0loy, c0hiy)), fminf(fmaxf(c0loz, c0hiz), best.t));
-            const float t1n = fmaxf(fmaxf(fminf(c1lox, c1hix), fminf(c1loy, c1hiy)), fmaxf(fminf(c1loz, c1hiz), r.tmin));
-            const float t1f = fminf(fminf(fmaxf(c1lox, c1hix), fmaxf(c1loy, c1hiy)), fminf(fmaxf(c1loz, c1hiz), best.t));
-            const bool h0 = t0n <= t0f, h1 = t1n <= t1f;
-            const int32_t l0 = (int32_t)f2u(lk.x), l1 = (int32_t)f2u(lk.y);
-            if (!h0 && !h1) {
-                if (sp == 0) { st.node = MIRO_BVH2_DONE; return true; }
-                node = stack[--sp];
-            } else {
-                node = h0 ? l0 : l1;
-                if (h0 && h1) {
-                    int32_t other = l1;
-                    if (t1n < t0n) { node = l1; other = l0; }
-                    stack[sp++] = other;
-                }
+    w.node = w.tos;
+    if (w.tos != MIRO_BVH2_DONE) w.tos = stack[--w.sp];
+}
+
+// PF bit 0: prefetch the pushed far child (node or first triangle line) into L2; bit 1: into L1 instead;
+// bit 2: prefetch the triangles of a leaf reached by descent (the lane usually waits for the warp's leaf phase).
+template <int PF>
+MIRO_HD void bvh2_node_step(const float4* __restrict__ nodes, const float4* __restrict__ tris, const mirogpu_ray& r, Bvh2Walk& w,
+                            int32_t* __restrict__ stack, const BestHit& best)
+{
+    const F8 na = ld256(nodes + 4 * (size_t)w.node), nb = ld256(nodes + 4 * (size_t)w.node + 2);
+    const float4 n0 = na.lo, n1 = na.hi, nz = nb.lo, lk = nb.hi;
+    const float c0lox = n0.x * w.idx - w.oodx, c0hix = n0.y * w.idx - w.oodx;
+    const float c0loy = n0.z * w.idy - w.oody, c0hiy = n0.w * w.idy - w.oody;
+    const float c0loz = nz.x * w.idz - w.oodz, c0hiz = nz.y * w.idz - w.oodz;
+    const float c1lox = n1.x * w.idx - w.oodx, c1hix = n1.y * w.idx - w.oodx;
+    const float c1loy = n1.z * w.idy - w.oody, c1hiy = n1.w * w.idy - w.oody;
+    const float c1loz = nz.z * w.idz - w.oodz, c1hiz = nz.w * w.idz - w.oodz;
+    const float t0n = fmaxf(fmaxf(fminf(c0lox, c0hix), fminf(c0loy, c0hiy)), fmaxf(fminf(c0loz, c0hiz), r.tmin));
+    const float t0f = fminf(fminf(fmaxf(c0lox, c0hix), fmaxf(c0loy, c0hiy)), fminf(fmaxf(c0loz, c0hiz), best.t));
+    const float t1n = fmaxf(fmaxf(fminf(c1lox, c1hix), fminf(c1loy, c1hiy)), fmaxf(fminf(c1loz, c1hiz), r.tmin));
+    const float t1f = fminf(fminf(fmaxf(c1lox, c1hix), fmaxf(c1loy, c1hiy)), fminf(fmaxf(c1loz, c1hiz), best.t));
+    const bool h0 = t0n <= t0f, h1 = t1n <= t1f;
+    const int32_t l0 = (int32_t)f2u(lk.x), l1 = (int32_t)f2u(lk.y);
+    if (!h0 && !h1) {
+        bvh2_pop(w, stack);
+    } else {
+        int32_t next = h0 ? l0 : l1;
+        if (h0 && h1) {
+            int32_t other = l1;
+            if (t1n < t0n) { next = l1; other = l0; }
+            stack[w.sp++] = w.tos;
+            w.tos = other;
+            if (PF & 3) {
+                const float4* a = other >= 0 ? nodes + 4 * (size_t)other : tris + 4 * (size_t)(((uint32_t)~other) >> 3);
+                if (PF & 2) prefetch_l1(a); else prefetch_l2(a);
             }
         }
-        {
-            const uint32_t ref = (uint32_t)~node;
-            const uint32_t first = ref >> 3, count = (ref & 7u) + 1u;
-            for (uint32_t i = 0; i < count; ++i) {
-                const float4 v0 = ldg(tris + 3 * (first + i) + 0);
-                const float4 v1 = ldg(tris + 3 * (first + i) + 1);
-                const float4 v2 = ldg(tris + 3 * (first + i) + 2);
-                const bool acc = tri_test(v0, v1, v2, r, best);
-                if (ANY && acc) { st.node = MIRO_BVH2_DONE; return true; }
-            }
-            if (sp == 0) { st.node = MIRO_BVH2_DONE; return true; }
-            node = stack[--sp];
-            if (--budget <= 0) { st.node = node; st.sp = sp; return false; }
+        if ((PF & 4) && next < 0) {
+            const float4* a = tris + 4 * (size_t)(((uint32_t)~next) >> 3);
+            if (PF & 2) prefetch_l1(a); else prefetch_l2(a);
         }
+        w.node = next;
     }
+}
+
+template <bool ANY>
+MIRO_HD void bvh2_leaf_step(const float4* __restrict__ tris, const mirogpu_ray& r, Bvh2Walk& w, const int32_t* __restrict__ stack,
+                            BestHit& best)
+{
+    const uint32_t ref = (uint32_t)~w.node;
+    const uint32_t first = ref >> 3, count = (ref & 7u) + 1u;
+    for (uint32_t i = 0; i < count; ++i) {
+        const F8 ta = ld256(tris + 4 * (size_t)(first + i)), tb = ld256(tris + 4 * (size_t)(first + i) + 2);
+        const bool acc = tri_test(ta.lo, ta.hi, tb.lo, tb.hi, r, best);
+        if (ANY && acc) { w.node = MIRO_BVH2_DONE; return; }
+    }
+    bvh2_pop(w, stack);
 }
 
 // ---- CWBVH8 (80-byte nodes, eight 8-bit-quantised child boxes per fetch) --------------------------------
@@ -382,11 +437,9 @@ MIRO_HD void trace_cwbvh8(const uint4* __restrict__ nodes, const float4* __restr
             const int bit = bfind32(T.y);
             T.y &= ~(1u << bit);
             const uint32_t ti = T.x + (uint32_t)bit;
-            const float4 v0 = ldg(tris + 3 * (size_t)ti + 0);
-            const float4 v1 = ldg(tris + 3 * (size_t)ti + 1);
-            const float4 v2 = ldg(tris + 3 * (size_t)ti + 2);
+            const F8 ta = ld256(tris + 4 * (size_t)ti), tb = ld256(tris + 4 * (size_t)ti + 2);
             if (COUNT) cnt->tris++;
-            const bool acc = tri_test(v0, v1, v2, r, best);
+            const bool acc = tri_test(ta.lo, ta.hi, tb.lo, tb.hi, r, best);
             if (ANY && acc) return;
         }
         if ((G.y & 0xff000000u) == 0u) {

@@ -120,6 +120,10 @@ typedef struct mirogpu_scene_info {
 } mirogpu_scene_info;
 
 enum { MIROGPU_CLOSEST_HIT = 0, MIROGPU_ANY_HIT = 1 };
+/* Optional hint or-ed into a query mode: the batch is coherent (neighbouring rays start close together and point
+ * the same way, e.g. camera rays in pixel order).  Coherent batches go to the packet kernel (32 consecutive rays per
+ * warp, while-while), everything else to the hybrid-scheduled kernel with ray replacement.  Results are identical. */
+enum { MIROGPU_HINT_COHERENT = 0x100 };
 
 /* mode bits for mirogpu_render */
 enum {
@@ -184,8 +188,9 @@ int mirogpu_intersect_batch_device(mirogpu_handle h, const mirogpu_ray* d_rays, 
 /* Same query through the instrumented kernel; counters are accumulated into *c (host struct). */
 int mirogpu_intersect_batch_counted(mirogpu_handle h, const mirogpu_ray* rays, size_t n, mirogpu_hit* hits,
                                     int mode, mirogpu_counters* c);
-/* Kernel variant selection for measurement: 0 = persistent warps with ray replacement (default; BVH2) /
- * 32-ray tickets (CWBVH8), 1 = one thread per ray, 2 = persistent warps with plain 32-ray tickets. */
+/* Kernel variant selection for measurement: -1 = automatic (default: hybrid kernel for BVH2 unless the batch carries
+ * MIROGPU_HINT_COHERENT; packet kernel for CWBVH8), 0 = persistent warps taking 32-ray packets (while-while),
+ * 1 = one thread per ray, 2 = persistent warps with hybrid step scheduling + ray replacement (BVH2 only). */
 int mirogpu_set_kernel_variant(mirogpu_handle h, int variant);
 
 /* Reconstructs P, N (normalised as Scene::trace does for UV materials, Scene.cpp:262) and material id

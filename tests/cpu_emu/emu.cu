@@ -17,6 +17,9 @@ using namespace mirogpu;
 extern "C" int emu_trace(const float* tri_vertices, uint32_t ntris, int layout, int max_leaf, const mirogpu_ray* rays,
                          long n, mirogpu_hit* hits, int any_hit, unsigned long long* counters3, uint32_t* info4)
 {
+    // layout 2: the BVH2 tree walked through the single-step functions of the hybrid kernel
+    const int walk = layout >= 2 ? layout : 0;
+    if (layout >= 2) layout = MIROGPU_LAYOUT_BVH2;
     if (max_leaf <= 0) max_leaf = layout == MIROGPU_LAYOUT_CWBVH8 ? 3 : 4;
     if (layout == MIROGPU_LAYOUT_CWBVH8 && max_leaf > 3) max_leaf = 3;
     BinaryBvh bin = build_binary_sah(tri_vertices, ntris, max_leaf, 32);
@@ -36,7 +39,18 @@ extern "C" int emu_trace(const float* tri_vertices, uint32_t ntris, int layout, 
     for (long i = 0; i < n; ++i) {
         BestHit best;
         TraceCounters c = {0, 0, 0};
-        if (layout == MIROGPU_LAYOUT_BVH2) {
+        if (walk) {
+            Bvh2Walk st;
+            int32_t stack[MIRO_STACK + 1];
+            bvh2_begin(rays[i], st, best);
+            while (st.node != MIRO_BVH2_DONE) {
+                if (st.node >= 0) { bvh2_node_step<0>(nodes, tr, rays[i], st, stack, best); ++c.nodes; }
+                else {
+                    ++c.tris;
+                    if (any_hit) bvh2_leaf_step<true>(tr, rays[i], st, stack, best); else bvh2_leaf_step<false>(tr, rays[i], st, stack, best);
+                }
+            }
+        } else if (layout == MIROGPU_LAYOUT_BVH2) {
             if (any_hit) trace_bvh2<true, true>(nodes, tr, rays[i], best, &c); else trace_bvh2<false, true>(nodes, tr, rays[i], best, &c);
         } else {
             const uint4* n8 = reinterpret_cast<const uint4*>(nodes);

@@ -8,8 +8,9 @@ BVH2_NODE = np.dtype([("f", np.float32, 12), ("link", np.int32, 4)])
 CW_NODE = np.dtype([("p", np.float32, 3), ("e", np.uint8, 3), ("imask", np.uint8), ("child_base", np.uint32), ("tri_base", np.uint32),
                     ("meta", np.uint8, 8), ("qlox", np.uint8, 8), ("qloy", np.uint8, 8), ("qloz", np.uint8, 8),
                     ("qhix", np.uint8, 8), ("qhiy", np.uint8, 8), ("qhiz", np.uint8, 8)])
-TRI_REC = np.dtype([("a", np.float32, 3), ("prim_id", np.uint32), ("e1", np.float32, 3), ("pad0", np.float32), ("e2", np.float32, 3), ("pad1", np.float32)])
-assert BVH2_NODE.itemsize == 64 and CW_NODE.itemsize == 80 and TRI_REC.itemsize == 48
+TRI_REC = np.dtype([("a", np.float32, 3), ("prim_id", np.uint32), ("e1", np.float32, 3), ("nx", np.float32), ("e2", np.float32, 3), ("ny", np.float32),
+                    ("nz", np.float32), ("pad", np.float32, 3)])
+assert BVH2_NODE.itemsize == 64 and CW_NODE.itemsize == 80 and TRI_REC.itemsize == 64
 
 
 def emu_trace(emu, verts, rays, layout, any_hit=False, max_leaf=0):

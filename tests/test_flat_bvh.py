@@ -31,6 +31,11 @@ def test_bvh2_boxes_contain_reference_bounds(emu, oracle, scenes, name):
     assert sorted(order.tolist()) == list(range(V.shape[0]))            # a permutation: every triangle exactly once
     assert np.array_equal(tris["prim_id"], order)
     assert np.array_equal(tris["a"], V[order, 0:3]) and np.array_equal(tris["e1"], V[order, 3:6] - V[order, 0:3])
+    # the stored plane normal is cross(B-A, C-A) in separately rounded binary32 operations (Triangle.cpp:151)
+    e1, e2 = tris["e1"], tris["e2"]
+    assert np.array_equal(tris["nx"], e1[:, 1] * e2[:, 2] - e1[:, 2] * e2[:, 1])
+    assert np.array_equal(tris["ny"], e1[:, 2] * e2[:, 0] - e1[:, 0] * e2[:, 2])
+    assert np.array_equal(tris["nz"], e1[:, 0] * e2[:, 1] - e1[:, 1] * e2[:, 0])
     tlo, thi = _tri_bounds(V)
     tlo, thi = tlo[order], thi[order]
 

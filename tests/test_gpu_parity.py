@@ -26,6 +26,11 @@ LAYOUTS = [0, 1]
 GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "ref_hits.npz")
 
 
+def pkg_mod():
+    import importlib
+    return importlib.import_module("cse168-raytracer_b200")
+
+
 def ids_of(hits):
     i = hits["prim_id"].astype(np.int64)
     i[i == 0xFFFFFFFF] = -1
@@ -69,12 +74,13 @@ def test_closest_hit_equals_exhaustive_search(host_scenes, oracle_scene, name, l
     V = O.dump_triangles()[:, :9].reshape(-1, 3)
     rays = np.concatenate([O.eye_rays(128, 128), random_rays(20000, V.min(0), V.max(0), 42)])
     bt, bid, bP, bN = O.trace_brute(rays)
-    for variant in (0, 1, 2):
+    for variant in (-1, 0, 1, 2):   # automatic, 32-ray packets, one thread per ray, hybrid scheduling + ray replacement
         S.set_kernel_variant(variant)
-        hits = S.intersect(rays)
-        assert np.array_equal(ids_of(hits), bid)
-        assert np.array_equal(bits(hits["t"]), bits(bt))
-    S.set_kernel_variant(0)
+        for mode in (pkg_mod().CLOSEST_HIT, pkg_mod().CLOSEST_HIT | pkg_mod().HINT_COHERENT):
+            hits = S.intersect(rays, mode=mode)
+            assert np.array_equal(ids_of(hits), bid)
+            assert np.array_equal(bits(hits["t"]), bits(bt))
+    S.set_kernel_variant(-1)
 
 
 @pytest.mark.parametrize("layout", LAYOUTS)
@@ -245,7 +251,7 @@ def test_counters(host_scenes, pkg, layout):
     assert np.array_equal(hits, S.intersect(rays))
     assert c.rays == rays.shape[0] and c.hits == int((ids_of(hits) >= 0).sum())
     assert c.node_visits > 0 and c.triangle_tests > 0
-    assert c.bytes_fetched == c.node_visits * (64 if layout == 0 else 80) + c.triangle_tests * 48
+    assert c.bytes_fetched == c.node_visits * (64 if layout == 0 else 80) + c.triangle_tests * 64
 
 
 def test_full_size_properties_bunny20(host_scenes, pkg):
@@ -284,10 +290,10 @@ def test_full_size_properties_bunny20(host_scenes, pkg):
         anyh = S.intersect(rays, mode=pkg.ANY_HIT)
         assert np.array_equal(ids_of(anyh) >= 0, hit)
         # (4) both layouts and both kernel variants give the same answer
-        for variant in (1, 2):
+        for variant in (0, 1, 2):
             S.set_kernel_variant(variant)
             assert np.array_equal(S.intersect(rays), hits)
-        S.set_kernel_variant(0)
+        S.set_kernel_variant(-1)
         # (5) barycentrics of accepted hits respect the reference's epsilon slop
         assert (hits["beta"][hit] >= -1e-4).all() and (hits["gamma"][hit] >= -1e-4).all()
         assert (hits["beta"][hit] + hits["gamma"][hit] <= 1 + 1e-4 + 1e-7).all()
