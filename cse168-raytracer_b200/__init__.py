@@ -82,7 +82,7 @@ EXPORTS = [
     "mirogpu_intersect_batch", "mirogpu_intersect_batch_device", "mirogpu_intersect_batch_counted", "mirogpu_set_kernel_variant",
     "mirogpu_resolve_hits_device", "mirogpu_generate_primary_device", "mirogpu_generate_bounce_device", "mirogpu_rng_uniforms",
     "mirogpu_render", "mirogpu_render_rgb8", "mirogpu_tonemap_rgb8_device", "mirogpu_render_device", "mirogpu_last_call_stats", "mirogpu_photon_upload", "mirogpu_photon_gather",
-    "mirogpu_photon_gather_device",
+    "mirogpu_photon_gather_device", "mirogpu_photon_trace",
 ]
 
 
@@ -307,6 +307,14 @@ class MiroScene:
                                          ctypes.c_float(max_dist), int(k), _ptr(irr)))
         return irr
 
+    def photon_trace(self, light_index, caustic, seed, first, count):
+        """Scene::tracePhoton for emissions [first, first+count): returns (counts uint8 (count,), records float32 (count, 5, 9))."""
+        counts = np.zeros(count, np.uint8)
+        records = np.zeros((count, 5, 9), np.float32)
+        _check(lib.mirogpu_photon_trace(self._h, int(light_index), int(caustic), ctypes.c_uint32(seed), ctypes.c_uint64(first),
+                                        ctypes.c_uint32(count), _ptr(counts), _ptr(records)))
+        return counts, records
+
     def photon_gather_device(self, which, d_pos, d_normal, d_irr, max_dist=1e10, k=500):
         _check(lib.mirogpu_photon_gather_device(self._h, int(which), _ptr(d_pos), _ptr(d_normal), ctypes.c_size_t(d_pos.shape[0]),
                                                 ctypes.c_float(max_dist), int(k), _ptr(d_irr), _stream()))
@@ -340,6 +348,7 @@ def host_lib():
         _host.mh_precalc.restype = ctypes.c_double
         _host.mh_render.restype = ctypes.c_double
         _host.mh_scene_handle.restype = ctypes.c_void_p
+        _host.mh_trace_photons.restype = ctypes.c_long
     return _host
 
 
@@ -437,6 +446,14 @@ class HostScene:
         return out
 
     # photon maps
+    def set_photon_counts(self, global_photons, caustic_photons):
+        """Scene::PhotonsPerLightSource / CausticPhotonsPerLightSource for the next precalc() (this driver starts at 0 / 0)."""
+        self.h.mh_set_photon_counts(int(global_photons), int(caustic_photons))
+
+    def trace_photons(self, which):
+        """Scene::tracePhotons (which = 0) / traceCausticPhotons (1) on the device; returns the emissions consumed."""
+        return int(self.h.mh_trace_photons(int(which)))
+
     def pm_store(self, which, power, pos, direction):
         power = np.ascontiguousarray(power, np.float32).reshape(-1, 3)
         pos = np.ascontiguousarray(pos, np.float32).reshape(-1, 3)

@@ -26,6 +26,7 @@ public:
     void irradiance_estimate_batch(float* irrad3, const float* pos3, const float* normal3, size_t n, float max_dist, int nphotons) const;
     void attach(mirogpu_handle h, int which);   // uploads the balanced array to the device as map `which`
     int stored() const { return stored_photons; }
+    bool balanced() const { return m_balanced; }
     const Photon* data() const { return photons; }
 private:
     void balance_segment(Photon** pbal, Photon** porg, const int index, const int start, const int end);
@@ -35,5 +36,6 @@ private:
     float bbox_min[3], bbox_max[3];
     mirogpu_handle m_handle;
     int m_which;
+    bool m_balanced;
 };
 #endif

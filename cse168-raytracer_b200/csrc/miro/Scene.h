@@ -31,11 +31,20 @@ public:
     Photon_map& photonMap() { return *m_photonMap; }
     Photon_map& causticMap() { return *m_causticMap; }
     void setPhotonMapsEnabled(bool on) { m_usePhotonMaps = on; }
+    // Scene::tracePhotons / traceCausticPhotons (Scene.cpp:351-472): emit from every DirectionalAreaLight until the
+    // target number of photons is stored, scale by 1 / emissions, balance, upload.  The walks run on the device
+    // (mirogpu_photon_trace); store / scale / balance are the host's Photon_map.  Both are called by preCalc(), like
+    // the reference; a target of 0 only balances.  Return value: emissions consumed (the reference's totalPhotons).
+    long tracePhotons();
+    long traceCausticPhotons();
+    // Scene.h:67-68 (static const in the reference)
+    int PhotonsPerLightSource, CausticPhotonsPerLightSource;
     // render controls the reference fixes at compile time (Miro.h:13-15, -DDISABLE_SHADOWS)
     int renderSpp, renderJitter, renderMode, renderShadows;
     unsigned renderSeed;
     double lastRenderSeconds;
 protected:
+    long tracePhotonPass(Photon_map& map, int which, int target, bool caustic);
     void postProcess(HitInfo& minHit) const;
     Objects m_objects, m_unboundedObjects;
     Photon_map* m_photonMap;

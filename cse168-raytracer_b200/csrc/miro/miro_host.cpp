@@ -359,7 +359,8 @@ void Image::writePPM(const char* pcFile)
 
 // ================================= Scene =====================================================================
 Scene::Scene()
-    : renderSpp(1), renderJitter(0), renderMode(MIROGPU_RENDER_WHITTED), renderShadows(1), renderSeed(168), lastRenderSeconds(0),
+    : PhotonsPerLightSource(200000), CausticPhotonsPerLightSource(200000),
+      renderSpp(1), renderJitter(0), renderMode(MIROGPU_RENDER_WHITTED), renderShadows(1), renderSeed(168), lastRenderSeconds(0),
       m_bgColor(0.f), m_usePhotonMaps(false)
 {
     // the reference reserves 20.1 M photons per map up front (Scene.h:18); maps here grow on store()
@@ -388,8 +389,59 @@ void Scene::preCalc()
         ls.push_back(l);
     }
     if (mirogpu_scene_set_lights(m_bvh.handle(), ls.empty() ? 0 : ls.data(), (uint32_t)ls.size()) != MIROGPU_OK) fatal("Scene::preCalc lights");
+    // Scene.cpp:76-82: generate the photon maps (only DirectionalAreaLights emit, Scene.cpp:368)
+    bool emitter = false;
+    for (size_t i = 0; i < ls.size(); ++i) emitter |= ls[i].kind == 1;
+    if (emitter) {
+        tracePhotons();
+        traceCausticPhotons();
+    }
     if (m_photonMap->stored() > 0) m_photonMap->attach(m_bvh.handle(), 0);
     if (m_causticMap->stored() > 0) m_causticMap->attach(m_bvh.handle(), 1);
+}
+
+long Scene::tracePhotons() { return tracePhotonPass(*m_photonMap, 0, PhotonsPerLightSource, false); }
+long Scene::traceCausticPhotons() { return tracePhotonPass(*m_causticMap, 1, CausticPhotonsPerLightSource, true); }
+
+long Scene::tracePhotonPass(Photon_map& map, int which, int target, bool caustic)
+{
+    if (target == 0) {                                         // Scene.cpp:353-357
+        if (!map.balanced()) map.balance();                    // (a map the caller filled and balanced by hand stays as it is)
+        return 0;
+    }
+    long totalPhotons = 0;                                     // emissions consumed
+    int photonsAdded = 0;                                      // photons stored; neither is reset per light (Scene.cpp:360-361)
+    const long kMaxEmissions = 1L << 28;                       // the reference loops forever when nothing can be stored
+    std::vector<uint8_t> counts;
+    std::vector<float> records;
+    for (size_t l = 0; l < m_lights.size(); ++l) {
+        if (dynamic_cast<DirectionalAreaLight*>(m_lights[l]) == 0) continue;
+        uint64_t next = 0;                                     // emission index of this light = its random stream
+        uint32_t batch = 65536;
+        while (photonsAdded < target && totalPhotons < kMaxEmissions) {
+            counts.resize(batch); records.resize((size_t)batch * 45);
+            if (mirogpu_photon_trace(m_bvh.handle(), (int)l, caustic ? 1 : 0, renderSeed + (caustic ? 1u : 0u), ((uint64_t)l << 40) | next, batch,
+                                     counts.data(), records.data()) != MIROGPU_OK) fatal("Scene::tracePhotons");
+            const int before = photonsAdded;
+            uint32_t used = 0;
+            for (uint32_t i = 0; i < batch && photonsAdded < target; ++i, ++used) {   // "if (photonsAdded < PhotonsPerLightSource)", in emission order
+                const float* r = records.data() + (size_t)i * 45;
+                for (int j = 0; j < counts[i]; ++j) map.store(r + 9 * j, r + 9 * j + 3, r + 9 * j + 6);
+                photonsAdded += counts[i];
+                totalPhotons++;
+            }
+            next += used;
+            // size the next batch from the observed yield (photons per emission), with some slack
+            const double yield = std::max(1e-4, (double)(photonsAdded - before) / (double)std::max<uint32_t>(used, 1));
+            const double want = (double)(target - photonsAdded) / yield * 1.05 + 1024.0;
+            batch = (uint32_t)std::min(4194304.0, std::max(4096.0, want));
+        }
+    }
+    if (totalPhotons >= kMaxEmissions) fprintf(stderr, "Scene::tracePhotons: gave up after %ld emissions (%d of %d photons stored)\n", totalPhotons, photonsAdded, target);
+    if (totalPhotons > 0) map.scale_photon_power(1.0f / (float)totalPhotons);
+    map.balance();
+    if (map.stored() > 0) map.attach(m_bvh.handle(), which);
+    return totalPhotons;
 }
 
 // Scene.cpp:232-266 for UV-lookup materials with zero bump height: the perturbation vanishes, N is normalised.
@@ -447,7 +499,7 @@ void Scene::raytraceImage(Camera* cam, Image* img)
 
 // ================================= Photon_map ================================================================
 Photon_map::Photon_map(int max_phot)
-    : photons(0), stored_photons(0), half_stored_photons(0), max_photons(max_phot), prev_scale(1), m_handle(0), m_which(0)
+    : photons(0), stored_photons(0), half_stored_photons(0), max_photons(max_phot), prev_scale(1), m_handle(0), m_which(0), m_balanced(false)
 {
     photons = (Photon*)malloc(sizeof(Photon) * ((size_t)std::max(max_photons, 0) + 1));
     bbox_min[0] = bbox_min[1] = bbox_min[2] = 1e8f;
@@ -462,6 +514,7 @@ void Photon_map::store(const float power[3], const float pos[3], const float dir
         max_photons = max_photons ? 2 * max_photons : 1024;
         photons = (Photon*)realloc(photons, sizeof(Photon) * ((size_t)max_photons + 1));
     }
+    m_balanced = false;
     Photon* const node = &photons[++stored_photons];
     for (int i = 0; i < 3; ++i) {
         node->pos[i] = pos[i];
@@ -547,6 +600,7 @@ void Photon_map::balance(void)
         memcpy(photons, ordered.data(), sizeof(Photon) * ((size_t)stored_photons + 1));
     }
     half_stored_photons = stored_photons / 2 - 1;
+    m_balanced = true;
 }
 
 void Photon_map::attach(mirogpu_handle h, int which)

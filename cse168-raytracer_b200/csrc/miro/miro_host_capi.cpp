@@ -27,6 +27,7 @@ void mh_new_scene()
 {
     delete g_scene; delete g_camera; delete g_image;
     g_scene = new Scene; g_camera = new Camera; g_image = new Image;
+    g_scene->PhotonsPerLightSource = g_scene->CausticPhotonsPerLightSource = 0;   // see mh_set_photon_counts
     g_materials.clear(); g_prim_id.clear();
 }
 
@@ -78,6 +79,14 @@ void mh_add_directional_light(const float* pos, const float* normal, float radiu
     l->setColor(Vector3(color[0], color[1], color[2])); l->setWattage(wattage);
     g_scene->addLight(l);
 }
+
+// Photon targets of the next preCalc (Scene.h:67-68).  The driver starts every scene at 0 / 0 so that scenes with a
+// DirectionalAreaLight do not trace photons unless a test asks for them.
+void mh_set_photon_counts(int global_photons, int caustic_photons)
+{
+    g_scene->PhotonsPerLightSource = global_photons; g_scene->CausticPhotonsPerLightSource = caustic_photons;
+}
+long mh_trace_photons(int which) { return which == 0 ? g_scene->tracePhotons() : g_scene->traceCausticPhotons(); }
 
 void mh_set_bg_color(const float* c) { g_scene->setBgColor(Vector3(c[0], c[1], c[2])); }
 

@@ -65,6 +65,7 @@ struct mirogpu_scene {
     uint32_t nmaterials = 0;
     mirogpu_light* d_lights = nullptr;
     uint32_t nlights = 0;
+    std::vector<mirogpu_light> h_lights;   // host copy (photon emission parameters are derived on the host)
     unsigned long long* d_ticket = nullptr;  // persistent-kernel ticket counters (ring of 64)
     std::atomic<uint32_t> ticket_slot{0};
     mirogpu_scene_info info{};
@@ -172,6 +173,7 @@ void camera_basis(const mirogpu_camera& c, int W, int H, CameraBasis& b)
 // RenderScratch / render + photon implementations need the pieces above.
 #include "photon_impl.cuh"
 #include "render_impl.cuh"
+#include "photon_trace_impl.cuh"
 
 extern "C" {
 
@@ -343,12 +345,13 @@ int mirogpu_scene_set_lights(mirogpu_handle h, const mirogpu_light* lights, uint
     if (!h || (nlights && !lights)) return fail(MIROGPU_ERR_INVALID_ARG, "NULL argument");
     CUDA_TRY(cudaSetDevice(h->device));
     std::lock_guard<std::mutex> lk(h->mtx);
-    cudaFree(h->d_lights); h->d_lights = nullptr; h->nlights = 0;
+    cudaFree(h->d_lights); h->d_lights = nullptr; h->nlights = 0; h->h_lights.clear();
     if (nlights) {
         CUDA_TRY(cudaMalloc(&h->d_lights, nlights * sizeof(mirogpu_light)));
         CUDA_TRY(cudaMemcpy(h->d_lights, lights, nlights * sizeof(mirogpu_light), cudaMemcpyHostToDevice));
         h->nlights = nlights;
     }
+    h->h_lights.assign(lights, lights + nlights);
     return MIROGPU_OK;
 }
 
@@ -577,6 +580,55 @@ int mirogpu_tonemap_rgb8_device(mirogpu_handle h, const float* d_rgb, int width,
     k_frame_max<<<(unsigned)((nvals + 255) / 256), 256, 0, st>>>(d_rgb, nvals, gmax);
     k_tonemap<<<(unsigned)((nvals + 255) / 256), 256, 0, st>>>(const_cast<float*>(d_rgb), d_rgb8, width, 0, 1, height, gmax);
     CUDA_TRY(cudaGetLastError());
+    return MIROGPU_OK;
+}
+
+int mirogpu_photon_trace(mirogpu_handle h, int light_index, int caustic, uint32_t seed, uint64_t first_emission, uint32_t count,
+                         uint8_t* counts, float* records)
+{
+    if (!h || (count && (!counts || !records))) return fail(MIROGPU_ERR_INVALID_ARG, "NULL argument");
+    if (light_index < 0 || (size_t)light_index >= h->h_lights.size()) return fail(MIROGPU_ERR_INVALID_ARG, "light index out of range");
+    const mirogpu_light& L = h->h_lights[(size_t)light_index];
+    if (L.kind != 1) return fail(MIROGPU_ERR_INVALID_ARG, "photons are emitted from DirectionalAreaLights only (Scene.cpp:368)");
+    if (count == 0) return MIROGPU_OK;
+    CUDA_TRY(cudaSetDevice(h->device));
+    PhotonEmitter em; memset(&em, 0, sizeof em);
+    // getTangents (Utility.h:25-31), as SquareLight::preCalc calls it on the light normal
+    const float n[3] = {L.normal[0], L.normal[1], L.normal[2]};
+    float t1[3] = {0.f * n[2] - 1.f * n[1], 1.f * n[0] - 0.f * n[2], 0.f * n[1] - 0.f * n[0]};                 // cross((0,0,1), n)
+    if ((double)(t1[0] * t1[0] + t1[1] * t1[1] + t1[2] * t1[2]) < 1e-6) {
+        t1[0] = 1.f * n[2] - 0.f * n[1]; t1[1] = 0.f * n[0] - 0.f * n[2]; t1[2] = 0.f * n[1] - 1.f * n[0];        // cross((0,1,0), n)
+    }
+    const float t2[3] = {t1[1] * n[2] - t1[2] * n[1], t1[2] * n[0] - t1[0] * n[2], t1[0] * n[1] - t1[1] * n[0]};   // cross(t1, n)
+    // power = color * wattage, then *= PI r r (/ 10.f for the caustic pass): Scene.cpp:379-385, 431-434
+    const float pi = 3.1415926535897932384626433832795028841972f;
+    const float area = caustic ? pi * L.radius * L.radius / 10.f : pi * L.radius * L.radius;
+    for (int k = 0; k < 3; ++k) {
+        em.pos[k] = L.position[k]; em.normal[k] = n[k]; em.t1[k] = t1[k]; em.t2[k] = t2[k];
+        em.power[k] = L.color[k] * L.wattage * area;
+    }
+    em.radius = L.radius; em.caustic = caustic ? 1 : 0; em.seed = seed; em.first = first_emission; em.count = count;
+    unsigned char* d_counts = nullptr;
+    float* d_records = nullptr;
+    const size_t rec_bytes = (size_t)count * 9 * MIRO_PHOTON_MAX_RECORDS * sizeof(float);
+    cudaError_t e = cudaMalloc(&d_counts, count);
+    if (e == cudaSuccess) e = cudaMalloc(&d_records, rec_bytes);
+    if (e == cudaSuccess) e = cudaMemsetAsync(d_records, 0, rec_bytes, cudaStreamPerThread);
+    if (e == cudaSuccess) {
+        const unsigned grid = (count + 127) / 128;
+        if (h->layout == MIROGPU_LAYOUT_BVH2) k_photon_trace<MIROGPU_LAYOUT_BVH2><<<grid, 128, 0, cudaStreamPerThread>>>(h->ds, h->d_materials, em, d_counts, d_records);
+        else k_photon_trace<MIROGPU_LAYOUT_CWBVH8><<<grid, 128, 0, cudaStreamPerThread>>>(h->ds, h->d_materials, em, d_counts, d_records);
+        e = cudaGetLastError();
+    }
+    if (e == cudaSuccess) e = cudaMemcpyAsync(counts, d_counts, count, cudaMemcpyDeviceToHost, cudaStreamPerThread);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(records, d_records, rec_bytes, cudaMemcpyDeviceToHost, cudaStreamPerThread);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(cudaStreamPerThread);
+    cudaFree(d_counts); cudaFree(d_records);
+    if (e != cudaSuccess) return fail(MIROGPU_ERR_CUDA, std::string("photon_trace: ") + cudaGetErrorString(e));
+    {
+        std::lock_guard<std::mutex> lk(h->mtx);
+        h->last_rays = 0; h->last_launches = 1; h->stats_batches = 0;
+    }
     return MIROGPU_OK;
 }
 

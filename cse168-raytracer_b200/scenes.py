@@ -87,6 +87,32 @@ SCENES = {
         meshes=[("bunny", t, 0) for t in _bunny20_transforms()], triangles=[(FLOOR_BIG, 0)], materials=[LAMBERT_WHITE],
         lights=[dict(kind=0, pos=(10, 20, 10), color=(1, 1, 1), wattage=1000)],
         camera=dict(eye=(0, 5, 15), lookat=(0, 0, 0), up=(0, 1, 0), fov=45), size=(1920, 1080)),
+    # config 4 -- makeFlowerScene (assignment3.cpp:54-121) with the assets the reference tree holds: Petals2 + Stem + Leaf +
+    # WaterDrops.obj (stand-in for the missing WaterDropsMany.obj; FlowerCenter.obj is missing too).  The procedural
+    # textures are out of scope: flat colours; background colour instead of the missing HDR map.
+    "flower": dict(
+        meshes=[("Petals2", None, 0), ("Stem", None, 1), ("Leaf", None, 2), ("WaterDrops", None, 3)], triangles=[],
+        materials=[dict(kd=(0.9, 0.35, 0.55), ks=(0, 0, 0), kt=(0, 0, 0), shininess=500.0, refr=1.5),
+                   dict(kd=(0.25, 0.6, 0.2), ks=(0, 0, 0), kt=(0, 0, 0), shininess=1.0, refr=1.0),
+                   dict(kd=(0.1, 0.5, 0.15), ks=(0, 0, 0), kt=(0, 0, 0), shininess=1.0, refr=1.0),
+                   dict(kd=(1, 1, 1), ks=(0, 0, 0), kt=(1, 1, 1), shininess=250.0, refr=1.33)],       # assignment3.cpp:105
+        lights=[dict(kind=1, pos=(50, 50, 40), normal=tuple(-np.array([50, 50, 40.0]) / np.linalg.norm([50, 50, 40.0])), radius=7.0,
+                     color=(1, 1, 1), wattage=4)],                                                        # assignment3.cpp:78-86
+        bg=(1, 1, 1),
+        camera=dict(eye=(2, 4.4, 16.8), lookat=(3, 0, 4), up=(0, 1, 0), fov=30), size=(2048, 1365)),
+    # config 5 -- the cornell box in four material groups + WaterDrops.obj as caustic caster (assignment2.cpp:414-438),
+    # lit by a DirectionalAreaLight so that photons are emitted (Scene.cpp:368).  The reference script's placement
+    # (-2,-0.5,0) leaves the drops outside the light's downward beam (z > -0.23 against the disc's z in [-3.5,-1.5]); its
+    # caustic pass then never stores a photon and Scene::traceCausticPhotons loops forever (observed with the reference
+    # compiled here).  The drops are therefore moved under the light: translate(-1.1, 0.9, -3.8).
+    "cornell_drops": dict(
+        meshes=[("cornell_box_1", None, 0), ("cornell_box_2", None, 1), ("cornell_box_3", None, 2), ("cornell_box_4", None, 0),
+                ("WaterDrops", translate(-1.1, 0.9, -3.8).astype(np.float32), 3)], triangles=[],
+        materials=[LAMBERT_WHITE, dict(kd=(1, 0, 0), ks=(0, 0, 0), kt=(0, 0, 0), shininess=1.0, refr=1.0),
+                   dict(kd=(0, 1, 0), ks=(0, 0, 0), kt=(0, 0, 0), shininess=1.0, refr=1.0),
+                   dict(kd=(1, 1, 1), ks=(0, 0, 0), kt=(1, 1, 1), shininess=5.0, refr=1.5)],            # assignment2.cpp:433
+        lights=[dict(kind=1, pos=(2.5, 5.4, -2.5), normal=(0, -1, 0), radius=1.0, color=(1, 1, 1), wattage=160)],
+        camera=dict(eye=(2.5, 3, 3), lookat=(2.5, 2.5, 0), up=(0, 1, 0), fov=90), size=(512, 512)),
     # two-triangle smoke geometry (models/testobj.obj)
     "testobj": dict(
         meshes=[("testobj", None, 0)], triangles=[], materials=[LAMBERT_WHITE],
@@ -111,6 +137,8 @@ def realise(builder, name, obj_path_of):
             builder.add_point_light(l["pos"], l["color"], l["wattage"])
         else:
             builder.add_directional_light(l["pos"], l["normal"], l["radius"], l["color"], l["wattage"])
+    if "bg" in sc and hasattr(builder, "set_bg_color"):
+        builder.set_bg_color(sc["bg"])
     c = sc["camera"]
     builder.set_camera(c["eye"], c["lookat"], c["up"], c["fov"])
     return sc

@@ -15,6 +15,8 @@
  *                                  + Phong::shade's light loop and shadow query       Phong.cpp:44-161
  *   mirogpu_photon_upload       <- the balanced Photon array Photon_map::balance leaves   PhotonMap.cpp:314-359
  *   mirogpu_photon_gather       <- Photon_map::irradiance_estimate / locate_photons   PhotonMap.cpp:81-243
+ *   mirogpu_photon_trace        <- Scene::tracePhoton over the emissions of Scene::tracePhotons /
+ *                                  traceCausticPhotons                                     Scene.cpp:351-472, 526-641
  *
  * Conventions: every function returns an int status (MIROGPU_OK = 0), never throws, keeps no global
  * state besides the per-thread last-error string, and works on an opaque scene handle.  The caller owns
@@ -236,6 +238,18 @@ int mirogpu_last_call_stats(mirogpu_handle h, uint64_t* rays_traced, uint64_t* k
 /* which: 0 = global map, 1 = caustic map (Scene.h:58-59).  photons: (stored+1) records of the reference's
  * 28-byte Photon (PhotonMap.h:16-22) in the heap order Photon_map::balance produces; entry 0 is unused. */
 int mirogpu_photon_upload(mirogpu_handle h, int which, const void* photons, int stored);
+/* Scene::tracePhoton (Scene.cpp:526-641) for emissions [first_emission, first_emission + count) of light
+ * `light_index` -- a DirectionalAreaLight, the only kind the reference emits from (Scene.cpp:368): origin =
+ * samplePhotonOrigin (disc rejection sampling, DirectionalAreaLight.h:20-24), direction = the light normal, power =
+ * color * wattage * PI r^2, divided by 10 when caustic != 0 (Scene.cpp:379-385, 431-434).  Every emission is walked for
+ * up to TRACE_DEPTH_PHOTONS + 1 segments with the reference's roulette; a photon is recorded at each diffuse choice
+ * after the first hit (caustic pass: only once a specular surface has been left).  counts[i] (HOST, count bytes) = photons
+ * recorded by emission first_emission + i (0..5); records (HOST, count * 5 * 9 floats) holds for emission i up to five
+ * {power[3], pos[3], incoming dir[3]} triples at records + i*45.  Powers are unscaled: the caller stores them
+ * (Photon_map::store) in emission order until its target is met and scales by 1 / emissions (Scene.cpp:400).
+ * The walk is a pure function of (seed, emission index): any split of the range into calls / GPUs gives the same map. */
+int mirogpu_photon_trace(mirogpu_handle h, int light_index, int caustic, uint32_t seed, uint64_t first_emission, uint32_t count,
+                         uint8_t* counts, float* records);
 int mirogpu_photon_gather(mirogpu_handle h, int which, const float* pos3, const float* normal3, size_t n,
                           float max_dist, int k, float* irrad3);
 int mirogpu_photon_gather_device(mirogpu_handle h, int which, const float* d_pos3, const float* d_normal3, size_t n,

@@ -870,6 +870,92 @@ void pmBalance(PhotonMap* pm)
 // C interface -- mirrors oracle/ref_driver.cpp name for name (ref_* -> orc_*) so the same Python test
 // helper drives the reference, the oracle and (through mirogpu) the product.
 // =================================================================================================
+
+// ---- photon tracing: Scene::tracePhoton (Scene.cpp:526-641) and the emission of Scene::tracePhotons /
+// traceCausticPhotons (Scene.cpp:351-472).  The reference draws from an unseeded, racy rand(); every frand() here is a
+// counter-based uniform instead, a pure function of (seed, emission index, segment, purpose), the same stream the
+// device draws (Philox4x32-10, Salmon et al. SC'11: restated from the published algorithm), so a photon walk can be
+// compared emission by emission.  Per segment (1-based depth) one draw yields, in order: the roulette number
+// (Scene.cpp:543), the Fresnel coin (:621), and the two numbers of Ray::random (Ray.h:132-133).  The disc rejection
+// loop of sampleDisc (Utility.h:82-95) draws pair k = 0, 1, ... of purpose 4.
+static void philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0, uint32_t k1, uint32_t out[4])
+{
+    const uint32_t M0 = 0xD2511F53u, M1 = 0xCD9E8D57u, W0 = 0x9E3779B9u, W1 = 0xBB67AE85u;
+    for (int round = 0; round < 10; ++round) {
+        const uint64_t p0 = (uint64_t)M0 * c0, p1 = (uint64_t)M1 * c2;
+        const uint32_t n0 = (uint32_t)(p1 >> 32) ^ c1 ^ k0, n1 = (uint32_t)p1, n2 = (uint32_t)(p0 >> 32) ^ c3 ^ k1, n3 = (uint32_t)p0;
+        c0 = n0; c1 = n1; c2 = n2; c3 = n3;
+        k0 += W0; k1 += W1;
+    }
+    out[0] = c0; out[1] = c1; out[2] = c2; out[3] = c3;
+}
+static void uniform4(uint32_t seed, uint64_t index, uint32_t sample, uint32_t purpose, float u[4])
+{
+    uint32_t r[4];
+    philox4x32_10((uint32_t)index, sample, purpose, (uint32_t)(index >> 32), seed, 0x4D49524Fu, r);
+    for (int k = 0; k < 4; ++k) u[k] = (float)(r[k] >> 8) * (1.0f / 16777216.0f);
+}
+
+// One emission; returns the number of photons recorded (<= 5), records = {power[3], pos[3], dir[3]} each.
+static int tracePhotonWalk(const Light& L, const V3& t1, const V3& t2, bool caustic, uint32_t seed, uint64_t e, float* records)
+{
+    // Scene.cpp:379-388 (power) / :431-434 (caustic: / 10), DirectionalAreaLight.h:20-35
+    V3 power = L.color * L.wattage;
+    if (caustic) power = power * (PI * L.radius * L.radius / 10.f); else power = power * (PI * L.radius * L.radius);
+    V3 direction = L.normal;
+    V3 position;
+    {
+        float x_rand = 0, y_rand = 0;
+        for (uint32_t k = 0; k < 64; ++k) {
+            float u[4]; uniform4(seed, e, k, 4, u);
+            x_rand = (2 * u[0] - 1) * L.radius;
+            y_rand = (2 * u[1] - 1) * L.radius;
+            if (!(x_rand * x_rand + y_rand * y_rand > L.radius * L.radius)) break;
+        }
+        position = L.pos + (x_rand * t1 + y_rand * t2);
+    }
+    int depth = 0, n = 0;
+    Counters cn = {0, 0};
+    for (;;) {
+        if (depth > 5) return n;                                       // TRACE_DEPTH_PHOTONS, Miro.h:14
+        Ray ray; ray.o = position + kEps * direction; ray.d = direction;
+        Hit hit;
+        ++depth;
+        if (!sceneTrace(hit, ray, 0.0f, MIRO_TMAX, cn)) return n;
+        const Material& m = g->materials[hit.material];
+        float u[4]; uniform4(seed, e, (uint32_t)depth, 3, u);
+        const float rnd = u[0];
+        const V3 diffuseColor = m.kd;                                  // Phong::diffuse2D returns m_diffuse (Phong.h:20)
+        float prob[3];
+        prob[0] = average(diffuseColor);
+        prob[1] = prob[0] + average(m.ks);
+        prob[2] = prob[1] + average(m.kt);
+        if (rnd > prob[2]) return n;                                   // absorbed
+        if (rnd < prob[0]) {
+            if (depth > 1) {                                           // only indirect light is stored
+                float* r = records + 9 * n;
+                r[0] = power.x; r[1] = power.y; r[2] = power.z; r[3] = hit.P.x; r[4] = hit.P.y; r[5] = hit.P.z;
+                r[6] = direction.x; r[7] = direction.y; r[8] = direction.z;
+                ++n;
+            } else if (caustic) return 0;                              // caustic photons must leave a specular surface first
+            const float phi = std::asin(std::sqrt(u[2]));              // Ray::random, Ray.h:124-140
+            const float theta = 2.0f * PI * u[3];
+            const V3 dir = alignHemisphereToVector(hit.N, theta, phi);
+            position = hit.P + kEps * dir; direction = dir;
+            power = diffuseColor * power / prob[0];
+        } else if (rnd < prob[1]) {
+            if (!caustic && depth == 1) return n;
+            const Ray refl = reflectRay(ray, hit);
+            position = hit.P; direction = refl.d;
+        } else if (rnd < prob[2]) {
+            if (!caustic && depth == 1) return n;
+            const float Rs = reflectionCoefficient(ray, hit);
+            if (u[1] < Rs) { const Ray refl = reflectRay(ray, hit); position = hit.P; direction = refl.d; }
+            else { const Ray refr = refractRay(ray, hit); position = hit.P; direction = refr.d; }
+        } else return n;
+    }
+}
+
 extern "C" {
 
 void orc_new_scene()
@@ -1126,6 +1212,23 @@ void orc_tonemap(const float* rgb, long npix, unsigned char* out8)
         float m = 255 * v;
         out8[i] = m > 255 ? 255 : (unsigned char)m;
     }
+}
+
+
+// Emissions [first, first + count) of light `light`: counts[i] photons recorded by emission first + i, records
+// [i*45 .. ) = up to five {power, pos, dir} triples.  Powers are unscaled (the caller divides by the number of
+// emissions, Scene.cpp:400).
+void orc_trace_photons(int light, int caustic, unsigned seed, unsigned long long first, unsigned count, unsigned char* counts,
+                       float* records, int nthreads)
+{
+    const Light& L = g->lights[light];
+    V3 t1 = cross(V3(0, 0, 1), L.normal);                               // getTangents, Utility.h:25-31 (SquareLight::preCalc)
+    if (length2(t1) < 1e-6) t1 = cross(V3(0, 1, 0), L.normal);
+    const V3 t2 = cross(t1, L.normal);
+    if (nthreads <= 0) nthreads = omp_get_max_threads();
+#pragma omp parallel for schedule(dynamic, 256) num_threads(nthreads)
+    for (long i = 0; i < (long)count; ++i)
+        counts[i] = (unsigned char)tracePhotonWalk(L, t1, t2, caustic != 0, seed, first + (unsigned long long)i, records + 45 * i);
 }
 
 // ---- photon maps: which 0 / 1 = the scene's global / caustic map, >= 2 standalone -----------------

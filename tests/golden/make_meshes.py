@@ -9,7 +9,8 @@ import numpy as np
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import objio  # noqa: E402
 
-MODELS = ["bunny", "teapot", "cornell_box", "cornell_box_1", "cornell_box_2", "cornell_box_3", "cornell_box_4", "testobj", "sphere"]
+MODELS = ["bunny", "teapot", "cornell_box", "cornell_box_1", "cornell_box_2", "cornell_box_3", "cornell_box_4", "testobj", "sphere",
+          "Petals2", "Stem", "Leaf", "WaterDrops"]   # BASELINE configs 4 and 5
 
 if __name__ == "__main__":
     out = {}

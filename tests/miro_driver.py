@@ -137,6 +137,14 @@ class Driver:
         return rgb
 
     # ---- photon maps --------------------------------------------------------------------------
+    def trace_photons(self, light, caustic, seed, first, count, nthreads=0):
+        """oracle only: Scene::tracePhoton over emissions [first, first+count) with the counter-based uniforms."""
+        counts = np.zeros(count, np.uint8)
+        records = np.zeros((count, 5, 9), np.float32)
+        self._f("trace_photons")(int(light), int(caustic), ctypes.c_uint(seed), ctypes.c_ulonglong(first), ctypes.c_uint(count),
+                                 counts.ctypes.data_as(ctypes.c_void_p), records.ctypes.data_as(ctypes.c_void_p), int(nthreads))
+        return counts, records
+
     def pm_new(self, max_photons):
         return self._f("pm_new")(int(max_photons))
 

@@ -188,3 +188,55 @@ def test_render_with_photon_maps(pkg, scenes, oracle):
     assert np.isclose(img, ref, rtol=2e-4, atol=2e-5).mean() > 0.999
     for which in (0, 1):
         oracle.lib.orc_pm_reset(which, ctypes.c_int(1))
+
+
+def test_config4_flower_refractive_scene(pkg, scenes, oracle):
+    """BASELINE config 4 (Petals2 + Stem + Leaf + WaterDrops, water = Phong(1, 0, 1, 250, 1.33), DirectionalAreaLight):
+    the reflect / Fresnel / refract tree to depth 10 with closest-hit shadow rays (refractive occluders, Phong.cpp:99-113),
+    against the oracle's Scene::traceScene at reduced resolution, plus 4 jittered samples at a larger size for sanity."""
+    H, S = build_pair(pkg, scenes, oracle, "flower", layout=0)
+    assert S.info.num_triangles == 14784 + 1664 + 6144 + 20160
+    w, h = 384, 256
+    img = S.render(H.camera(), S.render_params(w, h, mode=pkg.RENDER_WHITTED, max_depth=10, bg=(1, 1, 1)))
+    ref = oracle.trace_scene(oracle.eye_rays(w, h), depth=10).reshape(h, w, 3)
+    assert np.isfinite(img).mean() > 0.999
+    a, b = tonemap_u8(oracle, np.nan_to_num(img)), tonemap_u8(oracle, np.nan_to_num(ref))
+    diff = np.abs(a.astype(int) - b.astype(int)).max(axis=2)
+    assert (diff <= 2).mean() > 0.99, (diff <= 2).mean()
+    assert psnr(a, b) >= 35, psnr(a, b)
+    rays_1spp = S.last_call_stats()[0]
+    assert rays_1spp > 2 * w * h                                       # primaries + shadow slots + secondary generations
+    # 4 spp, jittered (the config's sampling): every sample is an independent frame, so the ray count scales with it
+    p4 = S.render_params(768, 512, spp=4, jitter=1, mode=pkg.RENDER_WHITTED, max_depth=10, bg=(1, 1, 1))
+    img4 = S.render(H.camera(), p4)
+    assert np.isfinite(img4).mean() > 0.999 and S.last_call_stats()[0] > 3.5 * 4 * rays_1spp * 0.9
+    small = img4.reshape(256, 2, 384, 2, 3).mean(axis=(1, 3))           # box-filtered back to 384 x 256
+    assert np.abs(tonemap_u8(oracle, np.nan_to_num(small)).astype(int) - a.astype(int)).mean() < 6
+
+
+def test_config5_photon_map_render(pkg, scenes, oracle):
+    """BASELINE config 5 end to end on the device: Scene::preCalc traces both photon maps (device walks, host balance),
+    then the frame adds the kNN irradiance of both maps at every diffuse hit (Scene.cpp:286-299).  Checked against the
+    oracle's traceScene over the SAME maps (the host layer's balanced arrays loaded into the oracle)."""
+    H = pkg.HostScene(0)
+    for d in (oracle, H):
+        scenes.realise(d, "cornell_drops", objio.obj_path)
+    H.set_photon_counts(200000, 200000)
+    oracle.precalc(); H.precalc()
+    S = H.scene()
+    for which in (0, 1):
+        ph = H.pm_dump(which)
+        assert 200000 <= len(ph) - 1 <= 200005
+        oracle.lib.orc_pm_reset(which, ctypes.c_int(len(ph)))
+        oracle.lib.orc_pm_load(which, md._fp(ph.view(np.uint8)), ctypes.c_int(len(ph) - 1))
+    w, h = 128, 128
+    img = S.render(H.camera(), S.render_params(w, h, mode=pkg.RENDER_WHITTED, max_depth=10, use_photon_maps=1))
+    base = S.render(H.camera(), S.render_params(w, h, mode=pkg.RENDER_WHITTED, max_depth=10, use_photon_maps=0))
+    ref = oracle.trace_scene(oracle.eye_rays(w, h), depth=10).reshape(h, w, 3)
+    assert (np.nan_to_num(img) - np.nan_to_num(base)).max() > 1e-3     # the maps contribute
+    a, b = tonemap_u8(oracle, np.nan_to_num(img)), tonemap_u8(oracle, np.nan_to_num(ref))
+    diff = np.abs(a.astype(int) - b.astype(int)).max(axis=2)
+    assert (diff <= 2).mean() > 0.99, (diff <= 2).mean()
+    assert psnr(a, b) >= 35, psnr(a, b)
+    for which in (0, 1):
+        oracle.lib.orc_pm_reset(which, ctypes.c_int(1))
