@@ -33,12 +33,35 @@ sys.path.insert(0, os.path.join(ROOT, "tests"))   # objio (fixture -> .obj) and,
 METRIC = "closest-hit Mrays/s (sponza, primary+diffuse bounce)"
 SCENE = "bunny20"
 WIDTH, HEIGHT = 1920, 1080
-SPP = 4
+SPP = 16   # samples per step: sized so that one rank's share of a step is still milliseconds of device work at N = 8
 SEED = 168
 # SURVEY 8d yardstick: bytes/ray = 32*V + 36*T + 48 with V, T the scalar reference's node entries / triangle
 # tests per ray.  Measured live with the oracle on a subsample; these are the fall-back figures (SURVEY 8d,
 # bunny x20 bounce rays) if the oracle is unavailable.
 FALLBACK_VT = {"primary": (18.48, 3.37), "bounce": (22.43, 4.70)}
+
+
+def workload(ntris):
+    return (f"{SCENE}: reference makeBunny20Scene geometry ({ntris} triangles) and camera, declared stand-in for BASELINE config 3's "
+            f"sponza.obj (absent from the reference tree); {WIDTH}x{HEIGHT}, {SPP} jittered samples per step, one Ray::diffuse bounce ray per hit")
+
+
+_REAL_STDOUT = None
+
+
+def claim_stdout():
+    """The contract is ONE JSON line on stdout.  Libraries write there too (NCCL's version banner, the reference's progress
+    lines), so file descriptor 1 is pointed at stderr for the whole run and the JSON line goes to the saved descriptor."""
+    global _REAL_STDOUT
+    if _REAL_STDOUT is None:
+        sys.stdout.flush()
+        _REAL_STDOUT = os.fdopen(os.dup(1), "w")
+        os.dup2(2, 1)
+
+
+def emit(line):
+    _REAL_STDOUT.write(json.dumps(line) + "\n")
+    _REAL_STDOUT.flush()
 
 
 def bytes_per_ray(V, T):
@@ -200,14 +223,14 @@ def run_reference(args):
         "impl": "reference", "metric": METRIC, "value": value, "unit": "Mrays/s", "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": 1e3 * total_t / max(1, args.steps), "higher_is_better": True, "scaling": "strong",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": f"{SCENE} ({WIDTH}x{HEIGHT} camera of makeBunny20Scene; stand-in for the missing sponza.obj): per step every 4th row of one "
-                               "jittered sample + one Ray::diffuse bounce ray per hit, closest-hit through Scene::trace",
+        "config": {"workload": workload(D.num_objects()),
+                   "sample": "per step every 4th row of one jittered sample of the frame + one Ray::diffuse bounce ray per hit, closest-hit through Scene::trace",
                    "rays_per_step": total_r // max(1, args.steps), "threads": cores, "bvh_build_s": build_s},
         "cpu_baseline": {"value": value, "unit": "Mrays/s", "cores": cores, "kind": kind,
                          "sample": f"{total_r // max(1, args.steps)} rays per step (270 of 1080 rows of one sample + bounce), OpenMP over all host threads"},
         "e2e": {"value": value, "unit": "Mrays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 # ------------------------------------------------------------------------------------------------------------------
@@ -359,8 +382,7 @@ def run_ours(args):
             "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic",
             "config": {
-                "workload": f"{SCENE}: reference makeBunny20Scene geometry ({info.num_triangles} triangles) and camera, declared stand-in for BASELINE config 3's "
-                            f"sponza.obj (absent from the reference tree); {WIDTH}x{HEIGHT}, {SPP} jittered samples per step, one Ray::diffuse bounce ray per hit",
+                "workload": workload(info.num_triangles),
                 "rays_per_step": rays_total / args.steps, "primary_rays_per_step": prim_total / args.steps, "bounce_rays_per_step": live_total / args.steps,
                 "layout": args.layout, "kernel_variant": args.variant, "nodes": info.num_nodes, "node_mb": info.node_bytes / 1e6,
                 "triangle_mb": info.triangle_bytes / 1e6, "build_s": info.build_seconds + info.flatten_seconds,
@@ -381,7 +403,7 @@ def run_ours(args):
             "gpu_launches": int(4 * args.steps * world),
             "clocks": clocks,
         }
-        print(json.dumps(line), flush=True)
+        emit(line)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
@@ -400,6 +422,7 @@ def main():
     args = ap.parse_args()
     if args.warmup < 3:
         args.warmup = 3
+    claim_stdout()
     if args.impl == "reference":
         run_reference(args)
     else:
@@ -408,7 +431,7 @@ def main():
             # convenience: re-launch under torchrun when called as plain `python bench.py --gpus N`
             cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={args.gpus}", "--master-addr", "127.0.0.1",
                    "--master-port", "29541", os.path.abspath(__file__)] + sys.argv[1:]
-            raise SystemExit(subprocess.call(cmd))
+            raise SystemExit(subprocess.call(cmd, stdout=_REAL_STDOUT))
         run_ours(args)
 
 

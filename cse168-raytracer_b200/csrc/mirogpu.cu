@@ -88,10 +88,14 @@ template <bool ANY, int PF, int MINB, int NREP>
 cudaError_t launch_hybrid_inst(mirogpu_scene* h, const mirogpu_ray* d_rays, size_t n, mirogpu_hit* d_hits, unsigned long long* ticket,
                                cudaStream_t st, const uint32_t* d_n, uint32_t mult)
 {
-    int occ = 0;
-    cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_trace_bvh2_hybrid<ANY, PF, MINB, NREP>, 128, 0);
-    if (e != cudaSuccess) return e;
-    if (occ < 1) occ = 1;
+    static std::atomic<int> cached_occ{0};   // per instantiation; the answer depends only on the kernel and the device type
+    int occ = cached_occ.load(std::memory_order_relaxed);
+    if (occ == 0) {
+        cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_trace_bvh2_hybrid<ANY, PF, MINB, NREP>, 128, 0);
+        if (e != cudaSuccess) return e;
+        if (occ < 1) occ = 1;
+        cached_occ.store(occ, std::memory_order_relaxed);
+    }
     size_t grid = (size_t)h->sm_count * occ;
     const size_t need = (n + 127) / 128;
     if (grid > need) grid = need;
@@ -124,10 +128,14 @@ cudaError_t launch_trace(mirogpu_scene* h, const mirogpu_ray* d_rays, size_t n, 
     cudaError_t e = cudaMemsetAsync(ticket, 0, sizeof(unsigned long long), st);
     if (e != cudaSuccess) return e;
     if (LAYOUT == MIROGPU_LAYOUT_BVH2 && (h->variant == 2 || (h->variant < 0 && !coherent)) && n < 0xFF000000ull) return launch_hybrid<ANY>(h, d_rays, n, d_hits, ticket, st, d_n, mult);
-    int occ = 0;
-    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_trace_persistent<LAYOUT, ANY>, 128, 0);
-    if (e != cudaSuccess) return e;
-    if (occ < 1) occ = 1;
+    static std::atomic<int> cached_occ{0};
+    int occ = cached_occ.load(std::memory_order_relaxed);
+    if (occ == 0) {
+        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_trace_persistent<LAYOUT, ANY>, 128, 0);
+        if (e != cudaSuccess) return e;
+        if (occ < 1) occ = 1;
+        cached_occ.store(occ, std::memory_order_relaxed);
+    }
     size_t grid = (size_t)h->sm_count * occ;
     const size_t need = (n + 127) / 128;
     if (grid > need) grid = need;
