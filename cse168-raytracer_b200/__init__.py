@@ -23,7 +23,7 @@ LIB_PATH = os.path.join(_PKG, "libmirogpu.so")
 
 MISS = 0xFFFFFFFF
 TMAX = np.float32(1e12)
-LAYOUT_BVH2, LAYOUT_CWBVH8 = 0, 1
+LAYOUT_BVH2, LAYOUT_CWBVH8, LAYOUT_BVH4 = 0, 1, 2
 CLOSEST_HIT, ANY_HIT = 0, 1
 HINT_COHERENT = 0x100   # or-ed into a query mode: camera-like batch -> packet kernel
 RENDER_WHITTED, RENDER_DIFFUSE_BOUNCE, RENDER_PRIMARY_ONLY = 0, 1, 2

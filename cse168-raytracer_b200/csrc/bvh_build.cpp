@@ -271,6 +271,84 @@ void flatten_bvh2(const BinaryBvh& b, FlatBvh& out)
     }
 }
 
+
+// ---------------------------------------------------------------------------------------------------
+void flatten_bvh4(const BinaryBvh& b, FlatBvh& out)
+{
+    out.layout = 2;
+    out.order = b.order;
+    out.root = b.nodes[0].box;
+    out.max_depth = 0;
+    out.nodes4.clear();
+    auto leaf_ref = [](const BinaryNode& n) -> int32_t { return ~(int32_t)((n.first << 3) | (n.count - 1)); };
+    auto blank = []() {
+        Bvh4Node fn; std::memset(&fn, 0, sizeof fn);
+        for (int c = 0; c < 4; ++c) {   // empty slot: both planes at +inf on every axis (see flatten_bvh2)
+            fn.lox[c] = fn.hix[c] = fn.loy[c] = fn.hiy[c] = fn.loz[c] = fn.hiz[c] = kInf;
+            fn.link[c] = (int32_t)0x80000000;
+        }
+        return fn;
+    };
+    auto put_child = [](Bvh4Node& fn, int c, const Aabb& bx) {
+        fn.lox[c] = bx.lo[0]; fn.hix[c] = bx.hi[0]; fn.loy[c] = bx.lo[1]; fn.hiy[c] = bx.hi[1]; fn.loz[c] = bx.lo[2]; fn.hiz[c] = bx.hi[2];
+    };
+    if (b.nodes[0].left < 0) {
+        Bvh4Node fn = blank();
+        if (b.nodes[0].count > 0) { put_child(fn, 0, b.nodes[0].box); fn.link[0] = leaf_ref(b.nodes[0]); }
+        out.nodes4.push_back(fn);
+        return;
+    }
+    // children of a wide node: start from the two binary children, keep opening the internal child with the largest
+    // surface area until there are four (or nothing left to open)
+    auto collect = [&](uint32_t n, int32_t ch[4]) -> int {
+        int k = 0;
+        ch[k++] = b.nodes[n].left; ch[k++] = b.nodes[n].right;
+        while (k < 4) {
+            int best = -1; float best_area = -1.f;
+            for (int i = 0; i < k; ++i) {
+                const BinaryNode& c = b.nodes[ch[i]];
+                if (c.left < 0) continue;
+                const float a = box_half_area(c.box);
+                if (a > best_area) { best_area = a; best = i; }
+            }
+            if (best < 0) break;
+            const int32_t open = ch[best];
+            ch[best] = b.nodes[open].left;
+            ch[k++] = b.nodes[open].right;
+        }
+        return k;
+    };
+    // depth-first numbering of the wide nodes (a subtree is contiguous in HBM)
+    struct Item { uint32_t bnode; uint32_t depth; uint32_t pending; };   // pending: stack entries left behind by the ancestors
+    std::vector<int32_t> flat_index(b.nodes.size(), -1);
+    out.max_stack = 0;
+    std::vector<Item> stack; stack.push_back({0u, 1u, 0u});
+    std::vector<uint32_t> wide_order;
+    while (!stack.empty()) {
+        const Item it = stack.back(); stack.pop_back();
+        flat_index[it.bnode] = (int32_t)wide_order.size();
+        wide_order.push_back(it.bnode);
+        out.max_depth = std::max(out.max_depth, it.depth);
+        int32_t ch[4];
+        const int k = collect(it.bnode, ch);
+        out.max_stack = std::max(out.max_stack, it.pending + (uint32_t)(k - 1));
+        for (int i = k - 1; i >= 0; --i)
+            if (b.nodes[ch[i]].left >= 0) stack.push_back({(uint32_t)ch[i], it.depth + 1, it.pending + (uint32_t)(k - 1)});
+    }
+    out.nodes4.resize(wide_order.size());
+    for (size_t i = 0; i < wide_order.size(); ++i) {
+        Bvh4Node fn = blank();
+        int32_t ch[4];
+        const int k = collect(wide_order[i], ch);
+        for (int c = 0; c < k; ++c) {
+            const BinaryNode& cn = b.nodes[ch[c]];
+            put_child(fn, c, cn.box);
+            fn.link[c] = cn.left >= 0 ? flat_index[ch[c]] : leaf_ref(cn);
+        }
+        out.nodes4[i] = fn;
+    }
+}
+
 // ---------------------------------------------------------------------------------------------------
 namespace {
 struct WideChild { int32_t bnode; };

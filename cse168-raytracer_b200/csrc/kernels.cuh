@@ -15,7 +15,7 @@
 namespace mirogpu {
 
 struct DeviceScene {
-    const float4* nodes;   // BVH2: 4 float4 per node; CWBVH8: 5 uint4 per node
+    const float4* nodes;   // BVH2: 4 float4 per node; BVH4: 8 float4 per node; CWBVH8: 5 uint4 per node
     const float4* tris;    // 3 float4 per triangle, leaf order
     const float4* shade;   // 6 float4 per primitive, prim-id order: (A,mat) e1 e2 nA nB nC
     uint32_t num_tris;
@@ -32,6 +32,7 @@ template <int LAYOUT, bool ANY, bool COUNT>
 __device__ __forceinline__ void trace_one(const DeviceScene& s, const mirogpu_ray& r, BestHit& best, TraceCounters* c)
 {
     if (LAYOUT == MIROGPU_LAYOUT_BVH2) trace_bvh2<ANY, COUNT>(s.nodes, s.tris, r, best, c);
+    else if (LAYOUT == MIROGPU_LAYOUT_BVH4) trace_bvh4<ANY, COUNT>(s.nodes, s.tris, r, best, c);
     else trace_cwbvh8<ANY, COUNT>(reinterpret_cast<const uint4*>(s.nodes), s.tris, r, best, c);
 }
 
@@ -111,7 +112,7 @@ __global__ void __launch_bounds__(128) k_trace_persistent(DeviceScene s, const m
     }
 }
 
-// Persistent warps, hybrid step scheduling + ray replacement (BVH2).  In the while-while kernel a round costs the
+// Persistent warps, hybrid step scheduling + ray replacement (BVH2 and BVH4).  In the while-while kernel a round costs the
 // warp max-over-lanes(descent length) node steps plus max-over-lanes(leaf size) triangle tests, and on incoherent
 // rays the descent lengths differ so much that 7 of 32 lanes are busy on average (ncu; tools/simt_sim.cu replays
 // the same rays and predicts the same figure).  Here every iteration the warp votes: it takes node steps while at
@@ -121,8 +122,8 @@ __global__ void __launch_bounds__(128) k_trace_persistent(DeviceScene s, const m
 // are claimed from a global ticket one ahead of use and prefetched into L2 while the warp works on the current one.
 //   PF    prefetch flags of bvh2_node_step; bit 3: prefetch the pool claimed ahead         MINB  resident CTAs per SM asked of the compiler
 //   NREP  node steps per vote (a lane that leaves the inner nodes sits the rest out)
-template <bool ANY, int PF, int MINB, int NREP>
-__global__ void __launch_bounds__(128, MINB) k_trace_bvh2_hybrid(DeviceScene s, const mirogpu_ray* __restrict__ rays, size_t n,
+template <int LAYOUT, bool ANY, int PF, int MINB, int NREP>
+__global__ void __launch_bounds__(128, MINB) k_trace_hybrid(DeviceScene s, const mirogpu_ray* __restrict__ rays, size_t n,
                                                                  mirogpu_hit* __restrict__ hits, unsigned long long* __restrict__ ticket,
                                                                  int nmin, int period, int min_idle, uint32_t pool,
                                                                  const uint32_t* __restrict__ d_n, uint32_t mult)
@@ -137,7 +138,7 @@ __global__ void __launch_bounds__(128, MINB) k_trace_bvh2_hybrid(DeviceScene s, 
     mirogpu_ray r;
     Bvh2Walk w;
     BestHit best;
-    int32_t stack[MIRO_STACK + 1];
+    int32_t stack[(LAYOUT == MIROGPU_LAYOUT_BVH4 ? MIRO_STACK4 : MIRO_STACK) + 1];
     r.ox = r.oy = r.oz = r.tmin = r.dx = r.dy = r.dz = r.tmax = 0.f;
     w.node = w.tos = MIRO_BVH2_DONE; w.sp = 0;
     w.idx = w.idy = w.idz = w.oodx = w.oody = w.oodz = 0.f;
@@ -186,7 +187,10 @@ __global__ void __launch_bounds__(128, MINB) k_trace_bvh2_hybrid(DeviceScene s, 
             if (mn != 0u && (__popc(mn) >= nmin || ml == 0u)) {
 #pragma unroll
                 for (int rep = 0; rep < NREP; ++rep)
-                    if (w.node >= 0) bvh2_node_step<PF>(s.nodes, s.tris, r, w, stack, best);
+                    if (w.node >= 0) {
+                        if (LAYOUT == MIROGPU_LAYOUT_BVH4) bvh4_node_step<PF>(s.nodes, s.tris, r, w, stack, best);
+                        else bvh2_node_step<PF>(s.nodes, s.tris, r, w, stack, best);
+                    }
             } else if (w.node < 0 && w.node != MIRO_BVH2_DONE) {
                 bvh2_leaf_step<ANY>(s.tris, r, w, stack, best);
             }

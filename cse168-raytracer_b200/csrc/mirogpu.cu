@@ -84,14 +84,14 @@ namespace {
 
 // n is the number of rays, or -- when d_n is given -- an upper bound on it: the kernels then read the real count
 // *d_n * mult from device memory (wavefront queues whose size the host never sees).
-template <bool ANY, int PF, int MINB, int NREP>
+template <int LAYOUT, bool ANY, int PF, int MINB, int NREP>
 cudaError_t launch_hybrid_inst(mirogpu_scene* h, const mirogpu_ray* d_rays, size_t n, mirogpu_hit* d_hits, unsigned long long* ticket,
                                cudaStream_t st, const uint32_t* d_n, uint32_t mult)
 {
     static std::atomic<int> cached_occ{0};   // per instantiation; the answer depends only on the kernel and the device type
     int occ = cached_occ.load(std::memory_order_relaxed);
     if (occ == 0) {
-        cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_trace_bvh2_hybrid<ANY, PF, MINB, NREP>, 128, 0);
+        cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_trace_hybrid<LAYOUT, ANY, PF, MINB, NREP>, 128, 0);
         if (e != cudaSuccess) return e;
         if (occ < 1) occ = 1;
         cached_occ.store(occ, std::memory_order_relaxed);
@@ -99,19 +99,19 @@ cudaError_t launch_hybrid_inst(mirogpu_scene* h, const mirogpu_ray* d_rays, size
     size_t grid = (size_t)h->sm_count * occ;
     const size_t need = (n + 127) / 128;
     if (grid > need) grid = need;
-    k_trace_bvh2_hybrid<ANY, PF, MINB, NREP><<<(unsigned)grid, 128, 0, st>>>(h->ds, d_rays, n, d_hits, ticket, h->hyb_nmin, h->hyb_period,
+    k_trace_hybrid<LAYOUT, ANY, PF, MINB, NREP><<<(unsigned)grid, 128, 0, st>>>(h->ds, d_rays, n, d_hits, ticket, h->hyb_nmin, h->hyb_period,
                                                                             h->hyb_min_idle, (uint32_t)h->hyb_pool, d_n, mult);
     return cudaGetLastError();
 }
 
-template <bool ANY>
+template <int LAYOUT, bool ANY>
 cudaError_t launch_hybrid(mirogpu_scene* h, const mirogpu_ray* d_rays, size_t n, mirogpu_hit* d_hits, unsigned long long* ticket,
                           cudaStream_t st, const uint32_t* d_n, uint32_t mult)
 {
-#define MIRO_HYB(PF, MINB, NREP) if (h->hyb_pf == PF && h->hyb_minb == MINB && h->hyb_nrep == NREP) return launch_hybrid_inst<ANY, PF, MINB, NREP>(h, d_rays, n, d_hits, ticket, st, d_n, mult);
-    MIRO_HYB(0, 9, 2) MIRO_HYB(4, 9, 2) MIRO_HYB(0, 8, 2) MIRO_HYB(0, 9, 1) MIRO_HYB(0, 9, 3)
+#define MIRO_HYB(PF, MINB, NREP) if (h->hyb_pf == PF && h->hyb_minb == MINB && h->hyb_nrep == NREP) return launch_hybrid_inst<LAYOUT, ANY, PF, MINB, NREP>(h, d_rays, n, d_hits, ticket, st, d_n, mult);
+    MIRO_HYB(0, 9, 2) MIRO_HYB(4, 9, 2) MIRO_HYB(0, 8, 2) MIRO_HYB(0, 9, 1) MIRO_HYB(0, 8, 1) MIRO_HYB(0, 7, 1) MIRO_HYB(0, 7, 2) MIRO_HYB(4, 8, 1)
 #undef MIRO_HYB
-    return launch_hybrid_inst<ANY, 0, 9, 2>(h, d_rays, n, d_hits, ticket, st, d_n, mult);
+    return launch_hybrid_inst<LAYOUT, ANY, 0, 9, 2>(h, d_rays, n, d_hits, ticket, st, d_n, mult);
 }
 
 template <int LAYOUT, bool ANY>
@@ -127,7 +127,8 @@ cudaError_t launch_trace(mirogpu_scene* h, const mirogpu_ray* d_rays, size_t n, 
     unsigned long long* ticket = h->d_ticket + (h->ticket_slot.fetch_add(1) & 63u);
     cudaError_t e = cudaMemsetAsync(ticket, 0, sizeof(unsigned long long), st);
     if (e != cudaSuccess) return e;
-    if (LAYOUT == MIROGPU_LAYOUT_BVH2 && (h->variant == 2 || (h->variant < 0 && !coherent)) && n < 0xFF000000ull) return launch_hybrid<ANY>(h, d_rays, n, d_hits, ticket, st, d_n, mult);
+    if (LAYOUT != MIROGPU_LAYOUT_CWBVH8 && (h->variant == 2 || (h->variant < 0 && !coherent)) && n < 0xFF000000ull)
+        return launch_hybrid<LAYOUT == MIROGPU_LAYOUT_CWBVH8 ? MIROGPU_LAYOUT_BVH2 : LAYOUT, ANY>(h, d_rays, n, d_hits, ticket, st, d_n, mult);
     static std::atomic<int> cached_occ{0};
     int occ = cached_occ.load(std::memory_order_relaxed);
     if (occ == 0) {
@@ -151,6 +152,9 @@ cudaError_t dispatch_trace(mirogpu_scene* h, const mirogpu_ray* d_rays, size_t n
     if (h->layout == MIROGPU_LAYOUT_BVH2)
         return any ? launch_trace<MIROGPU_LAYOUT_BVH2, true>(h, d_rays, n, d_hits, st, d_n, mult, coherent)
                    : launch_trace<MIROGPU_LAYOUT_BVH2, false>(h, d_rays, n, d_hits, st, d_n, mult, coherent);
+    if (h->layout == MIROGPU_LAYOUT_BVH4)
+        return any ? launch_trace<MIROGPU_LAYOUT_BVH4, true>(h, d_rays, n, d_hits, st, d_n, mult, coherent)
+                   : launch_trace<MIROGPU_LAYOUT_BVH4, false>(h, d_rays, n, d_hits, st, d_n, mult, coherent);
     return any ? launch_trace<MIROGPU_LAYOUT_CWBVH8, true>(h, d_rays, n, d_hits, st, d_n, mult, coherent)
                : launch_trace<MIROGPU_LAYOUT_CWBVH8, false>(h, d_rays, n, d_hits, st, d_n, mult, coherent);
 }
@@ -210,11 +214,11 @@ int mirogpu_scene_create(const float* tri_vertices, const float* tri_normals, co
     mirogpu_build_options o;
     o.layout = MIROGPU_LAYOUT_CWBVH8; o.max_leaf = 0; o.sah_bins = 32; o.device = -1;
     if (opt) o = *opt;
-    if (o.layout != MIROGPU_LAYOUT_BVH2 && o.layout != MIROGPU_LAYOUT_CWBVH8) return fail(MIROGPU_ERR_INVALID_ARG, "unknown layout");
+    if (o.layout != MIROGPU_LAYOUT_BVH2 && o.layout != MIROGPU_LAYOUT_CWBVH8 && o.layout != MIROGPU_LAYOUT_BVH4) return fail(MIROGPU_ERR_INVALID_ARG, "unknown layout");
     if (o.max_leaf <= 0) if (const char* e = getenv("MIROGPU_MAX_LEAF")) o.max_leaf = atoi(e);   // tuning knob
     if (o.max_leaf <= 0) o.max_leaf = (o.layout == MIROGPU_LAYOUT_CWBVH8) ? 3 : 4;
     if (o.layout == MIROGPU_LAYOUT_CWBVH8 && o.max_leaf > 3) o.max_leaf = 3;
-    if (o.layout == MIROGPU_LAYOUT_BVH2 && o.max_leaf > 8) o.max_leaf = 8;
+    if (o.layout != MIROGPU_LAYOUT_CWBVH8 && o.max_leaf > 8) o.max_leaf = 8;
     if (o.sah_bins <= 0) o.sah_bins = 32;
 
     int ndev = 0;
@@ -246,12 +250,16 @@ int mirogpu_scene_create(const float* tri_vertices, const float* tri_normals, co
     BinaryBvh bin = build_binary_sah(tri_vertices, ntris, o.max_leaf, o.sah_bins);
     double t1 = now_s();
     FlatBvh flat;
-    if (o.layout == MIROGPU_LAYOUT_BVH2) flatten_bvh2(bin, flat); else flatten_cwbvh8(bin, flat);
+    if (o.layout == MIROGPU_LAYOUT_BVH2) flatten_bvh2(bin, flat);
+    else if (o.layout == MIROGPU_LAYOUT_BVH4) flatten_bvh4(bin, flat);
+    else flatten_cwbvh8(bin, flat);
+    if (o.layout == MIROGPU_LAYOUT_BVH4 && flat.max_stack > MIRO_STACK4) { delete h; return fail(MIROGPU_ERR_INVALID_ARG, "BVH4 tree needs a deeper traversal stack than the kernels carry"); }
     make_tri_records(tri_vertices, flat.order, h->h_tris);
     double t2 = now_s();
 
     const void* node_src; size_t node_bytes;
     if (o.layout == MIROGPU_LAYOUT_BVH2) { node_src = flat.nodes2.data(); node_bytes = flat.nodes2.size() * sizeof(Bvh2Node); }
+    else if (o.layout == MIROGPU_LAYOUT_BVH4) { node_src = flat.nodes4.data(); node_bytes = flat.nodes4.size() * sizeof(Bvh4Node); }
     else { node_src = flat.nodes8.data(); node_bytes = flat.nodes8.size() * sizeof(Cwbvh8Node); }
     h->h_nodes.assign((const uint8_t*)node_src, (const uint8_t*)node_src + node_bytes);
 
@@ -315,7 +323,7 @@ int mirogpu_scene_create(const float* tri_vertices, const float* tri_normals, co
 
     mirogpu_scene_info& in = h->info;
     in.num_triangles = ntris;
-    in.num_nodes = (uint32_t)(o.layout == MIROGPU_LAYOUT_BVH2 ? flat.nodes2.size() : flat.nodes8.size());
+    in.num_nodes = (uint32_t)(o.layout == MIROGPU_LAYOUT_BVH2 ? flat.nodes2.size() : o.layout == MIROGPU_LAYOUT_BVH4 ? flat.nodes4.size() : flat.nodes8.size());
     in.num_binary_nodes = (uint32_t)bin.nodes.size();
     in.num_binary_leaves = bin.num_leaves;
     in.max_depth = o.layout == MIROGPU_LAYOUT_BVH2 ? bin.max_depth : flat.max_depth;
@@ -464,7 +472,10 @@ int mirogpu_intersect_batch_counted(mirogpu_handle h, const mirogpu_ray* rays, s
     CUDA_TRY(cudaMemcpy(d_r, rays, n * sizeof(mirogpu_ray), cudaMemcpyHostToDevice));
     const unsigned grid = (unsigned)((n + 127) / 128);
     const bool any = mode == MIROGPU_ANY_HIT;
-    if (h->layout == MIROGPU_LAYOUT_BVH2) {
+    if (h->layout == MIROGPU_LAYOUT_BVH4) {
+        if (any) k_trace_simple<MIROGPU_LAYOUT_BVH4, true, true><<<grid, 128>>>(h->ds, d_r, n, d_h, d_c, nullptr, 1);
+        else k_trace_simple<MIROGPU_LAYOUT_BVH4, false, true><<<grid, 128>>>(h->ds, d_r, n, d_h, d_c, nullptr, 1);
+    } else if (h->layout == MIROGPU_LAYOUT_BVH2) {
         if (any) k_trace_simple<MIROGPU_LAYOUT_BVH2, true, true><<<grid, 128>>>(h->ds, d_r, n, d_h, d_c, nullptr, 1);
         else k_trace_simple<MIROGPU_LAYOUT_BVH2, false, true><<<grid, 128>>>(h->ds, d_r, n, d_h, d_c, nullptr, 1);
     } else {
@@ -476,7 +487,7 @@ int mirogpu_intersect_batch_counted(mirogpu_handle h, const mirogpu_ray* rays, s
     CUDA_TRY(cudaMemcpy(hc, d_c, sizeof hc, cudaMemcpyDeviceToHost));
     CUDA_TRY(cudaMemcpy(hits, d_h, n * sizeof(mirogpu_hit), cudaMemcpyDeviceToHost));
     cudaFree(d_r); cudaFree(d_h); cudaFree(d_c);
-    const uint64_t node_size = h->layout == MIROGPU_LAYOUT_BVH2 ? 64 : 80;
+    const uint64_t node_size = h->layout == MIROGPU_LAYOUT_BVH2 ? 64 : h->layout == MIROGPU_LAYOUT_BVH4 ? 128 : 80;
     c->rays += n; c->node_visits += hc[0]; c->box_tests += hc[1]; c->triangle_tests += hc[2]; c->hits += hc[3];
     c->bytes_fetched += hc[0] * node_size + hc[2] * sizeof(TriRecord);
     return MIROGPU_OK;
@@ -625,6 +636,7 @@ int mirogpu_photon_trace(mirogpu_handle h, int light_index, int caustic, uint32_
     if (e == cudaSuccess) {
         const unsigned grid = (count + 127) / 128;
         if (h->layout == MIROGPU_LAYOUT_BVH2) k_photon_trace<MIROGPU_LAYOUT_BVH2><<<grid, 128, 0, cudaStreamPerThread>>>(h->ds, h->d_materials, em, d_counts, d_records);
+        else if (h->layout == MIROGPU_LAYOUT_BVH4) k_photon_trace<MIROGPU_LAYOUT_BVH4><<<grid, 128, 0, cudaStreamPerThread>>>(h->ds, h->d_materials, em, d_counts, d_records);
         else k_photon_trace<MIROGPU_LAYOUT_CWBVH8><<<grid, 128, 0, cudaStreamPerThread>>>(h->ds, h->d_materials, em, d_counts, d_records);
         e = cudaGetLastError();
     }

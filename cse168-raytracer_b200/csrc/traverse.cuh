@@ -197,6 +197,7 @@ MIRO_HD float safe_rcp(float d)
 }
 
 #define MIRO_STACK 64
+#define MIRO_STACK4 96   /* BVH4 pushes up to three entries per level; flatten_bvh4 computes the exact need and scene creation checks it */
 
 // ---- BVH2 (64-byte nodes, two child boxes per fetch) ---------------------------------------------------
 template <bool ANY, bool COUNT>
@@ -354,6 +355,69 @@ MIRO_HD void bvh2_leaf_step(const float4* __restrict__ tris, const mirogpu_ray& 
         if (ANY && acc) { w.node = MIRO_BVH2_DONE; return; }
     }
     bvh2_pop(w, stack);
+}
+
+// ---- BVH4 (128-byte nodes, four full-precision child boxes per fetch) ---------------------------------------------
+// Node = 8 x float4: (lo.x[4]) (hi.x[4]) (lo.y[4]) (hi.y[4]) (lo.z[4]) (hi.z[4]) (link[4]) (pad) -- four 256-bit loads, one
+// cache line.  Same walk state and leaf step as BVH2.  Child order: a three-comparator tournament finds the nearest
+// hit child (descended next); the two first-round losers are pushed first, the runner-up of the final last, so the
+// nearer of the remaining children tends to be popped earlier.  Misses carry distance +inf and are never pushed.
+template <int PF>
+MIRO_HD void bvh4_node_step(const float4* __restrict__ nodes, const float4* __restrict__ tris, const mirogpu_ray& r, Bvh2Walk& w,
+                            int32_t* __restrict__ stack, const BestHit& best)
+{
+    const float4* p = nodes + 8 * (size_t)w.node;
+    const F8 X = ld256(p), Y = ld256(p + 2), Z = ld256(p + 4), L = ld256(p + 6);
+    const float lox[4] = {X.lo.x, X.lo.y, X.lo.z, X.lo.w}, hix[4] = {X.hi.x, X.hi.y, X.hi.z, X.hi.w};
+    const float loy[4] = {Y.lo.x, Y.lo.y, Y.lo.z, Y.lo.w}, hiy[4] = {Y.hi.x, Y.hi.y, Y.hi.z, Y.hi.w};
+    const float loz[4] = {Z.lo.x, Z.lo.y, Z.lo.z, Z.lo.w}, hiz[4] = {Z.hi.x, Z.hi.y, Z.hi.z, Z.hi.w};
+    const int32_t lk[4] = {(int32_t)f2u(L.lo.x), (int32_t)f2u(L.lo.y), (int32_t)f2u(L.lo.z), (int32_t)f2u(L.lo.w)};
+    const float kFar = u2f(0x7f800000u);
+    float d[4];
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+        const float ax = lox[c] * w.idx - w.oodx, bx = hix[c] * w.idx - w.oodx;
+        const float ay = loy[c] * w.idy - w.oody, by = hiy[c] * w.idy - w.oody;
+        const float az = loz[c] * w.idz - w.oodz, bz = hiz[c] * w.idz - w.oodz;
+        const float tn = fmaxf(fmaxf(fminf(ax, bx), fminf(ay, by)), fmaxf(fminf(az, bz), r.tmin));
+        const float tf = fminf(fminf(fmaxf(ax, bx), fmaxf(ay, by)), fminf(fmaxf(az, bz), best.t));
+        d[c] = tn <= tf ? tn : kFar;
+    }
+    // tournament on (distance, link)
+    float da = d[0], db = d[1], dc = d[2], de = d[3];
+    int32_t la = lk[0], lb = lk[1], lc = lk[2], le = lk[3];
+    if (db < da) { const float t = da; da = db; db = t; const int32_t u = la; la = lb; lb = u; }
+    if (de < dc) { const float t = dc; dc = de; de = t; const int32_t u = lc; lc = le; le = u; }
+    if (dc < da) { const float t = da; da = dc; dc = t; const int32_t u = la; la = lc; lc = u; }
+    if (!(da < kFar)) { bvh2_pop(w, stack); return; }
+    if (db < kFar) { stack[w.sp++] = w.tos; w.tos = lb; }
+    if (de < kFar) { stack[w.sp++] = w.tos; w.tos = le; }
+    if (dc < kFar) { stack[w.sp++] = w.tos; w.tos = lc; }
+    if ((PF & 4) && la < 0) {
+        const float4* a = tris + 4 * (size_t)(((uint32_t)~la) >> 3);
+        if (PF & 2) prefetch_l1(a); else prefetch_l2(a);
+    }
+    w.node = la;
+}
+
+// Whole walk of one ray (packet / one-thread-per-ray kernels, the photon walker, the counting build).
+template <bool ANY, bool COUNT>
+MIRO_HD void trace_bvh4(const float4* __restrict__ nodes, const float4* __restrict__ tris, const mirogpu_ray& r, BestHit& best,
+                        TraceCounters* cnt)
+{
+    Bvh2Walk w;
+    int32_t stack[MIRO_STACK4 + 1];
+    bvh2_begin(r, w, best);
+    for (;;) {
+        while (w.node >= 0) {
+            if (COUNT) { cnt->nodes++; cnt->boxes += 4; }
+            bvh4_node_step<0>(nodes, tris, r, w, stack, best);
+        }
+        if (w.node == MIRO_BVH2_DONE) return;
+        if (COUNT) cnt->tris += (((uint32_t)~w.node) & 7u) + 1u;
+        bvh2_leaf_step<ANY>(tris, r, w, stack, best);
+        if (w.node == MIRO_BVH2_DONE) return;
+    }
 }
 
 // ---- CWBVH8 (80-byte nodes, eight 8-bit-quantised child boxes per fetch) --------------------------------

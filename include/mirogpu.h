@@ -95,11 +95,11 @@ typedef struct mirogpu_camera {
     float fov_degrees;
 } mirogpu_camera;
 
-enum { MIROGPU_LAYOUT_BVH2 = 0, MIROGPU_LAYOUT_CWBVH8 = 1 };
+enum { MIROGPU_LAYOUT_BVH2 = 0, MIROGPU_LAYOUT_CWBVH8 = 1, MIROGPU_LAYOUT_BVH4 = 2 };
 
 typedef struct mirogpu_build_options {
     int32_t layout;       /* MIROGPU_LAYOUT_*; default CWBVH8 */
-    int32_t max_leaf;     /* triangles per leaf (BVH2: <= 4 like the reference's OBJECTS_PER_LEAF; CWBVH8: <= 3) */
+    int32_t max_leaf;     /* triangles per leaf (BVH2 / BVH4: <= 4 like the reference's OBJECTS_PER_LEAF; CWBVH8: <= 3) */
     int32_t sah_bins;     /* binned SAH resolution, default 32 */
     int32_t device;       /* CUDA device ordinal, -1 = current device */
 } mirogpu_build_options;

@@ -8,9 +8,11 @@ BVH2_NODE = np.dtype([("f", np.float32, 12), ("link", np.int32, 4)])
 CW_NODE = np.dtype([("p", np.float32, 3), ("e", np.uint8, 3), ("imask", np.uint8), ("child_base", np.uint32), ("tri_base", np.uint32),
                     ("meta", np.uint8, 8), ("qlox", np.uint8, 8), ("qloy", np.uint8, 8), ("qloz", np.uint8, 8),
                     ("qhix", np.uint8, 8), ("qhiy", np.uint8, 8), ("qhiz", np.uint8, 8)])
+BVH4_NODE = np.dtype([("lox", np.float32, 4), ("hix", np.float32, 4), ("loy", np.float32, 4), ("hiy", np.float32, 4), ("loz", np.float32, 4), ("hiz", np.float32, 4),
+                      ("link", np.int32, 4), ("pad", np.int32, 4)])
 TRI_REC = np.dtype([("a", np.float32, 3), ("prim_id", np.uint32), ("e1", np.float32, 3), ("nx", np.float32), ("e2", np.float32, 3), ("ny", np.float32),
                     ("nz", np.float32), ("pad", np.float32, 3)])
-assert BVH2_NODE.itemsize == 64 and CW_NODE.itemsize == 80 and TRI_REC.itemsize == 64
+assert BVH2_NODE.itemsize == 64 and CW_NODE.itemsize == 80 and TRI_REC.itemsize == 64 and BVH4_NODE.itemsize == 128
 
 
 def emu_trace(emu, verts, rays, layout, any_hit=False, max_leaf=0):
@@ -35,7 +37,7 @@ def emu_build(emu, verts, layout, max_leaf=0):
     tris = np.zeros(sizes[1], TRI_REC)
     emu.emu_build(vp, ctypes.c_uint32(verts.shape[0]), int(layout), int(max_leaf), nodes.ctypes.data_as(ctypes.c_void_p),
                   order.ctypes.data_as(ctypes.c_void_p), tris.ctypes.data_as(ctypes.c_void_p), sizes)
-    return nodes.view(BVH2_NODE if layout == 0 else CW_NODE), order, tris, dict(binary_nodes=sizes[2], binary_leaves=sizes[3], depth=sizes[4])
+    return nodes.view({0: BVH2_NODE, 1: CW_NODE, 3: BVH4_NODE}[layout]), order, tris, dict(binary_nodes=sizes[2], binary_leaves=sizes[3], depth=sizes[4])
 
 
 def hit_ids(hits):

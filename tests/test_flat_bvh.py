@@ -114,3 +114,42 @@ def test_cwbvh8_is_smaller_than_bvh2(emu, oracle, scenes):
     n2, *_ = emu_build(emu, V, 0)
     n8, *_ = emu_build(emu, V, 1)
     assert n8.nbytes < 0.5 * n2.nbytes
+
+
+@pytest.mark.parametrize("name", ["testobj", "cornell", "teapot", "bunny_teapot"])
+def test_bvh4_boxes_contain_reference_bounds(emu, oracle, scenes, name):
+    """The 4-wide collapse: every triangle exactly once, every child box contains the reference bounds (triangle bounds +
+    epsilon) of everything below it, and the stack need the builder reports fits the kernels' stack."""
+    V = _verts(oracle, scenes, name)
+    nodes, order, tris, info = emu_build(emu, V, 3)
+    assert sorted(order.tolist()) == list(range(V.shape[0]))
+    assert info["depth"] <= 96                                            # FlatBvh::max_stack vs MIRO_STACK4
+    tlo, thi = _tri_bounds(V)
+    tlo, thi = tlo[order], thi[order]
+    seen = np.zeros(len(order), bool)
+
+    def check(ref, lo, hi):
+        if ref < 0:
+            r = ~ref
+            first, count = r >> 3, (r & 7) + 1
+            assert count <= 4 and not seen[first:first + count].any()
+            seen[first:first + count] = True
+            slo, shi = tlo[first:first + count].min(0), thi[first:first + count].max(0)
+        else:
+            nd = nodes[ref]
+            parts = []
+            for c in range(4):
+                clo = np.array([nd["lox"][c], nd["loy"][c], nd["loz"][c]]); chi = np.array([nd["hix"][c], nd["hiy"][c], nd["hiz"][c]])
+                if np.isinf(clo).all():
+                    continue
+                parts.append(check(int(nd["link"][c]), clo, chi))
+            assert parts
+            slo, shi = np.min([p[0] for p in parts], 0), np.max([p[1] for p in parts], 0)
+        if lo is not None:
+            assert np.all(lo <= slo) and np.all(hi >= shi)
+        return slo, shi
+
+    import sys
+    sys.setrecursionlimit(10000)
+    check(0, None, None)
+    assert seen.all()
