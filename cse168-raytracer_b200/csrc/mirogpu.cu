@@ -253,6 +253,10 @@ int mirogpu_scene_create(const float* tri_vertices, const float* tri_normals, co
     if (o.layout == MIROGPU_LAYOUT_BVH2) flatten_bvh2(bin, flat);
     else if (o.layout == MIROGPU_LAYOUT_BVH4) flatten_bvh4(bin, flat);
     else flatten_cwbvh8(bin, flat);
+    // a walk pushes at most one entry per level (BVH2 / CWBVH8 groups) resp. flat.max_stack entries (BVH4): refuse a tree the
+    // kernels' fixed per-thread stacks cannot hold rather than overrun them (the builder's depth cap makes this unreachable
+    // below ~16 M triangles)
+    if (o.layout != MIROGPU_LAYOUT_BVH4 && bin.max_depth > MIRO_STACK) { delete h; return fail(MIROGPU_ERR_INVALID_ARG, "tree deeper than the kernels' traversal stack"); }
     if (o.layout == MIROGPU_LAYOUT_BVH4 && flat.max_stack > MIRO_STACK4) { delete h; return fail(MIROGPU_ERR_INVALID_ARG, "BVH4 tree needs a deeper traversal stack than the kernels carry"); }
     make_tri_records(tri_vertices, flat.order, h->h_tris);
     double t2 = now_s();
