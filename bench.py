@@ -248,7 +248,7 @@ def run_ours(args):
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     pkg = importlib.import_module("cse168-raytracer_b200")
     scenes = importlib.import_module("cse168-raytracer_b200.scenes")
-    layout = {"bvh2": pkg.LAYOUT_BVH2, "cwbvh8": pkg.LAYOUT_CWBVH8, "bvh4": pkg.LAYOUT_BVH4}[args.layout]
+    layout = {"bvh2": pkg.LAYOUT_BVH2, "cwbvh8": pkg.LAYOUT_CWBVH8, "bvh4": pkg.LAYOUT_BVH4, "qbvh4": pkg.LAYOUT_QBVH4}[args.layout]
     H = build_host_scene(pkg, scenes, layout)       # BVH replicated on every GPU
     S = H.scene()
     S.set_kernel_variant(args.variant)
@@ -393,7 +393,7 @@ def run_ours(args):
                 "bytes_per_ray": {"primary": bpr_p, "bounce": bpr_b, "V_T": vt, "source": vt_src},
                 "reference_bvh_nodes": ref_nodes,
             },
-            "roofline": {"bound": "hbm", "kernel": ("k_trace_hybrid" if (args.layout in ("bvh2", "bvh4") and args.variant in (-1, 2)) else
+            "roofline": {"bound": "hbm", "kernel": ("k_trace_hybrid" if (args.layout in ("bvh2", "bvh4", "qbvh4") and args.variant in (-1, 2)) else
                                                     "k_trace_simple" if args.variant == 1 else "k_trace_persistent") + " (bounce rays, closest hit)", "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
                          "note": "algorithmic bytes = live bounce rays per launch x (32V + 36T + 48) B; the scene is mostly L2-resident, so DRAM traffic is far below this"},
@@ -416,7 +416,7 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--layout", default=os.environ.get("MIROGPU_LAYOUT", "bvh2"), choices=["bvh2", "cwbvh8", "bvh4"])
+    ap.add_argument("--layout", default=os.environ.get("MIROGPU_LAYOUT", "qbvh4"), choices=["bvh2", "cwbvh8", "bvh4", "qbvh4"])
     ap.add_argument("--variant", type=int, default=int(os.environ.get("MIROGPU_VARIANT", "-1")))
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg (faster iteration)")
     args = ap.parse_args()

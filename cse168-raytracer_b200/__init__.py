@@ -23,7 +23,7 @@ LIB_PATH = os.path.join(_PKG, "libmirogpu.so")
 
 MISS = 0xFFFFFFFF
 TMAX = np.float32(1e12)
-LAYOUT_BVH2, LAYOUT_CWBVH8, LAYOUT_BVH4 = 0, 1, 2
+LAYOUT_BVH2, LAYOUT_CWBVH8, LAYOUT_BVH4, LAYOUT_QBVH4 = 0, 1, 2, 3
 CLOSEST_HIT, ANY_HIT = 0, 1
 HINT_COHERENT = 0x100   # or-ed into a query mode: camera-like batch -> packet kernel
 RENDER_WHITTED, RENDER_DIFFUSE_BOUNCE, RENDER_PRIMARY_ONLY = 0, 1, 2
@@ -154,7 +154,7 @@ def phong(kd=(1, 1, 1), ks=(0, 0, 0), kt=(0, 0, 0), shininess=1.0, refract_index
 class MiroScene:
     """One scene resident in HBM on the current CUDA device (replicated per rank in multi-GPU runs)."""
 
-    def __init__(self, tri_vertices, tri_normals=None, material_ids=None, materials=None, layout=LAYOUT_CWBVH8,
+    def __init__(self, tri_vertices, tri_normals=None, material_ids=None, materials=None, layout=LAYOUT_QBVH4,
                  max_leaf=0, sah_bins=32, device=-1):
         v = np.ascontiguousarray(tri_vertices, np.float32).reshape(-1, 9)
         n = None if tri_normals is None else np.ascontiguousarray(tri_normals, np.float32).reshape(-1, 9)
@@ -360,7 +360,7 @@ class HostScene:
     """Drives the C++ host layer the way a user of the reference drives Scene / Camera (one global scene,
     like the reference's g_scene).  Same method names as the checker drivers in tests/miro_driver.py."""
 
-    def __init__(self, layout=LAYOUT_CWBVH8):
+    def __init__(self, layout=LAYOUT_QBVH4):
         self.h = host_lib()
         self.layout = layout
 

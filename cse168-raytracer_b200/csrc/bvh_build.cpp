@@ -350,6 +350,53 @@ void flatten_bvh4(const BinaryBvh& b, FlatBvh& out)
 }
 
 // ---------------------------------------------------------------------------------------------------
+void flatten_qbvh4(const BinaryBvh& b, FlatBvh& out)
+{
+    flatten_bvh4(b, out);
+    out.layout = 3;
+    out.nodesq.resize(out.nodes4.size());
+    const double kMargin = 0.02;   // cells; covers the few-ulp rounding of the device decode (traverse.cuh, qbvh4_node_step)
+#pragma omp parallel for schedule(static)
+    for (int64_t i = 0; i < (int64_t)out.nodes4.size(); ++i) {
+        const Bvh4Node& w = out.nodes4[i];
+        Qbvh4Node q; std::memset(&q, 0, sizeof q);
+        const float* lo[3] = {w.lox, w.loy, w.loz};
+        const float* hi[3] = {w.hix, w.hiy, w.hiz};
+        uint8_t* qlo[3] = {q.qlox, q.qloy, q.qloz};
+        uint8_t* qhi[3] = {q.qhix, q.qhiy, q.qhiz};
+        bool used[4];
+        for (int c = 0; c < 4; ++c) used[c] = std::isfinite(w.lox[c]);
+        for (int a = 0; a < 3; ++a) {
+            float mn = kInf, mx = -kInf;
+            for (int c = 0; c < 4; ++c) if (used[c]) { mn = std::min(mn, lo[a][c]); mx = std::max(mx, hi[a][c]); }
+            if (!(mn <= mx)) { mn = 0.f; mx = 0.f; }
+            q.origin[a] = mn;
+            // smallest power-of-two cell with origin + (255 - margin) * cell >= max; retried one notch coarser if a plane
+            // still lands above 255 after outward rounding
+            int e = (int)std::ceil(std::log2(std::max((double)mx - (double)mn, 1e-30) / (255.0 - 2.0 * kMargin)));
+            e = std::max(-100, std::min(100, e));
+            for (;;) {
+                const double cell = std::ldexp(1.0, e);
+                bool ok = true;
+                for (int c = 0; c < 4 && ok; ++c) {
+                    if (!used[c]) { qlo[a][c] = 255; qhi[a][c] = 0; continue; }
+                    const double l = std::floor(((double)lo[a][c] - (double)mn) / cell - kMargin);
+                    const double h = std::ceil(((double)hi[a][c] - (double)mn) / cell + kMargin);
+                    if (h > 255.0) { ok = false; break; }
+                    qlo[a][c] = (uint8_t)std::max(0.0, l);
+                    qhi[a][c] = (uint8_t)h;
+                }
+                if (ok) break;
+                ++e;
+            }
+            q.e[a] = (uint8_t)(e + 127);
+        }
+        for (int c = 0; c < 4; ++c) q.link[c] = w.link[c];
+        out.nodesq[(size_t)i] = q;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------
 namespace {
 struct WideChild { int32_t bnode; };
 }

@@ -67,6 +67,23 @@ struct Bvh4Node {
 };
 static_assert(sizeof(Bvh4Node) == 128, "Bvh4Node must be 128 bytes");
 
+// ---- QBVH4 flat layout (64 B / node = two 32-byte sectors) ---------------------------------------------------------
+// The same four-wide collapse as BVH4 with the child boxes quantised to 8 bits per plane on a per-node grid: grid
+// origin = the node's min corner (binary32), one power-of-two cell size per axis (biased exponent byte), planes =
+// origin + q * cell with q rounded outward (plus a safety margin that covers the decode's rounding).  Half the
+// sectors per visit of BVH4 / the same as BVH2 at half the visits -- the traversal is bound by L1 wavefronts per ray.
+//   origin[3] | ex,ey,ez,0 | qlo.x[4] qhi.x[4] qlo.y[4] qhi.y[4] || qlo.z[4] qhi.z[4] | link[4] | pad[2]
+// Empty slot: qlo = 255, qhi = 0 on every axis (an inverted interval never passes the slab test).
+struct Qbvh4Node {
+    float origin[3];
+    uint8_t e[3], pad0;
+    uint8_t qlox[4], qhix[4], qloy[4], qhiy[4];
+    uint8_t qloz[4], qhiz[4];
+    int32_t link[4];
+    int32_t pad[2];
+};
+static_assert(sizeof(Qbvh4Node) == 64, "Qbvh4Node must be 64 bytes");
+
 // ---- CWBVH8 flat layout (80 B / node) ----------------------------------------------------------------
 struct Cwbvh8Node {
     float p[3];          // quantisation grid origin (node box min)
@@ -97,6 +114,7 @@ struct FlatBvh {
     std::vector<Bvh2Node> nodes2;
     std::vector<Cwbvh8Node> nodes8;
     std::vector<Bvh4Node> nodes4;
+    std::vector<Qbvh4Node> nodesq;
     std::vector<uint32_t> order;  // flat triangle slot -> prim id
     Aabb root;
     uint32_t max_depth = 0;
@@ -106,6 +124,7 @@ struct FlatBvh {
 void flatten_bvh2(const BinaryBvh& b, FlatBvh& out);
 void flatten_cwbvh8(const BinaryBvh& b, FlatBvh& out);
 void flatten_bvh4(const BinaryBvh& b, FlatBvh& out);
+void flatten_qbvh4(const BinaryBvh& b, FlatBvh& out);   // flatten_bvh4, then quantise each node
 void make_tri_records(const float* tri_vertices, const std::vector<uint32_t>& order, std::vector<TriRecord>& out);
 
 }  // namespace mirogpu

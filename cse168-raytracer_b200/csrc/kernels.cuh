@@ -15,7 +15,7 @@
 namespace mirogpu {
 
 struct DeviceScene {
-    const float4* nodes;   // BVH2: 4 float4 per node; BVH4: 8 float4 per node; CWBVH8: 5 uint4 per node
+    const float4* nodes;   // BVH2: 4 float4 per node; BVH4: 8 float4 per node; QBVH4: 4 float4 per node; CWBVH8: 5 uint4 per node
     const float4* tris;    // 3 float4 per triangle, leaf order
     const float4* shade;   // 6 float4 per primitive, prim-id order: (A,mat) e1 e2 nA nB nC
     uint32_t num_tris;
@@ -33,6 +33,7 @@ __device__ __forceinline__ void trace_one(const DeviceScene& s, const mirogpu_ra
 {
     if (LAYOUT == MIROGPU_LAYOUT_BVH2) trace_bvh2<ANY, COUNT>(s.nodes, s.tris, r, best, c);
     else if (LAYOUT == MIROGPU_LAYOUT_BVH4) trace_bvh4<ANY, COUNT>(s.nodes, s.tris, r, best, c);
+    else if (LAYOUT == MIROGPU_LAYOUT_QBVH4) trace_qbvh4<ANY, COUNT>(s.nodes, s.tris, r, best, c);
     else trace_cwbvh8<ANY, COUNT>(reinterpret_cast<const uint4*>(s.nodes), s.tris, r, best, c);
 }
 
@@ -112,7 +113,7 @@ __global__ void __launch_bounds__(128) k_trace_persistent(DeviceScene s, const m
     }
 }
 
-// Persistent warps, hybrid step scheduling + ray replacement (BVH2 and BVH4).  In the while-while kernel a round costs the
+// Persistent warps, hybrid step scheduling + ray replacement (BVH2, BVH4, QBVH4).  In the while-while kernel a round costs the
 // warp max-over-lanes(descent length) node steps plus max-over-lanes(leaf size) triangle tests, and on incoherent
 // rays the descent lengths differ so much that 7 of 32 lanes are busy on average (ncu; tools/simt_sim.cu replays
 // the same rays and predicts the same figure).  Here every iteration the warp votes: it takes node steps while at
@@ -138,7 +139,7 @@ __global__ void __launch_bounds__(128, MINB) k_trace_hybrid(DeviceScene s, const
     mirogpu_ray r;
     Bvh2Walk w;
     BestHit best;
-    int32_t stack[(LAYOUT == MIROGPU_LAYOUT_BVH4 ? MIRO_STACK4 : MIRO_STACK) + 1];
+    int32_t stack[(LAYOUT == MIROGPU_LAYOUT_BVH2 ? MIRO_STACK : MIRO_STACK4) + 1];
     r.ox = r.oy = r.oz = r.tmin = r.dx = r.dy = r.dz = r.tmax = 0.f;
     w.node = w.tos = MIRO_BVH2_DONE; w.sp = 0;
     w.idx = w.idy = w.idz = w.oodx = w.oody = w.oodz = 0.f;
@@ -188,7 +189,8 @@ __global__ void __launch_bounds__(128, MINB) k_trace_hybrid(DeviceScene s, const
 #pragma unroll
                 for (int rep = 0; rep < NREP; ++rep)
                     if (w.node >= 0) {
-                        if (LAYOUT == MIROGPU_LAYOUT_BVH4) bvh4_node_step<PF>(s.nodes, s.tris, r, w, stack, best);
+                        if (LAYOUT == MIROGPU_LAYOUT_QBVH4) qbvh4_node_step<PF>(s.nodes, s.tris, r, w, stack, best);
+                        else if (LAYOUT == MIROGPU_LAYOUT_BVH4) bvh4_node_step<PF>(s.nodes, s.tris, r, w, stack, best);
                         else bvh2_node_step<PF>(s.nodes, s.tris, r, w, stack, best);
                     }
             } else if (w.node < 0 && w.node != MIRO_BVH2_DONE) {

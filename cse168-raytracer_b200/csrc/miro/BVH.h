@@ -13,7 +13,7 @@
 
 class BVH {
 public:
-    BVH() : m_handle(0), m_objects(0), m_layout(MIROGPU_LAYOUT_CWBVH8) {}
+    BVH() : m_handle(0), m_objects(0), m_layout(MIROGPU_LAYOUT_QBVH4) {}
     ~BVH();
     void build(Objects* objs, int depth = 0);
     bool intersect(HitInfo& result, const Ray& ray, float tMin = 0.0f, float tMax = MIRO_TMAX) const;

@@ -18,7 +18,7 @@
 namespace {
 std::vector<Material*> g_materials;
 std::map<const Object*, int> g_prim_id;
-int g_layout = MIROGPU_LAYOUT_CWBVH8;
+int g_layout = MIROGPU_LAYOUT_QBVH4;
 }
 
 extern "C" {

@@ -127,7 +127,9 @@ cudaError_t launch_trace(mirogpu_scene* h, const mirogpu_ray* d_rays, size_t n, 
     unsigned long long* ticket = h->d_ticket + (h->ticket_slot.fetch_add(1) & 63u);
     cudaError_t e = cudaMemsetAsync(ticket, 0, sizeof(unsigned long long), st);
     if (e != cudaSuccess) return e;
-    if (LAYOUT != MIROGPU_LAYOUT_CWBVH8 && (h->variant == 2 || (h->variant < 0 && !coherent)) && n < 0xFF000000ull)
+    // automatic choice: the hybrid-scheduled kernel, except coherent batches on BVH2, where 32-ray packets walking in
+    // lockstep are cheaper (QBVH4: hybrid 10.8 vs packets 9.2 Grays/s on camera rays; BVH2: 10.5 vs 11.5)
+    if (LAYOUT != MIROGPU_LAYOUT_CWBVH8 && (h->variant == 2 || (h->variant < 0 && !(coherent && LAYOUT == MIROGPU_LAYOUT_BVH2))) && n < 0xFF000000ull)
         return launch_hybrid<LAYOUT == MIROGPU_LAYOUT_CWBVH8 ? MIROGPU_LAYOUT_BVH2 : LAYOUT, ANY>(h, d_rays, n, d_hits, ticket, st, d_n, mult);
     static std::atomic<int> cached_occ{0};
     int occ = cached_occ.load(std::memory_order_relaxed);
@@ -155,6 +157,9 @@ cudaError_t dispatch_trace(mirogpu_scene* h, const mirogpu_ray* d_rays, size_t n
     if (h->layout == MIROGPU_LAYOUT_BVH4)
         return any ? launch_trace<MIROGPU_LAYOUT_BVH4, true>(h, d_rays, n, d_hits, st, d_n, mult, coherent)
                    : launch_trace<MIROGPU_LAYOUT_BVH4, false>(h, d_rays, n, d_hits, st, d_n, mult, coherent);
+    if (h->layout == MIROGPU_LAYOUT_QBVH4)
+        return any ? launch_trace<MIROGPU_LAYOUT_QBVH4, true>(h, d_rays, n, d_hits, st, d_n, mult, coherent)
+                   : launch_trace<MIROGPU_LAYOUT_QBVH4, false>(h, d_rays, n, d_hits, st, d_n, mult, coherent);
     return any ? launch_trace<MIROGPU_LAYOUT_CWBVH8, true>(h, d_rays, n, d_hits, st, d_n, mult, coherent)
                : launch_trace<MIROGPU_LAYOUT_CWBVH8, false>(h, d_rays, n, d_hits, st, d_n, mult, coherent);
 }
@@ -212,9 +217,10 @@ int mirogpu_scene_create(const float* tri_vertices, const float* tri_normals, co
     if (ntris && !tri_vertices) return fail(MIROGPU_ERR_INVALID_ARG, "tri_vertices is NULL");
     if (ntris >= (1u << 28) - 16u) return fail(MIROGPU_ERR_INVALID_ARG, "too many triangles (limit 2^28 - 16)");
     mirogpu_build_options o;
-    o.layout = MIROGPU_LAYOUT_CWBVH8; o.max_leaf = 0; o.sah_bins = 32; o.device = -1;
+    o.layout = MIROGPU_LAYOUT_QBVH4; o.max_leaf = 0; o.sah_bins = 32; o.device = -1;
     if (opt) o = *opt;
-    if (o.layout != MIROGPU_LAYOUT_BVH2 && o.layout != MIROGPU_LAYOUT_CWBVH8 && o.layout != MIROGPU_LAYOUT_BVH4) return fail(MIROGPU_ERR_INVALID_ARG, "unknown layout");
+    if (o.layout != MIROGPU_LAYOUT_BVH2 && o.layout != MIROGPU_LAYOUT_CWBVH8 && o.layout != MIROGPU_LAYOUT_BVH4 && o.layout != MIROGPU_LAYOUT_QBVH4)
+        return fail(MIROGPU_ERR_INVALID_ARG, "unknown layout");
     if (o.max_leaf <= 0) if (const char* e = getenv("MIROGPU_MAX_LEAF")) o.max_leaf = atoi(e);   // tuning knob
     if (o.max_leaf <= 0) o.max_leaf = (o.layout == MIROGPU_LAYOUT_CWBVH8) ? 3 : 4;
     if (o.layout == MIROGPU_LAYOUT_CWBVH8 && o.max_leaf > 3) o.max_leaf = 3;
@@ -237,6 +243,7 @@ int mirogpu_scene_create(const float* tri_vertices, const float* tri_normals, co
     cudaDeviceProp prop;
     CUDA_TRY(cudaGetDeviceProperties(&prop, dev));
     h->sm_count = prop.multiProcessorCount;
+    if (o.layout == MIROGPU_LAYOUT_QBVH4 || o.layout == MIROGPU_LAYOUT_BVH4) { h->hyb_period = 2; h->hyb_min_idle = 6; }   // measured optimum of the four-wide steps
     if (const char* e = getenv("MIROGPU_POOL")) { const int v = atoi(e); if (v >= 32 && v <= 65536) h->hyb_pool = v; }
     if (const char* e = getenv("MIROGPU_NREP")) h->hyb_nrep = atoi(e);
     if (const char* e = getenv("MIROGPU_NMIN")) { const int v = atoi(e); if (v >= 1 && v <= 32) h->hyb_nmin = v; }
@@ -252,18 +259,21 @@ int mirogpu_scene_create(const float* tri_vertices, const float* tri_normals, co
     FlatBvh flat;
     if (o.layout == MIROGPU_LAYOUT_BVH2) flatten_bvh2(bin, flat);
     else if (o.layout == MIROGPU_LAYOUT_BVH4) flatten_bvh4(bin, flat);
+    else if (o.layout == MIROGPU_LAYOUT_QBVH4) flatten_qbvh4(bin, flat);
     else flatten_cwbvh8(bin, flat);
     // a walk pushes at most one entry per level (BVH2 / CWBVH8 groups) resp. flat.max_stack entries (BVH4): refuse a tree the
     // kernels' fixed per-thread stacks cannot hold rather than overrun them (the builder's depth cap makes this unreachable
     // below ~16 M triangles)
-    if (o.layout != MIROGPU_LAYOUT_BVH4 && bin.max_depth > MIRO_STACK) { delete h; return fail(MIROGPU_ERR_INVALID_ARG, "tree deeper than the kernels' traversal stack"); }
-    if (o.layout == MIROGPU_LAYOUT_BVH4 && flat.max_stack > MIRO_STACK4) { delete h; return fail(MIROGPU_ERR_INVALID_ARG, "BVH4 tree needs a deeper traversal stack than the kernels carry"); }
+    const bool wide4 = o.layout == MIROGPU_LAYOUT_BVH4 || o.layout == MIROGPU_LAYOUT_QBVH4;
+    if (!wide4 && bin.max_depth > MIRO_STACK) { delete h; return fail(MIROGPU_ERR_INVALID_ARG, "tree deeper than the kernels' traversal stack"); }
+    if (wide4 && flat.max_stack > MIRO_STACK4) { delete h; return fail(MIROGPU_ERR_INVALID_ARG, "BVH4 tree needs a deeper traversal stack than the kernels carry"); }
     make_tri_records(tri_vertices, flat.order, h->h_tris);
     double t2 = now_s();
 
     const void* node_src; size_t node_bytes;
     if (o.layout == MIROGPU_LAYOUT_BVH2) { node_src = flat.nodes2.data(); node_bytes = flat.nodes2.size() * sizeof(Bvh2Node); }
     else if (o.layout == MIROGPU_LAYOUT_BVH4) { node_src = flat.nodes4.data(); node_bytes = flat.nodes4.size() * sizeof(Bvh4Node); }
+    else if (o.layout == MIROGPU_LAYOUT_QBVH4) { node_src = flat.nodesq.data(); node_bytes = flat.nodesq.size() * sizeof(Qbvh4Node); }
     else { node_src = flat.nodes8.data(); node_bytes = flat.nodes8.size() * sizeof(Cwbvh8Node); }
     h->h_nodes.assign((const uint8_t*)node_src, (const uint8_t*)node_src + node_bytes);
 
@@ -327,7 +337,7 @@ int mirogpu_scene_create(const float* tri_vertices, const float* tri_normals, co
 
     mirogpu_scene_info& in = h->info;
     in.num_triangles = ntris;
-    in.num_nodes = (uint32_t)(o.layout == MIROGPU_LAYOUT_BVH2 ? flat.nodes2.size() : o.layout == MIROGPU_LAYOUT_BVH4 ? flat.nodes4.size() : flat.nodes8.size());
+    in.num_nodes = (uint32_t)(o.layout == MIROGPU_LAYOUT_BVH2 ? flat.nodes2.size() : wide4 ? flat.nodes4.size() : flat.nodes8.size());
     in.num_binary_nodes = (uint32_t)bin.nodes.size();
     in.num_binary_leaves = bin.num_leaves;
     in.max_depth = o.layout == MIROGPU_LAYOUT_BVH2 ? bin.max_depth : flat.max_depth;
@@ -479,6 +489,9 @@ int mirogpu_intersect_batch_counted(mirogpu_handle h, const mirogpu_ray* rays, s
     if (h->layout == MIROGPU_LAYOUT_BVH4) {
         if (any) k_trace_simple<MIROGPU_LAYOUT_BVH4, true, true><<<grid, 128>>>(h->ds, d_r, n, d_h, d_c, nullptr, 1);
         else k_trace_simple<MIROGPU_LAYOUT_BVH4, false, true><<<grid, 128>>>(h->ds, d_r, n, d_h, d_c, nullptr, 1);
+    } else if (h->layout == MIROGPU_LAYOUT_QBVH4) {
+        if (any) k_trace_simple<MIROGPU_LAYOUT_QBVH4, true, true><<<grid, 128>>>(h->ds, d_r, n, d_h, d_c, nullptr, 1);
+        else k_trace_simple<MIROGPU_LAYOUT_QBVH4, false, true><<<grid, 128>>>(h->ds, d_r, n, d_h, d_c, nullptr, 1);
     } else if (h->layout == MIROGPU_LAYOUT_BVH2) {
         if (any) k_trace_simple<MIROGPU_LAYOUT_BVH2, true, true><<<grid, 128>>>(h->ds, d_r, n, d_h, d_c, nullptr, 1);
         else k_trace_simple<MIROGPU_LAYOUT_BVH2, false, true><<<grid, 128>>>(h->ds, d_r, n, d_h, d_c, nullptr, 1);
@@ -491,7 +504,7 @@ int mirogpu_intersect_batch_counted(mirogpu_handle h, const mirogpu_ray* rays, s
     CUDA_TRY(cudaMemcpy(hc, d_c, sizeof hc, cudaMemcpyDeviceToHost));
     CUDA_TRY(cudaMemcpy(hits, d_h, n * sizeof(mirogpu_hit), cudaMemcpyDeviceToHost));
     cudaFree(d_r); cudaFree(d_h); cudaFree(d_c);
-    const uint64_t node_size = h->layout == MIROGPU_LAYOUT_BVH2 ? 64 : h->layout == MIROGPU_LAYOUT_BVH4 ? 128 : 80;
+    const uint64_t node_size = h->layout == MIROGPU_LAYOUT_BVH2 ? 64 : h->layout == MIROGPU_LAYOUT_BVH4 ? 128 : h->layout == MIROGPU_LAYOUT_QBVH4 ? 64 : 80;
     c->rays += n; c->node_visits += hc[0]; c->box_tests += hc[1]; c->triangle_tests += hc[2]; c->hits += hc[3];
     c->bytes_fetched += hc[0] * node_size + hc[2] * sizeof(TriRecord);
     return MIROGPU_OK;
@@ -641,6 +654,7 @@ int mirogpu_photon_trace(mirogpu_handle h, int light_index, int caustic, uint32_
         const unsigned grid = (count + 127) / 128;
         if (h->layout == MIROGPU_LAYOUT_BVH2) k_photon_trace<MIROGPU_LAYOUT_BVH2><<<grid, 128, 0, cudaStreamPerThread>>>(h->ds, h->d_materials, em, d_counts, d_records);
         else if (h->layout == MIROGPU_LAYOUT_BVH4) k_photon_trace<MIROGPU_LAYOUT_BVH4><<<grid, 128, 0, cudaStreamPerThread>>>(h->ds, h->d_materials, em, d_counts, d_records);
+        else if (h->layout == MIROGPU_LAYOUT_QBVH4) k_photon_trace<MIROGPU_LAYOUT_QBVH4><<<grid, 128, 0, cudaStreamPerThread>>>(h->ds, h->d_materials, em, d_counts, d_records);
         else k_photon_trace<MIROGPU_LAYOUT_CWBVH8><<<grid, 128, 0, cudaStreamPerThread>>>(h->ds, h->d_materials, em, d_counts, d_records);
         e = cudaGetLastError();
     }

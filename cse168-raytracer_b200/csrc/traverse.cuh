@@ -13,6 +13,7 @@
 
 #include <cstdint>
 #include <cuda_runtime.h>
+#include <cuda_fp16.h>
 
 #include "../../include/mirogpu.h"
 
@@ -357,6 +358,43 @@ MIRO_HD void bvh2_leaf_step(const float4* __restrict__ tris, const mirogpu_ray& 
     bvh2_pop(w, stack);
 }
 
+
+// Child order of the four-wide layouts: a three-comparator tournament on (entry distance, link) finds the nearest hit
+// child, which is descended next; the two first-round losers are pushed first and the runner-up of the final last, so
+// the nearer of the remaining children tends to be popped earlier.  Misses carry distance +inf and are never pushed.
+template <int PF>
+MIRO_HD void wide4_descend(const float d[4], const int32_t lk[4], const float4* __restrict__ tris, Bvh2Walk& w, int32_t* __restrict__ stack)
+{
+    const float kFar = u2f(0x7f800000u);
+    float da = d[0], db = d[1], dc = d[2], de = d[3];
+    int32_t la = lk[0], lb = lk[1], lc = lk[2], le = lk[3];
+    if (db < da) { const float t = da; da = db; db = t; const int32_t u = la; la = lb; lb = u; }
+    if (de < dc) { const float t = dc; dc = de; de = t; const int32_t u = lc; lc = le; le = u; }
+    if (dc < da) { const float t = da; da = dc; dc = t; const int32_t u = la; la = lc; lc = u; }
+    if (!(da < kFar)) { bvh2_pop(w, stack); return; }
+    if (db < kFar) { stack[w.sp++] = w.tos; w.tos = lb; }
+    if (de < kFar) { stack[w.sp++] = w.tos; w.tos = le; }
+    if (dc < kFar) { stack[w.sp++] = w.tos; w.tos = lc; }
+    if ((PF & 4) && la < 0) {
+        const float4* a = tris + 4 * (size_t)(((uint32_t)~la) >> 3);
+        if (PF & 2) prefetch_l1(a); else prefetch_l2(a);
+    }
+    w.node = la;
+}
+
+// f[i] = 1024 + byte i of w, exactly.  Device: two PRMTs build the four binary16 values 0x64bb (= 1024 + bb, bb fits the
+// 10-bit mantissa) and the half -> float conversions run on the FMA pipe, which the traversal leaves mostly idle.
+MIRO_HD void unpack_planes(uint32_t w, float f[4])
+{
+#ifdef __CUDA_ARCH__
+    const uint32_t p01 = __byte_perm(w, 0x64646464u, 0x4140), p23 = __byte_perm(w, 0x64646464u, 0x4342);
+    const __half2 h01 = *reinterpret_cast<const __half2*>(&p01), h23 = *reinterpret_cast<const __half2*>(&p23);
+    f[0] = __low2float(h01); f[1] = __high2float(h01); f[2] = __low2float(h23); f[3] = __high2float(h23);
+#else
+    for (int i = 0; i < 4; ++i) f[i] = 1024.0f + (float)((w >> (8 * i)) & 0xffu);
+#endif
+}
+
 // ---- BVH4 (128-byte nodes, four full-precision child boxes per fetch) ---------------------------------------------
 // Node = 8 x float4: (lo.x[4]) (hi.x[4]) (lo.y[4]) (hi.y[4]) (lo.z[4]) (hi.z[4]) (link[4]) (pad) -- four 256-bit loads, one
 // cache line.  Same walk state and leaf step as BVH2.  Child order: a three-comparator tournament finds the nearest
@@ -383,21 +421,7 @@ MIRO_HD void bvh4_node_step(const float4* __restrict__ nodes, const float4* __re
         const float tf = fminf(fminf(fmaxf(ax, bx), fmaxf(ay, by)), fminf(fmaxf(az, bz), best.t));
         d[c] = tn <= tf ? tn : kFar;
     }
-    // tournament on (distance, link)
-    float da = d[0], db = d[1], dc = d[2], de = d[3];
-    int32_t la = lk[0], lb = lk[1], lc = lk[2], le = lk[3];
-    if (db < da) { const float t = da; da = db; db = t; const int32_t u = la; la = lb; lb = u; }
-    if (de < dc) { const float t = dc; dc = de; de = t; const int32_t u = lc; lc = le; le = u; }
-    if (dc < da) { const float t = da; da = dc; dc = t; const int32_t u = la; la = lc; lc = u; }
-    if (!(da < kFar)) { bvh2_pop(w, stack); return; }
-    if (db < kFar) { stack[w.sp++] = w.tos; w.tos = lb; }
-    if (de < kFar) { stack[w.sp++] = w.tos; w.tos = le; }
-    if (dc < kFar) { stack[w.sp++] = w.tos; w.tos = lc; }
-    if ((PF & 4) && la < 0) {
-        const float4* a = tris + 4 * (size_t)(((uint32_t)~la) >> 3);
-        if (PF & 2) prefetch_l1(a); else prefetch_l2(a);
-    }
-    w.node = la;
+    wide4_descend<PF>(d, lk, tris, w, stack);
 }
 
 // Whole walk of one ray (packet / one-thread-per-ray kernels, the photon walker, the counting build).
@@ -412,6 +436,61 @@ MIRO_HD void trace_bvh4(const float4* __restrict__ nodes, const float4* __restri
         while (w.node >= 0) {
             if (COUNT) { cnt->nodes++; cnt->boxes += 4; }
             bvh4_node_step<0>(nodes, tris, r, w, stack, best);
+        }
+        if (w.node == MIRO_BVH2_DONE) return;
+        if (COUNT) cnt->tris += (((uint32_t)~w.node) & 7u) + 1u;
+        bvh2_leaf_step<ANY>(tris, r, w, stack, best);
+        if (w.node == MIRO_BVH2_DONE) return;
+    }
+}
+
+// ---- QBVH4 (64-byte nodes, four child boxes quantised to 8 bits per plane on a per-node grid) ------------------------
+// Node = 4 x float4: (origin.xyz, ex|ey<<8|ez<<16) (qlo.x[4], qhi.x[4], qlo.y[4], qhi.y[4]) (qlo.z[4], qhi.z[4], link0, link1)
+// (link2, link3, -, -): two 256-bit loads.  A plane is origin + q * cell with cell = 2^(e-127); along the ray
+//   t = (origin + q cell - o) / d = (1024 + q) * (cell / d) + ((origin - o) / d - 1024 cell / d),
+// one FMA per plane once the two per-axis constants are formed.  The near / far plane words are picked by the sign of
+// the direction (two selects per axis), so no per-plane min / max is needed.  The builder rounds q outward with a
+// margin of 0.02 cell, far above the rounding of this decode (about 3 ulp of 4 node extents).
+template <int PF>
+MIRO_HD void qbvh4_node_step(const float4* __restrict__ nodes, const float4* __restrict__ tris, const mirogpu_ray& r, Bvh2Walk& w,
+                             int32_t* __restrict__ stack, const BestHit& best)
+{
+    const float4* p = nodes + 4 * (size_t)w.node;
+    const F8 A = ld256(p), B = ld256(p + 2);
+    const uint32_t ew = f2u(A.lo.w);
+    const float cx = u2f((ew & 0xffu) << 23) * w.idx, cy = u2f(((ew >> 8) & 0xffu) << 23) * w.idy, cz = u2f(((ew >> 16) & 0xffu) << 23) * w.idz;
+    const float bx = fmaf(-1024.0f, cx, fmaf(A.lo.x, w.idx, -w.oodx));
+    const float by = fmaf(-1024.0f, cy, fmaf(A.lo.y, w.idy, -w.oody));
+    const float bz = fmaf(-1024.0f, cz, fmaf(A.lo.z, w.idz, -w.oodz));
+    const bool px = w.idx >= 0.f, py = w.idy >= 0.f, pz = w.idz >= 0.f;
+    const uint32_t qlx = f2u(A.hi.x), qhx = f2u(A.hi.y), qly = f2u(A.hi.z), qhy = f2u(A.hi.w), qlz = f2u(B.lo.x), qhz = f2u(B.lo.y);
+    float nx[4], fx[4], ny[4], fy[4], nz[4], fz[4];
+    unpack_planes(px ? qlx : qhx, nx); unpack_planes(px ? qhx : qlx, fx);
+    unpack_planes(py ? qly : qhy, ny); unpack_planes(py ? qhy : qly, fy);
+    unpack_planes(pz ? qlz : qhz, nz); unpack_planes(pz ? qhz : qlz, fz);
+    const int32_t lk[4] = {(int32_t)f2u(B.lo.z), (int32_t)f2u(B.lo.w), (int32_t)f2u(B.hi.x), (int32_t)f2u(B.hi.y)};
+    const float kFar = u2f(0x7f800000u);
+    float d[4];
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+        const float tn = fmaxf(fmaxf(fmaf(nx[c], cx, bx), fmaf(ny[c], cy, by)), fmaxf(fmaf(nz[c], cz, bz), r.tmin));
+        const float tf = fminf(fminf(fmaf(fx[c], cx, bx), fmaf(fy[c], cy, by)), fminf(fmaf(fz[c], cz, bz), best.t));
+        d[c] = tn <= tf ? tn : kFar;
+    }
+    wide4_descend<PF>(d, lk, tris, w, stack);
+}
+
+template <bool ANY, bool COUNT>
+MIRO_HD void trace_qbvh4(const float4* __restrict__ nodes, const float4* __restrict__ tris, const mirogpu_ray& r, BestHit& best,
+                         TraceCounters* cnt)
+{
+    Bvh2Walk w;
+    int32_t stack[MIRO_STACK4 + 1];
+    bvh2_begin(r, w, best);
+    for (;;) {
+        while (w.node >= 0) {
+            if (COUNT) { cnt->nodes++; cnt->boxes += 4; }
+            qbvh4_node_step<0>(nodes, tris, r, w, stack, best);
         }
         if (w.node == MIRO_BVH2_DONE) return;
         if (COUNT) cnt->tris += (((uint32_t)~w.node) & 7u) + 1u;

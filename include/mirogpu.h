@@ -95,11 +95,11 @@ typedef struct mirogpu_camera {
     float fov_degrees;
 } mirogpu_camera;
 
-enum { MIROGPU_LAYOUT_BVH2 = 0, MIROGPU_LAYOUT_CWBVH8 = 1, MIROGPU_LAYOUT_BVH4 = 2 };
+enum { MIROGPU_LAYOUT_BVH2 = 0, MIROGPU_LAYOUT_CWBVH8 = 1, MIROGPU_LAYOUT_BVH4 = 2, MIROGPU_LAYOUT_QBVH4 = 3 };
 
 typedef struct mirogpu_build_options {
-    int32_t layout;       /* MIROGPU_LAYOUT_*; default CWBVH8 */
-    int32_t max_leaf;     /* triangles per leaf (BVH2 / BVH4: <= 4 like the reference's OBJECTS_PER_LEAF; CWBVH8: <= 3) */
+    int32_t layout;       /* MIROGPU_LAYOUT_*; default QBVH4 (the fastest measured) */
+    int32_t max_leaf;     /* triangles per leaf (BVH2 / BVH4 / QBVH4: <= 4 like the reference's OBJECTS_PER_LEAF; CWBVH8: <= 3) */
     int32_t sah_bins;     /* binned SAH resolution, default 32 */
     int32_t device;       /* CUDA device ordinal, -1 = current device */
 } mirogpu_build_options;
@@ -190,9 +190,10 @@ int mirogpu_intersect_batch_device(mirogpu_handle h, const mirogpu_ray* d_rays, 
 /* Same query through the instrumented kernel; counters are accumulated into *c (host struct). */
 int mirogpu_intersect_batch_counted(mirogpu_handle h, const mirogpu_ray* rays, size_t n, mirogpu_hit* hits,
                                     int mode, mirogpu_counters* c);
-/* Kernel variant selection for measurement: -1 = automatic (default: hybrid kernel for BVH2 unless the batch carries
- * MIROGPU_HINT_COHERENT; packet kernel for CWBVH8), 0 = persistent warps taking 32-ray packets (while-while),
- * 1 = one thread per ray, 2 = persistent warps with hybrid step scheduling + ray replacement (BVH2 only). */
+/* Kernel variant selection for measurement: -1 = automatic (default: the hybrid kernel, except BVH2 batches carrying
+ * MIROGPU_HINT_COHERENT and all CWBVH8 batches, which go to the packet kernel), 0 = persistent warps taking 32-ray
+ * packets (while-while), 1 = one thread per ray, 2 = persistent warps with hybrid step scheduling + ray replacement
+ * (BVH2, BVH4, QBVH4). */
 int mirogpu_set_kernel_variant(mirogpu_handle h, int variant);
 
 /* Reconstructs P, N (normalised as Scene::trace does for UV materials, Scene.cpp:262) and material id

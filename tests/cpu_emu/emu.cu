@@ -19,21 +19,22 @@ extern "C" int emu_trace(const float* tri_vertices, uint32_t ntris, int layout, 
 {
     // layout 2: the BVH2 tree walked through the single-step functions of the hybrid kernel; layout 3: BVH4
     const int walk = layout == 2 ? 2 : 0;
-    const bool wide4 = layout == 3;
+    const bool wide4 = layout == 3, quant4 = layout == 4;
     if (layout >= 2) layout = MIROGPU_LAYOUT_BVH2;
     if (max_leaf <= 0) max_leaf = layout == MIROGPU_LAYOUT_CWBVH8 ? 3 : 4;
     if (layout == MIROGPU_LAYOUT_CWBVH8 && max_leaf > 3) max_leaf = 3;
     BinaryBvh bin = build_binary_sah(tri_vertices, ntris, max_leaf, 32);
     FlatBvh flat;
-    if (wide4) flatten_bvh4(bin, flat); else if (layout == MIROGPU_LAYOUT_BVH2) flatten_bvh2(bin, flat); else flatten_cwbvh8(bin, flat);
+    if (quant4) flatten_qbvh4(bin, flat); else if (wide4) flatten_bvh4(bin, flat); else if (layout == MIROGPU_LAYOUT_BVH2) flatten_bvh2(bin, flat); else flatten_cwbvh8(bin, flat);
     std::vector<TriRecord> tris;
     make_tri_records(tri_vertices, flat.order, tris);
-    if (wide4 && flat.max_stack > MIRO_STACK4) return 1;
+    if ((wide4 || quant4) && flat.max_stack > MIRO_STACK4) return 1;
     if (info4) {
-        info4[0] = (uint32_t)(wide4 ? flat.nodes4.size() : layout == MIROGPU_LAYOUT_BVH2 ? flat.nodes2.size() : flat.nodes8.size());
+        info4[0] = (uint32_t)((wide4 || quant4) ? flat.nodes4.size() : layout == MIROGPU_LAYOUT_BVH2 ? flat.nodes2.size() : flat.nodes8.size());
         info4[1] = (uint32_t)bin.nodes.size(); info4[2] = bin.num_leaves; info4[3] = flat.max_depth;
     }
-    const float4* nodes = wide4 ? reinterpret_cast<const float4*>(flat.nodes4.data())
+    const float4* nodes = quant4 ? reinterpret_cast<const float4*>(flat.nodesq.data())
+                          : wide4 ? reinterpret_cast<const float4*>(flat.nodes4.data())
                           : layout == MIROGPU_LAYOUT_BVH2 ? reinterpret_cast<const float4*>(flat.nodes2.data())
                                                           : reinterpret_cast<const float4*>(flat.nodes8.data());
     const float4* tr = reinterpret_cast<const float4*>(tris.data());
@@ -42,7 +43,9 @@ extern "C" int emu_trace(const float* tri_vertices, uint32_t ntris, int layout, 
     for (long i = 0; i < n; ++i) {
         BestHit best;
         TraceCounters c = {0, 0, 0};
-        if (wide4) {
+        if (quant4) {
+            if (any_hit) trace_qbvh4<true, true>(nodes, tr, rays[i], best, &c); else trace_qbvh4<false, true>(nodes, tr, rays[i], best, &c);
+        } else if (wide4) {
             if (any_hit) trace_bvh4<true, true>(nodes, tr, rays[i], best, &c); else trace_bvh4<false, true>(nodes, tr, rays[i], best, &c);
         } else if (walk) {
             Bvh2Walk st;
@@ -78,11 +81,11 @@ extern "C" int emu_build(const float* tri_vertices, uint32_t ntris, int layout, 
     if (layout == MIROGPU_LAYOUT_CWBVH8 && max_leaf > 3) max_leaf = 3;
     BinaryBvh bin = build_binary_sah(tri_vertices, ntris, max_leaf, 32);
     FlatBvh flat;
-    if (layout == 3) flatten_bvh4(bin, flat); else if (layout == MIROGPU_LAYOUT_BVH2) flatten_bvh2(bin, flat); else flatten_cwbvh8(bin, flat);
-    const size_t nb = layout == 3 ? flat.nodes4.size() * sizeof(Bvh4Node)
+    if (layout == 4) flatten_qbvh4(bin, flat); else if (layout == 3) flatten_bvh4(bin, flat); else if (layout == MIROGPU_LAYOUT_BVH2) flatten_bvh2(bin, flat); else flatten_cwbvh8(bin, flat);
+    const size_t nb = layout == 4 ? flat.nodesq.size() * sizeof(Qbvh4Node) : layout == 3 ? flat.nodes4.size() * sizeof(Bvh4Node)
                                   : layout == MIROGPU_LAYOUT_BVH2 ? flat.nodes2.size() * sizeof(Bvh2Node) : flat.nodes8.size() * sizeof(Cwbvh8Node);
-    sizes[0] = nb; sizes[1] = flat.order.size(); sizes[2] = bin.nodes.size(); sizes[3] = bin.num_leaves; sizes[4] = layout == 3 ? flat.max_stack : flat.max_depth;
-    if (out_nodes) memcpy(out_nodes, layout == 3 ? (const void*)flat.nodes4.data() : layout == MIROGPU_LAYOUT_BVH2 ? (const void*)flat.nodes2.data() : (const void*)flat.nodes8.data(), nb);
+    sizes[0] = nb; sizes[1] = flat.order.size(); sizes[2] = bin.nodes.size(); sizes[3] = bin.num_leaves; sizes[4] = layout >= 3 ? flat.max_stack : flat.max_depth;
+    if (out_nodes) memcpy(out_nodes, layout == 4 ? (const void*)flat.nodesq.data() : layout == 3 ? (const void*)flat.nodes4.data() : layout == MIROGPU_LAYOUT_BVH2 ? (const void*)flat.nodes2.data() : (const void*)flat.nodes8.data(), nb);
     if (out_order) memcpy(out_order, flat.order.data(), flat.order.size() * sizeof(uint32_t));
     if (out_tris) {
         std::vector<TriRecord> tris;

@@ -10,9 +10,11 @@ CW_NODE = np.dtype([("p", np.float32, 3), ("e", np.uint8, 3), ("imask", np.uint8
                     ("qhix", np.uint8, 8), ("qhiy", np.uint8, 8), ("qhiz", np.uint8, 8)])
 BVH4_NODE = np.dtype([("lox", np.float32, 4), ("hix", np.float32, 4), ("loy", np.float32, 4), ("hiy", np.float32, 4), ("loz", np.float32, 4), ("hiz", np.float32, 4),
                       ("link", np.int32, 4), ("pad", np.int32, 4)])
+QBVH4_NODE = np.dtype([("origin", np.float32, 3), ("e", np.uint8, 3), ("pad0", np.uint8), ("qlox", np.uint8, 4), ("qhix", np.uint8, 4), ("qloy", np.uint8, 4),
+                       ("qhiy", np.uint8, 4), ("qloz", np.uint8, 4), ("qhiz", np.uint8, 4), ("link", np.int32, 4), ("pad", np.int32, 2)])
 TRI_REC = np.dtype([("a", np.float32, 3), ("prim_id", np.uint32), ("e1", np.float32, 3), ("nx", np.float32), ("e2", np.float32, 3), ("ny", np.float32),
                     ("nz", np.float32), ("pad", np.float32, 3)])
-assert BVH2_NODE.itemsize == 64 and CW_NODE.itemsize == 80 and TRI_REC.itemsize == 64 and BVH4_NODE.itemsize == 128
+assert BVH2_NODE.itemsize == 64 and CW_NODE.itemsize == 80 and TRI_REC.itemsize == 64 and BVH4_NODE.itemsize == 128 and QBVH4_NODE.itemsize == 64
 
 
 def emu_trace(emu, verts, rays, layout, any_hit=False, max_leaf=0):
@@ -37,7 +39,7 @@ def emu_build(emu, verts, layout, max_leaf=0):
     tris = np.zeros(sizes[1], TRI_REC)
     emu.emu_build(vp, ctypes.c_uint32(verts.shape[0]), int(layout), int(max_leaf), nodes.ctypes.data_as(ctypes.c_void_p),
                   order.ctypes.data_as(ctypes.c_void_p), tris.ctypes.data_as(ctypes.c_void_p), sizes)
-    return nodes.view({0: BVH2_NODE, 1: CW_NODE, 3: BVH4_NODE}[layout]), order, tris, dict(binary_nodes=sizes[2], binary_leaves=sizes[3], depth=sizes[4])
+    return nodes.view({0: BVH2_NODE, 1: CW_NODE, 3: BVH4_NODE, 4: QBVH4_NODE}[layout]), order, tris, dict(binary_nodes=sizes[2], binary_leaves=sizes[3], depth=sizes[4])
 
 
 def hit_ids(hits):

@@ -22,7 +22,7 @@ from conftest import bits, random_rays, subsample_rays
 pytestmark = pytest.mark.gpu
 torch = pytest.importorskip("torch")
 
-LAYOUTS = [0, 1, 2]   # BVH2, CWBVH8, BVH4
+LAYOUTS = [0, 1, 2, 3]   # BVH2, CWBVH8, BVH4, QBVH4
 GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "ref_hits.npz")
 
 
@@ -251,7 +251,7 @@ def test_counters(host_scenes, pkg, layout):
     assert np.array_equal(hits, S.intersect(rays))
     assert c.rays == rays.shape[0] and c.hits == int((ids_of(hits) >= 0).sum())
     assert c.node_visits > 0 and c.triangle_tests > 0
-    assert c.bytes_fetched == c.node_visits * {0: 64, 1: 80, 2: 128}[layout] + c.triangle_tests * 64
+    assert c.bytes_fetched == c.node_visits * {0: 64, 1: 80, 2: 128, 3: 64}[layout] + c.triangle_tests * 64
 
 
 def test_full_size_properties_bunny20(host_scenes, pkg):

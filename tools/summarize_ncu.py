@@ -35,7 +35,7 @@ def num(x): return float(x["value"].replace(",", ""))
 def to_bytes(m):
     v = num(m); u = m["unit"].lower()
     return v * {"byte": 1, "kbyte": 1e3, "mbyte": 1e6, "gbyte": 1e9}[u]
-b = next(l for l in launches if "hybrid" in l["kernel"]) if any("hybrid" in l["kernel"] for l in launches) else launches[0]
+b = max(launches, key=lambda l: num(l["gpu__time_duration.sum"]))   # of a step's two trace launches the bounce-ray one is the longer
 summary = {"source": f"profiles/{tag}_ncu_full.json (ncu --set full --clock-control none, bench.py --steps 2 --warmup 3 --no-cpu; the bounce-ray launch of a timed step)",
            "kernel": b["kernel"].split("(")[0],
            "bounce_trace_dram_bytes_per_launch": int(to_bytes(b["dram__bytes_read.sum"]) + to_bytes(b["dram__bytes_write.sum"])),
