@@ -144,16 +144,22 @@ __global__ void __launch_bounds__(128, MINB) k_trace_hybrid(DeviceScene s, const
     w.node = w.tos = MIRO_BVH2_DONE; w.sp = 0;
     w.idx = w.idy = w.idz = w.oodx = w.oody = w.oodz = 0.f;
     best.t = 0.f; best.prim = MIROGPU_MISS; best.beta = best.gamma = 0.f;
-    auto claim = [&]() -> uint32_t {
+    // Pools shrink near the end of the batch (guided self-scheduling): once fewer than two full pools per warp of the grid
+    // remain, warps claim 16 rays at a time, so the last warps to finish are at most a quarter-pool apart.
+    const uint32_t tail = 2u * pool * (gridDim.x * (blockDim.x >> 5));
+    uint32_t nxt_len = 0;
+    auto claim = [&](uint32_t seen) -> uint32_t {
+        const uint32_t grain = (n32 - min(seen, n32) < tail) ? min(pool, 16u) : pool;
         unsigned long long base64 = 0;
-        if (lane == 0) base64 = atomicAdd(ticket, (unsigned long long)pool);
+        if (lane == 0) base64 = atomicAdd(ticket, (unsigned long long)grain);
         const uint32_t base = (uint32_t)min(base64, (unsigned long long)n32);
         const uint32_t b = __shfl_sync(0xffffffffu, base, 0);
+        nxt_len = min(grain, n32 - b);
         // one 128-byte line holds four rays
-        if (PF & 8) for (uint32_t k = 4 * lane; k < pool && k < n32 - b; k += 128) prefetch_l2(rays + b + k);
+        if (PF & 8) for (uint32_t k = 4 * lane; k < nxt_len; k += 128) prefetch_l2(rays + b + k);
         return b;
     };
-    nxt = claim();
+    nxt = claim(0u);
     for (;;) {
         // ---- hand new rays to idle lanes (two passes, so a lane that drew a dead ray gets another) ----
         unsigned idle = __ballot_sync(0xffffffffu, w.node == MIRO_BVH2_DONE);
@@ -161,8 +167,8 @@ __global__ void __launch_bounds__(128, MINB) k_trace_hybrid(DeviceScene s, const
             for (int pass = 0; pass < 2 && idle; ++pass) {
                 if (cur >= cur_end) {
                     if (nxt >= n32) break;   // drained
-                    cur = nxt; cur_end = nxt + min(pool, n32 - nxt);
-                    nxt = claim();
+                    cur = nxt; cur_end = nxt + nxt_len;
+                    nxt = claim(cur);
                 }
                 if (w.node == MIRO_BVH2_DONE) {
                     const uint32_t i = cur + __popc(idle & lt_mask);

@@ -366,11 +366,13 @@ template <int PF>
 MIRO_HD void wide4_descend(const float d[4], const int32_t lk[4], const float4* __restrict__ tris, Bvh2Walk& w, int32_t* __restrict__ stack)
 {
     const float kFar = u2f(0x7f800000u);
-    float da = d[0], db = d[1], dc = d[2], de = d[3];
-    int32_t la = lk[0], lb = lk[1], lc = lk[2], le = lk[3];
-    if (db < da) { const float t = da; da = db; db = t; const int32_t u = la; la = lb; lb = u; }
-    if (de < dc) { const float t = dc; dc = de; de = t; const int32_t u = lc; lc = le; le = u; }
-    if (dc < da) { const float t = da; da = dc; dc = t; const int32_t u = la; la = lc; lc = u; }
+    // comparators written as min / max on the distances and selects on the links (no register shuffling)
+    const bool p01 = d[1] < d[0], p23 = d[3] < d[2];
+    const float w01 = fminf(d[0], d[1]), db = fmaxf(d[0], d[1]), w23 = fminf(d[2], d[3]), de = fmaxf(d[2], d[3]);
+    const int32_t m01 = p01 ? lk[1] : lk[0], lb = p01 ? lk[0] : lk[1], m23 = p23 ? lk[3] : lk[2], le = p23 ? lk[2] : lk[3];
+    const bool pf = w23 < w01;
+    const float da = fminf(w01, w23), dc = fmaxf(w01, w23);
+    const int32_t la = pf ? m23 : m01, lc = pf ? m01 : m23;
     if (!(da < kFar)) { bvh2_pop(w, stack); return; }
     if (db < kFar) { stack[w.sp++] = w.tos; w.tos = lb; }
     if (de < kFar) { stack[w.sp++] = w.tos; w.tos = le; }
@@ -382,16 +384,17 @@ MIRO_HD void wide4_descend(const float d[4], const int32_t lk[4], const float4* 
     w.node = la;
 }
 
-// f[i] = 1024 + byte i of w, exactly.  Device: two PRMTs build the four binary16 values 0x64bb (= 1024 + bb, bb fits the
-// 10-bit mantissa) and the half -> float conversions run on the FMA pipe, which the traversal leaves mostly idle.
+// f[i] = 2^-24 * byte i of w, exactly.  Device: two PRMTs build the four binary16 values 0x00bb -- subnormal halves,
+// worth bb * 2^-24 -- and the (exact) half -> float conversions run on the FMA pipe, which the traversal leaves mostly
+// idle.  The 2^24 is folded into the per-axis cell constant (a power of two, so exactly).
 MIRO_HD void unpack_planes(uint32_t w, float f[4])
 {
 #ifdef __CUDA_ARCH__
-    const uint32_t p01 = __byte_perm(w, 0x64646464u, 0x4140), p23 = __byte_perm(w, 0x64646464u, 0x4342);
+    const uint32_t p01 = __byte_perm(w, 0u, 0x4140), p23 = __byte_perm(w, 0u, 0x4342);
     const __half2 h01 = *reinterpret_cast<const __half2*>(&p01), h23 = *reinterpret_cast<const __half2*>(&p23);
     f[0] = __low2float(h01); f[1] = __high2float(h01); f[2] = __low2float(h23); f[3] = __high2float(h23);
 #else
-    for (int i = 0; i < 4; ++i) f[i] = 1024.0f + (float)((w >> (8 * i)) & 0xffu);
+    for (int i = 0; i < 4; ++i) f[i] = (float)((w >> (8 * i)) & 0xffu) * (1.0f / 16777216.0f);
 #endif
 }
 
@@ -447,10 +450,10 @@ MIRO_HD void trace_bvh4(const float4* __restrict__ nodes, const float4* __restri
 // ---- QBVH4 (64-byte nodes, four child boxes quantised to 8 bits per plane on a per-node grid) ------------------------
 // Node = 4 x float4: (origin.xyz, ex|ey<<8|ez<<16) (qlo.x[4], qhi.x[4], qlo.y[4], qhi.y[4]) (qlo.z[4], qhi.z[4], link0, link1)
 // (link2, link3, -, -): two 256-bit loads.  A plane is origin + q * cell with cell = 2^(e-127); along the ray
-//   t = (origin + q cell - o) / d = (1024 + q) * (cell / d) + ((origin - o) / d - 1024 cell / d),
+//   t = (origin + q cell - o) / d = (q 2^-24) * (2^24 cell / d) + (origin - o) / d,
 // one FMA per plane once the two per-axis constants are formed.  The near / far plane words are picked by the sign of
 // the direction (two selects per axis), so no per-plane min / max is needed.  The builder rounds q outward with a
-// margin of 0.02 cell, far above the rounding of this decode (about 3 ulp of 4 node extents).
+// margin of 0.02 cell, far above the rounding of this decode (a few ulp of the plane distance).
 template <int PF>
 MIRO_HD void qbvh4_node_step(const float4* __restrict__ nodes, const float4* __restrict__ tris, const mirogpu_ray& r, Bvh2Walk& w,
                              int32_t* __restrict__ stack, const BestHit& best)
@@ -458,10 +461,10 @@ MIRO_HD void qbvh4_node_step(const float4* __restrict__ nodes, const float4* __r
     const float4* p = nodes + 4 * (size_t)w.node;
     const F8 A = ld256(p), B = ld256(p + 2);
     const uint32_t ew = f2u(A.lo.w);
-    const float cx = u2f((ew & 0xffu) << 23) * w.idx, cy = u2f(((ew >> 8) & 0xffu) << 23) * w.idy, cz = u2f(((ew >> 16) & 0xffu) << 23) * w.idz;
-    const float bx = fmaf(-1024.0f, cx, fmaf(A.lo.x, w.idx, -w.oodx));
-    const float by = fmaf(-1024.0f, cy, fmaf(A.lo.y, w.idy, -w.oody));
-    const float bz = fmaf(-1024.0f, cz, fmaf(A.lo.z, w.idz, -w.oodz));
+    // cell * 2^24 (the planes arrive as q * 2^-24): the exponent bytes are at most 227, so + 24 stays a finite exponent
+    const float cx = u2f(((ew & 0xffu) + 24u) << 23) * w.idx, cy = u2f((((ew >> 8) & 0xffu) + 24u) << 23) * w.idy,
+                cz = u2f((((ew >> 16) & 0xffu) + 24u) << 23) * w.idz;
+    const float bx = fmaf(A.lo.x, w.idx, -w.oodx), by = fmaf(A.lo.y, w.idy, -w.oody), bz = fmaf(A.lo.z, w.idz, -w.oodz);
     const bool px = w.idx >= 0.f, py = w.idy >= 0.f, pz = w.idz >= 0.f;
     const uint32_t qlx = f2u(A.hi.x), qhx = f2u(A.hi.y), qly = f2u(A.hi.z), qhy = f2u(A.hi.w), qlz = f2u(B.lo.x), qhz = f2u(B.lo.y);
     float nx[4], fx[4], ny[4], fy[4], nz[4], fz[4];
