@@ -73,27 +73,44 @@ __global__ void __launch_bounds__(256) k_render_primary(CameraBasis cb, int widt
 
 __device__ __forceinline__ float dot3(const float a[3], const float b[3]) { return a[0] * b[0] + a[1] * b[1] + a[2] * b[2]; }
 
-__device__ __forceinline__ void push_item(const WaveParams& p, Queue& next, uint32_t* next_count, uint32_t* dropped, const float o[3],
-                                          const float d[3], uint32_t pixel, float wr, float wg, float wb, float packed_depth_sample)
+// fixed_slot >= 0: the child takes that slot (one child per item, queue position = item position: no counter at all);
+// otherwise slots are allocated from *next_count.  Returns true when a child was written.
+__device__ __forceinline__ bool push_item(const WaveParams& p, Queue& next, uint32_t* next_count, uint32_t* dropped, const float o[3],
+                                          const float d[3], uint32_t pixel, float wr, float wg, float wb, float packed_depth_sample,
+                                          int64_t fixed_slot = -1)
 {
-    if (!(wr > 0.f || wg > 0.f || wb > 0.f)) return;
-    const uint32_t slot = atomicAdd(next_count, 1u);
-    if (slot >= p.cap) { atomicAdd(dropped, 1u); return; }
+    if (!(wr > 0.f || wg > 0.f || wb > 0.f)) return false;
+    if (fixed_slot >= 0) {
+        float4* r = reinterpret_cast<float4*>(next.rays + fixed_slot);
+        r[0] = make_float4(o[0], o[1], o[2], 0.0f);
+        r[1] = make_float4(d[0], d[1], d[2], MIROGPU_TMAX);
+        next.pix[fixed_slot] = pixel;
+        next.weight[fixed_slot] = make_float4(wr, wg, wb, packed_depth_sample);
+        return true;
+    }
+    // warp-aggregated append: the lanes that reach this point together take consecutive slots with ONE atomic, which
+    // also keeps the next wave's rays in the order of this wave's items (neighbouring pixels stay neighbours)
+    const unsigned peers = __activemask();
+    const unsigned lane = threadIdx.x & 31u;
+    const int leader = __ffs(peers) - 1;
+    uint32_t base = 0;
+    if ((int)lane == leader) base = atomicAdd(next_count, (uint32_t)__popc(peers));
+    base = __shfl_sync(peers, base, leader);
+    const uint32_t slot = base + (uint32_t)__popc(peers & ((1u << lane) - 1u));
+    if (slot >= p.cap) { atomicAdd(dropped, 1u); return false; }
     float4* r = reinterpret_cast<float4*>(next.rays + slot);
     r[0] = make_float4(o[0], o[1], o[2], 0.0f);
     r[1] = make_float4(d[0], d[1], d[2], MIROGPU_TMAX);
     next.pix[slot] = pixel;
     next.weight[slot] = make_float4(wr, wg, wb, packed_depth_sample);
+    return true;
 }
 
-// One wave of Scene::traceScene bodies.  shadow_* arrays have nlights slots per item.
-__global__ void __launch_bounds__(128) k_shade(WaveParams p, Queue cur, uint32_t n, const uint32_t* __restrict__ d_n, Queue next,
-                                               uint32_t* next_count, uint32_t* dropped, mirogpu_ray* shadow_rays, float4* shadow_cd,
-                                               float4* shadow_ch, float* accum, float* gather_pos, float* gather_nrm, float4* gather_w)
+// Returns true when the item wrote its (single) child in place -- diffuse-bounce mode only.
+__device__ __forceinline__ bool shade_item(const WaveParams& p, const Queue& cur, uint32_t i, Queue& next, uint32_t* next_count, uint32_t* dropped,
+                                           mirogpu_ray* shadow_rays, float4* shadow_cd, float4* shadow_ch, float* accum, float* gather_pos,
+                                           float* gather_nrm, float4* gather_w)
 {
-    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (d_n) n = min(n, *d_n);
-    if (i >= n) return;
     const float4 hv = __ldg(reinterpret_cast<const float4*>(cur.hits + i));
     const float4 w = cur.weight[i];
     const uint32_t lpix = cur.pix[i];
@@ -104,12 +121,12 @@ __global__ void __launch_bounds__(128) k_shade(WaveParams p, Queue cur, uint32_t
     if (p.shadows)
         for (uint32_t li = 0; li < p.nlights; ++li) shadow_rays[(size_t)i * p.nlights + li].tmax = -1.0f;   // inactive unless set below
     if (__float_as_uint(hv.y) == MIROGPU_MISS) {
-        if (ray.tmax < ray.tmin) return;   // dead item
+        if (ray.tmax < ray.tmin) return false;   // dead item
         // Scene.cpp:338-342: environment / background colour
         atomicAdd(accum + 3 * (size_t)pixel + 0, w.x * p.bg[0]);
         atomicAdd(accum + 3 * (size_t)pixel + 1, w.y * p.bg[1]);
         atomicAdd(accum + 3 * (size_t)pixel + 2, w.z * p.bg[2]);
-        return;
+        return false;
     }
     mirogpu_hit h; h.t = hv.x; h.prim_id = __float_as_uint(hv.y); h.beta = hv.z; h.gamma = hv.w;
     const SurfacePoint sp = resolve_hit(p.ds, h);
@@ -179,7 +196,7 @@ __global__ void __launch_bounds__(128) k_shade(WaveParams p, Queue cur, uint32_t
     // ---- secondary rays -------------------------------------------------------------------------------
     const int depth_now = unpack_depth(w.w);
     const int depth_next = depth_now - 1;          // --depth (Scene.cpp:282)
-    if (depth_next < 0) return;
+    if (depth_next < 0) return false;
     const float depth_left = pack_ds(depth_next, sb);
     if (p.mode == MIROGPU_RENDER_DIFFUSE_BOUNCE) {
         if (diffuse && depth_now == p.max_depth) {   // one cosine-weighted bounce from the first hit only
@@ -189,14 +206,14 @@ __global__ void __launch_bounds__(128) k_shade(WaveParams p, Queue cur, uint32_t
             float d[3];
             align_hemisphere(sp.N, xmul(xmul(2.0f, MIRO_PI), u2), asinf(sqrtf(u1)), d);
             const float o[3] = {sp.P[0] + d[0] * MIRO_EPS, sp.P[1] + d[1] * MIRO_EPS, sp.P[2] + d[2] * MIRO_EPS};
-            push_item(p, next, next_count, dropped, o, d, lpix, w.x * m.kd[0], w.y * m.kd[1], w.z * m.kd[2], pack_ds(0, sb));
+            return push_item(p, next, next_count, dropped, o, d, lpix, w.x * m.kd[0], w.y * m.kd[1], w.z * m.kd[2], pack_ds(0, sb), (int64_t)i);
         }
-        return;
+        return false;
     }
-    if (p.mode != MIROGPU_RENDER_WHITTED) return;
+    if (p.mode != MIROGPU_RENDER_WHITTED) return false;
     const bool reflective = m.ks[0] > 0.f || m.ks[1] > 0.f || m.ks[2] > 0.f;
     const bool refractive = m.kt[0] > 0.f || m.kt[1] > 0.f || m.kt[2] > 0.f;
-    if (!reflective && !refractive) return;
+    if (!reflective && !refractive) return false;
     // Ray::reflect (Ray.h:160-163)
     const float dn = dot3(sp.N, rd);
     float dr[3] = {rd[0] - 2.f * dn * sp.N[0], rd[1] - 2.f * dn * sp.N[1], rd[2] - 2.f * dn * sp.N[2]};
@@ -236,6 +253,28 @@ __global__ void __launch_bounds__(128) k_shade(WaveParams p, Queue cur, uint32_t
             const float ot[3] = {sp.P[0] + dt[0] * MIRO_EPS, sp.P[1] + dt[1] * MIRO_EPS, sp.P[2] + dt[2] * MIRO_EPS};
             push_item(p, next, next_count, dropped, ot, dt, lpix, w.x * m.kt[0] * tw, w.y * m.kt[1] * tw, w.z * m.kt[2] * tw, depth_left);
         }
+    }
+    return false;
+}
+
+// One wave of Scene::traceScene bodies.  shadow_* arrays have nlights slots per item.
+// Diffuse-bounce mode: an item has at most one child, so the child takes the item's own queue position and no slot
+// counter is touched (a single-address atomic per warp serialises at the L2 atomic unit: 520 k of them made this kernel
+// as slow as the trace it feeds); items without a child leave a dead ray (tmax < tmin) there instead.
+__global__ void __launch_bounds__(128) k_shade(WaveParams p, Queue cur, uint32_t n, const uint32_t* __restrict__ d_n, Queue next,
+                                               uint32_t* next_count, uint32_t* dropped, mirogpu_ray* shadow_rays, float4* shadow_cd,
+                                               float4* shadow_ch, float* accum, float* gather_pos, float* gather_nrm, float4* gather_w)
+{
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (d_n) n = min(n, *d_n);
+    const bool in_place = p.mode == MIROGPU_RENDER_DIFFUSE_BOUNCE && d_n == nullptr;   // wave 0: the only one with children
+    if (in_place && i == 0) *next_count = n;
+    if (i >= n) return;
+    const bool wrote = shade_item(p, cur, i, next, next_count, dropped, shadow_rays, shadow_cd, shadow_ch, accum, gather_pos, gather_nrm, gather_w);
+    if (in_place && !wrote) {
+        float4* r = reinterpret_cast<float4*>(next.rays + i);
+        r[0] = make_float4(0.f, 0.f, 0.f, 0.0f);
+        r[1] = make_float4(0.f, 0.f, 1.f, -1.0f);
     }
 }
 
