@@ -56,6 +56,7 @@ struct mirogpu_scene {
     int sm_count = 148;
     // hybrid kernel (variant 2) knobs; env MIROGPU_NMIN / _PERIOD / _MINIDLE / _POOL / _PF / _MINB / _NREP override (tuning)
     int hyb_nmin = 16, hyb_period = 4, hyb_min_idle = 8, hyb_pool = 64, hyb_nrep = 2;
+    int packets_per_ticket = 1;                            // packet kernel: 32-ray packets per ticket; env MIROGPU_PPT
     int hyb_pf = 0, hyb_minb = 9;                          // prefetch flags (traverse.cuh), min resident CTAs
     DeviceScene ds{};
     void* d_nodes = nullptr;
@@ -142,7 +143,7 @@ cudaError_t launch_trace(mirogpu_scene* h, const mirogpu_ray* d_rays, size_t n, 
     size_t grid = (size_t)h->sm_count * occ;
     const size_t need = (n + 127) / 128;
     if (grid > need) grid = need;
-    k_trace_persistent<LAYOUT, ANY><<<(unsigned)grid, 128, 0, st>>>(h->ds, d_rays, n, d_hits, ticket, d_n, mult);
+    k_trace_persistent<LAYOUT, ANY><<<(unsigned)grid, 128, 0, st>>>(h->ds, d_rays, n, d_hits, ticket, d_n, mult, (uint32_t)h->packets_per_ticket);
     return cudaGetLastError();
 }
 
@@ -246,6 +247,7 @@ int mirogpu_scene_create(const float* tri_vertices, const float* tri_normals, co
     if (o.layout == MIROGPU_LAYOUT_QBVH4 || o.layout == MIROGPU_LAYOUT_BVH4) { h->hyb_period = 2; h->hyb_min_idle = 6; }   // measured optimum of the four-wide steps
     if (const char* e = getenv("MIROGPU_POOL")) { const int v = atoi(e); if (v >= 32 && v <= 65536) h->hyb_pool = v; }
     if (const char* e = getenv("MIROGPU_NREP")) h->hyb_nrep = atoi(e);
+    if (const char* e = getenv("MIROGPU_PPT")) { const int v = atoi(e); if (v >= 1 && v <= 64) h->packets_per_ticket = v; }
     if (const char* e = getenv("MIROGPU_NMIN")) { const int v = atoi(e); if (v >= 1 && v <= 32) h->hyb_nmin = v; }
     if (const char* e = getenv("MIROGPU_PERIOD")) { const int v = atoi(e); if (v >= 1 && v <= 100000) h->hyb_period = v; }
     if (const char* e = getenv("MIROGPU_PF")) h->hyb_pf = atoi(e);
