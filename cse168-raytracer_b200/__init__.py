@@ -24,6 +24,7 @@ LIB_PATH = os.path.join(_PKG, "libmirogpu.so")
 MISS = 0xFFFFFFFF
 TMAX = np.float32(1e12)
 LAYOUT_BVH2, LAYOUT_CWBVH8, LAYOUT_BVH4, LAYOUT_QBVH4 = 0, 1, 2, 3
+BUILDER_SAH_HOST, BUILDER_LBVH_DEVICE = 0, 1
 CLOSEST_HIT, ANY_HIT = 0, 1
 HINT_COHERENT = 0x100   # or-ed into a query mode: camera-like batch -> packet kernel
 RENDER_WHITTED, RENDER_DIFFUSE_BOUNCE, RENDER_PRIMARY_ONLY = 0, 1, 2
@@ -39,13 +40,14 @@ class MiroGpuError(RuntimeError):
 
 
 class BuildOptions(ctypes.Structure):
-    _fields_ = [("layout", ctypes.c_int32), ("max_leaf", ctypes.c_int32), ("sah_bins", ctypes.c_int32), ("device", ctypes.c_int32)]
+    _fields_ = [("layout", ctypes.c_int32), ("max_leaf", ctypes.c_int32), ("sah_bins", ctypes.c_int32), ("device", ctypes.c_int32),
+                ("builder", ctypes.c_int32)]
 
 
 class SceneInfo(ctypes.Structure):
     _fields_ = [("num_triangles", ctypes.c_uint32), ("num_nodes", ctypes.c_uint32), ("num_binary_nodes", ctypes.c_uint32),
                 ("num_binary_leaves", ctypes.c_uint32), ("max_depth", ctypes.c_uint32), ("layout", ctypes.c_int32),
-                ("node_bytes", ctypes.c_uint64), ("triangle_bytes", ctypes.c_uint64), ("shading_bytes", ctypes.c_uint64),
+                ("builder", ctypes.c_int32), ("_pad", ctypes.c_int32), ("node_bytes", ctypes.c_uint64), ("triangle_bytes", ctypes.c_uint64), ("shading_bytes", ctypes.c_uint64),
                 ("build_seconds", ctypes.c_double), ("flatten_seconds", ctypes.c_double), ("upload_seconds", ctypes.c_double),
                 ("bounds_min", ctypes.c_float * 3), ("bounds_max", ctypes.c_float * 3)]
 
@@ -155,7 +157,7 @@ class MiroScene:
     """One scene resident in HBM on the current CUDA device (replicated per rank in multi-GPU runs)."""
 
     def __init__(self, tri_vertices, tri_normals=None, material_ids=None, materials=None, layout=LAYOUT_QBVH4,
-                 max_leaf=0, sah_bins=32, device=-1):
+                 max_leaf=0, sah_bins=32, device=-1, builder=BUILDER_SAH_HOST):
         v = np.ascontiguousarray(tri_vertices, np.float32).reshape(-1, 9)
         n = None if tri_normals is None else np.ascontiguousarray(tri_normals, np.float32).reshape(-1, 9)
         m = None if material_ids is None else np.ascontiguousarray(material_ids, np.uint32).reshape(-1)
@@ -167,7 +169,7 @@ class MiroScene:
         if materials:
             mats = (Material * len(materials))(*materials)
             nmats = len(materials)
-        opt = BuildOptions(int(layout), int(max_leaf), int(sah_bins), int(device))
+        opt = BuildOptions(int(layout), int(max_leaf), int(sah_bins), int(device), int(builder))
         self._h = ctypes.c_void_p()
         _check(lib.mirogpu_scene_create(_ptr(v), _ptr(n), _ptr(m), ctypes.c_uint32(v.shape[0]), mats, ctypes.c_uint32(nmats),
                                         ctypes.byref(opt), ctypes.byref(self._h)))
@@ -360,13 +362,15 @@ class HostScene:
     """Drives the C++ host layer the way a user of the reference drives Scene / Camera (one global scene,
     like the reference's g_scene).  Same method names as the checker drivers in tests/miro_driver.py."""
 
-    def __init__(self, layout=LAYOUT_QBVH4):
+    def __init__(self, layout=LAYOUT_QBVH4, builder=BUILDER_SAH_HOST):
         self.h = host_lib()
         self.layout = layout
+        self.builder = builder
 
     def new_scene(self):
         self.h.mh_new_scene()
         self.h.mh_set_layout(int(self.layout))
+        self.h.mh_set_builder(int(self.builder))
 
     def new_material(self, kd=(1, 1, 1), ks=(0, 0, 0), kt=(0, 0, 0), shininess=1.0, refr=1.0):
         return self.h.mh_new_material(_f3(kd), _f3(ks), _f3(kt), ctypes.c_float(shininess), ctypes.c_float(refr))

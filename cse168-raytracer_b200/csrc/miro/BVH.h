@@ -13,7 +13,7 @@
 
 class BVH {
 public:
-    BVH() : m_handle(0), m_objects(0), m_layout(MIROGPU_LAYOUT_QBVH4) {}
+    BVH() : m_handle(0), m_objects(0), m_layout(MIROGPU_LAYOUT_QBVH4), m_builder(MIROGPU_BUILDER_SAH_HOST) {}
     ~BVH();
     void build(Objects* objs, int depth = 0);
     bool intersect(HitInfo& result, const Ray& ray, float tMin = 0.0f, float tMax = MIRO_TMAX) const;
@@ -21,6 +21,7 @@ public:
     // results[i] is filled like intersect() would; returns the number of hits.
     size_t intersectBatch(const Ray* rays, size_t n, HitInfo* results, bool* hitFlags, float tMin = 0.0f, float tMax = MIRO_TMAX) const;
     void setLayout(int layout) { m_layout = layout; }
+    void setBuilder(int builder) { m_builder = builder; }   // MIROGPU_BUILDER_*: host SAH (default) or device LBVH
     mirogpu_handle handle() const { return m_handle; }
     const std::vector<Object*>& fallbackObjects() const { return m_other; }
 protected:
@@ -29,6 +30,6 @@ protected:
     Objects* m_objects;               // borrowed, as in the reference (BVH.cpp:84)
     std::vector<Triangle*> m_tris;    // device prim id -> Triangle
     std::vector<Object*> m_other;     // bounded non-triangle objects: tested on the host after the device query
-    int m_layout;
+    int m_layout, m_builder;
 };
 #endif

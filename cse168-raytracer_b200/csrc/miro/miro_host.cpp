@@ -243,7 +243,7 @@ void BVH::build(Objects* objs, int)
         matIds.push_back(it->second);
         m_tris.push_back(t);
     }
-    mirogpu_build_options opt; opt.layout = m_layout; opt.max_leaf = 0; opt.sah_bins = 32; opt.device = -1;
+    mirogpu_build_options opt; opt.layout = m_layout; opt.max_leaf = 0; opt.sah_bins = 32; opt.device = -1; opt.builder = m_builder;
     const int rc = mirogpu_scene_create(verts.data(), norms.data(), matIds.data(), (uint32_t)m_tris.size(),
                                         mats.empty() ? 0 : mats.data(), (uint32_t)mats.size(), &opt, &m_handle);
     if (rc != MIROGPU_OK) fatal("BVH::build");

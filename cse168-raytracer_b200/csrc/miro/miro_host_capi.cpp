@@ -19,6 +19,7 @@ namespace {
 std::vector<Material*> g_materials;
 std::map<const Object*, int> g_prim_id;
 int g_layout = MIROGPU_LAYOUT_QBVH4;
+int g_builder = MIROGPU_BUILDER_SAH_HOST;
 }
 
 extern "C" {
@@ -32,6 +33,7 @@ void mh_new_scene()
 }
 
 void mh_set_layout(int layout) { g_layout = layout; }
+void mh_set_builder(int builder) { g_builder = builder; }
 
 int mh_new_material(const float* kd, const float* ks, const float* kt, float shininess, float refr_index)
 {
@@ -99,7 +101,7 @@ void mh_precalc_host_only()
 
 double mh_precalc()
 {
-    g_scene->bvh().setLayout(g_layout);
+    g_scene->bvh().setLayout(g_layout); g_scene->bvh().setBuilder(g_builder);
     g_scene->preCalc();
     g_prim_id.clear();
     const Objects* objs = g_scene->objects();

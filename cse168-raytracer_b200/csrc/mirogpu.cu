@@ -57,6 +57,7 @@ struct mirogpu_scene {
     // hybrid kernel (variant 2) knobs; env MIROGPU_NMIN / _PERIOD / _MINIDLE / _POOL / _PF / _MINB / _NREP override (tuning)
     int hyb_nmin = 16, hyb_period = 4, hyb_min_idle = 8, hyb_pool = 64, hyb_nrep = 2;
     int packets_per_ticket = 1;                            // packet kernel: 32-ray packets per ticket; env MIROGPU_PPT
+    size_t node_bytes_dev = 0, tri_bytes_dev = 0;
     int hyb_pf = 0, hyb_minb = 9;                          // prefetch flags (traverse.cuh), min resident CTAs
     DeviceScene ds{};
     void* d_nodes = nullptr;
@@ -192,6 +193,7 @@ void camera_basis(const mirogpu_camera& c, int W, int H, CameraBasis& b)
 #include "photon_impl.cuh"
 #include "render_impl.cuh"
 #include "photon_trace_impl.cuh"
+#include "lbvh_impl.cuh"
 
 extern "C" {
 
@@ -218,8 +220,11 @@ int mirogpu_scene_create(const float* tri_vertices, const float* tri_normals, co
     if (ntris && !tri_vertices) return fail(MIROGPU_ERR_INVALID_ARG, "tri_vertices is NULL");
     if (ntris >= (1u << 28) - 16u) return fail(MIROGPU_ERR_INVALID_ARG, "too many triangles (limit 2^28 - 16)");
     mirogpu_build_options o;
-    o.layout = MIROGPU_LAYOUT_QBVH4; o.max_leaf = 0; o.sah_bins = 32; o.device = -1;
+    o.layout = MIROGPU_LAYOUT_QBVH4; o.max_leaf = 0; o.sah_bins = 32; o.device = -1; o.builder = MIROGPU_BUILDER_SAH_HOST;
     if (opt) o = *opt;
+    if (const char* e = getenv("MIROGPU_BUILDER")) { if (!strcmp(e, "lbvh")) o.builder = MIROGPU_BUILDER_LBVH_DEVICE; }   // tuning knob
+    if (o.builder != MIROGPU_BUILDER_SAH_HOST && o.builder != MIROGPU_BUILDER_LBVH_DEVICE) return fail(MIROGPU_ERR_INVALID_ARG, "unknown builder");
+    if (o.builder == MIROGPU_BUILDER_LBVH_DEVICE && o.layout != MIROGPU_LAYOUT_QBVH4) return fail(MIROGPU_ERR_INVALID_ARG, "the device builder emits the QBVH4 layout only");
     if (o.layout != MIROGPU_LAYOUT_BVH2 && o.layout != MIROGPU_LAYOUT_CWBVH8 && o.layout != MIROGPU_LAYOUT_BVH4 && o.layout != MIROGPU_LAYOUT_QBVH4)
         return fail(MIROGPU_ERR_INVALID_ARG, "unknown layout");
     if (o.max_leaf <= 0) if (const char* e = getenv("MIROGPU_MAX_LEAF")) o.max_leaf = atoi(e);   // tuning knob
@@ -254,30 +259,45 @@ int mirogpu_scene_create(const float* tri_vertices, const float* tri_normals, co
     if (const char* e = getenv("MIROGPU_MINB")) h->hyb_minb = atoi(e);
     if (const char* e = getenv("MIROGPU_MINIDLE")) { const int v = atoi(e); if (v >= 1 && v <= 32) h->hyb_min_idle = v; }
 
-    // ---- host build ------------------------------------------------------------------------------
+    // ---- device build (LBVH) -----------------------------------------------------------------------
     double t0 = now_s();
-    BinaryBvh bin = build_binary_sah(tri_vertices, ntris, o.max_leaf, o.sah_bins);
-    double t1 = now_s();
+    LbvhOut lb;
+    bool device_built = false;
+    if (o.builder == MIROGPU_BUILDER_LBVH_DEVICE) {
+        const cudaError_t be = build_lbvh_device(tri_vertices, ntris, std::min(o.max_leaf, 4), lb);
+        if (be != cudaSuccess) { delete h; return fail(be == cudaErrorMemoryAllocation ? MIROGPU_ERR_OOM : MIROGPU_ERR_CUDA, std::string("device BVH build: ") + cudaGetErrorString(be)); }
+        if (lb.max_stack <= MIRO_STACK4) device_built = true;
+        else { cudaFree(lb.d_geom); lb.d_geom = nullptr; }   // a Morton tree too deep for the kernels' stacks: use the host builder
+    }
+    // ---- host build ------------------------------------------------------------------------------
+    BinaryBvh bin;
     FlatBvh flat;
-    if (o.layout == MIROGPU_LAYOUT_BVH2) flatten_bvh2(bin, flat);
-    else if (o.layout == MIROGPU_LAYOUT_BVH4) flatten_bvh4(bin, flat);
-    else if (o.layout == MIROGPU_LAYOUT_QBVH4) flatten_qbvh4(bin, flat);
-    else flatten_cwbvh8(bin, flat);
-    // a walk pushes at most one entry per level (BVH2 / CWBVH8 groups) resp. flat.max_stack entries (BVH4): refuse a tree the
-    // kernels' fixed per-thread stacks cannot hold rather than overrun them (the builder's depth cap makes this unreachable
-    // below ~16 M triangles)
+    double t1 = now_s(), t2 = t1;
     const bool wide4 = o.layout == MIROGPU_LAYOUT_BVH4 || o.layout == MIROGPU_LAYOUT_QBVH4;
-    if (!wide4 && bin.max_depth > MIRO_STACK) { delete h; return fail(MIROGPU_ERR_INVALID_ARG, "tree deeper than the kernels' traversal stack"); }
-    if (wide4 && flat.max_stack > MIRO_STACK4) { delete h; return fail(MIROGPU_ERR_INVALID_ARG, "BVH4 tree needs a deeper traversal stack than the kernels carry"); }
-    make_tri_records(tri_vertices, flat.order, h->h_tris);
-    double t2 = now_s();
-
-    const void* node_src; size_t node_bytes;
-    if (o.layout == MIROGPU_LAYOUT_BVH2) { node_src = flat.nodes2.data(); node_bytes = flat.nodes2.size() * sizeof(Bvh2Node); }
-    else if (o.layout == MIROGPU_LAYOUT_BVH4) { node_src = flat.nodes4.data(); node_bytes = flat.nodes4.size() * sizeof(Bvh4Node); }
-    else if (o.layout == MIROGPU_LAYOUT_QBVH4) { node_src = flat.nodesq.data(); node_bytes = flat.nodesq.size() * sizeof(Qbvh4Node); }
-    else { node_src = flat.nodes8.data(); node_bytes = flat.nodes8.size() * sizeof(Cwbvh8Node); }
-    h->h_nodes.assign((const uint8_t*)node_src, (const uint8_t*)node_src + node_bytes);
+    const void* node_src = nullptr; size_t node_bytes = 0;
+    if (!device_built) {
+        t0 = now_s();
+        bin = build_binary_sah(tri_vertices, ntris, o.max_leaf, o.sah_bins);
+        t1 = now_s();
+        if (o.layout == MIROGPU_LAYOUT_BVH2) flatten_bvh2(bin, flat);
+        else if (o.layout == MIROGPU_LAYOUT_BVH4) flatten_bvh4(bin, flat);
+        else if (o.layout == MIROGPU_LAYOUT_QBVH4) flatten_qbvh4(bin, flat);
+        else flatten_cwbvh8(bin, flat);
+        // a walk pushes at most one entry per level (BVH2 / CWBVH8 groups) resp. flat.max_stack entries (BVH4): refuse a tree the
+        // kernels' fixed per-thread stacks cannot hold rather than overrun them (the builder's depth cap makes this unreachable
+        // below ~16 M triangles)
+        if (!wide4 && bin.max_depth > MIRO_STACK) { delete h; return fail(MIROGPU_ERR_INVALID_ARG, "tree deeper than the kernels' traversal stack"); }
+        if (wide4 && flat.max_stack > MIRO_STACK4) { delete h; return fail(MIROGPU_ERR_INVALID_ARG, "BVH4 tree needs a deeper traversal stack than the kernels carry"); }
+        make_tri_records(tri_vertices, flat.order, h->h_tris);
+        t2 = now_s();
+        if (o.layout == MIROGPU_LAYOUT_BVH2) { node_src = flat.nodes2.data(); node_bytes = flat.nodes2.size() * sizeof(Bvh2Node); }
+        else if (o.layout == MIROGPU_LAYOUT_BVH4) { node_src = flat.nodes4.data(); node_bytes = flat.nodes4.size() * sizeof(Bvh4Node); }
+        else if (o.layout == MIROGPU_LAYOUT_QBVH4) { node_src = flat.nodesq.data(); node_bytes = flat.nodesq.size() * sizeof(Qbvh4Node); }
+        else { node_src = flat.nodes8.data(); node_bytes = flat.nodes8.size() * sizeof(Cwbvh8Node); }
+        h->h_nodes.assign((const uint8_t*)node_src, (const uint8_t*)node_src + node_bytes);
+    } else {
+        node_bytes = lb.node_bytes;   // the host copies for mirogpu_debug_copy_* are fetched from the device on demand
+    }
 
     // shading records in prim-id order: (A, material) e1 e2 nA nB nC
     std::vector<float4> shade((size_t)ntris * 6);
@@ -304,7 +324,7 @@ int mirogpu_scene_create(const float* tri_vertices, const float* tri_normals, co
     }
 
     // ---- upload ------------------------------------------------------------------------------------
-    const size_t tri_bytes = h->h_tris.size() * sizeof(TriRecord), shade_bytes = shade.size() * sizeof(float4);
+    const size_t tri_bytes = device_built ? lb.tri_bytes : h->h_tris.size() * sizeof(TriRecord), shade_bytes = shade.size() * sizeof(float4);
     auto bail = [&](cudaError_t e, const char* what) {
         std::string msg = std::string(what) + ": " + cudaGetErrorString(e);
         mirogpu_scene_destroy(h);
@@ -312,14 +332,16 @@ int mirogpu_scene_create(const float* tri_vertices, const float* tri_normals, co
     };
     cudaError_t e;
     // nodes and triangles share one allocation (the traversal working set is one address range)
-    const size_t node_span = (std::max<size_t>(node_bytes, 16) + 255) & ~(size_t)255;
-    if ((e = cudaMalloc(&h->d_nodes, node_span + std::max<size_t>(tri_bytes, 16))) != cudaSuccess) return bail(e, "cudaMalloc nodes + triangles");
+    const size_t node_span = device_built ? lb.node_span : (std::max<size_t>(node_bytes, 16) + 255) & ~(size_t)255;
+    if (device_built) h->d_nodes = lb.d_geom;
+    else if ((e = cudaMalloc(&h->d_nodes, node_span + std::max<size_t>(tri_bytes, 16))) != cudaSuccess) return bail(e, "cudaMalloc nodes + triangles");
     h->d_tris = static_cast<char*>(h->d_nodes) + node_span;
+    h->node_bytes_dev = node_bytes; h->tri_bytes_dev = tri_bytes;
     if ((e = cudaMalloc(&h->d_shade, std::max<size_t>(shade_bytes, 16))) != cudaSuccess) return bail(e, "cudaMalloc shading records");
     if ((e = cudaMalloc(&h->d_materials, mats.size() * sizeof(mirogpu_material))) != cudaSuccess) return bail(e, "cudaMalloc materials");
     if ((e = cudaMalloc(&h->d_ticket, 64 * sizeof(unsigned long long))) != cudaSuccess) return bail(e, "cudaMalloc tickets");
-    if (node_bytes && (e = cudaMemcpy(h->d_nodes, node_src, node_bytes, cudaMemcpyHostToDevice)) != cudaSuccess) return bail(e, "upload nodes");
-    if (tri_bytes && (e = cudaMemcpy(h->d_tris, h->h_tris.data(), tri_bytes, cudaMemcpyHostToDevice)) != cudaSuccess) return bail(e, "upload triangles");
+    if (!device_built && node_bytes && (e = cudaMemcpy(h->d_nodes, node_src, node_bytes, cudaMemcpyHostToDevice)) != cudaSuccess) return bail(e, "upload nodes");
+    if (!device_built && tri_bytes && (e = cudaMemcpy(h->d_tris, h->h_tris.data(), tri_bytes, cudaMemcpyHostToDevice)) != cudaSuccess) return bail(e, "upload triangles");
     if (shade_bytes && (e = cudaMemcpy(h->d_shade, shade.data(), shade_bytes, cudaMemcpyHostToDevice)) != cudaSuccess) return bail(e, "upload shading records");
     if ((e = cudaMemcpy(h->d_materials, mats.data(), mats.size() * sizeof(mirogpu_material), cudaMemcpyHostToDevice)) != cudaSuccess) return bail(e, "upload materials");
     if ((e = cudaMemset(h->d_ticket, 0, 64 * sizeof(unsigned long long))) != cudaSuccess) return bail(e, "memset tickets");
@@ -339,14 +361,15 @@ int mirogpu_scene_create(const float* tri_vertices, const float* tri_normals, co
 
     mirogpu_scene_info& in = h->info;
     in.num_triangles = ntris;
-    in.num_nodes = (uint32_t)(o.layout == MIROGPU_LAYOUT_BVH2 ? flat.nodes2.size() : wide4 ? flat.nodes4.size() : flat.nodes8.size());
-    in.num_binary_nodes = (uint32_t)bin.nodes.size();
-    in.num_binary_leaves = bin.num_leaves;
-    in.max_depth = o.layout == MIROGPU_LAYOUT_BVH2 ? bin.max_depth : flat.max_depth;
+    in.num_nodes = device_built ? lb.num_nodes : (uint32_t)(o.layout == MIROGPU_LAYOUT_BVH2 ? flat.nodes2.size() : wide4 ? flat.nodes4.size() : flat.nodes8.size());
+    in.num_binary_nodes = device_built ? (ntris ? 2 * ntris - 1 : 0) : (uint32_t)bin.nodes.size();
+    in.num_binary_leaves = device_built ? ntris : bin.num_leaves;
+    in.max_depth = device_built ? lb.max_depth : (o.layout == MIROGPU_LAYOUT_BVH2 ? bin.max_depth : flat.max_depth);
+    in.builder = device_built ? MIROGPU_BUILDER_LBVH_DEVICE : MIROGPU_BUILDER_SAH_HOST;
     in.layout = o.layout;
     in.node_bytes = node_bytes; in.triangle_bytes = tri_bytes; in.shading_bytes = shade_bytes;
-    in.build_seconds = t1 - t0; in.flatten_seconds = t2 - t1; in.upload_seconds = t3 - t2;
-    for (int k = 0; k < 3; ++k) { in.bounds_min[k] = flat.root.lo[k]; in.bounds_max[k] = flat.root.hi[k]; }
+    in.build_seconds = device_built ? lb.seconds : t1 - t0; in.flatten_seconds = device_built ? 0.0 : t2 - t1; in.upload_seconds = t3 - t2;
+    for (int k = 0; k < 3; ++k) { in.bounds_min[k] = device_built ? lb.lo[k] : flat.root.lo[k]; in.bounds_max[k] = device_built ? lb.hi[k] : flat.root.hi[k]; }
     *out = h;
     return MIROGPU_OK;
 }
@@ -390,8 +413,11 @@ int mirogpu_scene_set_lights(mirogpu_handle h, const mirogpu_light* lights, uint
 int mirogpu_debug_copy_nodes(mirogpu_handle h, void* out, uint64_t* bytes)
 {
     if (!h || !bytes) return fail(MIROGPU_ERR_INVALID_ARG, "NULL argument");
-    const uint64_t need = h->h_nodes.size();
-    if (out && *bytes >= need) memcpy(out, h->h_nodes.data(), need);
+    const uint64_t need = h->node_bytes_dev;
+    if (out && *bytes >= need) {
+        if (h->h_nodes.size() == need) memcpy(out, h->h_nodes.data(), need);
+        else { CUDA_TRY(cudaSetDevice(h->device)); CUDA_TRY(cudaMemcpy(out, h->d_nodes, need, cudaMemcpyDeviceToHost)); }   // built on the device
+    }
     *bytes = need;
     return MIROGPU_OK;
 }
@@ -399,8 +425,11 @@ int mirogpu_debug_copy_nodes(mirogpu_handle h, void* out, uint64_t* bytes)
 int mirogpu_debug_copy_triangles(mirogpu_handle h, void* out, uint64_t* bytes)
 {
     if (!h || !bytes) return fail(MIROGPU_ERR_INVALID_ARG, "NULL argument");
-    const uint64_t need = h->h_tris.size() * sizeof(TriRecord);
-    if (out && *bytes >= need) memcpy(out, h->h_tris.data(), need);
+    const uint64_t need = h->tri_bytes_dev;
+    if (out && *bytes >= need) {
+        if (h->h_tris.size() * sizeof(TriRecord) == need) memcpy(out, h->h_tris.data(), need);
+        else { CUDA_TRY(cudaSetDevice(h->device)); CUDA_TRY(cudaMemcpy(out, h->d_tris, need, cudaMemcpyDeviceToHost)); }
+    }
     *bytes = need;
     return MIROGPU_OK;
 }

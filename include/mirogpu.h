@@ -97,11 +97,18 @@ typedef struct mirogpu_camera {
 
 enum { MIROGPU_LAYOUT_BVH2 = 0, MIROGPU_LAYOUT_CWBVH8 = 1, MIROGPU_LAYOUT_BVH4 = 2, MIROGPU_LAYOUT_QBVH4 = 3 };
 
+/* Who builds the tree (BVH::build, BVH.cpp:60-339).  SAH_HOST: binned SAH on the host cores (best trees; 0.5 s for 1.4 M
+ * triangles).  LBVH_DEVICE: Morton-order linear BVH built, collapsed four-wide and quantised entirely on the GPU
+ * (milliseconds; trees trace slower; QBVH4 only; falls back to SAH_HOST if the Morton tree is too deep for the kernels'
+ * stacks).  Both give identical hits. */
+enum { MIROGPU_BUILDER_SAH_HOST = 0, MIROGPU_BUILDER_LBVH_DEVICE = 1 };
+
 typedef struct mirogpu_build_options {
     int32_t layout;       /* MIROGPU_LAYOUT_*; default QBVH4 (the fastest measured) */
     int32_t max_leaf;     /* triangles per leaf (BVH2 / BVH4 / QBVH4: <= 4 like the reference's OBJECTS_PER_LEAF; CWBVH8: <= 3) */
     int32_t sah_bins;     /* binned SAH resolution, default 32 */
     int32_t device;       /* CUDA device ordinal, -1 = current device */
+    int32_t builder;      /* MIROGPU_BUILDER_*; default SAH_HOST */
 } mirogpu_build_options;
 
 typedef struct mirogpu_scene_info {
@@ -111,6 +118,8 @@ typedef struct mirogpu_scene_info {
     uint32_t num_binary_leaves;
     uint32_t max_depth;
     int32_t layout;
+    int32_t builder;           /* MIROGPU_BUILDER_* that produced the tree in HBM */
+    int32_t _pad;
     uint64_t node_bytes;
     uint64_t triangle_bytes;
     uint64_t shading_bytes;

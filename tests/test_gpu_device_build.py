@@ -1,0 +1,128 @@
+"""GPU tier: acceleration-structure construction on the device (MIROGPU_BUILDER_LBVH_DEVICE; SURVEY 8f-1, the
+counterpart of BVH::build, BVH.cpp:60-339).  A BVH only prunes the search, so hits must be IDENTICAL -- ids, t, beta,
+gamma bit for bit -- to the host-built SAH tree and to the oracle's exhaustive search; the tree the device built is
+checked structurally (every triangle exactly once, decoded boxes contain the reference bounds of everything below)."""
+import numpy as np
+import pytest
+
+import objio
+from conftest import bits, random_rays
+from emu_helpers import QBVH4_NODE, TRI_REC
+
+pytestmark = pytest.mark.gpu
+torch = pytest.importorskip("torch")
+
+EPS = np.float32(1e-4)
+
+
+def _verts(oracle, scenes, name):
+    scenes.realise(oracle, name, objio.obj_path)
+    oracle.precalc()
+    return np.ascontiguousarray(oracle.dump_triangles()[:, :9])
+
+
+@pytest.mark.parametrize("name", ["testobj", "cornell", "teapot", "bunny_teapot"])
+def test_device_built_tree_gives_identical_hits(pkg, scenes, oracle, name):
+    V = _verts(oracle, scenes, name)
+    dev = pkg.MiroScene(V, layout=pkg.LAYOUT_QBVH4, builder=pkg.BUILDER_LBVH_DEVICE)
+    host = pkg.MiroScene(V, layout=pkg.LAYOUT_QBVH4, builder=pkg.BUILDER_SAH_HOST)
+    assert dev.info.builder == pkg.BUILDER_LBVH_DEVICE and host.info.builder == pkg.BUILDER_SAH_HOST
+    assert dev.info.num_triangles == V.shape[0] and np.allclose(dev.info.bounds_min, host.info.bounds_min, atol=1e-3)
+    P = V.reshape(-1, 3)
+    rays = np.concatenate([oracle.eye_rays(96, 96), random_rays(30000, P.min(0), P.max(0), 7)])
+    a, b = dev.intersect(rays), host.intersect(rays)
+    assert np.array_equal(a, b)
+    if V.shape[0] <= 2000:
+        bt, bid, _, _ = oracle.trace_brute(rays)
+        ids = a["prim_id"].astype(np.int64); ids[ids == 0xFFFFFFFF] = -1
+        assert np.array_equal(ids, bid) and np.array_equal(bits(a["t"]), bits(bt))
+    for variant in (0, 1, 2):
+        dev.set_kernel_variant(variant)
+        assert np.array_equal(dev.intersect(rays), b)
+    assert np.array_equal(dev.intersect(rays, mode=pkg.ANY_HIT)["prim_id"] != 0xFFFFFFFF, b["prim_id"] != 0xFFFFFFFF)
+
+
+@pytest.mark.parametrize("name", ["cornell", "teapot", "bunny_teapot"])
+def test_device_built_tree_structure(pkg, scenes, oracle, name):
+    V = _verts(oracle, scenes, name)
+    S = pkg.MiroScene(V, layout=pkg.LAYOUT_QBVH4, builder=pkg.BUILDER_LBVH_DEVICE)
+    nodes = S.nodes_bytes().view(QBVH4_NODE)
+    tris = S.triangles_bytes().view(TRI_REC)
+    assert len(nodes) == S.info.num_nodes and len(tris) == V.shape[0]
+    order = tris["prim_id"]
+    assert sorted(order.tolist()) == list(range(V.shape[0]))
+    assert np.array_equal(tris["a"], V[order, 0:3]) and np.array_equal(tris["e1"], V[order, 3:6] - V[order, 0:3])
+    e1, e2 = tris["e1"], tris["e2"]
+    assert np.array_equal(tris["nx"], e1[:, 1] * e2[:, 2] - e1[:, 2] * e2[:, 1])
+    Pt = V.reshape(-1, 3, 3)
+    tlo, thi = (Pt.min(1) - EPS)[order], (Pt.max(1) + EPS)[order]
+    cell = np.ldexp(1.0, nodes["e"].astype(np.int64) - 127)
+    seen = np.zeros(len(order), bool)
+    visited = np.zeros(len(nodes), bool)
+    stack = [(0, None, None)]
+    # iterative post-order is awkward; do a recursive check with an explicit bound on depth instead
+    import sys
+    sys.setrecursionlimit(20000)
+
+    def check(ref, lo, hi):
+        if ref < 0:
+            r = ~ref
+            first, count = r >> 3, (r & 7) + 1
+            assert count <= 4 and not seen[first:first + count].any()
+            seen[first:first + count] = True
+            slo, shi = tlo[first:first + count].min(0), thi[first:first + count].max(0)
+        else:
+            assert not visited[ref]
+            visited[ref] = True
+            nd = nodes[ref]
+            parts = []
+            for c in range(4):
+                if nd["qlox"][c] == 255 and nd["qhix"][c] == 0:
+                    continue   # empty slot
+                clo = nd["origin"].astype(np.float64) + np.array([nd["qlox"][c], nd["qloy"][c], nd["qloz"][c]]) * cell[ref]
+                chi = nd["origin"].astype(np.float64) + np.array([nd["qhix"][c], nd["qhiy"][c], nd["qhiz"][c]]) * cell[ref]
+                parts.append(check(int(nd["link"][c]), clo, chi))
+            assert parts
+            slo, shi = np.min([p[0] for p in parts], 0), np.max([p[1] for p in parts], 0)
+        if lo is not None:
+            assert np.all(lo <= slo) and np.all(hi >= shi)
+        return slo, shi
+
+    check(0, None, None)
+    assert seen.all() and visited.all()
+
+
+def test_edge_cases_of_the_device_builder(pkg):
+    empty = pkg.MiroScene(np.zeros((0, 9), np.float32), builder=pkg.BUILDER_LBVH_DEVICE)
+    r = np.zeros((4, 8), np.float32); r[:, 6] = 1; r[:, 7] = 1e12
+    assert (empty.intersect(r)["prim_id"] == 0xFFFFFFFF).all()
+    V = np.array([[0, 0, 0, 1, 0, 0, 0, 1, 0]], np.float32)
+    one = pkg.MiroScene(V, builder=pkg.BUILDER_LBVH_DEVICE)
+    r[:, 0:3] = [0.25, 0.25, 1.0]; r[:, 4:7] = [0, 0, -1]
+    h = one.intersect(r)
+    assert (h["prim_id"] == 0).all() and np.allclose(h["t"], 1.0)
+    # many identical triangles: all Morton keys equal, the hierarchy falls back to positions; ties go to the smallest id
+    D = pkg.MiroScene(np.repeat(V, 37, axis=0), builder=pkg.BUILDER_LBVH_DEVICE)
+    assert (D.intersect(r)["prim_id"] == 0).all()
+    with pytest.raises(pkg.MiroGpuError):
+        pkg.MiroScene(V, layout=pkg.LAYOUT_BVH2, builder=pkg.BUILDER_LBVH_DEVICE)
+
+
+def test_device_build_of_the_bench_scene(pkg, scenes):
+    """1.39 M triangles through the host layer (BVH::setBuilder): same hits as the host-built SAH tree.  Measured on a B200:
+    63 ms on the device (incl. the 50 MB vertex upload and one sync per level of the wide tree) against 420 ms of binned
+    SAH on 16 host threads -- and 20.7 s for the reference's BVH::build."""
+    H = pkg.HostScene(pkg.LAYOUT_QBVH4, builder=pkg.BUILDER_LBVH_DEVICE)
+    scenes.realise(H, "bunny20", objio.obj_path)
+    H.precalc()
+    S = H.scene()
+    info = S.info
+    assert info.builder == pkg.BUILDER_LBVH_DEVICE and info.num_triangles == 1389021
+    assert info.build_seconds < 5.0      # first CUDA use in a process adds module-load time; the steady figure is in DESIGN.md
+    rays = H.eye_rays(480, 270)
+    a = S.intersect(rays)
+    H2 = pkg.HostScene(pkg.LAYOUT_QBVH4)
+    scenes.realise(H2, "bunny20", objio.obj_path)
+    H2.precalc()
+    assert H2.scene().info.builder == pkg.BUILDER_SAH_HOST
+    assert np.array_equal(H2.scene().intersect(rays), a)
