@@ -5,7 +5,7 @@
 // the host binned-SAH builder (bvh_build.cpp), whose trees trace faster.
 //
 //   k_lbvh_bounds      conservative triangle bounds (the same formula as triangle_bounds, bvh_build.cpp) + scene bounds
-//   k_lbvh_morton      63-bit Morton code of the box centre (21 bits per axis)
+//   k_lbvh_morton      63-bit Morton code of the box centre (21 bits per axis); bit 63 sets the few huge triangles apart
 //   cub radix sort     (key, triangle) pairs -- a library sort, as for any plain sort
 //   k_lbvh_hierarchy   Karras 2012: every internal node finds its key range and split in parallel
 //   k_lbvh_refit       bottom-up union of boxes (second arrival at a node continues upwards)
@@ -81,13 +81,18 @@ __global__ void __launch_bounds__(256) k_lbvh_morton(uint32_t n, const float4* _
     if (i >= n) return;
     uint32_t q[3];
     const float c[3] = {0.5f * (blo[i].x + bhi[i].x), 0.5f * (blo[i].y + bhi[i].y), 0.5f * (blo[i].z + bhi[i].z)};
+    const float e[3] = {bhi[i].x - blo[i].x, bhi[i].y - blo[i].y, bhi[i].z - blo[i].z};
+    bool big = false;   // a triangle spanning more than 1/8 of the scene along some axis
     for (int k = 0; k < 3; ++k) {
         const float lo = ord2f(scene[k]), hi = ord2f(scene[3 + k]);
         const float ext = hi - lo;
         const float t = ext > 0.f ? (c[k] - lo) / ext : 0.f;
         q[k] = (uint32_t)fminf(fmaxf(t * 2097152.0f, 0.f), 2097151.0f);
+        big |= e[k] > 0.125f * ext;
     }
-    keys[i] = (spread21(q[0]) << 2) | (spread21(q[1]) << 1) | spread21(q[2]);
+    // Bit 63 separates the few huge triangles from the rest, so the root's split isolates them: left among their Morton
+    // neighbours, one ground-plane triangle would blow up the boxes of a whole root-to-leaf path that every ray then walks.
+    keys[i] = (big ? 0ull : 0x8000000000000000ull) | (spread21(q[0]) << 2) | (spread21(q[1]) << 1) | spread21(q[2]);
     idx[i] = i;
 }
 
@@ -326,10 +331,10 @@ inline cudaError_t build_lbvh_device(const float* tri_vertices, uint32_t ntris, 
         LB(dalloc((void**)&idx2, (size_t)n * 4)); LB(dalloc((void**)&idx, (size_t)n * 4));
         k_lbvh_morton<<<g256, 256, 0, st>>>(n, blo, bhi, scene, keys2, idx2);
         size_t sort_bytes = 0;
-        LB(cub::DeviceRadixSort::SortPairs(nullptr, sort_bytes, keys2, keys, idx2, idx, (int)n, 0, 63, st));
+        LB(cub::DeviceRadixSort::SortPairs(nullptr, sort_bytes, keys2, keys, idx2, idx, (int)n, 0, 64, st));
         void* sort_tmp = nullptr;
         LB(dalloc(&sort_tmp, sort_bytes));
-        LB(cub::DeviceRadixSort::SortPairs(sort_tmp, sort_bytes, keys2, keys, idx2, idx, (int)n, 0, 63, st));
+        LB(cub::DeviceRadixSort::SortPairs(sort_tmp, sort_bytes, keys2, keys, idx2, idx, (int)n, 0, 64, st));
         LB(dalloc((void**)&child, (size_t)n * 8)); LB(dalloc((void**)&range, (size_t)n * 8));
         LB(dalloc((void**)&parent, (size_t)2 * n * 4));
         LB(dalloc((void**)&nlo, (size_t)2 * n * 16)); LB(dalloc((void**)&nhi, (size_t)2 * n * 16));

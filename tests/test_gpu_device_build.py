@@ -110,7 +110,7 @@ def test_edge_cases_of_the_device_builder(pkg):
 
 def test_device_build_of_the_bench_scene(pkg, scenes):
     """1.39 M triangles through the host layer (BVH::setBuilder): same hits as the host-built SAH tree.  Measured on a B200:
-    63 ms on the device (incl. the 50 MB vertex upload and one sync per level of the wide tree) against 420 ms of binned
+    19 ms on the device (incl. the 50 MB vertex upload and one sync per level of the wide tree) against 420 ms of binned
     SAH on 16 host threads -- and 20.7 s for the reference's BVH::build (SURVEY 8a1)."""
     H = pkg.HostScene(pkg.LAYOUT_QBVH4, builder=pkg.BUILDER_LBVH_DEVICE)
     scenes.realise(H, "bunny20", objio.obj_path)
