@@ -212,6 +212,13 @@ def test_config4_flower_refractive_scene(pkg, scenes, oracle):
     assert np.isfinite(img4).mean() > 0.999 and S.last_call_stats()[0] > 3.5 * 4 * rays_1spp * 0.9
     small = img4.reshape(256, 2, 384, 2, 3).mean(axis=(1, 3))           # box-filtered back to 384 x 256
     assert np.abs(tonemap_u8(oracle, np.nan_to_num(small)).astype(int) - a.astype(int)).mean() < 6
+    # the config's own size, 2048 x 1365 at 4 spp: same picture (block means agree with the small frame), ray count scales
+    W, Hh = scenes.SCENES["flower"]["size"]
+    full = S.render(H.camera(), S.render_params(W, Hh, spp=4, jitter=1, mode=pkg.RENDER_WHITTED, max_depth=10, bg=(1, 1, 1)))
+    assert full.shape == (Hh, W, 3) and np.isfinite(full).mean() > 0.999
+    assert S.last_call_stats()[0] > 0.9 * 4 * rays_1spp * (W * Hh) / (w * h)
+    fb = np.nan_to_num(full)
+    assert abs(float(np.clip(fb, 0, 4).mean()) / float(np.clip(np.nan_to_num(img), 0, 4).mean()) - 1) < 0.05
 
 
 def test_config5_photon_map_render(pkg, scenes, oracle):
@@ -238,5 +245,10 @@ def test_config5_photon_map_render(pkg, scenes, oracle):
     diff = np.abs(a.astype(int) - b.astype(int)).max(axis=2)
     assert (diff <= 2).mean() > 0.99, (diff <= 2).mean()
     assert psnr(a, b) >= 35, psnr(a, b)
+    # the config's own size, 512 x 512: finite, and the same picture as the small frame on average
+    Wc, Hc = scenes.SCENES["cornell_drops"]["size"]
+    full = S.render(H.camera(), S.render_params(Wc, Hc, mode=pkg.RENDER_WHITTED, max_depth=10, use_photon_maps=1))
+    assert np.isfinite(full).mean() > 0.999
+    assert abs(float(np.clip(np.nan_to_num(full), 0, 4).mean()) / float(np.clip(np.nan_to_num(img), 0, 4).mean()) - 1) < 0.05
     for which in (0, 1):
         oracle.lib.orc_pm_reset(which, ctypes.c_int(1))
