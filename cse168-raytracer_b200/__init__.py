@@ -84,7 +84,7 @@ EXPORTS = [
     "mirogpu_intersect_batch", "mirogpu_intersect_batch_device", "mirogpu_intersect_batch_counted", "mirogpu_set_kernel_variant",
     "mirogpu_resolve_hits_device", "mirogpu_generate_primary_device", "mirogpu_generate_bounce_device", "mirogpu_rng_uniforms",
     "mirogpu_render", "mirogpu_render_rgb8", "mirogpu_tonemap_rgb8_device", "mirogpu_render_device", "mirogpu_last_call_stats", "mirogpu_photon_upload", "mirogpu_photon_gather",
-    "mirogpu_photon_gather_device", "mirogpu_photon_trace",
+    "mirogpu_photon_gather_device", "mirogpu_photon_trace", "mirogpu_photon_set_exact",
 ]
 
 
@@ -300,6 +300,10 @@ class MiroScene:
         photons = np.ascontiguousarray(photons)
         assert photons.dtype == PHOTON_DTYPE
         _check(lib.mirogpu_photon_upload(self._h, int(which), _ptr(photons), int(photons.shape[0] - 1)))
+
+    def photon_set_exact(self, which, exact):
+        """exact=True: the reference's search verbatim, one query per thread (bit-identical); default False: one query per warp."""
+        _check(lib.mirogpu_photon_set_exact(self._h, int(which), int(bool(exact))))
 
     def photon_gather(self, which, pos, normal, max_dist=1e10, k=500):
         pos = np.ascontiguousarray(pos, np.float32).reshape(-1, 3)

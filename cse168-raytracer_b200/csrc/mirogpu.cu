@@ -711,6 +711,14 @@ int mirogpu_photon_upload(mirogpu_handle h, int which, const void* photons, int 
     return rc == MIROGPU_OK ? rc : fail(rc, err);
 }
 
+int mirogpu_photon_set_exact(mirogpu_handle h, int which, int exact)
+{
+    if (!h || which < 0 || which > 1) return fail(MIROGPU_ERR_INVALID_ARG, "bad argument");
+    std::lock_guard<std::mutex> lk(h->mtx);
+    h->pm[which].exact = exact != 0;
+    return MIROGPU_OK;
+}
+
 int mirogpu_photon_gather_device(mirogpu_handle h, int which, const float* d_pos3, const float* d_normal3, size_t n,
                                  float max_dist, int k, float* d_irrad3, void* cuda_stream)
 {

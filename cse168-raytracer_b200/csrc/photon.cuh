@@ -16,6 +16,7 @@ struct PhotonMapDevice {
     float4* d_photons = nullptr;  // 2 float4 per photon: (pos.xyz, plane|theta<<8|phi<<16 bits) (power.xyz, 0)
     float* d_tables = nullptr;    // costheta[256] sintheta[256] cosphi[256] sinphi[256]  (PhotonMap.cpp:47-53)
     int stored = 0, half_stored = 0;
+    bool exact = false;           // true: the reference's search verbatim, one query per thread (bit-identical estimates); see photon_impl.cuh
     int upload(const void* photons28, int stored, std::string& err);
     void release()
     {

@@ -260,6 +260,12 @@ int mirogpu_photon_upload(mirogpu_handle h, int which, const void* photons, int 
  * The walk is a pure function of (seed, emission index): any split of the range into calls / GPUs gives the same map. */
 int mirogpu_photon_trace(mirogpu_handle h, int light_index, int caustic, uint32_t seed, uint64_t first_emission, uint32_t count,
                          uint8_t* counts, float* records);
+/* Gather search of map `which`.  exact = 0 (default): one query per warp -- a shared stack of kd nodes and a shared
+ * candidate buffer, 32 nodes tested per step, the k-th distance found by bisection when the buffer fills; it ends with the
+ * same k nearest photons as the reference's search, summed in another order (estimates agree to ~1e-6 relative; k <= 704, larger k uses the exact search).
+ * exact = 1: the reference's search verbatim, one query per thread (same visiting order, heap and summation order:
+ * bit-identical estimates), several times slower. */
+int mirogpu_photon_set_exact(mirogpu_handle h, int which, int exact);
 int mirogpu_photon_gather(mirogpu_handle h, int which, const float* pos3, const float* normal3, size_t n,
                           float max_dist, int k, float* irrad3);
 int mirogpu_photon_gather_device(mirogpu_handle h, int which, const float* d_pos3, const float* d_normal3, size_t n,

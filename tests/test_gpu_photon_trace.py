@@ -79,6 +79,7 @@ def test_scene_trace_photons_against_the_reference(pkg, scenes, drops, which, na
     assert_statistical_parity(stats(rec, emissions), golden()[name], target)
     # and the map is live on the device: the gather sees it
     q = np.array([[2.5, 0.0, -2.5], [1.0, 0.0, -1.0]], np.float32); qn = np.array([[0, 1, 0], [0, 1, 0]], np.float32)
+    S.photon_set_exact(which, True)
     irr = S.photon_gather(which, q, qn, 1e10, 100)
     assert (irr > 0).all()
     O.lib.orc_pm_reset(which, len(ph))

@@ -147,24 +147,69 @@ def _photon_cloud(n, seed):
     return pw, pos, d
 
 
+def knn_estimate(ph, q, qn, max_dist, k):
+    """Irradiance by exhaustive search in numpy: the k nearest photons that pass the direction filter (PhotonMap.cpp:183-186)
+    among those the reference's walk can reach, summed and divided by pi r_k^2 -- or, when at most k exist inside max_dist, all
+    of them over pi max_dist^2 (the reference's radius only shrinks once its k-set overflows, PhotonMap.cpp:211-239)."""
+    stored = len(ph) - 1
+    half = stored // 2 - 1
+    reach = max(1, 2 * half - 1) if half >= 1 else 1          # children are only followed below half_stored (PhotonMap.cpp:161)
+    P = ph["pos"][1:reach + 1].astype(np.float32); W = ph["power"][1:reach + 1].astype(np.float32)
+    ang = np.arange(256, dtype=np.float64) * (1.0 / 256.0) * np.pi
+    ct, st_, cp, sp_ = np.cos(ang).astype(np.float32), np.sin(ang).astype(np.float32), np.cos(2 * ang).astype(np.float32), np.sin(2 * ang).astype(np.float32)
+    th, phi = ph["theta"][1:reach + 1], ph["phi"][1:reach + 1]
+    D = np.stack([st_[th] * cp[phi], st_[th] * sp_[phi], ct[th]], axis=1).astype(np.float32)
+    out = np.zeros((len(q), 3), np.float32)
+    r2max = np.float32(max_dist) * np.float32(max_dist)
+    for i in range(len(q)):
+        dx = P[:, 0] - q[i, 0]; dy = P[:, 1] - q[i, 1]; dz = P[:, 2] - q[i, 2]
+        d2 = (dx * dx + dy * dy) + dz * dz
+        dots = (D[:, 0] * qn[i, 0] + D[:, 1] * qn[i, 1]) + D[:, 2] * qn[i, 2]
+        ok = (d2 < r2max) & (dots < 0)
+        cand = np.nonzero(ok)[0]
+        if len(cand) > k:
+            order = cand[np.argsort(d2[cand], kind="stable")[:k]]
+            r2 = d2[order[-1]]
+        else:
+            order, r2 = cand, r2max
+        tmp = np.float32((1.0 / np.pi) / np.float64(r2))
+        out[i] = W[order].astype(np.float64).sum(0).astype(np.float32) * tmp
+    return out
+
+
 @pytest.mark.parametrize("nphot", [1, 7, 1000, 60000])
-def test_photon_gather_is_bit_identical(pkg, scenes, oracle, nphot):
+def test_photon_gather(pkg, scenes, oracle, nphot):
+    """exact mode (one query per thread, the reference's search verbatim): bit-identical to the oracle.
+    default mode (one query per warp): the k nearest photons, checked against an exhaustive search; it equals the reference's
+    result except where the reference's own quirk bites -- its first overflow evicts the farthest of the first k photons it
+    visited even when the newcomer is farther (PhotonMap.cpp:211-239), which loses a true neighbour exactly when those first k
+    were the k nearest: common for k = 1, never seen for k = 500 on 200 000 photons."""
     H, S = build_pair(pkg, scenes, oracle, "testobj")
     pw, pos, d = _photon_cloud(nphot, 4)
     w = oracle.pm_new(nphot)
     oracle.pm_store(w, pw, pos, d); oracle.pm_scale(w, 1.0 / nphot); oracle.pm_balance(w)
-    S.photon_upload(0, oracle.pm_dump(w))
+    ph = oracle.pm_dump(w)
+    S.photon_upload(0, ph)
     rng = np.random.default_rng(5)
-    q = (rng.random((3000, 3), dtype=np.float32) * np.float32(5)).astype(np.float32); q[:, 1] *= 0.02
-    qn = np.tile(np.array([[0, 1, 0]], np.float32), (3000, 1))
-    qn[::3] = rng.normal(size=(1000, 3)).astype(np.float32)
+    nq = 3000 if nphot <= 1000 else 600
+    q = (rng.random((nq, 3), dtype=np.float32) * np.float32(5)).astype(np.float32); q[:, 1] *= 0.02
+    qn = np.tile(np.array([[0, 1, 0]], np.float32), (nq, 1))
+    qn[::3] = rng.normal(size=(len(qn[::3]), 3)).astype(np.float32)
     for k, md_ in ((500, 1e10), (50, 1e10), (1, 1e10), (50, 0.3), (512, 1e10)):
         a = oracle.pm_irradiance(w, q, qn, md_, k)
+        S.photon_set_exact(0, True)
         b = S.photon_gather(0, q, qn, md_, k)
         assert np.array_equal(bits(a), bits(b)), (nphot, k, md_)
+        S.photon_set_exact(0, False)
+        c = S.photon_gather(0, q, qn, md_, k)
+        e = knn_estimate(ph, q, qn, md_, k)
+        assert np.allclose(c, e, rtol=2e-5, atol=0), (nphot, k, md_, float(np.abs(c - e).max()))
+        agree = np.isclose(c, a, rtol=2e-5, atol=0).all(axis=1).mean()
+        assert agree > (0.999 if k >= 500 else 0.5), (nphot, k, md_, agree)
     assert oracle.pm_irradiance(w, q, qn, 1e10, 50).max() > 0 or nphot < 50
     # through the host layer's Photon_map (store / scale / balance on the host, gather on the device)
     H.pm_store(1, pw, pos, d); H.pm_scale(1, 1.0 / nphot); H.pm_balance(1); H.pm_attach(1)
+    S.photon_set_exact(1, True)
     c = H.pm_irradiance(1, q, qn, 1e10, 100)
     assert np.array_equal(bits(c), bits(oracle.pm_irradiance(w, q, qn, 1e10, 100)))
 
