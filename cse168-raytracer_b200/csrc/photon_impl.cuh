@@ -10,6 +10,7 @@
 #ifndef MIROGPU_PHOTON_IMPL_CUH
 #define MIROGPU_PHOTON_IMPL_CUH
 
+#include <atomic>
 #include <cmath>
 #include <vector>
 
@@ -328,15 +329,15 @@ cudaError_t photon_gather_launch(const PhotonMapDevice& pm, const float* d_pos3,
                                                                       active, n, d_n, max_dist, k, d_irrad3);
         return cudaGetLastError();
     }
-    static bool attr_set = false;
     const size_t smem = sizeof(GatherWarpShared) * MIRO_GW_WARPS;
-    if (!attr_set) {
-        cudaError_t e = cudaFuncSetAttribute(k_photon_gather_warp, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e != cudaSuccess) return e;
-        attr_set = true;
-    }
     int dev = 0, sms = 148;
     cudaGetDevice(&dev);
+    static std::atomic<bool> attr_set[64];   // the opt-in to > 48 KB of dynamic shared memory is per device
+    if (dev < 0 || dev >= 64 || !attr_set[dev].load()) {
+        cudaError_t e = cudaFuncSetAttribute(k_photon_gather_warp, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        if (dev >= 0 && dev < 64) attr_set[dev].store(true);
+    }
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     const size_t want = (n + MIRO_GW_WARPS - 1) / MIRO_GW_WARPS;
     int occ = 1;
