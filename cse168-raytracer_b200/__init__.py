@@ -84,7 +84,7 @@ EXPORTS = [
     "mirogpu_intersect_batch", "mirogpu_intersect_batch_device", "mirogpu_intersect_batch_counted", "mirogpu_set_kernel_variant",
     "mirogpu_resolve_hits_device", "mirogpu_generate_primary_device", "mirogpu_generate_bounce_device", "mirogpu_rng_uniforms",
     "mirogpu_render", "mirogpu_render_rgb8", "mirogpu_tonemap_rgb8_device", "mirogpu_render_device", "mirogpu_last_call_stats", "mirogpu_photon_upload", "mirogpu_photon_gather",
-    "mirogpu_photon_gather_device", "mirogpu_photon_trace", "mirogpu_photon_set_exact",
+    "mirogpu_photon_gather_device", "mirogpu_photon_trace", "mirogpu_photon_set_exact", "mirogpu_host_alloc", "mirogpu_host_free",
 ]
 
 
@@ -95,6 +95,9 @@ def _load():
             "The engine has no CPU or PyTorch fallback.")
     lib = ctypes.CDLL(LIB_PATH)
     lib.mirogpu_last_error.restype = ctypes.c_char_p
+    lib.mirogpu_host_alloc.restype = ctypes.c_void_p
+    lib.mirogpu_host_alloc.argtypes = [ctypes.c_size_t]
+    lib.mirogpu_host_free.argtypes = [ctypes.c_void_p]
     return lib
 
 
@@ -447,10 +450,12 @@ class HostScene:
     def set_render(self, spp=1, jitter=0, mode=RENDER_WHITTED, shadows=1, seed=168, use_photon_maps=0):
         self.h.mh_set_render(int(spp), int(jitter), int(mode), int(shadows), ctypes.c_uint(seed), int(use_photon_maps))
 
-    def render(self, w, h):
+    def render(self, w, h, out=None):
         """Camera::click -> Scene::raytraceImage; returns the 8-bit image (h, w, 3), row 0 = bottom."""
-        out = np.zeros((h, w, 3), np.uint8)
-        self.h.mh_render(int(w), int(h), _ptr(out))
+        if out is None:
+            out = np.zeros((h, w, 3), np.uint8)
+        assert out.dtype == np.uint8 and out.shape == (h, w, 3) and out.flags.c_contiguous
+        self.last_render_seconds = float(self.h.mh_render(int(w), int(h), _ptr(out)))   # Scene::raytraceImage's own timer (Scene.cpp:206)
         return out
 
     # photon maps

@@ -11,8 +11,8 @@ public:
         Pixel() : r(0), g(0), b(0) {}
         Pixel(unsigned char ir, unsigned char ig, unsigned char ib) : r(ir), g(ig), b(ib) {}
     };
-    Image() : m_pixels(0), m_width(0), m_height(0) {}
-    ~Image() { delete[] m_pixels; }
+    Image() : m_pixels(0), m_width(0), m_height(0), m_pinned(false) {}
+    ~Image() { release(); }
     void resize(int width, int height);
     void setPixel(int x, int y, const Vector3& p);
     void setPixel(int x, int y, const Pixel& p);
@@ -22,7 +22,9 @@ public:
     int width() const { return m_width; }
     int height() const { return m_height; }
 private:
-    Pixel* m_pixels;
+    void release();
+    Pixel* m_pixels;      // page-locked when the device runtime grants it: the frame lands here by one DMA per render
     int m_width, m_height;
+    bool m_pinned;
 };
 #endif

@@ -2,6 +2,7 @@
 // interfaces implemented over the C ABI in include/mirogpu.h.  Host code keeps the reference's binary32
 // operand order wherever a value feeds the device (geometry ingest, camera basis, hit reconstruction), so
 // this file is compiled with -ffp-contract=off and no -march flag.
+#include <algorithm>
 #include <chrono>
 #include <cmath>
 #include <cstdio>
@@ -327,10 +328,20 @@ void Camera::click(Scene* pScene, Image* pImage)
     pScene->raytraceImage(this, pImage);
 }
 
+void Image::release()
+{
+    if (m_pinned) mirogpu_host_free(m_pixels); else delete[] m_pixels;
+    m_pixels = 0; m_pinned = false;
+}
 void Image::resize(int width, int height)
 {
-    delete[] m_pixels;
-    m_pixels = new Pixel[(size_t)width * height];
+    if (m_pixels && width == m_width && height == m_height) return;   // Camera::click on the same Image, frame after frame
+    release();
+    const size_t n = (size_t)std::max(width, 0) * std::max(height, 0);
+    m_pixels = static_cast<Pixel*>(mirogpu_host_alloc(n * sizeof(Pixel)));
+    m_pinned = m_pixels != 0;
+    if (m_pixels) for (size_t i = 0; i < n; ++i) m_pixels[i] = Pixel();
+    else m_pixels = new Pixel[n];
     m_width = width; m_height = height;
 }
 namespace {
@@ -346,7 +357,7 @@ void Image::setPixel(int x, int y, const Pixel& p)
 }
 void Image::clear(const Vector3& c)
 {
-    for (int y = 0; y < m_height; ++y) for (int x = 0; x < m_width; ++x) setPixel(x, y, c);
+    std::fill(m_pixels, m_pixels + (size_t)m_width * m_height, Pixel(mapByte(c.x), mapByte(c.y), mapByte(c.z)));
 }
 void Image::writePPM(const char* pcFile)
 {

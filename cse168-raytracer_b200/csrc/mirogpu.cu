@@ -593,6 +593,14 @@ int mirogpu_rng_uniforms(uint32_t seed, uint32_t sample, uint32_t dimension, siz
     return MIROGPU_OK;
 }
 
+void* mirogpu_host_alloc(size_t bytes)
+{
+    void* p = nullptr;
+    if (cudaHostAlloc(&p, bytes ? bytes : 1, cudaHostAllocDefault) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+    return p;
+}
+void mirogpu_host_free(void* p) { if (p) cudaFreeHost(p); }
+
 int mirogpu_last_call_stats(mirogpu_handle h, uint64_t* rays_traced, uint64_t* kernel_launches)
 {
     if (!h) return fail(MIROGPU_ERR_INVALID_ARG, "NULL handle");

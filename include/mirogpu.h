@@ -241,6 +241,11 @@ int mirogpu_tonemap_rgb8_device(mirogpu_handle h, const float* d_rgb, int width,
  * the stream is synchronised by the caller only if sync != 0. */
 int mirogpu_render_device(mirogpu_handle h, const mirogpu_camera* cam, const mirogpu_render_params* p, float* d_rgb,
                           void* cuda_stream);
+/* Page-locked host memory for buffers that cross the boundary every frame (the reference's Image::m_pixels, Image.cpp:22,
+ * ray / hit arrays of a batch): copies to and from it run as one DMA instead of being staged through the driver's bounce
+ * buffer.  Plain malloc'd memory is accepted everywhere as well.  mirogpu_host_alloc returns NULL on failure. */
+void* mirogpu_host_alloc(size_t bytes);
+void mirogpu_host_free(void* p);
 /* Rays traced (all kinds) and kernels launched by the last render / intersect call on this handle. */
 int mirogpu_last_call_stats(mirogpu_handle h, uint64_t* rays_traced, uint64_t* kernel_launches);
 

@@ -297,3 +297,30 @@ def test_config5_photon_map_render(pkg, scenes, oracle):
     assert abs(float(np.clip(np.nan_to_num(full), 0, 4).mean()) / float(np.clip(np.nan_to_num(img), 0, 4).mean()) - 1) < 0.05
     for which in (0, 1):
         oracle.lib.orc_pm_reset(which, ctypes.c_int(1))
+
+
+def test_page_locked_host_buffers_and_image_reuse(pkg, scenes, oracle):
+    """mirogpu_host_alloc / mirogpu_host_free: a page-locked frame buffer takes the same bytes as a pageable one, and
+    Camera::click on the same Image (Image::resize to the same size) keeps its pixels across frames."""
+    H, S = build_pair(pkg, scenes, oracle, "cornell")
+    w, h = 96, 64
+    p = S.render_params(w, h, spp=1, jitter=0, mode=pkg.RENDER_WHITTED, tonemap=1, shadows=1)
+    want = S.render_rgb8(H.camera(), p)
+    ptr = pkg.lib.mirogpu_host_alloc(w * h * 3)
+    assert ptr
+    try:
+        buf = np.ctypeslib.as_array(ctypes.cast(ptr, ctypes.POINTER(ctypes.c_ubyte)), shape=(h, w, 3))
+        buf[:] = 7
+        got = S.render_rgb8(H.camera(), p, out=buf)
+        assert np.array_equal(got, want) and want.max() > 0
+    finally:
+        pkg.lib.mirogpu_host_free(ptr)
+    pkg.lib.mirogpu_host_free(None)
+    H.set_render(spp=1, jitter=0, mode=pkg.RENDER_WHITTED, shadows=1, seed=168, use_photon_maps=0)
+    a = H.render(w, h)
+    out = np.zeros((h, w, 3), np.uint8)
+    b = H.render(w, h, out=out)
+    assert b is out and np.array_equal(a, b) and np.array_equal(a, want)
+    assert H.last_render_seconds > 0
+    c = H.render(w // 2, h // 2)      # a different size reallocates
+    assert c.shape == (h // 2, w // 2, 3) and c.max() > 0
