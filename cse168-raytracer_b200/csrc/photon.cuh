@@ -15,13 +15,15 @@ namespace mirogpu {
 struct PhotonMapDevice {
     float4* d_photons = nullptr;  // 2 float4 per photon: (pos.xyz, plane|theta<<8|phi<<16 bits) (power.xyz, 0)
     float* d_tables = nullptr;    // costheta[256] sintheta[256] cosphi[256] sinphi[256]  (PhotonMap.cpp:47-53)
+    float4* d_search = nullptr;   // warp-per-query search records, 32 B per photon: (pos.xyz, same bits) (direction.xyz from the tables, 0)
+    unsigned int* d_tickets = nullptr;   // chunk counters of the warp-per-query launches (one per launch in flight)
     int stored = 0, half_stored = 0;
     bool exact = false;           // true: the reference's search verbatim, one query per thread (bit-identical estimates); see photon_impl.cuh
     int upload(const void* photons28, int stored, std::string& err);
     void release()
     {
-        cudaFree(d_photons); cudaFree(d_tables);
-        d_photons = nullptr; d_tables = nullptr; stored = half_stored = 0;
+        cudaFree(d_photons); cudaFree(d_tables); cudaFree(d_search); cudaFree(d_tickets);
+        d_photons = nullptr; d_tables = nullptr; d_search = nullptr; d_tickets = nullptr; stored = half_stored = 0;
     }
 };
 

@@ -12,9 +12,16 @@
 
 #include <atomic>
 #include <cmath>
+#include <cstdlib>
 #include <vector>
 
 namespace mirogpu {
+
+static inline int env_int(const char* name, int dflt)
+{
+    const char* e = getenv(name);
+    return e ? atoi(e) : dflt;
+}
 
 int PhotonMapDevice::upload(const void* photons28, int n, std::string& err)
 {
@@ -39,7 +46,19 @@ int PhotonMapDevice::upload(const void* photons28, int n, std::string& err)
     }
     cudaError_t e = cudaMalloc(&d_photons, packed.size() * sizeof(float4));
     if (e == cudaSuccess) e = cudaMalloc(&d_tables, tab.size() * sizeof(float));
+    if (e == cudaSuccess) e = cudaMalloc(&d_search, packed.size() * sizeof(float4));
+    if (e == cudaSuccess) e = cudaMalloc(&d_tickets, 64 * sizeof(unsigned int));
     if (e == cudaSuccess) e = cudaMemcpy(d_photons, packed.data(), packed.size() * sizeof(float4), cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) {
+        // the power half of each record becomes the photon's direction, multiplied out of the tables the way
+        // Photon_map::photon_dir does (PhotonMap.cpp:68-74: single binary32 products, so host and device agree bit for bit)
+        for (int i = 1; i <= n; ++i) {
+            const Photon28& p = src[i];
+            const float st = tab[256 + p.theta];
+            packed[2 * (size_t)i + 1] = make_float4(xmul(st, tab[512 + p.phi]), xmul(st, tab[768 + p.phi]), tab[p.theta], 0.f);
+        }
+        e = cudaMemcpy(d_search, packed.data(), packed.size() * sizeof(float4), cudaMemcpyHostToDevice);
+    }
     if (e == cudaSuccess) e = cudaMemcpy(d_tables, tab.data(), tab.size() * sizeof(float), cudaMemcpyHostToDevice);
     if (e != cudaSuccess) { err = std::string("photon upload: ") + cudaGetErrorString(e); release(); return e == cudaErrorMemoryAllocation ? MIROGPU_ERR_OOM : MIROGPU_ERR_CUDA; }
     stored = n;
@@ -204,118 +223,169 @@ __device__ __forceinline__ float gather_select(GatherWarpShared& sh, int& n, int
     return __uint_as_float(tau);
 }
 
-__global__ void __launch_bounds__(32 * MIRO_GW_WARPS) k_photon_gather_warp(const float4* __restrict__ photons, const float* __restrict__ tables, int stored,
+// Queries are claimed in chunks of `chunk` consecutive indices (a ticket counter), because consecutive queries are
+// neighbouring pixels: the k photons that answered one query bound the search radius of the next -- if all k also face
+// the next query's normal, the k-th nearest facing photon of the next query is no farther than the farthest of them.
+// Starting the walk with that radius instead of max_dist saves most of the visits on evenly lit surfaces (config 5:
+// 12 k -> 3 k per query on the walls); the result is the same k nearest photons.
+template <int NPL>   // nodes per lane and iteration
+__global__ void __launch_bounds__(32 * MIRO_GW_WARPS) k_photon_gather_warp(const float4* __restrict__ photons, const float4* __restrict__ search, int stored,
                                                                           int half_stored, const float* __restrict__ pos3, const float* __restrict__ nrm3,
                                                                           const float4* __restrict__ active, size_t n, const uint32_t* __restrict__ d_n,
-                                                                          float max_dist, int kmax, float* __restrict__ irr3)
+                                                                          float max_dist, int kmax, float* __restrict__ irr3, unsigned int* ticket,
+                                                                          int chunk, int seed_on)
 {
     extern __shared__ unsigned char gw_smem[];
     GatherWarpShared& sh = reinterpret_cast<GatherWarpShared*>(gw_smem)[threadIdx.x >> 5];
     const unsigned lane = threadIdx.x & 31u;
     const unsigned lt = (1u << lane) - 1u;
     if (d_n) n = min(n, (size_t)*d_n);
-    const size_t nwarps = (size_t)gridDim.x * MIRO_GW_WARPS;
-    for (size_t q = (size_t)blockIdx.x * MIRO_GW_WARPS + (threadIdx.x >> 5); q < n; q += nwarps) {
-        if (active && active[q].w == 0.f) {
-            if (lane < 3) irr3[3 * q + lane] = 0.f;
-            continue;
-        }
-        const float px = pos3[3 * q], py = pos3[3 * q + 1], pz = pos3[3 * q + 2];
-        const float nx = nrm3[3 * q], ny = nrm3[3 * q + 1], nz = nrm3[3 * q + 2];
-        const float full_r2 = xmul(max_dist, max_dist);
-        float r2 = full_r2;         // warp-uniform: current squared search radius
-        bool overflowed = false;    // more than k photons have been accepted (the reference's heap was built)
-        int sp = 0, ncand = 0;      // warp-uniform
-        if (stored >= 1) {
-            if (lane == 0) { sh.stack_node[0] = 1u; sh.stack_bound[0] = 0.f; }
-            sp = 1;
-        }
-        __syncwarp();
-        while (sp > 0) {
-            // two nodes per lane and iteration (64 per warp): twice the loads in flight per round trip to L2.  Near the
-            // stack's capacity fall back to 32, then to one node per iteration (plain DFS grows by at most one entry per level).
-            const int m = sp > MIRO_GW_STACK - 160 ? 1 : (sp > MIRO_GW_STACK - 448 ? min(sp, 32) : min(sp, 64));
-            uint32_t node[2] = {0u, 0u};
-            float bound[2] = {0.f, 0.f};
-            bool act[2];
-#pragma unroll
-            for (int b = 0; b < 2; ++b) {
-                const int e = (int)lane + 32 * b;
-                act[b] = e < m;
-                if (act[b]) { node[b] = sh.stack_node[sp - 1 - e]; bound[b] = sh.stack_bound[sp - 1 - e]; act[b] = bound[b] < r2; }
+    const float full_r2 = xmul(max_dist, max_dist);
+    const unsigned long long nchunks = (n + (size_t)chunk - 1) / (size_t)chunk;
+    for (;;) {
+        unsigned int c0 = 0u;
+        if (lane == 0) c0 = atomicAdd(ticket, 1u);
+        c0 = __shfl_sync(0xffffffffu, c0, 0);
+        if (c0 >= nchunks) break;
+        const size_t qb = (size_t)c0 * (size_t)chunk;
+        const size_t qe = min(n, qb + (size_t)chunk);
+        bool prev_valid = false;    // sh.cand_id[0 .. kmax) holds the k photons of the previous query of this chunk
+        for (size_t q = qb; q < qe; ++q) {
+            if (active && active[q].w == 0.f) {
+                if (lane < 3) irr3[3 * q + lane] = 0.f;
+                continue;
             }
-            sp -= m;
-            __syncwarp();
-            float4 ph[2];
-#pragma unroll
-            for (int b = 0; b < 2; ++b) ph[b] = act[b] ? __ldg(photons + 2 * (size_t)node[b]) : make_float4(0.f, 0.f, 0.f, 0.f);
-            bool push_near[2] = {false, false}, push_far[2] = {false, false}, accept[2] = {false, false};
-            uint32_t near_child[2] = {0u, 0u}, far_child[2] = {0u, 0u};
-            float far_bound[2] = {0.f, 0.f}, dist2[2] = {0.f, 0.f};
-#pragma unroll
-            for (int b = 0; b < 2; ++b) {
-                if (!act[b]) continue;
-                const uint32_t bits = __float_as_uint(ph[b].w);
-                if ((int)node[b] < half_stored) {
-                    const uint32_t plane = bits & 3u;
-                    const float qc = plane == 0 ? px : (plane == 1 ? py : pz);
-                    const float pc = plane == 0 ? ph[b].x : (plane == 1 ? ph[b].y : ph[b].z);
-                    const float dist1 = xsub(qc, pc);
-                    near_child[b] = dist1 > 0.0f ? 2 * node[b] + 1 : 2 * node[b];
-                    far_child[b] = dist1 > 0.0f ? 2 * node[b] : 2 * node[b] + 1;
-                    push_near[b] = true;
-                    const float p2 = xmul(dist1, dist1);
-                    push_far[b] = p2 < r2;                    // PhotonMap.cpp:169,172
-                    far_bound[b] = fmaxf(bound[b], p2);
+            const float px = pos3[3 * q], py = pos3[3 * q + 1], pz = pos3[3 * q + 2];
+            const float nx = nrm3[3 * q], ny = nrm3[3 * q + 1], nz = nrm3[3 * q + 2];
+            float r2_seed = full_r2;
+            bool seeded = false;
+            if (seed_on && prev_valid) {
+                bool all_face = true;
+                float dmax = 0.f;
+                for (int i = (int)lane; i < kmax; i += 32) {
+                    const F8 ph = ld256(search + 2 * (size_t)sh.cand_id[i]);
+                    float t = xsub(ph.lo.x, px);
+                    float d = xmul(t, t);
+                    t = xsub(ph.lo.y, py); d = xadd(d, xmul(t, t));
+                    t = xsub(ph.lo.z, pz); d = xadd(d, xmul(t, t));
+                    all_face = all_face && xdot(ph.hi.x, ph.hi.y, ph.hi.z, nx, ny, nz) < 0.0f;
+                    dmax = fmaxf(dmax, d);
                 }
-                float t = xsub(ph[b].x, px);
-                dist2[b] = xmul(t, t);
-                t = xsub(ph[b].y, py); dist2[b] = xadd(dist2[b], xmul(t, t));
-                t = xsub(ph[b].z, pz); dist2[b] = xadd(dist2[b], xmul(t, t));
-                const uint32_t th = (bits >> 8) & 0xffu, phi = (bits >> 16) & 0xffu;
-                const float st = __ldg(tables + 256 + th);
-                const float dx = xmul(st, __ldg(tables + 512 + phi)), dy = xmul(st, __ldg(tables + 768 + phi)), dz = __ldg(tables + th);
-                accept[b] = dist2[b] < r2 && xdot(dx, dy, dz, nx, ny, nz) < 0.0f;   // PhotonMap.cpp:183-186
-            }
-            // children: far sides first, near sides on top of them (the near side of the topmost node ends on top)
-#pragma unroll
-            for (int b = 1; b >= 0; --b) {
-                const unsigned fm = __ballot_sync(0xffffffffu, push_far[b]);
-                if (push_far[b]) { const int o = sp + __popc(fm & lt); sh.stack_node[o] = far_child[b]; sh.stack_bound[o] = far_bound[b]; }
-                sp += __popc(fm);
-            }
-#pragma unroll
-            for (int b = 1; b >= 0; --b) {
-                const unsigned nm = __ballot_sync(0xffffffffu, push_near[b]);
-                if (push_near[b]) { const int o = sp + __popc(nm & lt); sh.stack_node[o] = near_child[b]; sh.stack_bound[o] = bound[b]; }
-                sp += __popc(nm);
-            }
-#pragma unroll
-            for (int b = 0; b < 2; ++b) {
-                const unsigned am = __ballot_sync(0xffffffffu, accept[b]);
-                if (accept[b]) { const int o = ncand + __popc(am & lt); sh.cand_d2[o] = dist2[b]; sh.cand_id[o] = node[b]; }
-                ncand += __popc(am);
+                all_face = __all_sync(0xffffffffu, all_face);
+                dmax = __uint_as_float(__reduce_max_sync(0xffffffffu, __float_as_uint(dmax)));
+                if (all_face) {
+                    r2_seed = fmaxf(__fmul_ru(dmax, 1.000001f), 1e-37f);    // strictly above the farthest of them
+                    seeded = r2_seed < full_r2;
+                }
             }
             __syncwarp();
-            if (ncand > MIRO_GW_CAND - 64) {   // the next iteration could overflow the buffer: keep the k nearest
-                r2 = gather_select(sh, ncand, kmax, lane);
-                overflowed = true;
-                // the k-th itself stays in the buffer; later photons must be strictly closer than the radius, as in the reference
+            float r2;                   // warp-uniform: current squared search radius
+            bool overflowed;            // more than k photons have been accepted (the reference's heap was built)
+            int ncand;
+            for (;;) {
+                r2 = seeded ? r2_seed : full_r2;
+                overflowed = false;
+                int sp = 0;
+                ncand = 0;
+                if (stored >= 1) {
+                    if (lane == 0) { sh.stack_node[0] = 1u; sh.stack_bound[0] = 0.f; }
+                    sp = 1;
+                }
+                __syncwarp();
+                while (sp > 0) {
+                    // NPL nodes per lane and iteration: that many loads in flight per round trip to L2.  Near the stack's
+                    // capacity fall back to 32, then to one node per iteration (plain DFS grows by at most one entry per level).
+                    const int m = sp > MIRO_GW_STACK - 32 * NPL - 96 ? 1 : (sp > MIRO_GW_STACK - 448 ? min(sp, 32) : min(sp, 32 * NPL));
+                    uint32_t node[NPL];
+                    float bound[NPL];
+                    bool act[NPL];
+#pragma unroll
+                    for (int b = 0; b < NPL; ++b) {
+                        const int e = (int)lane + 32 * b;
+                        node[b] = 0u; bound[b] = 0.f;
+                        act[b] = e < m;
+                        if (act[b]) { node[b] = sh.stack_node[sp - 1 - e]; bound[b] = sh.stack_bound[sp - 1 - e]; act[b] = bound[b] < r2; }
+                    }
+                    sp -= m;
+                    __syncwarp();
+                    F8 ph[NPL];   // one 256-bit load per node: position, plane bits and direction share a sector
+#pragma unroll
+                    for (int b = 0; b < NPL; ++b) {
+                        if (act[b]) ph[b] = ld256(search + 2 * (size_t)node[b]);
+                        else ph[b].lo = ph[b].hi = make_float4(0.f, 0.f, 0.f, 0.f);
+                    }
+                    bool push_near[NPL], push_far[NPL], accept[NPL];
+                    uint32_t near_child[NPL], far_child[NPL];
+                    float far_bound[NPL], dist2[NPL];
+#pragma unroll
+                    for (int b = 0; b < NPL; ++b) {
+                        push_near[b] = push_far[b] = accept[b] = false;
+                        near_child[b] = far_child[b] = 0u; far_bound[b] = dist2[b] = 0.f;
+                        if (!act[b]) continue;
+                        if ((int)node[b] < half_stored) {
+                            const uint32_t plane = __float_as_uint(ph[b].lo.w) & 3u;
+                            const float qc = plane == 0 ? px : (plane == 1 ? py : pz);
+                            const float pc = plane == 0 ? ph[b].lo.x : (plane == 1 ? ph[b].lo.y : ph[b].lo.z);
+                            const float dist1 = xsub(qc, pc);
+                            near_child[b] = dist1 > 0.0f ? 2 * node[b] + 1 : 2 * node[b];
+                            far_child[b] = dist1 > 0.0f ? 2 * node[b] : 2 * node[b] + 1;
+                            push_near[b] = true;
+                            const float p2 = xmul(dist1, dist1);
+                            push_far[b] = p2 < r2;                    // PhotonMap.cpp:169,172
+                            far_bound[b] = fmaxf(bound[b], p2);
+                        }
+                        float t = xsub(ph[b].lo.x, px);
+                        dist2[b] = xmul(t, t);
+                        t = xsub(ph[b].lo.y, py); dist2[b] = xadd(dist2[b], xmul(t, t));
+                        t = xsub(ph[b].lo.z, pz); dist2[b] = xadd(dist2[b], xmul(t, t));
+                        accept[b] = dist2[b] < r2 && xdot(ph[b].hi.x, ph[b].hi.y, ph[b].hi.z, nx, ny, nz) < 0.0f;   // PhotonMap.cpp:183-186
+                    }
+                    // children: far sides first, near sides on top of them (the near side of the topmost node ends on top)
+#pragma unroll
+                    for (int b = NPL - 1; b >= 0; --b) {
+                        const unsigned fm = __ballot_sync(0xffffffffu, push_far[b]);
+                        if (push_far[b]) { const int o = sp + __popc(fm & lt); sh.stack_node[o] = far_child[b]; sh.stack_bound[o] = far_bound[b]; }
+                        sp += __popc(fm);
+                    }
+#pragma unroll
+                    for (int b = NPL - 1; b >= 0; --b) {
+                        const unsigned nm = __ballot_sync(0xffffffffu, push_near[b]);
+                        if (push_near[b]) { const int o = sp + __popc(nm & lt); sh.stack_node[o] = near_child[b]; sh.stack_bound[o] = bound[b]; }
+                        sp += __popc(nm);
+                    }
+#pragma unroll
+                    for (int b = 0; b < NPL; ++b) {
+                        const unsigned am = __ballot_sync(0xffffffffu, accept[b]);
+                        if (accept[b]) { const int o = ncand + __popc(am & lt); sh.cand_d2[o] = dist2[b]; sh.cand_id[o] = node[b]; }
+                        ncand += __popc(am);
+                    }
+                    __syncwarp();
+                    if (ncand > MIRO_GW_CAND - 32 * NPL) {   // the next iteration could overflow the buffer: keep the k nearest
+                        r2 = gather_select(sh, ncand, kmax, lane);
+                        overflowed = true;
+                        // the k-th itself stays in the buffer; later photons must be strictly closer than the radius, as in the reference
+                    }
+                }
+                if (ncand > kmax) { r2 = gather_select(sh, ncand, kmax, lane); overflowed = true; }
+                // A seeded walk that ends with exactly k photons cannot tell "exactly k facing photons exist" (the reference then
+                // never builds its heap and divides by max_dist^2) from "more lie beyond the seed radius": walk again unseeded.
+                if (seeded && !overflowed) { seeded = false; continue; }
+                break;
             }
+            float sx = 0.f, sy = 0.f, sz = 0.f;
+            for (int i = (int)lane; i < ncand; i += 32) {
+                const float4 pw = __ldg(photons + 2 * (size_t)sh.cand_id[i] + 1);
+                sx += pw.x; sy += pw.y; sz += pw.z;
+            }
+            for (int o = 16; o > 0; o >>= 1) {
+                sx += __shfl_xor_sync(0xffffffffu, sx, o); sy += __shfl_xor_sync(0xffffffffu, sy, o); sz += __shfl_xor_sync(0xffffffffu, sz, o);
+            }
+            // density estimate over the k-th nearest distance if the k-set overflowed, else over max_dist (PhotonMap.cpp:136)
+            const float tmp = (float)(((double)1.0f / 3.14159265358979323846) / (double)(overflowed ? r2 : full_r2));
+            if (lane == 0) { irr3[3 * q] = xmul(sx, tmp); irr3[3 * q + 1] = xmul(sy, tmp); irr3[3 * q + 2] = xmul(sz, tmp); }
+            prev_valid = ncand == kmax;
+            __syncwarp();
         }
-        if (ncand > kmax) { r2 = gather_select(sh, ncand, kmax, lane); overflowed = true; }
-        float sx = 0.f, sy = 0.f, sz = 0.f;
-        for (int i = (int)lane; i < ncand; i += 32) {
-            const float4 pw = __ldg(photons + 2 * (size_t)sh.cand_id[i] + 1);
-            sx += pw.x; sy += pw.y; sz += pw.z;
-        }
-        for (int o = 16; o > 0; o >>= 1) {
-            sx += __shfl_xor_sync(0xffffffffu, sx, o); sy += __shfl_xor_sync(0xffffffffu, sy, o); sz += __shfl_xor_sync(0xffffffffu, sz, o);
-        }
-        // density estimate over the k-th nearest distance if the k-set overflowed, else over max_dist (PhotonMap.cpp:136)
-        const float tmp = (float)(((double)1.0f / 3.14159265358979323846) / (double)(overflowed ? r2 : full_r2));
-        if (lane == 0) { irr3[3 * q] = xmul(sx, tmp); irr3[3 * q + 1] = xmul(sy, tmp); irr3[3 * q + 2] = xmul(sz, tmp); }
-        __syncwarp();
     }
 }
 
@@ -324,7 +394,7 @@ cudaError_t photon_gather_launch(const PhotonMapDevice& pm, const float* d_pos3,
 {
     if (n == 0) return cudaSuccess;
     if (!pm.d_photons) return cudaMemsetAsync(d_irrad3, 0, n * 12, st);   // empty map: zero irradiance, like a map with no photons
-    if (pm.exact || k + 128 > MIRO_GW_CAND) {
+    if (pm.exact || k + 128 > MIRO_GW_CAND || k < 1) {
         k_photon_gather<<<(unsigned)((n + 127) / 128), 128, 0, st>>>(pm.d_photons, pm.d_tables, pm.stored, pm.half_stored, d_pos3, d_normal3,
                                                                       active, n, d_n, max_dist, k, d_irrad3);
         return cudaGetLastError();
@@ -334,17 +404,35 @@ cudaError_t photon_gather_launch(const PhotonMapDevice& pm, const float* d_pos3,
     cudaGetDevice(&dev);
     static std::atomic<bool> attr_set[64];   // the opt-in to > 48 KB of dynamic shared memory is per device
     if (dev < 0 || dev >= 64 || !attr_set[dev].load()) {
-        cudaError_t e = cudaFuncSetAttribute(k_photon_gather_warp, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        cudaError_t e = cudaFuncSetAttribute(k_photon_gather_warp<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(k_photon_gather_warp<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
         if (dev >= 0 && dev < 64) attr_set[dev].store(true);
     }
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    const size_t want = (n + MIRO_GW_WARPS - 1) / MIRO_GW_WARPS;
+    // knobs (defaults measured on config 5): queries per ticket, neighbour seeding, nodes per lane and iteration.  A chunk is the
+    // unit of load balance and some queries cost 100x the median (a ceiling few photons face: 1400 iterations), so chunks
+    // stay short: 8 beats 16 and 32 (41 / 47 / 57 ms) although longer chunks seed more queries; 4 nodes per lane lose to 2.
+    static const int chunk = std::max(1, env_int("MIROGPU_GATHER_CHUNK", 8));
+    static const int seed_on = env_int("MIROGPU_GATHER_SEED", 1);
+    static const int npl = env_int("MIROGPU_GATHER_NPL", 2);
+    const size_t want = ((n + chunk - 1) / chunk + MIRO_GW_WARPS - 1) / MIRO_GW_WARPS;
+    static std::atomic<unsigned> launch_seq{0};
+    unsigned int* ticket = pm.d_tickets + (launch_seq.fetch_add(1) % 64u);   // one counter per launch in flight
+    cudaError_t e = cudaMemsetAsync(ticket, 0, 4, st);
+    if (e != cudaSuccess) return e;
     int occ = 1;
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_photon_gather_warp, 32 * MIRO_GW_WARPS, smem);
-    const unsigned grid = (unsigned)std::min<size_t>(want, (size_t)sms * std::max(occ, 1));   // persistent warps, grid-stride over queries
-    k_photon_gather_warp<<<grid, 32 * MIRO_GW_WARPS, smem, st>>>(pm.d_photons, pm.d_tables, pm.stored, pm.half_stored, d_pos3, d_normal3,
-                                                                 active, n, d_n, max_dist, k, d_irrad3);
+    if (npl == 4) {
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_photon_gather_warp<4>, 32 * MIRO_GW_WARPS, smem);
+        const unsigned grid = (unsigned)std::min<size_t>(want, (size_t)sms * std::max(occ, 1));
+        k_photon_gather_warp<4><<<grid, 32 * MIRO_GW_WARPS, smem, st>>>(pm.d_photons, pm.d_search, pm.stored, pm.half_stored, d_pos3, d_normal3,
+                                                                        active, n, d_n, max_dist, k, d_irrad3, ticket, chunk, seed_on);
+    } else {
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_photon_gather_warp<2>, 32 * MIRO_GW_WARPS, smem);
+        const unsigned grid = (unsigned)std::min<size_t>(want, (size_t)sms * std::max(occ, 1));   // persistent warps
+        k_photon_gather_warp<2><<<grid, 32 * MIRO_GW_WARPS, smem, st>>>(pm.d_photons, pm.d_search, pm.stored, pm.half_stored, d_pos3, d_normal3,
+                                                                        active, n, d_n, max_dist, k, d_irrad3, ticket, chunk, seed_on);
+    }
     return cudaGetLastError();
 }
 

@@ -214,6 +214,47 @@ def test_photon_gather(pkg, scenes, oracle, nphot):
     assert np.array_equal(bits(c), bits(oracle.pm_irradiance(w, q, qn, 1e10, 100)))
 
 
+def test_photon_gather_neighbouring_queries(pkg, scenes, oracle):
+    """Neighbouring queries (pixel order) seed each other's search radius inside a chunk: same k nearest photons as the
+    exhaustive search, for smooth runs, for runs whose normal flips (the seed must be dropped) and for k-sets that tie the
+    photon count (a seeded walk that ends with exactly k photons is repeated unseeded)."""
+    H, S = build_pair(pkg, scenes, oracle, "testobj")
+    nphot = 30000
+    pw, pos, d = _photon_cloud(nphot, 11)
+    w = oracle.pm_new(nphot)
+    oracle.pm_store(w, pw, pos, d); oracle.pm_scale(w, 1.0 / nphot); oracle.pm_balance(w)
+    ph = oracle.pm_dump(w)
+    S.photon_upload(0, ph)
+    S.photon_set_exact(0, False)
+    rng = np.random.default_rng(12)
+    nq = 640
+    t = np.arange(nq, dtype=np.float32)
+    q = np.stack([0.5 + 0.006 * t, 0.01 + 0.0 * t, 1.0 + 0.004 * t], axis=1).astype(np.float32)      # a scanline across the floor
+    qn = np.tile(np.array([[0, 1, 0]], np.float32), (nq, 1)) + rng.normal(size=(nq, 3)).astype(np.float32) * np.float32(1e-3)
+    qn[200:230] *= -1                 # a stretch seen from below: other photons face it
+    qn[400] = [1, 0, 0]
+    for k, md_ in ((500, 1e10), (60, 1e10), (60, 0.05), (1, 1e10)):
+        c = S.photon_gather(0, q, qn, md_, k)
+        e = knn_estimate(ph, q, qn, md_, k)
+        assert np.allclose(c, e, rtol=2e-5, atol=0), (k, md_, float(np.abs(c - e).max()))
+        assert c.max() > 0
+    # exactly k facing photons in the whole map: never an overflow, the estimate divides by max_dist^2
+    few = 40
+    pw2, pos2, d2 = _photon_cloud(few, 13)
+    d2[:, 1] = -np.abs(d2[:, 1]) - 0.1
+    w2 = oracle.pm_new(few)
+    oracle.pm_store(w2, pw2, pos2, d2); oracle.pm_scale(w2, 1.0 / few); oracle.pm_balance(w2)
+    ph2 = oracle.pm_dump(w2)
+    S.photon_upload(1, ph2)
+    qn2 = np.tile(np.array([[0, 1, 0]], np.float32), (nq, 1))
+    e = knn_estimate(ph2, q, qn2, 1e3, few)
+    reach = int((e != 0).any(axis=1).sum())
+    for k in (few, few - 3, few - 9):
+        c = S.photon_gather(1, q, qn2, 1e3, k)
+        assert np.allclose(c, knn_estimate(ph2, q, qn2, 1e3, k), rtol=2e-5, atol=0), k
+    assert reach > 0
+
+
 def test_render_with_photon_maps(pkg, scenes, oracle):
     """Config 5's gather inside the frame: irradiance of both maps added at diffuse hits (Scene.cpp:286-299)."""
     H, S = build_pair(pkg, scenes, oracle, "cornell")
