@@ -205,7 +205,8 @@ __global__ void __launch_bounds__(128, MINB) k_trace_hybrid(DeviceScene s, const
                         else bvh2_node_step<PF>(s.nodes, s.tris, r, w, stack, best);
                     }
             } else if (w.node < 0 && w.node != MIRO_BVH2_DONE) {
-                bvh2_leaf_step<ANY>(s.tris, r, w, stack, best);
+                if (PF & 16) bvh2_leaf_step_one<ANY>(s.tris, r, w, stack, best);
+                else bvh2_leaf_step<ANY>(s.tris, r, w, stack, best);
             }
             if (w.node == MIRO_BVH2_DONE && ((mn | ml) >> lane & 1u)) store_hit(hits, my, best);
         }

@@ -358,6 +358,20 @@ MIRO_HD void bvh2_leaf_step(const float4* __restrict__ tris, const mirogpu_ray& 
     bvh2_pop(w, stack);
 }
 
+// One triangle of the leaf per call; a leaf with more stays the lane's node (first + 1, count - 1), so the warp's next vote
+// decides again between node steps and another leaf phase and a leaf phase never loops over the longest leaf of the warp.
+template <bool ANY>
+MIRO_HD void bvh2_leaf_step_one(const float4* __restrict__ tris, const mirogpu_ray& r, Bvh2Walk& w, const int32_t* __restrict__ stack,
+                                BestHit& best)
+{
+    const uint32_t ref = (uint32_t)~w.node;
+    const uint32_t first = ref >> 3;
+    const F8 ta = ld256(tris + 4 * (size_t)first), tb = ld256(tris + 4 * (size_t)first + 2);
+    const bool acc = tri_test(ta.lo, ta.hi, tb.lo, tb.hi, r, best);
+    if (ANY && acc) { w.node = MIRO_BVH2_DONE; return; }
+    if (ref & 7u) w.node = (int32_t)~(ref + 7u);   // first + 1 (ref + 8), count - 1 (ref - 1)
+    else bvh2_pop(w, stack);
+}
 
 // Child order of the four-wide layouts: a three-comparator tournament on (entry distance, link) finds the nearest hit
 // child, which is descended next; the two first-round losers are pushed first and the runner-up of the final last, so
