@@ -246,10 +246,19 @@ struct SurfacePoint {
 
 // Triangle.cpp:160-162 then Scene::trace's normalisation (Scene.cpp:262; all materials are UV-lookup Phong
 // with zero bump height, so the perturbation term is exactly zero).
-__device__ __forceinline__ SurfacePoint resolve_hit(const DeviceScene& s, const mirogpu_hit& h)
+struct ShadeRecord {   // 96 bytes, 32-byte aligned: three 256-bit loads (three L1 wavefronts for a divergent warp instead of six)
+    F8 r0, r1, r2;
+};
+__device__ __forceinline__ ShadeRecord load_shade_record(const DeviceScene& s, uint32_t prim)
 {
-    const float4* q = s.shade + 6 * (size_t)h.prim_id;
-    const float4 A = __ldg(q), e1 = __ldg(q + 1), e2 = __ldg(q + 2), nA = __ldg(q + 3), nB = __ldg(q + 4), nC = __ldg(q + 5);
+    const float4* q = s.shade + 6 * (size_t)prim;
+    ShadeRecord r;
+    r.r0 = ld256(q); r.r1 = ld256(q + 2); r.r2 = ld256(q + 4);
+    return r;
+}
+__device__ __forceinline__ SurfacePoint resolve_hit(const ShadeRecord& rec, const mirogpu_hit& h)
+{
+    const float4 A = rec.r0.lo, e1 = rec.r0.hi, e2 = rec.r1.lo, nA = rec.r1.hi, nB = rec.r2.lo, nC = rec.r2.hi;
     SurfacePoint sp;
     sp.P[0] = xadd(xadd(A.x, xmul(e1.x, h.beta)), xmul(e2.x, h.gamma));
     sp.P[1] = xadd(xadd(A.y, xmul(e1.y, h.beta)), xmul(e2.y, h.gamma));
@@ -263,6 +272,10 @@ __device__ __forceinline__ SurfacePoint resolve_hit(const DeviceScene& s, const 
     sp.N[0] = xmul(n[0], inv); sp.N[1] = xmul(n[1], inv); sp.N[2] = xmul(n[2], inv);
     sp.material = __float_as_uint(A.w);
     return sp;
+}
+__device__ __forceinline__ SurfacePoint resolve_hit(const DeviceScene& s, const mirogpu_hit& h)
+{
+    return resolve_hit(load_shade_record(s, h.prim_id), h);
 }
 
 __global__ void __launch_bounds__(256) k_resolve_hits(DeviceScene s, const mirogpu_hit* __restrict__ hits, size_t n,
@@ -286,7 +299,8 @@ __global__ void __launch_bounds__(256) k_resolve_hits(DeviceScene s, const mirog
 // generated bounce rays are compared with a tolerance and hit parity is checked on the dumped rays.
 __device__ __forceinline__ void align_hemisphere(const float v[3], float theta, float phi, float out[3])
 {
-    const float sp = sinf(phi), cp = cosf(phi), st = sinf(theta), ct = cosf(theta);
+    float sp, cp, st, ct;
+    sincosf(phi, &sp, &cp); sincosf(theta, &st, &ct);   // one range reduction per angle
     const float u1 = xmul(sp, ct), u2 = xmul(sp, st), u3 = cp;
     // t1 = cross((0,0,1), v)
     float t1[3] = {xsub(xmul(0.f, v[2]), xmul(1.f, v[1])), xsub(xmul(1.f, v[0]), xmul(0.f, v[2])), xsub(xmul(0.f, v[1]), xmul(0.f, v[0]))};
@@ -308,36 +322,58 @@ __device__ __forceinline__ void align_hemisphere(const float v[3], float theta, 
 }
 
 // Ray::diffuse, Ray.h:109-122, with (u1,u2) from the counter RNG in place of rand().
-__global__ void __launch_bounds__(256) k_gen_bounce(DeviceScene s, const mirogpu_ray* __restrict__ rays,
-                                                     const mirogpu_hit* __restrict__ hits, size_t n, uint32_t seed, uint32_t sample,
-                                                     uint32_t index_base, mirogpu_ray* __restrict__ out, unsigned long long* live_count)
+#define MIRO_GENB_THREADS 128
+// Two hits per thread (i and i + 128 of a 256-item tile): the kernel is a chain of two dependent fetches (the hit, then the
+// 96-byte shading record it names) in front of ~300 instructions, so it runs at the latency of those fetches; both hits
+// and then both records are requested before anything is computed.
+template <int MIRO_GENB_ITEMS>
+__global__ void __launch_bounds__(MIRO_GENB_THREADS) k_gen_bounce(DeviceScene s, const mirogpu_ray* __restrict__ rays,
+                                                                   const mirogpu_hit* __restrict__ hits, size_t n, uint32_t seed, uint32_t sample,
+                                                                   uint32_t index_base, mirogpu_ray* __restrict__ out, unsigned long long* live_count)
 {
-    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    float4 hv = make_float4(0.f, __uint_as_float(MIROGPU_MISS), 0.f, 0.f);
-    if (i < n) hv = __ldg(reinterpret_cast<const float4*>(hits + i));
-    mirogpu_hit h; h.t = hv.x; h.prim_id = __float_as_uint(hv.y); h.beta = hv.z; h.gamma = hv.w;
+    const size_t base = (size_t)blockIdx.x * (MIRO_GENB_THREADS * MIRO_GENB_ITEMS) + threadIdx.x;
+    mirogpu_hit h[MIRO_GENB_ITEMS];
+#pragma unroll
+    for (int k = 0; k < MIRO_GENB_ITEMS; ++k) {
+        const size_t i = base + (size_t)k * MIRO_GENB_THREADS;
+        float4 hv = make_float4(0.f, __uint_as_float(MIROGPU_MISS), 0.f, 0.f);
+        if (i < n) hv = __ldcs(reinterpret_cast<const float4*>(hits + i));
+        h[k].t = hv.x; h[k].prim_id = __float_as_uint(hv.y); h[k].beta = hv.z; h[k].gamma = hv.w;
+    }
+    ShadeRecord rec[MIRO_GENB_ITEMS];
+#pragma unroll
+    for (int k = 0; k < MIRO_GENB_ITEMS; ++k) {
+        if (h[k].prim_id != MIROGPU_MISS) rec[k] = load_shade_record(s, h[k].prim_id);
+        else rec[k].r0.lo = rec[k].r0.hi = rec[k].r1.lo = rec[k].r1.hi = rec[k].r2.lo = rec[k].r2.hi = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
     if (live_count) {   // one atomic per warp
-        const unsigned live = __ballot_sync(0xffffffffu, h.prim_id != MIROGPU_MISS);
-        if ((threadIdx.x & 31) == 0 && live) atomicAdd(live_count, (unsigned long long)__popc(live));
+        unsigned cnt = 0;
+#pragma unroll
+        for (int k = 0; k < MIRO_GENB_ITEMS; ++k) cnt += __popc(__ballot_sync(0xffffffffu, h[k].prim_id != MIROGPU_MISS));
+        if ((threadIdx.x & 31) == 0 && cnt) atomicAdd(live_count, (unsigned long long)cnt);
     }
-    if (i >= n) return;
-    float4 a, b;
-    if (h.prim_id == MIROGPU_MISS) {
-        a = make_float4(0.f, 0.f, 0.f, 0.f); b = make_float4(0.f, 0.f, 1.f, -1.0f);  // tmax < tmin: never hits
-    } else {
-        const SurfacePoint sp = resolve_hit(s, h);
-        float u1, u2;
-        uniform2(seed, index_base + (uint32_t)i, sample, RNG_DIM_BOUNCE, u1, u2);
-        const float phi = asinf(sqrtf(u1));
-        const float theta = xmul(xmul(2.0f, MIRO_PI), u2);
-        float d[3];
-        align_hemisphere(sp.N, theta, phi, d);
-        a.x = xadd(sp.P[0], xmul(d[0], MIRO_EPS)); a.y = xadd(sp.P[1], xmul(d[1], MIRO_EPS)); a.z = xadd(sp.P[2], xmul(d[2], MIRO_EPS));
-        a.w = 0.0f;
-        b.x = d[0]; b.y = d[1]; b.z = d[2]; b.w = MIROGPU_TMAX;
+#pragma unroll
+    for (int k = 0; k < MIRO_GENB_ITEMS; ++k) {
+        const size_t i = base + (size_t)k * MIRO_GENB_THREADS;
+        if (i >= n) continue;
+        float4 a, b;
+        if (h[k].prim_id == MIROGPU_MISS) {
+            a = make_float4(0.f, 0.f, 0.f, 0.f); b = make_float4(0.f, 0.f, 1.f, -1.0f);  // tmax < tmin: never hits
+        } else {
+            const SurfacePoint sp = resolve_hit(rec[k], h[k]);
+            float u1, u2;
+            uniform2(seed, index_base + (uint32_t)i, sample, RNG_DIM_BOUNCE, u1, u2);
+            const float phi = asinf(sqrtf(u1));
+            const float theta = xmul(xmul(2.0f, MIRO_PI), u2);
+            float d[3];
+            align_hemisphere(sp.N, theta, phi, d);
+            a.x = xadd(sp.P[0], xmul(d[0], MIRO_EPS)); a.y = xadd(sp.P[1], xmul(d[1], MIRO_EPS)); a.z = xadd(sp.P[2], xmul(d[2], MIRO_EPS));
+            a.w = 0.0f;
+            b.x = d[0]; b.y = d[1]; b.z = d[2]; b.w = MIROGPU_TMAX;
+        }
+        float4* o = reinterpret_cast<float4*>(out + i);
+        __stcs(o, a); __stcs(o + 1, b);
     }
-    float4* o = reinterpret_cast<float4*>(out + i);
-    o[0] = a; o[1] = b;
 }
 
 }  // namespace mirogpu

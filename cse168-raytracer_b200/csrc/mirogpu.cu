@@ -583,8 +583,16 @@ int mirogpu_generate_bounce_device(mirogpu_handle h, const mirogpu_ray* d_rays, 
     if (!h || (n && (!d_rays || !d_hits || !d_out))) return fail(MIROGPU_ERR_INVALID_ARG, "NULL argument");
     if (n == 0) return MIROGPU_OK;
     CUDA_TRY(cudaSetDevice(h->device));
-    k_gen_bounce<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)cuda_stream>>>(h->ds, d_rays, d_hits, n, seed, sample, index_base,
-                                                                                       d_out, d_live_count);
+    static const int items = getenv("MIROGPU_GENB_ITEMS") ? atoi(getenv("MIROGPU_GENB_ITEMS")) : 2;   // tuning knob: hits per thread
+    const cudaStream_t st = (cudaStream_t)cuda_stream;
+#define MIRO_GENB(K)                                                                                                              \
+    {                                                                                                                             \
+        const size_t tile = (size_t)MIRO_GENB_THREADS * K;                                                                        \
+        k_gen_bounce<K><<<(unsigned)((n + tile - 1) / tile), MIRO_GENB_THREADS, 0, st>>>(h->ds, d_rays, d_hits, n, seed, sample, \
+                                                                                         index_base, d_out, d_live_count);      \
+    }
+    if (items == 1) MIRO_GENB(1) else if (items == 3) MIRO_GENB(3) else if (items == 4) MIRO_GENB(4) else MIRO_GENB(2)
+#undef MIRO_GENB
     CUDA_TRY(cudaGetLastError());
     return MIROGPU_OK;
 }

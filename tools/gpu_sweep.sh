@@ -11,7 +11,7 @@ while read -r label rest; do
   python - "$label" <<'PY'
 import json, sys
 d = json.load(open('gpurun_out/bench_x.json'))
-print(sys.argv[1], 'value', round(d['value']), 'primary', round(d['config']['primary_mrays_s']), 'bounce', round(d['config']['bounce_mrays_s']),
+print(sys.argv[1], "value", round(d["value"]), "ms_step", round(d["ms_per_step"], 3), 'primary', round(d['config']['primary_mrays_s']), 'bounce', round(d['config']['bounce_mrays_s']),
       'e2e', round(d['e2e']['value']), 'nodes', d['config']['nodes'], 'build_s', round(d['config']['build_s'], 3))
 PY
 done
