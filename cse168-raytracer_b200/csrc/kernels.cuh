@@ -323,9 +323,9 @@ __device__ __forceinline__ void align_hemisphere(const float v[3], float theta, 
 
 // Ray::diffuse, Ray.h:109-122, with (u1,u2) from the counter RNG in place of rand().
 #define MIRO_GENB_THREADS 128
-// Two hits per thread (i and i + 128 of a 256-item tile): the kernel is a chain of two dependent fetches (the hit, then the
-// 96-byte shading record it names) in front of ~300 instructions, so it runs at the latency of those fetches; both hits
-// and then both records are requested before anything is computed.
+// MIRO_GENB_ITEMS hits per thread (i, i + 128, ... of a tile; 4 by default): the kernel is a chain of two dependent fetches (the
+// hit, then the 96-byte shading record it names) in front of ~300 instructions, so it runs at the latency of those fetches; all
+// hits and then all records of the thread are requested before anything is computed.
 template <int MIRO_GENB_ITEMS>
 __global__ void __launch_bounds__(MIRO_GENB_THREADS) k_gen_bounce(DeviceScene s, const mirogpu_ray* __restrict__ rays,
                                                                    const mirogpu_hit* __restrict__ hits, size_t n, uint32_t seed, uint32_t sample,

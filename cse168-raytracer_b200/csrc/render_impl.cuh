@@ -107,11 +107,10 @@ __device__ __forceinline__ bool push_item(const WaveParams& p, Queue& next, uint
 }
 
 // Returns true when the item wrote its (single) child in place -- diffuse-bounce mode only.
-__device__ __forceinline__ bool shade_item(const WaveParams& p, const Queue& cur, uint32_t i, Queue& next, uint32_t* next_count, uint32_t* dropped,
-                                           mirogpu_ray* shadow_rays, float4* shadow_cd, float4* shadow_ch, float* accum, float* gather_pos,
-                                           float* gather_nrm, float4* gather_w)
+__device__ __forceinline__ bool shade_item(const WaveParams& p, const Queue& cur, uint32_t i, const float4 hv, const ShadeRecord& rec, Queue& next,
+                                           uint32_t* next_count, uint32_t* dropped, mirogpu_ray* shadow_rays, float4* shadow_cd, float4* shadow_ch,
+                                           float* accum, float* gather_pos, float* gather_nrm, float4* gather_w)
 {
-    const float4 hv = __ldg(reinterpret_cast<const float4*>(cur.hits + i));
     const float4 w = cur.weight[i];
     const uint32_t lpix = cur.pix[i];
     const uint32_t sb = unpack_sample(w.w);
@@ -129,7 +128,7 @@ __device__ __forceinline__ bool shade_item(const WaveParams& p, const Queue& cur
         return false;
     }
     mirogpu_hit h; h.t = hv.x; h.prim_id = __float_as_uint(hv.y); h.beta = hv.z; h.gamma = hv.w;
-    const SurfacePoint sp = resolve_hit(p.ds, h);
+    const SurfacePoint sp = resolve_hit(rec, h);
     const mirogpu_material m = p.mats[sp.material];
     const float rd[3] = {ray.dx, ray.dy, ray.dz};
     float direct[3] = {0.f, 0.f, 0.f};
@@ -261,20 +260,42 @@ __device__ __forceinline__ bool shade_item(const WaveParams& p, const Queue& cur
 // Diffuse-bounce mode: an item has at most one child, so the child takes the item's own queue position and no slot
 // counter is touched (a single-address atomic per warp serialises at the L2 atomic unit: 520 k of them made this kernel
 // as slow as the trace it feeds); items without a child leave a dead ray (tmax < tmin) there instead.
-__global__ void __launch_bounds__(128) k_shade(WaveParams p, Queue cur, uint32_t n, const uint32_t* __restrict__ d_n, Queue next,
-                                               uint32_t* next_count, uint32_t* dropped, mirogpu_ray* shadow_rays, float4* shadow_cd,
-                                               float4* shadow_ch, float* accum, float* gather_pos, float* gather_nrm, float4* gather_w)
+// MIRO_SHADE_ITEMS items per thread (i, i + 128, ... of a tile): all hits, then all 96-byte shading records are requested before
+// any item is shaded.  Measured: 2 items per thread pay in k_gen_bounce (same fetch chain) but not here -- 96 registers and the
+// queue / accumulation atomics of two items in one thread cost more than the overlap wins (e2e 6.93 -> 6.71 Grays/s) -- so 1.
+#define MIRO_SHADE_THREADS 128
+#define MIRO_SHADE_ITEMS 1
+__global__ void __launch_bounds__(MIRO_SHADE_THREADS) k_shade(WaveParams p, Queue cur, uint32_t n, const uint32_t* __restrict__ d_n, Queue next,
+                                                              uint32_t* next_count, uint32_t* dropped, mirogpu_ray* shadow_rays, float4* shadow_cd,
+                                                              float4* shadow_ch, float* accum, float* gather_pos, float* gather_nrm, float4* gather_w)
 {
-    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    const uint32_t base = blockIdx.x * (MIRO_SHADE_THREADS * MIRO_SHADE_ITEMS) + threadIdx.x;
     if (d_n) n = min(n, *d_n);
     const bool in_place = p.mode == MIROGPU_RENDER_DIFFUSE_BOUNCE && d_n == nullptr;   // wave 0: the only one with children
-    if (in_place && i == 0) *next_count = n;
-    if (i >= n) return;
-    const bool wrote = shade_item(p, cur, i, next, next_count, dropped, shadow_rays, shadow_cd, shadow_ch, accum, gather_pos, gather_nrm, gather_w);
-    if (in_place && !wrote) {
-        float4* r = reinterpret_cast<float4*>(next.rays + i);
-        r[0] = make_float4(0.f, 0.f, 0.f, 0.0f);
-        r[1] = make_float4(0.f, 0.f, 1.f, -1.0f);
+    if (in_place && base == 0) *next_count = n;
+    float4 hv[MIRO_SHADE_ITEMS];
+    ShadeRecord rec[MIRO_SHADE_ITEMS];
+#pragma unroll
+    for (int k = 0; k < MIRO_SHADE_ITEMS; ++k) {
+        const uint32_t i = base + k * MIRO_SHADE_THREADS;
+        hv[k] = i < n ? __ldg(reinterpret_cast<const float4*>(cur.hits + i)) : make_float4(0.f, __uint_as_float(MIROGPU_MISS), 0.f, 0.f);
+    }
+#pragma unroll
+    for (int k = 0; k < MIRO_SHADE_ITEMS; ++k) {
+        if (__float_as_uint(hv[k].y) != MIROGPU_MISS) rec[k] = load_shade_record(p.ds, __float_as_uint(hv[k].y));
+        else rec[k].r0.lo = rec[k].r0.hi = rec[k].r1.lo = rec[k].r1.hi = rec[k].r2.lo = rec[k].r2.hi = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+#pragma unroll
+    for (int k = 0; k < MIRO_SHADE_ITEMS; ++k) {
+        const uint32_t i = base + k * MIRO_SHADE_THREADS;
+        if (i >= n) continue;
+        const bool wrote = shade_item(p, cur, i, hv[k], rec[k], next, next_count, dropped, shadow_rays, shadow_cd, shadow_ch, accum, gather_pos,
+                                      gather_nrm, gather_w);
+        if (in_place && !wrote) {
+            float4* r = reinterpret_cast<float4*>(next.rays + i);
+            r[0] = make_float4(0.f, 0.f, 0.f, 0.0f);
+            r[1] = make_float4(0.f, 0.f, 1.f, -1.0f);
+        }
     }
 }
 
@@ -512,7 +533,7 @@ int render_device(mirogpu_scene* h, const mirogpu_camera& cam, const mirogpu_ren
         for (int wave = 0; wave < MIRO_MAX_WAVES && wave <= rp.max_depth; ++wave) {
             const uint32_t* d_n = wave == 0 ? nullptr : counters + wave;
             RT(dispatch_trace(h, q[cur].rays, bound, q[cur].hits, MIROGPU_CLOSEST_HIT | (wave == 0 ? MIROGPU_HINT_COHERENT : 0), st, d_n, 1));
-            k_shade<<<(unsigned)((bound + 127) / 128), 128, 0, st>>>(wp, q[cur], (uint32_t)bound, d_n, q[cur ^ 1], counters + wave + 1, counters + 17,
+            k_shade<<<(unsigned)((bound + MIRO_SHADE_THREADS * MIRO_SHADE_ITEMS - 1) / (MIRO_SHADE_THREADS * MIRO_SHADE_ITEMS)), MIRO_SHADE_THREADS, 0, st>>>(wp, q[cur], (uint32_t)bound, d_n, q[cur ^ 1], counters + wave + 1, counters + 17,
                                                                       srays, scd, sch, planes, gpos, gnrm, gw);
             launches += 2;
             if (shadows) {
