@@ -265,7 +265,7 @@ __device__ __forceinline__ bool shade_item(const WaveParams& p, const Queue& cur
 // queue / accumulation atomics of two items in one thread cost more than the overlap wins (e2e 6.93 -> 6.71 Grays/s) -- so 1.
 #define MIRO_SHADE_THREADS 128
 #define MIRO_SHADE_ITEMS 1
-__global__ void __launch_bounds__(MIRO_SHADE_THREADS) k_shade(WaveParams p, Queue cur, uint32_t n, const uint32_t* __restrict__ d_n, Queue next,
+__global__ void __launch_bounds__(MIRO_SHADE_THREADS, 8) k_shade(WaveParams p, Queue cur, uint32_t n, const uint32_t* __restrict__ d_n, Queue next,
                                                               uint32_t* next_count, uint32_t* dropped, mirogpu_ray* shadow_rays, float4* shadow_cd,
                                                               float4* shadow_ch, float* accum, float* gather_pos, float* gather_nrm, float4* gather_w)
 {
