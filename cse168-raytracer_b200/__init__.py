@@ -85,6 +85,7 @@ EXPORTS = [
     "mirogpu_resolve_hits_device", "mirogpu_generate_primary_device", "mirogpu_generate_bounce_device", "mirogpu_rng_uniforms",
     "mirogpu_render", "mirogpu_render_rgb8", "mirogpu_tonemap_rgb8_device", "mirogpu_render_device", "mirogpu_last_call_stats", "mirogpu_photon_upload", "mirogpu_photon_gather",
     "mirogpu_photon_gather_device", "mirogpu_photon_trace", "mirogpu_photon_set_exact", "mirogpu_host_alloc", "mirogpu_host_free",
+    "mirogpu_frame_max_device", "mirogpu_tonemap_rows_rgb8_device",
 ]
 
 
@@ -294,6 +295,18 @@ class MiroScene:
     def tonemap_rgb8_device(self, d_rgb, d_rgb8):
         h, w = d_rgb.shape[0], d_rgb.shape[1]
         _check(lib.mirogpu_tonemap_rgb8_device(self._h, _ptr(d_rgb), int(w), int(h), _ptr(d_rgb8), _stream()))
+
+    def frame_max_device(self, d_rgb, rows, d_max):
+        """Largest non-NaN value over this shard's rows of the full-frame float buffer -> d_max (1 float, device)."""
+        h, w = d_rgb.shape[0], d_rgb.shape[1]
+        rb, re_, rs, rp = rows
+        _check(lib.mirogpu_frame_max_device(self._h, _ptr(d_rgb), int(w), int(h), int(rb), int(re_), int(rs), int(rp), _ptr(d_max), _stream()))
+
+    def tonemap_rows_rgb8_device(self, d_rgb, rows, d_max, d_rgb8):
+        """Tone map + 8-bit conversion of this shard's rows with the frame-wide maximum d_max (see mirogpu.h)."""
+        h, w = d_rgb.shape[0], d_rgb.shape[1]
+        rb, re_, rs, rp = rows
+        _check(lib.mirogpu_tonemap_rows_rgb8_device(self._h, _ptr(d_rgb), int(w), int(h), int(rb), int(re_), int(rs), int(rp), _ptr(d_max), _ptr(d_rgb8), _stream()))
 
     def render_device(self, cam, params, d_rgb):
         _check(lib.mirogpu_render_device(self._h, ctypes.byref(cam), ctypes.byref(params), _ptr(d_rgb), _stream()))

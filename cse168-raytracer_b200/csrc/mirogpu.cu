@@ -669,6 +669,40 @@ int mirogpu_tonemap_rgb8_device(mirogpu_handle h, const float* d_rgb, int width,
     return MIROGPU_OK;
 }
 
+static bool rows_ok(int width, int height, int row_begin, int row_end, int row_stride, int row_phase)
+{
+    return width > 0 && height > 0 && row_stride >= 1 && row_phase >= 0 && row_phase < row_stride && row_begin >= 0 && row_end <= height && row_begin <= row_end;
+}
+
+int mirogpu_frame_max_device(mirogpu_handle h, const float* d_rgb, int width, int height, int row_begin, int row_end, int row_stride,
+                             int row_phase, float* d_max, void* cuda_stream)
+{
+    if (!h || !d_rgb || !d_max || !rows_ok(width, height, row_begin, row_end, row_stride, row_phase)) return fail(MIROGPU_ERR_INVALID_ARG, "bad argument");
+    CUDA_TRY(cudaSetDevice(h->device));
+    cudaStream_t st = (cudaStream_t)cuda_stream;
+    const float ninf = -INFINITY;
+    CUDA_TRY(cudaMemcpyAsync(d_max, &ninf, 4, cudaMemcpyHostToDevice, st));
+    const int first_row = row_begin + row_phase;
+    const int nrows = first_row < row_end ? (row_end - first_row + row_stride - 1) / row_stride : 0;
+    const size_t nvals = (size_t)nrows * width * 3;
+    if (nvals) k_frame_max_rows<<<(unsigned)((nvals + 255) / 256), 256, 0, st>>>(d_rgb, width, first_row, row_stride, nrows, d_max);
+    CUDA_TRY(cudaGetLastError());
+    return MIROGPU_OK;
+}
+
+int mirogpu_tonemap_rows_rgb8_device(mirogpu_handle h, const float* d_rgb, int width, int height, int row_begin, int row_end,
+                                     int row_stride, int row_phase, const float* d_max, uint8_t* d_rgb8, void* cuda_stream)
+{
+    if (!h || !d_rgb || !d_max || !d_rgb8 || !rows_ok(width, height, row_begin, row_end, row_stride, row_phase)) return fail(MIROGPU_ERR_INVALID_ARG, "bad argument");
+    CUDA_TRY(cudaSetDevice(h->device));
+    const int first_row = row_begin + row_phase;
+    const int nrows = first_row < row_end ? (row_end - first_row + row_stride - 1) / row_stride : 0;
+    const size_t nvals = (size_t)nrows * width * 3;
+    if (nvals) k_tonemap<<<(unsigned)((nvals + 255) / 256), 256, 0, (cudaStream_t)cuda_stream>>>(const_cast<float*>(d_rgb), d_rgb8, width, first_row, row_stride, nrows, d_max);
+    CUDA_TRY(cudaGetLastError());
+    return MIROGPU_OK;
+}
+
 int mirogpu_photon_trace(mirogpu_handle h, int light_index, int caustic, uint32_t seed, uint64_t first_emission, uint32_t count,
                          uint8_t* counts, float* records)
 {

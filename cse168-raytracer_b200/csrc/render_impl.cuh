@@ -404,6 +404,33 @@ __global__ void __launch_bounds__(256) k_tonemap(float* rgb, unsigned char* rgb8
     else rgb[o] = v;
 }
 
+// Largest non-NaN value over rows row_begin + j*row_stride of a full-frame buffer (atomic max into *gmax).
+__global__ void __launch_bounds__(256) k_frame_max_rows(const float* __restrict__ rgb, int width, int row_begin, int row_stride, int nrows_local, float* gmax)
+{
+    const size_t n = (size_t)nrows_local * width * 3;
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    float v = -INFINITY;
+    if (i < n) {
+        const size_t per_row = (size_t)width * 3;
+        const float a = rgb[((size_t)row_begin + (i / per_row) * (size_t)row_stride) * per_row + i % per_row];
+        if (a == a) v = a;
+    }
+    for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_down_sync(0xffffffffu, v, o));
+    __shared__ float sm[8];
+    if ((threadIdx.x & 31) == 0) sm[threadIdx.x >> 5] = v;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (int k = 1; k < 8; ++k) v = fmaxf(v, sm[k]);
+        unsigned int* g = reinterpret_cast<unsigned int*>(gmax);
+        unsigned int old = *g;
+        while (v > __uint_as_float(old)) {
+            const unsigned int assumed = old;
+            old = atomicCAS(g, assumed, __float_as_uint(v));
+            if (old == assumed) break;
+        }
+    }
+}
+
 __global__ void __launch_bounds__(256) k_frame_max(const float* __restrict__ rgb, size_t n, float* gmax)
 {
     const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;

@@ -42,6 +42,34 @@ def gather_rows(local_rows, height, world, rank, out=None, group=None):
     return out
 
 
+class RowGather:
+    """gather_rows with its buffers allocated once (one per frame size / dtype): the per-frame cost is one copy of this
+    rank's rows into the send buffer, one all_gather_into_tensor, and one strided copy that puts the rows back in frame order."""
+
+    def __init__(self, height, width, channels, dtype, device, world, rank, group=None):
+        self.height, self.world, self.rank, self.group = height, world, rank, group
+        self.nmax = max_rows(height, world)
+        self.send = torch.zeros((self.nmax, width, channels), dtype=dtype, device=device)
+        self.recv = torch.empty((world * self.nmax, width, channels), dtype=dtype, device=device)
+        self.out = torch.empty((height, width, channels), dtype=dtype, device=device)
+
+    def __call__(self, frame):
+        """frame: full-frame tensor whose rows rank::world are valid on this rank.  Returns the complete frame."""
+        if self.world == 1:
+            return frame
+        mine = frame[self.rank::self.world]
+        self.send[: mine.shape[0]].copy_(mine)
+        dist.all_gather_into_tensor(self.recv, self.send, group=self.group)
+        if self.height % self.world == 0:      # every shard has nmax rows: one strided copy
+            self.out.view(self.nmax, self.world, *self.out.shape[1:]).copy_(self.recv.view(self.world, self.nmax, *self.out.shape[1:]).transpose(0, 1))
+        else:
+            recv = self.recv.view(self.world, self.nmax, *self.out.shape[1:])
+            for r in range(self.world):
+                k = len(range(r, self.height, self.world))
+                self.out[r::self.world].copy_(recv[r, :k])
+        return self.out
+
+
 def reduce_max(value, group=None):
     """Max over ranks of one float (the NaN-replacement intensity of the tone map, Scene.cpp:157-164)."""
     if not dist.is_initialized() or dist.get_world_size(group) == 1:

@@ -237,6 +237,16 @@ int mirogpu_render(mirogpu_handle h, const mirogpu_camera* cam, const mirogpu_re
 int mirogpu_render_rgb8(mirogpu_handle h, const mirogpu_camera* cam, const mirogpu_render_params* p, uint8_t* rgb8_out);
 /* Tone map + 8-bit conversion of a complete DEVICE float frame (after a multi-GPU gather). */
 int mirogpu_tonemap_rgb8_device(mirogpu_handle h, const float* d_rgb, int width, int height, uint8_t* d_rgb8, void* cuda_stream);
+/* The same tone map for a frame whose rows are sharded over several GPUs, in two steps around the one exchange it needs: the
+ * largest non-NaN value of the frame replaces NaN pixels (Scene.cpp:157-164), so each rank reduces its own rows
+ * (mirogpu_frame_max_device -> *d_max, -inf if it has none), the ranks combine the values (one float, max), and each rank
+ * maps its own rows to 8 bits with the combined value (mirogpu_tonemap_rows_rgb8_device).  Rows are those of a render call:
+ * row_begin + row_phase + j * row_stride < row_end.  d_rgb and d_rgb8 are full-frame DEVICE buffers; only those rows are
+ * read / written. */
+int mirogpu_frame_max_device(mirogpu_handle h, const float* d_rgb, int width, int height, int row_begin, int row_end, int row_stride,
+                             int row_phase, float* d_max, void* cuda_stream);
+int mirogpu_tonemap_rows_rgb8_device(mirogpu_handle h, const float* d_rgb, int width, int height, int row_begin, int row_end,
+                                     int row_stride, int row_phase, const float* d_max, uint8_t* d_rgb8, void* cuda_stream);
 /* d_rgb: DEVICE buffer of the same shape.  rays_traced (host, may be NULL) receives the ray count after
  * the stream is synchronised by the caller only if sync != 0. */
 int mirogpu_render_device(mirogpu_handle h, const mirogpu_camera* cam, const mirogpu_render_params* p, float* d_rgb,

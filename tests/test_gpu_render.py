@@ -62,6 +62,20 @@ def test_whitted_render_matches_reference_semantics(pkg, scenes, oracle, name, s
     S.tonemap_rgb8_device(d_rgb, d_u8)
     torch.cuda.synchronize()
     assert np.array_equal(d_u8.cpu().numpy(), u8b)
+    # the tone map of a frame sharded by rows: per-shard maxima, combined (what the ranks all-reduce), then per-shard mapping
+    d_rgb[h // 3, w // 2, 1] = float("nan")                    # a NaN pixel takes the frame-wide maximum (Scene.cpp:157-164)
+    S.tonemap_rgb8_device(d_rgb, d_u8)
+    whole = d_u8.cpu().numpy().copy()
+    d_m = torch.empty(3, dtype=torch.float32, device="cuda"); d_u8.zero_()
+    shards = [(0, h, 3, r) for r in range(3)]
+    for r, rows in enumerate(shards):
+        S.frame_max_device(d_rgb, rows, d_m[r:r + 1])
+    d_all = d_m.max().reshape(1)
+    assert float(d_all) == float(np.nanmax(d_rgb.cpu().numpy()))
+    for rows in shards:
+        S.tonemap_rows_rgb8_device(d_rgb, rows, d_all, d_u8)
+    torch.cuda.synchronize()
+    assert np.array_equal(d_u8.cpu().numpy(), whole)
     # no shadows == the reference's -DDISABLE_SHADOWS build: brighter or equal everywhere
     p2 = S.render_params(w, h, mode=pkg.RENDER_WHITTED, tonemap=0, shadows=0)
     img2 = S.render(H.camera(), p2)

@@ -28,6 +28,14 @@ WORKER = textwrap.dedent('''
     assert torch.equal(got, full), "gathered frame differs"
     got8 = sh.gather_rows((local %% 251).to(torch.uint8), H, world, rank)
     assert torch.equal(got8, (full %% 251).to(torch.uint8))
+    # the preallocated gather of bench.py's e2e path: the frame holds this rank's rows, junk elsewhere; both row-count cases
+    for hh in (H, 6 * world):
+        ref = (torch.arange(hh * W * 3, dtype=torch.int64).reshape(hh, W, 3) %% 251).to(torch.uint8)
+        g = sh.RowGather(hh, W, 3, torch.uint8, "cpu", world, rank)
+        for rep in range(2):
+            frame = torch.full((hh, W, 3), 7, dtype=torch.uint8)
+            frame[rank::world] = ref[rank::world]
+            assert torch.equal(g(frame), ref), "RowGather frame differs"
     m = sh.reduce_max(torch.tensor([float(rank) + 0.5]))
     assert float(m) == world - 0.5
     # every row is owned by exactly one rank
