@@ -158,6 +158,23 @@ def cpu_leg(rays_p, rays_b, want_counters=True, kind_pref="reference"):
                       sample=f"{rays_p.shape[0]} primary + {rays_b.shape[0]} live bounce rays = one whole step ({SPP} samples of {WIDTH}x{HEIGHT}, the GPU's own rays), "
                              f"Scene::trace over OpenMP dynamic chunks of 4096; reference BVH build {build_s:.1f} s not timed",
                       seconds=secs)
+    # also the reference's shipped configuration (-msse4.1: 4-wide box tests with _mm_rcp_ps, triangle packets; not
+    # parity grade) as a second throughput baseline on the same rays
+    if kind == "reference" and os.path.exists(md.REF_SSE_SO):
+        E = md.reference("sse")
+        devnull = os.open(os.devnull, os.O_WRONLY)
+        saved = os.dup(1)
+        os.dup2(devnull, 1)
+        try:
+            scenes.realise(E, SCENE, objio.obj_path)
+            E.precalc()
+            E.trace_time(rays[:100000], 0)
+            secs_sse, _ = E.trace_time(rays, 0)
+        finally:
+            os.dup2(saved, 1)
+            os.close(devnull)
+        out["cpu"]["sse_build"] = dict(value=rays.shape[0] / secs_sse / 1e6, unit="Mrays/s", seconds=secs_sse,
+                                       note="the reference compiled with -msse4.1 (Makedefs:14-15), same rays, same threads")
     if want_counters:
         O = D if kind == "port" else md.oracle()
         if kind != "port":
