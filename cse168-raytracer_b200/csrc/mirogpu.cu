@@ -111,7 +111,7 @@ cudaError_t launch_hybrid(mirogpu_scene* h, const mirogpu_ray* d_rays, size_t n,
                           cudaStream_t st, const uint32_t* d_n, uint32_t mult)
 {
 #define MIRO_HYB(PF, MINB, NREP) if (h->hyb_pf == PF && h->hyb_minb == MINB && h->hyb_nrep == NREP) return launch_hybrid_inst<LAYOUT, ANY, PF, MINB, NREP>(h, d_rays, n, d_hits, ticket, st, d_n, mult);
-    MIRO_HYB(0, 9, 2) MIRO_HYB(0, 8, 2) MIRO_HYB(0, 9, 1) MIRO_HYB(0, 9, 3) MIRO_HYB(16, 9, 2) MIRO_HYB(16, 9, 3) MIRO_HYB(16, 9, 1) MIRO_HYB(16, 9, 4)
+    MIRO_HYB(0, 9, 2) MIRO_HYB(0, 8, 2) MIRO_HYB(0, 9, 1) MIRO_HYB(0, 9, 3) MIRO_HYB(16, 9, 2) MIRO_HYB(16, 9, 3)
 #undef MIRO_HYB
     return LAYOUT == MIROGPU_LAYOUT_QBVH4 ? launch_hybrid_inst<LAYOUT, ANY, 16, 9, 3>(h, d_rays, n, d_hits, ticket, st, d_n, mult)
                                           : launch_hybrid_inst<LAYOUT, ANY, 0, 9, 2>(h, d_rays, n, d_hits, ticket, st, d_n, mult);
