@@ -218,12 +218,14 @@ __global__ void __launch_bounds__(256) k_gen_primary(CameraBasis cb, int width, 
                                                       int nrows_local, int jitter, uint32_t seed, uint32_t sample_begin,
                                                       uint32_t sample_count, mirogpu_ray* __restrict__ rays)
 {
-    const size_t npix = (size_t)nrows_local * width;
-    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= npix * sample_count) return;
-    const uint32_t s = (uint32_t)(i / npix);
-    const size_t lp = i - (size_t)s * npix;
-    const int x = (int)(lp % width), y = first_row + (int)(lp / width) * row_stride;
+    // grid: x over the shard's pixels, y over the samples -- 32-bit index arithmetic (one division), no 64-bit div / mod
+    const uint32_t npix = (uint32_t)nrows_local * (uint32_t)width;
+    const uint32_t lp = blockIdx.x * blockDim.x + threadIdx.x;
+    if (lp >= npix) return;
+    const uint32_t s = blockIdx.y;
+    const size_t i = (size_t)s * npix + lp;
+    const uint32_t row = lp / (uint32_t)width;
+    const int x = (int)(lp - row * (uint32_t)width), y = first_row + (int)row * row_stride;
     float dx = 0.5f, dy = 0.5f;
     if (jitter) uniform2(seed, (uint32_t)((size_t)y * width + x), sample_begin + s, RNG_DIM_PIXEL, dx, dy);
     const float U = xadd(cb.left, xmul(xsub(cb.right, cb.left), xdiv(xadd((float)x, dx), (float)width)));

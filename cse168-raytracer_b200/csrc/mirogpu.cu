@@ -570,8 +570,13 @@ int mirogpu_generate_primary_device(mirogpu_handle h, const mirogpu_camera* cam,
     CUDA_TRY(cudaSetDevice(h->device));
     CameraBasis cb;
     camera_basis(*cam, width, height, cb);
-    k_gen_primary<<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)cuda_stream>>>(cb, width, height, first_row, row_stride, nrows,
-                                                                                            jitter, seed, sample_begin, sample_count, d_rays);
+    const size_t npix = (size_t)nrows * width;
+    if (npix >= (1ull << 31)) return fail(MIROGPU_ERR_UNSUPPORTED, "frame too large");
+    for (uint32_t s0 = 0; s0 < sample_count; s0 += 65535u) {   // grid y carries the sample index
+        const uint32_t ns = std::min(sample_count - s0, 65535u);
+        k_gen_primary<<<dim3((unsigned)((npix + 255) / 256), ns), 256, 0, (cudaStream_t)cuda_stream>>>(cb, width, height, first_row, row_stride, nrows, jitter, seed,
+                                                                                                     sample_begin + s0, ns, d_rays + (size_t)s0 * npix);
+    }
     CUDA_TRY(cudaGetLastError());
     return MIROGPU_OK;
 }

@@ -50,12 +50,14 @@ __global__ void __launch_bounds__(256) k_render_primary(CameraBasis cb, int widt
                                                          int nrows_local, int jitter, uint32_t seed, uint32_t sample_base, uint32_t nsamples,
                                                          int max_depth, Queue q)
 {
-    const size_t npix = (size_t)nrows_local * width;
-    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= npix * nsamples) return;
-    const uint32_t sb = (uint32_t)(i / npix);
-    const size_t lp = i - (size_t)sb * npix;
-    const int x = (int)(lp % width), y = row_begin + (int)(lp / width) * row_stride;
+    // grid: x over the shard's pixels, y over the samples of the batch (32-bit index arithmetic)
+    const uint32_t npix = (uint32_t)nrows_local * (uint32_t)width;
+    const uint32_t lp = blockIdx.x * blockDim.x + threadIdx.x;
+    if (lp >= npix) return;
+    const uint32_t sb = blockIdx.y;
+    const size_t i = (size_t)sb * npix + lp;
+    const uint32_t row = lp / (uint32_t)width;
+    const int x = (int)(lp - row * (uint32_t)width), y = row_begin + (int)row * row_stride;
     float dx = 0.5f, dy = 0.5f;
     if (jitter) uniform2(seed, (uint32_t)((size_t)y * width + x), sample_base + sb, RNG_DIM_PIXEL, dx, dy);
     const float U = xadd(cb.left, xmul(xsub(cb.right, cb.left), xdiv(xadd((float)x, dx), (float)width)));
@@ -553,7 +555,7 @@ int render_device(mirogpu_scene* h, const mirogpu_camera& cam, const mirogpu_ren
         RT(cudaMemsetAsync(planes, 0, items * 12, st));
         RT(cudaMemsetAsync(counters, 0, 18 * 4, st));
         int cur = 0;
-        k_render_primary<<<(unsigned)((items + 255) / 256), 256, 0, st>>>(cb, rp.width, rp.height, first_row, rp.row_stride, nrows, rp.jitter, rp.seed,
+        k_render_primary<<<dim3((unsigned)((npix + 255) / 256), nb), 256, 0, st>>>(cb, rp.width, rp.height, first_row, rp.row_stride, nrows, rp.jitter, rp.seed,
                                                                            s0, nb, rp.max_depth, q[cur]);
         launches++;
         size_t bound = items;
