@@ -24,7 +24,7 @@ LIB_PATH = os.path.join(_PKG, "libmirogpu.so")
 MISS = 0xFFFFFFFF
 TMAX = np.float32(1e12)
 LAYOUT_BVH2, LAYOUT_CWBVH8, LAYOUT_BVH4, LAYOUT_QBVH4 = 0, 1, 2, 3
-BUILDER_SAH_HOST, BUILDER_LBVH_DEVICE = 0, 1
+BUILDER_SAH_HOST, BUILDER_LBVH_DEVICE, BUILDER_PLOC_DEVICE = 0, 1, 2
 CLOSEST_HIT, ANY_HIT = 0, 1
 HINT_COHERENT = 0x100   # or-ed into a query mode: camera-like batch -> packet kernel
 RENDER_WHITTED, RENDER_DIFFUSE_BOUNCE, RENDER_PRIMARY_ONLY = 0, 1, 2
@@ -85,7 +85,7 @@ EXPORTS = [
     "mirogpu_resolve_hits_device", "mirogpu_generate_primary_device", "mirogpu_generate_bounce_device", "mirogpu_rng_uniforms",
     "mirogpu_render", "mirogpu_render_rgb8", "mirogpu_tonemap_rgb8_device", "mirogpu_render_device", "mirogpu_last_call_stats", "mirogpu_photon_upload", "mirogpu_photon_gather",
     "mirogpu_photon_gather_device", "mirogpu_photon_trace", "mirogpu_photon_set_exact", "mirogpu_host_alloc", "mirogpu_host_free",
-    "mirogpu_frame_max_device", "mirogpu_tonemap_rows_rgb8_device",
+    "mirogpu_frame_max_device", "mirogpu_tonemap_rows_rgb8_device", "mirogpu_release_build_scratch",
 ]
 
 
@@ -99,6 +99,7 @@ def _load():
     lib.mirogpu_host_alloc.restype = ctypes.c_void_p
     lib.mirogpu_host_alloc.argtypes = [ctypes.c_size_t]
     lib.mirogpu_host_free.argtypes = [ctypes.c_void_p]
+    lib.mirogpu_release_build_scratch.restype = None
     return lib
 
 

@@ -21,6 +21,7 @@
 #define MIROGPU_LBVH_IMPL_CUH
 
 #include <cub/device/device_radix_sort.cuh>
+#include <cub/device/device_scan.cuh>
 
 namespace mirogpu {
 
@@ -137,13 +138,14 @@ __global__ void __launch_bounds__(256) k_lbvh_hierarchy(int n, const unsigned lo
 
 __global__ void __launch_bounds__(256) k_lbvh_refit(int n, const uint32_t* __restrict__ idx, const float4* __restrict__ blo, const float4* __restrict__ bhi,
                                                      const int2* __restrict__ child, const int* __restrict__ parent, float4* __restrict__ nlo,
-                                                     float4* __restrict__ nhi, uint32_t* __restrict__ arrived)
+                                                     float4* __restrict__ nhi, uint32_t* __restrict__ arrived, int2* __restrict__ range)
 {
     const int p = blockIdx.x * blockDim.x + threadIdx.x;
     if (p >= n) return;
     const uint32_t t = idx[p];
     int node = n - 1 + p;
     nlo[node] = blo[t]; nhi[node] = bhi[t];
+    range[node] = make_int2(p, p);
     __threadfence();
     node = parent[node];
     while (node >= 0) {
@@ -158,6 +160,110 @@ __global__ void __launch_bounds__(256) k_lbvh_refit(int n, const uint32_t* __res
     }
 }
 
+// ---- PLOC (parallel locally-ordered clustering, Meister & Bittner 2018): bottom-up agglomeration along the Morton order ----
+// The clusters (at first the triangles) stay in Morton order; every round each cluster looks `radius` neighbours to either
+// side for the partner whose union box has the smallest area, mutual choices merge into a new binary node, and the
+// survivors are compacted.  The result approaches agglomerative clustering -- far better boxes than Morton median splits
+// where meshes overlap -- in ~30 rounds of three small kernels and a scan.  Node numbering as above (leaf p = n-1+p);
+// merges take ids n-2, n-3, ... so that the last one, the root, is node 0.
+#define MIRO_PLOC_RADIUS 16
+#define MIRO_PLOC_THREADS 256
+
+__global__ void __launch_bounds__(256) k_ploc_init(int n, const uint32_t* __restrict__ idx, const float4* __restrict__ blo, const float4* __restrict__ bhi,
+                                                    int* __restrict__ cid, float4* __restrict__ clo, float4* __restrict__ chi, float4* __restrict__ nlo,
+                                                    float4* __restrict__ nhi, int* __restrict__ size, int* __restrict__ parent)
+{
+    const int p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= n) return;
+    const uint32_t t = idx[p];
+    const float4 a = blo[t], b = bhi[t];
+    cid[p] = n - 1 + p; clo[p] = a; chi[p] = b;
+    nlo[n - 1 + p] = a; nhi[n - 1 + p] = b; size[n - 1 + p] = 1; parent[n - 1 + p] = -1;
+}
+
+__global__ void __launch_bounds__(MIRO_PLOC_THREADS) k_ploc_nearest(int m, const float4* __restrict__ clo, const float4* __restrict__ chi, int* __restrict__ nn)
+{
+    __shared__ float4 slo[MIRO_PLOC_THREADS + 2 * MIRO_PLOC_RADIUS], shi[MIRO_PLOC_THREADS + 2 * MIRO_PLOC_RADIUS];
+    const int b0 = blockIdx.x * MIRO_PLOC_THREADS - MIRO_PLOC_RADIUS;
+    for (int k = threadIdx.x; k < MIRO_PLOC_THREADS + 2 * MIRO_PLOC_RADIUS; k += MIRO_PLOC_THREADS) {
+        const int j = b0 + k;
+        if (j >= 0 && j < m) { slo[k] = clo[j]; shi[k] = chi[j]; }
+    }
+    __syncthreads();
+    const int i = blockIdx.x * MIRO_PLOC_THREADS + threadIdx.x;
+    if (i >= m) return;
+    const float4 a = slo[threadIdx.x + MIRO_PLOC_RADIUS], b = shi[threadIdx.x + MIRO_PLOC_RADIUS];
+    float best = INFINITY; int bj = -1;
+    for (int k = 0; k <= 2 * MIRO_PLOC_RADIUS; ++k) {        // ascending j: ties keep the smaller index
+        const int j = b0 + (int)threadIdx.x + k;
+        if (j < 0 || j >= m || j == i) continue;
+        const float4 c = slo[threadIdx.x + k], d = shi[threadIdx.x + k];
+        const float dx = fmaxf(b.x, d.x) - fminf(a.x, c.x), dy = fmaxf(b.y, d.y) - fminf(a.y, c.y), dz = fmaxf(b.z, d.z) - fminf(a.z, c.z);
+        const float area = dx * dy + dy * dz + dz * dx;
+        if (area < best) { best = area; bj = j; }
+    }
+    nn[i] = bj;
+}
+
+// flags[i] = 1 when slot i survives the round (unmerged, or the lower index of a merged pair, which then holds the new node)
+__global__ void __launch_bounds__(256) k_ploc_merge(int m, int n, const int* __restrict__ nn, int* __restrict__ cid, float4* __restrict__ clo,
+                                                     float4* __restrict__ chi, uint32_t* __restrict__ merges, int2* __restrict__ child,
+                                                     int* __restrict__ parent, float4* __restrict__ nlo, float4* __restrict__ nhi, int* __restrict__ size,
+                                                     int* __restrict__ flags)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= m) return;
+    const int j = nn[i];
+    int keep = 1;
+    if (j >= 0 && nn[j] == i) {
+        if (i < j) {
+            const int id = n - 2 - (int)atomicAdd(merges, 1u);
+            const int a = cid[i], b = cid[j];
+            const float4 la = clo[i], lb = clo[j], ha = chi[i], hb = chi[j];
+            const float4 lo = make_float4(fminf(la.x, lb.x), fminf(la.y, lb.y), fminf(la.z, lb.z), 0.f);
+            const float4 hi = make_float4(fmaxf(ha.x, hb.x), fmaxf(ha.y, hb.y), fmaxf(ha.z, hb.z), 0.f);
+            child[id] = make_int2(a, b); parent[a] = id; parent[b] = id; parent[id] = -1;
+            nlo[id] = lo; nhi[id] = hi; size[id] = size[a] + size[b];
+            // slot i is read by nobody else in this kernel after nn (its partner j only reads nn): safe to overwrite in place
+            cid[i] = id; clo[i] = lo; chi[i] = hi;
+        } else keep = 0;
+    }
+    flags[i] = keep;
+}
+
+__global__ void __launch_bounds__(256) k_ploc_compact(int m, const int* __restrict__ flags, const int* __restrict__ pos, const int* __restrict__ cid,
+                                                       const float4* __restrict__ clo, const float4* __restrict__ chi, int* __restrict__ ocid,
+                                                       float4* __restrict__ oclo, float4* __restrict__ ochi, int* __restrict__ new_m)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= m) return;
+    if (flags[i]) { const int o = pos[i]; ocid[o] = cid[i]; oclo[o] = clo[i]; ochi[o] = chi[i]; }
+    if (i == m - 1) *new_m = pos[i] + flags[i];
+}
+
+// Position of every node's first triangle in the depth-first leaf order: the sizes of the left siblings on the way up.
+__global__ void __launch_bounds__(256) k_ploc_ranges(int total, const int2* __restrict__ child, const int* __restrict__ parent, const int* __restrict__ size,
+                                                      int2* __restrict__ range, uint32_t* __restrict__ too_deep)
+{
+    const int v = blockIdx.x * blockDim.x + threadIdx.x;
+    if (v >= total) return;
+    int first = 0, u = v, steps = 0;
+    for (int p = parent[u]; p >= 0; p = parent[u]) {
+        const int2 c = child[p];
+        if (c.y == u) first += size[c.x];
+        u = p;
+        if (++steps > 8192) { atomicExch(too_deep, 1u); break; }
+    }
+    range[v] = make_int2(first, first + size[v] - 1);
+}
+
+__global__ void __launch_bounds__(256) k_ploc_order(int n, const uint32_t* __restrict__ idx, const int2* __restrict__ range, uint32_t* __restrict__ order)
+{
+    const int p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= n) return;
+    order[range[n - 1 + p].x] = idx[p];
+}
+
 struct LbvhFrontier { int bnode; uint32_t slot, pending, depth; };
 
 // counters: [0] wide nodes allocated, [1] next frontier size, [2] max stack need, [3] max depth
@@ -169,8 +275,8 @@ __global__ void __launch_bounds__(128) k_lbvh_collapse(int n, int max_leaf, cons
     const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= ncur) return;
     const LbvhFrontier fr = cur[t];
-    auto size_of = [&](int node) { return node >= n - 1 ? 1 : range[node].y - range[node].x + 1; };
-    auto first_of = [&](int node) { return node >= n - 1 ? node - (n - 1) : range[node].x; };
+    auto size_of = [&](int node) { return range[node].y - range[node].x + 1; };   // range: positions in the leaf order, all 2n-1 nodes
+    auto first_of = [&](int node) { return range[node].x; };
     auto area_of = [&](int node) {
         const float4 a = nlo[node], b = nhi[node];
         const float dx = b.x - a.x, dy = b.y - a.y, dz = b.z - a.z;
@@ -272,17 +378,63 @@ __global__ void __launch_bounds__(256) k_lbvh_tri_records(uint32_t n, const floa
     out[i] = r;
 }
 
+// The builders' scratch memory (~400-500 bytes per triangle) is ONE allocation that stays cached for the next build on the same
+// device: allocating and, above all, freeing half a gigabyte costs the driver far more than the build itself (measured: build
+// 19 ms, cudaFree of its scratch 60-630 ms).  mirogpu_release_build_scratch() returns it.
+struct BuildScratch {
+    std::mutex mtx;
+    int device = -1;
+    char* ptr = nullptr;
+    size_t bytes = 0;
+    void release_locked()
+    {
+        if (ptr) {
+            int cur = 0;
+            cudaGetDevice(&cur);
+            if (cur != device) cudaSetDevice(device);
+            cudaFree(ptr);
+            if (cur != device) cudaSetDevice(cur);
+        }
+        ptr = nullptr; bytes = 0; device = -1;
+    }
+};
+inline BuildScratch& build_scratch() { static BuildScratch s; return s; }
+
 // Builds QBVH4 nodes + triangle records on the current device from HOST vertices.  Returns cudaSuccess and fills `o`;
 // o.max_stack may exceed what the kernels carry -- the caller checks and falls back to the host builder.
-inline cudaError_t build_lbvh_device(const float* tri_vertices, uint32_t ntris, int max_leaf, LbvhOut& o)
+inline cudaError_t build_lbvh_device(const float* tri_vertices, uint32_t ntris, int max_leaf, LbvhOut& o, bool ploc = false)
 {
     if (max_leaf < 1) max_leaf = 1;
     if (max_leaf > 4) max_leaf = 4;
     const uint32_t n = ntris;
     cudaError_t e = cudaSuccess;
+    // all temporaries come out of ONE allocation (cudaMalloc / cudaFree of two dozen 20-90 MB buffers cost more than the build)
+    const size_t per_tri = 36 + 32 + 16 + 8 + 8 + 16 + 8 + 64 + 4 + 64 + 16 + 16 /* sort scratch */ + (ploc ? 8 + 64 + 12 + 8 : 0);
+    const size_t pool_bytes = (size_t)n * per_tri + ((size_t)n / 2 + 2) * (sizeof(Bvh4Node) + 2 * 16) + (8u << 20);
+    BuildScratch& scratch = build_scratch();
+    std::lock_guard<std::mutex> scratch_lock(scratch.mtx);   // one device build at a time per process
+    char* pool = nullptr;
+    size_t pool_used = 0;
     std::vector<void*> tmp;
-    auto dalloc = [&](void** p, size_t bytes) { cudaError_t r = cudaMalloc(p, std::max<size_t>(bytes, 16)); if (r == cudaSuccess) tmp.push_back(*p); return r; };
-    auto cleanup = [&]() { for (void* p : tmp) cudaFree(p); tmp.clear(); };
+    auto dalloc = [&](void** p, size_t bytes) {
+        bytes = (std::max<size_t>(bytes, 16) + 255) & ~(size_t)255;
+        if (!pool) {
+            int dev = 0;
+            cudaGetDevice(&dev);
+            if (scratch.device != dev || scratch.bytes < pool_bytes) {
+                scratch.release_locked();
+                const cudaError_t r = cudaMalloc((void**)&scratch.ptr, pool_bytes);
+                if (r != cudaSuccess) { scratch.ptr = nullptr; return r; }
+                scratch.device = dev; scratch.bytes = pool_bytes;
+            }
+            pool = scratch.ptr;
+        }
+        if (pool_used + bytes <= pool_bytes) { *p = pool + pool_used; pool_used += bytes; return cudaSuccess; }
+        const cudaError_t r = cudaMalloc(p, bytes);     // the estimate fell short (library scratch larger than expected)
+        if (r == cudaSuccess) tmp.push_back(*p);
+        return r;
+    };
+    auto cleanup = [&]() { for (void* p : tmp) cudaFree(p); tmp.clear(); pool = nullptr; };
 #define LB(x) do { e = (x); if (e != cudaSuccess) { cleanup(); if (o.d_geom) { cudaFree(o.d_geom); o.d_geom = nullptr; } return e; } } while (0)
     cudaStream_t st = cudaStreamPerThread;
     const auto t0 = std::chrono::steady_clock::now();
@@ -335,13 +487,55 @@ inline cudaError_t build_lbvh_device(const float* tri_vertices, uint32_t ntris, 
         void* sort_tmp = nullptr;
         LB(dalloc(&sort_tmp, sort_bytes));
         LB(cub::DeviceRadixSort::SortPairs(sort_tmp, sort_bytes, keys2, keys, idx2, idx, (int)n, 0, 64, st));
-        LB(dalloc((void**)&child, (size_t)n * 8)); LB(dalloc((void**)&range, (size_t)n * 8));
+        LB(dalloc((void**)&child, (size_t)n * 8)); LB(dalloc((void**)&range, (size_t)2 * n * 8));
         LB(dalloc((void**)&parent, (size_t)2 * n * 4));
         LB(dalloc((void**)&nlo, (size_t)2 * n * 16)); LB(dalloc((void**)&nhi, (size_t)2 * n * 16));
-        LB(dalloc((void**)&arrived, (size_t)n * 4));
-        LB(cudaMemsetAsync(arrived, 0, (size_t)n * 4, st));
-        k_lbvh_hierarchy<<<(n - 1 + 255) / 256, 256, 0, st>>>((int)n, keys, child, parent, range);
-        k_lbvh_refit<<<g256, 256, 0, st>>>((int)n, idx, blo, bhi, child, parent, nlo, nhi, arrived);
+        if (!ploc) {
+            LB(dalloc((void**)&arrived, (size_t)n * 4));
+            LB(cudaMemsetAsync(arrived, 0, (size_t)n * 4, st));
+            k_lbvh_hierarchy<<<(n - 1 + 255) / 256, 256, 0, st>>>((int)n, keys, child, parent, range);
+            k_lbvh_refit<<<g256, 256, 0, st>>>((int)n, idx, blo, bhi, child, parent, nlo, nhi, arrived, range);
+        } else {
+            int *cid[2] = {nullptr, nullptr}, *nn = nullptr, *flags = nullptr, *pos = nullptr, *size = nullptr, *d_m = nullptr;
+            float4 *clo[2] = {nullptr, nullptr}, *chi[2] = {nullptr, nullptr};
+            uint32_t* pc = nullptr;   // [0] merges so far, [1] a walk to the root gave up
+            for (int k = 0; k < 2; ++k) { LB(dalloc((void**)&cid[k], (size_t)n * 4)); LB(dalloc((void**)&clo[k], (size_t)n * 16)); LB(dalloc((void**)&chi[k], (size_t)n * 16)); }
+            LB(dalloc((void**)&nn, (size_t)n * 4)); LB(dalloc((void**)&flags, (size_t)n * 4)); LB(dalloc((void**)&pos, (size_t)n * 4));
+            LB(dalloc((void**)&size, (size_t)2 * n * 4)); LB(dalloc((void**)&d_m, 4)); LB(dalloc((void**)&pc, 8));
+            LB(cudaMemsetAsync(pc, 0, 8, st));
+            size_t scan_bytes = 0;
+            LB(cub::DeviceScan::ExclusiveSum(nullptr, scan_bytes, flags, pos, (int)n, st));
+            void* scan_tmp = nullptr;
+            LB(dalloc(&scan_tmp, scan_bytes));
+            k_ploc_init<<<g256, 256, 0, st>>>((int)n, idx, blo, bhi, cid[0], clo[0], chi[0], nlo, nhi, size, parent);
+            int m = (int)n, cur = 0;
+            const bool dbg = getenv("MIROGPU_DEBUG_BUILD") != nullptr;
+            const auto tp0 = std::chrono::steady_clock::now();
+            int rounds = 0;
+            for (int round = 0; m > 1 && round < 4096; ++round) {
+                ++rounds;
+                if (dbg && (round < 40 || round % 50 == 0)) fprintf(stderr, "ploc round %d m %d t %.3f ms\n", round, m, 1e3 * std::chrono::duration<double>(std::chrono::steady_clock::now() - tp0).count());
+                const unsigned gm = (unsigned)((m + 255) / 256);
+                k_ploc_nearest<<<(unsigned)((m + MIRO_PLOC_THREADS - 1) / MIRO_PLOC_THREADS), MIRO_PLOC_THREADS, 0, st>>>(m, clo[cur], chi[cur], nn);
+                k_ploc_merge<<<gm, 256, 0, st>>>(m, (int)n, nn, cid[cur], clo[cur], chi[cur], pc, child, parent, nlo, nhi, size, flags);
+                LB(cub::DeviceScan::ExclusiveSum(scan_tmp, scan_bytes, flags, pos, m, st));
+                k_ploc_compact<<<gm, 256, 0, st>>>(m, flags, pos, cid[cur], clo[cur], chi[cur], cid[cur ^ 1], clo[cur ^ 1], chi[cur ^ 1], d_m);
+                int new_m = 0;
+                LB(cudaMemcpyAsync(&new_m, d_m, 4, cudaMemcpyDeviceToHost, st));
+                LB(cudaStreamSynchronize(st));
+                if (new_m >= m || new_m < 1) { cleanup(); cudaFree(o.d_geom); o.d_geom = nullptr; return cudaErrorUnknown; }   // cannot happen: a mutual pair always exists
+                m = new_m; cur ^= 1;
+            }
+            k_ploc_ranges<<<(unsigned)((2 * n - 1 + 255) / 256), 256, 0, st>>>((int)(2 * n - 1), child, parent, size, range, pc + 1);
+            uint32_t h_pc[2] = {0, 0};
+            LB(cudaMemcpyAsync(h_pc, pc, 8, cudaMemcpyDeviceToHost, st));
+            LB(cudaStreamSynchronize(st));
+            if (dbg) fprintf(stderr, "ploc rounds %d, clustering + ranges %.3f ms\n", rounds, 1e3 * std::chrono::duration<double>(std::chrono::steady_clock::now() - tp0).count());
+            if (m != 1 || h_pc[0] != n - 1 || h_pc[1] != 0) { cleanup(); cudaFree(o.d_geom); o.d_geom = nullptr; return cudaErrorUnknown; }
+            // triangles in the depth-first order of the agglomerated tree: every subtree is a contiguous run again
+            k_ploc_order<<<g256, 256, 0, st>>>((int)n, idx, range, idx2);
+            std::swap(idx, idx2);
+        }
         // level-by-level collapse into four-wide nodes
         LbvhFrontier *fa = nullptr, *fb = nullptr;
         LB(dalloc((void**)&fa, (size_t)capacity * sizeof(LbvhFrontier))); LB(dalloc((void**)&fb, (size_t)capacity * sizeof(LbvhFrontier)));
@@ -351,7 +545,10 @@ inline cudaError_t build_lbvh_device(const float* tri_vertices, uint32_t ntris, 
         const LbvhFrontier rootf = {0, 0u, 0u, 1u};
         LB(cudaMemcpyAsync(fa, &rootf, sizeof rootf, cudaMemcpyHostToDevice, st));
         uint32_t ncur = 1;
+        const auto tc0 = std::chrono::steady_clock::now();
+        int levels = 0;
         for (int level = 0; ncur > 0 && level < 4096; ++level) {
+            ++levels;
             k_lbvh_collapse<<<(ncur + 127) / 128, 128, 0, st>>>((int)n, max_leaf, child, range, nlo, nhi, fa, ncur, fb, counters, wide, capacity);
             uint32_t hc[4];
             LB(cudaMemcpyAsync(hc, counters, sizeof hc, cudaMemcpyDeviceToHost, st));
@@ -362,6 +559,7 @@ inline cudaError_t build_lbvh_device(const float* tri_vertices, uint32_t ntris, 
             LB(cudaMemcpyAsync(counters + 1, &zero, 4, cudaMemcpyHostToDevice, st));
             std::swap(fa, fb);
         }
+        if (getenv("MIROGPU_DEBUG_BUILD")) fprintf(stderr, "collapse: %d levels, %.3f ms, %u wide nodes, max stack %u; since start %.3f ms\n", levels, 1e3 * std::chrono::duration<double>(std::chrono::steady_clock::now() - tc0).count(), num_wide, o.max_stack, 1e3 * std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count());
     }
     o.num_nodes = num_wide;
     o.node_bytes = (size_t)num_wide * sizeof(Qbvh4Node);
@@ -371,8 +569,10 @@ inline cudaError_t build_lbvh_device(const float* tri_vertices, uint32_t ntris, 
     LB(cudaStreamSynchronize(st));
     auto of = [](uint32_t u) { uint32_t b = (u & 0x80000000u) ? (u & 0x7fffffffu) : ~u; float f; memcpy(&f, &b, 4); return f; };
     for (int k = 0; k < 3; ++k) { o.lo[k] = n ? of(h_scene[k]) : 0.f; o.hi[k] = n ? of(h_scene[3 + k]) : 0.f; }
+    const double before_cleanup = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
     cleanup();
     o.seconds = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+    if (getenv("MIROGPU_DEBUG_BUILD")) fprintf(stderr, "device build %.3f ms (%.3f ms before freeing the scratch pool of %.0f MB, %.0f MB used)\n", 1e3 * o.seconds, 1e3 * before_cleanup, pool_bytes / 1048576.0, pool_used / 1048576.0);
 #undef LB
     return cudaSuccess;
 }

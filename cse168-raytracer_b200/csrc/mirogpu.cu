@@ -223,9 +223,14 @@ int mirogpu_scene_create(const float* tri_vertices, const float* tri_normals, co
     mirogpu_build_options o;
     o.layout = MIROGPU_LAYOUT_QBVH4; o.max_leaf = 0; o.sah_bins = 32; o.device = -1; o.builder = MIROGPU_BUILDER_SAH_HOST;
     if (opt) o = *opt;
-    if (const char* e = getenv("MIROGPU_BUILDER")) { if (!strcmp(e, "lbvh")) o.builder = MIROGPU_BUILDER_LBVH_DEVICE; }   // tuning knob
-    if (o.builder != MIROGPU_BUILDER_SAH_HOST && o.builder != MIROGPU_BUILDER_LBVH_DEVICE) return fail(MIROGPU_ERR_INVALID_ARG, "unknown builder");
-    if (o.builder == MIROGPU_BUILDER_LBVH_DEVICE && o.layout != MIROGPU_LAYOUT_QBVH4) return fail(MIROGPU_ERR_INVALID_ARG, "the device builder emits the QBVH4 layout only");
+    if (const char* e = getenv("MIROGPU_BUILDER")) {   // tuning knob
+        if (!strcmp(e, "lbvh")) o.builder = MIROGPU_BUILDER_LBVH_DEVICE;
+        else if (!strcmp(e, "ploc")) o.builder = MIROGPU_BUILDER_PLOC_DEVICE;
+        if (o.builder != MIROGPU_BUILDER_SAH_HOST && o.layout != MIROGPU_LAYOUT_QBVH4) o.builder = MIROGPU_BUILDER_SAH_HOST;   // the knob only applies where it can
+    }
+    const bool device_builder = o.builder == MIROGPU_BUILDER_LBVH_DEVICE || o.builder == MIROGPU_BUILDER_PLOC_DEVICE;
+    if (o.builder != MIROGPU_BUILDER_SAH_HOST && !device_builder) return fail(MIROGPU_ERR_INVALID_ARG, "unknown builder");
+    if (device_builder && o.layout != MIROGPU_LAYOUT_QBVH4) return fail(MIROGPU_ERR_INVALID_ARG, "the device builders emit the QBVH4 layout only");
     if (o.layout != MIROGPU_LAYOUT_BVH2 && o.layout != MIROGPU_LAYOUT_CWBVH8 && o.layout != MIROGPU_LAYOUT_BVH4 && o.layout != MIROGPU_LAYOUT_QBVH4)
         return fail(MIROGPU_ERR_INVALID_ARG, "unknown layout");
     if (o.max_leaf <= 0) if (const char* e = getenv("MIROGPU_MAX_LEAF")) o.max_leaf = atoi(e);   // tuning knob
@@ -266,8 +271,8 @@ int mirogpu_scene_create(const float* tri_vertices, const float* tri_normals, co
     double t0 = now_s();
     LbvhOut lb;
     bool device_built = false;
-    if (o.builder == MIROGPU_BUILDER_LBVH_DEVICE) {
-        const cudaError_t be = build_lbvh_device(tri_vertices, ntris, std::min(o.max_leaf, 4), lb);
+    if (device_builder) {
+        const cudaError_t be = build_lbvh_device(tri_vertices, ntris, std::min(o.max_leaf, 4), lb, o.builder == MIROGPU_BUILDER_PLOC_DEVICE);
         if (be != cudaSuccess) { delete h; return fail(be == cudaErrorMemoryAllocation ? MIROGPU_ERR_OOM : MIROGPU_ERR_CUDA, std::string("device BVH build: ") + cudaGetErrorString(be)); }
         if (lb.max_stack <= MIRO_STACK4) device_built = true;
         else { cudaFree(lb.d_geom); lb.d_geom = nullptr; }   // a Morton tree too deep for the kernels' stacks: use the host builder
@@ -368,7 +373,7 @@ int mirogpu_scene_create(const float* tri_vertices, const float* tri_normals, co
     in.num_binary_nodes = device_built ? (ntris ? 2 * ntris - 1 : 0) : (uint32_t)bin.nodes.size();
     in.num_binary_leaves = device_built ? ntris : bin.num_leaves;
     in.max_depth = device_built ? lb.max_depth : (o.layout == MIROGPU_LAYOUT_BVH2 ? bin.max_depth : flat.max_depth);
-    in.builder = device_built ? MIROGPU_BUILDER_LBVH_DEVICE : MIROGPU_BUILDER_SAH_HOST;
+    in.builder = device_built ? o.builder : MIROGPU_BUILDER_SAH_HOST;
     in.layout = o.layout;
     in.node_bytes = node_bytes; in.triangle_bytes = tri_bytes; in.shading_bytes = shade_bytes;
     in.build_seconds = device_built ? lb.seconds : t1 - t0; in.flatten_seconds = device_built ? 0.0 : t2 - t1; in.upload_seconds = t3 - t2;
@@ -607,6 +612,13 @@ int mirogpu_rng_uniforms(uint32_t seed, uint32_t sample, uint32_t dimension, siz
     if (n && !out) return fail(MIROGPU_ERR_INVALID_ARG, "NULL argument");
     for (size_t i = 0; i < n; ++i) uniform2(seed, (uint32_t)(first + i), sample, dimension, out[2 * i], out[2 * i + 1]);
     return MIROGPU_OK;
+}
+
+void mirogpu_release_build_scratch(void)
+{
+    BuildScratch& s = build_scratch();
+    std::lock_guard<std::mutex> lk(s.mtx);
+    s.release_locked();
 }
 
 void* mirogpu_host_alloc(size_t bytes)

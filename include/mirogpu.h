@@ -97,11 +97,17 @@ typedef struct mirogpu_camera {
 
 enum { MIROGPU_LAYOUT_BVH2 = 0, MIROGPU_LAYOUT_CWBVH8 = 1, MIROGPU_LAYOUT_BVH4 = 2, MIROGPU_LAYOUT_QBVH4 = 3 };
 
-/* Who builds the tree (BVH::build, BVH.cpp:60-339).  SAH_HOST: binned SAH on the host cores (best trees; 0.5 s for 1.4 M
- * triangles).  LBVH_DEVICE: Morton-order linear BVH built, collapsed four-wide and quantised entirely on the GPU
- * (milliseconds; trees trace slower; QBVH4 only; falls back to SAH_HOST if the Morton tree is too deep for the kernels'
- * stacks).  Both give identical hits. */
-enum { MIROGPU_BUILDER_SAH_HOST = 0, MIROGPU_BUILDER_LBVH_DEVICE = 1 };
+/* Who builds the tree (BVH::build, BVH.cpp:60-339).  SAH_HOST: binned SAH on the host cores (0.5 s for 1.4 M triangles).
+ * LBVH_DEVICE: Morton-order linear BVH (Karras) built, collapsed four-wide and quantised entirely on the GPU (milliseconds;
+ * trees trace much slower where meshes overlap).  PLOC_DEVICE: the same pipeline with the binary tree made by parallel
+ * locally-ordered clustering -- bottom-up merges of Morton neighbours by smallest union area (tens of milliseconds; tree
+ * quality close to SAH).  The device builders emit QBVH4 only and fall back to SAH_HOST if their tree is too deep for the
+ * kernels' stacks.  All give identical hits. */
+enum { MIROGPU_BUILDER_SAH_HOST = 0, MIROGPU_BUILDER_LBVH_DEVICE = 1, MIROGPU_BUILDER_PLOC_DEVICE = 2 };
+
+/* The device builders keep their scratch allocation (400-500 bytes per triangle of the largest scene built so far) for the
+ * next build in this process; this returns it to the driver. */
+void mirogpu_release_build_scratch(void);
 
 typedef struct mirogpu_build_options {
     int32_t layout;       /* MIROGPU_LAYOUT_*; default QBVH4 (the fastest measured) */

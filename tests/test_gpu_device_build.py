@@ -21,12 +21,16 @@ def _verts(oracle, scenes, name):
     return np.ascontiguousarray(oracle.dump_triangles()[:, :9])
 
 
+BUILDERS = [1, 2]     # MIROGPU_BUILDER_LBVH_DEVICE (Karras), MIROGPU_BUILDER_PLOC_DEVICE (locally-ordered clustering)
+
+
+@pytest.mark.parametrize("builder", BUILDERS)
 @pytest.mark.parametrize("name", ["testobj", "cornell", "teapot", "bunny_teapot"])
-def test_device_built_tree_gives_identical_hits(pkg, scenes, oracle, name):
+def test_device_built_tree_gives_identical_hits(pkg, scenes, oracle, name, builder):
     V = _verts(oracle, scenes, name)
-    dev = pkg.MiroScene(V, layout=pkg.LAYOUT_QBVH4, builder=pkg.BUILDER_LBVH_DEVICE)
+    dev = pkg.MiroScene(V, layout=pkg.LAYOUT_QBVH4, builder=builder)
     host = pkg.MiroScene(V, layout=pkg.LAYOUT_QBVH4, builder=pkg.BUILDER_SAH_HOST)
-    assert dev.info.builder == pkg.BUILDER_LBVH_DEVICE and host.info.builder == pkg.BUILDER_SAH_HOST
+    assert dev.info.builder == builder and host.info.builder == pkg.BUILDER_SAH_HOST
     assert dev.info.num_triangles == V.shape[0] and np.allclose(dev.info.bounds_min, host.info.bounds_min, atol=1e-3)
     P = V.reshape(-1, 3)
     rays = np.concatenate([oracle.eye_rays(96, 96), random_rays(30000, P.min(0), P.max(0), 7)])
@@ -42,10 +46,11 @@ def test_device_built_tree_gives_identical_hits(pkg, scenes, oracle, name):
     assert np.array_equal(dev.intersect(rays, mode=pkg.ANY_HIT)["prim_id"] != 0xFFFFFFFF, b["prim_id"] != 0xFFFFFFFF)
 
 
+@pytest.mark.parametrize("builder", BUILDERS)
 @pytest.mark.parametrize("name", ["cornell", "teapot", "bunny_teapot"])
-def test_device_built_tree_structure(pkg, scenes, oracle, name):
+def test_device_built_tree_structure(pkg, scenes, oracle, name, builder):
     V = _verts(oracle, scenes, name)
-    S = pkg.MiroScene(V, layout=pkg.LAYOUT_QBVH4, builder=pkg.BUILDER_LBVH_DEVICE)
+    S = pkg.MiroScene(V, layout=pkg.LAYOUT_QBVH4, builder=builder)
     nodes = S.nodes_bytes().view(QBVH4_NODE)
     tris = S.triangles_bytes().view(TRI_REC)
     assert len(nodes) == S.info.num_nodes and len(tris) == V.shape[0]
@@ -92,37 +97,38 @@ def test_device_built_tree_structure(pkg, scenes, oracle, name):
     assert seen.all() and visited.all()
 
 
-def test_edge_cases_of_the_device_builder(pkg):
-    empty = pkg.MiroScene(np.zeros((0, 9), np.float32), builder=pkg.BUILDER_LBVH_DEVICE)
+@pytest.mark.parametrize("builder", BUILDERS)
+def test_edge_cases_of_the_device_builder(pkg, builder):
+    empty = pkg.MiroScene(np.zeros((0, 9), np.float32), builder=builder)
     r = np.zeros((4, 8), np.float32); r[:, 6] = 1; r[:, 7] = 1e12
     assert (empty.intersect(r)["prim_id"] == 0xFFFFFFFF).all()
     V = np.array([[0, 0, 0, 1, 0, 0, 0, 1, 0]], np.float32)
-    one = pkg.MiroScene(V, builder=pkg.BUILDER_LBVH_DEVICE)
+    one = pkg.MiroScene(V, builder=builder)
     r[:, 0:3] = [0.25, 0.25, 1.0]; r[:, 4:7] = [0, 0, -1]
     h = one.intersect(r)
     assert (h["prim_id"] == 0).all() and np.allclose(h["t"], 1.0)
     # many identical triangles: all Morton keys equal, the hierarchy falls back to positions; ties go to the smallest id
-    D = pkg.MiroScene(np.repeat(V, 37, axis=0), builder=pkg.BUILDER_LBVH_DEVICE)
+    D = pkg.MiroScene(np.repeat(V, 37, axis=0), builder=builder)
     assert (D.intersect(r)["prim_id"] == 0).all()
     with pytest.raises(pkg.MiroGpuError):
-        pkg.MiroScene(V, layout=pkg.LAYOUT_BVH2, builder=pkg.BUILDER_LBVH_DEVICE)
+        pkg.MiroScene(V, layout=pkg.LAYOUT_BVH2, builder=builder)
 
 
 def test_device_build_of_the_bench_scene(pkg, scenes):
     """1.39 M triangles through the host layer (BVH::setBuilder): same hits as the host-built SAH tree.  Measured on a B200:
     19 ms on the device (incl. the 50 MB vertex upload and one sync per level of the wide tree) against 420 ms of binned
     SAH on 16 host threads -- and 20.7 s for the reference's BVH::build (SURVEY 8a1)."""
-    H = pkg.HostScene(pkg.LAYOUT_QBVH4, builder=pkg.BUILDER_LBVH_DEVICE)
-    scenes.realise(H, "bunny20", objio.obj_path)
-    H.precalc()
-    S = H.scene()
-    info = S.info
-    assert info.builder == pkg.BUILDER_LBVH_DEVICE and info.num_triangles == 1389021
-    assert info.build_seconds < 5.0      # first CUDA use in a process adds module-load time; the steady figure is in DESIGN.md
-    rays = H.eye_rays(480, 270)
-    a = S.intersect(rays)
     H2 = pkg.HostScene(pkg.LAYOUT_QBVH4)
     scenes.realise(H2, "bunny20", objio.obj_path)
     H2.precalc()
     assert H2.scene().info.builder == pkg.BUILDER_SAH_HOST
-    assert np.array_equal(H2.scene().intersect(rays), a)
+    rays = H2.eye_rays(480, 270)
+    want = H2.scene().intersect(rays)
+    for builder in BUILDERS:
+        H = pkg.HostScene(pkg.LAYOUT_QBVH4, builder=builder)
+        scenes.realise(H, "bunny20", objio.obj_path)
+        H.precalc()
+        info = H.scene().info
+        assert info.builder == builder and info.num_triangles == 1389021
+        assert info.build_seconds < 5.0      # first CUDA use in a process adds module-load time; the steady figures are in DESIGN.md
+        assert np.array_equal(H.scene().intersect(rays), want)
