@@ -9,6 +9,9 @@
 //   cub radix sort     (key, triangle) pairs -- a library sort, as for any plain sort
 //   k_lbvh_hierarchy   Karras 2012: every internal node finds its key range and split in parallel
 //   k_lbvh_refit       bottom-up union of boxes (second arrival at a node continues upwards)
+//   k_ploc_*           MIROGPU_BUILDER_PLOC_DEVICE: instead of the two steps above, bottom-up merges of Morton neighbours by
+//                      smallest union area (parallel locally-ordered clustering), then the triangles are put in the depth-
+//                      first order of that tree
 //   k_lbvh_collapse    one launch per level of the wide tree: a node takes its binary subtree's children, opening the
 //                      largest-area child until four; subtrees of <= max_leaf triangles become leaves (their triangles are
 //                      contiguous in Morton order)
@@ -166,7 +169,8 @@ __global__ void __launch_bounds__(256) k_lbvh_refit(int n, const uint32_t* __res
 // survivors are compacted.  The result approaches agglomerative clustering -- far better boxes than Morton median splits
 // where meshes overlap -- in ~30 rounds of three small kernels and a scan.  Node numbering as above (leaf p = n-1+p);
 // merges take ids n-2, n-3, ... so that the last one, the root, is node 0.
-#define MIRO_PLOC_RADIUS 16
+#define MIRO_PLOC_RADIUS 64          /* neighbours examined to either side (tuning knob MIROGPU_PLOC_RADIUS, at most 64); camera rays on the bench scene: 8 -> 5.20, 16 -> 5.48, 32 -> 5.68, 64 -> 5.77 Grays/s, build 9-10 ms throughout */
+#define MIRO_PLOC_MAX_RADIUS 64
 #define MIRO_PLOC_THREADS 256
 
 __global__ void __launch_bounds__(256) k_ploc_init(int n, const uint32_t* __restrict__ idx, const float4* __restrict__ blo, const float4* __restrict__ bhi,
@@ -181,20 +185,21 @@ __global__ void __launch_bounds__(256) k_ploc_init(int n, const uint32_t* __rest
     nlo[n - 1 + p] = a; nhi[n - 1 + p] = b; size[n - 1 + p] = 1; parent[n - 1 + p] = -1;
 }
 
-__global__ void __launch_bounds__(MIRO_PLOC_THREADS) k_ploc_nearest(int m, const float4* __restrict__ clo, const float4* __restrict__ chi, int* __restrict__ nn)
+__global__ void __launch_bounds__(MIRO_PLOC_THREADS) k_ploc_nearest(int m, int radius, const float4* __restrict__ clo, const float4* __restrict__ chi,
+                                                                    int* __restrict__ nn)
 {
-    __shared__ float4 slo[MIRO_PLOC_THREADS + 2 * MIRO_PLOC_RADIUS], shi[MIRO_PLOC_THREADS + 2 * MIRO_PLOC_RADIUS];
-    const int b0 = blockIdx.x * MIRO_PLOC_THREADS - MIRO_PLOC_RADIUS;
-    for (int k = threadIdx.x; k < MIRO_PLOC_THREADS + 2 * MIRO_PLOC_RADIUS; k += MIRO_PLOC_THREADS) {
+    __shared__ float4 slo[MIRO_PLOC_THREADS + 2 * MIRO_PLOC_MAX_RADIUS], shi[MIRO_PLOC_THREADS + 2 * MIRO_PLOC_MAX_RADIUS];
+    const int b0 = blockIdx.x * MIRO_PLOC_THREADS - radius;
+    for (int k = threadIdx.x; k < MIRO_PLOC_THREADS + 2 * radius; k += MIRO_PLOC_THREADS) {
         const int j = b0 + k;
         if (j >= 0 && j < m) { slo[k] = clo[j]; shi[k] = chi[j]; }
     }
     __syncthreads();
     const int i = blockIdx.x * MIRO_PLOC_THREADS + threadIdx.x;
     if (i >= m) return;
-    const float4 a = slo[threadIdx.x + MIRO_PLOC_RADIUS], b = shi[threadIdx.x + MIRO_PLOC_RADIUS];
+    const float4 a = slo[threadIdx.x + radius], b = shi[threadIdx.x + radius];
     float best = INFINITY; int bj = -1;
-    for (int k = 0; k <= 2 * MIRO_PLOC_RADIUS; ++k) {        // ascending j: ties keep the smaller index
+    for (int k = 0; k <= 2 * radius; ++k) {        // ascending j: ties keep the smaller index
         const int j = b0 + (int)threadIdx.x + k;
         if (j < 0 || j >= m || j == i) continue;
         const float4 c = slo[threadIdx.x + k], d = shi[threadIdx.x + k];
@@ -509,6 +514,8 @@ inline cudaError_t build_lbvh_device(const float* tri_vertices, uint32_t ntris, 
             LB(dalloc(&scan_tmp, scan_bytes));
             k_ploc_init<<<g256, 256, 0, st>>>((int)n, idx, blo, bhi, cid[0], clo[0], chi[0], nlo, nhi, size, parent);
             int m = (int)n, cur = 0;
+            int radius = MIRO_PLOC_RADIUS;
+            if (const char* ev = getenv("MIROGPU_PLOC_RADIUS")) radius = std::min(std::max(atoi(ev), 1), MIRO_PLOC_MAX_RADIUS);
             const bool dbg = getenv("MIROGPU_DEBUG_BUILD") != nullptr;
             const auto tp0 = std::chrono::steady_clock::now();
             int rounds = 0;
@@ -516,7 +523,7 @@ inline cudaError_t build_lbvh_device(const float* tri_vertices, uint32_t ntris, 
                 ++rounds;
                 if (dbg && (round < 40 || round % 50 == 0)) fprintf(stderr, "ploc round %d m %d t %.3f ms\n", round, m, 1e3 * std::chrono::duration<double>(std::chrono::steady_clock::now() - tp0).count());
                 const unsigned gm = (unsigned)((m + 255) / 256);
-                k_ploc_nearest<<<(unsigned)((m + MIRO_PLOC_THREADS - 1) / MIRO_PLOC_THREADS), MIRO_PLOC_THREADS, 0, st>>>(m, clo[cur], chi[cur], nn);
+                k_ploc_nearest<<<(unsigned)((m + MIRO_PLOC_THREADS - 1) / MIRO_PLOC_THREADS), MIRO_PLOC_THREADS, 0, st>>>(m, radius, clo[cur], chi[cur], nn);
                 k_ploc_merge<<<gm, 256, 0, st>>>(m, (int)n, nn, cid[cur], clo[cur], chi[cur], pc, child, parent, nlo, nhi, size, flags);
                 LB(cub::DeviceScan::ExclusiveSum(scan_tmp, scan_bytes, flags, pos, m, st));
                 k_ploc_compact<<<gm, 256, 0, st>>>(m, flags, pos, cid[cur], clo[cur], chi[cur], cid[cur ^ 1], clo[cur ^ 1], chi[cur ^ 1], d_m);
