@@ -9,6 +9,8 @@
 #include "../../include/mirogpu.h"
 
 #define MIRO_PHOTON_KMAX 512
+#define MIRO_GW_TICKET_SPAN 8192   /* segment cursors of one warp-per-query launch: one per warp of the grid (the grid is capped accordingly) */
+#define MIRO_GW_TICKET_SLOTS 8      /* launches in flight */
 
 namespace mirogpu {
 
@@ -16,7 +18,7 @@ struct PhotonMapDevice {
     float4* d_photons = nullptr;  // 2 float4 per photon: (pos.xyz, plane|theta<<8|phi<<16 bits) (power.xyz, 0)
     float* d_tables = nullptr;    // costheta[256] sintheta[256] cosphi[256] sinphi[256]  (PhotonMap.cpp:47-53)
     float4* d_search = nullptr;   // warp-per-query search records, 32 B per photon: (pos.xyz, same bits) (direction.xyz from the tables, 0)
-    unsigned int* d_tickets = nullptr;   // chunk counters of the warp-per-query launches (one per launch in flight)
+    unsigned int* d_tickets = nullptr;   // segment cursors of the warp-per-query launches (MIRO_GW_TICKET_SLOTS arrays of MIRO_GW_TICKET_SPAN)
     int stored = 0, half_stored = 0;
     bool exact = false;           // true: the reference's search verbatim, one query per thread (bit-identical estimates); see photon_impl.cuh
     int upload(const void* photons28, int stored, std::string& err);

@@ -47,7 +47,7 @@ int PhotonMapDevice::upload(const void* photons28, int n, std::string& err)
     cudaError_t e = cudaMalloc(&d_photons, packed.size() * sizeof(float4));
     if (e == cudaSuccess) e = cudaMalloc(&d_tables, tab.size() * sizeof(float));
     if (e == cudaSuccess) e = cudaMalloc(&d_search, packed.size() * sizeof(float4));
-    if (e == cudaSuccess) e = cudaMalloc(&d_tickets, 64 * sizeof(unsigned int));
+    if (e == cudaSuccess) e = cudaMalloc(&d_tickets, (size_t)MIRO_GW_TICKET_SLOTS * MIRO_GW_TICKET_SPAN * sizeof(unsigned int));
     if (e == cudaSuccess) e = cudaMemcpy(d_photons, packed.data(), packed.size() * sizeof(float4), cudaMemcpyHostToDevice);
     if (e == cudaSuccess) {
         // the power half of each record becomes the photon's direction, multiplied out of the tables the way
@@ -223,9 +223,10 @@ __device__ __forceinline__ float gather_select(GatherWarpShared& sh, int& n, int
     return __uint_as_float(tau);
 }
 
-// Queries are claimed in chunks of `chunk` consecutive indices (a ticket counter), because consecutive queries are
-// neighbouring pixels: the k photons that answered one query bound the search radius of the next -- if all k also face
-// the next query's normal, the k-th nearest facing photon of the next query is no farther than the farthest of them.
+// Queries are claimed in chunks of `chunk` consecutive indices, because consecutive queries are neighbouring pixels: the k
+// photons that answered one query bound the search radius of the next one the warp answers -- if all k also face that
+// query's normal, its k-th nearest facing photon is no farther than the farthest of them (true for any two queries; it
+// is a tight bound for neighbours).
 // Starting the walk with that radius instead of max_dist saves most of the visits on evenly lit surfaces (config 5:
 // 12 k -> 3 k per query on the walls); the result is the same k nearest photons.
 template <int NPL>   // nodes per lane and iteration
@@ -241,15 +242,31 @@ __global__ void __launch_bounds__(32 * MIRO_GW_WARPS) k_photon_gather_warp(const
     const unsigned lt = (1u << lane) - 1u;
     if (d_n) n = min(n, (size_t)*d_n);
     const float full_r2 = xmul(max_dist, max_dist);
-    const unsigned long long nchunks = (n + (size_t)chunk - 1) / (size_t)chunk;
-    for (;;) {
-        unsigned int c0 = 0u;
-        if (lane == 0) c0 = atomicAdd(ticket, 1u);
-        c0 = __shfl_sync(0xffffffffu, c0, 0);
-        if (c0 >= nchunks) break;
-        const size_t qb = (size_t)c0 * (size_t)chunk;
-        const size_t qe = min(n, qb + (size_t)chunk);
-        bool prev_valid = false;    // sh.cand_id[0 .. kmax) holds the k photons of the previous query of this chunk
+    // Work distribution: the query range is cut into one contiguous segment per warp; a warp takes chunks of its home segment in
+    // order (so nearly every query has its predecessor's photons to seed from, not just 7 of 8) and, when that is exhausted, takes
+    // chunks from the other segments' cursors -- segments differ 100-fold in cost, the chunk stays the unit of load balance.
+    const uint32_t W = gridDim.x * MIRO_GW_WARPS, wid = blockIdx.x * MIRO_GW_WARPS + (threadIdx.x >> 5);
+    const size_t seg_len = (((n + W - 1) / W + (size_t)chunk - 1) / (size_t)chunk) * (size_t)chunk;
+    bool prev_valid = false;    // sh.cand_id[0 .. kmax) holds the k photons of the previous query this warp answered
+    uint32_t scanned = 0;       // segments (from home, cyclically) already found exhausted
+    while (scanned < W) {
+        bool has = false;
+        if (scanned + lane < W) {
+            const uint32_t v = (wid + scanned + lane) % W;
+            const size_t sv = (size_t)v * seg_len;
+            if (sv < n) has = *(volatile unsigned int*)(ticket + v) < (unsigned int)(min(n, sv + seg_len) - sv);
+        }
+        const unsigned work = __ballot_sync(0xffffffffu, has);
+        if (work == 0u) { scanned += 32u; continue; }
+        scanned += (uint32_t)(__ffs(work) - 1);              // stay on this segment until it is exhausted
+        const uint32_t v = (wid + scanned) % W;
+        const size_t sv = (size_t)v * seg_len, lv = min(n, sv + seg_len) - sv;
+        unsigned int off = 0u;
+        if (lane == 0) off = atomicAdd(ticket + v, (unsigned int)chunk);
+        off = __shfl_sync(0xffffffffu, off, 0);
+        if (off >= lv) continue;                              // another warp took the last chunk meanwhile
+        const size_t qb = sv + off;
+        const size_t qe = min(sv + lv, qb + (size_t)chunk);
         for (size_t q = qb; q < qe; ++q) {
             if (active && active[q].w == 0.f) {
                 if (lane < 3) irr3[3 * q + lane] = 0.f;
@@ -410,26 +427,27 @@ cudaError_t photon_gather_launch(const PhotonMapDevice& pm, const float* d_pos3,
         if (dev >= 0 && dev < 64) attr_set[dev].store(true);
     }
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    // knobs (defaults measured on config 5): queries per ticket, neighbour seeding, nodes per lane and iteration.  A chunk is the
-    // unit of load balance and some queries cost 100x the median (a ceiling few photons face: 1400 iterations), so chunks
-    // stay short: 8 beats 16 and 32 (41 / 47 / 57 ms) although longer chunks seed more queries; 4 nodes per lane lose to 2.
-    static const int chunk = std::max(1, env_int("MIROGPU_GATHER_CHUNK", 8));
+    // knobs (defaults measured on config 5): queries per claim, neighbour seeding, nodes per lane and iteration.  A chunk is the
+    // unit of load balance and some queries cost 100x the median (a ceiling few photons face: 1400 iterations).  Since a warp
+    // walks its home segment in order, seeding does not depend on the chunk size, and short chunks balance best: 1 / 2 / 4 / 8 /
+    // 16 queries give 37.9 / 36.6 / 37.0 / 38.8 / 45.6 ms on the global map; 4 nodes per lane lose to 2.
+    static const int chunk = std::max(1, env_int("MIROGPU_GATHER_CHUNK", 2));
     static const int seed_on = env_int("MIROGPU_GATHER_SEED", 1);
     static const int npl = env_int("MIROGPU_GATHER_NPL", 2);
     const size_t want = ((n + chunk - 1) / chunk + MIRO_GW_WARPS - 1) / MIRO_GW_WARPS;
     static std::atomic<unsigned> launch_seq{0};
-    unsigned int* ticket = pm.d_tickets + (launch_seq.fetch_add(1) % 64u);   // one counter per launch in flight
-    cudaError_t e = cudaMemsetAsync(ticket, 0, 4, st);
+    unsigned int* ticket = pm.d_tickets + (size_t)(launch_seq.fetch_add(1) % MIRO_GW_TICKET_SLOTS) * MIRO_GW_TICKET_SPAN;   // one cursor array per launch in flight
+    cudaError_t e = cudaMemsetAsync(ticket, 0, MIRO_GW_TICKET_SPAN * sizeof(unsigned int), st);
     if (e != cudaSuccess) return e;
     int occ = 1;
     if (npl == 4) {
         cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_photon_gather_warp<4>, 32 * MIRO_GW_WARPS, smem);
-        const unsigned grid = (unsigned)std::min<size_t>(want, (size_t)sms * std::max(occ, 1));
+        const unsigned grid = (unsigned)std::min<size_t>(std::min<size_t>(want, (size_t)sms * std::max(occ, 1)), MIRO_GW_TICKET_SPAN / MIRO_GW_WARPS);
         k_photon_gather_warp<4><<<grid, 32 * MIRO_GW_WARPS, smem, st>>>(pm.d_photons, pm.d_search, pm.stored, pm.half_stored, d_pos3, d_normal3,
                                                                         active, n, d_n, max_dist, k, d_irrad3, ticket, chunk, seed_on);
     } else {
         cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_photon_gather_warp<2>, 32 * MIRO_GW_WARPS, smem);
-        const unsigned grid = (unsigned)std::min<size_t>(want, (size_t)sms * std::max(occ, 1));   // persistent warps
+        const unsigned grid = (unsigned)std::min<size_t>(std::min<size_t>(want, (size_t)sms * std::max(occ, 1)), MIRO_GW_TICKET_SPAN / MIRO_GW_WARPS);   // persistent warps
         k_photon_gather_warp<2><<<grid, 32 * MIRO_GW_WARPS, smem, st>>>(pm.d_photons, pm.d_search, pm.stored, pm.half_stored, d_pos3, d_normal3,
                                                                         active, n, d_n, max_dist, k, d_irrad3, ticket, chunk, seed_on);
     }
