@@ -18,8 +18,9 @@ extern "C" int emu_trace(const float* tri_vertices, uint32_t ntris, int layout, 
                          long n, mirogpu_hit* hits, int any_hit, unsigned long long* counters3, uint32_t* info4)
 {
     // layout 2: the BVH2 tree walked through the single-step functions of the hybrid kernel; layout 3: BVH4
+    // layout 5: QBVH4 walked through the default hybrid kernel's steps -- qbvh4_node_step + one triangle per leaf step
     const int walk = layout == 2 ? 2 : 0;
-    const bool wide4 = layout == 3, quant4 = layout == 4;
+    const bool wide4 = layout == 3, quant4 = layout == 4 || layout == 5, steps4 = layout == 5;
     if (layout >= 2) layout = MIROGPU_LAYOUT_BVH2;
     if (max_leaf <= 0) max_leaf = layout == MIROGPU_LAYOUT_CWBVH8 ? 3 : 4;
     if (layout == MIROGPU_LAYOUT_CWBVH8 && max_leaf > 3) max_leaf = 3;
@@ -43,7 +44,18 @@ extern "C" int emu_trace(const float* tri_vertices, uint32_t ntris, int layout, 
     for (long i = 0; i < n; ++i) {
         BestHit best;
         TraceCounters c = {0, 0, 0};
-        if (quant4) {
+        if (steps4) {
+            Bvh2Walk st;
+            int32_t stack[MIRO_STACK4 + 1];
+            bvh2_begin(rays[i], st, best);
+            while (st.node != MIRO_BVH2_DONE) {
+                if (st.node >= 0) { qbvh4_node_step<0>(nodes, tr, rays[i], st, stack, best); ++c.nodes; c.boxes += 4; }
+                else {
+                    ++c.tris;
+                    if (any_hit) bvh2_leaf_step_one<true>(tr, rays[i], st, stack, best); else bvh2_leaf_step_one<false>(tr, rays[i], st, stack, best);
+                }
+            }
+        } else if (quant4) {
             if (any_hit) trace_qbvh4<true, true>(nodes, tr, rays[i], best, &c); else trace_qbvh4<false, true>(nodes, tr, rays[i], best, &c);
         } else if (wide4) {
             if (any_hit) trace_bvh4<true, true>(nodes, tr, rays[i], best, &c); else trace_bvh4<false, true>(nodes, tr, rays[i], best, &c);
@@ -81,6 +93,7 @@ extern "C" int emu_build(const float* tri_vertices, uint32_t ntris, int layout, 
     if (layout == MIROGPU_LAYOUT_CWBVH8 && max_leaf > 3) max_leaf = 3;
     BinaryBvh bin = build_binary_sah(tri_vertices, ntris, max_leaf, 32);
     FlatBvh flat;
+    if (layout == 5) layout = 4;
     if (layout == 4) flatten_qbvh4(bin, flat); else if (layout == 3) flatten_bvh4(bin, flat); else if (layout == MIROGPU_LAYOUT_BVH2) flatten_bvh2(bin, flat); else flatten_cwbvh8(bin, flat);
     const size_t nb = layout == 4 ? flat.nodesq.size() * sizeof(Qbvh4Node) : layout == 3 ? flat.nodes4.size() * sizeof(Bvh4Node)
                                   : layout == MIROGPU_LAYOUT_BVH2 ? flat.nodes2.size() * sizeof(Bvh2Node) : flat.nodes8.size() * sizeof(Cwbvh8Node);

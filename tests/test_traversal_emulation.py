@@ -13,7 +13,7 @@ import objio
 from conftest import bits, random_rays, subsample_rays
 from emu_helpers import emu_trace, hit_ids
 
-LAYOUTS = [0, 1, 2, 3, 4]   # BVH2, CWBVH8, BVH2 via the single-step functions of the hybrid kernel, BVH4, QBVH4
+LAYOUTS = [0, 1, 2, 3, 4, 5]   # BVH2, CWBVH8, BVH2 via the single-step functions of the hybrid kernel, BVH4, QBVH4, QBVH4 via the default kernel's steps (one triangle per leaf step)
 
 
 def _scene(oracle, scenes, name):
