@@ -37,15 +37,35 @@ inline float box_half_area(const Aabb& b)
 }
 
 struct Builder {
-    const Aabb* pb;             // per-primitive bounds
-    const float* pc;            // per-primitive centroid (3 floats)
-    uint32_t* idx;              // permutation being partitioned in place
+    // The triangle list is partitioned as 32-byte records (bounds + id), not as indices into per-triangle arrays: every pass
+    // of every level then streams through contiguous memory instead of gathering (the build is a memory walk, nothing else).
+    struct Prim { Aabb b; uint32_t id, pad; };
+    static float centre(const Prim& p, int k) { return 0.5f * (p.b.lo[k] + p.b.hi[k]); }
+    Prim* prims;                // the records, partitioned in place
     BinaryNode* nodes;
     std::atomic<uint32_t> next_node{1};
     std::atomic<uint32_t> num_leaves{0};
     std::atomic<uint32_t> max_depth{0};
     int max_leaf, bins;
     float trav_cost = 1.0f;     // cost of one node visit relative to one triangle test
+    Prim* tmp = nullptr;        // scratch records for the parallel partition of big nodes (ntris entries)
+
+    // Nodes above this size are processed by several tasks per pass (bounds, binning, partition): near the root a node's
+    // triangle list is the whole scene, and one thread walking it five times is most of the build.  Partial results are
+    // combined with min / max / integer sums and the partition is stable, so the tree is the one the serial passes give.
+    static const uint32_t kBig = 65536, kChunk = 32768;
+    struct BinSet { Aabb bb[3][256]; uint32_t bc[3][256]; };
+
+    template <typename F>
+    void for_chunks(uint32_t begin, uint32_t end, F f)
+    {
+        const uint32_t nchunks = (end - begin + kChunk - 1) / kChunk;
+        for (uint32_t c = 0; c < nchunks; ++c) {
+#pragma omp task default(shared) firstprivate(c)
+            f(c, begin + c * kChunk, std::min(end, begin + (c + 1) * kChunk));
+        }
+#pragma omp taskwait
+    }
 
     void note_depth(uint32_t d)
     {
@@ -66,13 +86,23 @@ struct Builder {
     {
         Aabb box, cbox;
         box_reset(box); box_reset(cbox);
-        for (uint32_t i = begin; i < end; ++i) {
-            const uint32_t p = idx[i];
-            box_grow(box, pb[p]);
-            for (int k = 0; k < 3; ++k) { cbox.lo[k] = std::min(cbox.lo[k], pc[3 * p + k]); cbox.hi[k] = std::max(cbox.hi[k], pc[3 * p + k]); }
-        }
-        nodes[ni].box = box;
         const uint32_t n = end - begin;
+        const bool big = n > kBig;
+        const uint32_t nchunks = big ? (n + kChunk - 1) / kChunk : 0;
+        auto bounds_of = [&](uint32_t b, uint32_t e, Aabb& bx, Aabb& cx) {
+            for (uint32_t i = b; i < e; ++i) {
+                const Prim& p = prims[i];
+                box_grow(bx, p.b);
+                for (int k = 0; k < 3; ++k) { const float c = centre(p, k); cx.lo[k] = std::min(cx.lo[k], c); cx.hi[k] = std::max(cx.hi[k], c); }
+            }
+        };
+        if (big) {
+            std::vector<Aabb> part(2 * (size_t)nchunks);
+            for (auto& a : part) box_reset(a);
+            for_chunks(begin, end, [&](uint32_t c, uint32_t b, uint32_t e) { bounds_of(b, e, part[2 * c], part[2 * c + 1]); });
+            for (uint32_t c = 0; c < nchunks; ++c) { box_grow(box, part[2 * c]); box_grow(cbox, part[2 * c + 1]); }
+        } else bounds_of(begin, end, box, cbox);
+        nodes[ni].box = box;
         if (n <= 1) { make_leaf(ni, begin, end, depth); return; }
 
         // --- binned SAH over the three axes -----------------------------------------------------
@@ -81,20 +111,42 @@ struct Builder {
         float best_cost = kInf;
         // Past depth 40 only median splits are taken, which bounds the depth by 40 + log2(n).
         if (depth < 40) {
-            std::vector<Aabb> bb(B);
-            std::vector<uint32_t> bc(B);
-            std::vector<float> right_area(B);
+            // one pass over the triangles fills the bins of all three axes (the lists are index-permuted, so every pass is a
+            // gather over the per-triangle arrays: three passes cost three times the cache misses)
+            float lo3[3], scale3[3];
+            bool use[3];
             for (int axis = 0; axis < 3; ++axis) {
-                const float lo = cbox.lo[axis], ext = cbox.hi[axis] - cbox.lo[axis];
-                if (!(ext > 0.f)) continue;
-                const float scale = (float)B / ext;
-                for (int b = 0; b < B; ++b) { box_reset(bb[b]); bc[b] = 0; }
-                for (uint32_t i = begin; i < end; ++i) {
-                    const uint32_t p = idx[i];
-                    int b = (int)((pc[3 * p + axis] - lo) * scale);
-                    b = b < 0 ? 0 : (b >= B ? B - 1 : b);
-                    bc[b]++; box_grow(bb[b], pb[p]);
+                const float ext = cbox.hi[axis] - cbox.lo[axis];
+                lo3[axis] = cbox.lo[axis]; use[axis] = ext > 0.f; scale3[axis] = use[axis] ? (float)B / ext : 0.f;
+            }
+            auto fill = [&](BinSet& S, uint32_t b0, uint32_t e0) {
+                for (int axis = 0; axis < 3; ++axis) for (int b = 0; b < B; ++b) { box_reset(S.bb[axis][b]); S.bc[axis][b] = 0; }
+                for (uint32_t i = b0; i < e0; ++i) {
+                    const Prim& p = prims[i];
+                    const Aabb& pbx = p.b;
+                    for (int axis = 0; axis < 3; ++axis) {
+                        if (!use[axis]) continue;
+                        int b = (int)((centre(p, axis) - lo3[axis]) * scale3[axis]);
+                        b = b < 0 ? 0 : (b >= B ? B - 1 : b);
+                        S.bc[axis][b]++; box_grow(S.bb[axis][b], pbx);
+                    }
                 }
+            };
+            static thread_local BinSet local;     // used between here and the split decision only: no task switch in between
+            std::vector<BinSet> sets;
+            if (big) {
+                sets.resize(nchunks);
+                for_chunks(begin, end, [&](uint32_t c, uint32_t b0, uint32_t e0) { fill(sets[c], b0, e0); });
+                for (uint32_t c = 1; c < nchunks; ++c)
+                    for (int axis = 0; axis < 3; ++axis)
+                        for (int b = 0; b < B; ++b) { sets[0].bc[axis][b] += sets[c].bc[axis][b]; box_grow(sets[0].bb[axis][b], sets[c].bb[axis][b]); }
+            } else fill(local, begin, end);
+            const BinSet& S = big ? sets[0] : local;
+            float right_area[256];
+            for (int axis = 0; axis < 3; ++axis) {
+                if (!use[axis]) continue;
+                const Aabb* bb = S.bb[axis];
+                const uint32_t* bc = S.bc[axis];
                 Aabb acc; box_reset(acc);
                 for (int b = B - 1; b > 0; --b) { box_grow(acc, bb[b]); right_area[b] = box_half_area(acc); }
                 box_reset(acc);
@@ -119,13 +171,31 @@ struct Builder {
         if (best_axis >= 0) {
             const float lo = cbox.lo[best_axis], scale = (float)B / (cbox.hi[best_axis] - cbox.lo[best_axis]);
             const int axis = best_axis, split = best_split;
-            const float* c = pc;
-            uint32_t* m = std::partition(idx + begin, idx + end, [=](uint32_t p) {
-                int b = (int)((c[3 * p + axis] - lo) * scale);
+            auto goes_left = [=](const Prim& p) {
+                int b = (int)((centre(p, axis) - lo) * scale);
                 b = b < 0 ? 0 : (b >= B ? B - 1 : b);
                 return b <= split;
-            });
-            mid = (uint32_t)(m - idx);
+            };
+            if (big) {
+                // stable partition in two parallel passes: count per chunk, then scatter to the scratch permutation and copy back
+                std::vector<uint32_t> nleft(nchunks + 1, 0);
+                for_chunks(begin, end, [&](uint32_t ch, uint32_t b0, uint32_t e0) {
+                    uint32_t k = 0;
+                    for (uint32_t i = b0; i < e0; ++i) k += goes_left(prims[i]) ? 1u : 0u;
+                    nleft[ch + 1] = k;
+                });
+                for (uint32_t ch = 0; ch < nchunks; ++ch) nleft[ch + 1] += nleft[ch];
+                const uint32_t total_left = nleft[nchunks];
+                for_chunks(begin, end, [&](uint32_t ch, uint32_t b0, uint32_t e0) {
+                    uint32_t l = begin + nleft[ch], r = begin + total_left + ((b0 - begin) - nleft[ch]);
+                    for (uint32_t i = b0; i < e0; ++i) { const Prim& p = prims[i]; if (goes_left(p)) tmp[l++] = p; else tmp[r++] = p; }
+                });
+                for_chunks(begin, end, [&](uint32_t, uint32_t b0, uint32_t e0) { memcpy(prims + b0, tmp + b0, (size_t)(e0 - b0) * sizeof(Prim)); });
+                mid = begin + total_left;
+            } else {
+                Prim* m = std::partition(prims + begin, prims + end, goes_left);
+                mid = (uint32_t)(m - prims);
+            }
         } else {
             mid = begin;
         }
@@ -136,10 +206,9 @@ struct Builder {
             if (e1 > e0) axis = 1;
             if (e2 > std::max(e0, e1)) axis = 2;
             mid = begin + n / 2;
-            const float* c = pc;
-            std::nth_element(idx + begin, idx + mid, idx + end, [=](uint32_t a, uint32_t b) {
-                const float ca = c[3 * a + axis], cb = c[3 * b + axis];
-                return ca < cb || (ca == cb && a < b);
+            std::nth_element(prims + begin, prims + mid, prims + end, [=](const Prim& a, const Prim& b) {
+                const float ca = centre(a, axis), cb = centre(b, axis);
+                return ca < cb || (ca == cb && a.id < b.id);
             });
         }
         const uint32_t l = next_node.fetch_add(2), r = l + 1;
@@ -196,21 +265,23 @@ BinaryBvh build_binary_sah(const float* tri_vertices, uint32_t ntris, int max_le
         out.nodes.push_back(n); out.num_leaves = 1;
         return out;
     }
-    std::vector<Aabb> pb(ntris);
-    std::vector<float> pc((size_t)ntris * 3);
+    std::vector<Builder::Prim> prims(ntris), scratch(ntris);
 #pragma omp parallel for schedule(static)
     for (int64_t i = 0; i < (int64_t)ntris; ++i) {
-        triangle_bounds(tri_vertices + 9 * i, pb[i]);
-        for (int k = 0; k < 3; ++k) pc[3 * i + k] = 0.5f * (pb[i].lo[k] + pb[i].hi[k]);
+        triangle_bounds(tri_vertices + 9 * i, prims[i].b);
+        prims[i].id = (uint32_t)i; prims[i].pad = 0;
     }
     out.nodes.resize((size_t)2 * ntris);
     Builder b;
-    b.pb = pb.data(); b.pc = pc.data(); b.idx = out.order.data(); b.nodes = out.nodes.data();
+    b.prims = prims.data(); b.nodes = out.nodes.data();
     b.max_leaf = max_leaf; b.bins = bins;
+    b.tmp = scratch.data();
     if (const char* e = getenv("MIROGPU_CTRAV")) { const float v = (float)atof(e); if (v > 0.f && v < 100.f) b.trav_cost = v; }   // tuning knob
 #pragma omp parallel
 #pragma omp single nowait
     b.build(0, 0, ntris, 0);
+#pragma omp parallel for schedule(static)
+    for (int64_t i = 0; i < (int64_t)ntris; ++i) out.order[i] = prims[i].id;
     out.nodes.resize(b.next_node.load());
     out.num_leaves = b.num_leaves.load();
     out.max_depth = b.max_depth.load();

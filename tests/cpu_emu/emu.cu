@@ -5,6 +5,7 @@
 // produces, so the traversal / flattening logic can be checked against the oracle in the CPU test
 // tier (no GPU in the build container).  It is compiled into tests/cpu_emu/libmiro_emu.so and is
 // never linked into libmirogpu.so: the product has no CPU path.
+#include <chrono>
 #include <cstdint>
 #include <cstring>
 #include <vector>
@@ -91,10 +92,16 @@ extern "C" int emu_build(const float* tri_vertices, uint32_t ntris, int layout, 
 {
     if (max_leaf <= 0) max_leaf = layout == MIROGPU_LAYOUT_CWBVH8 ? 3 : 4;
     if (layout == MIROGPU_LAYOUT_CWBVH8 && max_leaf > 3) max_leaf = 3;
+    const auto t0 = std::chrono::steady_clock::now();
     BinaryBvh bin = build_binary_sah(tri_vertices, ntris, max_leaf, 32);
+    const auto t1 = std::chrono::steady_clock::now();
     FlatBvh flat;
     if (layout == 5) layout = 4;
     if (layout == 4) flatten_qbvh4(bin, flat); else if (layout == 3) flatten_bvh4(bin, flat); else if (layout == MIROGPU_LAYOUT_BVH2) flatten_bvh2(bin, flat); else flatten_cwbvh8(bin, flat);
+    if (sizes) {   // seconds of the two phases, as IEEE doubles
+        const double bs = std::chrono::duration<double>(t1 - t0).count(), fs = std::chrono::duration<double>(std::chrono::steady_clock::now() - t1).count();
+        memcpy(&sizes[5], &bs, 8); memcpy(&sizes[6], &fs, 8);
+    }
     const size_t nb = layout == 4 ? flat.nodesq.size() * sizeof(Qbvh4Node) : layout == 3 ? flat.nodes4.size() * sizeof(Bvh4Node)
                                   : layout == MIROGPU_LAYOUT_BVH2 ? flat.nodes2.size() * sizeof(Bvh2Node) : flat.nodes8.size() * sizeof(Cwbvh8Node);
     sizes[0] = nb; sizes[1] = flat.order.size(); sizes[2] = bin.nodes.size(); sizes[3] = bin.num_leaves; sizes[4] = layout >= 3 ? flat.max_stack : flat.max_depth;

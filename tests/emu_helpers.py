@@ -31,7 +31,7 @@ def emu_trace(emu, verts, rays, layout, any_hit=False, max_leaf=0):
 
 def emu_build(emu, verts, layout, max_leaf=0):
     verts = np.ascontiguousarray(verts, np.float32).reshape(-1, 9)
-    sizes = (ctypes.c_uint64 * 5)()
+    sizes = (ctypes.c_uint64 * 8)()
     vp = verts.ctypes.data_as(ctypes.c_void_p)
     emu.emu_build(vp, ctypes.c_uint32(verts.shape[0]), int(layout), int(max_leaf), None, None, None, sizes)
     nodes = np.zeros(sizes[0], np.uint8)
