@@ -8,6 +8,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <memory>
 #include <mutex>
 #include <string>
 #include <vector>
@@ -307,12 +308,17 @@ int mirogpu_scene_create(const float* tri_vertices, const float* tri_normals, co
         node_bytes = lb.node_bytes;   // the host copies for mirogpu_debug_copy_* are fetched from the device on demand
     }
 
-    // shading records in prim-id order: (A, material) e1 e2 nA nB nC
-    std::vector<float4> shade((size_t)ntris * 6);
-    for (size_t i = 0; i < ntris; ++i) {
+    // shading records in prim-id order: (A, material) e1 e2 nA nB nC -- 96 bytes per triangle, written by all host threads
+    // (133 MB for the bench scene: a single thread spends longer here than the device builders spend on the whole tree)
+    const size_t shade_count = (size_t)ntris * 6;
+    std::unique_ptr<float4[]> shade(new float4[std::max<size_t>(shade_count, 1)]);
+    bool bad_material = false;
+#pragma omp parallel for schedule(static) reduction(|| : bad_material)
+    for (int64_t ii = 0; ii < (int64_t)ntris; ++ii) {
+        const size_t i = (size_t)ii;
         const float* v = tri_vertices + 9 * i;
         uint32_t m = material_ids ? material_ids[i] : 0u;
-        if (nmaterials && m >= nmaterials) { delete h; return fail(MIROGPU_ERR_INVALID_ARG, "material id out of range"); }
+        if (nmaterials && m >= nmaterials) { bad_material = true; m = 0u; }
         float4 A = make_float4(v[0], v[1], v[2], 0.f);
         memcpy(&A.w, &m, 4);
         shade[6 * i + 0] = A;
@@ -323,6 +329,11 @@ int mirogpu_scene_create(const float* tri_vertices, const float* tri_normals, co
             else shade[6 * i + 3 + k] = make_float4(0.f, 1.f, 0.f, 0.f);
         }
     }
+    if (bad_material) {
+        if (device_built && lb.d_geom) cudaFree(lb.d_geom);
+        delete h;
+        return fail(MIROGPU_ERR_INVALID_ARG, "material id out of range");
+    }
     std::vector<mirogpu_material> mats;
     if (materials && nmaterials) mats.assign(materials, materials + nmaterials);
     else {
@@ -332,7 +343,7 @@ int mirogpu_scene_create(const float* tri_vertices, const float* tri_normals, co
     }
 
     // ---- upload ------------------------------------------------------------------------------------
-    const size_t tri_bytes = device_built ? lb.tri_bytes : h->h_tris.size() * sizeof(TriRecord), shade_bytes = shade.size() * sizeof(float4);
+    const size_t tri_bytes = device_built ? lb.tri_bytes : h->h_tris.size() * sizeof(TriRecord), shade_bytes = shade_count * sizeof(float4);
     auto bail = [&](cudaError_t e, const char* what) {
         std::string msg = std::string(what) + ": " + cudaGetErrorString(e);
         mirogpu_scene_destroy(h);
@@ -350,7 +361,7 @@ int mirogpu_scene_create(const float* tri_vertices, const float* tri_normals, co
     if ((e = cudaMalloc(&h->d_ticket, 64 * sizeof(unsigned long long))) != cudaSuccess) return bail(e, "cudaMalloc tickets");
     if (!device_built && node_bytes && (e = cudaMemcpy(h->d_nodes, node_src, node_bytes, cudaMemcpyHostToDevice)) != cudaSuccess) return bail(e, "upload nodes");
     if (!device_built && tri_bytes && (e = cudaMemcpy(h->d_tris, h->h_tris.data(), tri_bytes, cudaMemcpyHostToDevice)) != cudaSuccess) return bail(e, "upload triangles");
-    if (shade_bytes && (e = cudaMemcpy(h->d_shade, shade.data(), shade_bytes, cudaMemcpyHostToDevice)) != cudaSuccess) return bail(e, "upload shading records");
+    if (shade_bytes && (e = cudaMemcpy(h->d_shade, shade.get(), shade_bytes, cudaMemcpyHostToDevice)) != cudaSuccess) return bail(e, "upload shading records");
     if ((e = cudaMemcpy(h->d_materials, mats.data(), mats.size() * sizeof(mirogpu_material), cudaMemcpyHostToDevice)) != cudaSuccess) return bail(e, "upload materials");
     if ((e = cudaMemset(h->d_ticket, 0, 64 * sizeof(unsigned long long))) != cudaSuccess) return bail(e, "memset tickets");
     h->nmaterials = (uint32_t)mats.size();
