@@ -1,8 +1,10 @@
 // kernels.cuh -- sm_100a kernels of the ray-intersection engine (included once by mirogpu.cu).
 //
+//   k_trace_hybrid      the default: persistent warps that vote every iteration between node steps and a leaf phase and hand
+//                       finished lanes the next rays of the warp's pool (see the comment above the kernel)
 //   k_trace_simple      one thread per ray, grid covers the batch (bring-up / comparison variant)
 //   k_trace_persistent  persistent warps: grid = SMs x resident CTAs, every warp pulls 32-ray packets from
-//                       a global ticket counter until the batch is drained
+//                       a global ticket counter until the batch is drained (BVH2 coherent batches, CWBVH8)
 //   k_gen_primary       Camera::eyeRay for a block of rows (Camera.cpp:104-161)
 //   k_gen_bounce        Ray::diffuse at every hit (Ray.h:109-122, Utility.h:34-50)
 //   k_resolve_hits      P, N, material from (prim, beta, gamma) (Triangle.cpp:160-166, Scene.cpp:262)
@@ -16,7 +18,7 @@ namespace mirogpu {
 
 struct DeviceScene {
     const float4* nodes;   // BVH2: 4 float4 per node; BVH4: 8 float4 per node; QBVH4: 4 float4 per node; CWBVH8: 5 uint4 per node
-    const float4* tris;    // 3 float4 per triangle, leaf order
+    const float4* tris;    // 4 float4 (64 B) per triangle, leaf order: (A, prim) (B-A, n.x) (C-A, n.y) (n.z, -, -, -)
     const float4* shade;   // 6 float4 per primitive, prim-id order: (A,mat) e1 e2 nA nB nC
     uint32_t num_tris;
 };
