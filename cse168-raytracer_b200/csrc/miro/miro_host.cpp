@@ -82,49 +82,99 @@ void splitFaceToken(char* tok, int& v, int& t, int& n)
 }
 }  // namespace
 
-void TriangleMesh::loadObj(FILE* fp, const Matrix4x4& ctm)
+// OBJ ingest (TriangleMeshLoad.cpp:25-168), same results as the reference's loader bit for bit, organised for speed: the file
+// is read once, cut into the reference's fgets(line, 80) pieces (a longer line continues as a new "line", as there), the
+// numbers of all pieces are parsed by all host threads (strtof / atoi: the conversions sscanf itself performs), and only the
+// order-dependent assembly -- transforms, index tuples, synthesised normals -- runs sequentially over the parsed records.
+namespace {
+struct ObjPiece {
+    const char* p; int len;
+    char kind;            // 'v' vertex, 'n' normal, 'f' face, 0 anything else
+    float f[3];
+    int v[3], n[3];
+};
+inline void parsePiece(ObjPiece& q)
 {
     char line[81];
-    int nv = 0, nf = 0;
-    while (fgets(line, 80, fp)) {               // 80-byte reads: longer lines split, exactly like the reference
-        if (line[0] == 'v') { if (line[1] != 'n' && line[1] != 't') nv++; }
-        else if (line[0] == 'f') nf++;
+    memcpy(line, q.p, (size_t)q.len); line[q.len] = 0;
+    if (q.kind == 'v' || q.kind == 'n') {
+        char* c = line + (q.kind == 'n' ? 2 : 1);
+        q.f[0] = q.f[1] = q.f[2] = 0.f;
+        for (int k = 0; k < 3; ++k) { char* e = 0; const float x = strtof(c, &e); if (e == c) break; q.f[k] = x; c = e; }
+    } else if (q.kind == 'f') {
+        char* c = line + 1;
+        for (int k = 0; k < 3; ++k) {
+            while (*c == ' ' || *c == '\t' || *c == '\n' || *c == '\r' || *c == '\v' || *c == '\f') ++c;
+            char* tok = c;
+            while (*c && !(*c == ' ' || *c == '\t' || *c == '\n' || *c == '\r' || *c == '\v' || *c == '\f')) ++c;
+            if (*c) *c++ = 0;
+            int t = 0;
+            splitFaceToken(tok, q.v[k], t, q.n[k]);
+        }
     }
+}
+}  // namespace
+
+void TriangleMesh::loadObj(FILE* fp, const Matrix4x4& ctm)
+{
+    fseek(fp, 0, SEEK_END);
+    const long fsize = ftell(fp);
     fseek(fp, 0, SEEK_SET);
+    std::vector<char> text((size_t)std::max(fsize, 0L) + 1);
+    const size_t got = fsize > 0 ? fread(text.data(), 1, (size_t)fsize, fp) : 0;
+    text[got] = 0;
+    // the pieces fgets(line, 80, fp) would return: up to 79 bytes, ending after a newline if one comes first
+    std::vector<ObjPiece> pieces;
+    pieces.reserve(got / 24 + 16);
+    int nv = 0, nf = 0;
+    for (size_t s0 = 0; s0 < got;) {
+        const size_t lim = std::min(got - s0, (size_t)79);
+        const void* nl = memchr(text.data() + s0, '\n', lim);
+        const size_t len = nl ? (size_t)((const char*)nl - (text.data() + s0)) + 1 : lim;
+        ObjPiece q;
+        q.p = text.data() + s0; q.len = (int)len; q.kind = 0;
+        const char c0 = q.p[0], c1 = len > 1 ? q.p[1] : 0;
+        if (c0 == 'v') { if (c1 == 'n') q.kind = 'n'; else if (c1 != 't') { q.kind = 'v'; nv++; } }
+        else if (c0 == 'f') { q.kind = 'f'; nf++; }
+        q.v[0] = q.v[1] = q.v[2] = q.n[0] = q.n[1] = q.n[2] = 0;
+        pieces.push_back(q);
+        s0 += len;
+    }
+#pragma omp parallel for schedule(static)
+    for (long i = 0; i < (long)pieces.size(); ++i)
+        if (pieces[i].kind) parsePiece(pieces[i]);
+
     const int ncap = std::max(nv, nf * 3);
     m_normals = new Vector3[ncap];
     m_vertices = new Vector3[nv];
     m_numVertices = nv;
     m_normalIndices = new TupleI3[nf];
     m_vertexIndices = new TupleI3[nf];
-    std::vector<std::vector<int> > around(nv);   // normal slots touching each vertex
     std::vector<char> synthesised(ncap, 0);
     Matrix4x4 nctm = ctm;
     nctm.invert();
     nctm.transpose();
     int nverts = 0, nnormals = 0;
     m_numTris = 0;
-    while (fgets(line, 80, fp)) {
-        if (line[0] == 'v' && line[1] == 'n') {
-            float x, y, z; sscanf(&line[2], "%f %f %f\n", &x, &y, &z);
-            m_normals[nnormals] = nctm * Vector3(x, y, z);
+    // normal slots touching each vertex, in order of appearance: (vertex, slot) pairs now, grouped per vertex below
+    std::vector<std::pair<int, int> > touch;
+    touch.reserve((size_t)nf * 3);
+    for (size_t pi = 0; pi < pieces.size(); ++pi) {
+        const ObjPiece& q = pieces[pi];
+        if (q.kind == 'n') {
+            m_normals[nnormals] = nctm * Vector3(q.f[0], q.f[1], q.f[2]);
             m_normals[nnormals].normalize();
             nnormals++;
-        } else if (line[0] == 'v' && line[1] == 't') {
-            // texture coordinates are not used on this path
-        } else if (line[0] == 'v') {
-            float x, y, z; sscanf(&line[1], "%f %f %f\n", &x, &y, &z);
-            m_vertices[nverts++] = ctm * Vector3(x, y, z);
-        } else if (line[0] == 'f') {
-            char tok[3][32];
-            sscanf(&line[1], "%s %s %s\n", tok[0], tok[1], tok[2]);
+        } else if (q.kind == 'v') {
+            m_vertices[nverts++] = ctm * Vector3(q.f[0], q.f[1], q.f[2]);
+        } else if (q.kind == 'f') {
             TupleI3& vi = m_vertexIndices[m_numTris];
             TupleI3& ni = m_normalIndices[m_numTris];
-            int v = 0, t = 0, n = 0;
+            int n = 0;
             for (int k = 0; k < 3; ++k) {
-                splitFaceToken(tok[k], v, t, n);
-                vi.v[k] = v - 1;
-                if (n) { ni.v[k] = n - 1; around[v - 1].push_back(n - 1); }
+                n = q.n[k];
+                vi.v[k] = q.v[k] - 1;
+                if (n) { ni.v[k] = n - 1; touch.push_back(std::make_pair(q.v[k] - 1, n - 1)); }
             }
             if (!n) {   // the LAST token decides, as in the reference
                 const Vector3 e1 = m_vertices[vi.v[1]] - m_vertices[vi.v[0]];
@@ -134,21 +184,29 @@ void TriangleMesh::loadObj(FILE* fp, const Matrix4x4& ctm)
                     m_normals[nnormals].normalize();
                     synthesised[nnormals] = 1;
                     ni.v[k] = nnormals;
-                    around[vi.v[k]].push_back(nnormals);
+                    touch.push_back(std::make_pair(vi.v[k], nnormals));
                     nnormals++;
                 }
             }
             m_numTris++;
         }
     }
+    // group the touches per vertex, keeping their order (counting sort)
+    std::vector<int> start((size_t)nv + 1, 0), slots(touch.size());
+    for (size_t j = 0; j < touch.size(); ++j) if (touch[j].first >= 0 && touch[j].first < nv) start[(size_t)touch[j].first + 1]++;
+    for (int i = 0; i < nv; ++i) start[(size_t)i + 1] += start[i];
+    {
+        std::vector<int> fill(start.begin(), start.end() - 1);
+        for (size_t j = 0; j < touch.size(); ++j) if (touch[j].first >= 0 && touch[j].first < nv) slots[(size_t)fill[touch[j].first]++] = touch[j].second;
+    }
     for (int i = 0; i < nverts; ++i) {
-        const std::vector<int>& a = around[i];
-        if (a.empty()) continue;
+        const int b0 = start[i], e0 = start[(size_t)i + 1];
+        if (b0 == e0) continue;
         Vector3 avg;                             // default-constructed: (0,1,2), as the reference accumulates from
-        for (size_t j = 0; j < a.size(); ++j) avg += m_normals[a[j]];
-        avg /= (float)a.size();
+        for (int j = b0; j < e0; ++j) avg += m_normals[slots[j]];
+        avg /= (float)(e0 - b0);
         avg.normalize();
-        for (size_t j = 0; j < a.size(); ++j) if (synthesised[a[j]]) m_normals[a[j]] = avg;
+        for (int j = b0; j < e0; ++j) if (synthesised[slots[j]]) m_normals[slots[j]] = avg;
     }
 }
 
