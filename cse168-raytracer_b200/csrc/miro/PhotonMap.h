@@ -30,6 +30,7 @@ public:
     const Photon* data() const { return photons; }
 private:
     void balance_segment(Photon** pbal, Photon** porg, const int index, const int start, const int end);
+    void balance_segment_box(Photon** pbal, Photon** porg, int index, int start, int end, const float* lo3, const float* hi3);
     void median_split(Photon** p, const int start, const int end, const int median, const int axis);
     Photon* photons;
     int stored_photons, half_stored_photons, max_photons, prev_scale;

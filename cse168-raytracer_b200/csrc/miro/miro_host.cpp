@@ -625,35 +625,46 @@ void Photon_map::median_split(Photon** p, const int start, const int end, const 
     }
 }
 
-void Photon_map::balance_segment(Photon** pbal, Photon** porg, const int index, const int start, const int end)
+// PhotonMap.cpp:404-466.  The reference narrows the member bounding box around each recursive call and restores it
+// afterwards; here the box travels by value, which makes the two sub-segments independent -- they own disjoint runs of porg
+// and disjoint heap slots of pbal -- so large ones are balanced as parallel tasks.  Same medians, same axes, same array.
+void Photon_map::balance_segment_box(Photon** pbal, Photon** porg, int index, int start, int end, const float* lo3, const float* hi3)
 {
+    float lo[3] = {lo3[0], lo3[1], lo3[2]}, hi[3] = {hi3[0], hi3[1], hi3[2]};
     // left-balanced median (Jensen, "Realistic Image Synthesis using Photon Mapping", ch. 6)
     const int count = end - start + 1;
     int median = 1;
     while (4 * median <= count) median += median;
     if (3 * median <= count) median = 2 * median + start - 1; else median = end - median + 1;
     int axis = 2;
-    const float ex = bbox_max[0] - bbox_min[0], ey = bbox_max[1] - bbox_min[1], ez = bbox_max[2] - bbox_min[2];
+    const float ex = hi[0] - lo[0], ey = hi[1] - lo[1], ez = hi[2] - lo[2];
     if (ex > ey && ex > ez) axis = 0; else if (ey > ez) axis = 1;
     median_split(porg, start, end, median, axis);
     pbal[index] = porg[median];
     pbal[index]->plane = (short)axis;
-    if (median > start) {
-        if (start < median - 1) {
-            const float keep = bbox_max[axis];
-            bbox_max[axis] = pbal[index]->pos[axis];
-            balance_segment(pbal, porg, 2 * index, start, median - 1);
-            bbox_max[axis] = keep;
-        } else pbal[2 * index] = porg[start];
+    const float split = pbal[index]->pos[axis];
+    const bool left_rec = median > start && start < median - 1, right_rec = median < end && median + 1 < end;
+    if (median > start && !left_rec) pbal[2 * index] = porg[start];
+    if (median < end && !right_rec) pbal[2 * index + 1] = porg[end];
+    float lhi[3] = {hi[0], hi[1], hi[2]}, rlo[3] = {lo[0], lo[1], lo[2]};
+    lhi[axis] = split; rlo[axis] = split;
+    if (count > 16384 && left_rec && right_rec) {
+#pragma omp task default(shared) firstprivate(index, start, median, lo, lhi)
+        balance_segment_box(pbal, porg, 2 * index, start, median - 1, lo, lhi);
+#pragma omp task default(shared) firstprivate(index, median, end, rlo, hi)
+        balance_segment_box(pbal, porg, 2 * index + 1, median + 1, end, rlo, hi);
+#pragma omp taskwait
+    } else {
+        if (left_rec) balance_segment_box(pbal, porg, 2 * index, start, median - 1, lo, lhi);
+        if (right_rec) balance_segment_box(pbal, porg, 2 * index + 1, median + 1, end, rlo, hi);
     }
-    if (median < end) {
-        if (median + 1 < end) {
-            const float keep = bbox_min[axis];
-            bbox_min[axis] = pbal[index]->pos[axis];
-            balance_segment(pbal, porg, 2 * index + 1, median + 1, end);
-            bbox_min[axis] = keep;
-        } else pbal[2 * index + 1] = porg[end];
-    }
+}
+
+void Photon_map::balance_segment(Photon** pbal, Photon** porg, const int index, const int start, const int end)
+{
+#pragma omp parallel
+#pragma omp single nowait
+    balance_segment_box(pbal, porg, index, start, end, bbox_min, bbox_max);
 }
 
 void Photon_map::balance(void)

@@ -79,9 +79,9 @@ def test_host_ingest_with_transforms(pkg, oracle, scenes):
     assert np.array_equal(bits(oracle.dump_triangles()), bits(H.dump_triangles()))
 
 
-def test_host_photon_balance_matches_reference_semantics(pkg, oracle):
+@pytest.mark.parametrize("n", [4097, 70001])      # the larger map goes through the task-parallel segments of the host balance
+def test_host_photon_balance_matches_reference_semantics(pkg, oracle, n):
     rng = np.random.default_rng(9)
-    n = 4097
     pos = rng.random((n, 3), dtype=np.float32) * 3
     d = rng.normal(size=(n, 3)).astype(np.float32); d /= np.linalg.norm(d, axis=1, keepdims=True)
     pw = rng.random((n, 3), dtype=np.float32)
