@@ -407,7 +407,8 @@ void flatten_bvh4(const BinaryBvh& b, FlatBvh& out)
             if (b.nodes[ch[i]].left >= 0) stack.push_back({(uint32_t)ch[i], it.depth + 1, it.pending + (uint32_t)(k - 1)});
     }
     out.nodes4.resize(wide_order.size());
-    for (size_t i = 0; i < wide_order.size(); ++i) {
+#pragma omp parallel for schedule(static)
+    for (int64_t i = 0; i < (int64_t)wide_order.size(); ++i) {   // every wide node is written from the binary tree alone
         Bvh4Node fn = blank();
         int32_t ch[4];
         const int k = collect(wide_order[i], ch);
