@@ -530,7 +530,7 @@ inline cudaError_t build_lbvh_device(const float* tri_vertices, uint32_t ntris, 
                 int new_m = 0;
                 LB(cudaMemcpyAsync(&new_m, d_m, 4, cudaMemcpyDeviceToHost, st));
                 LB(cudaStreamSynchronize(st));
-                if (new_m >= m || new_m < 1) { cleanup(); cudaFree(o.d_geom); o.d_geom = nullptr; return cudaErrorUnknown; }   // cannot happen: a mutual pair always exists
+                if (new_m >= m || new_m < 1) { cleanup(); cudaFree(o.d_geom); o.d_geom = nullptr; return cudaErrorNotSupported; }   // cannot happen: a mutual pair always exists
                 m = new_m; cur ^= 1;
             }
             k_ploc_ranges<<<(unsigned)((2 * n - 1 + 255) / 256), 256, 0, st>>>((int)(2 * n - 1), child, parent, size, range, pc + 1);
@@ -538,7 +538,9 @@ inline cudaError_t build_lbvh_device(const float* tri_vertices, uint32_t ntris, 
             LB(cudaMemcpyAsync(h_pc, pc, 8, cudaMemcpyDeviceToHost, st));
             LB(cudaStreamSynchronize(st));
             if (dbg) fprintf(stderr, "ploc rounds %d, clustering + ranges %.3f ms\n", rounds, 1e3 * std::chrono::duration<double>(std::chrono::steady_clock::now() - tp0).count());
-            if (m != 1 || h_pc[0] != n - 1 || h_pc[1] != 0) { cleanup(); cudaFree(o.d_geom); o.d_geom = nullptr; return cudaErrorUnknown; }
+            // cudaErrorNotSupported = "this builder gives up on this input" (thousands of coincident boxes merge one pair per round and run
+            // into the round cap; a chain deeper than the walk cap): the caller falls back to the host builder
+            if (m != 1 || h_pc[0] != n - 1 || h_pc[1] != 0) { cleanup(); cudaFree(o.d_geom); o.d_geom = nullptr; return cudaErrorNotSupported; }
             // triangles in the depth-first order of the agglomerated tree: every subtree is a contiguous run again
             k_ploc_order<<<g256, 256, 0, st>>>((int)n, idx, range, idx2);
             std::swap(idx, idx2);

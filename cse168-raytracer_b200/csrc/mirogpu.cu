@@ -274,9 +274,10 @@ int mirogpu_scene_create(const float* tri_vertices, const float* tri_normals, co
     bool device_built = false;
     if (device_builder) {
         const cudaError_t be = build_lbvh_device(tri_vertices, ntris, std::min(o.max_leaf, 4), lb, o.builder == MIROGPU_BUILDER_PLOC_DEVICE);
-        if (be != cudaSuccess) { delete h; return fail(be == cudaErrorMemoryAllocation ? MIROGPU_ERR_OOM : MIROGPU_ERR_CUDA, std::string("device BVH build: ") + cudaGetErrorString(be)); }
-        if (lb.max_stack <= MIRO_STACK4) device_built = true;
-        else { cudaFree(lb.d_geom); lb.d_geom = nullptr; }   // a Morton tree too deep for the kernels' stacks: use the host builder
+        if (be == cudaErrorNotSupported) lb.d_geom = nullptr;   // the device builder gave up on this input (see lbvh_impl.cuh): use the host builder
+        else if (be != cudaSuccess) { delete h; return fail(be == cudaErrorMemoryAllocation ? MIROGPU_ERR_OOM : MIROGPU_ERR_CUDA, std::string("device BVH build: ") + cudaGetErrorString(be)); }
+        else if (lb.max_stack <= MIRO_STACK4) device_built = true;
+        else { cudaFree(lb.d_geom); lb.d_geom = nullptr; }   // a tree too deep for the kernels' stacks: use the host builder
     }
     // ---- host build ------------------------------------------------------------------------------
     BinaryBvh bin;
