@@ -41,9 +41,31 @@ SEED = 168
 FALLBACK_VT = {"primary": (18.48, 3.37), "bounce": (22.43, 4.70)}
 
 
-def workload(ntris):
-    return (f"{SCENE}: reference makeBunny20Scene geometry ({ntris} triangles) and camera, declared stand-in for BASELINE config 3's "
-            f"sponza.obj (absent from the reference tree); {WIDTH}x{HEIGHT}, {SPP} jittered samples per step, one Ray::diffuse bounce ray per hit")
+NTRIS = 1389021   # makeBunny20Scene: 20 x 69 451 bunny triangles + the floor triangle (checked against the built scene)
+
+
+def workload(ntris=NTRIS):
+    return (f"{SCENE}: the reference's makeBunny20Scene geometry ({ntris} triangles, bit-identical to the script's: tests/test_scene_scripts.py) and camera, "
+            f"declared stand-in for BASELINE config 3's sponza.obj (absent from the reference tree); {WIDTH}x{HEIGHT}, {SPP} jittered samples per step, "
+            f"one Ray::diffuse bounce ray per hit")
+
+
+def shared_config():
+    """The `config` both arms print, key for key: one workload.  What differs per arm (how much of a step a CPU step samples,
+    kernel and layout choices, measured figures) goes under `detail`."""
+    return {"workload": workload(), "scene": SCENE, "triangles": NTRIS, "width": WIDTH, "height": HEIGHT, "samples_per_step": SPP,
+            "rays": "jittered Camera::eyeRay -> closest hit -> one Ray::diffuse per hit -> closest hit", "seed": SEED,
+            "l2": "inputs larger than L2: each step writes and re-reads its ray / hit buffers (3.2 GB per step at N = 1, 96 B per ray) between "
+                  "kernels, far beyond the 126 MB L2; no explicit flush"}
+
+
+def load_scenes():
+    """scenes.py by path: the CPU arms must not import the package (which maps libmirogpu.so)."""
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("_miro_scenes", os.path.join(ROOT, "cse168-raytracer_b200", "scenes.py"))
+    m = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(m)
+    return m
 
 
 _REAL_STDOUT = None
@@ -132,119 +154,141 @@ def build_host_scene(pkg, scenes, layout):
 
 
 # ------------------------------------------------------------------------------------------------------------------
-def cpu_leg(rays_p, rays_b, want_counters=True, kind_pref="reference"):
-    """Times the reference's CPU path (oracle/_ref; else the oracle port) on the given rays with all host threads,
-    and measures V, T per ray with the oracle's exact counters on a subsample."""
+def _quiet():
+    """Context: file descriptor 1 -> /dev/null (the reference prints progress to stdout)."""
+    class Q:
+        def __enter__(self):
+            self.devnull = os.open(os.devnull, os.O_WRONLY); self.saved = os.dup(1); os.dup2(self.devnull, 1)
+        def __exit__(self, *a):
+            os.dup2(self.saved, 1); os.close(self.devnull); os.close(self.saved)
+    return Q()
+
+
+def measure_vt(rays_p, rays_b, threads):
+    """V (node entries) and T (triangle tests) per ray of the SCALAR REFERENCE on these rays: the oracle restatement's counters
+    (bit-exact with the reference's -DSTATS build, tests/test_oracle_vs_reference.py)."""
     import miro_driver as md
     import objio
-    scenes = importlib.import_module("cse168-raytracer_b200.scenes")
+    scenes = load_scenes()
+    O = md.oracle()
+    with _quiet():
+        scenes.realise(O, SCENE, objio.obj_path)
+        O.precalc()
+        vt = {}
+        for name, r in (("primary", rays_p), ("bounce", rays_b)):
+            O.stats_reset_rays()
+            O.trace(r, threads)
+            st = O.stats()
+            vt[name] = (st["ray_box"] / max(1, r.shape[0]), st["ray_tri"] / max(1, r.shape[0]))
+        st = O.stats()
+    return vt, (st["nodes"], st["leaves"])
+
+
+def cpu_leg(rays_p, rays_b, kind_pref="reference"):
+    """Times the reference's CPU path (oracle/_ref; else the oracle port) on the given rays with all host threads and KEEPS its
+    answers (t, prim id) for the parity block."""
+    import miro_driver as md
+    import objio
+    scenes = load_scenes()
     cores = os.cpu_count() or 1
     out = {}
     kind = "reference" if (kind_pref == "reference" and os.path.exists(md.REF_SO)) else "port"
     D = md.reference("scalar") if kind == "reference" else md.oracle()
-    devnull = os.open(os.devnull, os.O_WRONLY)
-    saved = os.dup(1)
-    os.dup2(devnull, 1)   # the reference prints progress to stdout; keep the JSON line clean
-    try:
+    rays = np.concatenate([rays_p, rays_b])
+    with _quiet():
         scenes.realise(D, SCENE, objio.obj_path)
         build_s = D.precalc()
-        rays = np.concatenate([rays_p, rays_b])
-        D.trace_time(rays[:100000], 0)   # warm the caches / thread pool
-        secs, hits = D.trace_time(rays, 0)
-    finally:
-        os.dup2(saved, 1)
-        os.close(devnull)
+        D.trace_time(rays[:100000], cores)   # warm the caches / thread pool
+        secs, t, ids = D.trace_time_hits(rays, cores)
+    out["hits"] = (t, ids)
     out["cpu"] = dict(value=rays.shape[0] / secs / 1e6, unit="Mrays/s", cores=cores, kind=kind,
                       sample=f"{rays_p.shape[0]} primary + {rays_b.shape[0]} live bounce rays = one whole step ({SPP} samples of {WIDTH}x{HEIGHT}, the GPU's own rays), "
-                             f"Scene::trace over OpenMP dynamic chunks of 4096; reference BVH build {build_s:.1f} s not timed",
+                             f"Scene::trace over OpenMP dynamic chunks of 4096 on {cores} threads, (t, object) kept per ray; reference BVH build {build_s:.1f} s not timed",
                       seconds=secs)
     # SURVEY 8d: also the reference's shipped configuration (-msse4.1: 4-wide box tests with _mm_rcp_ps, triangle packets; not
     # parity grade) as a second throughput baseline on the same rays
     if kind == "reference" and os.path.exists(md.REF_SSE_SO):
         E = md.reference("sse")
-        devnull = os.open(os.devnull, os.O_WRONLY)
-        saved = os.dup(1)
-        os.dup2(devnull, 1)
-        try:
+        with _quiet():
             scenes.realise(E, SCENE, objio.obj_path)
             E.precalc()
-            E.trace_time(rays[:100000], 0)
-            secs_sse, _ = E.trace_time(rays, 0)
-        finally:
-            os.dup2(saved, 1)
-            os.close(devnull)
+            E.trace_time(rays[:100000], cores)
+            secs_sse, _ = E.trace_time(rays, cores)
         out["cpu"]["sse_build"] = dict(value=rays.shape[0] / secs_sse / 1e6, unit="Mrays/s", seconds=secs_sse,
                                        note="the reference compiled with -msse4.1 (Makedefs:14-15), same rays, same threads")
-    if want_counters:
-        O = D if kind == "port" else md.oracle()
-        if kind != "port":
-            scenes.realise(O, SCENE, objio.obj_path)
-            O.precalc()
-        vt = {}
-        for name, r in (("primary", rays_p[::16]), ("bounce", rays_b[::16])):
-            O.stats_reset_rays()
-            O.trace(r, 0)
-            st = O.stats()
-            vt[name] = (st["ray_box"] / r.shape[0], st["ray_tri"] / r.shape[0])
-        out["vt"] = vt
-        st = O.stats()
-        out["ref_nodes"] = (st["nodes"], st["leaves"])
     return out
+
+
+def parity_block(gpu_hits, ref_t, ref_id):
+    """GPU closest hits against the reference's Scene::trace on the same rays (north_star: ids exact except <= 1e-5 of rays in the
+    documented classes, t within 1e-5 relative)."""
+    n = int(ref_id.shape[0])
+    gid = gpu_hits[:, 1].copy().view(np.int32)          # MIROGPU_MISS = 0xFFFFFFFF reads as -1, the reference's miss id
+    gt = gpu_hits[:, 0]
+    mism = gid != ref_id
+    both = (~mism) & (ref_id >= 0)
+    rel = np.abs(gt[both].astype(np.float64) - ref_t[both]) / np.maximum(np.abs(ref_t[both].astype(np.float64)), 1e-30)
+    bit_same = gt.view(np.uint32) == ref_t.view(np.uint32)
+    mi = np.flatnonzero(mism)
+    ties = int(np.count_nonzero(gt[mi] == ref_t[mi]))
+    gpu_closer = int(np.count_nonzero(gt[mi] < ref_t[mi]))      # hits the reference's own tree culls (its boxes lack the slop band)
+    gpu_farther = int(np.count_nonzero(gt[mi] > ref_t[mi]))     # would be a hit the GPU lost: must be 0
+    return {"rays": n, "against": "the reference's Scene::trace (oracle/_ref, scalar build) on the identical rays of the last timed step",
+            "id_mismatches": int(mi.shape[0]), "id_mismatch_frac": float(mi.shape[0]) / max(1, n),
+            "mismatch_classes": {"equal_t_tie": ties, "gpu_closer_reference_culled": gpu_closer, "gpu_farther": gpu_farther},
+            "max_rel_t": float(rel.max()) if rel.size else 0.0, "t_bit_identical_frac": float(np.count_nonzero(bit_same)) / max(1, n),
+            "gate": "id_mismatch_frac <= 1e-5 and max_rel_t <= 1e-5 and gpu_farther == 0"}
 
 
 # ------------------------------------------------------------------------------------------------------------------
 def run_reference(args):
-    """The reference's own CPU implementation of the path on the box's host cores (rank 0 only)."""
+    """The reference's own CPU implementation of the path on the box's host cores (rank 0 only).  A step of this arm is ONE
+    of the workload's 16 samples of the frame (2 073 600 jittered camera rays + a Ray::diffuse bounce ray per hit), so that
+    --steps 20 --warmup 5 ends within minutes; the rate is per ray, so it compares directly."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
+    import ctypes
     import miro_driver as md
     import objio
-    scenes = importlib.import_module("cse168-raytracer_b200.scenes")
+    scenes = load_scenes()
     cores = os.cpu_count() or 1
     kind = "reference" if os.path.exists(md.REF_SO) else "port"
     D = md.reference("scalar") if kind == "reference" else md.oracle()
     O = md.oracle()
-    devnull = os.open(os.devnull, os.O_WRONLY)
-    saved = os.dup(1)
-    os.dup2(devnull, 1)
-    try:
+    threads = D.host_threads()
+    with _quiet():
         scenes.realise(D, SCENE, objio.obj_path)
         build_s = D.precalc()
         scenes.realise(O, SCENE, objio.obj_path)   # camera + Ray::diffuse restatement for ray generation (no BVH build)
-        # bounded sample per step: every 4th row of one jittered sample of the frame + its bounce rays
-        rows = np.arange(0, HEIGHT, 4)
         rng = np.random.default_rng(SEED)
-        import ctypes
         times, nrays = [], []
+        D.trace_time(np.zeros((100000, 8), np.float32), threads)   # thread pool up
         for it in range(args.warmup + args.steps):
             jit = rng.random((WIDTH * HEIGHT, 2), dtype=np.float32)
-            full = np.zeros((WIDTH * HEIGHT, 8), np.float32)
-            O.lib.orc_eye_rays_jitter(WIDTH, HEIGHT, md._fp(jit), md._fp(full))
-            rays = np.ascontiguousarray(full.reshape(HEIGHT, WIDTH, 8)[rows].reshape(-1, 8))
-            s_primary, _ = D.trace_time(rays, 0)          # timed: Scene::trace over all host threads, no output traffic
-            t, ids, P, N = D.trace(rays, 0)               # untimed: the hits, to generate the bounce rays from
+            rays = np.zeros((WIDTH * HEIGHT, 8), np.float32)
+            O.lib.orc_eye_rays_jitter(WIDTH, HEIGHT, md._fp(jit), md._fp(rays))
+            s_primary, _ = D.trace_time(rays, threads)     # timed: Scene::trace over all host threads, no output traffic
+            t, ids, P, N = D.trace(rays, threads)          # untimed: the hits, to generate the bounce rays from
             u = rng.random((rays.shape[0], 2), dtype=np.float32)
             br = np.zeros_like(rays)
             O.lib.orc_diffuse_rays(md._fp(P), md._fp(N), md._fp(ids), md._fp(u), ctypes.c_long(rays.shape[0]), md._fp(br))
             br = np.ascontiguousarray(br[ids >= 0])
-            s_bounce, _ = D.trace_time(br, 0)
+            s_bounce, _ = D.trace_time(br, threads)
             if it >= args.warmup:
                 times.append(s_primary + s_bounce); nrays.append(rays.shape[0] + br.shape[0])
-    finally:
-        os.dup2(saved, 1)
-        os.close(devnull)
     total_t, total_r = float(np.sum(times)), int(np.sum(nrays))
     value = total_r / total_t / 1e6
+    sample = (f"{total_r // max(1, args.steps)} rays per step = one of the workload's {SPP} samples of the {WIDTH}x{HEIGHT} frame + its bounce rays, "
+              f"Scene::trace per ray, OpenMP dynamic chunks of 4096 on {threads} host threads ({cores} logical CPUs)")
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": "Mrays/s", "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": 1e3 * total_t / max(1, args.steps), "higher_is_better": True, "scaling": "strong",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": workload(D.num_objects()),
-                   "sample": "per step every 4th row of one jittered sample of the frame + one Ray::diffuse bounce ray per hit, closest-hit through Scene::trace",
-                   "rays_per_step": total_r // max(1, args.steps), "threads": cores, "bvh_build_s": build_s},
-        "cpu_baseline": {"value": value, "unit": "Mrays/s", "cores": cores, "kind": kind,
-                         "sample": f"{total_r // max(1, args.steps)} rays per step (270 of 1080 rows of one sample + bounce), OpenMP over all host threads"},
+        "config": shared_config(),
+        "detail": {"sample": sample, "rays_per_step": total_r // max(1, args.steps), "threads": threads, "bvh_build_s": build_s,
+                   "library": "oracle/_ref/libmiro_ref.so (the unmodified reference, scalar build)" if kind == "reference" else "oracle/libmiro_oracle.so (port)"},
+        "cpu_baseline": {"value": value, "unit": "Mrays/s", "cores": threads, "kind": kind, "sample": sample},
         "e2e": {"value": value, "unit": "Mrays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     emit(line)
@@ -284,6 +328,7 @@ def run_ours(args):
     index_base = (rank * 0x01000000) & 0xFFFFFFFF
 
     def step(it, ev=None):
+        if ev: ev[4].record()
         S.generate_primary(cam, WIDTH, HEIGHT, d_rays, rows=rows, jitter=1, seed=SEED, sample=it * SPP, samples=SPP)
         if ev: ev[0].record()
         S.intersect_device(d_rays, d_hits, mode=pkg.CLOSEST_HIT | pkg.HINT_COHERENT)
@@ -305,7 +350,7 @@ def run_ours(args):
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
-    evs = [[torch.cuda.Event(enable_timing=True) for _ in range(4)] for _ in range(args.steps)]
+    evs = [[torch.cuda.Event(enable_timing=True) for _ in range(5)] for _ in range(args.steps)]
     t_begin, t_end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
     t_begin.record()
@@ -319,6 +364,8 @@ def run_ours(args):
     live_local = int(d_live.item())
     prim_ms = float(np.mean([e[0].elapsed_time(e[1]) for e in evs]))
     bounce_ms = float(np.mean([e[2].elapsed_time(e[3]) for e in evs]))
+    genb_ms = float(np.mean([e[1].elapsed_time(e[2]) for e in evs]))
+    genp_ms = float(np.mean([e[4].elapsed_time(e[0]) for e in evs]))
 
     # ---- e2e: Scene::raytraceImage-shaped call, host framebuffer out, every step --------------------------------
     e2e_steps = args.steps
@@ -326,6 +373,9 @@ def run_ours(args):
                         rows=rows, shadows=0)
     host_fb = torch.empty((HEIGHT, WIDTH, 3), dtype=torch.uint8).pin_memory()   # the reference's Image: 3 bytes per pixel
     e2e_rays = 0
+    e2e_call = "mirogpu_render_rgb8 (Scene::raytraceImage -> 8-bit Image), diffuse-bounce mode, pinned host framebuffer; rays = primary + LIVE bounce rays"
+    if world > 1:
+        e2e_call += " per rank -> all_reduce(max) of the tone-map constant, 8-bit rows, NCCL all_gather of the row shards, rank 0 copies the frame to the host"
     if world == 1:
         def e2e_step(it):
             p.seed = SEED + it
@@ -363,73 +413,120 @@ def run_ours(args):
         clocks = sampler.stop()
 
     # ---- aggregate over ranks: max time, summed rays ------------------------------------------------------------
-    stats = torch.tensor([ms_local, e2e_s_local, prim_ms, bounce_ms], dtype=torch.float64, device=dev)
+    stats = torch.tensor([ms_local, e2e_s_local, prim_ms, bounce_ms, genb_ms, genp_ms], dtype=torch.float64, device=dev)
     sums = torch.tensor([float(n * args.steps), float(live_local), float(e2e_rays)], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(stats, op=dist.ReduceOp.MAX)
         dist.all_reduce(sums, op=dist.ReduceOp.SUM)
-    ms_total, e2e_s, prim_ms, bounce_ms = [float(x) for x in stats.tolist()]
+    ms_total, e2e_s, prim_ms, bounce_ms, genb_ms, genp_ms = [float(x) for x in stats.tolist()]
     prim_total, live_total, e2e_total = [float(x) for x in sums.tolist()]
     rays_total = prim_total + live_total
     value = rays_total / (ms_total * 1e-3) / 1e6
     e2e_value = e2e_total / e2e_s / 1e6
 
     line = None
+    rc = 0
     if rank == 0:
         peak, peak_src = peaks()
-        cpu, vt, ref_nodes = None, dict(FALLBACK_VT), None
+        cpu, vt, ref_nodes, parity = None, dict(FALLBACK_VT), None, None
         vt_src = "SURVEY 8d figures (oracle not run)"
+        threads = os.cpu_count() or 1
+        # the rays of the last timed step, exactly as the GPU generated them (all SPP samples of this rank's rows)
+        rp = d_rays.cpu().numpy()
+        rb_all = d_b.cpu().numpy()
+        live = rb_all[:, 7] >= rb_all[:, 3]
+        rb = np.ascontiguousarray(rb_all[live])
+        del rb_all
+        if not args.no_cpu:
+            try:
+                # V, T per ray: the scalar reference's counters on every 16th of this rank's rays -- at every N, so that the
+                # roofline fractions of a scaling run are comparable
+                vt, ref_nodes = measure_vt(rp[::16], rb[::16], threads)
+                vt_src = "scalar reference counters (oracle restatement, bit-exact with -DSTATS) on every 16th of rank 0's rays of the last timed step"
+            except Exception as exc:
+                vt_src = "SURVEY 8d figures (oracle failed: %r)" % (exc,)
         if world == 1 and not args.no_cpu:
-            # the rays of the last timed step, exactly as the GPU generated them (all SPP samples)
-            rp = d_rays.cpu().numpy()
-            rb = d_b.cpu().numpy()
-            rb = np.ascontiguousarray(rb[rb[:, 7] >= rb[:, 3]])
             try:
                 leg = cpu_leg(rp, rb)
-                cpu, vt, ref_nodes = leg["cpu"], leg.get("vt", vt), leg.get("ref_nodes")
-                vt_src = "scalar reference counters (oracle restatement, bit-exact with -DSTATS) on every 16th of these rays"
+                cpu = leg["cpu"]
+                ref_t, ref_id = leg["hits"]
+                gh = np.concatenate([d_hits.cpu().numpy(), d_h2.cpu().numpy()[live]])
+                parity = parity_block(gh, ref_t, ref_id)
+                c = parity["mismatch_classes"]
+                if parity["id_mismatch_frac"] > 1e-5 or parity["max_rel_t"] > 1e-5 or c["gpu_farther"] != 0:
+                    rc = 3
+                    sys.stderr.write("bench.py: PARITY GATE FAILED: %s\n" % json.dumps(parity))
             except Exception as exc:   # the CPU leg is a reported baseline, never a reason to lose the GPU number
                 cpu = {"error": repr(exc)}
         bpr_p, bpr_b = bytes_per_ray(*vt["primary"]), bytes_per_ray(*vt["bounce"])
         live_per_launch = live_total / max(1, args.steps) / world
         achieved = live_per_launch * bpr_b / (bounce_ms * 1e-3) / 1e9
-        traffic = None
+        traffic, traffic_src = None, None
         try:
             with open(os.path.join(ROOT, "profiles", "ncu_summary.json")) as f:
-                traffic = json.load(f).get("bounce_trace_dram_bytes_per_launch")
+                js = json.load(f)
+                traffic, traffic_src = js.get("bounce_trace_dram_bytes_per_launch"), js.get("source")
         except Exception:
             pass
+        kernel = ("k_trace_hybrid" if (args.layout in ("bvh2", "bvh4", "qbvh4") and args.variant in (-1, 2)) else
+                  "k_trace_simple" if args.variant == 1 else "k_trace_persistent")
         line = {
             "metric": METRIC, "value": value, "unit": "Mrays/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic",
-            "config": {
-                "workload": workload(info.num_triangles),
+            "config": shared_config(),
+            "detail": {
                 "rays_per_step": rays_total / args.steps, "primary_rays_per_step": prim_total / args.steps, "bounce_rays_per_step": live_total / args.steps,
                 "layout": args.layout, "kernel_variant": args.variant, "nodes": info.num_nodes, "node_mb": info.node_bytes / 1e6,
                 "triangle_mb": info.triangle_bytes / 1e6, "build_s": info.build_seconds + info.flatten_seconds,
                 "sharding": f"image rows interleaved over {world} rank(s), BVH replicated",
-                "l2": "inputs larger than L2: each step rewrites and rereads %.0f MB of ray/hit buffers per GPU, evicting the scene between its kernels" % (n * 96 / 1e6),
+                "per_gpu_ms": {"primary_trace": prim_ms, "gen_bounce": genb_ms, "bounce_trace": bounce_ms, "gen_primary": genp_ms,
+                               "note": "max over ranks of each rank's mean over the timed steps (CUDA events on the launching stream)"},
                 "primary_mrays_s": (prim_total / args.steps / world) / (prim_ms * 1e-3) / 1e6 * world,
                 "bounce_mrays_s": (live_total / args.steps / world) / (bounce_ms * 1e-3) / 1e6 * world,
                 "bytes_per_ray": {"primary": bpr_p, "bounce": bpr_b, "V_T": vt, "source": vt_src},
                 "reference_bvh_nodes": ref_nodes,
+                "e2e_rays_per_step": e2e_total / max(1, e2e_steps), "e2e_ms_per_step": 1e3 * e2e_s / max(1, e2e_steps),
             },
-            "roofline": {"bound": "hbm", "kernel": ("k_trace_hybrid" if (args.layout in ("bvh2", "bvh4", "qbvh4") and args.variant in (-1, 2)) else
-                                                    "k_trace_simple" if args.variant == 1 else "k_trace_persistent") + " (bounce rays, closest hit)", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                         "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
+            "parity": parity,
+            "roofline": {"bound": "hbm", "kernel": kernel + " (bounce rays, closest hit)", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                         "frac": achieved / peak, "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src,
                          "note": "algorithmic bytes = live bounce rays per launch x (32V + 36T + 48) B; the scene is mostly L2-resident, so DRAM traffic is far below this"},
             "cpu_baseline": cpu,
             "e2e": {"value": e2e_value, "unit": "Mrays/s", "h2d_bytes_per_step": 40 + 17 * 4, "d2h_bytes_per_step": WIDTH * HEIGHT * 3,
-                    "call": "mirogpu_render_rgb8 (Scene::raytraceImage -> 8-bit Image), diffuse-bounce mode, pinned host framebuffer" + ("" if world == 1 else " per rank -> all_reduce(max) of the tone-map constant, 8-bit rows, NCCL all_gather of the row shards")},
+                    "call": e2e_call},
             "gpu_launches": int(4 * args.steps * world),
             "clocks": clocks,
         }
+        if world == 1 and not args.no_extras:
+            line["extra"] = run_extras()
         emit(line)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
+    if rc:
+        raise SystemExit(rc)
     return line
+
+
+def run_extras():
+    """The other BASELINE configs and entry points, measured outside the timed region by the tools/ scripts (one subprocess each,
+    one JSON object each): frame times of configs 1 / 2 / 4 / 5 with the fraction of pixels within 2/255 of the REAL reference's
+    image, photon gather rate on config 5 against its yardstick, BVH::build seconds per builder, the host-buffer batch API."""
+    out = {}
+    env = dict(os.environ, MIRO_REF_ALL="1")
+    for key, script, tmo in (("configs", "bench_configs.py", 240), ("photon_gather", "bench_gather.py", 120), ("bvh_build", "bench_build.py", 120),
+                             ("host_batch_api", "bench_host_batch.py", 120)):
+        path = os.path.join(ROOT, "tools", script)
+        if not os.path.exists(path):
+            continue
+        try:
+            r = subprocess.run([sys.executable, path], capture_output=True, text=True, timeout=tmo, env=env)
+            lines = [l for l in r.stdout.splitlines() if l.startswith("{")]
+            out[key] = json.loads(lines[-1]) if (r.returncode == 0 and lines) else {"error": (r.stderr or r.stdout)[-400:]}
+        except Exception as exc:
+            out[key] = {"error": repr(exc)}
+    return out
 
 
 def main():
@@ -440,7 +537,8 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--layout", default=os.environ.get("MIROGPU_LAYOUT", "qbvh4"), choices=["bvh2", "cwbvh8", "bvh4", "qbvh4"])
     ap.add_argument("--variant", type=int, default=int(os.environ.get("MIROGPU_VARIANT", "-1")))
-    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg (faster iteration)")
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline / parity legs (faster iteration)")
+    ap.add_argument("--no-extras", action="store_true", help="skip the untimed extra measurements (other configs, gather, builders)")
     args = ap.parse_args()
     if args.warmup < 3:
         args.warmup = 3

@@ -267,6 +267,10 @@ __device__ __forceinline__ bool shade_item(const WaveParams& p, const Queue& cur
 // queue / accumulation atomics of two items in one thread cost more than the overlap wins (e2e 6.93 -> 6.71 Grays/s) -- so 1.
 #define MIRO_SHADE_THREADS 128
 #define MIRO_SHADE_ITEMS 1
+// counter block of a render (uint32 slots): [0..16] wave sizes, [17] dropped children, [18] tone-map maximum, [20..21] 64-bit
+// secondary-ray total of the frame, [24..55] live children of in-place waves (spread by block)
+#define MIRO_DROPPED_SLOT 17
+#define MIRO_LIVE_SLOT0 24
 __global__ void __launch_bounds__(MIRO_SHADE_THREADS, 8) k_shade(WaveParams p, Queue cur, uint32_t n, const uint32_t* __restrict__ d_n, Queue next,
                                                               uint32_t* next_count, uint32_t* dropped, mirogpu_ray* shadow_rays, float4* shadow_cd,
                                                               float4* shadow_ch, float* accum, float* gather_pos, float* gather_nrm, float4* gather_w)
@@ -275,6 +279,8 @@ __global__ void __launch_bounds__(MIRO_SHADE_THREADS, 8) k_shade(WaveParams p, Q
     if (d_n) n = min(n, *d_n);
     const bool in_place = p.mode == MIROGPU_RENDER_DIFFUSE_BOUNCE && d_n == nullptr;   // wave 0: the only one with children
     if (in_place && base == 0) *next_count = n;
+    uint32_t* live_slots = dropped + (MIRO_LIVE_SLOT0 - MIRO_DROPPED_SLOT);
+    bool any_child = false;
     float4 hv[MIRO_SHADE_ITEMS];
     ShadeRecord rec[MIRO_SHADE_ITEMS];
 #pragma unroll
@@ -298,6 +304,13 @@ __global__ void __launch_bounds__(MIRO_SHADE_THREADS, 8) k_shade(WaveParams p, Q
             r[0] = make_float4(0.f, 0.f, 0.f, 0.0f);
             r[1] = make_float4(0.f, 0.f, 1.f, -1.0f);
         }
+        any_child |= wrote;
+    }
+    // In-place waves fill every slot, dead or alive; the LIVE children are what the frame's ray count reports (a dead slot is
+    // answered without traversal).  One non-returning add per warp, spread over 32 addresses by block.
+    if (in_place && MIRO_SHADE_ITEMS == 1) {
+        const unsigned live = __popc(__ballot_sync(0xffffffffu, any_child));
+        if ((threadIdx.x & 31u) == 0u && live) atomicAdd(live_slots + (blockIdx.x & 31u), live);
     }
 }
 
@@ -458,10 +471,13 @@ __global__ void __launch_bounds__(256) k_frame_max(const float* __restrict__ rgb
 #define MIRO_SAMPLE_BATCH 8
 
 // Adds this batch's secondary wave sizes (counters[1..16]) to the frame's running 64-bit total.
-__global__ void k_sum_wave_counters(const uint32_t* __restrict__ counters, unsigned long long* total)
+// in_place (diffuse-bounce frames): wave 1 holds a slot per item of wave 0, dead or alive; its rays are the live children
+// k_shade counted.
+__global__ void k_sum_wave_counters(const uint32_t* __restrict__ counters, unsigned long long* total, int in_place)
 {
     unsigned long long s = 0;
-    for (int w = 1; w <= MIRO_MAX_WAVES; ++w) s += counters[w];
+    if (in_place) for (int k = 0; k < 32; ++k) s += counters[MIRO_LIVE_SLOT0 + k];
+    else for (int w = 1; w <= MIRO_MAX_WAVES; ++w) s += counters[w];
     *total += s;
 }
 
@@ -554,6 +570,7 @@ int render_device(mirogpu_scene* h, const mirogpu_camera& cam, const mirogpu_ren
         wp.sample_base = s0;
         RT(cudaMemsetAsync(planes, 0, items * 12, st));
         RT(cudaMemsetAsync(counters, 0, 18 * 4, st));
+        if (rp.mode == MIROGPU_RENDER_DIFFUSE_BOUNCE) RT(cudaMemsetAsync(counters + MIRO_LIVE_SLOT0, 0, 32 * 4, st));
         int cur = 0;
         k_render_primary<<<dim3((unsigned)((npix + 255) / 256), nb), 256, 0, st>>>(cb, rp.width, rp.height, first_row, rp.row_stride, nrows, rp.jitter, rp.seed,
                                                                            s0, nb, rp.max_depth, q[cur]);
@@ -593,7 +610,7 @@ int render_device(mirogpu_scene* h, const mirogpu_camera& cam, const mirogpu_ren
         }
         k_fold_planes<<<(unsigned)((npix * 3 + 255) / 256), 256, 0, st>>>(planes, nb, npix * 3, frame);
         launches++;
-        k_sum_wave_counters<<<1, 1, 0, st>>>(counters, d_total);
+        k_sum_wave_counters<<<1, 1, 0, st>>>(counters, d_total, rp.mode == MIROGPU_RENDER_DIFFUSE_BOUNCE ? 1 : 0);
         launches++;
         host_rays += items * (shadows ? 1 + nl : 1);
     }

@@ -3,40 +3,69 @@
 The constants come from the reference's scene scripts (assignment2.cpp:24-442); a description is then
 realised by whichever implementation is under test -- the reference compiled in place, the oracle, or
 the product's host layer -- through the same builder calls, so all three see identical inputs.
-Transforms are composed in float64 and rounded once to binary32; every implementation receives those
-same sixteen floats (row order, Matrix4x4.h:21-24).
+Transforms are composed the way the scripts compose them -- binary32 Matrix4x4 products in the reference's
+operand order -- so a scene realised from here holds the same triangles, bit for bit, as the reference's own
+make*Scene() (tests/test_scene_scripts.py checks that against the reference compiled in place); every
+implementation receives those same sixteen floats (row order, Matrix4x4.h:21-24).
 """
 import math
 
 import numpy as np
 
 
+F = np.float32
+PI_F = F(3.1415926535897932384626433832795028841972)   # Miro.h:10 (a float constant)
+
+
 def translate(x, y, z):
-    m = np.eye(4)
-    m[:3, 3] = [x, y, z]
+    """assignment2.cpp:467-474 -- float parameters."""
+    m = np.eye(4, dtype=np.float32)
+    m[:3, 3] = [F(x), F(y), F(z)]
     return m
 
 
 def scale(x, y, z):
-    return np.diag([x, y, z, 1.0])
+    return np.diag([F(x), F(y), F(z), F(1)]).astype(np.float32)
 
 
 def rotate(angle_deg, x, y, z):
-    """assignment2.cpp:486-518 -- note the axis is used as given (not normalised), like the reference."""
-    rad = angle_deg * (math.pi / 180.0)
-    c, s = math.cos(rad), math.sin(rad)
-    cinv = 1 - c
-    return np.array([[x * x + c * (1 - x * x), x * y * cinv + z * s, x * z * cinv - y * s, 0],
-                     [x * y * cinv - z * s, y * y + c * (1 - y * y), y * z * cinv + x * s, 0],
-                     [x * z * cinv + y * s, y * z * cinv - x * s, z * z + c * (1 - z * z), 0],
-                     [0, 0, 0, 1.0]])
+    """assignment2.cpp:486-518 in its own arithmetic: `float rad = angle*(PI/180.)` is formed in double and rounded once,
+    cos / sin are the float overloads of <math.h>, every product and sum after that is binary32.  The axis is used as
+    given (not normalised), like the reference."""
+    x, y, z = F(x), F(y), F(z)
+    rad = F(float(F(angle_deg)) * (float(PI_F) / 180.0))
+    c, s = F(math.cos(float(rad))), F(math.sin(float(rad)))
+    one = F(1)
+    x2, y2, z2 = x * x, y * y, z * z
+    cinv = one - c
+    xy, xz, yz = x * y, x * z, y * z
+    xs, ys, zs = x * s, y * s, z * s
+    xzcinv, xycinv, yzcinv = xz * cinv, xy * cinv, yz * cinv
+    return np.array([[x2 + c * (one - x2), xy * cinv + zs, xzcinv - ys, 0],
+                     [xycinv - zs, y2 + c * (one - y2), yzcinv + xs, 0],
+                     [xzcinv + ys, yzcinv - xs, z2 + c * (one - z2), 0],
+                     [0, 0, 0, 1]], dtype=np.float32)
+
+
+def matmul_f32(a, b):
+    """Matrix4x4::operator*= (Matrix4x4.h:462-499): every entry is ((a1 b1 + a2 b2) + a3 b3) + a4 b4 in binary32, no FMA."""
+    a = np.asarray(a, np.float32); b = np.asarray(b, np.float32)
+    out = np.zeros((4, 4), np.float32)
+    for i in range(4):
+        for j in range(4):
+            acc = a[i, 0] * b[0, j]
+            for k in (1, 2, 3):
+                acc = F(acc + F(a[i, k] * b[k, j]))
+            out[i, j] = acc
+    return out
 
 
 def _chain(*ms):
-    out = np.eye(4)
+    """xform.setIdentity(); xform *= m1; xform *= m2; ... as the scene scripts write it."""
+    out = np.eye(4, dtype=np.float32)
     for m in ms:
-        out = out @ m
-    return out.astype(np.float32)
+        out = matmul_f32(out, m)
+    return out
 
 
 FLOOR_BIG = dict(v=[-100, 0, -100, 0, 0, 100, 100, 0, -100], n=[0, 1, 0] * 3)   # assignment2.cpp:101-109
@@ -45,7 +74,7 @@ LAMBERT_WHITE = dict(kd=(1, 1, 1), ks=(0, 0, 0), kt=(0, 0, 0), shininess=1.0, re
 
 
 def _bunny20_transforms():
-    x2 = rotate(110, 0, 1, 0) @ scale(.6, 1, 1.1)
+    x2 = _chain(rotate(110, 0, 1, 0), scale(.6, 1, 1.1))   # assignment2.cpp:150-152
     base = [
         [scale(0.3, 2.0, 0.7), translate(-1, .4, .3), rotate(25, .3, .1, .6)],
         [scale(.6, 1.2, .9), translate(7.6, .8, .6)],
@@ -58,6 +87,7 @@ def _bunny20_transforms():
         [translate(-3, .4, 6), rotate(-30, 0, 1, 0)],
         [translate(3, 0.5, -2), rotate(180, 0, 1, 0), scale(1.5, 1.5, 1.5)],
     ]
+    # bunnies 11-20: xform = xform2; xform *= ... (assignment2.cpp:236-330)
     return [_chain(*b) for b in base] + [_chain(x2, *b) for b in base]
 
 
@@ -79,7 +109,7 @@ SCENES = {
         camera=dict(eye=(0, 5, 15), lookat=(0, 0, 0), up=(0, 1, 0), fov=45), size=(512, 512)),
     # config 2 -- bunny + teapot at (-4,0,2) + floor, bunny camera, 1024^2
     "bunny_teapot": dict(
-        meshes=[("bunny", None, 0), ("teapot", translate(-4, 0, 2).astype(np.float32), 0)], triangles=[(FLOOR_BIG, 0)],
+        meshes=[("bunny", None, 0), ("teapot", translate(-4, 0, 2), 0)], triangles=[(FLOOR_BIG, 0)],
         materials=[LAMBERT_WHITE], lights=[dict(kind=0, pos=(10, 20, 10), color=(1, 1, 1), wattage=1000)],
         camera=dict(eye=(0, 5, 15), lookat=(0, 0, 0), up=(0, 1, 0), fov=45), size=(1024, 1024)),
     # config 3 stand-in -- makeBunny20Scene (assignment2.cpp:123-338): sponza.obj is absent from the reference tree
@@ -107,7 +137,7 @@ SCENES = {
     # compiled here).  The drops are therefore moved under the light: translate(-1.1, 0.9, -3.8).
     "cornell_drops": dict(
         meshes=[("cornell_box_1", None, 0), ("cornell_box_2", None, 1), ("cornell_box_3", None, 2), ("cornell_box_4", None, 0),
-                ("WaterDrops", translate(-1.1, 0.9, -3.8).astype(np.float32), 3)], triangles=[],
+                ("WaterDrops", translate(-1.1, 0.9, -3.8), 3)], triangles=[],
         materials=[LAMBERT_WHITE, dict(kd=(1, 0, 0), ks=(0, 0, 0), kt=(0, 0, 0), shininess=1.0, refr=1.0),
                    dict(kd=(0, 1, 0), ks=(0, 0, 0), kt=(0, 0, 0), shininess=1.0, refr=1.0),
                    dict(kd=(1, 1, 1), ks=(0, 0, 0), kt=(1, 1, 1), shininess=5.0, refr=1.5)],            # assignment2.cpp:433

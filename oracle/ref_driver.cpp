@@ -67,6 +67,10 @@ void rebuild_prim_ids()
 }
 }  // namespace
 
+// scene scripts of the reference (C++ linkage), see ref_make_scene
+void makeTeapotScene(); void makeBunny1Scene(); void makeBunny20Scene(); void makeCornellScene();
+void A1makeSphereScene(); void A1makeTeapotScene();
+
 extern "C" {
 
 int ref_build_flags()
@@ -164,6 +168,27 @@ void ref_add_directional_light(const float* pos, const float* normal, float radi
     g_scene->addLight(l);
 }
 
+// The reference's OWN scene scripts (assignment1.cpp / assignment2.cpp, compiled in place, unmodified): each builds g_scene /
+// g_camera / g_image, loads its models from paths relative to the working directory (the caller chdir()s to the reference
+// tree) and calls Scene::preCalc itself.  Returns 0, or -1 for an unknown name.  Pins tests/../scenes.py against the scripts.
+int ref_make_scene(const char* name)
+{
+    const std::string n(name);
+    g_materials.clear(); g_prim_id.clear();
+#ifdef STATS
+    Stats::BVH_Nodes = Stats::BVH_LeafNodes = 0;
+#endif
+    if (n == "teapot") makeTeapotScene();
+    else if (n == "bunny1") makeBunny1Scene();
+    else if (n == "bunny20") makeBunny20Scene();
+    else if (n == "cornell") makeCornellScene();
+    else if (n == "a1_sphere") A1makeSphereScene();
+    else if (n == "a1_teapot") A1makeTeapotScene();
+    else return -1;
+    rebuild_prim_ids();
+    return 0;
+}
+
 void ref_set_bg_color(const float* c) { g_scene->setBgColor(Vector3(c[0], c[1], c[2])); }
 
 void ref_srand(unsigned seed) { srand(seed); }
@@ -206,7 +231,7 @@ void ref_dump_triangles(float* out18)
 // N is the normal after Scene::trace's UV-material normalisation (Scene.cpp:262).
 void ref_trace(const float* rays, long n, float* out_t, int* out_id, float* out_P, float* out_N, int nthreads)
 {
-    if (nthreads <= 0) nthreads = omp_get_max_threads();
+    if (nthreads <= 0) nthreads = omp_get_num_procs();
 #pragma omp parallel for schedule(dynamic, 4096) num_threads(nthreads)
     for (long i = 0; i < n; ++i) {
         const float* r = rays + 8 * i;
@@ -231,7 +256,7 @@ void ref_trace(const float* rays, long n, float* out_t, int* out_id, float* out_
 // Same loop, results discarded except a checksum: the timing leg (no output traffic).
 double ref_trace_time(const float* rays, long n, int nthreads, long* out_hits)
 {
-    if (nthreads <= 0) nthreads = omp_get_max_threads();
+    if (nthreads <= 0) nthreads = omp_get_num_procs();
     long hits = 0;
     double t = -omp_get_wtime();
 #pragma omp parallel for schedule(dynamic, 4096) num_threads(nthreads) reduction(+ : hits)
@@ -245,6 +270,35 @@ double ref_trace_time(const float* rays, long n, int nthreads, long* out_hits)
     if (out_hits) *out_hits = hits;
     return t;
 }
+
+// The timing leg that KEEPS its answers (bench.py's parity block compares them with the GPU's hits on the same rays).  Inside the
+// timed loop only hit.t and the hit.object pointer are stored; pointers are mapped to prim ids after the clock stops.
+double ref_trace_time_hits(const float* rays, long n, int nthreads, float* out_t, int* out_id)
+{
+    if (nthreads <= 0) nthreads = omp_get_num_procs();
+    std::vector<const Object*> obj((size_t)n);
+    double t = -omp_get_wtime();
+#pragma omp parallel for schedule(dynamic, 4096) num_threads(nthreads)
+    for (long i = 0; i < n; ++i) {
+        const float* r = rays + 8 * i;
+        Ray ray(Vector3(r[0], r[1], r[2]), Vector3(r[4], r[5], r[6]));
+        HitInfo hit;
+        obj[i] = g_scene->trace(hit, ray, r[3], r[7]) ? hit.object : 0;
+        out_t[i] = hit.t;
+    }
+    t += omp_get_wtime();
+#pragma omp parallel for schedule(static) num_threads(nthreads)
+    for (long i = 0; i < n; ++i) {
+        if (!obj[i]) { out_id[i] = -1; continue; }
+        std::tr1::unordered_map<const Object*, int>::const_iterator it = g_prim_id.find(obj[i]);
+        out_id[i] = (it == g_prim_id.end()) ? -2 : it->second;
+    }
+    return t;
+}
+
+// Host threads the timing legs use when asked for "all" (nthreads <= 0): the processor count, not OMP_NUM_THREADS -- torchrun
+// exports OMP_NUM_THREADS=1 to its workers.
+int ref_host_threads() { return omp_get_num_procs(); }
 
 // out9: BVH_Nodes, BVH_LeafNodes, Rays, Primary, Secondary, Shadow, Photon_Bounces, Ray_Box, Ray_Tri.
 int ref_stats_get(long long* out9)
@@ -303,7 +357,7 @@ double ref_render(int w, int h, unsigned char* rgb8)
 // Scene::traceScene per ray: the pre-tone-map radiance the render accumulates (Scene.cpp:270).
 void ref_trace_scene(const float* rays, long n, int depth, float* rgb, int nthreads)
 {
-    if (nthreads <= 0) nthreads = omp_get_max_threads();
+    if (nthreads <= 0) nthreads = omp_get_num_procs();
 #pragma omp parallel for schedule(dynamic, 1024) num_threads(nthreads)
     for (long i = 0; i < n; ++i) {
         const float* r = rays + 8 * i;
@@ -354,7 +408,7 @@ void ref_pm_irradiance(int which, const float* pos, const float* nrm, long n, fl
                        float* irr, int nthreads)
 {
     Photon_map* pm = pm_of(which);
-    if (nthreads <= 0) nthreads = omp_get_max_threads();
+    if (nthreads <= 0) nthreads = omp_get_num_procs();
 #pragma omp parallel for schedule(dynamic, 64) num_threads(nthreads)
     for (long i = 0; i < n; ++i)
         pm->irradiance_estimate(irr + 3 * i, pos + 3 * i, nrm + 3 * i, max_dist, k);

@@ -110,6 +110,20 @@ class Driver:
         s = self._f("trace_time")(_fp(rays), ctypes.c_long(rays.shape[0]), int(nthreads), ctypes.byref(hits))
         return s, hits.value
 
+    def trace_time_hits(self, rays, nthreads=0):
+        """The timing leg that keeps its answers: (seconds, t, prim_id (-1 = miss))."""
+        rays = np.ascontiguousarray(rays, np.float32).reshape(-1, 8)
+        n = rays.shape[0]
+        t = np.zeros(n, np.float32)
+        ids = np.zeros(n, np.int32)
+        f = self._f("trace_time_hits")
+        f.restype = ctypes.c_double
+        s = f(_fp(rays), ctypes.c_long(n), int(nthreads), _fp(t), _fp(ids))
+        return s, t, ids
+
+    def host_threads(self):
+        return int(self._f("host_threads")())
+
     def stats(self):
         out = (ctypes.c_longlong * 9)()
         self._f("stats_get")(out)

@@ -302,3 +302,46 @@ def test_full_size_properties_bunny20(host_scenes, pkg):
     h8 = S.intersect(sample)
     H2, S2 = host_scenes("bunny20", 0)
     assert np.array_equal(S2.intersect(sample), h8)
+
+
+def test_headline_config_vs_reference_traversal(host_scenes, oracle_scene, pkg):
+    """The bench's own configuration -- bunny20, layout 3 (QBVH4), automatic kernel choice (k_trace_hybrid<3,...>) -- against
+    the reference's traversal (oracle restatement of BVH.cpp:438-658 + Triangle.cpp:150-158, bit-identical to oracle/_ref) on
+    > 2 M of the bench's rays: every 16th jittered camera ray of one 1920x1080 sample... times 8 samples, and the bounce
+    rays the GPU generated from them.  Gates of BASELINE.json: ids equal except <= 1e-5 of rays in the documented classes,
+    |t_gpu - t_ref| <= 1e-5 |t_ref| wherever the id matches; the GPU never returns a farther hit than the reference."""
+    H, S = host_scenes("bunny20", 3)
+    assert S.info.layout == 3 and S.info.num_triangles == 1389021
+    S.set_kernel_variant(-1)
+    O = oracle_scene("bunny20")
+    cam = H.camera()
+    w, h, spp = 1920, 1080, 8
+    n = w * h * spp
+    d_rays = torch.empty((n, 8), dtype=torch.float32, device="cuda")
+    d_hits = torch.empty((n, 4), dtype=torch.float32, device="cuda")
+    d_b = torch.empty((n, 8), dtype=torch.float32, device="cuda")
+    d_h2 = torch.empty((n, 4), dtype=torch.float32, device="cuda")
+    S.generate_primary(cam, w, h, d_rays, jitter=1, seed=168, sample=0, samples=spp)
+    S.intersect_device(d_rays, d_hits, mode=pkg.CLOSEST_HIT | pkg.HINT_COHERENT)
+    S.generate_bounce(d_rays, d_hits, d_b, seed=168, sample=0)
+    S.intersect_device(d_b, d_h2)
+    torch.cuda.synchronize()
+    total = 0
+    for dr, dh, stride in ((d_rays, d_hits, 13), (d_b, d_h2, 11)):
+        rays = np.ascontiguousarray(dr.cpu().numpy()[::stride])
+        hits = dh.cpu().numpy().view(pkg.HIT_DTYPE).reshape(-1)[::stride].copy()
+        keep = rays[:, 7] >= rays[:, 3]            # dead bounce slots (parent missed) carry an empty interval
+        rays, hits = np.ascontiguousarray(rays[keep]), hits[keep]
+        t_ref, id_ref, _, _ = O.trace(rays)
+        ids = ids_of(hits)
+        m = rays.shape[0]
+        total += m
+        mism = ids != id_ref
+        assert mism.sum() <= max(1, int(1e-5 * m)), f"{mism.sum()} of {m} ids differ from the reference's traversal"
+        # every mismatch is a documented class: an equal-t tie, or a hit the reference's own tree culled (GPU closer)
+        assert (hits["t"][mism] <= t_ref[mism]).all()
+        same = (~mism) & (id_ref >= 0)
+        rel = np.abs(hits["t"][same].astype(np.float64) - t_ref[same]) / np.abs(t_ref[same].astype(np.float64))
+        assert rel.max() <= 1e-5
+        assert np.array_equal(bits(hits["t"][~mism]), bits(t_ref[~mism]))   # in fact bit-identical
+    assert total >= 2_000_000
