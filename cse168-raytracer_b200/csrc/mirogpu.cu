@@ -50,7 +50,57 @@ double now_s()
 
 }  // namespace
 
+// Device allocation released on scope exit (error paths included).
+struct DevBuf {
+    void* p = nullptr;
+    DevBuf() = default;
+    DevBuf(const DevBuf&) = delete;
+    DevBuf& operator=(const DevBuf&) = delete;
+    ~DevBuf() { if (p) cudaFree(p); }
+    cudaError_t alloc(size_t bytes) { return cudaMalloc(&p, bytes ? bytes : 16); }
+    template <typename T> T* as() const { return static_cast<T*>(p); }
+};
+
+// Staging of the host-buffer batch API: a stream, device ray / hit buffers that grow on demand, and a small page-locked
+// pair for tiny batches (the reference's call pattern is ONE ray per BVH::intersect call: no allocation, no stream
+// creation and no pageable-copy staging on that path).  Slots belong to the scene handle; a call borrows one.
+#define MIRO_SMALL_BATCH 1024
+struct BatchSlot {
+    cudaStream_t st = nullptr;
+    mirogpu_ray* d_r = nullptr; mirogpu_hit* d_h = nullptr; size_t cap = 0;
+    mirogpu_ray* h_r = nullptr; mirogpu_hit* h_h = nullptr;   // page-locked, MIRO_SMALL_BATCH entries, device-visible (UVA)
+    unsigned long long* d_c = nullptr;                          // 4 counters of the instrumented kernel
+    bool busy = false;
+    cudaError_t init()
+    {
+        cudaError_t e = cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking);
+        if (e == cudaSuccess) e = cudaHostAlloc(&h_r, MIRO_SMALL_BATCH * sizeof(mirogpu_ray), cudaHostAllocMapped);
+        if (e == cudaSuccess) e = cudaHostAlloc(&h_h, MIRO_SMALL_BATCH * sizeof(mirogpu_hit), cudaHostAllocMapped);
+        if (e == cudaSuccess) e = cudaMalloc(&d_c, 4 * sizeof(unsigned long long));
+        return e;
+    }
+    cudaError_t ensure(size_t n)
+    {
+        if (n <= cap) return cudaSuccess;
+        cudaFree(d_r); cudaFree(d_h); d_r = nullptr; d_h = nullptr; cap = 0;
+        cudaError_t e = cudaMalloc(&d_r, n * sizeof(mirogpu_ray));
+        if (e == cudaSuccess) e = cudaMalloc(&d_h, n * sizeof(mirogpu_hit));
+        if (e == cudaSuccess) cap = n;
+        return e;
+    }
+    void release()
+    {
+        cudaFree(d_r); cudaFree(d_h); cudaFree(d_c);
+        if (h_r) cudaFreeHost(h_r);
+        if (h_h) cudaFreeHost(h_h);
+        if (st) cudaStreamDestroy(st);
+        d_r = nullptr; d_h = nullptr; d_c = nullptr; h_r = nullptr; h_h = nullptr; st = nullptr; cap = 0;
+    }
+};
+
 struct mirogpu_scene {
+    std::vector<std::unique_ptr<BatchSlot>> slots;   // guarded by slot_mtx
+    std::mutex slot_mtx;
     int device = 0;
     int layout = MIROGPU_LAYOUT_CWBVH8;
     int variant = -1;   // mirogpu_set_kernel_variant
@@ -197,6 +247,51 @@ void camera_basis(const mirogpu_camera& c, int W, int H, CameraBasis& b)
 #include "photon_trace_impl.cuh"
 #include "lbvh_impl.cuh"
 
+namespace {
+// Borrow / return a staging slot of the handle.
+BatchSlot* slot_acquire(mirogpu_scene* h, cudaError_t& e)
+{
+    e = cudaSuccess;
+    std::lock_guard<std::mutex> lk(h->slot_mtx);
+    for (auto& s : h->slots) if (!s->busy) { s->busy = true; return s.get(); }
+    std::unique_ptr<BatchSlot> s(new (std::nothrow) BatchSlot);
+    if (!s) { e = cudaErrorMemoryAllocation; return nullptr; }
+    e = s->init();
+    if (e != cudaSuccess) { s->release(); (void)cudaGetLastError(); return nullptr; }
+    s->busy = true;
+    h->slots.push_back(std::move(s));
+    return h->slots.back().get();
+}
+void slot_release(mirogpu_scene* h, BatchSlot* s)
+{
+    if (!s) return;
+    std::lock_guard<std::mutex> lk(h->slot_mtx);
+    s->busy = false;
+}
+struct SlotGuard {
+    mirogpu_scene* h; BatchSlot* s;
+    ~SlotGuard() { slot_release(h, s); }
+};
+int cuda_code(cudaError_t e) { return e == cudaErrorMemoryAllocation ? MIROGPU_ERR_OOM : MIROGPU_ERR_CUDA; }
+
+template <bool COUNT>
+cudaError_t launch_simple(mirogpu_scene* h, const mirogpu_ray* d_r, size_t n, mirogpu_hit* d_h, bool any, unsigned long long* d_c, cudaStream_t st)
+{
+    const unsigned grid = (unsigned)((n + 127) / 128);
+#define MIRO_SIMPLE(L)                                                                                 \
+    {                                                                                                  \
+        if (any) k_trace_simple<L, true, COUNT><<<grid, 128, 0, st>>>(h->ds, d_r, n, d_h, d_c, nullptr, 1);  \
+        else k_trace_simple<L, false, COUNT><<<grid, 128, 0, st>>>(h->ds, d_r, n, d_h, d_c, nullptr, 1);     \
+    }
+    if (h->layout == MIROGPU_LAYOUT_BVH4) MIRO_SIMPLE(MIROGPU_LAYOUT_BVH4)
+    else if (h->layout == MIROGPU_LAYOUT_QBVH4) MIRO_SIMPLE(MIROGPU_LAYOUT_QBVH4)
+    else if (h->layout == MIROGPU_LAYOUT_BVH2) MIRO_SIMPLE(MIROGPU_LAYOUT_BVH2)
+    else MIRO_SIMPLE(MIROGPU_LAYOUT_CWBVH8)
+#undef MIRO_SIMPLE
+    return cudaGetLastError();
+}
+}  // namespace
+
 extern "C" {
 
 int mirogpu_version(void) { return MIROGPU_VERSION; }
@@ -253,9 +348,12 @@ int mirogpu_scene_create(const float* tri_vertices, const float* tri_normals, co
     mirogpu_scene* h = new (std::nothrow) mirogpu_scene;
     if (!h) return fail(MIROGPU_ERR_OOM, "host allocation failed");
     h->device = dev; h->layout = o.layout;
-    cudaDeviceProp prop;
-    CUDA_TRY(cudaGetDeviceProperties(&prop, dev));
-    h->sm_count = prop.multiProcessorCount;
+    {
+        int sms = 0;
+        const cudaError_t pe = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+        if (pe != cudaSuccess) { delete h; return fail(MIROGPU_ERR_CUDA, std::string("cudaDeviceGetAttribute: ") + cudaGetErrorString(pe)); }
+        h->sm_count = sms;
+    }
     if (o.layout == MIROGPU_LAYOUT_QBVH4 || o.layout == MIROGPU_LAYOUT_BVH4) { h->hyb_period = 2; h->hyb_min_idle = 6; }   // measured optimum of the four-wide steps
     // QBVH4: one triangle per leaf phase, three node steps per vote, node steps while >= 20 lanes want one (7.28 -> 7.53 Grays/s)
     if (o.layout == MIROGPU_LAYOUT_QBVH4) { h->hyb_pf = 16; h->hyb_nrep = 3; h->hyb_nmin = 20; }
@@ -319,7 +417,7 @@ int mirogpu_scene_create(const float* tri_vertices, const float* tri_normals, co
         const size_t i = (size_t)ii;
         const float* v = tri_vertices + 9 * i;
         uint32_t m = material_ids ? material_ids[i] : 0u;
-        if (nmaterials && m >= nmaterials) { bad_material = true; m = 0u; }
+        if (m >= std::max(materials ? nmaterials : 0u, 1u)) { bad_material = true; m = 0u; }   // no table = one white Lambert
         float4 A = make_float4(v[0], v[1], v[2], 0.f);
         memcpy(&A.w, &m, 4);
         shade[6 * i + 0] = A;
@@ -402,6 +500,7 @@ int mirogpu_scene_destroy(mirogpu_handle h)
     cudaFree(h->d_lights); cudaFree(h->d_ticket);
     if (h->h_stats) cudaFreeHost(h->h_stats);
     for (int i = 0; i < 2; ++i) h->pm[i].release();
+    for (auto& sl : h->slots) sl->release();
     h->scratch.release();
     (void)cudaGetLastError();
     delete h;
@@ -458,7 +557,7 @@ int mirogpu_set_kernel_variant(mirogpu_handle h, int variant)
 {
     if (!h) return fail(MIROGPU_ERR_INVALID_ARG, "NULL handle");
     if (variant < -1 || variant > 2)
-        return fail(MIROGPU_ERR_INVALID_ARG, "variant must be -1 (automatic), 0 (persistent warps, 32-ray tickets, while-while), 1 (one thread per ray) or 2 (persistent warps, hybrid step scheduling + ray replacement; BVH2 only)");
+        return fail(MIROGPU_ERR_INVALID_ARG, "variant must be -1 (automatic), 0 (persistent warps, 32-ray tickets, while-while), 1 (one thread per ray) or 2 (persistent warps, hybrid step scheduling + ray replacement; BVH2, BVH4, QBVH4)");
     h->variant = variant;
     return MIROGPU_OK;
 }
@@ -478,8 +577,10 @@ int mirogpu_intersect_batch_device(mirogpu_handle h, const mirogpu_ray* d_rays, 
     return MIROGPU_OK;
 }
 
-// Host-buffer query: chunks of up to 4 Mi rays are double-buffered over two streams so the H2D copy of
-// chunk k+1 and the D2H copy of chunk k-1 overlap the traversal of chunk k.
+// Host-buffer query.  Tiny batches (the reference calls BVH::intersect one ray at a time): the rays are copied into the
+// slot's page-locked buffer, ONE kernel (a thread per ray) reads them and writes the hits through the mapping, one stream
+// synchronisation -- no device allocation, no copy engine.  Large batches: chunks of up to 4 Mi rays double-buffered over two
+// slots so the H2D copy of chunk k+1 and the D2H copy of chunk k-1 overlap the traversal of chunk k.
 int mirogpu_intersect_batch(mirogpu_handle h, const mirogpu_ray* rays, size_t n, mirogpu_hit* hits, int mode)
 {
     if (!h || (n && (!rays || !hits))) return fail(MIROGPU_ERR_INVALID_ARG, "NULL argument");
@@ -487,38 +588,47 @@ int mirogpu_intersect_batch(mirogpu_handle h, const mirogpu_ray* rays, size_t n,
         return fail(MIROGPU_ERR_INVALID_ARG, "unknown mode");
     if (n == 0) return MIROGPU_OK;
     CUDA_TRY(cudaSetDevice(h->device));
-    const size_t chunk = std::min<size_t>(n, (size_t)4 << 20);
-    cudaStream_t st[2];
-    mirogpu_ray* d_r[2] = {nullptr, nullptr};
-    mirogpu_hit* d_h[2] = {nullptr, nullptr};
-    const int nbuf = n > chunk ? 2 : 1;
-    int rc = MIROGPU_OK;
-    for (int b = 0; b < nbuf; ++b) {
-        CUDA_TRY(cudaStreamCreateWithFlags(&st[b], cudaStreamNonBlocking));
-        CUDA_TRY(cudaMalloc(&d_r[b], chunk * sizeof(mirogpu_ray)));
-        CUDA_TRY(cudaMalloc(&d_h[b], chunk * sizeof(mirogpu_hit)));
-    }
+    cudaError_t e;
+    SlotGuard g0{h, slot_acquire(h, e)};
+    if (!g0.s) return fail(cuda_code(e), std::string("intersect_batch staging: ") + cudaGetErrorString(e));
     uint64_t launches = 0;
-    size_t k = 0;
-    for (size_t off = 0; off < n && rc == MIROGPU_OK; off += chunk, ++k) {
-        const int b = (int)(k % nbuf);
-        const size_t m = std::min(chunk, n - off);
-        cudaError_t e = cudaMemcpyAsync(d_r[b], rays + off, m * sizeof(mirogpu_ray), cudaMemcpyHostToDevice, st[b]);
-        if (e == cudaSuccess) e = dispatch_trace(h, d_r[b], m, d_h[b], mode, st[b]);
-        if (e == cudaSuccess) e = cudaMemcpyAsync(hits + off, d_h[b], m * sizeof(mirogpu_hit), cudaMemcpyDeviceToHost, st[b]);
-        if (e != cudaSuccess) rc = fail(MIROGPU_ERR_CUDA, std::string("intersect_batch: ") + cudaGetErrorString(e));
-        launches++;
-    }
-    for (int b = 0; b < nbuf; ++b) {
-        cudaError_t e = cudaStreamSynchronize(st[b]);
-        if (e != cudaSuccess && rc == MIROGPU_OK) rc = fail(MIROGPU_ERR_CUDA, std::string("intersect_batch sync: ") + cudaGetErrorString(e));
-        cudaFree(d_r[b]); cudaFree(d_h[b]); cudaStreamDestroy(st[b]);
+    if (n <= MIRO_SMALL_BATCH) {
+        memcpy(g0.s->h_r, rays, n * sizeof(mirogpu_ray));
+        e = launch_simple<false>(h, g0.s->h_r, n, g0.s->h_h, (mode & 0xff) == MIROGPU_ANY_HIT, nullptr, g0.s->st);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(g0.s->st);
+        if (e != cudaSuccess) return fail(MIROGPU_ERR_CUDA, std::string("intersect_batch: ") + cudaGetErrorString(e));
+        memcpy(hits, g0.s->h_h, n * sizeof(mirogpu_hit));
+        launches = 1;
+    } else {
+        const size_t chunk = std::min<size_t>(n, (size_t)4 << 20);
+        const int nbuf = n > chunk ? 2 : 1;
+        SlotGuard g1{h, nbuf == 2 ? slot_acquire(h, e) : nullptr};
+        if (nbuf == 2 && !g1.s) return fail(cuda_code(e), std::string("intersect_batch staging: ") + cudaGetErrorString(e));
+        BatchSlot* sl[2] = {g0.s, g1.s};
+        for (int b = 0; b < nbuf; ++b)
+            if ((e = sl[b]->ensure(chunk)) != cudaSuccess) { (void)cudaGetLastError(); return fail(cuda_code(e), std::string("intersect_batch staging: ") + cudaGetErrorString(e)); }
+        int rc = MIROGPU_OK;
+        size_t k = 0;
+        for (size_t off = 0; off < n && rc == MIROGPU_OK; off += chunk, ++k) {
+            BatchSlot* s = sl[k % nbuf];
+            const size_t m = std::min(chunk, n - off);
+            e = cudaMemcpyAsync(s->d_r, rays + off, m * sizeof(mirogpu_ray), cudaMemcpyHostToDevice, s->st);
+            if (e == cudaSuccess) e = dispatch_trace(h, s->d_r, m, s->d_h, mode, s->st);
+            if (e == cudaSuccess) e = cudaMemcpyAsync(hits + off, s->d_h, m * sizeof(mirogpu_hit), cudaMemcpyDeviceToHost, s->st);
+            if (e != cudaSuccess) rc = fail(MIROGPU_ERR_CUDA, std::string("intersect_batch: ") + cudaGetErrorString(e));
+            launches++;
+        }
+        for (int b = 0; b < nbuf; ++b) {
+            e = cudaStreamSynchronize(sl[b]->st);
+            if (e != cudaSuccess && rc == MIROGPU_OK) rc = fail(MIROGPU_ERR_CUDA, std::string("intersect_batch sync: ") + cudaGetErrorString(e));
+        }
+        if (rc != MIROGPU_OK) return rc;
     }
     {
         std::lock_guard<std::mutex> lk(h->mtx);
         h->last_rays = n; h->last_launches = launches; h->stats_batches = 0;
     }
-    return rc;
+    return MIROGPU_OK;
 }
 
 int mirogpu_intersect_batch_counted(mirogpu_handle h, const mirogpu_ray* rays, size_t n, mirogpu_hit* hits, int mode,
@@ -529,32 +639,19 @@ int mirogpu_intersect_batch_counted(mirogpu_handle h, const mirogpu_ray* rays, s
         return fail(MIROGPU_ERR_INVALID_ARG, "unknown mode");
     if (n == 0) return MIROGPU_OK;
     CUDA_TRY(cudaSetDevice(h->device));
-    mirogpu_ray* d_r = nullptr; mirogpu_hit* d_h = nullptr; unsigned long long* d_c = nullptr;
-    CUDA_TRY(cudaMalloc(&d_r, n * sizeof(mirogpu_ray)));
-    CUDA_TRY(cudaMalloc(&d_h, n * sizeof(mirogpu_hit)));
-    CUDA_TRY(cudaMalloc(&d_c, 4 * sizeof(unsigned long long)));
-    CUDA_TRY(cudaMemset(d_c, 0, 4 * sizeof(unsigned long long)));
-    CUDA_TRY(cudaMemcpy(d_r, rays, n * sizeof(mirogpu_ray), cudaMemcpyHostToDevice));
-    const unsigned grid = (unsigned)((n + 127) / 128);
-    const bool any = mode == MIROGPU_ANY_HIT;
-    if (h->layout == MIROGPU_LAYOUT_BVH4) {
-        if (any) k_trace_simple<MIROGPU_LAYOUT_BVH4, true, true><<<grid, 128>>>(h->ds, d_r, n, d_h, d_c, nullptr, 1);
-        else k_trace_simple<MIROGPU_LAYOUT_BVH4, false, true><<<grid, 128>>>(h->ds, d_r, n, d_h, d_c, nullptr, 1);
-    } else if (h->layout == MIROGPU_LAYOUT_QBVH4) {
-        if (any) k_trace_simple<MIROGPU_LAYOUT_QBVH4, true, true><<<grid, 128>>>(h->ds, d_r, n, d_h, d_c, nullptr, 1);
-        else k_trace_simple<MIROGPU_LAYOUT_QBVH4, false, true><<<grid, 128>>>(h->ds, d_r, n, d_h, d_c, nullptr, 1);
-    } else if (h->layout == MIROGPU_LAYOUT_BVH2) {
-        if (any) k_trace_simple<MIROGPU_LAYOUT_BVH2, true, true><<<grid, 128>>>(h->ds, d_r, n, d_h, d_c, nullptr, 1);
-        else k_trace_simple<MIROGPU_LAYOUT_BVH2, false, true><<<grid, 128>>>(h->ds, d_r, n, d_h, d_c, nullptr, 1);
-    } else {
-        if (any) k_trace_simple<MIROGPU_LAYOUT_CWBVH8, true, true><<<grid, 128>>>(h->ds, d_r, n, d_h, d_c, nullptr, 1);
-        else k_trace_simple<MIROGPU_LAYOUT_CWBVH8, false, true><<<grid, 128>>>(h->ds, d_r, n, d_h, d_c, nullptr, 1);
-    }
-    CUDA_TRY(cudaGetLastError());
-    unsigned long long hc[4];
-    CUDA_TRY(cudaMemcpy(hc, d_c, sizeof hc, cudaMemcpyDeviceToHost));
-    CUDA_TRY(cudaMemcpy(hits, d_h, n * sizeof(mirogpu_hit), cudaMemcpyDeviceToHost));
-    cudaFree(d_r); cudaFree(d_h); cudaFree(d_c);
+    cudaError_t e;
+    SlotGuard g{h, slot_acquire(h, e)};
+    if (!g.s) return fail(cuda_code(e), std::string("intersect_batch_counted staging: ") + cudaGetErrorString(e));
+    BatchSlot* s = g.s;
+    unsigned long long hc[4] = {0, 0, 0, 0};
+    e = s->ensure(n);
+    if (e == cudaSuccess) e = cudaMemsetAsync(s->d_c, 0, 4 * sizeof(unsigned long long), s->st);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(s->d_r, rays, n * sizeof(mirogpu_ray), cudaMemcpyHostToDevice, s->st);
+    if (e == cudaSuccess) e = launch_simple<true>(h, s->d_r, n, s->d_h, (mode & 0xff) == MIROGPU_ANY_HIT, s->d_c, s->st);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(hc, s->d_c, sizeof hc, cudaMemcpyDeviceToHost, s->st);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(hits, s->d_h, n * sizeof(mirogpu_hit), cudaMemcpyDeviceToHost, s->st);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(s->st);
+    if (e != cudaSuccess) { (void)cudaGetLastError(); return fail(cuda_code(e), std::string("intersect_batch_counted: ") + cudaGetErrorString(e)); }
     const uint64_t node_size = h->layout == MIROGPU_LAYOUT_BVH2 ? 64 : h->layout == MIROGPU_LAYOUT_BVH4 ? 128 : h->layout == MIROGPU_LAYOUT_QBVH4 ? 64 : 80;
     c->rays += n; c->node_visits += hc[0]; c->box_tests += hc[1]; c->triangle_tests += hc[2]; c->hits += hc[3];
     c->bytes_fetched += hc[0] * node_size + hc[2] * sizeof(TriRecord);
@@ -819,14 +916,17 @@ int mirogpu_photon_gather(mirogpu_handle h, int which, const float* pos3, const 
     if (k < 1 || k > MIRO_PHOTON_KMAX) return fail(MIROGPU_ERR_INVALID_ARG, "k out of range (1..512)");
     if (n == 0) return MIROGPU_OK;
     CUDA_TRY(cudaSetDevice(h->device));
-    float *d_p = nullptr, *d_n = nullptr, *d_i = nullptr;
-    CUDA_TRY(cudaMalloc(&d_p, n * 12)); CUDA_TRY(cudaMalloc(&d_n, n * 12)); CUDA_TRY(cudaMalloc(&d_i, n * 12));
-    CUDA_TRY(cudaMemcpy(d_p, pos3, n * 12, cudaMemcpyHostToDevice));
-    CUDA_TRY(cudaMemcpy(d_n, normal3, n * 12, cudaMemcpyHostToDevice));
-    cudaError_t e = photon_gather_launch(h->pm[which], d_p, d_n, n, max_dist, k, d_i, cudaStreamPerThread);
+    DevBuf bp, bn, bi;
+    cudaError_t e = bp.alloc(n * 12);
+    if (e == cudaSuccess) e = bn.alloc(n * 12);
+    if (e == cudaSuccess) e = bi.alloc(n * 12);
+    if (e != cudaSuccess) { (void)cudaGetLastError(); return fail(cuda_code(e), std::string("photon_gather staging: ") + cudaGetErrorString(e)); }
+    float *d_p = bp.as<float>(), *d_n = bn.as<float>(), *d_i = bi.as<float>();
+    e = cudaMemcpyAsync(d_p, pos3, n * 12, cudaMemcpyHostToDevice, cudaStreamPerThread);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(d_n, normal3, n * 12, cudaMemcpyHostToDevice, cudaStreamPerThread);
+    if (e == cudaSuccess) e = photon_gather_launch(h->pm[which], d_p, d_n, n, max_dist, k, d_i, cudaStreamPerThread);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(irrad3, d_i, n * 12, cudaMemcpyDeviceToHost, cudaStreamPerThread);
     if (e == cudaSuccess) e = cudaStreamSynchronize(cudaStreamPerThread);
-    if (e == cudaSuccess) e = cudaMemcpy(irrad3, d_i, n * 12, cudaMemcpyDeviceToHost);
-    cudaFree(d_p); cudaFree(d_n); cudaFree(d_i);
     if (e != cudaSuccess) return fail(MIROGPU_ERR_CUDA, std::string("photon_gather: ") + cudaGetErrorString(e));
     return MIROGPU_OK;
 }

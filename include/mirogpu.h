@@ -283,7 +283,7 @@ int mirogpu_photon_trace(mirogpu_handle h, int light_index, int caustic, uint32_
                          uint8_t* counts, float* records);
 /* Gather search of map `which`.  exact = 0 (default): one query per warp -- a shared stack of kd nodes and a shared
  * candidate buffer, 32 nodes tested per step, the k-th distance found by bisection when the buffer fills; it ends with the
- * same k nearest photons as the reference's search, summed in another order (estimates agree to ~1e-6 relative; k <= 640, larger k uses the exact search).
+ * same k nearest photons as the reference's search, summed in another order (estimates agree to ~1e-6 relative; k <= 512).
  * exact = 1: the reference's search verbatim, one query per thread (same visiting order, heap and summation order:
  * bit-identical estimates), several times slower. */
 int mirogpu_photon_set_exact(mirogpu_handle h, int which, int exact);
