@@ -389,20 +389,36 @@ void flatten_bvh4(const BinaryBvh& b, FlatBvh& out)
         }
         return k;
     };
-    // depth-first numbering of the wide nodes (a subtree is contiguous in HBM)
+    // numbering of the wide nodes: a short breadth-first prefix, then depth-first (a subtree is contiguous in HBM)
     struct Item { uint32_t bnode; uint32_t depth; uint32_t pending; };   // pending: stack entries left behind by the ancestors
     std::vector<int32_t> flat_index(b.nodes.size(), -1);
     out.max_stack = 0;
-    std::vector<Item> stack; stack.push_back({0u, 1u, 0u});
+    // The first MIRO_TOP_NODES wide nodes are numbered breadth-first (the top levels occupy indices [0, 85): levels of 1 + 4 +
+    // 16 + 64 nodes when full -- the hybrid kernel can stage that prefix in shared memory), everything below depth-first.
     std::vector<uint32_t> wide_order;
-    while (!stack.empty()) {
-        const Item it = stack.back(); stack.pop_back();
+    std::vector<Item> top; top.push_back({0u, 1u, 0u});
+    size_t head = 0;
+    auto visit = [&](const Item& it, int32_t ch[4]) -> int {
         flat_index[it.bnode] = (int32_t)wide_order.size();
         wide_order.push_back(it.bnode);
         out.max_depth = std::max(out.max_depth, it.depth);
-        int32_t ch[4];
         const int k = collect(it.bnode, ch);
         out.max_stack = std::max(out.max_stack, it.pending + (uint32_t)(k - 1));
+        return k;
+    };
+    while (head < top.size() && wide_order.size() < MIRO_TOP_NODES) {
+        const Item it = top[head++];
+        int32_t ch[4];
+        const int k = visit(it, ch);
+        for (int i = 0; i < k; ++i)
+            if (b.nodes[ch[i]].left >= 0) top.push_back({(uint32_t)ch[i], it.depth + 1, it.pending + (uint32_t)(k - 1)});
+    }
+    std::vector<Item> stack;
+    for (size_t r = top.size(); r > head; --r) stack.push_back(top[r - 1]);   // the subtrees below the prefix, first one on top
+    while (!stack.empty()) {
+        const Item it = stack.back(); stack.pop_back();
+        int32_t ch[4];
+        const int k = visit(it, ch);
         for (int i = k - 1; i >= 0; --i)
             if (b.nodes[ch[i]].left >= 0) stack.push_back({(uint32_t)ch[i], it.depth + 1, it.pending + (uint32_t)(k - 1)});
     }

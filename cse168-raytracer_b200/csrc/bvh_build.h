@@ -20,6 +20,9 @@
 #include <cstdint>
 #include <vector>
 
+// four-wide layouts: the first MIRO_TOP_NODES nodes are the top levels in breadth-first order (1 + 4 + 16 + 64)
+#define MIRO_TOP_NODES 85
+
 namespace mirogpu {
 
 struct Aabb {

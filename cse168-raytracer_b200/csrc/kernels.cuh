@@ -130,12 +130,23 @@ __global__ void __launch_bounds__(128) k_trace_persistent(DeviceScene s, const m
 // are claimed from a global ticket one ahead of use and prefetched into L2 while the warp works on the current one.
 //   PF    prefetch flags of bvh2_node_step; bit 3: prefetch the pool claimed ahead         MINB  resident CTAs per SM asked of the compiler
 //   NREP  node steps per vote (a lane that leaves the inner nodes sits the rest out)
-template <int LAYOUT, bool ANY, int PF, int MINB, int NREP>
+//   SHORT stack entries per lane kept in shared memory ([entry][thread], conflict-free), deeper ones in local memory (0: all local)
+//   STAGE QBVH4 only: the first STAGE nodes (top levels, breadth-first numbering) copied into shared memory by every CTA
+template <int LAYOUT, bool ANY, int PF, int MINB, int NREP, int SHORT = 0, int STAGE = 0>
 __global__ void __launch_bounds__(128, MINB) k_trace_hybrid(DeviceScene s, const mirogpu_ray* __restrict__ rays, size_t n,
                                                                  mirogpu_hit* __restrict__ hits, unsigned long long* __restrict__ ticket,
                                                                  int nmin, int period, int min_idle, uint32_t pool,
-                                                                 const uint32_t* __restrict__ d_n, uint32_t mult)
+                                                                 const uint32_t* __restrict__ d_n, uint32_t mult, uint32_t num_nodes)
 {
+    constexpr int DEPTH = (LAYOUT == MIROGPU_LAYOUT_BVH2 ? MIRO_STACK : MIRO_STACK4) + 1;
+    __shared__ int32_t s_stack[SHORT > 0 ? SHORT * 128 : 1];
+    __shared__ float4 s_top[STAGE > 0 ? STAGE * 4 : 1];
+    if (STAGE > 0) {
+        // nodes past the end of a small tree are never addressed (links only name existing nodes)
+        const uint32_t cnt = min((uint32_t)STAGE, num_nodes) * 4u;
+        for (uint32_t k = threadIdx.x; k < cnt; k += 128) s_top[k] = __ldg(s.nodes + k);
+        __syncthreads();
+    }
     if (d_n) n = min(n, (size_t)*d_n * mult);
     const unsigned lane = threadIdx.x & 31u;
     const unsigned lt_mask = (1u << lane) - 1u;
@@ -146,7 +157,9 @@ __global__ void __launch_bounds__(128, MINB) k_trace_hybrid(DeviceScene s, const
     mirogpu_ray r;
     Bvh2Walk w;
     BestHit best;
-    int32_t stack[(LAYOUT == MIROGPU_LAYOUT_BVH2 ? MIRO_STACK : MIRO_STACK4) + 1];
+    int32_t pleaf = MIRO_BVH2_DONE;   // PF bit 6: the postponed leaf (none otherwise; the compiler drops it)
+    SplitStack<SHORT, DEPTH, 128> stack;
+    stack.sm = s_stack + threadIdx.x;
     r.ox = r.oy = r.oz = r.tmin = r.dx = r.dy = r.dz = r.tmax = 0.f;
     w.node = w.tos = MIRO_BVH2_DONE; w.sp = 0;
     w.idx = w.idy = w.idz = w.oodx = w.oody = w.oodz = 0.f;
@@ -169,7 +182,7 @@ __global__ void __launch_bounds__(128, MINB) k_trace_hybrid(DeviceScene s, const
     nxt = claim(0u);
     for (;;) {
         // ---- hand new rays to idle lanes (two passes, so a lane that drew a dead ray gets another) ----
-        unsigned idle = __ballot_sync(0xffffffffu, w.node == MIRO_BVH2_DONE);
+        unsigned idle = __ballot_sync(0xffffffffu, w.node == MIRO_BVH2_DONE && pleaf == MIRO_BVH2_DONE);
         if (__popc(idle) >= min_idle) {
             for (int pass = 0; pass < 2 && idle; ++pass) {
                 if (cur >= cur_end) {
@@ -177,7 +190,7 @@ __global__ void __launch_bounds__(128, MINB) k_trace_hybrid(DeviceScene s, const
                     cur = nxt; cur_end = nxt + nxt_len;
                     nxt = claim(cur);
                 }
-                if (w.node == MIRO_BVH2_DONE) {
+                if (w.node == MIRO_BVH2_DONE && pleaf == MIRO_BVH2_DONE) {
                     const uint32_t i = cur + __popc(idle & lt_mask);
                     if (i < cur_end) {
                         r = load_ray(rays, i);
@@ -187,12 +200,40 @@ __global__ void __launch_bounds__(128, MINB) k_trace_hybrid(DeviceScene s, const
                     }
                 }
                 cur = min(cur + (uint32_t)__popc(idle), cur_end);
-                idle = __ballot_sync(0xffffffffu, w.node == MIRO_BVH2_DONE);
+                idle = __ballot_sync(0xffffffffu, w.node == MIRO_BVH2_DONE && pleaf == MIRO_BVH2_DONE);
             }
             if (idle == 0xffffffffu) {
                 if (cur >= cur_end && nxt >= n32) return;
                 continue;
             }
+        }
+        if (PF & 64) {
+            // Postponed leaves: a lane whose descent reaches a leaf parks it in `pleaf` and walks on (its best.t is stale until the
+            // parked leaf is tested, so it may enter a few nodes it would have culled); it only stops for a leaf phase when a second
+            // leaf turns up.  More lanes take part in every node step, and leaf phases start with more lanes holding a leaf.
+            for (int it = 0; it < period; ++it) {
+                const bool at_leaf = w.node < 0 && w.node != MIRO_BVH2_DONE;
+                const unsigned mn = __ballot_sync(0xffffffffu, w.node >= 0);
+                const unsigned ml = __ballot_sync(0xffffffffu, pleaf != MIRO_BVH2_DONE || at_leaf);
+                if ((mn | ml) == 0u) break;
+                if (mn != 0u && (__popc(mn) >= nmin || ml == 0u)) {
+#pragma unroll
+                    for (int rep = 0; rep < NREP; ++rep)
+                        if (w.node >= 0) {
+                            qbvh4_node_step<PF, decltype(stack), STAGE>(s.nodes, s.tris, r, w, stack, best, s_top);
+                            if (w.node < 0 && w.node != MIRO_BVH2_DONE && pleaf == MIRO_BVH2_DONE) { pleaf = w.node; bvh2_pop(w, stack); }
+                        }
+                } else {
+                    if (pleaf == MIRO_BVH2_DONE && at_leaf) { pleaf = w.node; bvh2_pop(w, stack); }
+                    if (pleaf != MIRO_BVH2_DONE) {
+                        bool hit;
+                        pleaf = leaf_ref_test_one(s.tris, r, pleaf, best, hit);
+                        if (ANY && hit) { pleaf = MIRO_BVH2_DONE; w.node = MIRO_BVH2_DONE; }
+                    }
+                }
+                if (w.node == MIRO_BVH2_DONE && pleaf == MIRO_BVH2_DONE && ((mn | ml) >> lane & 1u)) store_hit(hits, my, best);
+            }
+            continue;
         }
         for (int it = 0; it < period; ++it) {
             const unsigned mn = __ballot_sync(0xffffffffu, w.node >= 0);
@@ -202,12 +243,13 @@ __global__ void __launch_bounds__(128, MINB) k_trace_hybrid(DeviceScene s, const
 #pragma unroll
                 for (int rep = 0; rep < NREP; ++rep)
                     if (w.node >= 0) {
-                        if (LAYOUT == MIROGPU_LAYOUT_QBVH4) qbvh4_node_step<PF>(s.nodes, s.tris, r, w, stack, best);
+                        if (LAYOUT == MIROGPU_LAYOUT_QBVH4) qbvh4_node_step<PF, decltype(stack), STAGE>(s.nodes, s.tris, r, w, stack, best, s_top);
                         else if (LAYOUT == MIROGPU_LAYOUT_BVH4) bvh4_node_step<PF>(s.nodes, s.tris, r, w, stack, best);
                         else bvh2_node_step<PF>(s.nodes, s.tris, r, w, stack, best);
                     }
             } else if (w.node < 0 && w.node != MIRO_BVH2_DONE) {
-                if (PF & 16) bvh2_leaf_step_one<ANY>(s.tris, r, w, stack, best);
+                if (PF & 32) bvh2_leaf_step_two<ANY>(s.tris, r, w, stack, best);
+                else if (PF & 16) bvh2_leaf_step_one<ANY>(s.tris, r, w, stack, best);
                 else bvh2_leaf_step<ANY>(s.tris, r, w, stack, best);
             }
             if (w.node == MIRO_BVH2_DONE && ((mn | ml) >> lane & 1u)) store_hit(hits, my, best);

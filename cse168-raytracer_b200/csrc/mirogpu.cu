@@ -110,6 +110,7 @@ struct mirogpu_scene {
     int packets_per_ticket = 1;                            // packet kernel: 32-ray packets per ticket; env MIROGPU_PPT
     size_t node_bytes_dev = 0, tri_bytes_dev = 0;
     int hyb_pf = 0, hyb_minb = 9;                          // prefetch flags (traverse.cuh), min resident CTAs
+    int hyb_short = 0, hyb_stage = 0;                      // shared-memory stack entries per lane / staged top nodes (QBVH4); env MIROGPU_SHORT / _STAGE
     DeviceScene ds{};
     void* d_nodes = nullptr;
     void* d_tris = nullptr;
@@ -137,14 +138,14 @@ namespace {
 
 // n is the number of rays, or -- when d_n is given -- an upper bound on it: the kernels then read the real count
 // *d_n * mult from device memory (wavefront queues whose size the host never sees).
-template <int LAYOUT, bool ANY, int PF, int MINB, int NREP>
+template <int LAYOUT, bool ANY, int PF, int MINB, int NREP, int SHORT = 0, int STAGE = 0>
 cudaError_t launch_hybrid_inst(mirogpu_scene* h, const mirogpu_ray* d_rays, size_t n, mirogpu_hit* d_hits, unsigned long long* ticket,
                                cudaStream_t st, const uint32_t* d_n, uint32_t mult)
 {
     static std::atomic<int> cached_occ{0};   // per instantiation; the answer depends only on the kernel and the device type
     int occ = cached_occ.load(std::memory_order_relaxed);
     if (occ == 0) {
-        cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_trace_hybrid<LAYOUT, ANY, PF, MINB, NREP>, 128, 0);
+        cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_trace_hybrid<LAYOUT, ANY, PF, MINB, NREP, SHORT, STAGE>, 128, 0);
         if (e != cudaSuccess) return e;
         if (occ < 1) occ = 1;
         cached_occ.store(occ, std::memory_order_relaxed);
@@ -152,8 +153,8 @@ cudaError_t launch_hybrid_inst(mirogpu_scene* h, const mirogpu_ray* d_rays, size
     size_t grid = (size_t)h->sm_count * occ;
     const size_t need = (n + 127) / 128;
     if (grid > need) grid = need;
-    k_trace_hybrid<LAYOUT, ANY, PF, MINB, NREP><<<(unsigned)grid, 128, 0, st>>>(h->ds, d_rays, n, d_hits, ticket, h->hyb_nmin, h->hyb_period,
-                                                                            h->hyb_min_idle, (uint32_t)h->hyb_pool, d_n, mult);
+    k_trace_hybrid<LAYOUT, ANY, PF, MINB, NREP, SHORT, STAGE><<<(unsigned)grid, 128, 0, st>>>(h->ds, d_rays, n, d_hits, ticket, h->hyb_nmin, h->hyb_period,
+                                                                            h->hyb_min_idle, (uint32_t)h->hyb_pool, d_n, mult, h->info.num_nodes);
     return cudaGetLastError();
 }
 
@@ -161,11 +162,23 @@ template <int LAYOUT, bool ANY>
 cudaError_t launch_hybrid(mirogpu_scene* h, const mirogpu_ray* d_rays, size_t n, mirogpu_hit* d_hits, unsigned long long* ticket,
                           cudaStream_t st, const uint32_t* d_n, uint32_t mult)
 {
-#define MIRO_HYB(PF, MINB, NREP) if (h->hyb_pf == PF && h->hyb_minb == MINB && h->hyb_nrep == NREP) return launch_hybrid_inst<LAYOUT, ANY, PF, MINB, NREP>(h, d_rays, n, d_hits, ticket, st, d_n, mult);
+#define MIRO_HYB(PF, MINB, NREP) if (h->hyb_pf == PF && h->hyb_minb == MINB && h->hyb_nrep == NREP && h->hyb_short == 0 && h->hyb_stage == 0) return launch_hybrid_inst<LAYOUT, ANY, PF, MINB, NREP>(h, d_rays, n, d_hits, ticket, st, d_n, mult);
     MIRO_HYB(0, 9, 2) MIRO_HYB(0, 8, 2) MIRO_HYB(0, 9, 1) MIRO_HYB(0, 9, 3) MIRO_HYB(16, 9, 2) MIRO_HYB(16, 9, 3)
 #undef MIRO_HYB
-    return LAYOUT == MIROGPU_LAYOUT_QBVH4 ? launch_hybrid_inst<LAYOUT, ANY, 16, 9, 3>(h, d_rays, n, d_hits, ticket, st, d_n, mult)
-                                          : launch_hybrid_inst<LAYOUT, ANY, 0, 9, 2>(h, d_rays, n, d_hits, ticket, st, d_n, mult);
+    if (LAYOUT == MIROGPU_LAYOUT_QBVH4) {
+        // shared-memory short stack / staged top levels (north star; measured in profiles/r02_*): selectable combinations
+#define MIRO_HYB2(MINB, SHORT, STAGE) if (h->hyb_pf == 16 && h->hyb_nrep == 3 && h->hyb_minb == MINB && h->hyb_short == SHORT && h->hyb_stage == STAGE) return launch_hybrid_inst<MIROGPU_LAYOUT_QBVH4, ANY, 16, MINB, 3, SHORT, STAGE>(h, d_rays, n, d_hits, ticket, st, d_n, mult);
+        MIRO_HYB2(9, 4, 0) MIRO_HYB2(9, 8, 0) MIRO_HYB2(9, 12, 0) MIRO_HYB2(9, 16, 0) MIRO_HYB2(10, 8, 0) MIRO_HYB2(10, 12, 0) MIRO_HYB2(10, 16, 0)
+        MIRO_HYB2(9, 0, 21) MIRO_HYB2(9, 0, 85) MIRO_HYB2(9, 8, 21) MIRO_HYB2(9, 8, 85) MIRO_HYB2(9, 16, 85) MIRO_HYB2(10, 0, 0) MIRO_HYB2(12, 8, 0) MIRO_HYB2(12, 16, 0)
+#undef MIRO_HYB2
+        // leaf-phase variants: two triangles per phase (PF 48), one postponed leaf per lane (PF 80)
+#define MIRO_HYB3(PF, MINB, NREP, SHORT) if (h->hyb_pf == PF && h->hyb_minb == MINB && h->hyb_nrep == NREP && h->hyb_short == SHORT && h->hyb_stage == 0) return launch_hybrid_inst<MIROGPU_LAYOUT_QBVH4, ANY, PF, MINB, NREP, SHORT, 0>(h, d_rays, n, d_hits, ticket, st, d_n, mult);
+        MIRO_HYB3(48, 9, 3, 0) MIRO_HYB3(48, 9, 3, 8) MIRO_HYB3(80, 9, 3, 0) MIRO_HYB3(80, 9, 3, 8) MIRO_HYB3(80, 9, 2, 0) MIRO_HYB3(80, 9, 2, 8) MIRO_HYB3(80, 10, 3, 8)
+#undef MIRO_HYB3
+        if (getenv("MIROGPU_STRICT")) return cudaErrorInvalidValue;   // measurement runs: an uninstantiated knob combination must not silently time the default
+        return launch_hybrid_inst<LAYOUT, ANY, 16, 9, 3>(h, d_rays, n, d_hits, ticket, st, d_n, mult);
+    }
+    return launch_hybrid_inst<LAYOUT, ANY, 0, 9, 2>(h, d_rays, n, d_hits, ticket, st, d_n, mult);
 }
 
 template <int LAYOUT, bool ANY>
@@ -364,6 +377,8 @@ int mirogpu_scene_create(const float* tri_vertices, const float* tri_normals, co
     if (const char* e = getenv("MIROGPU_PERIOD")) { const int v = atoi(e); if (v >= 1 && v <= 100000) h->hyb_period = v; }
     if (const char* e = getenv("MIROGPU_PF")) h->hyb_pf = atoi(e);
     if (const char* e = getenv("MIROGPU_MINB")) h->hyb_minb = atoi(e);
+    if (const char* e = getenv("MIROGPU_SHORT")) h->hyb_short = atoi(e);
+    if (const char* e = getenv("MIROGPU_STAGE")) h->hyb_stage = atoi(e);
     if (const char* e = getenv("MIROGPU_MINIDLE")) { const int v = atoi(e); if (v >= 1 && v <= 32) h->hyb_min_idle = v; }
 
     // ---- device build (LBVH) -----------------------------------------------------------------------

@@ -108,6 +108,44 @@ __device__ __forceinline__ bool push_item(const WaveParams& p, Queue& next, uint
     return true;
 }
 
+// One light of Phong::shade's loop up to the shadow query (Phong.cpp:61-158): unit vector to the light, its distance, the
+// diffuse term (light colour x kd^2: Phong::diffuse2D returns m_diffuse, so kd enters squared, Phong.cpp:146, Phong.h:20) and
+// the highlight (exponent fixed at 500, Phong.cpp:152).  false: the point lies outside a DirectionalAreaLight's beam.
+__device__ __forceinline__ bool light_terms(const mirogpu_light L, const SurfacePoint& sp, const mirogpu_material& m, const float rd[3],
+                                            float l[3], float& dist, float cd[3], float& hl)
+{
+    if (L.kind == 1) { l[0] = -L.normal[0]; l[1] = -L.normal[1]; l[2] = -L.normal[2]; }
+    else { l[0] = L.position[0] - sp.P[0]; l[1] = L.position[1] - sp.P[1]; l[2] = L.position[2] - sp.P[2]; }
+    float falloff = dot3(l, l);
+    dist = sqrtf(falloff);
+    const float invd = 1.0f / dist;
+    l[0] *= invd; l[1] *= invd; l[2] *= invd;
+    float nDotL;
+    if (L.kind == 1) {
+        const float nl[3] = {-L.normal[0], -L.normal[1], -L.normal[2]};
+        nDotL = dot3(sp.N, nl);
+        const float lp[3] = {L.position[0] - sp.P[0], L.position[1] - sp.P[1], L.position[2] - sp.P[2]};
+        const float t = dot3(L.normal, lp) / -1.0f;
+        const float q[3] = {sp.P[0] - t * L.normal[0] - L.position[0], sp.P[1] - t * L.normal[1] - L.position[1], sp.P[2] - t * L.normal[2] - L.position[2]};
+        if (dot3(q, q) > L.radius * L.radius) return false;
+        falloff = 1.0f / MIRO_PI;
+    } else {
+        nDotL = dot3(sp.N, l);
+        falloff = 1.0f / (falloff * 4.0f * MIRO_PI * MIRO_PI);
+    }
+    const float dterm = fmaxf(0.0f, nDotL * falloff * L.wattage);
+    cd[0] = L.color[0] * dterm * m.kd[0] * m.kd[0]; cd[1] = L.color[1] * dterm * m.kd[1] * m.kd[1]; cd[2] = L.color[2] * dterm * m.kd[2] * m.kd[2];
+    hl = 0.f;
+    if (m.shininess < INFINITY) {
+        const float ldn = 2.0f * dot3(l, sp.N);
+        const float r[3] = {-l[0] + ldn * sp.N[0], -l[1] + ldn * sp.N[1], -l[2] + ldn * sp.N[2]};
+        const float e[3] = {-rd[0], -rd[1], -rd[2]};
+        const float c = fmaxf(0.0f, fminf(1.f, dot3(e, r)));
+        hl = fmaxf(0.0f, powf(c, 500.0f) * falloff * L.wattage);
+    }
+    return true;
+}
+
 // Returns true when the item wrote its (single) child in place -- diffuse-bounce mode only.
 __device__ __forceinline__ bool shade_item(const WaveParams& p, const Queue& cur, uint32_t i, const float4 hv, const ShadeRecord& rec, Queue& next,
                                            uint32_t* next_count, uint32_t* dropped, mirogpu_ray* shadow_rays, float4* shadow_cd, float4* shadow_ch,
@@ -137,38 +175,8 @@ __device__ __forceinline__ bool shade_item(const WaveParams& p, const Queue& cur
 
     // ---- Phong::shade light loop -------------------------------------------------------------------
     for (uint32_t li = 0; li < p.nlights; ++li) {
-        const mirogpu_light L = p.lights[li];
-        float l[3];
-        if (L.kind == 1) { l[0] = -L.normal[0]; l[1] = -L.normal[1]; l[2] = -L.normal[2]; }
-        else { l[0] = L.position[0] - sp.P[0]; l[1] = L.position[1] - sp.P[1]; l[2] = L.position[2] - sp.P[2]; }
-        float falloff = dot3(l, l);
-        const float dist = sqrtf(falloff);
-        const float invd = 1.0f / dist;
-        l[0] *= invd; l[1] *= invd; l[2] *= invd;
-        float nDotL;
-        if (L.kind == 1) {
-            const float nl[3] = {-L.normal[0], -L.normal[1], -L.normal[2]};
-            nDotL = dot3(sp.N, nl);
-            const float lp[3] = {L.position[0] - sp.P[0], L.position[1] - sp.P[1], L.position[2] - sp.P[2]};
-            const float t = dot3(L.normal, lp) / -1.0f;
-            const float q[3] = {sp.P[0] - t * L.normal[0] - L.position[0], sp.P[1] - t * L.normal[1] - L.position[1], sp.P[2] - t * L.normal[2] - L.position[2]};
-            if (dot3(q, q) > L.radius * L.radius) continue;
-            falloff = 1.0f / MIRO_PI;
-        } else {
-            nDotL = dot3(sp.N, l);
-            falloff = 1.0f / (falloff * 4.0f * MIRO_PI * MIRO_PI);
-        }
-        const float dterm = fmaxf(0.0f, nDotL * falloff * L.wattage);
-        // diffuseColor * m_diffuse: Phong::diffuse2D returns m_diffuse, so kd enters squared (Phong.cpp:146, Phong.h:20)
-        float cd[3] = {L.color[0] * dterm * m.kd[0] * m.kd[0], L.color[1] * dterm * m.kd[1] * m.kd[1], L.color[2] * dterm * m.kd[2] * m.kd[2]};
-        float hl = 0.f;
-        if (m.shininess < INFINITY) {
-            const float ldn = 2.0f * dot3(l, sp.N);
-            const float r[3] = {-l[0] + ldn * sp.N[0], -l[1] + ldn * sp.N[1], -l[2] + ldn * sp.N[2]};
-            const float e[3] = {-rd[0], -rd[1], -rd[2]};
-            const float c = fmaxf(0.0f, fminf(1.f, dot3(e, r)));
-            hl = fmaxf(0.0f, powf(c, 500.0f) * falloff * L.wattage);   // exponent fixed at 500 (Phong.cpp:152)
-        }
+        float l[3], cd[3], dist, hl;
+        if (!light_terms(p.lights[li], sp, m, rd, l, dist, cd, hl)) continue;
         if (p.shadows) {
             if (cd[0] > 0.f || cd[1] > 0.f || cd[2] > 0.f || hl > 0.f) {
                 const size_t s = (size_t)i * p.nlights + li;
@@ -467,6 +475,141 @@ __global__ void __launch_bounds__(256) k_frame_max(const float* __restrict__ rgb
     }
 }
 
+
+// ---- BASELINE config 3 as two fused waves (MIROGPU_RENDER_DIFFUSE_BOUNCE without shadow rays or photon maps) -----------------
+// The general wavefront above carries {ray, pixel, weight, depth} per path item through queues.  In this mode none of that
+// is data: item i IS (sample i / npix, pixel i % npix), wave 0's weight is 1 and its ray is a pure function of (pixel, sample)
+// -- recomputed here (Camera::eyeRay, ~40 instructions) instead of being re-read -- and wave 1's weight is the kd of the
+// material wave 0 hit (4 bytes).  Every item owns its slot of the per-sample plane, so radiance is stored, not accumulated
+// atomically: wave 0 writes its direct term, wave 1 adds its own -- the same two floating-point additions, in the same order,
+// as the general path's atomics, hence bit-identical frames.  The bounce ray overwrites the camera ray in place.
+// Per item: wave 0 moves 16 (hit) + 96 (shading record) + 32 (bounce ray) + 4 + 12 bytes, wave 1 16 + 16 + 96 + 4 + 24.
+#define MIRO_BW_THREADS 128
+template <int ITEMS>
+__global__ void __launch_bounds__(MIRO_BW_THREADS) k_bounce_wave0(WaveParams p, CameraBasis cb, int height, int nrows_local, int jitter, uint32_t nitems,
+                                                                  const mirogpu_hit* __restrict__ hits, mirogpu_ray* __restrict__ rays,
+                                                                  uint32_t* __restrict__ parent_mat, float* __restrict__ planes, uint32_t* live_slots)
+{
+    const uint32_t base = blockIdx.x * (MIRO_BW_THREADS * ITEMS) + threadIdx.x;
+    float4 hv[ITEMS];
+    ShadeRecord rec[ITEMS];
+#pragma unroll
+    for (int k = 0; k < ITEMS; ++k) {
+        const uint32_t i = base + k * MIRO_BW_THREADS;
+        hv[k] = i < nitems ? __ldcs(reinterpret_cast<const float4*>(hits + i)) : make_float4(0.f, __uint_as_float(MIROGPU_MISS), 0.f, 0.f);
+    }
+#pragma unroll
+    for (int k = 0; k < ITEMS; ++k) {
+        if (__float_as_uint(hv[k].y) != MIROGPU_MISS) rec[k] = load_shade_record(p.ds, __float_as_uint(hv[k].y));
+        else rec[k].r0.lo = rec[k].r0.hi = rec[k].r1.lo = rec[k].r1.hi = rec[k].r2.lo = rec[k].r2.hi = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+    unsigned live = 0;
+#pragma unroll
+    for (int k = 0; k < ITEMS; ++k) {
+        const uint32_t i = base + k * MIRO_BW_THREADS;
+        bool child = false;
+        if (i < nitems) {
+            const uint32_t sb = i / p.npix, lpix = i - sb * p.npix;
+            float4 r0 = make_float4(0.f, 0.f, 0.f, 0.0f), r1 = make_float4(0.f, 0.f, 1.f, -1.0f);   // dead slot: tmax < tmin
+            uint32_t mat = MIROGPU_MISS;
+            float out[3];
+            if (__float_as_uint(hv[k].y) == MIROGPU_MISS) {
+                out[0] = p.bg[0]; out[1] = p.bg[1]; out[2] = p.bg[2];                                // Scene.cpp:338-342
+            } else {
+                // the camera ray of this item, as k_gen_primary made it (bit-exact: same operations)
+                const uint32_t row = lpix / (uint32_t)p.width;
+                const int x = (int)(lpix - row * (uint32_t)p.width), y = p.first_row + (int)row * p.row_stride;
+                float dx = 0.5f, dy = 0.5f;
+                const uint32_t frame_pixel = (uint32_t)y * (uint32_t)p.width + (uint32_t)x;
+                if (jitter) uniform2(p.seed, frame_pixel, p.sample_base + sb, RNG_DIM_PIXEL, dx, dy);
+                const float U = xadd(cb.left, xmul(xsub(cb.right, cb.left), xdiv(xadd((float)x, dx), (float)p.width)));
+                const float V = xadd(cb.bottom, xmul(xsub(cb.top, cb.bottom), xdiv(xadd((float)y, dy), (float)height)));
+                float rd[3];
+#pragma unroll
+                for (int c = 0; c < 3; ++c) rd[c] = xsub(xadd(xmul(cb.u[c], U), xmul(cb.v[c], V)), cb.w[c]);
+                const float inv = xdiv(1.0f, xsqrt(xdot(rd[0], rd[1], rd[2], rd[0], rd[1], rd[2])));
+                rd[0] = xmul(rd[0], inv); rd[1] = xmul(rd[1], inv); rd[2] = xmul(rd[2], inv);
+                mirogpu_hit h; h.t = hv[k].x; h.prim_id = __float_as_uint(hv[k].y); h.beta = hv[k].z; h.gamma = hv[k].w;
+                const SurfacePoint sp = resolve_hit(rec[k], h);
+                const mirogpu_material m = p.mats[sp.material];
+                float direct[3] = {0.f, 0.f, 0.f};
+                for (uint32_t li = 0; li < p.nlights; ++li) {
+                    float l[3], cd[3], dist, hl;
+                    if (!light_terms(p.lights[li], sp, m, rd, l, dist, cd, hl)) continue;
+                    direct[0] += cd[0] + hl; direct[1] += cd[1] + hl; direct[2] += cd[2] + hl;
+                }
+                out[0] = 1.f * direct[0]; out[1] = 1.f * direct[1]; out[2] = 1.f * direct[2];
+                if (m.kd[0] > 0.f || m.kd[1] > 0.f || m.kd[2] > 0.f) {   // Ray::diffuse from the first hit (Ray.h:109-122)
+                    float u1, u2;
+                    uniform2(p.seed, frame_pixel, p.sample_base + sb, RNG_DIM_BOUNCE, u1, u2);
+                    float d[3];
+                    align_hemisphere(sp.N, xmul(xmul(2.0f, MIRO_PI), u2), asinf(sqrtf(u1)), d);
+                    r0 = make_float4(sp.P[0] + d[0] * MIRO_EPS, sp.P[1] + d[1] * MIRO_EPS, sp.P[2] + d[2] * MIRO_EPS, 0.0f);
+                    r1 = make_float4(d[0], d[1], d[2], MIROGPU_TMAX);
+                    mat = sp.material;
+                    child = true;
+                }
+            }
+            float4* r = reinterpret_cast<float4*>(rays + i);
+            __stcs(r, r0); __stcs(r + 1, r1);
+            parent_mat[i] = mat;
+            float* o = planes + 3 * (size_t)i;     // plane of sample sb, pixel lpix: (sb * npix + lpix) = i
+            o[0] = out[0]; o[1] = out[1]; o[2] = out[2];
+        }
+        live += __popc(__ballot_sync(0xffffffffu, child));
+    }
+    if ((threadIdx.x & 31u) == 0u && live) atomicAdd(live_slots + (blockIdx.x & 31u), live);
+}
+
+template <int ITEMS>
+__global__ void __launch_bounds__(MIRO_BW_THREADS) k_bounce_wave1(WaveParams p, uint32_t nitems, const mirogpu_hit* __restrict__ hits,
+                                                                  const mirogpu_ray* __restrict__ rays, const uint32_t* __restrict__ parent_mat,
+                                                                  float* __restrict__ planes)
+{
+    const uint32_t base = blockIdx.x * (MIRO_BW_THREADS * ITEMS) + threadIdx.x;
+    float4 hv[ITEMS];
+    uint32_t pm[ITEMS];
+    ShadeRecord rec[ITEMS];
+#pragma unroll
+    for (int k = 0; k < ITEMS; ++k) {
+        const uint32_t i = base + k * MIRO_BW_THREADS;
+        pm[k] = i < nitems ? __ldcs(parent_mat + i) : MIROGPU_MISS;
+        hv[k] = (i < nitems && pm[k] != MIROGPU_MISS) ? __ldcs(reinterpret_cast<const float4*>(hits + i)) : make_float4(0.f, __uint_as_float(MIROGPU_MISS), 0.f, 0.f);
+    }
+#pragma unroll
+    for (int k = 0; k < ITEMS; ++k) {
+        if (__float_as_uint(hv[k].y) != MIROGPU_MISS) rec[k] = load_shade_record(p.ds, __float_as_uint(hv[k].y));
+        else rec[k].r0.lo = rec[k].r0.hi = rec[k].r1.lo = rec[k].r1.hi = rec[k].r2.lo = rec[k].r2.hi = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+#pragma unroll
+    for (int k = 0; k < ITEMS; ++k) {
+        const uint32_t i = base + k * MIRO_BW_THREADS;
+        if (i >= nitems || pm[k] == MIROGPU_MISS) continue;        // no bounce ray in this slot
+        const mirogpu_material pmat = p.mats[pm[k]];
+        const float w[3] = {1.f * pmat.kd[0], 1.f * pmat.kd[1], 1.f * pmat.kd[2]};
+        float add[3];
+        if (__float_as_uint(hv[k].y) == MIROGPU_MISS) {
+            add[0] = w[0] * p.bg[0]; add[1] = w[1] * p.bg[1]; add[2] = w[2] * p.bg[2];
+        } else {
+            const float4 dv = __ldcs(reinterpret_cast<const float4*>(rays + i) + 1);
+            const float rd[3] = {dv.x, dv.y, dv.z};
+            mirogpu_hit h; h.t = hv[k].x; h.prim_id = __float_as_uint(hv[k].y); h.beta = hv[k].z; h.gamma = hv[k].w;
+            const SurfacePoint sp = resolve_hit(rec[k], h);
+            const mirogpu_material m = p.mats[sp.material];
+            float direct[3] = {0.f, 0.f, 0.f};
+            for (uint32_t li = 0; li < p.nlights; ++li) {
+                float l[3], cd[3], dist, hl;
+                if (!light_terms(p.lights[li], sp, m, rd, l, dist, cd, hl)) continue;
+                direct[0] += cd[0] + hl; direct[1] += cd[1] + hl; direct[2] += cd[2] + hl;
+            }
+            if (direct[0] == 0.f && direct[1] == 0.f && direct[2] == 0.f) continue;
+            add[0] = w[0] * direct[0]; add[1] = w[1] * direct[1]; add[2] = w[2] * direct[2];
+        }
+        float* o = planes + 3 * (size_t)i;
+        o[0] += add[0]; o[1] += add[1]; o[2] += add[2];
+    }
+}
+
 #define MIRO_MAX_WAVES 16
 #define MIRO_SAMPLE_BATCH 8
 
@@ -517,6 +660,64 @@ int render_device(mirogpu_scene* h, const mirogpu_camera& cam, const mirogpu_ren
     const bool use_pm = rp.use_photon_maps && (h->pm[0].stored > 0 || h->pm[1].stored > 0);
 
     RenderScratch& sc = h->scratch;
+    if (rp.mode == MIROGPU_RENDER_DIFFUSE_BOUNCE && !shadows && !use_pm && rp.max_depth >= 1 && !getenv("MIROGPU_GENERAL_WAVEFRONT")) {
+        // ---- two fused waves (see k_bounce_wave0) ------------------------------------------------------------------------
+        const uint32_t fb = (uint32_t)std::min(rp.spp, 16);
+        const size_t fitems0 = npix * fb;
+        if (fitems0 >= (1ull << 31)) { err = "frame too large"; return MIROGPU_ERR_UNSUPPORTED; }
+        RT(sc.ensure(0, fitems0 * sizeof(mirogpu_ray))); RT(sc.ensure(2, fitems0 * sizeof(mirogpu_hit)));
+        RT(sc.ensure(3, fitems0 * 4)); RT(sc.ensure(12, fitems0 * 12));
+        const size_t fbytes = (npix * 12 + 15) / 16 * 16;
+        RT(sc.ensure(10, fbytes + 256));
+        float* frame = reinterpret_cast<float*>(sc.buf[10]);
+        uint32_t* counters = reinterpret_cast<uint32_t*>(reinterpret_cast<char*>(sc.buf[10]) + fbytes);
+        unsigned long long* d_total = reinterpret_cast<unsigned long long*>(counters + 20);
+        mirogpu_ray* rays = reinterpret_cast<mirogpu_ray*>(sc.buf[0]);
+        mirogpu_hit* hits = reinterpret_cast<mirogpu_hit*>(sc.buf[2]);
+        uint32_t* pmat = reinterpret_cast<uint32_t*>(sc.buf[3]);
+        float* planes = reinterpret_cast<float*>(sc.buf[12]);
+        WaveParams wp;
+        wp.ds = h->ds; wp.mats = h->d_materials; wp.lights = h->d_lights; wp.nlights = h->nlights;
+        wp.mode = rp.mode; wp.shadows = 0; wp.max_depth = rp.max_depth; wp.use_pm = 0;
+        for (int k = 0; k < 3; ++k) wp.bg[k] = rp.bg_color[k];
+        wp.seed = rp.seed; wp.sample = 0; wp.cap = (uint32_t)fitems0;
+        wp.width = rp.width; wp.first_row = first_row; wp.row_stride = rp.row_stride; wp.npix = (uint32_t)npix;
+        CameraBasis cb;
+        camera_basis(cam, rp.width, rp.height, cb);
+        uint64_t launches = 0, host_rays = 0;
+        RT(cudaMemsetAsync(frame, 0, fbytes + 256, st));
+        constexpr int BW = 4;   // items per thread, like k_gen_bounce
+        for (uint32_t s0 = 0; s0 < (uint32_t)rp.spp; s0 += fb) {
+            const uint32_t nb = std::min<uint32_t>(fb, (uint32_t)rp.spp - s0);
+            const size_t items = npix * nb;
+            wp.sample_base = s0;
+            k_gen_primary<<<dim3((unsigned)((npix + 255) / 256), nb), 256, 0, st>>>(cb, rp.width, rp.height, first_row, rp.row_stride, nrows, rp.jitter, rp.seed, s0, nb, rays);
+            RT(dispatch_trace(h, rays, items, hits, MIROGPU_CLOSEST_HIT | MIROGPU_HINT_COHERENT, st));
+            const unsigned grid = (unsigned)((items + MIRO_BW_THREADS * BW - 1) / (MIRO_BW_THREADS * BW));
+            k_bounce_wave0<BW><<<grid, MIRO_BW_THREADS, 0, st>>>(wp, cb, rp.height, nrows, rp.jitter, (uint32_t)items, hits, rays, pmat, planes, counters + MIRO_LIVE_SLOT0);
+            RT(dispatch_trace(h, rays, items, hits, MIROGPU_CLOSEST_HIT, st));
+            k_bounce_wave1<BW><<<grid, MIRO_BW_THREADS, 0, st>>>(wp, (uint32_t)items, hits, rays, pmat, planes);
+            k_fold_planes<<<(unsigned)((npix * 3 + 255) / 256), 256, 0, st>>>(planes, nb, npix * 3, frame);
+            launches += 6;
+            host_rays += items;
+        }
+        k_sum_wave_counters<<<1, 1, 0, st>>>(counters, d_total, 1);   // live bounce rays of all batches (the slots are never reset within a frame)
+        float* gmax = reinterpret_cast<float*>(counters + 18);
+        const float ninf = -INFINITY;
+        RT(cudaMemcpyAsync(gmax, &ninf, 4, cudaMemcpyHostToDevice, st));
+        const size_t nvals = npix * 3;
+        k_resolve_frame<<<(unsigned)((nvals + 255) / 256), 256, 0, st>>>(frame, rp.width, first_row, rp.row_stride, nrows, 1.0f / (float)rp.spp, rp.spp, d_rgb, gmax);
+        launches += 2;
+        if (rp.tonemap || d_rgb8) {
+            k_tonemap<<<(unsigned)((nvals + 255) / 256), 256, 0, st>>>(d_rgb, d_rgb8, rp.width, first_row, rp.row_stride, nrows, gmax);
+            launches++;
+        }
+        RT(cudaGetLastError());
+        RT(cudaMemcpyAsync(h->h_stats, d_total, 8, cudaMemcpyDeviceToHost, st));
+        h->last_rays = host_rays; h->last_launches = launches;
+        h->stats_batches = 1; h->stats_mult = 1;
+        return MIROGPU_OK;
+    }
     // 0,1: queue A/B rays  2: hits  3,4: pix A/B  5,6: weight A/B  7: shadow rays  8: shadow hits  9: shadow cd+ch
     // 10: frame accumulator + counters  11: gather  12: per-sample planes
     RT(sc.ensure(0, cap * sizeof(mirogpu_ray))); RT(sc.ensure(1, cap * sizeof(mirogpu_ray)));

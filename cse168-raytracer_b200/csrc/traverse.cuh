@@ -296,17 +296,36 @@ MIRO_HD void bvh2_begin(const mirogpu_ray& r, Bvh2Walk& w, BestHit& best)
     best.t = r.tmax; best.prim = MIROGPU_MISS; best.beta = 0.f; best.gamma = 0.f;
 }
 
-MIRO_HD void bvh2_pop(Bvh2Walk& w, const int32_t* __restrict__ stack)
+// Where the walk's stack lives.  LocalStack: a per-thread array (local memory).  SplitStack (hybrid kernel): the first SHORT
+// entries of every lane in shared memory, laid out [entry][thread] so that a warp's access is conflict-free whatever the
+// lanes' depths are (bank = lane), deeper entries in a local array -- a divergent local-memory access costs one L1
+// wavefront per distinct line, the shared one always exactly one.
+template <int N>
+struct LocalStack {
+    int32_t a[N];
+    MIRO_HD void put(int i, int32_t v) { a[i] = v; }
+    MIRO_HD int32_t get(int i) const { return a[i]; }
+};
+template <int SHORT, int N, int THREADS>
+struct SplitStack {
+    int32_t* sm;   // this thread's column of the CTA's [SHORT][THREADS] array
+    int32_t a[N > SHORT ? N - SHORT : 1];
+    MIRO_HD void put(int i, int32_t v) { if (i < SHORT) sm[i * THREADS] = v; else a[i - SHORT] = v; }
+    MIRO_HD int32_t get(int i) const { return i < SHORT ? sm[i * THREADS] : a[i - SHORT]; }
+};
+
+template <typename STK>
+MIRO_HD void bvh2_pop(Bvh2Walk& w, const STK& stack)
 {
     w.node = w.tos;
-    if (w.tos != MIRO_BVH2_DONE) w.tos = stack[--w.sp];
+    if (w.tos != MIRO_BVH2_DONE) w.tos = stack.get(--w.sp);
 }
 
 // PF bit 0: prefetch the pushed far child (node or first triangle line) into L2; bit 1: into L1 instead;
 // bit 2: prefetch the triangles of a leaf reached by descent (the lane usually waits for the warp's leaf phase).
-template <int PF>
+template <int PF, typename STK>
 MIRO_HD void bvh2_node_step(const float4* __restrict__ nodes, const float4* __restrict__ tris, const mirogpu_ray& r, Bvh2Walk& w,
-                            int32_t* __restrict__ stack, const BestHit& best)
+                            STK& stack, const BestHit& best)
 {
     const F8 na = ld256(nodes + 4 * (size_t)w.node), nb = ld256(nodes + 4 * (size_t)w.node + 2);
     const float4 n0 = na.lo, n1 = na.hi, nz = nb.lo, lk = nb.hi;
@@ -329,7 +348,7 @@ MIRO_HD void bvh2_node_step(const float4* __restrict__ nodes, const float4* __re
         if (h0 && h1) {
             int32_t other = l1;
             if (t1n < t0n) { next = l1; other = l0; }
-            stack[w.sp++] = w.tos;
+            stack.put(w.sp++, w.tos);
             w.tos = other;
             if (PF & 3) {
                 const float4* a = other >= 0 ? nodes + 4 * (size_t)other : tris + 4 * (size_t)(((uint32_t)~other) >> 3);
@@ -344,8 +363,8 @@ MIRO_HD void bvh2_node_step(const float4* __restrict__ nodes, const float4* __re
     }
 }
 
-template <bool ANY>
-MIRO_HD void bvh2_leaf_step(const float4* __restrict__ tris, const mirogpu_ray& r, Bvh2Walk& w, const int32_t* __restrict__ stack,
+template <bool ANY, typename STK>
+MIRO_HD void bvh2_leaf_step(const float4* __restrict__ tris, const mirogpu_ray& r, Bvh2Walk& w, const STK& stack,
                             BestHit& best)
 {
     const uint32_t ref = (uint32_t)~w.node;
@@ -360,8 +379,8 @@ MIRO_HD void bvh2_leaf_step(const float4* __restrict__ tris, const mirogpu_ray& 
 
 // One triangle of the leaf per call; a leaf with more stays the lane's node (first + 1, count - 1), so the warp's next vote
 // decides again between node steps and another leaf phase and a leaf phase never loops over the longest leaf of the warp.
-template <bool ANY>
-MIRO_HD void bvh2_leaf_step_one(const float4* __restrict__ tris, const mirogpu_ray& r, Bvh2Walk& w, const int32_t* __restrict__ stack,
+template <bool ANY, typename STK>
+MIRO_HD void bvh2_leaf_step_one(const float4* __restrict__ tris, const mirogpu_ray& r, Bvh2Walk& w, const STK& stack,
                                 BestHit& best)
 {
     const uint32_t ref = (uint32_t)~w.node;
@@ -373,11 +392,39 @@ MIRO_HD void bvh2_leaf_step_one(const float4* __restrict__ tris, const mirogpu_r
     else bvh2_pop(w, stack);
 }
 
+// Up to two triangles of the leaf per call (PF bit 5): fewer leaf phases -- and votes -- per ray than one at a time, at the
+// price of lanes with a single triangle idling through the second test.
+template <bool ANY, typename STK>
+MIRO_HD void bvh2_leaf_step_two(const float4* __restrict__ tris, const mirogpu_ray& r, Bvh2Walk& w, const STK& stack, BestHit& best)
+{
+    const uint32_t ref = (uint32_t)~w.node;
+    const uint32_t first = ref >> 3, left = ref & 7u;   // left = count - 1
+    const F8 ta = ld256(tris + 4 * (size_t)first), tb = ld256(tris + 4 * (size_t)first + 2);
+    F8 tc, td;
+    if (left) { tc = ld256(tris + 4 * (size_t)first + 4); td = ld256(tris + 4 * (size_t)first + 6); }
+    bool acc = tri_test(ta.lo, ta.hi, tb.lo, tb.hi, r, best);
+    if (left && !(ANY && acc)) acc |= tri_test(tc.lo, tc.hi, td.lo, td.hi, r, best);
+    if (ANY && acc) { w.node = MIRO_BVH2_DONE; return; }
+    if (left >= 2u) w.node = (int32_t)~(ref + 14u);   // first + 2 (ref + 16), count - 2 (ref - 2)
+    else bvh2_pop(w, stack);
+}
+
+// One triangle of a postponed leaf reference (PF bit 6, see k_trace_hybrid); returns the reference of what is left of the leaf
+// (MIRO_BVH2_DONE = nothing).  hit: a triangle was accepted.
+MIRO_HD int32_t leaf_ref_test_one(const float4* __restrict__ tris, const mirogpu_ray& r, int32_t leaf, BestHit& best, bool& hit)
+{
+    const uint32_t ref = (uint32_t)~leaf;
+    const uint32_t first = ref >> 3;
+    const F8 ta = ld256(tris + 4 * (size_t)first), tb = ld256(tris + 4 * (size_t)first + 2);
+    hit = tri_test(ta.lo, ta.hi, tb.lo, tb.hi, r, best);
+    return (ref & 7u) ? (int32_t)~(ref + 7u) : MIRO_BVH2_DONE;
+}
+
 // Child order of the four-wide layouts: a three-comparator tournament on (entry distance, link) finds the nearest hit
 // child, which is descended next; the two first-round losers are pushed first and the runner-up of the final last, so
 // the nearer of the remaining children tends to be popped earlier.  Misses carry distance +inf and are never pushed.
-template <int PF>
-MIRO_HD void wide4_descend(const float d[4], const int32_t lk[4], const float4* __restrict__ tris, Bvh2Walk& w, int32_t* __restrict__ stack)
+template <int PF, typename STK>
+MIRO_HD void wide4_descend(const float d[4], const int32_t lk[4], const float4* __restrict__ tris, Bvh2Walk& w, STK& stack)
 {
     const float kFar = u2f(0x7f800000u);
     // comparators written as min / max on the distances and selects on the links (no register shuffling)
@@ -388,9 +435,9 @@ MIRO_HD void wide4_descend(const float d[4], const int32_t lk[4], const float4* 
     const float da = fminf(w01, w23), dc = fmaxf(w01, w23);
     const int32_t la = pf ? m23 : m01, lc = pf ? m01 : m23;
     if (!(da < kFar)) { bvh2_pop(w, stack); return; }
-    if (db < kFar) { stack[w.sp++] = w.tos; w.tos = lb; }
-    if (de < kFar) { stack[w.sp++] = w.tos; w.tos = le; }
-    if (dc < kFar) { stack[w.sp++] = w.tos; w.tos = lc; }
+    if (db < kFar) { stack.put(w.sp++, w.tos); w.tos = lb; }
+    if (de < kFar) { stack.put(w.sp++, w.tos); w.tos = le; }
+    if (dc < kFar) { stack.put(w.sp++, w.tos); w.tos = lc; }
     if ((PF & 4) && la < 0) {
         const float4* a = tris + 4 * (size_t)(((uint32_t)~la) >> 3);
         if (PF & 2) prefetch_l1(a); else prefetch_l2(a);
@@ -417,9 +464,9 @@ MIRO_HD void unpack_planes(uint32_t w, float f[4])
 // cache line.  Same walk state and leaf step as BVH2.  Child order: a three-comparator tournament finds the nearest
 // hit child (descended next); the two first-round losers are pushed first, the runner-up of the final last, so the
 // nearer of the remaining children tends to be popped earlier.  Misses carry distance +inf and are never pushed.
-template <int PF>
+template <int PF, typename STK>
 MIRO_HD void bvh4_node_step(const float4* __restrict__ nodes, const float4* __restrict__ tris, const mirogpu_ray& r, Bvh2Walk& w,
-                            int32_t* __restrict__ stack, const BestHit& best)
+                            STK& stack, const BestHit& best)
 {
     const float4* p = nodes + 8 * (size_t)w.node;
     const F8 X = ld256(p), Y = ld256(p + 2), Z = ld256(p + 4), L = ld256(p + 6);
@@ -447,7 +494,7 @@ MIRO_HD void trace_bvh4(const float4* __restrict__ nodes, const float4* __restri
                         TraceCounters* cnt)
 {
     Bvh2Walk w;
-    int32_t stack[MIRO_STACK4 + 1];
+    LocalStack<MIRO_STACK4 + 1> stack;
     bvh2_begin(r, w, best);
     for (;;) {
         while (w.node >= 0) {
@@ -468,12 +515,20 @@ MIRO_HD void trace_bvh4(const float4* __restrict__ nodes, const float4* __restri
 // one FMA per plane once the two per-axis constants are formed.  The near / far plane words are picked by the sign of
 // the direction (two selects per axis), so no per-plane min / max is needed.  The builder rounds q outward with a
 // margin of 0.02 cell, far above the rounding of this decode (a few ulp of the plane distance).
-template <int PF>
+// STAGE > 0 (device, hybrid kernel): nodes [0, STAGE) -- the top levels, numbered breadth-first by the flattener -- are read from
+// the CTA's copy in shared memory (`staged`, 4 float4 per node) instead of through L1.
+template <int PF, typename STK, int STAGE = 0>
 MIRO_HD void qbvh4_node_step(const float4* __restrict__ nodes, const float4* __restrict__ tris, const mirogpu_ray& r, Bvh2Walk& w,
-                             int32_t* __restrict__ stack, const BestHit& best)
+                             STK& stack, const BestHit& best, const float4* staged = nullptr)
 {
     const float4* p = nodes + 4 * (size_t)w.node;
-    const F8 A = ld256(p), B = ld256(p + 2);
+    F8 A, B;
+    if (STAGE > 0 && w.node < STAGE) {
+        const float4* q = staged + 4 * w.node;
+        A.lo = q[0]; A.hi = q[1]; B.lo = q[2]; B.hi = q[3];
+    } else {
+        A = ld256(p); B = ld256(p + 2);
+    }
     const uint32_t ew = f2u(A.lo.w);
     // cell * 2^24 (the planes arrive as q * 2^-24): the exponent bytes are at most 227, so + 24 stays a finite exponent
     const float cx = u2f(((ew & 0xffu) + 24u) << 23) * w.idx, cy = u2f((((ew >> 8) & 0xffu) + 24u) << 23) * w.idy,
@@ -502,7 +557,7 @@ MIRO_HD void trace_qbvh4(const float4* __restrict__ nodes, const float4* __restr
                          TraceCounters* cnt)
 {
     Bvh2Walk w;
-    int32_t stack[MIRO_STACK4 + 1];
+    LocalStack<MIRO_STACK4 + 1> stack;
     bvh2_begin(r, w, best);
     for (;;) {
         while (w.node >= 0) {

@@ -47,7 +47,7 @@ extern "C" int emu_trace(const float* tri_vertices, uint32_t ntris, int layout, 
         TraceCounters c = {0, 0, 0};
         if (steps4) {
             Bvh2Walk st;
-            int32_t stack[MIRO_STACK4 + 1];
+            LocalStack<MIRO_STACK4 + 1> stack;
             bvh2_begin(rays[i], st, best);
             while (st.node != MIRO_BVH2_DONE) {
                 if (st.node >= 0) { qbvh4_node_step<0>(nodes, tr, rays[i], st, stack, best); ++c.nodes; c.boxes += 4; }
@@ -62,7 +62,7 @@ extern "C" int emu_trace(const float* tri_vertices, uint32_t ntris, int layout, 
             if (any_hit) trace_bvh4<true, true>(nodes, tr, rays[i], best, &c); else trace_bvh4<false, true>(nodes, tr, rays[i], best, &c);
         } else if (walk) {
             Bvh2Walk st;
-            int32_t stack[MIRO_STACK + 1];
+            LocalStack<MIRO_STACK + 1> stack;
             bvh2_begin(rays[i], st, best);
             while (st.node != MIRO_BVH2_DONE) {
                 if (st.node >= 0) { bvh2_node_step<0>(nodes, tr, rays[i], st, stack, best); ++c.nodes; }

@@ -123,6 +123,45 @@ def test_diffuse_bounce_render(pkg, scenes, oracle):
     assert close.all(axis=1).mean() > 0.998, close.all(axis=1).mean()
 
 
+def test_fused_bounce_waves_equal_the_general_wavefront(pkg, scenes, oracle):
+    """MIROGPU_RENDER_DIFFUSE_BOUNCE without shadow rays runs as two fused waves (k_bounce_wave0 / k_bounce_wave1: implicit
+    pixel / weight, camera ray recomputed, plain stores into the per-sample planes).  Frames must equal the general
+    wavefront's bit for bit -- full frame, several sample batches, row shards -- and the reported ray count is primary +
+    LIVE bounce rays (dead slots of missed pixels are not rays)."""
+    import os
+    for name, (w, h) in (("teapot", (200, 150)), ("cornell", (96, 64))):
+        H, S = build_pair(pkg, scenes, oracle, name)
+        cam = H.camera()
+        for spp in (1, 3, 20):
+            p = S.render_params(w, h, mode=pkg.RENDER_DIFFUSE_BOUNCE, jitter=1, spp=spp, seed=7, shadows=0, bg=(0.1, 0.2, 0.3))
+            fused = S.render(cam, p)
+            rays_fused = S.last_call_stats()[0]
+            os.environ["MIROGPU_GENERAL_WAVEFRONT"] = "1"
+            try:
+                general = S.render(cam, p)
+                rays_general = S.last_call_stats()[0]
+            finally:
+                del os.environ["MIROGPU_GENERAL_WAVEFRONT"]
+            assert np.array_equal(bits(fused), bits(general))
+            assert rays_fused == rays_general
+            # primary + live bounce rays, counted independently: one bounce ray per camera ray that hit something (kd > 0 everywhere)
+            n = w * h * spp
+            d_rays = torch.empty((n, 8), dtype=torch.float32, device="cuda"); d_hits = torch.empty((n, 4), dtype=torch.float32, device="cuda")
+            S.generate_primary(cam, w, h, d_rays, jitter=1, seed=7, sample=0, samples=spp)
+            S.intersect_device(d_rays, d_hits)
+            torch.cuda.synchronize()
+            live = int((d_hits.view(torch.int32)[:, 1] != -1).sum().item())
+            assert rays_fused == n + live
+        p = S.render_params(w, h, mode=pkg.RENDER_DIFFUSE_BOUNCE, jitter=1, spp=3, seed=7, shadows=0, bg=(0.1, 0.2, 0.3))
+        full = S.render(cam, p)
+        acc = np.full((h, w, 3), np.nan, np.float32)
+        for r in range(3):
+            S.render(cam, S.render_params(w, h, mode=pkg.RENDER_DIFFUSE_BOUNCE, jitter=1, spp=3, seed=7, shadows=0, bg=(0.1, 0.2, 0.3), rows=(0, h, 3, r)), out=acc)
+        assert np.array_equal(bits(acc), bits(full))
+        u8 = S.render_rgb8(cam, p)
+        assert np.abs(u8.astype(int) - tonemap_u8(oracle, full).astype(int)).max() <= 1   # expf on the device vs libm
+
+
 def test_specular_and_refractive_materials(pkg, scenes, oracle):
     """Reflection / Fresnel / refraction recursion (Scene.cpp:302-336) and the refractive-occluder shadow rule
     (Phong.cpp:99-113): cornell box + a glass sphere + a mirror teapot."""
