@@ -157,7 +157,7 @@ __global__ void __launch_bounds__(128, MINB) k_trace_hybrid(DeviceScene s, const
     mirogpu_ray r;
     Bvh2Walk w;
     BestHit best;
-    int32_t pleaf = MIRO_BVH2_DONE;   // PF bit 6: the postponed leaf (none otherwise; the compiler drops it)
+    int32_t pleaf = MIRO_BVH2_DONE, pleaf2 = MIRO_BVH2_DONE;   // PF bits 6, 7: postponed leaves (none otherwise; the compiler drops them)
     SplitStack<SHORT, DEPTH, 128> stack;
     stack.sm = s_stack + threadIdx.x;
     r.ox = r.oy = r.oz = r.tmin = r.dx = r.dy = r.dz = r.tmax = 0.f;
@@ -208,9 +208,10 @@ __global__ void __launch_bounds__(128, MINB) k_trace_hybrid(DeviceScene s, const
             }
         }
         if (PF & 64) {
-            // Postponed leaves: a lane whose descent reaches a leaf parks it in `pleaf` and walks on (its best.t is stale until the
-            // parked leaf is tested, so it may enter a few nodes it would have culled); it only stops for a leaf phase when a second
-            // leaf turns up.  More lanes take part in every node step, and leaf phases start with more lanes holding a leaf.
+            // Postponed leaves: a lane whose descent reaches a leaf parks it in `pleaf` (PF bit 7: a second one in `pleaf2`) and walks
+            // on (its best.t is stale until the parked leaf is tested, so it may enter a few nodes it would have culled); it only
+            // stops for a leaf phase when one more leaf turns up than it can park.  More lanes take part in every node step, and
+            // leaf phases start with more lanes holding a leaf.
             for (int it = 0; it < period; ++it) {
                 const bool at_leaf = w.node < 0 && w.node != MIRO_BVH2_DONE;
                 const unsigned mn = __ballot_sync(0xffffffffu, w.node >= 0);
@@ -221,14 +222,18 @@ __global__ void __launch_bounds__(128, MINB) k_trace_hybrid(DeviceScene s, const
                     for (int rep = 0; rep < NREP; ++rep)
                         if (w.node >= 0) {
                             qbvh4_node_step<PF, decltype(stack), STAGE>(s.nodes, s.tris, r, w, stack, best, s_top);
-                            if (w.node < 0 && w.node != MIRO_BVH2_DONE && pleaf == MIRO_BVH2_DONE) { pleaf = w.node; bvh2_pop(w, stack); }
+                            if (w.node < 0 && w.node != MIRO_BVH2_DONE) {
+                                if (pleaf == MIRO_BVH2_DONE) { pleaf = w.node; bvh2_pop(w, stack); }
+                                else if ((PF & 128) && pleaf2 == MIRO_BVH2_DONE) { pleaf2 = w.node; bvh2_pop(w, stack); }
+                            }
                         }
                 } else {
                     if (pleaf == MIRO_BVH2_DONE && at_leaf) { pleaf = w.node; bvh2_pop(w, stack); }
                     if (pleaf != MIRO_BVH2_DONE) {
                         bool hit;
                         pleaf = leaf_ref_test_one(s.tris, r, pleaf, best, hit);
-                        if (ANY && hit) { pleaf = MIRO_BVH2_DONE; w.node = MIRO_BVH2_DONE; }
+                        if (ANY && hit) { pleaf = pleaf2 = MIRO_BVH2_DONE; w.node = MIRO_BVH2_DONE; }
+                        else if ((PF & 128) && pleaf == MIRO_BVH2_DONE) { pleaf = pleaf2; pleaf2 = MIRO_BVH2_DONE; }
                     }
                 }
                 if (w.node == MIRO_BVH2_DONE && pleaf == MIRO_BVH2_DONE && ((mn | ml) >> lane & 1u)) store_hit(hits, my, best);

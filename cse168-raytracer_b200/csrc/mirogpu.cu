@@ -109,7 +109,8 @@ struct mirogpu_scene {
     int hyb_nmin = 16, hyb_period = 4, hyb_min_idle = 8, hyb_pool = 64, hyb_nrep = 2;
     int packets_per_ticket = 1;                            // packet kernel: 32-ray packets per ticket; env MIROGPU_PPT
     size_t node_bytes_dev = 0, tri_bytes_dev = 0;
-    int hyb_pf = 0, hyb_minb = 9;                          // prefetch flags (traverse.cuh), min resident CTAs
+    int hyb_pf = 0, hyb_minb = 10;                         // step flags (traverse.cuh / k_trace_hybrid), min resident CTAs (10: 48 registers)
+    int hyb_pf_inc = 0, hyb_nmin_inc = 16;                 // the same two knobs for batches NOT flagged coherent
     int hyb_short = 0, hyb_stage = 0;                      // shared-memory stack entries per lane / staged top nodes (QBVH4); env MIROGPU_SHORT / _STAGE
     DeviceScene ds{};
     void* d_nodes = nullptr;
@@ -140,7 +141,7 @@ namespace {
 // *d_n * mult from device memory (wavefront queues whose size the host never sees).
 template <int LAYOUT, bool ANY, int PF, int MINB, int NREP, int SHORT = 0, int STAGE = 0>
 cudaError_t launch_hybrid_inst(mirogpu_scene* h, const mirogpu_ray* d_rays, size_t n, mirogpu_hit* d_hits, unsigned long long* ticket,
-                               cudaStream_t st, const uint32_t* d_n, uint32_t mult)
+                               cudaStream_t st, const uint32_t* d_n, uint32_t mult, int nmin)
 {
     static std::atomic<int> cached_occ{0};   // per instantiation; the answer depends only on the kernel and the device type
     int occ = cached_occ.load(std::memory_order_relaxed);
@@ -153,32 +154,35 @@ cudaError_t launch_hybrid_inst(mirogpu_scene* h, const mirogpu_ray* d_rays, size
     size_t grid = (size_t)h->sm_count * occ;
     const size_t need = (n + 127) / 128;
     if (grid > need) grid = need;
-    k_trace_hybrid<LAYOUT, ANY, PF, MINB, NREP, SHORT, STAGE><<<(unsigned)grid, 128, 0, st>>>(h->ds, d_rays, n, d_hits, ticket, h->hyb_nmin, h->hyb_period,
+    k_trace_hybrid<LAYOUT, ANY, PF, MINB, NREP, SHORT, STAGE><<<(unsigned)grid, 128, 0, st>>>(h->ds, d_rays, n, d_hits, ticket, nmin, h->hyb_period,
                                                                             h->hyb_min_idle, (uint32_t)h->hyb_pool, d_n, mult, h->info.num_nodes);
     return cudaGetLastError();
 }
 
 template <int LAYOUT, bool ANY>
 cudaError_t launch_hybrid(mirogpu_scene* h, const mirogpu_ray* d_rays, size_t n, mirogpu_hit* d_hits, unsigned long long* ticket,
-                          cudaStream_t st, const uint32_t* d_n, uint32_t mult)
+                          cudaStream_t st, const uint32_t* d_n, uint32_t mult, bool coherent)
 {
-#define MIRO_HYB(PF, MINB, NREP) if (h->hyb_pf == PF && h->hyb_minb == MINB && h->hyb_nrep == NREP && h->hyb_short == 0 && h->hyb_stage == 0) return launch_hybrid_inst<LAYOUT, ANY, PF, MINB, NREP>(h, d_rays, n, d_hits, ticket, st, d_n, mult);
-    MIRO_HYB(0, 9, 2) MIRO_HYB(0, 8, 2) MIRO_HYB(0, 9, 1) MIRO_HYB(0, 9, 3) MIRO_HYB(16, 9, 2) MIRO_HYB(16, 9, 3)
+    // per-kind knobs: batches flagged coherent (camera rays in pixel order) walk without postponed leaves
+    const int pf = coherent ? h->hyb_pf : h->hyb_pf_inc, nrep = h->hyb_nrep, minb = h->hyb_minb, sh = h->hyb_short, stg = h->hyb_stage;
+    const int nmin = coherent ? h->hyb_nmin : h->hyb_nmin_inc;
+#define MIRO_HYB(PF, MINB, NREP) if (pf == PF && minb == MINB && nrep == NREP && sh == 0 && stg == 0) return launch_hybrid_inst<LAYOUT, ANY, PF, MINB, NREP>(h, d_rays, n, d_hits, ticket, st, d_n, mult, nmin);
+    MIRO_HYB(0, 9, 2) MIRO_HYB(0, 8, 2) MIRO_HYB(0, 9, 1) MIRO_HYB(0, 9, 3) MIRO_HYB(0, 10, 2) MIRO_HYB(16, 9, 2) MIRO_HYB(16, 9, 3) MIRO_HYB(16, 10, 3)
 #undef MIRO_HYB
     if (LAYOUT == MIROGPU_LAYOUT_QBVH4) {
-        // shared-memory short stack / staged top levels (north star; measured in profiles/r02_*): selectable combinations
-#define MIRO_HYB2(MINB, SHORT, STAGE) if (h->hyb_pf == 16 && h->hyb_nrep == 3 && h->hyb_minb == MINB && h->hyb_short == SHORT && h->hyb_stage == STAGE) return launch_hybrid_inst<MIROGPU_LAYOUT_QBVH4, ANY, 16, MINB, 3, SHORT, STAGE>(h, d_rays, n, d_hits, ticket, st, d_n, mult);
-        MIRO_HYB2(9, 4, 0) MIRO_HYB2(9, 8, 0) MIRO_HYB2(9, 12, 0) MIRO_HYB2(9, 16, 0) MIRO_HYB2(10, 8, 0) MIRO_HYB2(10, 12, 0) MIRO_HYB2(10, 16, 0)
-        MIRO_HYB2(9, 0, 21) MIRO_HYB2(9, 0, 85) MIRO_HYB2(9, 8, 21) MIRO_HYB2(9, 8, 85) MIRO_HYB2(9, 16, 85) MIRO_HYB2(10, 0, 0) MIRO_HYB2(12, 8, 0) MIRO_HYB2(12, 16, 0)
+        // shared-memory short stack / staged top levels (north star; measured and rejected): kept selectable
+#define MIRO_HYB2(MINB, SHORT, STAGE) if (pf == 16 && nrep == 3 && minb == MINB && sh == SHORT && stg == STAGE) return launch_hybrid_inst<MIROGPU_LAYOUT_QBVH4, ANY, 16, MINB, 3, SHORT, STAGE>(h, d_rays, n, d_hits, ticket, st, d_n, mult, nmin);
+        MIRO_HYB2(9, 8, 0) MIRO_HYB2(9, 16, 0) MIRO_HYB2(10, 8, 0) MIRO_HYB2(10, 16, 0) MIRO_HYB2(9, 0, 21) MIRO_HYB2(9, 0, 85) MIRO_HYB2(9, 8, 85) MIRO_HYB2(10, 0, 85)
 #undef MIRO_HYB2
-        // leaf-phase variants: two triangles per phase (PF 48), one postponed leaf per lane (PF 80)
-#define MIRO_HYB3(PF, MINB, NREP, SHORT) if (h->hyb_pf == PF && h->hyb_minb == MINB && h->hyb_nrep == NREP && h->hyb_short == SHORT && h->hyb_stage == 0) return launch_hybrid_inst<MIROGPU_LAYOUT_QBVH4, ANY, PF, MINB, NREP, SHORT, 0>(h, d_rays, n, d_hits, ticket, st, d_n, mult);
-        MIRO_HYB3(48, 9, 3, 0) MIRO_HYB3(48, 9, 3, 8) MIRO_HYB3(80, 9, 3, 0) MIRO_HYB3(80, 9, 3, 8) MIRO_HYB3(80, 9, 2, 0) MIRO_HYB3(80, 9, 2, 8) MIRO_HYB3(80, 10, 3, 8)
+        // leaf-phase variants: two triangles per phase (PF 48), one postponed leaf per lane (PF 80, the default for incoherent batches), two (PF 208)
+#define MIRO_HYB3(PF, MINB, NREP, SHORT) if (pf == PF && minb == MINB && nrep == NREP && sh == SHORT && stg == 0) return launch_hybrid_inst<MIROGPU_LAYOUT_QBVH4, ANY, PF, MINB, NREP, SHORT, 0>(h, d_rays, n, d_hits, ticket, st, d_n, mult, nmin);
+        MIRO_HYB3(48, 9, 3, 0) MIRO_HYB3(80, 9, 3, 0) MIRO_HYB3(80, 10, 3, 8) MIRO_HYB3(80, 10, 3, 0) MIRO_HYB3(80, 10, 2, 0) MIRO_HYB3(208, 10, 3, 0) MIRO_HYB3(208, 9, 3, 0) MIRO_HYB3(208, 10, 2, 0)
 #undef MIRO_HYB3
         if (getenv("MIROGPU_STRICT")) return cudaErrorInvalidValue;   // measurement runs: an uninstantiated knob combination must not silently time the default
-        return launch_hybrid_inst<LAYOUT, ANY, 16, 9, 3>(h, d_rays, n, d_hits, ticket, st, d_n, mult);
+        return coherent ? launch_hybrid_inst<LAYOUT, ANY, 16, 10, 3>(h, d_rays, n, d_hits, ticket, st, d_n, mult)
+                        : launch_hybrid_inst<MIROGPU_LAYOUT_QBVH4, ANY, 80, 10, 3, 0, 0>(h, d_rays, n, d_hits, ticket, st, d_n, mult, nmin);
     }
-    return launch_hybrid_inst<LAYOUT, ANY, 0, 9, 2>(h, d_rays, n, d_hits, ticket, st, d_n, mult);
+    return launch_hybrid_inst<LAYOUT, ANY, 0, 10, 2>(h, d_rays, n, d_hits, ticket, st, d_n, mult, nmin);
 }
 
 template <int LAYOUT, bool ANY>
@@ -197,7 +201,7 @@ cudaError_t launch_trace(mirogpu_scene* h, const mirogpu_ray* d_rays, size_t n, 
     // automatic choice: the hybrid-scheduled kernel, except coherent batches on BVH2, where 32-ray packets walking in
     // lockstep are cheaper (QBVH4: hybrid 10.8 vs packets 9.2 Grays/s on camera rays; BVH2: 10.5 vs 11.5)
     if (LAYOUT != MIROGPU_LAYOUT_CWBVH8 && (h->variant == 2 || (h->variant < 0 && !(coherent && LAYOUT == MIROGPU_LAYOUT_BVH2))) && n < 0xFF000000ull)
-        return launch_hybrid<LAYOUT == MIROGPU_LAYOUT_CWBVH8 ? MIROGPU_LAYOUT_BVH2 : LAYOUT, ANY>(h, d_rays, n, d_hits, ticket, st, d_n, mult);
+        return launch_hybrid<LAYOUT == MIROGPU_LAYOUT_CWBVH8 ? MIROGPU_LAYOUT_BVH2 : LAYOUT, ANY>(h, d_rays, n, d_hits, ticket, st, d_n, mult, coherent);
     static std::atomic<int> cached_occ{0};
     int occ = cached_occ.load(std::memory_order_relaxed);
     if (occ == 0) {
@@ -369,13 +373,17 @@ int mirogpu_scene_create(const float* tri_vertices, const float* tri_normals, co
     }
     if (o.layout == MIROGPU_LAYOUT_QBVH4 || o.layout == MIROGPU_LAYOUT_BVH4) { h->hyb_period = 2; h->hyb_min_idle = 6; }   // measured optimum of the four-wide steps
     // QBVH4: one triangle per leaf phase, three node steps per vote, node steps while >= 20 lanes want one (7.28 -> 7.53 Grays/s)
-    if (o.layout == MIROGPU_LAYOUT_QBVH4) { h->hyb_pf = 16; h->hyb_nrep = 3; h->hyb_nmin = 20; }
+    // incoherent batches: one postponed leaf per lane, node steps while >= 24 lanes want one (bounce rays 7.17 -> 8.02 Grays/s with 48 registers)
+    if (o.layout == MIROGPU_LAYOUT_QBVH4) { h->hyb_pf = 16; h->hyb_nrep = 3; h->hyb_nmin = 20; h->hyb_pf_inc = 80; h->hyb_nmin_inc = 24; }
+    else h->hyb_nmin_inc = h->hyb_nmin;
     if (const char* e = getenv("MIROGPU_POOL")) { const int v = atoi(e); if (v >= 32 && v <= 65536) h->hyb_pool = v; }
     if (const char* e = getenv("MIROGPU_NREP")) h->hyb_nrep = atoi(e);
     if (const char* e = getenv("MIROGPU_PPT")) { const int v = atoi(e); if (v >= 1 && v <= 64) h->packets_per_ticket = v; }
-    if (const char* e = getenv("MIROGPU_NMIN")) { const int v = atoi(e); if (v >= 1 && v <= 32) h->hyb_nmin = v; }
+    if (const char* e = getenv("MIROGPU_NMIN")) { const int v = atoi(e); if (v >= 1 && v <= 32) h->hyb_nmin = h->hyb_nmin_inc = v; }
+    if (const char* e = getenv("MIROGPU_NMIN_INC")) { const int v = atoi(e); if (v >= 1 && v <= 32) h->hyb_nmin_inc = v; }
     if (const char* e = getenv("MIROGPU_PERIOD")) { const int v = atoi(e); if (v >= 1 && v <= 100000) h->hyb_period = v; }
-    if (const char* e = getenv("MIROGPU_PF")) h->hyb_pf = atoi(e);
+    if (const char* e = getenv("MIROGPU_PF")) h->hyb_pf = h->hyb_pf_inc = atoi(e);
+    if (const char* e = getenv("MIROGPU_PF_INC")) h->hyb_pf_inc = atoi(e);
     if (const char* e = getenv("MIROGPU_MINB")) h->hyb_minb = atoi(e);
     if (const char* e = getenv("MIROGPU_SHORT")) h->hyb_short = atoi(e);
     if (const char* e = getenv("MIROGPU_STAGE")) h->hyb_stage = atoi(e);

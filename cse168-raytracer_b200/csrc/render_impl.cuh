@@ -108,40 +108,55 @@ __device__ __forceinline__ bool push_item(const WaveParams& p, Queue& next, uint
     return true;
 }
 
-// One light of Phong::shade's loop up to the shadow query (Phong.cpp:61-158): unit vector to the light, its distance, the
-// diffuse term (light colour x kd^2: Phong::diffuse2D returns m_diffuse, so kd enters squared, Phong.cpp:146, Phong.h:20) and
-// the highlight (exponent fixed at 500, Phong.cpp:152).  false: the point lies outside a DirectionalAreaLight's beam.
+// pow(float, int) as the reference's gnu++98 build evaluates it (Phong.cpp:152 -> __builtin_powif -> libgcc __powisf2): binary
+// exponentiation in binary32, every product rounded.  m >= 0.
+__device__ __forceinline__ float powi_ref(float x, int m)
+{
+    unsigned n = (unsigned)m;
+    float y = (n & 1u) ? x : 1.0f;
+    while (n >>= 1) {
+        x = xmul(x, x);
+        if (n & 1u) y = xmul(y, x);
+    }
+    return y;
+}
+
+// One light of Phong::shade's loop up to the shadow query (Phong.cpp:61-158), in the reference's operand order with separately
+// rounded operations (no FMA contraction: every kernel that inlines this produces the same bits, and they are the bits of the
+// reference's x86 build): unit vector to the light, its distance, the diffuse term colour * ((max(0, N.l * falloff * W) * kd) * kd)
+// (Phong::diffuse2D returns m_diffuse, so kd enters twice, Phong.cpp:146, Phong.h:20) and the highlight (exponent fixed at 500,
+// Phong.cpp:152).  false: the point lies outside a DirectionalAreaLight's beam.
 __device__ __forceinline__ bool light_terms(const mirogpu_light L, const SurfacePoint& sp, const mirogpu_material& m, const float rd[3],
                                             float l[3], float& dist, float cd[3], float& hl)
 {
     if (L.kind == 1) { l[0] = -L.normal[0]; l[1] = -L.normal[1]; l[2] = -L.normal[2]; }
-    else { l[0] = L.position[0] - sp.P[0]; l[1] = L.position[1] - sp.P[1]; l[2] = L.position[2] - sp.P[2]; }
-    float falloff = dot3(l, l);
-    dist = sqrtf(falloff);
-    const float invd = 1.0f / dist;
-    l[0] *= invd; l[1] *= invd; l[2] *= invd;
+    else { l[0] = xsub(L.position[0], sp.P[0]); l[1] = xsub(L.position[1], sp.P[1]); l[2] = xsub(L.position[2], sp.P[2]); }
+    float falloff = xdot(l[0], l[1], l[2], l[0], l[1], l[2]);
+    dist = xsqrt(falloff);
+    const float invd = xdiv(1.0f, dist);
+    l[0] = xmul(l[0], invd); l[1] = xmul(l[1], invd); l[2] = xmul(l[2], invd);
     float nDotL;
     if (L.kind == 1) {
-        const float nl[3] = {-L.normal[0], -L.normal[1], -L.normal[2]};
-        nDotL = dot3(sp.N, nl);
-        const float lp[3] = {L.position[0] - sp.P[0], L.position[1] - sp.P[1], L.position[2] - sp.P[2]};
-        const float t = dot3(L.normal, lp) / -1.0f;
-        const float q[3] = {sp.P[0] - t * L.normal[0] - L.position[0], sp.P[1] - t * L.normal[1] - L.position[1], sp.P[2] - t * L.normal[2] - L.position[2]};
-        if (dot3(q, q) > L.radius * L.radius) return false;
-        falloff = 1.0f / MIRO_PI;
+        nDotL = xdot(sp.N[0], sp.N[1], sp.N[2], -L.normal[0], -L.normal[1], -L.normal[2]);
+        const float t = xdiv(xdot(L.normal[0], L.normal[1], L.normal[2], xsub(L.position[0], sp.P[0]), xsub(L.position[1], sp.P[1]), xsub(L.position[2], sp.P[2])), -1.0f);
+        const float q0 = xsub(xsub(sp.P[0], xmul(L.normal[0], t)), L.position[0]), q1 = xsub(xsub(sp.P[1], xmul(L.normal[1], t)), L.position[1]),
+                    q2 = xsub(xsub(sp.P[2], xmul(L.normal[2], t)), L.position[2]);
+        if (xdot(q0, q1, q2, q0, q1, q2) > xmul(L.radius, L.radius)) return false;
+        falloff = xdiv(1.0f, MIRO_PI);
     } else {
-        nDotL = dot3(sp.N, l);
-        falloff = 1.0f / (falloff * 4.0f * MIRO_PI * MIRO_PI);
+        nDotL = xdot(sp.N[0], sp.N[1], sp.N[2], l[0], l[1], l[2]);
+        falloff = xdiv(1.0f, xmul(xmul(xmul(falloff, 4.0f), MIRO_PI), MIRO_PI));
     }
-    const float dterm = fmaxf(0.0f, nDotL * falloff * L.wattage);
-    cd[0] = L.color[0] * dterm * m.kd[0] * m.kd[0]; cd[1] = L.color[1] * dterm * m.kd[1] * m.kd[1]; cd[2] = L.color[2] * dterm * m.kd[2] * m.kd[2];
+    const float dterm = fmaxf(0.0f, xmul(xmul(nDotL, falloff), L.wattage));
+    cd[0] = xmul(L.color[0], xmul(xmul(m.kd[0], dterm), m.kd[0]));
+    cd[1] = xmul(L.color[1], xmul(xmul(m.kd[1], dterm), m.kd[1]));
+    cd[2] = xmul(L.color[2], xmul(xmul(m.kd[2], dterm), m.kd[2]));
     hl = 0.f;
     if (m.shininess < INFINITY) {
-        const float ldn = 2.0f * dot3(l, sp.N);
-        const float r[3] = {-l[0] + ldn * sp.N[0], -l[1] + ldn * sp.N[1], -l[2] + ldn * sp.N[2]};
-        const float e[3] = {-rd[0], -rd[1], -rd[2]};
-        const float c = fmaxf(0.0f, fminf(1.f, dot3(e, r)));
-        hl = fmaxf(0.0f, powf(c, 500.0f) * falloff * L.wattage);
+        const float ldn = xmul(2.0f, xdot(l[0], l[1], l[2], sp.N[0], sp.N[1], sp.N[2]));
+        const float r0 = xadd(-l[0], xmul(sp.N[0], ldn)), r1 = xadd(-l[1], xmul(sp.N[1], ldn)), r2 = xadd(-l[2], xmul(sp.N[2], ldn));
+        const float c = fmaxf(0.0f, fminf(1.f, xdot(-rd[0], -rd[1], -rd[2], r0, r1, r2)));
+        hl = fmaxf(0.0f, xmul(xmul(powi_ref(c, 500), falloff), L.wattage));
     }
     return true;
 }
@@ -162,9 +177,9 @@ __device__ __forceinline__ bool shade_item(const WaveParams& p, const Queue& cur
     if (__float_as_uint(hv.y) == MIROGPU_MISS) {
         if (ray.tmax < ray.tmin) return false;   // dead item
         // Scene.cpp:338-342: environment / background colour
-        atomicAdd(accum + 3 * (size_t)pixel + 0, w.x * p.bg[0]);
-        atomicAdd(accum + 3 * (size_t)pixel + 1, w.y * p.bg[1]);
-        atomicAdd(accum + 3 * (size_t)pixel + 2, w.z * p.bg[2]);
+        atomicAdd(accum + 3 * (size_t)pixel + 0, xmul(w.x, p.bg[0]));
+        atomicAdd(accum + 3 * (size_t)pixel + 1, xmul(w.y, p.bg[1]));
+        atomicAdd(accum + 3 * (size_t)pixel + 2, xmul(w.z, p.bg[2]));
         return false;
     }
     mirogpu_hit h; h.t = hv.x; h.prim_id = __float_as_uint(hv.y); h.beta = hv.z; h.gamma = hv.w;
@@ -181,19 +196,19 @@ __device__ __forceinline__ bool shade_item(const WaveParams& p, const Queue& cur
             if (cd[0] > 0.f || cd[1] > 0.f || cd[2] > 0.f || hl > 0.f) {
                 const size_t s = (size_t)i * p.nlights + li;
                 float4* r = reinterpret_cast<float4*>(shadow_rays + s);
-                r[0] = make_float4(sp.P[0] + l[0] * MIRO_EPS, sp.P[1] + l[1] * MIRO_EPS, sp.P[2] + l[2] * MIRO_EPS, 0.0f);
+                r[0] = make_float4(xadd(sp.P[0], xmul(l[0], MIRO_EPS)), xadd(sp.P[1], xmul(l[1], MIRO_EPS)), xadd(sp.P[2], xmul(l[2], MIRO_EPS)), 0.0f);
                 r[1] = make_float4(l[0], l[1], l[2], dist);
                 shadow_cd[s] = make_float4(w.x * cd[0], w.y * cd[1], w.z * cd[2], __uint_as_float(pixel));
                 shadow_ch[s] = make_float4(w.x * hl, w.y * hl, w.z * hl, 0.f);
             }
         } else {
-            direct[0] += cd[0] + hl; direct[1] += cd[1] + hl; direct[2] += cd[2] + hl;
+            direct[0] = xadd(xadd(direct[0], cd[0]), hl); direct[1] = xadd(xadd(direct[1], cd[1]), hl); direct[2] = xadd(xadd(direct[2], cd[2]), hl);   // L = L + diffuse; L = L + highlights (Phong.cpp:146-156)
         }
     }
     if (!p.shadows && (direct[0] != 0.f || direct[1] != 0.f || direct[2] != 0.f)) {
-        atomicAdd(accum + 3 * (size_t)pixel + 0, w.x * direct[0]);
-        atomicAdd(accum + 3 * (size_t)pixel + 1, w.y * direct[1]);
-        atomicAdd(accum + 3 * (size_t)pixel + 2, w.z * direct[2]);
+        atomicAdd(accum + 3 * (size_t)pixel + 0, xmul(w.x, direct[0]));
+        atomicAdd(accum + 3 * (size_t)pixel + 1, xmul(w.y, direct[1]));
+        atomicAdd(accum + 3 * (size_t)pixel + 2, xmul(w.z, direct[2]));
     }
     const bool diffuse = m.kd[0] > 0.f || m.kd[1] > 0.f || m.kd[2] > 0.f;
     // photon-map irradiance at diffuse hits (Scene.cpp:286-299): queued for the gather kernel
@@ -214,8 +229,8 @@ __device__ __forceinline__ bool shade_item(const WaveParams& p, const Queue& cur
             uniform2(p.seed, frame_pixel, p.sample_base + sb, RNG_DIM_BOUNCE, u1, u2);
             float d[3];
             align_hemisphere(sp.N, xmul(xmul(2.0f, MIRO_PI), u2), asinf(sqrtf(u1)), d);
-            const float o[3] = {sp.P[0] + d[0] * MIRO_EPS, sp.P[1] + d[1] * MIRO_EPS, sp.P[2] + d[2] * MIRO_EPS};
-            return push_item(p, next, next_count, dropped, o, d, lpix, w.x * m.kd[0], w.y * m.kd[1], w.z * m.kd[2], pack_ds(0, sb), (int64_t)i);
+            const float o[3] = {xadd(sp.P[0], xmul(d[0], MIRO_EPS)), xadd(sp.P[1], xmul(d[1], MIRO_EPS)), xadd(sp.P[2], xmul(d[2], MIRO_EPS))};
+            return push_item(p, next, next_count, dropped, o, d, lpix, xmul(w.x, m.kd[0]), xmul(w.y, m.kd[1]), xmul(w.z, m.kd[2]), pack_ds(0, sb), (int64_t)i);
         }
         return false;
     }
@@ -536,7 +551,7 @@ __global__ void __launch_bounds__(MIRO_BW_THREADS) k_bounce_wave0(WaveParams p, 
                 for (uint32_t li = 0; li < p.nlights; ++li) {
                     float l[3], cd[3], dist, hl;
                     if (!light_terms(p.lights[li], sp, m, rd, l, dist, cd, hl)) continue;
-                    direct[0] += cd[0] + hl; direct[1] += cd[1] + hl; direct[2] += cd[2] + hl;
+                    direct[0] = xadd(xadd(direct[0], cd[0]), hl); direct[1] = xadd(xadd(direct[1], cd[1]), hl); direct[2] = xadd(xadd(direct[2], cd[2]), hl);   // L = L + diffuse; L = L + highlights (Phong.cpp:146-156)
                 }
                 out[0] = 1.f * direct[0]; out[1] = 1.f * direct[1]; out[2] = 1.f * direct[2];
                 if (m.kd[0] > 0.f || m.kd[1] > 0.f || m.kd[2] > 0.f) {   // Ray::diffuse from the first hit (Ray.h:109-122)
@@ -544,7 +559,7 @@ __global__ void __launch_bounds__(MIRO_BW_THREADS) k_bounce_wave0(WaveParams p, 
                     uniform2(p.seed, frame_pixel, p.sample_base + sb, RNG_DIM_BOUNCE, u1, u2);
                     float d[3];
                     align_hemisphere(sp.N, xmul(xmul(2.0f, MIRO_PI), u2), asinf(sqrtf(u1)), d);
-                    r0 = make_float4(sp.P[0] + d[0] * MIRO_EPS, sp.P[1] + d[1] * MIRO_EPS, sp.P[2] + d[2] * MIRO_EPS, 0.0f);
+                    r0 = make_float4(xadd(sp.P[0], xmul(d[0], MIRO_EPS)), xadd(sp.P[1], xmul(d[1], MIRO_EPS)), xadd(sp.P[2], xmul(d[2], MIRO_EPS)), 0.0f);
                     r1 = make_float4(d[0], d[1], d[2], MIROGPU_TMAX);
                     mat = sp.material;
                     child = true;
@@ -589,7 +604,7 @@ __global__ void __launch_bounds__(MIRO_BW_THREADS) k_bounce_wave1(WaveParams p, 
         const float w[3] = {1.f * pmat.kd[0], 1.f * pmat.kd[1], 1.f * pmat.kd[2]};
         float add[3];
         if (__float_as_uint(hv[k].y) == MIROGPU_MISS) {
-            add[0] = w[0] * p.bg[0]; add[1] = w[1] * p.bg[1]; add[2] = w[2] * p.bg[2];
+            add[0] = __fmul_rn(w[0], p.bg[0]); add[1] = __fmul_rn(w[1], p.bg[1]); add[2] = __fmul_rn(w[2], p.bg[2]);
         } else {
             const float4 dv = __ldcs(reinterpret_cast<const float4*>(rays + i) + 1);
             const float rd[3] = {dv.x, dv.y, dv.z};
@@ -600,13 +615,14 @@ __global__ void __launch_bounds__(MIRO_BW_THREADS) k_bounce_wave1(WaveParams p, 
             for (uint32_t li = 0; li < p.nlights; ++li) {
                 float l[3], cd[3], dist, hl;
                 if (!light_terms(p.lights[li], sp, m, rd, l, dist, cd, hl)) continue;
-                direct[0] += cd[0] + hl; direct[1] += cd[1] + hl; direct[2] += cd[2] + hl;
+                direct[0] = xadd(xadd(direct[0], cd[0]), hl); direct[1] = xadd(xadd(direct[1], cd[1]), hl); direct[2] = xadd(xadd(direct[2], cd[2]), hl);   // L = L + diffuse; L = L + highlights (Phong.cpp:146-156)
             }
             if (direct[0] == 0.f && direct[1] == 0.f && direct[2] == 0.f) continue;
-            add[0] = w[0] * direct[0]; add[1] = w[1] * direct[1]; add[2] = w[2] * direct[2];
+            add[0] = __fmul_rn(w[0], direct[0]); add[1] = __fmul_rn(w[1], direct[1]); add[2] = __fmul_rn(w[2], direct[2]);
         }
+        // separately rounded product and sum, like the general path's atomicAdd(plane, w * direct) -- no FMA contraction
         float* o = planes + 3 * (size_t)i;
-        o[0] += add[0]; o[1] += add[1]; o[2] += add[2];
+        o[0] = __fadd_rn(o[0], __fmul_rn(add[0], 1.0f)); o[1] = __fadd_rn(o[1], __fmul_rn(add[1], 1.0f)); o[2] = __fadd_rn(o[2], __fmul_rn(add[2], 1.0f));
     }
 }
 

@@ -310,8 +310,9 @@ template <int SHORT, int N, int THREADS>
 struct SplitStack {
     int32_t* sm;   // this thread's column of the CTA's [SHORT][THREADS] array
     int32_t a[N > SHORT ? N - SHORT : 1];
-    MIRO_HD void put(int i, int32_t v) { if (i < SHORT) sm[i * THREADS] = v; else a[i - SHORT] = v; }
-    MIRO_HD int32_t get(int i) const { return i < SHORT ? sm[i * THREADS] : a[i - SHORT]; }
+    // (SHORT > 0 &&: the index is a signed int the compiler cannot prove non-negative, so `i < 0` alone would keep the shared path alive)
+    MIRO_HD void put(int i, int32_t v) { if (SHORT > 0 && i < SHORT) sm[i * THREADS] = v; else a[i - SHORT] = v; }
+    MIRO_HD int32_t get(int i) const { return (SHORT > 0 && i < SHORT) ? sm[i * THREADS] : a[i - SHORT]; }
 };
 
 template <typename STK>
