@@ -179,7 +179,7 @@ cudaError_t launch_hybrid(mirogpu_scene* h, const mirogpu_ray* d_rays, size_t n,
         MIRO_HYB3(48, 9, 3, 0) MIRO_HYB3(80, 9, 3, 0) MIRO_HYB3(80, 10, 3, 8) MIRO_HYB3(80, 10, 3, 0) MIRO_HYB3(80, 10, 2, 0) MIRO_HYB3(208, 10, 3, 0) MIRO_HYB3(208, 9, 3, 0) MIRO_HYB3(208, 10, 2, 0)
 #undef MIRO_HYB3
         if (getenv("MIROGPU_STRICT")) return cudaErrorInvalidValue;   // measurement runs: an uninstantiated knob combination must not silently time the default
-        return coherent ? launch_hybrid_inst<LAYOUT, ANY, 16, 10, 3>(h, d_rays, n, d_hits, ticket, st, d_n, mult)
+        return coherent ? launch_hybrid_inst<LAYOUT, ANY, 16, 10, 3>(h, d_rays, n, d_hits, ticket, st, d_n, mult, nmin)
                         : launch_hybrid_inst<MIROGPU_LAYOUT_QBVH4, ANY, 80, 10, 3, 0, 0>(h, d_rays, n, d_hits, ticket, st, d_n, mult, nmin);
     }
     return launch_hybrid_inst<LAYOUT, ANY, 0, 10, 2>(h, d_rays, n, d_hits, ticket, st, d_n, mult, nmin);
