@@ -9,7 +9,7 @@ python bench.py > gpurun_out/bench_full.json 2> gpurun_out/bench_full.err; echo 
 python bench.py --impl reference --steps 3 --warmup 1 > gpurun_out/bench_reference.json 2> gpurun_out/bench_reference.err; echo "bench reference rc=$?"; tail -c 1200 gpurun_out/bench_reference.json
 for v in 0 1 2; do python bench.py --variant $v --no-cpu --steps 10 > gpurun_out/bench_v$v.json 2> gpurun_out/bench_v$v.err; echo "bench variant $v rc=$?"; done
 python bench.py --layout cwbvh8 --no-cpu --steps 10 > gpurun_out/bench_cwbvh8.json 2> gpurun_out/bench_cwbvh8.err; echo "bench cwbvh8 rc=$?"
-BENCH="python bench.py --steps 2 --warmup 3 --no-cpu"
+BENCH="python bench.py --steps 2 --warmup 3 --no-cpu --no-extras"
 $BENCH > gpurun_out/plain.log 2>&1 &&
 ncu --metrics gpu__time_duration.sum --clock-control none -c 80 --csv --log-file gpurun_out/launches.csv $BENCH > gpurun_out/ncu_launches.log 2>&1
 echo "ncu launches rc=$?"
