@@ -500,18 +500,21 @@ __global__ void __launch_bounds__(256) k_frame_max(const float* __restrict__ rgb
 // as the general path's atomics, hence bit-identical frames.  The bounce ray overwrites the camera ray in place.
 // Per item: wave 0 moves 16 (hit) + 96 (shading record) + 32 (bounce ray) + 4 + 12 bytes, wave 1 16 + 16 + 96 + 4 + 24.
 #define MIRO_BW_THREADS 128
-template <int ITEMS>
+// READ_DIR: take the camera ray's direction from the ray buffer (16 bytes per item) instead of recomputing it (~150 instructions)
+template <int ITEMS, bool READ_DIR>
 __global__ void __launch_bounds__(MIRO_BW_THREADS) k_bounce_wave0(WaveParams p, CameraBasis cb, int height, int nrows_local, int jitter, uint32_t nitems,
                                                                   const mirogpu_hit* __restrict__ hits, mirogpu_ray* __restrict__ rays,
                                                                   uint32_t* __restrict__ parent_mat, float* __restrict__ planes, uint32_t* live_slots)
 {
     const uint32_t base = blockIdx.x * (MIRO_BW_THREADS * ITEMS) + threadIdx.x;
     float4 hv[ITEMS];
+    float4 dv[ITEMS];
     ShadeRecord rec[ITEMS];
 #pragma unroll
     for (int k = 0; k < ITEMS; ++k) {
         const uint32_t i = base + k * MIRO_BW_THREADS;
         hv[k] = i < nitems ? __ldcs(reinterpret_cast<const float4*>(hits + i)) : make_float4(0.f, __uint_as_float(MIROGPU_MISS), 0.f, 0.f);
+        if (READ_DIR) dv[k] = i < nitems ? __ldcs(reinterpret_cast<const float4*>(rays + i) + 1) : make_float4(0.f, 0.f, 1.f, 0.f);
     }
 #pragma unroll
     for (int k = 0; k < ITEMS; ++k) {
@@ -534,16 +537,19 @@ __global__ void __launch_bounds__(MIRO_BW_THREADS) k_bounce_wave0(WaveParams p, 
                 // the camera ray of this item, as k_gen_primary made it (bit-exact: same operations)
                 const uint32_t row = lpix / (uint32_t)p.width;
                 const int x = (int)(lpix - row * (uint32_t)p.width), y = p.first_row + (int)row * p.row_stride;
-                float dx = 0.5f, dy = 0.5f;
                 const uint32_t frame_pixel = (uint32_t)y * (uint32_t)p.width + (uint32_t)x;
-                if (jitter) uniform2(p.seed, frame_pixel, p.sample_base + sb, RNG_DIM_PIXEL, dx, dy);
-                const float U = xadd(cb.left, xmul(xsub(cb.right, cb.left), xdiv(xadd((float)x, dx), (float)p.width)));
-                const float V = xadd(cb.bottom, xmul(xsub(cb.top, cb.bottom), xdiv(xadd((float)y, dy), (float)height)));
                 float rd[3];
+                if (READ_DIR) { rd[0] = dv[k].x; rd[1] = dv[k].y; rd[2] = dv[k].z; }
+                else {
+                    float dx = 0.5f, dy = 0.5f;
+                    if (jitter) uniform2(p.seed, frame_pixel, p.sample_base + sb, RNG_DIM_PIXEL, dx, dy);
+                    const float U = xadd(cb.left, xmul(xsub(cb.right, cb.left), xdiv(xadd((float)x, dx), (float)p.width)));
+                    const float V = xadd(cb.bottom, xmul(xsub(cb.top, cb.bottom), xdiv(xadd((float)y, dy), (float)height)));
 #pragma unroll
-                for (int c = 0; c < 3; ++c) rd[c] = xsub(xadd(xmul(cb.u[c], U), xmul(cb.v[c], V)), cb.w[c]);
-                const float inv = xdiv(1.0f, xsqrt(xdot(rd[0], rd[1], rd[2], rd[0], rd[1], rd[2])));
-                rd[0] = xmul(rd[0], inv); rd[1] = xmul(rd[1], inv); rd[2] = xmul(rd[2], inv);
+                    for (int c = 0; c < 3; ++c) rd[c] = xsub(xadd(xmul(cb.u[c], U), xmul(cb.v[c], V)), cb.w[c]);
+                    const float inv = xdiv(1.0f, xsqrt(xdot(rd[0], rd[1], rd[2], rd[0], rd[1], rd[2])));
+                    rd[0] = xmul(rd[0], inv); rd[1] = xmul(rd[1], inv); rd[2] = xmul(rd[2], inv);
+                }
                 mirogpu_hit h; h.t = hv[k].x; h.prim_id = __float_as_uint(hv[k].y); h.beta = hv[k].z; h.gamma = hv[k].w;
                 const SurfacePoint sp = resolve_hit(rec[k], h);
                 const mirogpu_material m = p.mats[sp.material];
@@ -702,7 +708,10 @@ int render_device(mirogpu_scene* h, const mirogpu_camera& cam, const mirogpu_ren
         camera_basis(cam, rp.width, rp.height, cb);
         uint64_t launches = 0, host_rays = 0;
         RT(cudaMemsetAsync(frame, 0, fbytes + 256, st));
-        constexpr int BW = 4;   // items per thread, like k_gen_bounce
+        // items per thread of the two wave kernels / camera direction re-read instead of recomputed (measured: profiles/r02_e2e_waves.json)
+        static const int bw_items = getenv("MIROGPU_BW_ITEMS") ? atoi(getenv("MIROGPU_BW_ITEMS")) : 4;
+        static const int bw_readd = getenv("MIROGPU_BW_READD") ? atoi(getenv("MIROGPU_BW_READD")) : 0;
+        const int BW = bw_items == 1 ? 1 : bw_items == 2 ? 2 : 4;
         for (uint32_t s0 = 0; s0 < (uint32_t)rp.spp; s0 += fb) {
             const uint32_t nb = std::min<uint32_t>(fb, (uint32_t)rp.spp - s0);
             const size_t items = npix * nb;
@@ -710,9 +719,14 @@ int render_device(mirogpu_scene* h, const mirogpu_camera& cam, const mirogpu_ren
             k_gen_primary<<<dim3((unsigned)((npix + 255) / 256), nb), 256, 0, st>>>(cb, rp.width, rp.height, first_row, rp.row_stride, nrows, rp.jitter, rp.seed, s0, nb, rays);
             RT(dispatch_trace(h, rays, items, hits, MIROGPU_CLOSEST_HIT | MIROGPU_HINT_COHERENT, st));
             const unsigned grid = (unsigned)((items + MIRO_BW_THREADS * BW - 1) / (MIRO_BW_THREADS * BW));
-            k_bounce_wave0<BW><<<grid, MIRO_BW_THREADS, 0, st>>>(wp, cb, rp.height, nrows, rp.jitter, (uint32_t)items, hits, rays, pmat, planes, counters + MIRO_LIVE_SLOT0);
+#define MIRO_W0(K, R) k_bounce_wave0<K, R><<<grid, MIRO_BW_THREADS, 0, st>>>(wp, cb, rp.height, nrows, rp.jitter, (uint32_t)items, hits, rays, pmat, planes, counters + MIRO_LIVE_SLOT0)
+            if (bw_readd) { if (BW == 1) MIRO_W0(1, true); else if (BW == 2) MIRO_W0(2, true); else MIRO_W0(4, true); }
+            else { if (BW == 1) MIRO_W0(1, false); else if (BW == 2) MIRO_W0(2, false); else MIRO_W0(4, false); }
+#undef MIRO_W0
             RT(dispatch_trace(h, rays, items, hits, MIROGPU_CLOSEST_HIT, st));
-            k_bounce_wave1<BW><<<grid, MIRO_BW_THREADS, 0, st>>>(wp, (uint32_t)items, hits, rays, pmat, planes);
+            if (BW == 1) k_bounce_wave1<1><<<grid, MIRO_BW_THREADS, 0, st>>>(wp, (uint32_t)items, hits, rays, pmat, planes);
+            else if (BW == 2) k_bounce_wave1<2><<<grid, MIRO_BW_THREADS, 0, st>>>(wp, (uint32_t)items, hits, rays, pmat, planes);
+            else k_bounce_wave1<4><<<grid, MIRO_BW_THREADS, 0, st>>>(wp, (uint32_t)items, hits, rays, pmat, planes);
             k_fold_planes<<<(unsigned)((npix * 3 + 255) / 256), 256, 0, st>>>(planes, nb, npix * 3, frame);
             launches += 6;
             host_rays += items;
