@@ -709,8 +709,10 @@ int render_device(mirogpu_scene* h, const mirogpu_camera& cam, const mirogpu_ren
         uint64_t launches = 0, host_rays = 0;
         RT(cudaMemsetAsync(frame, 0, fbytes + 256, st));
         // items per thread of the two wave kernels / camera direction re-read instead of recomputed (measured: profiles/r02_e2e_waves.json)
-        static const int bw_items = getenv("MIROGPU_BW_ITEMS") ? atoi(getenv("MIROGPU_BW_ITEMS")) : 4;
-        static const int bw_readd = getenv("MIROGPU_BW_READD") ? atoi(getenv("MIROGPU_BW_READD")) : 0;
+        // Measured on the bench frame (profiles/r02_e2e_waves.jsonl): 4 items per thread (144 registers, 18 % occupancy) 9.40 ms per
+        // frame, 2 items 8.61, 1 item 8.61; with the direction re-read 9.25 / 8.56 / 8.78 -> 2 items, direction re-read.
+        static const int bw_items = getenv("MIROGPU_BW_ITEMS") ? atoi(getenv("MIROGPU_BW_ITEMS")) : 2;
+        static const int bw_readd = getenv("MIROGPU_BW_READD") ? atoi(getenv("MIROGPU_BW_READD")) : 1;
         const int BW = bw_items == 1 ? 1 : bw_items == 2 ? 2 : 4;
         for (uint32_t s0 = 0; s0 < (uint32_t)rp.spp; s0 += fb) {
             const uint32_t nb = std::min<uint32_t>(fb, (uint32_t)rp.spp - s0);
