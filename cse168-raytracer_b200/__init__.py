@@ -86,6 +86,7 @@ EXPORTS = [
     "mirogpu_render", "mirogpu_render_rgb8", "mirogpu_tonemap_rgb8_device", "mirogpu_render_device", "mirogpu_last_call_stats", "mirogpu_photon_upload", "mirogpu_photon_gather",
     "mirogpu_photon_gather_device", "mirogpu_photon_trace", "mirogpu_photon_set_exact", "mirogpu_host_alloc", "mirogpu_host_free",
     "mirogpu_frame_max_device", "mirogpu_tonemap_rows_rgb8_device", "mirogpu_release_build_scratch",
+    "mirogpu_scene_create_ex", "mirogpu_scene_devices", "mirogpu_resolve_hits_rays_device",
 ]
 
 
@@ -212,6 +213,14 @@ class MiroScene:
         _check(lib.mirogpu_debug_copy_triangles(self._h, _ptr(out), ctypes.byref(n)))
         return out
 
+    def devices(self):
+        """CUDA device ordinals the scene is replicated on (mirogpu_scene_devices)."""
+        n = ctypes.c_uint32(0)
+        _check(lib.mirogpu_scene_devices(self._h, None, ctypes.c_uint32(0), ctypes.byref(n)))
+        arr = (ctypes.c_int32 * n.value)()
+        _check(lib.mirogpu_scene_devices(self._h, arr, ctypes.c_uint32(n.value), ctypes.byref(n)))
+        return list(arr)
+
     def set_kernel_variant(self, v):
         _check(lib.mirogpu_set_kernel_variant(self._h, int(v)))
 
@@ -250,8 +259,12 @@ class MiroScene:
         n = d_rays.shape[0] if n is None else n
         _check(lib.mirogpu_intersect_batch_device(self._h, _ptr(d_rays), ctypes.c_size_t(n), _ptr(d_hits), int(mode), _stream()))
 
-    def resolve_hits_device(self, d_hits, d_P=None, d_N=None, d_mat=None):
-        _check(lib.mirogpu_resolve_hits_device(self._h, _ptr(d_hits), ctypes.c_size_t(d_hits.shape[0]), _ptr(d_P), _ptr(d_N), _ptr(d_mat), _stream()))
+    def resolve_hits_device(self, d_hits, d_P=None, d_N=None, d_mat=None, d_rays=None):
+        """P, N (normalised as Scene::trace leaves it), material id per hit.  d_rays is required when the scene holds spheres / planes."""
+        if d_rays is not None:
+            _check(lib.mirogpu_resolve_hits_rays_device(self._h, _ptr(d_rays), _ptr(d_hits), ctypes.c_size_t(d_hits.shape[0]), _ptr(d_P), _ptr(d_N), _ptr(d_mat), _stream()))
+        else:
+            _check(lib.mirogpu_resolve_hits_device(self._h, _ptr(d_hits), ctypes.c_size_t(d_hits.shape[0]), _ptr(d_P), _ptr(d_N), _ptr(d_mat), _stream()))
 
     # ---- device ray generation ----------------------------------------------------------------------
     def generate_primary(self, cam, width, height, d_rays, rows=None, jitter=0, seed=168, sample=0, samples=1):
@@ -407,6 +420,16 @@ class HostScene:
 
     def add_triangle(self, v9, n9, material=0):
         self.h.mh_add_triangle((ctypes.c_float * 9)(*map(float, v9)), (ctypes.c_float * 9)(*map(float, n9)), int(material))
+
+    def add_sphere(self, center, radius, material=0):
+        self.h.mh_add_sphere(_f3(center), ctypes.c_float(radius), int(material))
+
+    def add_plane(self, normal, origin, material=0):
+        self.h.mh_add_plane(_f3(normal), _f3(origin), int(material))
+
+    def set_device_count(self, n):
+        """Replicate the scene on CUDA devices 0..n-1 at the next precalc(): Scene::raytraceImage then shards its rows over them."""
+        self.h.mh_set_device_count(int(n))
 
     def add_point_light(self, pos, color, wattage):
         self.h.mh_add_point_light(_f3(pos), _f3(color), ctypes.c_float(wattage))

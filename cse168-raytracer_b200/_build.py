@@ -95,6 +95,7 @@ def build_oracle(verbose=False):
     _run(["make", "-C", odir, "oracle"], verbose)
     if os.path.isdir("/root/reference"):
         _run(["make", "-C", odir, "ref"], verbose)
+        _run(["make", "-C", odir, "scripts"], verbose)   # the reference's assignment2.cpp against the host API layer
 
 
 def build_all(force=False, verbose=False):

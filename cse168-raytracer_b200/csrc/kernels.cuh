@@ -19,8 +19,10 @@ namespace mirogpu {
 struct DeviceScene {
     const float4* nodes;   // BVH2: 4 float4 per node; BVH4: 8 float4 per node; QBVH4: 4 float4 per node; CWBVH8: 5 uint4 per node
     const float4* tris;    // 4 float4 (64 B) per triangle, leaf order: (A, prim) (B-A, n.x) (C-A, n.y) (n.z, -, -, -)
-    const float4* shade;   // 6 float4 per primitive, prim-id order: (A,mat) e1 e2 nA nB nC
-    uint32_t num_tris;
+    const float4* shade;   // 6 float4 per primitive, prim-id order: (A,mat) (e1,kind) e2 nA nB nC; kind 1 sphere (centre,mat) (radius,1); 2 plane
+    const float4* planes;  // 2 float4 per plane: (normal, prim id bits) (origin, 0) -- the unbounded objects of Scene::trace (Scene.cpp:219-230)
+    uint32_t num_tris;     // all primitives (triangles, spheres, planes): the range of prim ids
+    uint32_t num_planes;
 };
 
 struct CameraBasis {       // what Camera::eyeRay caches in its statics (Camera.cpp:106-125)
@@ -30,6 +32,22 @@ struct CameraBasis {       // what Camera::eyeRay caches in its statics (Camera.
 
 #define MIRO_PI 3.1415926535897932384626433832795028841972f /* Miro.h:10 */
 
+// Scene::trace's loop over the unbounded objects (Scene.cpp:219-230) with Plane::intersect (Plane.cpp:33-48) inlined: a plane
+// replaces the tree's answer only if strictly closer, or -- nothing hit so far -- anywhere inside [tMin, tMax]; planes are
+// tried in insertion order.  fabs(ndotd) < 1e-6 is a double comparison in the reference.
+__device__ __forceinline__ void planes_test(const DeviceScene& s, const mirogpu_ray& r, BestHit& best)
+{
+    if (!(r.tmax >= r.tmin)) return;
+    for (uint32_t k = 0; k < s.num_planes; ++k) {
+        const float4 n = __ldg(s.planes + 2 * k), o = __ldg(s.planes + 2 * k + 1);
+        const float ndotd = xdot(n.x, n.y, n.z, r.dx, r.dy, r.dz);
+        if ((double)fabsf(ndotd) < 1e-6) continue;
+        const float t = xdiv(xdot(n.x, n.y, n.z, xsub(o.x, r.ox), xsub(o.y, r.oy), xsub(o.z, r.oz)), ndotd);
+        if (t < r.tmin || t > r.tmax) continue;
+        if (best.prim == MIROGPU_MISS || t < best.t) { best.t = t; best.prim = __float_as_uint(n.w); best.beta = 0.f; best.gamma = 0.f; }
+    }
+}
+
 template <int LAYOUT, bool ANY, bool COUNT>
 __device__ __forceinline__ void trace_one(const DeviceScene& s, const mirogpu_ray& r, BestHit& best, TraceCounters* c)
 {
@@ -37,6 +55,7 @@ __device__ __forceinline__ void trace_one(const DeviceScene& s, const mirogpu_ra
     else if (LAYOUT == MIROGPU_LAYOUT_BVH4) trace_bvh4<ANY, COUNT>(s.nodes, s.tris, r, best, c);
     else if (LAYOUT == MIROGPU_LAYOUT_QBVH4) trace_qbvh4<ANY, COUNT>(s.nodes, s.tris, r, best, c);
     else trace_cwbvh8<ANY, COUNT>(reinterpret_cast<const uint4*>(s.nodes), s.tris, r, best, c);
+    if (s.num_planes) planes_test(s, r, best);
 }
 
 // Rays and hits are streamed once per launch: loads/stores carry the evict-first hint so the batch does not push
@@ -236,7 +255,7 @@ __global__ void __launch_bounds__(128, MINB) k_trace_hybrid(DeviceScene s, const
                         else if ((PF & 128) && pleaf == MIRO_BVH2_DONE) { pleaf = pleaf2; pleaf2 = MIRO_BVH2_DONE; }
                     }
                 }
-                if (w.node == MIRO_BVH2_DONE && pleaf == MIRO_BVH2_DONE && ((mn | ml) >> lane & 1u)) store_hit(hits, my, best);
+                if (w.node == MIRO_BVH2_DONE && pleaf == MIRO_BVH2_DONE && ((mn | ml) >> lane & 1u)) { if (s.num_planes) planes_test(s, r, best); store_hit(hits, my, best); }
             }
             continue;
         }
@@ -257,7 +276,7 @@ __global__ void __launch_bounds__(128, MINB) k_trace_hybrid(DeviceScene s, const
                 else if (PF & 16) bvh2_leaf_step_one<ANY>(s.tris, r, w, stack, best);
                 else bvh2_leaf_step<ANY>(s.tris, r, w, stack, best);
             }
-            if (w.node == MIRO_BVH2_DONE && ((mn | ml) >> lane & 1u)) store_hit(hits, my, best);
+            if (w.node == MIRO_BVH2_DONE && ((mn | ml) >> lane & 1u)) { if (s.num_planes) planes_test(s, r, best); store_hit(hits, my, best); }
         }
     }
 }
@@ -307,6 +326,8 @@ __device__ __forceinline__ ShadeRecord load_shade_record(const DeviceScene& s, u
     r.r0 = ld256(q); r.r1 = ld256(q + 2); r.r2 = ld256(q + 4);
     return r;
 }
+__device__ __forceinline__ uint32_t record_kind(const ShadeRecord& rec) { return __float_as_uint(rec.r0.hi.w); }   // 0 triangle, 1 sphere, 2 plane
+
 __device__ __forceinline__ SurfacePoint resolve_hit(const ShadeRecord& rec, const mirogpu_hit& h)
 {
     const float4 A = rec.r0.lo, e1 = rec.r0.hi, e2 = rec.r1.lo, nA = rec.r1.hi, nB = rec.r2.lo, nC = rec.r2.hi;
@@ -324,12 +345,38 @@ __device__ __forceinline__ SurfacePoint resolve_hit(const ShadeRecord& rec, cons
     sp.material = __float_as_uint(A.w);
     return sp;
 }
-__device__ __forceinline__ SurfacePoint resolve_hit(const DeviceScene& s, const mirogpu_hit& h)
+// Spheres and planes: P = o + t d (Sphere.cpp:62, Plane.cpp:42); sphere N = (P - c).normalize() (Sphere.cpp:63-64), plane N =
+// its normal as given (Plane.cpp:44); Scene::trace then normalises N once more (Scene.cpp:262).
+__device__ __noinline__ SurfacePoint resolve_hit_analytic(const ShadeRecord& rec, const mirogpu_hit& h, float ox, float oy, float oz, float dx, float dy, float dz)
 {
-    return resolve_hit(load_shade_record(s, h.prim_id), h);
+    SurfacePoint sp;
+    sp.P[0] = xadd(ox, xmul(dx, h.t)); sp.P[1] = xadd(oy, xmul(dy, h.t)); sp.P[2] = xadd(oz, xmul(dz, h.t));
+    float n[3];
+    if (record_kind(rec) == 1u) {
+        n[0] = xsub(sp.P[0], rec.r0.lo.x); n[1] = xsub(sp.P[1], rec.r0.lo.y); n[2] = xsub(sp.P[2], rec.r0.lo.z);
+        const float i0 = xdiv(1.0f, xsqrt(xdot(n[0], n[1], n[2], n[0], n[1], n[2])));
+        n[0] = xmul(n[0], i0); n[1] = xmul(n[1], i0); n[2] = xmul(n[2], i0);
+    } else { n[0] = rec.r1.hi.x; n[1] = rec.r1.hi.y; n[2] = rec.r1.hi.z; }
+    const float inv = xdiv(1.0f, xsqrt(xdot(n[0], n[1], n[2], n[0], n[1], n[2])));
+    sp.N[0] = xmul(n[0], inv); sp.N[1] = xmul(n[1], inv); sp.N[2] = xmul(n[2], inv);
+    sp.material = __float_as_uint(rec.r0.lo.w);
+    return sp;
+}
+// Any primitive kind; the ray is only read (through `ray`) for the analytic kinds.
+__device__ __forceinline__ SurfacePoint resolve_hit(const ShadeRecord& rec, const mirogpu_hit& h, const mirogpu_ray* ray)
+{
+    if (record_kind(rec) == 0u) return resolve_hit(rec, h);
+    const float4* p = reinterpret_cast<const float4*>(ray);
+    const float4 a = p[0], b = p[1];
+    return resolve_hit_analytic(rec, h, a.x, a.y, a.z, b.x, b.y, b.z);
+}
+__device__ __forceinline__ SurfacePoint resolve_hit(const ShadeRecord& rec, const mirogpu_hit& h, const mirogpu_ray& r)
+{
+    if (record_kind(rec) == 0u) return resolve_hit(rec, h);
+    return resolve_hit_analytic(rec, h, r.ox, r.oy, r.oz, r.dx, r.dy, r.dz);
 }
 
-__global__ void __launch_bounds__(256) k_resolve_hits(DeviceScene s, const mirogpu_hit* __restrict__ hits, size_t n,
+__global__ void __launch_bounds__(256) k_resolve_hits(DeviceScene s, const mirogpu_ray* __restrict__ rays, const mirogpu_hit* __restrict__ hits, size_t n,
                                                        float* __restrict__ P, float* __restrict__ N, uint32_t* __restrict__ mat)
 {
     const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -339,7 +386,10 @@ __global__ void __launch_bounds__(256) k_resolve_hits(DeviceScene s, const mirog
     SurfacePoint sp;
     if (h.prim_id == MIROGPU_MISS) {
         sp.P[0] = sp.P[1] = sp.P[2] = 0.f; sp.N[0] = sp.N[1] = sp.N[2] = 0.f; sp.material = MIROGPU_MISS;
-    } else sp = resolve_hit(s, h);
+    } else {
+        const ShadeRecord rec = load_shade_record(s, h.prim_id);
+        sp = rays ? resolve_hit(rec, h, rays + i) : resolve_hit(rec, h);
+    }
     if (P) { P[3 * i] = sp.P[0]; P[3 * i + 1] = sp.P[1]; P[3 * i + 2] = sp.P[2]; }
     if (N) { N[3 * i] = sp.N[0]; N[3 * i + 1] = sp.N[1]; N[3 * i + 2] = sp.N[2]; }
     if (mat) mat[i] = sp.material;
@@ -411,7 +461,7 @@ __global__ void __launch_bounds__(MIRO_GENB_THREADS) k_gen_bounce(DeviceScene s,
         if (h[k].prim_id == MIROGPU_MISS) {
             a = make_float4(0.f, 0.f, 0.f, 0.f); b = make_float4(0.f, 0.f, 1.f, -1.0f);  // tmax < tmin: never hits
         } else {
-            const SurfacePoint sp = resolve_hit(rec[k], h[k]);
+            const SurfacePoint sp = resolve_hit(rec[k], h[k], rays + i);
             float u1, u2;
             uniform2(seed, index_base + (uint32_t)i, sample, RNG_DIM_BOUNCE, u1, u2);
             const float phi = asinf(sqrtf(u1));

@@ -23,11 +23,13 @@ protected:
 
 class SquareLight : public PointLight {
 public:
-    SquareLight() : m_normal(0, 1, 0) {}
+    SquareLight() : m_normal(0, 1, 0) { m_dimensions[0] = m_dimensions[1] = 1.f; }
     void setNormal(Vector3 n) { m_normal = n; }
     Vector3 getNormal() { return m_normal; }
+    void setDimensions(float width, float height) { m_dimensions[0] = width; m_dimensions[1] = height; }
 protected:
     Vector3 m_normal;
+    float m_dimensions[2];
 };
 
 class DirectionalAreaLight : public SquareLight {

@@ -20,6 +20,7 @@ public:
         if (pObj->isBounded()) m_objects.push_back(pObj); else m_unboundedObjects.push_back(pObj);
     }
     const Objects* objects() const { return &m_objects; }
+    const Objects* unboundedObjects() const { return &m_unboundedObjects; }
     void addLight(PointLight* pObj) { m_lights.push_back(pObj); }
     const Lights* lights() const { return &m_lights; }
     void preCalc();

@@ -7,6 +7,7 @@
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
+#include <cstdarg>
 #include <cstring>
 #include <map>
 #include <vector>
@@ -20,6 +21,10 @@
 #include "TriangleMesh.h"
 #include "Triangle.h"
 #include "PointLight.h"
+#include "Sphere.h"
+#include "Plane.h"
+#include "Console.h"
+#include "Utility.h"
 #include "BVH.h"
 #include "Camera.h"
 #include "Image.h"
@@ -31,7 +36,7 @@ Scene* g_scene = 0;
 Image* g_image = 0;
 
 namespace {
-[[noreturn]] void fatal(const char* what)
+[[noreturn]] void die(const char* what)
 {
     // the reference's fatal() prints and exits (Console.cpp:119-129); the device layer has no CPU fallback
     fprintf(stderr, "fatal: %s: %s\n", what, mirogpu_last_error());
@@ -260,21 +265,112 @@ bool Triangle::intersect(HitInfo& result, const Ray& r, float tMin, float tMax)
     return true;
 }
 
+// ================================= Sphere / Plane ============================================================
+// Sphere.cpp:28-69, statement for statement (this file is compiled without FMA contraction).
+bool Sphere::intersect(HitInfo& result, const Ray& ray, float tMin, float tMax)
+{
+    const Vector3 toO = ray.o - m_center;
+    const float a = ray.d.length2();
+    const float b = dot(2 * ray.d, toO);
+    const float c = toO.length2() - m_radius * m_radius;
+    const float discrim = b * b - 4.0f * a * c;
+    if (discrim < 0) return false;
+    const float sqrt_discrim = sqrtf(discrim);
+    const float t[2] = {(-b - sqrt_discrim) / (2.0f * a), (-b + sqrt_discrim) / (2.0f * a)};
+    if ((t[0] > tMin) && (t[0] < tMax)) result.t = t[0];
+    else if ((t[1] > tMin) && (t[1] < tMax)) result.t = t[1];
+    else return false;
+    fillHit(result, ray, result.t);
+    return true;
+}
+void Sphere::fillHit(HitInfo& result, const Ray& ray, float t) const
+{
+    result.t = t;
+    result.P = ray.o + t * ray.d;
+    result.N = (result.P - m_center);
+    result.N.normalize();
+    result.material = m_material;
+}
+// Plane.cpp:33-48
+bool Plane::intersect(HitInfo& result, const Ray& r, float tMin, float tMax)
+{
+    const float ndotd = dot(m_normal, r.d);
+    if (fabs(ndotd) < 1e-6) return false;
+    const float t = dot(m_normal, (m_origin - r.o)) / ndotd;
+    if (t < tMin || t > tMax) return false;
+    fillHit(result, r, t);
+    return true;
+}
+void Plane::fillHit(HitInfo& result, const Ray& r, float t) const
+{
+    result.P = r.o + t * r.d;
+    result.t = t;
+    result.N = m_normal;
+    result.material = m_material;
+}
+
+// ================================= Console / Utility ==========================================================
+#define MIRO_CONSOLE_FN(name, prefix, stream, after)            \
+    void name(const char* fmt, ...)                             \
+    {                                                           \
+        va_list ap; va_start(ap, fmt);                          \
+        fputs(prefix, stream); vfprintf(stream, fmt, ap);       \
+        va_end(ap); after;                                      \
+    }
+MIRO_CONSOLE_FN(warning, "warning: ", stderr, (void)0)
+MIRO_CONSOLE_FN(error, "error: ", stderr, (void)0)
+MIRO_CONSOLE_FN(debug, "", stdout, (void)0)
+MIRO_CONSOLE_FN(fatal, "fatal: ", stderr, exit(-1))
+#undef MIRO_CONSOLE_FN
+double getTime() { return wall(); }
+
 // ================================= BVH =======================================================================
 BVH::~BVH() { if (m_handle) mirogpu_scene_destroy(m_handle); }
 
+namespace {
+uint32_t materialIndex(const Material* mat, std::map<const Material*, uint32_t>& matIndex, std::vector<mirogpu_material>& mats)
+{
+    std::map<const Material*, uint32_t>::iterator it = matIndex.find(mat);
+    if (it == matIndex.end()) {
+        mirogpu_material mm; memset(&mm, 0, sizeof mm);
+        const Vector3 kd = mat ? mat->getDiffuse() : Vector3(1.f), ks = mat ? mat->getReflection() : Vector3(0.f),
+                      kt = mat ? mat->getRefraction() : Vector3(0.f);
+        for (int k = 0; k < 3; ++k) { mm.kd[k] = kd[k]; mm.ks[k] = ks[k]; mm.kt[k] = kt[k]; }
+        mm.shininess = mat ? mat->getShininess() : 1.f;
+        mm.refract_index = mat ? mat->getRefractionIndex() : 1.f;
+        it = matIndex.insert(std::make_pair(mat, (uint32_t)mats.size())).first;
+        mats.push_back(mm);
+    }
+    return it->second;
+}
+}  // namespace
+
+// BVH::build (BVH.h:33): the bounded objects of the list -- triangles and spheres -- become the leaf primitives of the device
+// tree, the scene's planes (setUnbounded) ride along as the device's post-walk list; objects of any other class stay on the
+// host and are tested after the device query.  Device primitive ids: triangles, then spheres, then planes, each in list order.
 void BVH::build(Objects* objs, int)
 {
     if (m_handle) { mirogpu_scene_destroy(m_handle); m_handle = 0; }
     m_objects = objs;
-    m_tris.clear(); m_other.clear();
+    m_prims.clear(); m_other.clear();
     std::map<const Material*, uint32_t> matIndex;
     std::vector<mirogpu_material> mats;
     std::vector<float> verts, norms;
     std::vector<uint32_t> matIds;
+    std::vector<Object*> sphereObjs, planeObjs;
+    std::vector<mirogpu_sphere> spheres;
+    std::vector<mirogpu_plane> planes;
     for (size_t i = 0; i < objs->size(); ++i) {
         Object* o = (*objs)[i];
         if (!o->isBounded()) continue;
+        if (Sphere* sp = dynamic_cast<Sphere*>(o)) {
+            mirogpu_sphere ms; memset(&ms, 0, sizeof ms);
+            const Vector3 c = sp->center();
+            ms.center[0] = c.x; ms.center[1] = c.y; ms.center[2] = c.z; ms.radius = sp->radius();
+            ms.material_id = materialIndex(sp->getMaterial(), matIndex, mats);
+            spheres.push_back(ms); sphereObjs.push_back(o);
+            continue;
+        }
         Triangle* t = dynamic_cast<Triangle*>(o);
         if (!t) { m_other.push_back(o); continue; }
         TriangleMesh* m = t->getMesh();
@@ -287,25 +383,43 @@ void BVH::build(Objects* objs, int)
             const Vector3& q = m->normals()[ni.v[k]];
             norms.push_back(q.x); norms.push_back(q.y); norms.push_back(q.z);
         }
-        const Material* mat = t->getMaterial();
-        std::map<const Material*, uint32_t>::iterator it = matIndex.find(mat);
-        if (it == matIndex.end()) {
-            mirogpu_material mm; memset(&mm, 0, sizeof mm);
-            const Vector3 kd = mat ? mat->getDiffuse() : Vector3(1.f), ks = mat ? mat->getReflection() : Vector3(0.f),
-                          kt = mat ? mat->getRefraction() : Vector3(0.f);
-            for (int k = 0; k < 3; ++k) { mm.kd[k] = kd[k]; mm.ks[k] = ks[k]; mm.kt[k] = kt[k]; }
-            mm.shininess = mat ? mat->getShininess() : 1.f;
-            mm.refract_index = mat ? mat->getRefractionIndex() : 1.f;
-            it = matIndex.insert(std::make_pair(mat, (uint32_t)mats.size())).first;
-            mats.push_back(mm);
-        }
-        matIds.push_back(it->second);
-        m_tris.push_back(t);
+        matIds.push_back(materialIndex(t->getMaterial(), matIndex, mats));
+        m_prims.push_back(t);
     }
+    m_ntris = (uint32_t)m_prims.size();
+    if (m_unbounded)
+        for (size_t i = 0; i < m_unbounded->size(); ++i)
+            if (Plane* pl = dynamic_cast<Plane*>((*m_unbounded)[i])) {
+                mirogpu_plane mp; memset(&mp, 0, sizeof mp);
+                for (int k = 0; k < 3; ++k) { mp.normal[k] = pl->normal()[k]; mp.origin[k] = pl->origin()[k]; }
+                mp.material_id = materialIndex(pl->getMaterial(), matIndex, mats);
+                planes.push_back(mp); planeObjs.push_back(pl);
+            }
+    m_nspheres = (uint32_t)spheres.size();
+    m_prims.insert(m_prims.end(), sphereObjs.begin(), sphereObjs.end());
+    m_prims.insert(m_prims.end(), planeObjs.begin(), planeObjs.end());
+    // devices: setDevices(), else MIROGPU_DEVICES = "all" | "0,1,..." , else the current device
+    std::vector<int32_t> devs(m_devices.begin(), m_devices.end());
+    if (devs.empty())
+        if (const char* e = getenv("MIROGPU_DEVICES")) {
+            if (!strcmp(e, "all")) { int n = 0; mirogpu_device_count(&n); for (int k = 0; k < n; ++k) devs.push_back(k); }
+            else for (const char* q = e; *q;) { devs.push_back(atoi(q)); while (*q && *q != ',') ++q; if (*q == ',') ++q; }
+        }
     mirogpu_build_options opt; opt.layout = m_layout; opt.max_leaf = 0; opt.sah_bins = 32; opt.device = -1; opt.builder = m_builder;
-    const int rc = mirogpu_scene_create(verts.data(), norms.data(), matIds.data(), (uint32_t)m_tris.size(),
-                                        mats.empty() ? 0 : mats.data(), (uint32_t)mats.size(), &opt, &m_handle);
-    if (rc != MIROGPU_OK) fatal("BVH::build");
+    mirogpu_scene_desc d; memset(&d, 0, sizeof d);
+    d.tri_vertices = verts.data(); d.tri_normals = norms.data(); d.tri_material_ids = matIds.data(); d.ntris = m_ntris;
+    d.spheres = spheres.empty() ? 0 : spheres.data(); d.nspheres = m_nspheres;
+    d.planes = planes.empty() ? 0 : planes.data(); d.nplanes = (uint32_t)planes.size();
+    d.materials = mats.empty() ? 0 : mats.data(); d.nmaterials = (uint32_t)mats.size();
+    d.devices = devs.empty() ? 0 : devs.data(); d.ndevices = (uint32_t)devs.size();
+    const int rc = mirogpu_scene_create_ex(&d, &opt, &m_handle);
+    if (rc != MIROGPU_OK) die("BVH::build");
+}
+
+bool BVH::onDevice(const Object* o) const
+{
+    for (size_t i = m_ntris; i < m_prims.size(); ++i) if (m_prims[i] == o) return true;   // spheres and planes (few)
+    return dynamic_cast<const Triangle*>(o) != 0;
 }
 
 bool BVH::finish(HitInfo& result, const mirogpu_hit& h, const Ray& ray, float tMin, float tMax) const
@@ -313,12 +427,14 @@ bool BVH::finish(HitInfo& result, const mirogpu_hit& h, const Ray& ray, float tM
     bool hit = false;
     result.t = tMax;                                  // miss contract of the reference (BVH.cpp:444)
     if (h.prim_id != MIROGPU_MISS) {
-        const Triangle* t = m_tris[h.prim_id];
-        t->fillHit(result, h.t, h.beta, h.gamma);
-        result.object = t;
+        Object* o = m_prims[h.prim_id];
+        if (h.prim_id < m_ntris) static_cast<const Triangle*>(o)->fillHit(result, h.t, h.beta, h.gamma);
+        else if (h.prim_id < m_ntris + m_nspheres) static_cast<const Sphere*>(o)->fillHit(result, ray, h.t);
+        else static_cast<const Plane*>(o)->fillHit(result, ray, h.t);
+        result.object = o;
         hit = true;
     }
-    for (size_t i = 0; i < m_other.size(); ++i) {     // spheres etc.: outside the device path
+    for (size_t i = 0; i < m_other.size(); ++i) {     // object classes the device does not know: tested here
         HitInfo tmp;
         if (m_other[i]->intersect(tmp, ray, tMin, result.t) && tmp.t < result.t) { result = tmp; result.object = m_other[i]; hit = true; }
     }
@@ -327,16 +443,16 @@ bool BVH::finish(HitInfo& result, const mirogpu_hit& h, const Ray& ray, float tM
 
 bool BVH::intersect(HitInfo& result, const Ray& ray, float tMin, float tMax) const
 {
-    if (!m_handle) fatal("BVH::intersect before build");
+    if (!m_handle) die("BVH::intersect before build");
     mirogpu_ray r = {ray.o.x, ray.o.y, ray.o.z, tMin, ray.d.x, ray.d.y, ray.d.z, tMax};
     mirogpu_hit h;
-    if (mirogpu_intersect_batch(m_handle, &r, 1, &h, MIROGPU_CLOSEST_HIT) != MIROGPU_OK) fatal("BVH::intersect");
+    if (mirogpu_intersect_batch(m_handle, &r, 1, &h, MIROGPU_CLOSEST_HIT) != MIROGPU_OK) die("BVH::intersect");
     return finish(result, h, ray, tMin, tMax);
 }
 
 size_t BVH::intersectBatch(const Ray* rays, size_t n, HitInfo* results, bool* hitFlags, float tMin, float tMax) const
 {
-    if (!m_handle) fatal("BVH::intersectBatch before build");
+    if (!m_handle) die("BVH::intersectBatch before build");
     std::vector<mirogpu_ray> rr(n);
     std::vector<mirogpu_hit> hh(n);
     for (size_t i = 0; i < n; ++i) {
@@ -344,7 +460,7 @@ size_t BVH::intersectBatch(const Ray* rays, size_t n, HitInfo* results, bool* hi
         mirogpu_ray r = {q.o.x, q.o.y, q.o.z, tMin, q.d.x, q.d.y, q.d.z, tMax};
         rr[i] = r;
     }
-    if (mirogpu_intersect_batch(m_handle, rr.data(), n, hh.data(), MIROGPU_CLOSEST_HIT) != MIROGPU_OK) fatal("BVH::intersectBatch");
+    if (mirogpu_intersect_batch(m_handle, rr.data(), n, hh.data(), MIROGPU_CLOSEST_HIT) != MIROGPU_OK) die("BVH::intersectBatch");
     size_t nh = 0;
     for (size_t i = 0; i < n; ++i) {
         const bool h = finish(results[i], hh[i], rays[i], tMin, tMax);
@@ -443,6 +559,8 @@ void Scene::preCalc()
 {
     for (Objects::iterator it = m_objects.begin(); it != m_objects.end(); ++it) (*it)->preCalc();
     for (Lights::iterator it = m_lights.begin(); it != m_lights.end(); ++it) (*it)->preCalc();
+    for (Objects::iterator it = m_unboundedObjects.begin(); it != m_unboundedObjects.end(); ++it) (*it)->preCalc();
+    m_bvh.setUnbounded(&m_unboundedObjects);
     m_bvh.build(&m_objects);
     std::vector<mirogpu_light> ls;
     for (size_t i = 0; i < m_lights.size(); ++i) {
@@ -457,7 +575,7 @@ void Scene::preCalc()
         }
         ls.push_back(l);
     }
-    if (mirogpu_scene_set_lights(m_bvh.handle(), ls.empty() ? 0 : ls.data(), (uint32_t)ls.size()) != MIROGPU_OK) fatal("Scene::preCalc lights");
+    if (mirogpu_scene_set_lights(m_bvh.handle(), ls.empty() ? 0 : ls.data(), (uint32_t)ls.size()) != MIROGPU_OK) die("Scene::preCalc lights");
     // Scene.cpp:76-82: generate the photon maps (only DirectionalAreaLights emit, Scene.cpp:368)
     bool emitter = false;
     for (size_t i = 0; i < ls.size(); ++i) emitter |= ls[i].kind == 1;
@@ -490,7 +608,7 @@ long Scene::tracePhotonPass(Photon_map& map, int which, int target, bool caustic
         while (photonsAdded < target && totalPhotons < kMaxEmissions) {
             counts.resize(batch); records.resize((size_t)batch * 45);
             if (mirogpu_photon_trace(m_bvh.handle(), (int)l, caustic ? 1 : 0, renderSeed + (caustic ? 1u : 0u), ((uint64_t)l << 40) | next, batch,
-                                     counts.data(), records.data()) != MIROGPU_OK) fatal("Scene::tracePhotons");
+                                     counts.data(), records.data()) != MIROGPU_OK) die("Scene::tracePhotons");
             const int before = photonsAdded;
             uint32_t used = 0;
             for (uint32_t i = 0; i < batch && photonsAdded < target; ++i, ++used) {   // "if (photonsAdded < PhotonsPerLightSource)", in emission order
@@ -518,8 +636,9 @@ void Scene::postProcess(HitInfo& minHit) const { minHit.N.normalize(); }
 
 bool Scene::trace(HitInfo& minHit, const Ray& ray, float tMin, float tMax) const
 {
-    bool result = m_bvh.intersect(minHit, ray, tMin, tMax);
+    bool result = m_bvh.intersect(minHit, ray, tMin, tMax);    // planes included (the device's post-walk list)
     for (size_t i = 0; i < m_unboundedObjects.size(); ++i) {
+        if (m_bvh.onDevice(m_unboundedObjects[i])) continue;
         HitInfo tmp;
         if (m_unboundedObjects[i]->intersect(tmp, ray, tMin, tMax) && (!result || tmp.t < minHit.t)) {
             result = true; minHit = tmp; minHit.object = m_unboundedObjects[i];
@@ -537,6 +656,7 @@ size_t Scene::traceBatch(const Ray* rays, size_t n, HitInfo* results, bool* hitF
     for (size_t r = 0; r < n; ++r) {
         bool result = flags[r] != 0;
         for (size_t i = 0; i < m_unboundedObjects.size(); ++i) {
+            if (m_bvh.onDevice(m_unboundedObjects[i])) continue;
             HitInfo tmp;
             if (m_unboundedObjects[i]->intersect(tmp, rays[r], tMin, tMax) && (!result || tmp.t < results[r].t)) {
                 result = true; results[r] = tmp; results[r].object = m_unboundedObjects[i];
@@ -561,7 +681,7 @@ void Scene::raytraceImage(Camera* cam, Image* img)
     const mirogpu_camera c = cam->abi();
     const double t0 = wall();
     // the device applies the tone map and Image::setPixel's 8-bit mapping; Image::Pixel is 3 bytes, row 0 = bottom
-    if (mirogpu_render_rgb8(m_bvh.handle(), &c, &p, img->getCharPixels()) != MIROGPU_OK) fatal("Scene::raytraceImage");
+    if (mirogpu_render_rgb8(m_bvh.handle(), &c, &p, img->getCharPixels()) != MIROGPU_OK) die("Scene::raytraceImage");
     lastRenderSeconds = wall() - t0;
     printf("Time spent raytracing image: %lf seconds.\n", lastRenderSeconds);
 }
@@ -686,13 +806,13 @@ void Photon_map::balance(void)
 void Photon_map::attach(mirogpu_handle h, int which)
 {
     m_handle = h; m_which = which;
-    if (mirogpu_photon_upload(h, which, photons, stored_photons) != MIROGPU_OK) fatal("Photon_map::attach");
+    if (mirogpu_photon_upload(h, which, photons, stored_photons) != MIROGPU_OK) die("Photon_map::attach");
 }
 
 void Photon_map::irradiance_estimate_batch(float* irrad3, const float* pos3, const float* normal3, size_t n, float max_dist, int nphotons) const
 {
-    if (!m_handle) fatal("Photon_map::irradiance_estimate before attach");
-    if (mirogpu_photon_gather(m_handle, m_which, pos3, normal3, n, max_dist, nphotons, irrad3) != MIROGPU_OK) fatal("Photon_map::irradiance_estimate");
+    if (!m_handle) die("Photon_map::irradiance_estimate before attach");
+    if (mirogpu_photon_gather(m_handle, m_which, pos3, normal3, n, max_dist, nphotons, irrad3) != MIROGPU_OK) die("Photon_map::irradiance_estimate");
 }
 
 void Photon_map::irradiance_estimate(float irrad[3], const float pos[3], const float normal[3], const float max_dist, const int nphotons) const

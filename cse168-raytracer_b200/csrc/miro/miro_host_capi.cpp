@@ -12,6 +12,8 @@
 #include "Image.h"
 #include "Triangle.h"
 #include "TriangleMesh.h"
+#include "Sphere.h"
+#include "Plane.h"
 #include "PointLight.h"
 #include "PhotonMap.h"
 
@@ -67,6 +69,26 @@ void mh_add_triangle(const float* v9, const float* n9, int material)
     g_scene->addObject(t);
 }
 
+void mh_add_sphere(const float* center, float radius, int material)
+{
+    Sphere* sp = new Sphere;
+    sp->setCenter(Vector3(center[0], center[1], center[2])); sp->setRadius(radius); sp->setMaterial(g_materials[material]);
+    g_scene->addObject(sp);
+}
+void mh_add_plane(const float* normal, const float* origin, int material)
+{
+    Plane* pl = new Plane;
+    pl->setNormal(Vector3(normal[0], normal[1], normal[2])); pl->setOrigin(Vector3(origin[0], origin[1], origin[2])); pl->setMaterial(g_materials[material]);
+    g_scene->addObject(pl);
+}
+// 0 = use MIROGPU_DEVICES / the current device; else the scene is replicated on devices 0 .. n-1 at the next precalc
+void mh_set_device_count(int n)
+{
+    std::vector<int> d;
+    for (int k = 0; k < n; ++k) d.push_back(k);
+    g_scene->bvh().setDevices(d);
+}
+
 void mh_add_point_light(const float* pos, const float* color, float wattage)
 {
     PointLight* l = new PointLight;
@@ -106,6 +128,8 @@ double mh_precalc()
     g_prim_id.clear();
     const Objects* objs = g_scene->objects();
     for (size_t i = 0; i < objs->size(); ++i) g_prim_id[(*objs)[i]] = (int)i;
+    const Objects* ub = g_scene->unboundedObjects();   // planes are numbered after the bounded objects (as the checker drivers do)
+    for (size_t i = 0; i < ub->size(); ++i) g_prim_id[(*ub)[i]] = (int)(objs->size() + i);
     mirogpu_scene_info info;
     mirogpu_scene_info_get(g_scene->bvh().handle(), &info);
     return info.build_seconds + info.flatten_seconds + info.upload_seconds;

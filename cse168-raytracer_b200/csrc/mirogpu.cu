@@ -11,6 +11,7 @@
 #include <memory>
 #include <mutex>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include <cuda_runtime.h>
@@ -116,6 +117,11 @@ struct mirogpu_scene {
     void* d_nodes = nullptr;
     void* d_tris = nullptr;
     void* d_shade = nullptr;
+    void* d_planes = nullptr;              // 2 float4 per plane (unbounded objects, tested after the walk)
+    uint32_t non_triangles = 0;            // spheres + planes: their hit points need the ray (resolve)
+    std::vector<mirogpu_scene*> replicas;  // the other devices of a multi-device handle (this struct is the first device's replica)
+    cudaStream_t mstream = nullptr;        // multi-device render: this replica's stream and its "rows are in place" event
+    cudaEvent_t mevent = nullptr;
     mirogpu_material* d_materials = nullptr;
     uint32_t nmaterials = 0;
     mirogpu_light* d_lights = nullptr;
@@ -325,15 +331,110 @@ int mirogpu_device_count(int* count)
     return MIROGPU_OK;
 }
 
-int mirogpu_scene_create(const float* tri_vertices, const float* tri_normals, const uint32_t* material_ids, uint32_t ntris,
-                         const mirogpu_material* materials, uint32_t nmaterials, const mirogpu_build_options* opt,
-                         mirogpu_handle* out)
-{
-    if (!out) return fail(MIROGPU_ERR_INVALID_ARG, "out handle is NULL");
-    *out = nullptr;
-    if (ntris && !tri_vertices) return fail(MIROGPU_ERR_INVALID_ARG, "tri_vertices is NULL");
-    if (ntris >= (1u << 28) - 16u) return fail(MIROGPU_ERR_INVALID_ARG, "too many triangles (limit 2^28 - 16)");
+}  // extern "C"
+
+namespace {
+
+// What one build produces on the host; uploaded once per device of the handle.
+struct HostBuild {
     mirogpu_build_options o;
+    const void* node_src = nullptr; size_t node_bytes = 0;
+    std::vector<TriRecord> tris;
+    std::unique_ptr<float4[]> shade; size_t shade_count = 0;
+    std::vector<mirogpu_material> mats;
+    std::vector<float4> planes;   // 2 per plane: (normal, prim id bits) (origin, 0)
+    BinaryBvh bin; FlatBvh flat;
+    uint32_t nprims = 0, ntris = 0, nspheres = 0, nplanes = 0;
+    mirogpu_scene_info info{};
+    bool any_refractive = false, any_specular = false;
+};
+
+void apply_tuning_knobs(mirogpu_scene* h, int layout)
+{
+    if (layout == MIROGPU_LAYOUT_QBVH4 || layout == MIROGPU_LAYOUT_BVH4) { h->hyb_period = 2; h->hyb_min_idle = 6; }   // measured optimum of the four-wide steps
+    // QBVH4: one triangle per leaf phase, three node steps per vote, node steps while >= 20 lanes want one (7.28 -> 7.53 Grays/s);
+    // incoherent batches: one postponed leaf per lane, node steps while >= 24 lanes want one (bounce rays 7.17 -> 8.02 Grays/s with 48 registers)
+    if (layout == MIROGPU_LAYOUT_QBVH4) { h->hyb_pf = 16; h->hyb_nrep = 3; h->hyb_nmin = 20; h->hyb_pf_inc = 80; h->hyb_nmin_inc = 24; }
+    else h->hyb_nmin_inc = h->hyb_nmin;
+    if (const char* e = getenv("MIROGPU_POOL")) { const int v = atoi(e); if (v >= 32 && v <= 65536) h->hyb_pool = v; }
+    if (const char* e = getenv("MIROGPU_NREP")) h->hyb_nrep = atoi(e);
+    if (const char* e = getenv("MIROGPU_PPT")) { const int v = atoi(e); if (v >= 1 && v <= 64) h->packets_per_ticket = v; }
+    if (const char* e = getenv("MIROGPU_NMIN")) { const int v = atoi(e); if (v >= 1 && v <= 32) h->hyb_nmin = h->hyb_nmin_inc = v; }
+    if (const char* e = getenv("MIROGPU_NMIN_INC")) { const int v = atoi(e); if (v >= 1 && v <= 32) h->hyb_nmin_inc = v; }
+    if (const char* e = getenv("MIROGPU_PERIOD")) { const int v = atoi(e); if (v >= 1 && v <= 100000) h->hyb_period = v; }
+    if (const char* e = getenv("MIROGPU_PF")) h->hyb_pf = h->hyb_pf_inc = atoi(e);
+    if (const char* e = getenv("MIROGPU_PF_INC")) h->hyb_pf_inc = atoi(e);
+    if (const char* e = getenv("MIROGPU_MINB")) h->hyb_minb = atoi(e);
+    if (const char* e = getenv("MIROGPU_SHORT")) h->hyb_short = atoi(e);
+    if (const char* e = getenv("MIROGPU_STAGE")) h->hyb_stage = atoi(e);
+    if (const char* e = getenv("MIROGPU_MINIDLE")) { const int v = atoi(e); if (v >= 1 && v <= 32) h->hyb_min_idle = v; }
+}
+
+// Uploads one replica of the scene to `dev`.  lb: a tree built on that device (device builders), or NULL.
+int upload_replica(const HostBuild& hb, int dev, const LbvhOut* lb, mirogpu_scene** out)
+{
+    *out = nullptr;
+    CUDA_TRY(cudaSetDevice(dev));
+    mirogpu_scene* h = new (std::nothrow) mirogpu_scene;
+    if (!h) return fail(MIROGPU_ERR_OOM, "host allocation failed");
+    h->device = dev; h->layout = hb.o.layout;
+    {
+        int sms = 0;
+        const cudaError_t pe = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+        if (pe != cudaSuccess) { delete h; return fail(MIROGPU_ERR_CUDA, std::string("cudaDeviceGetAttribute: ") + cudaGetErrorString(pe)); }
+        h->sm_count = sms;
+    }
+    apply_tuning_knobs(h, hb.o.layout);
+    const bool device_built = lb != nullptr;
+    const size_t node_bytes = device_built ? lb->node_bytes : hb.node_bytes;
+    const size_t tri_bytes = device_built ? lb->tri_bytes : hb.tris.size() * sizeof(TriRecord), shade_bytes = hb.shade_count * sizeof(float4);
+    auto bail = [&](cudaError_t e, const char* what) {
+        std::string msg = std::string(what) + ": " + cudaGetErrorString(e);
+        mirogpu_scene_destroy(h);
+        return fail(e == cudaErrorMemoryAllocation ? MIROGPU_ERR_OOM : MIROGPU_ERR_CUDA, msg);
+    };
+    cudaError_t e;
+    // nodes and triangles share one allocation (the traversal working set is one address range)
+    const size_t node_span = device_built ? lb->node_span : (std::max<size_t>(node_bytes, 16) + 255) & ~(size_t)255;
+    if (device_built) h->d_nodes = lb->d_geom;
+    else if ((e = cudaMalloc(&h->d_nodes, node_span + std::max<size_t>(tri_bytes, 16))) != cudaSuccess) return bail(e, "cudaMalloc nodes + triangles");
+    h->d_tris = static_cast<char*>(h->d_nodes) + node_span;
+    h->node_bytes_dev = node_bytes; h->tri_bytes_dev = tri_bytes;
+    if ((e = cudaMalloc(&h->d_shade, std::max<size_t>(shade_bytes, 16))) != cudaSuccess) return bail(e, "cudaMalloc shading records");
+    if ((e = cudaMalloc(&h->d_materials, hb.mats.size() * sizeof(mirogpu_material))) != cudaSuccess) return bail(e, "cudaMalloc materials");
+    if ((e = cudaMalloc(&h->d_ticket, 64 * sizeof(unsigned long long))) != cudaSuccess) return bail(e, "cudaMalloc tickets");
+    if (!hb.planes.empty() && (e = cudaMalloc(&h->d_planes, hb.planes.size() * sizeof(float4))) != cudaSuccess) return bail(e, "cudaMalloc planes");
+    if (!device_built && node_bytes && (e = cudaMemcpy(h->d_nodes, hb.node_src, node_bytes, cudaMemcpyHostToDevice)) != cudaSuccess) return bail(e, "upload nodes");
+    if (!device_built && tri_bytes && (e = cudaMemcpy(h->d_tris, hb.tris.data(), tri_bytes, cudaMemcpyHostToDevice)) != cudaSuccess) return bail(e, "upload triangles");
+    if (shade_bytes && (e = cudaMemcpy(h->d_shade, hb.shade.get(), shade_bytes, cudaMemcpyHostToDevice)) != cudaSuccess) return bail(e, "upload shading records");
+    if ((e = cudaMemcpy(h->d_materials, hb.mats.data(), hb.mats.size() * sizeof(mirogpu_material), cudaMemcpyHostToDevice)) != cudaSuccess) return bail(e, "upload materials");
+    if (!hb.planes.empty() && (e = cudaMemcpy(h->d_planes, hb.planes.data(), hb.planes.size() * sizeof(float4), cudaMemcpyHostToDevice)) != cudaSuccess) return bail(e, "upload planes");
+    if ((e = cudaMemset(h->d_ticket, 0, 64 * sizeof(unsigned long long))) != cudaSuccess) return bail(e, "memset tickets");
+    h->nmaterials = (uint32_t)hb.mats.size();
+    h->any_refractive = hb.any_refractive; h->any_specular = hb.any_specular;
+    if ((e = cudaHostAlloc(&h->h_stats, 64 * sizeof(uint32_t), cudaHostAllocDefault)) != cudaSuccess) return bail(e, "cudaHostAlloc stats");
+    memset(h->h_stats, 0, 64 * sizeof(uint32_t));
+    h->ds.nodes = reinterpret_cast<const float4*>(h->d_nodes);
+    h->ds.tris = reinterpret_cast<const float4*>(h->d_tris);
+    h->ds.shade = reinterpret_cast<const float4*>(h->d_shade);
+    h->ds.planes = reinterpret_cast<const float4*>(h->d_planes);
+    h->ds.num_tris = hb.nprims;
+    h->ds.num_planes = hb.nplanes;
+    h->non_triangles = hb.nspheres + hb.nplanes;
+    h->info = hb.info;
+    *out = h;
+    return MIROGPU_OK;
+}
+
+int scene_create_impl(const mirogpu_scene_desc& d, const mirogpu_build_options* opt, mirogpu_handle* out)
+{
+    *out = nullptr;
+    const uint32_t ntris = d.ntris, nspheres = d.nspheres, nplanes = d.nplanes;
+    if (ntris && !d.tri_vertices) return fail(MIROGPU_ERR_INVALID_ARG, "tri_vertices is NULL");
+    if ((nspheres && !d.spheres) || (nplanes && !d.planes)) return fail(MIROGPU_ERR_INVALID_ARG, "sphere / plane array is NULL");
+    if ((uint64_t)ntris + nspheres + nplanes >= (1u << 28) - 16u) return fail(MIROGPU_ERR_INVALID_ARG, "too many primitives (limit 2^28 - 16)");
+    HostBuild hb;
+    mirogpu_build_options& o = hb.o;
     o.layout = MIROGPU_LAYOUT_QBVH4; o.max_leaf = 0; o.sah_bins = 32; o.device = -1; o.builder = MIROGPU_BUILDER_SAH_HOST;
     if (opt) o = *opt;
     if (const char* e = getenv("MIROGPU_BUILDER")) {   // tuning knob
@@ -341,7 +442,7 @@ int mirogpu_scene_create(const float* tri_vertices, const float* tri_normals, co
         else if (!strcmp(e, "ploc")) o.builder = MIROGPU_BUILDER_PLOC_DEVICE;
         if (o.builder != MIROGPU_BUILDER_SAH_HOST && o.layout != MIROGPU_LAYOUT_QBVH4) o.builder = MIROGPU_BUILDER_SAH_HOST;   // the knob only applies where it can
     }
-    const bool device_builder = o.builder == MIROGPU_BUILDER_LBVH_DEVICE || o.builder == MIROGPU_BUILDER_PLOC_DEVICE;
+    bool device_builder = o.builder == MIROGPU_BUILDER_LBVH_DEVICE || o.builder == MIROGPU_BUILDER_PLOC_DEVICE;
     if (o.builder != MIROGPU_BUILDER_SAH_HOST && !device_builder) return fail(MIROGPU_ERR_INVALID_ARG, "unknown builder");
     if (device_builder && o.layout != MIROGPU_LAYOUT_QBVH4) return fail(MIROGPU_ERR_INVALID_ARG, "the device builders emit the QBVH4 layout only");
     if (o.layout != MIROGPU_LAYOUT_BVH2 && o.layout != MIROGPU_LAYOUT_CWBVH8 && o.layout != MIROGPU_LAYOUT_BVH4 && o.layout != MIROGPU_LAYOUT_QBVH4)
@@ -357,58 +458,60 @@ int mirogpu_scene_create(const float* tri_vertices, const float* tri_normals, co
         (void)cudaGetLastError();
         return fail(MIROGPU_ERR_NO_DEVICE, "no CUDA device: mirogpu has no CPU path");
     }
-    int dev = o.device;
-    if (dev < 0) CUDA_TRY(cudaGetDevice(&dev));
-    if (dev >= ndev) return fail(MIROGPU_ERR_INVALID_ARG, "device ordinal out of range");
-    CUDA_TRY(cudaSetDevice(dev));
-
-    mirogpu_scene* h = new (std::nothrow) mirogpu_scene;
-    if (!h) return fail(MIROGPU_ERR_OOM, "host allocation failed");
-    h->device = dev; h->layout = o.layout;
-    {
-        int sms = 0;
-        const cudaError_t pe = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-        if (pe != cudaSuccess) { delete h; return fail(MIROGPU_ERR_CUDA, std::string("cudaDeviceGetAttribute: ") + cudaGetErrorString(pe)); }
-        h->sm_count = sms;
+    std::vector<int> devs;
+    if (d.devices && d.ndevices) {
+        for (uint32_t i = 0; i < d.ndevices; ++i) {
+            if (d.devices[i] < 0 || d.devices[i] >= ndev) return fail(MIROGPU_ERR_INVALID_ARG, "device ordinal out of range");
+            for (int q : devs) if (q == d.devices[i]) return fail(MIROGPU_ERR_INVALID_ARG, "device listed twice");
+            devs.push_back(d.devices[i]);
+        }
+    } else {
+        int dev = o.device;
+        if (dev < 0) CUDA_TRY(cudaGetDevice(&dev));
+        if (dev >= ndev) return fail(MIROGPU_ERR_INVALID_ARG, "device ordinal out of range");
+        devs.push_back(dev);
     }
-    if (o.layout == MIROGPU_LAYOUT_QBVH4 || o.layout == MIROGPU_LAYOUT_BVH4) { h->hyb_period = 2; h->hyb_min_idle = 6; }   // measured optimum of the four-wide steps
-    // QBVH4: one triangle per leaf phase, three node steps per vote, node steps while >= 20 lanes want one (7.28 -> 7.53 Grays/s)
-    // incoherent batches: one postponed leaf per lane, node steps while >= 24 lanes want one (bounce rays 7.17 -> 8.02 Grays/s with 48 registers)
-    if (o.layout == MIROGPU_LAYOUT_QBVH4) { h->hyb_pf = 16; h->hyb_nrep = 3; h->hyb_nmin = 20; h->hyb_pf_inc = 80; h->hyb_nmin_inc = 24; }
-    else h->hyb_nmin_inc = h->hyb_nmin;
-    if (const char* e = getenv("MIROGPU_POOL")) { const int v = atoi(e); if (v >= 32 && v <= 65536) h->hyb_pool = v; }
-    if (const char* e = getenv("MIROGPU_NREP")) h->hyb_nrep = atoi(e);
-    if (const char* e = getenv("MIROGPU_PPT")) { const int v = atoi(e); if (v >= 1 && v <= 64) h->packets_per_ticket = v; }
-    if (const char* e = getenv("MIROGPU_NMIN")) { const int v = atoi(e); if (v >= 1 && v <= 32) h->hyb_nmin = h->hyb_nmin_inc = v; }
-    if (const char* e = getenv("MIROGPU_NMIN_INC")) { const int v = atoi(e); if (v >= 1 && v <= 32) h->hyb_nmin_inc = v; }
-    if (const char* e = getenv("MIROGPU_PERIOD")) { const int v = atoi(e); if (v >= 1 && v <= 100000) h->hyb_period = v; }
-    if (const char* e = getenv("MIROGPU_PF")) h->hyb_pf = h->hyb_pf_inc = atoi(e);
-    if (const char* e = getenv("MIROGPU_PF_INC")) h->hyb_pf_inc = atoi(e);
-    if (const char* e = getenv("MIROGPU_MINB")) h->hyb_minb = atoi(e);
-    if (const char* e = getenv("MIROGPU_SHORT")) h->hyb_short = atoi(e);
-    if (const char* e = getenv("MIROGPU_STAGE")) h->hyb_stage = atoi(e);
-    if (const char* e = getenv("MIROGPU_MINIDLE")) { const int v = atoi(e); if (v >= 1 && v <= 32) h->hyb_min_idle = v; }
+    if (devs.size() > 16) return fail(MIROGPU_ERR_INVALID_ARG, "more than 16 devices");
+    CUDA_TRY(cudaSetDevice(devs[0]));
+    // spheres enter the builder as proxy triangles whose bounding box is the sphere's ([c - r, c + r] exactly; the builder
+    // pads it further); the device builders make their own triangle records, so a scene with spheres is built on the host
+    const uint32_t nleafprims = ntris + nspheres;
+    hb.ntris = ntris; hb.nspheres = nspheres; hb.nplanes = nplanes; hb.nprims = nleafprims + nplanes;
+    if (nspheres && device_builder) { device_builder = false; o.builder = MIROGPU_BUILDER_SAH_HOST; }
+    if (devs.size() > 1 && device_builder) { device_builder = false; o.builder = MIROGPU_BUILDER_SAH_HOST; }   // one host build, N uploads
+    std::vector<float> verts_all;
+    const float* verts = d.tri_vertices;
+    if (nspheres) {
+        verts_all.resize((size_t)nleafprims * 9);
+        if (ntris) memcpy(verts_all.data(), d.tri_vertices, (size_t)ntris * 9 * sizeof(float));
+        for (uint32_t i = 0; i < nspheres; ++i) {
+            const mirogpu_sphere& sp = d.spheres[i];
+            float* v = verts_all.data() + (size_t)(ntris + i) * 9;
+            for (int k = 0; k < 3; ++k) { v[k] = sp.center[k] - sp.radius; v[3 + k] = sp.center[k] + sp.radius; }
+            v[6] = sp.center[0] - sp.radius; v[7] = sp.center[1] + sp.radius; v[8] = sp.center[2] - sp.radius;
+        }
+        verts = verts_all.data();
+    }
 
-    // ---- device build (LBVH) -----------------------------------------------------------------------
+    // ---- device build (LBVH / PLOC; single device, triangles only) ------------------------------------------------------
     double t0 = now_s();
     LbvhOut lb;
     bool device_built = false;
     if (device_builder) {
-        const cudaError_t be = build_lbvh_device(tri_vertices, ntris, std::min(o.max_leaf, 4), lb, o.builder == MIROGPU_BUILDER_PLOC_DEVICE);
+        const cudaError_t be = build_lbvh_device(verts, ntris, std::min(o.max_leaf, 4), lb, o.builder == MIROGPU_BUILDER_PLOC_DEVICE);
         if (be == cudaErrorNotSupported) lb.d_geom = nullptr;   // the device builder gave up on this input (see lbvh_impl.cuh): use the host builder
-        else if (be != cudaSuccess) { delete h; return fail(be == cudaErrorMemoryAllocation ? MIROGPU_ERR_OOM : MIROGPU_ERR_CUDA, std::string("device BVH build: ") + cudaGetErrorString(be)); }
+        else if (be != cudaSuccess) return fail(be == cudaErrorMemoryAllocation ? MIROGPU_ERR_OOM : MIROGPU_ERR_CUDA, std::string("device BVH build: ") + cudaGetErrorString(be));
         else if (lb.max_stack <= MIRO_STACK4) device_built = true;
         else { cudaFree(lb.d_geom); lb.d_geom = nullptr; }   // a tree too deep for the kernels' stacks: use the host builder
     }
     // ---- host build ------------------------------------------------------------------------------
-    BinaryBvh bin;
-    FlatBvh flat;
+    BinaryBvh& bin = hb.bin;
+    FlatBvh& flat = hb.flat;
     double t1 = now_s(), t2 = t1;
     const bool wide4 = o.layout == MIROGPU_LAYOUT_BVH4 || o.layout == MIROGPU_LAYOUT_QBVH4;
-    const void* node_src = nullptr; size_t node_bytes = 0;
     if (!device_built) {
         t0 = now_s();
-        bin = build_binary_sah(tri_vertices, ntris, o.max_leaf, o.sah_bins);
+        bin = build_binary_sah(verts, nleafprims, o.max_leaf, o.sah_bins);
         t1 = now_s();
         if (o.layout == MIROGPU_LAYOUT_BVH2) flatten_bvh2(bin, flat);
         else if (o.layout == MIROGPU_LAYOUT_BVH4) flatten_bvh4(bin, flat);
@@ -417,30 +520,41 @@ int mirogpu_scene_create(const float* tri_vertices, const float* tri_normals, co
         // a walk pushes at most one entry per level (BVH2 / CWBVH8 groups) resp. flat.max_stack entries (BVH4): refuse a tree the
         // kernels' fixed per-thread stacks cannot hold rather than overrun them (the builder's depth cap makes this unreachable
         // below ~16 M triangles)
-        if (!wide4 && bin.max_depth > MIRO_STACK) { delete h; return fail(MIROGPU_ERR_INVALID_ARG, "tree deeper than the kernels' traversal stack"); }
-        if (wide4 && flat.max_stack > MIRO_STACK4) { delete h; return fail(MIROGPU_ERR_INVALID_ARG, "BVH4 tree needs a deeper traversal stack than the kernels carry"); }
-        make_tri_records(tri_vertices, flat.order, h->h_tris);
+        if (!wide4 && bin.max_depth > MIRO_STACK) return fail(MIROGPU_ERR_INVALID_ARG, "tree deeper than the kernels' traversal stack");
+        if (wide4 && flat.max_stack > MIRO_STACK4) return fail(MIROGPU_ERR_INVALID_ARG, "BVH4 tree needs a deeper traversal stack than the kernels carry");
+        make_tri_records(verts, flat.order, hb.tris);
+        // sphere slots: (centre, prim id) (radius, 0, 0, 0) (0, 0, 0, 0) (0, kind = 1, 0, 0) -- see prim_test in traverse.cuh
+        if (nspheres)
+            for (TriRecord& r : hb.tris)
+                if (r.prim_id >= ntris) {
+                    const mirogpu_sphere& sp = d.spheres[r.prim_id - ntris];
+                    const uint32_t id = r.prim_id;
+                    memset(&r, 0, sizeof r);
+                    r.ax = sp.center[0]; r.ay = sp.center[1]; r.az = sp.center[2]; r.prim_id = id;
+                    r.e1x = sp.radius; r.pad[0] = 1.0f;
+                }
         t2 = now_s();
-        if (o.layout == MIROGPU_LAYOUT_BVH2) { node_src = flat.nodes2.data(); node_bytes = flat.nodes2.size() * sizeof(Bvh2Node); }
-        else if (o.layout == MIROGPU_LAYOUT_BVH4) { node_src = flat.nodes4.data(); node_bytes = flat.nodes4.size() * sizeof(Bvh4Node); }
-        else if (o.layout == MIROGPU_LAYOUT_QBVH4) { node_src = flat.nodesq.data(); node_bytes = flat.nodesq.size() * sizeof(Qbvh4Node); }
-        else { node_src = flat.nodes8.data(); node_bytes = flat.nodes8.size() * sizeof(Cwbvh8Node); }
-        h->h_nodes.assign((const uint8_t*)node_src, (const uint8_t*)node_src + node_bytes);
-    } else {
-        node_bytes = lb.node_bytes;   // the host copies for mirogpu_debug_copy_* are fetched from the device on demand
+        if (o.layout == MIROGPU_LAYOUT_BVH2) { hb.node_src = flat.nodes2.data(); hb.node_bytes = flat.nodes2.size() * sizeof(Bvh2Node); }
+        else if (o.layout == MIROGPU_LAYOUT_BVH4) { hb.node_src = flat.nodes4.data(); hb.node_bytes = flat.nodes4.size() * sizeof(Bvh4Node); }
+        else if (o.layout == MIROGPU_LAYOUT_QBVH4) { hb.node_src = flat.nodesq.data(); hb.node_bytes = flat.nodesq.size() * sizeof(Qbvh4Node); }
+        else { hb.node_src = flat.nodes8.data(); hb.node_bytes = flat.nodes8.size() * sizeof(Cwbvh8Node); }
     }
 
-    // shading records in prim-id order: (A, material) e1 e2 nA nB nC -- 96 bytes per triangle, written by all host threads
-    // (133 MB for the bench scene: a single thread spends longer here than the device builders spend on the whole tree)
-    const size_t shade_count = (size_t)ntris * 6;
-    std::unique_ptr<float4[]> shade(new float4[std::max<size_t>(shade_count, 1)]);
+    // shading records in prim-id order: (A, material) (e1, kind) e2 nA nB nC -- 96 bytes per primitive, written by all host threads
+    // (133 MB for the bench scene: a single thread spends longer here than the device builders spend on the whole tree).
+    // kind (bits of e1.w): 0 triangle, 1 sphere ((centre, material) (radius, 1)), 2 plane ((origin, material) (-, 2) - normal in the nA slot)
+    const uint32_t nmat_eff = std::max(d.materials ? d.nmaterials : 0u, 1u);   // no table = one white Lambert
+    hb.shade_count = (size_t)hb.nprims * 6;
+    hb.shade.reset(new float4[std::max<size_t>(hb.shade_count, 1)]);
+    float4* shade = hb.shade.get();
     bool bad_material = false;
+    const float* tri_vertices = d.tri_vertices; const float* tri_normals = d.tri_normals; const uint32_t* material_ids = d.tri_material_ids;
 #pragma omp parallel for schedule(static) reduction(|| : bad_material)
     for (int64_t ii = 0; ii < (int64_t)ntris; ++ii) {
         const size_t i = (size_t)ii;
         const float* v = tri_vertices + 9 * i;
         uint32_t m = material_ids ? material_ids[i] : 0u;
-        if (m >= std::max(materials ? nmaterials : 0u, 1u)) { bad_material = true; m = 0u; }   // no table = one white Lambert
+        if (m >= nmat_eff) { bad_material = true; m = 0u; }
         float4 A = make_float4(v[0], v[1], v[2], 0.f);
         memcpy(&A.w, &m, 4);
         shade[6 * i + 0] = A;
@@ -451,56 +565,46 @@ int mirogpu_scene_create(const float* tri_vertices, const float* tri_normals, co
             else shade[6 * i + 3 + k] = make_float4(0.f, 1.f, 0.f, 0.f);
         }
     }
+    auto kind_bits = [](uint32_t k) { float f; memcpy(&f, &k, 4); return f; };
+    for (uint32_t i = 0; i < nspheres; ++i) {
+        const mirogpu_sphere& sp = d.spheres[i];
+        uint32_t m = sp.material_id;
+        if (m >= nmat_eff) { bad_material = true; m = 0u; }
+        float4* r = shade + 6 * (size_t)(ntris + i);
+        for (int k = 0; k < 6; ++k) r[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+        r[0] = make_float4(sp.center[0], sp.center[1], sp.center[2], 0.f); memcpy(&r[0].w, &m, 4);
+        r[1] = make_float4(sp.radius, 0.f, 0.f, kind_bits(1u));
+    }
+    for (uint32_t i = 0; i < nplanes; ++i) {
+        const mirogpu_plane& pl = d.planes[i];
+        uint32_t m = pl.material_id;
+        if (m >= nmat_eff) { bad_material = true; m = 0u; }
+        const uint32_t id = nleafprims + i;
+        float4* r = shade + 6 * (size_t)id;
+        for (int k = 0; k < 6; ++k) r[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+        r[0] = make_float4(pl.origin[0], pl.origin[1], pl.origin[2], 0.f); memcpy(&r[0].w, &m, 4);
+        r[1] = make_float4(0.f, 0.f, 0.f, kind_bits(2u));
+        r[3] = make_float4(pl.normal[0], pl.normal[1], pl.normal[2], 0.f);
+        float4 n4 = make_float4(pl.normal[0], pl.normal[1], pl.normal[2], 0.f); memcpy(&n4.w, &id, 4);
+        hb.planes.push_back(n4);
+        hb.planes.push_back(make_float4(pl.origin[0], pl.origin[1], pl.origin[2], 0.f));
+    }
     if (bad_material) {
         if (device_built && lb.d_geom) cudaFree(lb.d_geom);
-        delete h;
         return fail(MIROGPU_ERR_INVALID_ARG, "material id out of range");
     }
-    std::vector<mirogpu_material> mats;
-    if (materials && nmaterials) mats.assign(materials, materials + nmaterials);
+    if (d.materials && d.nmaterials) hb.mats.assign(d.materials, d.materials + d.nmaterials);
     else {
         mirogpu_material m; memset(&m, 0, sizeof m);
         m.kd[0] = m.kd[1] = m.kd[2] = 1.f; m.shininess = 1.f; m.refract_index = 1.f;  // Lambert(Vector3(1)) = Phong defaults
-        mats.push_back(m);
+        hb.mats.push_back(m);
+    }
+    for (const mirogpu_material& m : hb.mats) {
+        hb.any_refractive |= m.kt[0] > 0.f || m.kt[1] > 0.f || m.kt[2] > 0.f;
+        hb.any_specular |= m.ks[0] > 0.f || m.ks[1] > 0.f || m.ks[2] > 0.f;
     }
 
-    // ---- upload ------------------------------------------------------------------------------------
-    const size_t tri_bytes = device_built ? lb.tri_bytes : h->h_tris.size() * sizeof(TriRecord), shade_bytes = shade_count * sizeof(float4);
-    auto bail = [&](cudaError_t e, const char* what) {
-        std::string msg = std::string(what) + ": " + cudaGetErrorString(e);
-        mirogpu_scene_destroy(h);
-        return fail(e == cudaErrorMemoryAllocation ? MIROGPU_ERR_OOM : MIROGPU_ERR_CUDA, msg);
-    };
-    cudaError_t e;
-    // nodes and triangles share one allocation (the traversal working set is one address range)
-    const size_t node_span = device_built ? lb.node_span : (std::max<size_t>(node_bytes, 16) + 255) & ~(size_t)255;
-    if (device_built) h->d_nodes = lb.d_geom;
-    else if ((e = cudaMalloc(&h->d_nodes, node_span + std::max<size_t>(tri_bytes, 16))) != cudaSuccess) return bail(e, "cudaMalloc nodes + triangles");
-    h->d_tris = static_cast<char*>(h->d_nodes) + node_span;
-    h->node_bytes_dev = node_bytes; h->tri_bytes_dev = tri_bytes;
-    if ((e = cudaMalloc(&h->d_shade, std::max<size_t>(shade_bytes, 16))) != cudaSuccess) return bail(e, "cudaMalloc shading records");
-    if ((e = cudaMalloc(&h->d_materials, mats.size() * sizeof(mirogpu_material))) != cudaSuccess) return bail(e, "cudaMalloc materials");
-    if ((e = cudaMalloc(&h->d_ticket, 64 * sizeof(unsigned long long))) != cudaSuccess) return bail(e, "cudaMalloc tickets");
-    if (!device_built && node_bytes && (e = cudaMemcpy(h->d_nodes, node_src, node_bytes, cudaMemcpyHostToDevice)) != cudaSuccess) return bail(e, "upload nodes");
-    if (!device_built && tri_bytes && (e = cudaMemcpy(h->d_tris, h->h_tris.data(), tri_bytes, cudaMemcpyHostToDevice)) != cudaSuccess) return bail(e, "upload triangles");
-    if (shade_bytes && (e = cudaMemcpy(h->d_shade, shade.get(), shade_bytes, cudaMemcpyHostToDevice)) != cudaSuccess) return bail(e, "upload shading records");
-    if ((e = cudaMemcpy(h->d_materials, mats.data(), mats.size() * sizeof(mirogpu_material), cudaMemcpyHostToDevice)) != cudaSuccess) return bail(e, "upload materials");
-    if ((e = cudaMemset(h->d_ticket, 0, 64 * sizeof(unsigned long long))) != cudaSuccess) return bail(e, "memset tickets");
-    h->nmaterials = (uint32_t)mats.size();
-    for (const mirogpu_material& m : mats) {
-        h->any_refractive |= m.kt[0] > 0.f || m.kt[1] > 0.f || m.kt[2] > 0.f;
-        h->any_specular |= m.ks[0] > 0.f || m.ks[1] > 0.f || m.ks[2] > 0.f;
-    }
-    if ((e = cudaHostAlloc(&h->h_stats, 64 * sizeof(uint32_t), cudaHostAllocDefault)) != cudaSuccess) return bail(e, "cudaHostAlloc stats");
-    memset(h->h_stats, 0, 64 * sizeof(uint32_t));
-    double t3 = now_s();
-
-    h->ds.nodes = reinterpret_cast<const float4*>(h->d_nodes);
-    h->ds.tris = reinterpret_cast<const float4*>(h->d_tris);
-    h->ds.shade = reinterpret_cast<const float4*>(h->d_shade);
-    h->ds.num_tris = ntris;
-
-    mirogpu_scene_info& in = h->info;
+    mirogpu_scene_info& in = hb.info;
     in.num_triangles = ntris;
     in.num_nodes = device_built ? lb.num_nodes : (uint32_t)(o.layout == MIROGPU_LAYOUT_BVH2 ? flat.nodes2.size() : wide4 ? flat.nodes4.size() : flat.nodes8.size());
     in.num_binary_nodes = device_built ? (ntris ? 2 * ntris - 1 : 0) : (uint32_t)bin.nodes.size();
@@ -508,23 +612,88 @@ int mirogpu_scene_create(const float* tri_vertices, const float* tri_normals, co
     in.max_depth = device_built ? lb.max_depth : (o.layout == MIROGPU_LAYOUT_BVH2 ? bin.max_depth : flat.max_depth);
     in.builder = device_built ? o.builder : MIROGPU_BUILDER_SAH_HOST;
     in.layout = o.layout;
-    in.node_bytes = node_bytes; in.triangle_bytes = tri_bytes; in.shading_bytes = shade_bytes;
-    in.build_seconds = device_built ? lb.seconds : t1 - t0; in.flatten_seconds = device_built ? 0.0 : t2 - t1; in.upload_seconds = t3 - t2;
+    in.node_bytes = device_built ? lb.node_bytes : hb.node_bytes;
+    in.triangle_bytes = device_built ? lb.tri_bytes : hb.tris.size() * sizeof(TriRecord); in.shading_bytes = hb.shade_count * sizeof(float4);
+    in.build_seconds = device_built ? lb.seconds : t1 - t0; in.flatten_seconds = device_built ? 0.0 : t2 - t1;
     for (int k = 0; k < 3; ++k) { in.bounds_min[k] = device_built ? lb.lo[k] : flat.root.lo[k]; in.bounds_max[k] = device_built ? lb.hi[k] : flat.root.hi[k]; }
-    *out = h;
+
+    // ---- upload: one replica per device ---------------------------------------------------------------------------------
+    const double tu = now_s();
+    mirogpu_scene* primary = nullptr;
+    int rc = upload_replica(hb, devs[0], device_built ? &lb : nullptr, &primary);
+    if (rc != MIROGPU_OK) { if (device_built && lb.d_geom && !primary) cudaFree(lb.d_geom); return rc; }
+    if (!device_built) { primary->h_nodes.assign((const uint8_t*)hb.node_src, (const uint8_t*)hb.node_src + hb.node_bytes); primary->h_tris = hb.tris; }
+    for (size_t k = 1; k < devs.size(); ++k) {
+        mirogpu_scene* rep = nullptr;
+        rc = upload_replica(hb, devs[k], nullptr, &rep);
+        if (rc != MIROGPU_OK) { const std::string msg = g_last_error; mirogpu_scene_destroy(primary); return fail(rc, msg); }
+        primary->replicas.push_back(rep);
+    }
+    // peer access between the replicas' devices (framebuffer gather over NVLink); failure only means staged copies
+    for (size_t a2 = 0; a2 < devs.size(); ++a2)
+        for (size_t b2 = 0; b2 < devs.size(); ++b2)
+            if (a2 != b2) {
+                int can = 0;
+                if (cudaDeviceCanAccessPeer(&can, devs[a2], devs[b2]) == cudaSuccess && can) {
+                    cudaSetDevice(devs[a2]);
+                    const cudaError_t pe = cudaDeviceEnablePeerAccess(devs[b2], 0);
+                    if (pe != cudaSuccess) (void)cudaGetLastError();   // already enabled is fine
+                }
+            }
+    cudaSetDevice(devs[0]);
+    primary->info.upload_seconds = now_s() - tu;
+    *out = primary;
+    return MIROGPU_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int mirogpu_scene_create(const float* tri_vertices, const float* tri_normals, const uint32_t* material_ids, uint32_t ntris,
+                         const mirogpu_material* materials, uint32_t nmaterials, const mirogpu_build_options* opt,
+                         mirogpu_handle* out)
+{
+    if (!out) return fail(MIROGPU_ERR_INVALID_ARG, "out handle is NULL");
+    mirogpu_scene_desc d; memset(&d, 0, sizeof d);
+    d.tri_vertices = tri_vertices; d.tri_normals = tri_normals; d.tri_material_ids = material_ids; d.ntris = ntris;
+    d.materials = materials; d.nmaterials = nmaterials;
+    return scene_create_impl(d, opt, out);
+}
+
+int mirogpu_scene_create_ex(const mirogpu_scene_desc* desc, const mirogpu_build_options* opt, mirogpu_handle* out)
+{
+    if (!out) return fail(MIROGPU_ERR_INVALID_ARG, "out handle is NULL");
+    *out = nullptr;
+    if (!desc) return fail(MIROGPU_ERR_INVALID_ARG, "desc is NULL");
+    return scene_create_impl(*desc, opt, out);
+}
+
+int mirogpu_scene_devices(mirogpu_handle h, int32_t* devices, uint32_t capacity, uint32_t* ndevices)
+{
+    if (!h || !ndevices) return fail(MIROGPU_ERR_INVALID_ARG, "NULL argument");
+    *ndevices = 1u + (uint32_t)h->replicas.size();
+    if (devices) {
+        if (capacity > 0) devices[0] = h->device;
+        for (size_t k = 0; k < h->replicas.size() && k + 1 < capacity; ++k) devices[k + 1] = h->replicas[k]->device;
+    }
     return MIROGPU_OK;
 }
 
 int mirogpu_scene_destroy(mirogpu_handle h)
 {
     if (!h) return MIROGPU_OK;
+    for (mirogpu_scene* r : h->replicas) mirogpu_scene_destroy(r);
+    h->replicas.clear();
     cudaSetDevice(h->device);
     cudaFree(h->d_nodes); cudaFree(h->d_shade); cudaFree(h->d_materials);   // d_tris lives inside d_nodes's allocation
-    cudaFree(h->d_lights); cudaFree(h->d_ticket);
+    cudaFree(h->d_lights); cudaFree(h->d_ticket); cudaFree(h->d_planes);
     if (h->h_stats) cudaFreeHost(h->h_stats);
     for (int i = 0; i < 2; ++i) h->pm[i].release();
     for (auto& sl : h->slots) sl->release();
     h->scratch.release();
+    if (h->mevent) cudaEventDestroy(h->mevent);
+    if (h->mstream) cudaStreamDestroy(h->mstream);
     (void)cudaGetLastError();
     delete h;
     return MIROGPU_OK;
@@ -540,6 +709,7 @@ int mirogpu_scene_info_get(mirogpu_handle h, mirogpu_scene_info* info)
 int mirogpu_scene_set_lights(mirogpu_handle h, const mirogpu_light* lights, uint32_t nlights)
 {
     if (!h || (nlights && !lights)) return fail(MIROGPU_ERR_INVALID_ARG, "NULL argument");
+    for (mirogpu_scene* r : h->replicas) { const int rc = mirogpu_scene_set_lights(r, lights, nlights); if (rc != MIROGPU_OK) return rc; }
     CUDA_TRY(cudaSetDevice(h->device));
     std::lock_guard<std::mutex> lk(h->mtx);
     cudaFree(h->d_lights); h->d_lights = nullptr; h->nlights = 0; h->h_lights.clear();
@@ -685,9 +855,21 @@ int mirogpu_resolve_hits_device(mirogpu_handle h, const mirogpu_hit* d_hits, siz
                                 uint32_t* d_material, void* cuda_stream)
 {
     if (!h || (n && !d_hits)) return fail(MIROGPU_ERR_INVALID_ARG, "NULL argument");
+    if (h->non_triangles) return fail(MIROGPU_ERR_INVALID_ARG, "the scene holds spheres / planes: their hit point is o + t d, use mirogpu_resolve_hits_rays_device");
     if (n == 0) return MIROGPU_OK;
     CUDA_TRY(cudaSetDevice(h->device));
-    k_resolve_hits<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)cuda_stream>>>(h->ds, d_hits, n, d_P, d_N, d_material);
+    k_resolve_hits<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)cuda_stream>>>(h->ds, nullptr, d_hits, n, d_P, d_N, d_material);
+    CUDA_TRY(cudaGetLastError());
+    return MIROGPU_OK;
+}
+
+int mirogpu_resolve_hits_rays_device(mirogpu_handle h, const mirogpu_ray* d_rays, const mirogpu_hit* d_hits, size_t n, float* d_P,
+                                     float* d_N, uint32_t* d_material, void* cuda_stream)
+{
+    if (!h || (n && (!d_hits || !d_rays))) return fail(MIROGPU_ERR_INVALID_ARG, "NULL argument");
+    if (n == 0) return MIROGPU_OK;
+    CUDA_TRY(cudaSetDevice(h->device));
+    k_resolve_hits<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)cuda_stream>>>(h->ds, d_rays, d_hits, n, d_P, d_N, d_material);
     CUDA_TRY(cudaGetLastError());
     return MIROGPU_OK;
 }
@@ -797,7 +979,8 @@ int mirogpu_render_device(mirogpu_handle h, const mirogpu_camera* cam, const mir
     if (!h || !cam || !p || !d_rgb) return fail(MIROGPU_ERR_INVALID_ARG, "NULL argument");
     CUDA_TRY(cudaSetDevice(h->device));
     std::string err;
-    const int rc = render_device(h, *cam, *p, d_rgb, nullptr, (cudaStream_t)cuda_stream, err);
+    const int rc = (!h->replicas.empty() && p->row_stride == 1) ? render_multi(h, *cam, *p, nullptr, nullptr, d_rgb, (cudaStream_t)cuda_stream, err)
+                                                                 : render_device(h, *cam, *p, d_rgb, nullptr, (cudaStream_t)cuda_stream, err);
     return rc == MIROGPU_OK ? rc : fail(rc, err);
 }
 
@@ -906,6 +1089,7 @@ int mirogpu_photon_trace(mirogpu_handle h, int light_index, int caustic, uint32_
 int mirogpu_photon_upload(mirogpu_handle h, int which, const void* photons, int stored)
 {
     if (!h || which < 0 || which > 1 || stored < 0 || (stored && !photons)) return fail(MIROGPU_ERR_INVALID_ARG, "bad argument");
+    for (mirogpu_scene* r : h->replicas) { const int rc = mirogpu_photon_upload(r, which, photons, stored); if (rc != MIROGPU_OK) return rc; }
     CUDA_TRY(cudaSetDevice(h->device));
     std::lock_guard<std::mutex> lk(h->mtx);
     std::string err;
@@ -916,6 +1100,7 @@ int mirogpu_photon_upload(mirogpu_handle h, int which, const void* photons, int 
 int mirogpu_photon_set_exact(mirogpu_handle h, int which, int exact)
 {
     if (!h || which < 0 || which > 1) return fail(MIROGPU_ERR_INVALID_ARG, "bad argument");
+    for (mirogpu_scene* r : h->replicas) mirogpu_photon_set_exact(r, which, exact);
     std::lock_guard<std::mutex> lk(h->mtx);
     h->pm[which].exact = exact != 0;
     return MIROGPU_OK;

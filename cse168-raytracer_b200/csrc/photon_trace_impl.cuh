@@ -74,7 +74,7 @@ __global__ void __launch_bounds__(128) k_photon_trace(DeviceScene s, const mirog
         trace_one<LAYOUT, false, false>(s, r, best, nullptr);
         if (best.prim == MIROGPU_MISS) break;
         mirogpu_hit h; h.t = best.t; h.prim_id = best.prim; h.beta = best.beta; h.gamma = best.gamma;
-        const SurfacePoint sp = resolve_hit(s, h);
+        const SurfacePoint sp = resolve_hit(load_shade_record(s, h.prim_id), h, r);
         const mirogpu_material m = mats[sp.material];
         float u[4];
         uniform4(em.seed, e, (uint32_t)depth, 3, u);

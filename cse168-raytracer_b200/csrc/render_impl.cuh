@@ -183,7 +183,7 @@ __device__ __forceinline__ bool shade_item(const WaveParams& p, const Queue& cur
         return false;
     }
     mirogpu_hit h; h.t = hv.x; h.prim_id = __float_as_uint(hv.y); h.beta = hv.z; h.gamma = hv.w;
-    const SurfacePoint sp = resolve_hit(rec, h);
+    const SurfacePoint sp = resolve_hit(rec, h, ray);
     const mirogpu_material m = p.mats[sp.material];
     const float rd[3] = {ray.dx, ray.dy, ray.dz};
     float direct[3] = {0.f, 0.f, 0.f};
@@ -351,7 +351,7 @@ __global__ void __launch_bounds__(256) k_shadow_accumulate(WaveParams p, const m
     float intensity = 1.f;
     if (__float_as_uint(hv.y) != MIROGPU_MISS) {
         mirogpu_hit h; h.t = hv.x; h.prim_id = __float_as_uint(hv.y); h.beta = hv.z; h.gamma = hv.w;
-        const SurfacePoint sp = resolve_hit(p.ds, h);
+        const SurfacePoint sp = resolve_hit(load_shade_record(p.ds, h.prim_id), h, r);
         const mirogpu_material m = p.mats[sp.material];
         if (!(m.kt[0] > 0.f || m.kt[1] > 0.f || m.kt[2] > 0.f)) return;      // opaque occluder
         const float l[3] = {r.dx, r.dy, r.dz};
@@ -551,7 +551,8 @@ __global__ void __launch_bounds__(MIRO_BW_THREADS) k_bounce_wave0(WaveParams p, 
                     rd[0] = xmul(rd[0], inv); rd[1] = xmul(rd[1], inv); rd[2] = xmul(rd[2], inv);
                 }
                 mirogpu_hit h; h.t = hv[k].x; h.prim_id = __float_as_uint(hv[k].y); h.beta = hv[k].z; h.gamma = hv[k].w;
-                const SurfacePoint sp = resolve_hit(rec[k], h);
+                const SurfacePoint sp = record_kind(rec[k]) == 0u ? resolve_hit(rec[k], h)
+                                                                  : resolve_hit_analytic(rec[k], h, cb.eye[0], cb.eye[1], cb.eye[2], rd[0], rd[1], rd[2]);
                 const mirogpu_material m = p.mats[sp.material];
                 float direct[3] = {0.f, 0.f, 0.f};
                 for (uint32_t li = 0; li < p.nlights; ++li) {
@@ -615,7 +616,7 @@ __global__ void __launch_bounds__(MIRO_BW_THREADS) k_bounce_wave1(WaveParams p, 
             const float4 dv = __ldcs(reinterpret_cast<const float4*>(rays + i) + 1);
             const float rd[3] = {dv.x, dv.y, dv.z};
             mirogpu_hit h; h.t = hv[k].x; h.prim_id = __float_as_uint(hv[k].y); h.beta = hv[k].z; h.gamma = hv[k].w;
-            const SurfacePoint sp = resolve_hit(rec[k], h);
+            const SurfacePoint sp = resolve_hit(rec[k], h, rays + i);
             const mirogpu_material m = p.mats[sp.material];
             float direct[3] = {0.f, 0.f, 0.f};
             for (uint32_t li = 0; li < p.nlights; ++li) {
@@ -868,10 +869,133 @@ int render_device(mirogpu_scene* h, const mirogpu_camera& cam, const mirogpu_ren
 #undef RT
 }
 
+// ---- one handle, several devices: Scene::raytraceImage sharded by image rows -----------------------------------
+// Replica k of N renders the rows row_begin + k + j N of the call's range on its own device and stream (the scene is replicated,
+// random numbers are keyed by frame pixel, so the frame equals the one-device frame bit for bit).  The tone map's one frame-wide
+// number -- the largest non-NaN value (Scene.cpp:157-164) -- is reduced per device, combined on the host (N floats), and
+// each device maps its own rows.  Host framebuffer: every device copies its rows straight into the caller's buffer (N DMA
+// engines in parallel).  Device framebuffer: the rows are gathered into the first device's buffer by peer copies (NVLink).
+mirogpu_scene* replica_of(mirogpu_scene* h, size_t k) { return k == 0 ? h : h->replicas[k - 1]; }
+
+cudaError_t replica_stream(mirogpu_scene* r)
+{
+    if (r->mstream) return cudaSuccess;
+    cudaError_t e = cudaStreamCreateWithFlags(&r->mstream, cudaStreamNonBlocking);
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&r->mevent, cudaEventDisableTiming);
+    return e;
+}
+
+// Phase 1 on every replica: float rows into its own full-frame buffer (scratch 13), the maximum of its rows into pinned memory.
+int render_multi_phase1(mirogpu_scene* h, const mirogpu_camera& cam, const mirogpu_render_params& rp, std::string& err)
+{
+    const size_t N = 1 + h->replicas.size();
+    const size_t npx = (size_t)rp.width * rp.height;
+    const bool dynamic_waves = rp.mode == MIROGPU_RENDER_WHITTED && (h->any_specular || h->any_refractive);
+    std::vector<int> rcs(N, MIROGPU_OK);
+    std::vector<std::string> errs(N);
+    auto work = [&](size_t k) {
+        mirogpu_scene* r = replica_of(h, k);
+        cudaError_t e = cudaSetDevice(r->device);
+        if (e == cudaSuccess) e = replica_stream(r);
+        if (e == cudaSuccess) { std::lock_guard<std::mutex> lk(r->mtx); e = r->scratch.ensure(13, npx * 12); if (e == cudaSuccess) e = r->scratch.ensure(14, npx * 3); if (e == cudaSuccess) e = r->scratch.ensure(15, 64); }
+        if (e != cudaSuccess) { errs[k] = std::string("multi-device render setup: ") + cudaGetErrorString(e); rcs[k] = MIROGPU_ERR_CUDA; return; }
+        mirogpu_render_params sub = rp;
+        sub.row_stride = (int)N; sub.row_phase = (int)k; sub.tonemap = 0;
+        float* d_rgb = reinterpret_cast<float*>(r->scratch.buf[13]);
+        rcs[k] = render_device(r, cam, sub, d_rgb, nullptr, r->mstream, errs[k]);
+        if (rcs[k] != MIROGPU_OK) return;
+        // this replica's maximum (render_device's own reduction lives in its scratch; redo it over the rows into buf[15])
+        float* d_max = reinterpret_cast<float*>(r->scratch.buf[15]);
+        const float ninf = -INFINITY;
+        const int first_row = rp.row_begin + (int)k;
+        const int nrows = first_row < rp.row_end ? (rp.row_end - first_row + (int)N - 1) / (int)N : 0;
+        e = cudaMemcpyAsync(d_max, &ninf, 4, cudaMemcpyHostToDevice, r->mstream);
+        const size_t nvals = (size_t)nrows * rp.width * 3;
+        if (e == cudaSuccess && nvals) k_frame_max_rows<<<(unsigned)((nvals + 255) / 256), 256, 0, r->mstream>>>(d_rgb, rp.width, first_row, (int)N, nrows, d_max);
+        if (e == cudaSuccess) e = cudaMemcpyAsync(r->h_stats + 32, d_max, 4, cudaMemcpyDeviceToHost, r->mstream);
+        if (e != cudaSuccess) { errs[k] = std::string("multi-device render: ") + cudaGetErrorString(e); rcs[k] = MIROGPU_ERR_CUDA; }
+    };
+    if (dynamic_waves) {   // wave sizes are read back per wave: one host thread per device so the round trips overlap
+        std::vector<std::thread> th;
+        for (size_t k = 0; k < N; ++k) th.emplace_back(work, k);
+        for (auto& t : th) t.join();
+    } else {
+        for (size_t k = 0; k < N; ++k) work(k);   // everything is asynchronous: issue device after device
+    }
+    for (size_t k = 0; k < N; ++k) if (rcs[k] != MIROGPU_OK) { err = errs[k]; return rcs[k]; }
+    return MIROGPU_OK;
+}
+
+int render_multi(mirogpu_scene* h, const mirogpu_camera& cam, const mirogpu_render_params& rp, float* rgb_out, unsigned char* rgb8_out,
+                 float* d_rgb_primary, cudaStream_t st_primary, std::string& err)
+{
+    if (rp.width <= 0 || rp.height <= 0 || rp.row_begin < 0 || rp.row_end > rp.height || rp.row_begin > rp.row_end) { err = "bad render parameters"; return MIROGPU_ERR_INVALID_ARG; }
+    const size_t N = 1 + h->replicas.size();
+    int rc = render_multi_phase1(h, cam, rp, err);
+    if (rc != MIROGPU_OK) return rc;
+    cudaError_t e = cudaSuccess;
+    float gmax = -INFINITY;
+    uint64_t rays = 0, launches = 0;
+    for (size_t k = 0; k < N && e == cudaSuccess; ++k) {
+        mirogpu_scene* r = replica_of(h, k);
+        cudaSetDevice(r->device);
+        e = cudaStreamSynchronize(r->mstream);
+        float m; memcpy(&m, r->h_stats + 32, 4);
+        if (m > gmax) gmax = m;
+        uint64_t a = 0, b = 0;
+        mirogpu_last_call_stats(r, &a, &b);
+        rays += a; launches += b;
+    }
+    const size_t rowf = (size_t)rp.width * 12, rowb = (size_t)rp.width * 3;
+    for (size_t k = 0; k < N && e == cudaSuccess; ++k) {
+        mirogpu_scene* r = replica_of(h, k);
+        cudaSetDevice(r->device);
+        const int first_row = rp.row_begin + (int)k;
+        const int nrows = first_row < rp.row_end ? (rp.row_end - first_row + (int)N - 1) / (int)N : 0;
+        if (nrows == 0) continue;
+        float* d_rgb = reinterpret_cast<float*>(r->scratch.buf[13]);
+        unsigned char* d_u8 = reinterpret_cast<unsigned char*>(r->scratch.buf[14]);
+        float* d_max = reinterpret_cast<float*>(r->scratch.buf[15]);
+        const size_t nvals = (size_t)nrows * rp.width * 3;
+        if (rgb8_out || rp.tonemap) {
+            e = cudaMemcpyAsync(d_max, &gmax, 4, cudaMemcpyHostToDevice, r->mstream);   // pageable 4-byte source: staged at once by the driver
+            if (e != cudaSuccess) break;
+            k_tonemap<<<(unsigned)((nvals + 255) / 256), 256, 0, r->mstream>>>(d_rgb, rgb8_out ? d_u8 : nullptr, rp.width, first_row, (int)N, nrows, d_max);
+            launches++;
+        }
+        if (rgb8_out) e = cudaMemcpy2DAsync(rgb8_out + (size_t)first_row * rowb, rowb * N, d_u8 + (size_t)first_row * rowb, rowb * N, rowb, nrows, cudaMemcpyDeviceToHost, r->mstream);
+        else if (rgb_out) e = cudaMemcpy2DAsync(reinterpret_cast<char*>(rgb_out) + (size_t)first_row * rowf, rowf * N, reinterpret_cast<char*>(d_rgb) + (size_t)first_row * rowf, rowf * N, rowf, nrows, cudaMemcpyDeviceToHost, r->mstream);
+        else if (d_rgb_primary) {   // gather on the first device: peer copy over NVLink, ordered into the caller's stream by an event
+            e = cudaMemcpy2DAsync(reinterpret_cast<char*>(d_rgb_primary) + (size_t)first_row * rowf, rowf * N, reinterpret_cast<char*>(d_rgb) + (size_t)first_row * rowf, rowf * N, rowf, nrows, cudaMemcpyDefault, r->mstream);
+            if (e == cudaSuccess) e = cudaEventRecord(r->mevent, r->mstream);
+        }
+    }
+    if (e == cudaSuccess && !rgb8_out && !rgb_out && d_rgb_primary) {
+        cudaSetDevice(h->device);
+        for (size_t k = 0; k < N && e == cudaSuccess; ++k) e = cudaStreamWaitEvent(st_primary, replica_of(h, k)->mevent, 0);
+    } else {
+        for (size_t k = 0; k < N; ++k) {
+            mirogpu_scene* r = replica_of(h, k);
+            cudaSetDevice(r->device);
+            const cudaError_t e2 = cudaStreamSynchronize(r->mstream);
+            if (e == cudaSuccess) e = e2;
+        }
+    }
+    cudaSetDevice(h->device);
+    if (e != cudaSuccess) { err = std::string("multi-device framebuffer gather: ") + cudaGetErrorString(e); return MIROGPU_ERR_CUDA; }
+    {
+        std::lock_guard<std::mutex> lk(h->mtx);
+        h->last_rays = rays; h->last_launches = launches; h->stats_batches = 0;
+    }
+    return MIROGPU_OK;
+}
+
 int render_host(mirogpu_scene* h, const mirogpu_camera& cam, const mirogpu_render_params& rp, float* rgb_out, unsigned char* rgb8_out,
                 std::string& err)
 {
     if (rp.width <= 0 || rp.height <= 0) { err = "bad render parameters"; return MIROGPU_ERR_INVALID_ARG; }
+    // a multi-device handle shards the rows itself -- unless the caller already asks for a shard (row_stride > 1)
+    if (!h->replicas.empty() && rp.row_stride == 1) return render_multi(h, cam, rp, rgb_out, rgb8_out, nullptr, nullptr, err);
     const size_t npx = (size_t)rp.width * rp.height;
     cudaError_t e;
     {

@@ -190,6 +190,40 @@ MIRO_HD bool tri_test(const float4 v0, const float4 v1, const float4 v2, const f
     return false;
 }
 
+// Sphere::intersect, Sphere.cpp:28-69, on a sphere slot of the leaf array: v0 = (centre, prim id bits), v1.x = radius.  Same
+// operations in the same order (a = |d|^2, b = (2 d) . (o - c), c = |o - c|^2 - r r, discriminant b b - 4 a c, the two roots
+// divided by 2 a), no FMA.  The reference takes the nearer root if it lies strictly inside (tMin, tMax) -- tMax being the best
+// hit so far in its leaf loop (BVH.cpp:498) -- else the farther one; a hit must then be strictly closer than the best
+// (BVH.cpp:500).  Equal t goes to the smaller primitive id here, as for triangles.
+MIRO_HD bool sphere_test(const float4 v0, const float4 v1, const mirogpu_ray& r, BestHit& best)
+{
+    const float tox = xsub(r.ox, v0.x), toy = xsub(r.oy, v0.y), toz = xsub(r.oz, v0.z);
+    const float a = xdot(r.dx, r.dy, r.dz, r.dx, r.dy, r.dz);
+    const float b = xdot(xmul(r.dx, 2.0f), xmul(r.dy, 2.0f), xmul(r.dz, 2.0f), tox, toy, toz);
+    const float c = xsub(xdot(tox, toy, toz, tox, toy, toz), xmul(v1.x, v1.x));
+    const float discrim = xsub(xmul(b, b), xmul(xmul(4.0f, a), c));
+    if (discrim < 0.f) return false;
+    const float sq = xsqrt(discrim), two_a = xmul(2.0f, a);
+    const float t0 = xdiv(xsub(-b, sq), two_a), t1 = xdiv(xadd(-b, sq), two_a);
+    const uint32_t prim = f2u(v0.w);
+    float t;
+    // (t0 > tMin && t0 < tMax) else (t1 > tMin && t1 < tMax), with tMax = the best hit so far; `closer` admits the tie rule
+    const bool closer0 = t0 < best.t || (t0 == best.t && prim < best.prim);
+    if (t0 > r.tmin && closer0) t = t0;
+    else if (t1 > r.tmin && (t1 < best.t || (t1 == best.t && prim < best.prim)) && !(t0 > r.tmin)) t = t1;
+    else return false;
+    if (!(t < r.tmax)) return false;   // the sphere's range test is strict at the far end too
+    best.t = t; best.prim = prim; best.beta = 0.f; best.gamma = 0.f;
+    return true;
+}
+
+// One slot of the leaf array: a triangle, or (v3.y != 0) a sphere.
+MIRO_HD bool prim_test(const float4 v0, const float4 v1, const float4 v2, const float4 v3, const mirogpu_ray& r, BestHit& best)
+{
+    if (f2u(v3.y) != 0u) return sphere_test(v0, v1, r, best);
+    return tri_test(v0, v1, v2, v3, r, best);
+}
+
 MIRO_HD float safe_rcp(float d)
 {
     // 1/d with |d| clamped away from zero so that 0 * inf never produces a NaN in the slab test
@@ -248,7 +282,7 @@ MIRO_HD void trace_bvh2(const float4* __restrict__ nodes, const float4* __restri
             for (uint32_t i = 0; i < count; ++i) {
                 const F8 ta = ld256(tris + 4 * (size_t)(first + i)), tb = ld256(tris + 4 * (size_t)(first + i) + 2);
                 if (COUNT) cnt->tris++;
-                const bool acc = tri_test(ta.lo, ta.hi, tb.lo, tb.hi, r, best);
+                const bool acc = prim_test(ta.lo, ta.hi, tb.lo, tb.hi, r, best);
                 if (ANY && acc) return;
             }
             if (sp == 0) return;
@@ -372,7 +406,7 @@ MIRO_HD void bvh2_leaf_step(const float4* __restrict__ tris, const mirogpu_ray& 
     const uint32_t first = ref >> 3, count = (ref & 7u) + 1u;
     for (uint32_t i = 0; i < count; ++i) {
         const F8 ta = ld256(tris + 4 * (size_t)(first + i)), tb = ld256(tris + 4 * (size_t)(first + i) + 2);
-        const bool acc = tri_test(ta.lo, ta.hi, tb.lo, tb.hi, r, best);
+        const bool acc = prim_test(ta.lo, ta.hi, tb.lo, tb.hi, r, best);
         if (ANY && acc) { w.node = MIRO_BVH2_DONE; return; }
     }
     bvh2_pop(w, stack);
@@ -387,7 +421,7 @@ MIRO_HD void bvh2_leaf_step_one(const float4* __restrict__ tris, const mirogpu_r
     const uint32_t ref = (uint32_t)~w.node;
     const uint32_t first = ref >> 3;
     const F8 ta = ld256(tris + 4 * (size_t)first), tb = ld256(tris + 4 * (size_t)first + 2);
-    const bool acc = tri_test(ta.lo, ta.hi, tb.lo, tb.hi, r, best);
+    const bool acc = prim_test(ta.lo, ta.hi, tb.lo, tb.hi, r, best);
     if (ANY && acc) { w.node = MIRO_BVH2_DONE; return; }
     if (ref & 7u) w.node = (int32_t)~(ref + 7u);   // first + 1 (ref + 8), count - 1 (ref - 1)
     else bvh2_pop(w, stack);
@@ -403,8 +437,8 @@ MIRO_HD void bvh2_leaf_step_two(const float4* __restrict__ tris, const mirogpu_r
     const F8 ta = ld256(tris + 4 * (size_t)first), tb = ld256(tris + 4 * (size_t)first + 2);
     F8 tc, td;
     if (left) { tc = ld256(tris + 4 * (size_t)first + 4); td = ld256(tris + 4 * (size_t)first + 6); }
-    bool acc = tri_test(ta.lo, ta.hi, tb.lo, tb.hi, r, best);
-    if (left && !(ANY && acc)) acc |= tri_test(tc.lo, tc.hi, td.lo, td.hi, r, best);
+    bool acc = prim_test(ta.lo, ta.hi, tb.lo, tb.hi, r, best);
+    if (left && !(ANY && acc)) acc |= prim_test(tc.lo, tc.hi, td.lo, td.hi, r, best);
     if (ANY && acc) { w.node = MIRO_BVH2_DONE; return; }
     if (left >= 2u) w.node = (int32_t)~(ref + 14u);   // first + 2 (ref + 16), count - 2 (ref - 2)
     else bvh2_pop(w, stack);
@@ -417,7 +451,7 @@ MIRO_HD int32_t leaf_ref_test_one(const float4* __restrict__ tris, const mirogpu
     const uint32_t ref = (uint32_t)~leaf;
     const uint32_t first = ref >> 3;
     const F8 ta = ld256(tris + 4 * (size_t)first), tb = ld256(tris + 4 * (size_t)first + 2);
-    hit = tri_test(ta.lo, ta.hi, tb.lo, tb.hi, r, best);
+    hit = prim_test(ta.lo, ta.hi, tb.lo, tb.hi, r, best);
     return (ref & 7u) ? (int32_t)~(ref + 7u) : MIRO_BVH2_DONE;
 }
 
@@ -655,7 +689,7 @@ MIRO_HD void trace_cwbvh8(const uint4* __restrict__ nodes, const float4* __restr
             const uint32_t ti = T.x + (uint32_t)bit;
             const F8 ta = ld256(tris + 4 * (size_t)ti), tb = ld256(tris + 4 * (size_t)ti + 2);
             if (COUNT) cnt->tris++;
-            const bool acc = tri_test(ta.lo, ta.hi, tb.lo, tb.hi, r, best);
+            const bool acc = prim_test(ta.lo, ta.hi, tb.lo, tb.hi, r, best);
             if (ANY && acc) return;
         }
         if ((G.y & 0xff000000u) == 0u) {

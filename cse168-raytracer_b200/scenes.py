@@ -91,7 +91,46 @@ def _bunny20_transforms():
     return [_chain(*b) for b in base] + [_chain(x2, *b) for b in base]
 
 
+def _spiral():
+    """makeSpiralScene (assignment1.cpp:8-76): 149 spheres on a spiral, a ground plane, one triangle with per-vertex normals.
+    The sphere parameters are formed in binary32 like the script's float variables (cos / sin: the float overloads)."""
+    spheres, mats = [], []
+    maxI, a = 150, F(0.15)
+    for i in range(1, maxI):
+        t = F(i) / F(maxI)
+        theta = F(F(4) * PI_F) * t
+        r = a * theta
+        x = r * F(math.cos(float(theta))); y = r * F(math.sin(float(theta)))
+        z = F(2) * (F(F(2) * PI_F) * a - r)
+        mats.append(dict(kd=(1.0, float(t), float(i % 2)), ks=(0, 0, 0), kt=(0, 0, 0), shininess=1.0, refr=1.0))   # Phong(Vector3(1.0f, t, i%2))
+        spheres.append(dict(c=(float(x), float(y), float(z)), r=float(r / F(10)), mat=len(mats) - 1))
+    mats.append(dict(kd=(1.0, 0, 0), ks=(0, 0, 0), kt=(0, 0, 0), shininess=1.0, refr=1.0)); plane_mat = len(mats) - 1
+    mats.append(dict(kd=(0, 1, 0), ks=(0, 0, 0), kt=(0, 0, 0), shininess=1.0, refr=1.0)); tri_mat = len(mats) - 1
+
+    def nrm(v):
+        v = np.asarray(v, np.float32)
+        l2 = F(F(v[0] * v[0]) + F(v[1] * v[1])); l2 = F(l2 + F(v[2] * v[2]))
+        return tuple(float(c) for c in v * (F(1) / np.sqrt(l2, dtype=np.float32)))
+    tri = dict(v=[0, 0, 0, 0, 3, 0, 5, 5, 0], n=[0, 0, -1, *nrm((0.1, 0.1, -1)), *nrm((-0.1, -0.2, -1))])
+    return dict(meshes=[], triangles=[(tri, tri_mat)], materials=mats, spheres=spheres,
+                planes=[dict(n=(0, 1, 0), o=(0, -2, 0), mat=plane_mat)],
+                lights=[dict(kind=0, pos=(-3, 15, -15), color=(1, 1, 1), wattage=1000)], bg=(1, 1, 1),
+                camera=dict(eye=(0, 0, -5), lookat=(0, 0, 0), up=(0, 1, 0), fov=45), size=(512, 512))
+
+
 SCENES = {
+    # makeSpiralScene (assignment1.cpp:8-76): spheres in the tree, a plane outside it
+    "spiral": _spiral(),
+    # two glass / mirror spheres over a plane with the teapot: non-triangle primitives under the recursive tracer
+    "spheres_teapot": dict(
+        meshes=[("teapot", None, 0)], triangles=[], materials=[LAMBERT_WHITE if False else dict(kd=(1, 1, 1), ks=(0, 0, 0), kt=(0, 0, 0), shininess=1.0, refr=1.0),
+                                                              dict(kd=(0.1, 0.1, 0.1), ks=(0.8, 0.8, 0.8), kt=(0, 0, 0), shininess=50.0, refr=1.0),
+                                                              dict(kd=(0, 0, 0), ks=(0, 0, 0), kt=(1, 1, 1), shininess=50.0, refr=1.5),
+                                                              dict(kd=(0.8, 0.7, 0.3), ks=(0, 0, 0), kt=(0, 0, 0), shininess=1.0, refr=1.0)],
+        spheres=[dict(c=(-2.2, 1.0, 0.5), r=1.0, mat=1), dict(c=(2.4, 0.8, 1.0), r=0.8, mat=2)],
+        planes=[dict(n=(0, 1, 0), o=(0, 0, 0), mat=3)],
+        lights=[dict(kind=0, pos=(10, 10, 10), color=(1, 1, 1), wattage=700)], bg=(0.2, 0.3, 0.5),
+        camera=dict(eye=(0, 3, 8), lookat=(0, 0.8, 0), up=(0, 1, 0), fov=45), size=(256, 256)),
     # config 1 -- makeCornellScene's camera/light on cornell_box.obj (assignment2.cpp:380-405)
     "cornell": dict(
         meshes=[("cornell_box", None, 0)], triangles=[], materials=[LAMBERT_WHITE],
@@ -162,6 +201,10 @@ def realise(builder, name, obj_path_of):
         builder.add_obj(obj_path_of(model), ctm, mat)
     for tri, mat in sc["triangles"]:
         builder.add_triangle(tri["v"], tri["n"], mat)
+    for sp in sc.get("spheres", []):
+        builder.add_sphere(sp["c"], sp["r"], sp["mat"])
+    for pl in sc.get("planes", []):
+        builder.add_plane(pl["n"], pl["o"], pl["mat"])
     for l in sc["lights"]:
         if l["kind"] == 0:
             builder.add_point_light(l["pos"], l["color"], l["wattage"])

@@ -9,6 +9,7 @@
  *   mirogpu_intersect_batch     <- BVH::intersect / BVH::intersectChildren            BVH.h:35-38, BVH.cpp:438-658
  *                                  + Triangle::intersect                              Triangle.cpp:136-169
  *                                  (= Scene::trace with no unbounded objects,         Scene.cpp:214-268)
+ *                                  + Sphere::intersect / Plane::intersect              Sphere.cpp:28-69, Plane.cpp:33-48
  *   mirogpu_generate_primary    <- Camera::eyeRay                                     Camera.cpp:104-161
  *   mirogpu_generate_bounce     <- Ray::diffuse / Ray::random                         Ray.h:109-140, Utility.h:34-50
  *   mirogpu_render(_rgb8)       <- Scene::raytraceImage + Scene::traceScene           Scene.cpp:93-212, 270-346
@@ -175,6 +176,42 @@ typedef struct mirogpu_counters {
     uint64_t bytes_fetched;  /* node + triangle bytes requested by the traversal */
 } mirogpu_counters;
 
+/* Sphere (Sphere.h:7-38, Sphere.cpp:28-69): a bounded object, a leaf primitive of the tree next to the triangles. */
+typedef struct mirogpu_sphere {
+    float center[3];
+    float radius;
+    uint32_t material_id;
+    uint32_t _pad;
+} mirogpu_sphere;
+
+/* Plane (Plane.h:12-36, Plane.cpp:33-48): an unbounded object -- tested after the tree walk like Scene::trace's
+ * m_unboundedObjects loop (Scene.cpp:219-230).  normal is used as given (Scene::trace normalises N afterwards). */
+typedef struct mirogpu_plane {
+    float normal[3];
+    float origin[3];
+    uint32_t material_id;
+    uint32_t _pad;
+} mirogpu_plane;
+
+/* Everything mirogpu_scene_create_ex builds a scene from.  Primitive ids: triangle i -> i, sphere j -> ntris + j,
+ * plane k -> ntris + nspheres + k.  devices / ndevices: the CUDA devices the scene is REPLICATED on (SURVEY 8b "device_mask",
+ * 8e: image rows shard over them, the tree is replicated); NULL / 0 = the one device of mirogpu_build_options.device. */
+typedef struct mirogpu_scene_desc {
+    const float* tri_vertices;         /* ntris x 9 floats (A, B, C) */
+    const float* tri_normals;          /* ntris x 9 floats (nA, nB, nC) or NULL */
+    const uint32_t* tri_material_ids;  /* ntris entries or NULL (all 0) */
+    uint32_t ntris;
+    uint32_t nspheres;
+    const mirogpu_sphere* spheres;
+    const mirogpu_plane* planes;
+    uint32_t nplanes;
+    uint32_t nmaterials;
+    const mirogpu_material* materials; /* NULL: one white Lambert */
+    const int32_t* devices;
+    uint32_t ndevices;
+    uint32_t _pad;
+} mirogpu_scene_desc;
+
 typedef struct mirogpu_scene* mirogpu_handle;
 
 /* ---- lifetime ------------------------------------------------------------------------------------------ */
@@ -189,6 +226,12 @@ int mirogpu_device_count(int* count);
 int mirogpu_scene_create(const float* tri_vertices, const float* tri_normals, const uint32_t* material_ids,
                          uint32_t ntris, const mirogpu_material* materials, uint32_t nmaterials,
                          const mirogpu_build_options* opt, mirogpu_handle* out);
+/* The same with spheres, planes and a device list (see mirogpu_scene_desc).  On a multi-device handle the batch queries run on
+ * the first device; mirogpu_render / mirogpu_render_rgb8 shard the image rows over all devices (row % ndevices) and gather the
+ * framebuffer on the first one over NVLink peer copies; *_device entry points address the first device's replica. */
+int mirogpu_scene_create_ex(const mirogpu_scene_desc* desc, const mirogpu_build_options* opt, mirogpu_handle* out);
+/* Number of devices the scene is replicated on and their ordinals (devices may be NULL; at most `capacity` entries written). */
+int mirogpu_scene_devices(mirogpu_handle h, int32_t* devices, uint32_t capacity, uint32_t* ndevices);
 int mirogpu_scene_destroy(mirogpu_handle h);
 int mirogpu_scene_info_get(mirogpu_handle h, mirogpu_scene_info* info);
 int mirogpu_scene_set_lights(mirogpu_handle h, const mirogpu_light* lights, uint32_t nlights);
@@ -215,6 +258,10 @@ int mirogpu_set_kernel_variant(mirogpu_handle h, int variant);
  * from hits.  Outputs are n x 3 floats / n uint32; any may be NULL. */
 int mirogpu_resolve_hits_device(mirogpu_handle h, const mirogpu_hit* d_hits, size_t n, float* d_P, float* d_N,
                                 uint32_t* d_material, void* cuda_stream);
+/* The same for scenes with spheres or planes, whose hit point is o + t d (Sphere.cpp:62, Plane.cpp:42): needs the rays.
+ * (mirogpu_resolve_hits_device fails with MIROGPU_ERR_INVALID_ARG on such a scene.) */
+int mirogpu_resolve_hits_rays_device(mirogpu_handle h, const mirogpu_ray* d_rays, const mirogpu_hit* d_hits, size_t n, float* d_P,
+                                     float* d_N, uint32_t* d_material, void* cuda_stream);
 
 /* ---- device-side ray generation ------------------------------------------------------------------------ */
 /* Camera::eyeRay for the pixels of this call's rows, for `sample_count` samples starting at `sample_begin`.

@@ -116,7 +116,8 @@ struct Mesh {                                                          // Triang
     int ntris;
 };
 struct Material { V3 kd, ks, kt; float shininess, refr; };             // Phong.cpp:13-32 after clamping
-struct Prim { int mesh, index, material; V3 cmin, cmax, center; };     // Triangle.h:40-42 + cached bounds
+struct Prim { int mesh, index, material; V3 cmin, cmax, center; float radius; };   // Triangle.h:40-42 + cached bounds; mesh < 0: a Sphere (Sphere.h:34-35: centre in `center`, radius)
+struct PlaneObj { V3 normal, origin; int material; };                  // Plane.h:35
 struct Light { int kind; V3 pos, color, normal; float wattage, radius; };  // 0 = PointLight, 1 = DirectionalAreaLight
 
 struct Node {                                                          // BVH.h:30-62
@@ -153,6 +154,7 @@ struct Scene {
     std::vector<Mesh*> meshes;
     std::vector<Material> materials;
     std::vector<Prim> prims;
+    std::vector<PlaneObj> planes;                                      // Scene::m_unboundedObjects (Scene.h:24-25)
     std::vector<Light> lights;
     Node* root;
     long long n_nodes, n_leaves;
@@ -256,6 +258,7 @@ void addPrim(int mesh, int index, int material)
 // Triangle::updateMinMax (Triangle.cpp:97-118) and Triangle::center (Triangle.cpp:41-48)
 void primPreCalc(Prim& p)
 {
+    if (p.mesh < 0) { p.cmin = p.center - V3(p.radius); p.cmax = p.center + V3(p.radius); return; }   // Sphere.h:21-23
     const Mesh* m = g->meshes[p.mesh];
     V3 v[3] = {m->vertices[m->vidx[3 * p.index]], m->vertices[m->vidx[3 * p.index + 1]], m->vertices[m->vidx[3 * p.index + 2]]};
     p.cmin = v[0]; p.cmax = v[0];
@@ -417,6 +420,44 @@ inline bool triIntersect(int prim, Hit& result, const Ray& r, float tMin, float 
     return true;
 }
 
+// Sphere::intersect, Sphere.cpp:28-69
+inline bool sphereIntersect(const Prim& p, Hit& result, const Ray& ray, float tMin, float tMax)
+{
+    const V3 toO = ray.o - p.center;
+    const float a = length2(ray.d);
+    const float b = dot(2 * ray.d, toO);
+    const float c = length2(toO) - p.radius * p.radius;
+    const float discrim = b * b - 4.0f * a * c;
+    if (discrim < 0) return false;
+    const float sqrt_discrim = sqrtf(discrim);
+    const float t[2] = {(-b - sqrt_discrim) / (2.0f * a), (-b + sqrt_discrim) / (2.0f * a)};
+    if ((t[0] > tMin) && (t[0] < tMax)) result.t = t[0];
+    else if ((t[1] > tMin) && (t[1] < tMax)) result.t = t[1];
+    else return false;
+    result.P = ray.o + result.t * ray.d;
+    result.N = normalized(result.P - p.center);
+    result.material = p.material;
+    return true;
+}
+// Plane::intersect, Plane.cpp:33-48
+inline bool planeIntersect(const PlaneObj& pl, Hit& result, const Ray& r, float tMin, float tMax)
+{
+    float ndotd = dot(pl.normal, r.d);
+    if (fabs(ndotd) < 1e-6) return false;
+    float t = dot(pl.normal, (pl.origin - r.o)) / ndotd;
+    if (t < tMin || t > tMax) return false;
+    result.P = r.o + t * r.d;
+    result.t = t;
+    result.N = pl.normal;
+    result.material = pl.material;
+    return true;
+}
+inline bool primIntersect(int prim, Hit& result, const Ray& r, float tMin, float tMax)
+{
+    const Prim& p = g->prims[prim];
+    return p.mesh < 0 ? sphereIntersect(p, result, r, tMin, tMax) : triIntersect(prim, result, r, tMin, tMax);
+}
+
 // BVH::intersectChildren, BVH.cpp:471-658 (scalar branch)
 bool intersectChildren(const Node* node, Hit& minHit, const Ray& ray, float tMin, float tMax, Counters& cn)
 {
@@ -425,8 +466,8 @@ bool intersectChildren(const Node* node, Hit& minHit, const Ray& ray, float tMin
     minHit.t = tMax;
     if (node->leaf) {
         for (size_t i = 0; i < node->objs.size(); ++i) {
-            cn.tri++;
-            if (triIntersect(node->objs[i], tempMinHit, ray, tMin, minHit.t)) {
+            if (g->prims[node->objs[i]].mesh >= 0) cn.tri++;           // Stats::Ray_Tri_Intersect counts Triangles only (BVH.cpp:495-497)
+            if (primIntersect(node->objs[i], tempMinHit, ray, tMin, minHit.t)) {
                 if (tempMinHit.t < minHit.t) {
                     hit = true;
                     minHit = tempMinHit;
@@ -482,11 +523,20 @@ bool bvhIntersect(Hit& minHit, const Ray& ray, float tMin, float tMax, Counters&
     return intersectChildren(root, minHit, ray, tMin, tMax, cn);
 }
 
-// Scene::trace, Scene.cpp:214-268.  No unbounded objects (planes are out of scope); all materials are
+// Scene::trace, Scene.cpp:214-268.  All materials are
 // UV-lookup Phong with bumpHeight2D == 0, so dx = dy = 0 and the branch reduces to N.normalize().
 bool sceneTrace(Hit& minHit, const Ray& ray, float tMin, float tMax, Counters& cn)
 {
     bool result = bvhIntersect(minHit, ray, tMin, tMax, cn);
+    for (size_t i = 0; i < g->planes.size(); i++) {                    // the unbounded objects, Scene.cpp:219-230
+        Hit tempMinHit;
+        bool ubresult = planeIntersect(g->planes[i], tempMinHit, ray, tMin, tMax);
+        if (ubresult && (!result || tempMinHit.t < minHit.t)) {
+            result = true;
+            minHit = tempMinHit;
+            minHit.object = (int)(g->prims.size() + i);
+        }
+    }
     if (result) {
         const float dx = 0.0f, dy = 0.0f;                              // (u2-u1)/(2*delta) with all heights 0
         float n[3] = {minHit.N.x, minHit.N.y, minHit.N.z};
@@ -509,10 +559,13 @@ bool bruteTrace(Hit& best, const Ray& ray, float tMin, float tMax)
     best.t = tMax;
     Hit tmp;
     for (size_t i = 0; i < g->prims.size(); ++i) {
-        if (triIntersect((int)i, tmp, ray, tMin, tMax)) {
+        if (primIntersect((int)i, tmp, ray, tMin, tMax)) {
             if (!(tmp.t == tmp.t)) continue;                           // NaN t: the leaf's strict < discards it (BVH.cpp:500)
             if (!hit ? (tmp.t <= best.t) : (tmp.t < best.t)) { best = tmp; best.object = (int)i; hit = true; }
         }
+    }
+    for (size_t i = 0; i < g->planes.size(); i++) {                    // then the unbounded objects, as Scene::trace does
+        if (planeIntersect(g->planes[i], tmp, ray, tMin, tMax) && (!hit || tmp.t < best.t)) { best = tmp; best.object = (int)(g->prims.size() + i); hit = true; }
     }
     return hit;
 }
@@ -1004,6 +1057,18 @@ void orc_add_triangle(const float* v9, const float* n9, int material)
     addPrim((int)g->meshes.size() - 1, 0, material);
 }
 
+// Sphere (Sphere.h) as a bounded scene object / Plane (Plane.h) as an unbounded one.  Plane ids follow the bounded objects.
+void orc_add_sphere(const float* center, float radius, int material)
+{
+    Prim p; p.mesh = -1; p.index = 0; p.material = material; p.center = V3(center[0], center[1], center[2]); p.radius = radius;
+    g->prims.push_back(p);
+}
+void orc_add_plane(const float* normal, const float* origin, int material)
+{
+    PlaneObj pl; pl.normal = V3(normal[0], normal[1], normal[2]); pl.origin = V3(origin[0], origin[1], origin[2]); pl.material = material;
+    g->planes.push_back(pl);
+}
+
 void orc_add_point_light(const float* pos, const float* color, float wattage)
 {
     Light l; l.kind = 0; l.pos = V3(pos[0], pos[1], pos[2]); l.color = V3(color[0], color[1], color[2]);
@@ -1040,8 +1105,9 @@ void orc_dump_triangles(float* out18)
 {
     for (size_t i = 0; i < g->prims.size(); ++i) {
         const Prim& p = g->prims[i];
-        const Mesh* m = g->meshes[p.mesh];
         float* o = out18 + 18 * i;
+        if (p.mesh < 0) { for (int k = 0; k < 18; ++k) o[k] = 0; continue; }
+        const Mesh* m = g->meshes[p.mesh];
         for (int k = 0; k < 3; ++k) {
             const V3& v = m->vertices[m->vidx[3 * p.index + k]];
             const V3& n = m->normals[m->nidx[3 * p.index + k]];

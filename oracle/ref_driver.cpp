@@ -40,6 +40,8 @@
 #include "Image.h"
 #include "Triangle.h"
 #include "TriangleMesh.h"
+#include "Sphere.h"
+#include "Plane.h"
 #include "Phong.h"
 #include "PointLight.h"
 #include "DirectionalAreaLight.h"
@@ -64,6 +66,8 @@ void rebuild_prim_ids()
     const Objects* objs = g_scene->objects();
     g_prim_id.rehash(2 * objs->size() + 16);
     for (size_t i = 0; i < objs->size(); ++i) g_prim_id[(*objs)[i]] = (int)i;
+    // unbounded objects (planes) are numbered after the bounded ones
+    for (size_t i = 0; i < g_scene->m_unboundedObjects.size(); ++i) g_prim_id[g_scene->m_unboundedObjects[i]] = (int)(objs->size() + i);
 }
 }  // namespace
 
@@ -147,6 +151,24 @@ void ref_add_triangle(const float* v9, const float* n9, int material)
     t->setMesh(mesh);
     t->setMaterial(g_materials[material]);
     g_scene->addObject(t);
+}
+
+// Reference Sphere / Plane objects (Sphere.h, Plane.h); Scene::addObject files the plane under the unbounded objects.
+void ref_add_sphere(const float* center, float radius, int material)
+{
+    Sphere* sp = new Sphere;
+    sp->setCenter(Vector3(center[0], center[1], center[2]));
+    sp->setRadius(radius);
+    sp->setMaterial(g_materials[material]);
+    g_scene->addObject(sp);
+}
+void ref_add_plane(const float* normal, const float* origin, int material)
+{
+    Plane* pl = new Plane;
+    pl->setNormal(Vector3(normal[0], normal[1], normal[2]));
+    pl->setOrigin(Vector3(origin[0], origin[1], origin[2]));
+    pl->setMaterial(g_materials[material]);
+    g_scene->addObject(pl);
 }
 
 void ref_add_point_light(const float* pos, const float* color, float wattage)

@@ -66,6 +66,12 @@ class Driver:
     def add_triangle(self, v9, n9, material=0):
         self._f("add_triangle")((ctypes.c_float * 9)(*map(float, v9)), (ctypes.c_float * 9)(*map(float, n9)), int(material))
 
+    def add_sphere(self, center, radius, material=0):
+        self._f("add_sphere")(_f3(center), ctypes.c_float(radius), int(material))
+
+    def add_plane(self, normal, origin, material=0):
+        self._f("add_plane")(_f3(normal), _f3(origin), int(material))
+
     def add_point_light(self, pos, color, wattage):
         self._f("add_point_light")(_f3(pos), _f3(color), ctypes.c_float(wattage))
 

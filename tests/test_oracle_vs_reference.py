@@ -12,7 +12,7 @@ import pytest
 
 import miro_driver as md
 import objio
-from conftest import bits, subsample_rays
+from conftest import bits, random_rays, subsample_rays
 
 
 def _both(reference, oracle, scenes, name):
@@ -95,3 +95,40 @@ def test_photon_map_bit_exact(reference, oracle):
     a = reference.pm_irradiance(wr, q, qn, 0.5, 50, 1)
     b = oracle.pm_irradiance(wo, q, qn, 0.5, 50, 1)
     assert np.array_equal(bits(a), bits(b))
+
+
+@pytest.mark.parametrize("name", ["spiral", "spheres_teapot"])
+def test_spheres_and_planes_bit_exact(reference_stats, oracle, scenes, name):
+    """Sphere::intersect (Sphere.cpp:28-69) inside the tree, Plane::intersect (Plane.cpp:33-48) in Scene::trace's unbounded
+    loop (Scene.cpp:219-230): restatement against the reference's own classes -- hits, P, N, counters, shaded radiance."""
+    R, O = reference_stats, oracle
+    _both(R, O, scenes, name)
+    sr, so = R.stats(), O.stats()
+    assert (sr["nodes"], sr["leaves"]) == (so["nodes"], so["leaves"])
+    w, h = scenes.SCENES[name]["size"]
+    rays = subsample_rays(O.eye_rays(w, h), w, h, 2)
+    R.stats_reset_rays(); O.stats_reset_rays()
+    a, b = R.trace(rays, 1), O.trace(rays, 1)
+    assert np.array_equal(a[1], b[1])
+    nbounded = O.num_objects()
+    kinds = set(np.unique(np.where(b[1] >= nbounded, 2, np.where(b[1] < 0, -1, 0))))
+    assert 2 in kinds and 0 in kinds          # planes and tree primitives are both hit
+    for x, y in zip((a[0], a[2], a[3]), (b[0], b[2], b[3])):
+        assert np.array_equal(bits(x), bits(y))
+    sr, so = R.stats(), O.stats()
+    assert (sr["ray_box"], sr["ray_tri"]) == (so["ray_box"], so["ray_tri"])
+    # incoherent rays from inside the scene (spheres entered from within: the far root)
+    rr = random_rays(20000, (-3, -2, -3), (3, 4, 3), 11)
+    a, b = R.trace(rr, 1), O.trace(rr, 1)
+    assert np.array_equal(a[1], b[1])
+    for x, y in zip((a[0], a[2], a[3]), (b[0], b[2], b[3])):
+        assert np.array_equal(bits(x), bits(y))
+    # bounded ranges exercise the strict (tMin, tMax) of the sphere and the inclusive one of the plane
+    rr2 = rr.copy(); rr2[:, 3] = 0.5; rr2[:, 7] = 6.0
+    a, b = R.trace(rr2, 1), O.trace(rr2, 1)
+    assert np.array_equal(a[1], b[1]) and np.array_equal(bits(a[0]), bits(b[0]))
+    # shaded radiance through Scene::traceScene (reflection / refraction on the spheres of spheres_teapot)
+    sub = subsample_rays(O.eye_rays(w, h), w, h, 8)
+    ra = R.trace_scene(sub, depth=10, nthreads=1)
+    rb = O.trace_scene(sub, depth=10, nthreads=1)
+    assert np.array_equal(bits(ra), bits(rb))
