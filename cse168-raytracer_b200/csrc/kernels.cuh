@@ -34,28 +34,36 @@ struct CameraBasis {       // what Camera::eyeRay caches in its statics (Camera.
 
 // Scene::trace's loop over the unbounded objects (Scene.cpp:219-230) with Plane::intersect (Plane.cpp:33-48) inlined: a plane
 // replaces the tree's answer only if strictly closer, or -- nothing hit so far -- anywhere inside [tMin, tMax]; planes are
-// tried in insertion order.  fabs(ndotd) < 1e-6 is a double comparison in the reference.
+// tried in insertion order.  fabs(ndotd) < 1e-6 is a double comparison in the reference.  Out of line and by value (see
+// sphere_hit_t): returns (t, prim id bits) of the answer after the planes.
+__device__ __noinline__ float2 planes_hit(const float4* __restrict__ planes, const uint32_t nplanes, const mirogpu_ray r, float best_t, uint32_t best_prim)
+{
+    if (r.tmax >= r.tmin)
+        for (uint32_t k = 0; k < nplanes; ++k) {
+            const float4 n = __ldg(planes + 2 * k), o = __ldg(planes + 2 * k + 1);
+            const float ndotd = xdot(n.x, n.y, n.z, r.dx, r.dy, r.dz);
+            if ((double)fabsf(ndotd) < 1e-6) continue;
+            const float t = xdiv(xdot(n.x, n.y, n.z, xsub(o.x, r.ox), xsub(o.y, r.oy), xsub(o.z, r.oz)), ndotd);
+            if (t < r.tmin || t > r.tmax) continue;
+            if (best_prim == MIROGPU_MISS || t < best_t) { best_t = t; best_prim = __float_as_uint(n.w); }
+        }
+    return make_float2(best_t, __uint_as_float(best_prim));
+}
 __device__ __forceinline__ void planes_test(const DeviceScene& s, const mirogpu_ray& r, BestHit& best)
 {
-    if (!(r.tmax >= r.tmin)) return;
-    for (uint32_t k = 0; k < s.num_planes; ++k) {
-        const float4 n = __ldg(s.planes + 2 * k), o = __ldg(s.planes + 2 * k + 1);
-        const float ndotd = xdot(n.x, n.y, n.z, r.dx, r.dy, r.dz);
-        if ((double)fabsf(ndotd) < 1e-6) continue;
-        const float t = xdiv(xdot(n.x, n.y, n.z, xsub(o.x, r.ox), xsub(o.y, r.oy), xsub(o.z, r.oz)), ndotd);
-        if (t < r.tmin || t > r.tmax) continue;
-        if (best.prim == MIROGPU_MISS || t < best.t) { best.t = t; best.prim = __float_as_uint(n.w); best.beta = 0.f; best.gamma = 0.f; }
-    }
+    const float2 a = planes_hit(s.planes, s.num_planes, r, best.t, best.prim);
+    if (__float_as_uint(a.y) != best.prim) { best.t = a.x; best.prim = __float_as_uint(a.y); best.beta = 0.f; best.gamma = 0.f; }
 }
 
-template <int LAYOUT, bool ANY, bool COUNT>
+// NT: the scene holds non-triangle primitives (sphere slots in the leaf array, planes after the walk).
+template <int LAYOUT, bool ANY, bool COUNT, bool NT = false>
 __device__ __forceinline__ void trace_one(const DeviceScene& s, const mirogpu_ray& r, BestHit& best, TraceCounters* c)
 {
-    if (LAYOUT == MIROGPU_LAYOUT_BVH2) trace_bvh2<ANY, COUNT>(s.nodes, s.tris, r, best, c);
-    else if (LAYOUT == MIROGPU_LAYOUT_BVH4) trace_bvh4<ANY, COUNT>(s.nodes, s.tris, r, best, c);
-    else if (LAYOUT == MIROGPU_LAYOUT_QBVH4) trace_qbvh4<ANY, COUNT>(s.nodes, s.tris, r, best, c);
-    else trace_cwbvh8<ANY, COUNT>(reinterpret_cast<const uint4*>(s.nodes), s.tris, r, best, c);
-    if (s.num_planes) planes_test(s, r, best);
+    if (LAYOUT == MIROGPU_LAYOUT_BVH2) trace_bvh2<ANY, COUNT, NT>(s.nodes, s.tris, r, best, c);
+    else if (LAYOUT == MIROGPU_LAYOUT_BVH4) trace_bvh4<ANY, COUNT, NT>(s.nodes, s.tris, r, best, c);
+    else if (LAYOUT == MIROGPU_LAYOUT_QBVH4) trace_qbvh4<ANY, COUNT, NT>(s.nodes, s.tris, r, best, c);
+    else trace_cwbvh8<ANY, COUNT, NT>(reinterpret_cast<const uint4*>(s.nodes), s.tris, r, best, c);
+    if (NT && s.num_planes) planes_test(s, r, best);
 }
 
 // Rays and hits are streamed once per launch: loads/stores carry the evict-first hint so the batch does not push
@@ -74,7 +82,7 @@ __device__ __forceinline__ void store_hit(mirogpu_hit* hits, size_t i, const Bes
     __stcs(reinterpret_cast<float4*>(hits + i), h);
 }
 
-template <int LAYOUT, bool ANY, bool COUNT>
+template <int LAYOUT, bool ANY, bool COUNT, bool NT = false>
 __global__ void __launch_bounds__(128) k_trace_simple(DeviceScene s, const mirogpu_ray* __restrict__ rays, size_t n,
                                                       mirogpu_hit* __restrict__ hits, unsigned long long* __restrict__ counters,
                                                       const uint32_t* __restrict__ d_n, uint32_t mult)
@@ -86,7 +94,7 @@ __global__ void __launch_bounds__(128) k_trace_simple(DeviceScene s, const mirog
     if (i < n) {
         const mirogpu_ray r = load_ray(rays, i);
         BestHit best;
-        trace_one<LAYOUT, ANY, COUNT>(s, r, best, &c);
+        trace_one<LAYOUT, ANY, COUNT, NT>(s, r, best, &c);
         store_hit(hits, i, best);
         hit = best.prim != MIROGPU_MISS;
     }
@@ -111,7 +119,7 @@ __global__ void __launch_bounds__(128) k_trace_simple(DeviceScene s, const mirog
 // warp takes a ticket for the next 32 consecutive rays.  Consecutive tickets keep primary rays of one
 // warp coherent; for incoherent batches the packet order is irrelevant and the ticket loop removes the
 // tail effect of uneven ray costs across CTAs.
-template <int LAYOUT, bool ANY>
+template <int LAYOUT, bool ANY, bool NT = false>
 __global__ void __launch_bounds__(128) k_trace_persistent(DeviceScene s, const mirogpu_ray* __restrict__ rays, size_t n,
                                                           mirogpu_hit* __restrict__ hits, unsigned long long* __restrict__ ticket,
                                                           const uint32_t* __restrict__ d_n, uint32_t mult, uint32_t packets_per_ticket)
@@ -131,7 +139,7 @@ __global__ void __launch_bounds__(128) k_trace_persistent(DeviceScene s, const m
             if (i < n) {
                 const mirogpu_ray r = load_ray(rays, i);
                 BestHit best;
-                trace_one<LAYOUT, ANY, false>(s, r, best, nullptr);
+                trace_one<LAYOUT, ANY, false, NT>(s, r, best, nullptr);
                 store_hit(hits, i, best);
             }
             __syncwarp();
@@ -151,7 +159,7 @@ __global__ void __launch_bounds__(128) k_trace_persistent(DeviceScene s, const m
 //   NREP  node steps per vote (a lane that leaves the inner nodes sits the rest out)
 //   SHORT stack entries per lane kept in shared memory ([entry][thread], conflict-free), deeper ones in local memory (0: all local)
 //   STAGE QBVH4 only: the first STAGE nodes (top levels, breadth-first numbering) copied into shared memory by every CTA
-template <int LAYOUT, bool ANY, int PF, int MINB, int NREP, int SHORT = 0, int STAGE = 0>
+template <int LAYOUT, bool ANY, int PF, int MINB, int NREP, int SHORT = 0, int STAGE = 0, bool NT = false>
 __global__ void __launch_bounds__(128, MINB) k_trace_hybrid(DeviceScene s, const mirogpu_ray* __restrict__ rays, size_t n,
                                                                  mirogpu_hit* __restrict__ hits, unsigned long long* __restrict__ ticket,
                                                                  int nmin, int period, int min_idle, uint32_t pool,
@@ -250,12 +258,12 @@ __global__ void __launch_bounds__(128, MINB) k_trace_hybrid(DeviceScene s, const
                     if (pleaf == MIRO_BVH2_DONE && at_leaf) { pleaf = w.node; bvh2_pop(w, stack); }
                     if (pleaf != MIRO_BVH2_DONE) {
                         bool hit;
-                        pleaf = leaf_ref_test_one(s.tris, r, pleaf, best, hit);
+                        pleaf = leaf_ref_test_one<NT>(s.tris, r, pleaf, best, hit);
                         if (ANY && hit) { pleaf = pleaf2 = MIRO_BVH2_DONE; w.node = MIRO_BVH2_DONE; }
                         else if ((PF & 128) && pleaf == MIRO_BVH2_DONE) { pleaf = pleaf2; pleaf2 = MIRO_BVH2_DONE; }
                     }
                 }
-                if (w.node == MIRO_BVH2_DONE && pleaf == MIRO_BVH2_DONE && ((mn | ml) >> lane & 1u)) { if (s.num_planes) planes_test(s, r, best); store_hit(hits, my, best); }
+                if (w.node == MIRO_BVH2_DONE && pleaf == MIRO_BVH2_DONE && ((mn | ml) >> lane & 1u)) { if (NT && s.num_planes) planes_test(s, r, best); store_hit(hits, my, best); }
             }
             continue;
         }
@@ -272,11 +280,11 @@ __global__ void __launch_bounds__(128, MINB) k_trace_hybrid(DeviceScene s, const
                         else bvh2_node_step<PF>(s.nodes, s.tris, r, w, stack, best);
                     }
             } else if (w.node < 0 && w.node != MIRO_BVH2_DONE) {
-                if (PF & 32) bvh2_leaf_step_two<ANY>(s.tris, r, w, stack, best);
-                else if (PF & 16) bvh2_leaf_step_one<ANY>(s.tris, r, w, stack, best);
-                else bvh2_leaf_step<ANY>(s.tris, r, w, stack, best);
+                if (PF & 32) bvh2_leaf_step_two<ANY, NT>(s.tris, r, w, stack, best);
+                else if (PF & 16) bvh2_leaf_step_one<ANY, NT>(s.tris, r, w, stack, best);
+                else bvh2_leaf_step<ANY, NT>(s.tris, r, w, stack, best);
             }
-            if (w.node == MIRO_BVH2_DONE && ((mn | ml) >> lane & 1u)) { if (s.num_planes) planes_test(s, r, best); store_hit(hits, my, best); }
+            if (w.node == MIRO_BVH2_DONE && ((mn | ml) >> lane & 1u)) { if (NT && s.num_planes) planes_test(s, r, best); store_hit(hits, my, best); }
         }
     }
 }
@@ -347,7 +355,7 @@ __device__ __forceinline__ SurfacePoint resolve_hit(const ShadeRecord& rec, cons
 }
 // Spheres and planes: P = o + t d (Sphere.cpp:62, Plane.cpp:42); sphere N = (P - c).normalize() (Sphere.cpp:63-64), plane N =
 // its normal as given (Plane.cpp:44); Scene::trace then normalises N once more (Scene.cpp:262).
-__device__ __noinline__ SurfacePoint resolve_hit_analytic(const ShadeRecord& rec, const mirogpu_hit& h, float ox, float oy, float oz, float dx, float dy, float dz)
+__device__ __forceinline__ SurfacePoint resolve_hit_analytic(const ShadeRecord& rec, const mirogpu_hit& h, float ox, float oy, float oz, float dx, float dy, float dz)
 {
     SurfacePoint sp;
     sp.P[0] = xadd(ox, xmul(dx, h.t)); sp.P[1] = xadd(oy, xmul(dy, h.t)); sp.P[2] = xadd(oz, xmul(dz, h.t));

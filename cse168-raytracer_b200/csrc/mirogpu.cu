@@ -198,12 +198,33 @@ cudaError_t launch_trace(mirogpu_scene* h, const mirogpu_ray* d_rays, size_t n, 
     if (n == 0) return cudaSuccess;
     if (h->variant == 1) {
         const unsigned grid = (unsigned)((n + 127) / 128);
-        k_trace_simple<LAYOUT, ANY, false><<<grid, 128, 0, st>>>(h->ds, d_rays, n, d_hits, nullptr, d_n, mult);
+        if (h->non_triangles) k_trace_simple<LAYOUT, ANY, false, true><<<grid, 128, 0, st>>>(h->ds, d_rays, n, d_hits, nullptr, d_n, mult);
+        else k_trace_simple<LAYOUT, ANY, false><<<grid, 128, 0, st>>>(h->ds, d_rays, n, d_hits, nullptr, d_n, mult);
         return cudaGetLastError();
     }
     unsigned long long* ticket = h->d_ticket + (h->ticket_slot.fetch_add(1) & 63u);
     cudaError_t e = cudaMemsetAsync(ticket, 0, sizeof(unsigned long long), st);
     if (e != cudaSuccess) return e;
+    if (h->non_triangles) {
+        // scenes with spheres / planes: the NT instantiations (sphere slots in the leaf array, planes after the walk) with the
+        // default scheduling of each layout -- the triangle-only kernels below compile without that code and keep their registers
+        const bool hybrid = LAYOUT != MIROGPU_LAYOUT_CWBVH8 && h->variant != 0 && n < 0xFF000000ull;
+        auto grid_of = [&](int occ) { size_t g = (size_t)h->sm_count * std::max(occ, 1); const size_t need = (n + 127) / 128; return (unsigned)std::min(g, need); };
+        int occ = 0;
+        if (hybrid) {
+            constexpr int L = LAYOUT == MIROGPU_LAYOUT_CWBVH8 ? MIROGPU_LAYOUT_BVH2 : LAYOUT;
+            constexpr int PFK = L == MIROGPU_LAYOUT_QBVH4 ? 16 : 0, NR = L == MIROGPU_LAYOUT_QBVH4 ? 3 : 2;
+            e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_trace_hybrid<L, ANY, PFK, 9, NR, 0, 0, true>, 128, 0);
+            if (e != cudaSuccess) return e;
+            k_trace_hybrid<L, ANY, PFK, 9, NR, 0, 0, true><<<grid_of(occ), 128, 0, st>>>(h->ds, d_rays, n, d_hits, ticket, h->hyb_nmin, h->hyb_period, h->hyb_min_idle,
+                                                                                     (uint32_t)h->hyb_pool, d_n, mult, h->info.num_nodes);
+        } else {
+            e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_trace_persistent<LAYOUT, ANY, true>, 128, 0);
+            if (e != cudaSuccess) return e;
+            k_trace_persistent<LAYOUT, ANY, true><<<grid_of(occ), 128, 0, st>>>(h->ds, d_rays, n, d_hits, ticket, d_n, mult, (uint32_t)h->packets_per_ticket);
+        }
+        return cudaGetLastError();
+    }
     // automatic choice: the hybrid-scheduled kernel, except coherent batches on BVH2, where 32-ray packets walking in
     // lockstep are cheaper (QBVH4: hybrid 10.8 vs packets 9.2 Grays/s on camera rays; BVH2: 10.5 vs 11.5)
     if (LAYOUT != MIROGPU_LAYOUT_CWBVH8 && (h->variant == 2 || (h->variant < 0 && !(coherent && LAYOUT == MIROGPU_LAYOUT_BVH2))) && n < 0xFF000000ull)
@@ -301,10 +322,13 @@ template <bool COUNT>
 cudaError_t launch_simple(mirogpu_scene* h, const mirogpu_ray* d_r, size_t n, mirogpu_hit* d_h, bool any, unsigned long long* d_c, cudaStream_t st)
 {
     const unsigned grid = (unsigned)((n + 127) / 128);
-#define MIRO_SIMPLE(L)                                                                                 \
-    {                                                                                                  \
-        if (any) k_trace_simple<L, true, COUNT><<<grid, 128, 0, st>>>(h->ds, d_r, n, d_h, d_c, nullptr, 1);  \
-        else k_trace_simple<L, false, COUNT><<<grid, 128, 0, st>>>(h->ds, d_r, n, d_h, d_c, nullptr, 1);     \
+#define MIRO_SIMPLE(L)                                                                                         \
+    {                                                                                                          \
+        if (h->non_triangles) {                                                                                \
+            if (any) k_trace_simple<L, true, COUNT, true><<<grid, 128, 0, st>>>(h->ds, d_r, n, d_h, d_c, nullptr, 1);  \
+            else k_trace_simple<L, false, COUNT, true><<<grid, 128, 0, st>>>(h->ds, d_r, n, d_h, d_c, nullptr, 1);     \
+        } else if (any) k_trace_simple<L, true, COUNT><<<grid, 128, 0, st>>>(h->ds, d_r, n, d_h, d_c, nullptr, 1);     \
+        else k_trace_simple<L, false, COUNT><<<grid, 128, 0, st>>>(h->ds, d_r, n, d_h, d_c, nullptr, 1);               \
     }
     if (h->layout == MIROGPU_LAYOUT_BVH4) MIRO_SIMPLE(MIROGPU_LAYOUT_BVH4)
     else if (h->layout == MIROGPU_LAYOUT_QBVH4) MIRO_SIMPLE(MIROGPU_LAYOUT_QBVH4)
@@ -523,7 +547,7 @@ int scene_create_impl(const mirogpu_scene_desc& d, const mirogpu_build_options* 
         if (!wide4 && bin.max_depth > MIRO_STACK) return fail(MIROGPU_ERR_INVALID_ARG, "tree deeper than the kernels' traversal stack");
         if (wide4 && flat.max_stack > MIRO_STACK4) return fail(MIROGPU_ERR_INVALID_ARG, "BVH4 tree needs a deeper traversal stack than the kernels carry");
         make_tri_records(verts, flat.order, hb.tris);
-        // sphere slots: (centre, prim id) (radius, 0, 0, 0) (0, 0, 0, 0) (0, kind = 1, 0, 0) -- see prim_test in traverse.cuh
+        // sphere slots: (centre, prim id) (0, 0, 0, 0) (0, 0, 0, 0) (0, kind = 1, radius, 0) -- see tri_test in traverse.cuh
         if (nspheres)
             for (TriRecord& r : hb.tris)
                 if (r.prim_id >= ntris) {
@@ -531,7 +555,7 @@ int scene_create_impl(const mirogpu_scene_desc& d, const mirogpu_build_options* 
                     const uint32_t id = r.prim_id;
                     memset(&r, 0, sizeof r);
                     r.ax = sp.center[0]; r.ay = sp.center[1]; r.az = sp.center[2]; r.prim_id = id;
-                    r.e1x = sp.radius; r.pad[0] = 1.0f;
+                    r.pad[0] = 1.0f; r.pad[1] = sp.radius;
                 }
         t2 = now_s();
         if (o.layout == MIROGPU_LAYOUT_BVH2) { hb.node_src = flat.nodes2.data(); hb.node_bytes = flat.nodes2.size() * sizeof(Bvh2Node); }
@@ -1068,10 +1092,16 @@ int mirogpu_photon_trace(mirogpu_handle h, int light_index, int caustic, uint32_
     if (e == cudaSuccess) e = cudaMemsetAsync(d_records, 0, rec_bytes, cudaStreamPerThread);
     if (e == cudaSuccess) {
         const unsigned grid = (count + 127) / 128;
-        if (h->layout == MIROGPU_LAYOUT_BVH2) k_photon_trace<MIROGPU_LAYOUT_BVH2><<<grid, 128, 0, cudaStreamPerThread>>>(h->ds, h->d_materials, em, d_counts, d_records);
-        else if (h->layout == MIROGPU_LAYOUT_BVH4) k_photon_trace<MIROGPU_LAYOUT_BVH4><<<grid, 128, 0, cudaStreamPerThread>>>(h->ds, h->d_materials, em, d_counts, d_records);
-        else if (h->layout == MIROGPU_LAYOUT_QBVH4) k_photon_trace<MIROGPU_LAYOUT_QBVH4><<<grid, 128, 0, cudaStreamPerThread>>>(h->ds, h->d_materials, em, d_counts, d_records);
-        else k_photon_trace<MIROGPU_LAYOUT_CWBVH8><<<grid, 128, 0, cudaStreamPerThread>>>(h->ds, h->d_materials, em, d_counts, d_records);
+#define MIRO_PT(L)                                                                                                                              \
+    {                                                                                                                                               \
+        if (h->non_triangles) k_photon_trace<L, true><<<grid, 128, 0, cudaStreamPerThread>>>(h->ds, h->d_materials, em, d_counts, d_records);       \
+        else k_photon_trace<L><<<grid, 128, 0, cudaStreamPerThread>>>(h->ds, h->d_materials, em, d_counts, d_records);                              \
+    }
+        if (h->layout == MIROGPU_LAYOUT_BVH2) MIRO_PT(MIROGPU_LAYOUT_BVH2)
+        else if (h->layout == MIROGPU_LAYOUT_BVH4) MIRO_PT(MIROGPU_LAYOUT_BVH4)
+        else if (h->layout == MIROGPU_LAYOUT_QBVH4) MIRO_PT(MIROGPU_LAYOUT_QBVH4)
+        else MIRO_PT(MIROGPU_LAYOUT_CWBVH8)
+#undef MIRO_PT
         e = cudaGetLastError();
     }
     if (e == cudaSuccess) e = cudaMemcpyAsync(counts, d_counts, count, cudaMemcpyDeviceToHost, cudaStreamPerThread);

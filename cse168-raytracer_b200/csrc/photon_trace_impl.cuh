@@ -40,7 +40,7 @@ __device__ __forceinline__ void uniform4(uint32_t seed, unsigned long long index
 
 __device__ __forceinline__ float average3(const float v[3]) { return xdiv(xadd(xadd(v[0], v[1]), v[2]), 3.0f); }   // Vector3.h:226-229
 
-template <int LAYOUT>
+template <int LAYOUT, bool NT = false>
 __global__ void __launch_bounds__(128) k_photon_trace(DeviceScene s, const mirogpu_material* __restrict__ mats, PhotonEmitter em,
                                                       unsigned char* __restrict__ counts, float* __restrict__ records)
 {
@@ -71,7 +71,7 @@ __global__ void __launch_bounds__(128) k_photon_trace(DeviceScene s, const mirog
         r.dx = dir[0]; r.dy = dir[1]; r.dz = dir[2]; r.tmin = 0.0f; r.tmax = MIROGPU_TMAX;
         ++depth;
         BestHit best;
-        trace_one<LAYOUT, false, false>(s, r, best, nullptr);
+        trace_one<LAYOUT, false, false, NT>(s, r, best, nullptr);
         if (best.prim == MIROGPU_MISS) break;
         mirogpu_hit h; h.t = best.t; h.prim_id = best.prim; h.beta = best.beta; h.gamma = best.gamma;
         const SurfacePoint sp = resolve_hit(load_shade_record(s, h.prim_id), h, r);

