@@ -119,6 +119,7 @@ struct mirogpu_scene {
     void* d_shade = nullptr;
     void* d_planes = nullptr;              // 2 float4 per plane (unbounded objects, tested after the walk)
     uint32_t non_triangles = 0;            // spheres + planes: their hit points need the ray (resolve)
+    int queue_mult = 4;                    // general wavefront, refractive scenes: path-queue capacity in units of the primary items (grows on overflow)
     std::vector<mirogpu_scene*> replicas;  // the other devices of a multi-device handle (this struct is the first device's replica)
     cudaStream_t mstream = nullptr;        // multi-device render: this replica's stream and its "rows are in place" event
     cudaEvent_t mevent = nullptr;
@@ -392,6 +393,7 @@ void apply_tuning_knobs(mirogpu_scene* h, int layout)
     if (const char* e = getenv("MIROGPU_SHORT")) h->hyb_short = atoi(e);
     if (const char* e = getenv("MIROGPU_STAGE")) h->hyb_stage = atoi(e);
     if (const char* e = getenv("MIROGPU_MINIDLE")) { const int v = atoi(e); if (v >= 1 && v <= 32) h->hyb_min_idle = v; }
+    if (const char* e = getenv("MIROGPU_QUEUE_MULT")) { const int v = atoi(e); if (v >= 1 && v <= 256) h->queue_mult = v; }   // tests: start small to exercise the overflow retry
 }
 
 // Uploads one replica of the scene to `dev`.  lb: a tree built on that device (device builders), or NULL.

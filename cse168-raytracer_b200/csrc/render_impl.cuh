@@ -649,9 +649,13 @@ __global__ void k_sum_wave_counters(const uint32_t* __restrict__ counters, unsig
 
 // d_rgb: full-frame float buffer (rows of this shard are written).  d_rgb8 (may be NULL): full-frame 8-bit
 // tone-mapped output (requires rp.tonemap semantics; used by mirogpu_render_rgb8).
-int render_device(mirogpu_scene* h, const mirogpu_camera& cam, const mirogpu_render_params& rp, float* d_rgb, unsigned char* d_rgb8,
-                  cudaStream_t st, std::string& err)
+// One attempt at a frame.  *overflow (general wavefront, refractive scenes): a wave produced more children than the path queues
+// hold (the reference recurses to TRACE_DEPTH with every child traced, Scene.cpp:301-335; a refractive hit spawns up to three) --
+// nothing has been delivered, the caller retries with larger queues.
+int render_device_once(mirogpu_scene* h, const mirogpu_camera& cam, const mirogpu_render_params& rp, float* d_rgb, unsigned char* d_rgb8,
+                       cudaStream_t st, std::string& err, bool* overflow)
 {
+    *overflow = false;
 #define RT(expr)                                                                     \
     do {                                                                             \
         cudaError_t _e = (expr);                                                     \
@@ -679,7 +683,7 @@ int render_device(mirogpu_scene* h, const mirogpu_camera& cam, const mirogpu_ren
     // Wave plan: diffuse-only Whitted frames have exactly one wave, diffuse-bounce frames exactly two (no host
     // round trip between waves: counts stay on the device); specular scenes read the queue size back each wave.
     const int static_waves = rp.mode == MIROGPU_RENDER_DIFFUSE_BOUNCE ? 2 : (whitted_secondary ? -1 : 1);
-    const size_t cap = items0 * (any_refractive && whitted_secondary ? 4 : 1);
+    const size_t cap = items0 * (any_refractive && whitted_secondary ? (size_t)h->queue_mult : 1);
     const bool use_pm = rp.use_photon_maps && (h->pm[0].stored > 0 || h->pm[1].stored > 0);
 
     RenderScratch& sc = h->scratch;
@@ -839,6 +843,7 @@ int render_device(mirogpu_scene* h, const mirogpu_camera& cam, const mirogpu_ren
                 RT(cudaMemcpyAsync(&next_n, counters + wave + 1, 4, cudaMemcpyDeviceToHost, st));
                 RT(cudaStreamSynchronize(st));
                 if (next_n == 0) break;
+                if (next_n > cap) { *overflow = true; return MIROGPU_OK; }   // children were dropped: this frame is void
                 bound = std::min<size_t>(cap, next_n);
             }
         }
@@ -867,6 +872,21 @@ int render_device(mirogpu_scene* h, const mirogpu_camera& cam, const mirogpu_ren
     h->stats_mult = shadows ? 1 + nl : 1;
     return MIROGPU_OK;
 #undef RT
+}
+
+// d_rgb: full-frame float buffer (rows of this shard are written).  d_rgb8 (may be NULL): full-frame 8-bit tone-mapped output.
+// Queues of the general wavefront start at 4x the primary items for refractive scenes and double (kept for the handle's later
+// frames) whenever a wave overflows them, so no child ray is ever dropped silently.
+int render_device(mirogpu_scene* h, const mirogpu_camera& cam, const mirogpu_render_params& rp, float* d_rgb, unsigned char* d_rgb8,
+                  cudaStream_t st, std::string& err)
+{
+    for (;;) {
+        bool overflow = false;
+        const int rc = render_device_once(h, cam, rp, d_rgb, d_rgb8, st, err, &overflow);
+        if (rc != MIROGPU_OK || !overflow) return rc;
+        if (h->queue_mult >= 256) { err = "path queues overflow even at 256x the primary rays"; return MIROGPU_ERR_UNSUPPORTED; }
+        h->queue_mult *= 2;
+    }
 }
 
 // ---- one handle, several devices: Scene::raytraceImage sharded by image rows -----------------------------------
