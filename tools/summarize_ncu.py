@@ -8,6 +8,9 @@ import csv, json, os, shutil, sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 tag = sys.argv[1] if len(sys.argv) > 1 else "r01"
 G = os.path.join(ROOT, "gpurun_out"); P = os.path.join(ROOT, "profiles")
+def src(name):   # tools/gpu_round2.sh prefixes its outputs with the tag; tools/gpu_round.sh does not
+    t = os.path.join(G, f"{tag}_{name}")
+    return t if os.path.exists(t) else os.path.join(G, name)
 KEEP = ["gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum", "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed",
         "lts__t_sector_hit_rate.pct", "l1tex__t_sector_hit_rate.pct", "l1tex__data_pipe_lsu_wavefronts.avg.pct_of_peak_sustained_elapsed",
         "l1tex__t_sectors_pipe_lsu_mem_global_op_ld.sum", "lts__t_sectors.sum", "lts__throughput.avg.pct_of_peak_sustained_elapsed",
@@ -21,13 +24,13 @@ KEEP = ["gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum
         "smsp__average_warps_issue_stalled_math_pipe_throttle_per_issue_active.ratio", "smsp__average_warps_issue_stalled_branch_resolving_per_issue_active.ratio",
         "smsp__average_warps_issue_stalled_short_scoreboard_per_issue_active.ratio", "l1tex__t_sectors_pipe_lsu_mem_local_op_ld.sum",
         "l1tex__t_sectors_pipe_lsu_mem_local_op_st.sum"]
-rows = list(csv.reader(open(os.path.join(G, "prof.raw.csv"))))
+rows = list(csv.reader(open(src("prof.raw.csv"))))
 hdr, units = rows[0], rows[1]
 launches = []
 for r in rows[2:]:
     d = dict(zip(hdr, r)); u = dict(zip(hdr, units))
     launches.append({"kernel": d["Kernel Name"], **{k: {"value": d[k], "unit": u[k]} for k in KEEP if k in d}})
-cmd = open(os.path.join(G, "ncu_full.log")).read()
+cmd = open(src("ncu_full.log")).read()
 out = {"command": "ncu --set full --clock-control none --import-source on -k regex:k_trace -s 7 -c 2 python bench.py --steps 2 --warmup 3 --no-cpu",
        "launches": launches}
 json.dump(out, open(os.path.join(P, f"{tag}_ncu_full.json"), "w"), indent=1)
@@ -49,7 +52,7 @@ summary = {"source": f"profiles/{tag}_ncu_full.json (ncu --set full --clock-cont
            "registers_per_thread": int(num(b["launch__registers_per_thread"]))}
 json.dump(summary, open(os.path.join(P, "ncu_summary.json"), "w"), indent=1)
 # launch list: keep only the CSV part
-with open(os.path.join(G, "launches.csv")) as f, open(os.path.join(P, f"{tag}_ncu_launches.csv"), "w") as o:
+with open(src("launches.csv")) as f, open(os.path.join(P, f"{tag}_ncu_launches.csv"), "w") as o:
     for line in f:
         if line.startswith('"'):
             o.write(line)
@@ -63,7 +66,7 @@ shares = {k: round(v / s, 4) for k, v in sorted(tot.items(), key=lambda x: -x[1]
 json.dump({"note": "share of summed device time per kernel over the whole ncu launch list (cold-cache, serialised)", "shares": shares},
           open(os.path.join(P, f"{tag}_ncu_launch_shares.json"), "w"), indent=1)
 for name in ("bench_full", "bench_reference", "bench_v0", "bench_v1", "bench_v2", "bench_cwbvh8"):
-    src = os.path.join(G, name + ".json")
-    if os.path.exists(src):
-        shutil.copy(src, os.path.join(P, f"{tag}_{name}.json"))
+    f = src(name + ".json")
+    if os.path.exists(f):
+        shutil.copy(f, os.path.join(P, f"{tag}_{name}.json"))
 print(json.dumps(summary, indent=1)); print(json.dumps(shares, indent=1))
