@@ -87,6 +87,7 @@ EXPORTS = [
     "mirogpu_photon_gather_device", "mirogpu_photon_trace", "mirogpu_photon_set_exact", "mirogpu_host_alloc", "mirogpu_host_free",
     "mirogpu_frame_max_device", "mirogpu_tonemap_rows_rgb8_device", "mirogpu_release_build_scratch",
     "mirogpu_scene_create_ex", "mirogpu_scene_devices", "mirogpu_resolve_hits_rays_device",
+    "mirogpu_photon_pass", "mirogpu_photon_download", "mirogpu_photon_balance",
 ]
 
 
@@ -157,6 +158,16 @@ def phong(kd=(1, 1, 1), ks=(0, 0, 0), kt=(0, 0, 0), shininess=1.0, refract_index
     m.shininess = float(shininess) if shininess >= 0 else float("inf")
     m.refract_index = float(refract_index)
     return m
+
+
+def photon_balance(photons, bbox_min, bbox_max, device=0):
+    """Photon_map::balance (PhotonMap.cpp:314-466) on the device for a store-order Photon array (entry 0 unused); returns the
+    heap-ordered copy."""
+    out = np.ascontiguousarray(photons).copy()
+    assert out.dtype == PHOTON_DTYPE
+    lo = np.ascontiguousarray(bbox_min, dtype=np.float32); hi = np.ascontiguousarray(bbox_max, dtype=np.float32)
+    _check(lib.mirogpu_photon_balance(int(device), _ptr(out), int(out.shape[0] - 1), _ptr(lo), _ptr(hi)))
+    return out
 
 
 class MiroScene:
@@ -330,6 +341,22 @@ class MiroScene:
         photons = np.ascontiguousarray(photons)
         assert photons.dtype == PHOTON_DTYPE
         _check(lib.mirogpu_photon_upload(self._h, int(which), _ptr(photons), int(photons.shape[0] - 1)))
+
+    def photon_pass(self, which, caustic, seed, target, max_emissions=0):
+        """Scene::tracePhotons / traceCausticPhotons on the device (emit, store, scale, balance); returns (emissions, stored)."""
+        em = ctypes.c_longlong(0); st = ctypes.c_int(0)
+        _check(lib.mirogpu_photon_pass(self._h, int(which), int(caustic), ctypes.c_uint32(seed), int(target), ctypes.c_longlong(max_emissions),
+                                       ctypes.byref(em), ctypes.byref(st)))
+        return int(em.value), int(st.value)
+
+    def photon_download(self, which):
+        """Map `which` as the reference's Photon array (stored + 1 records, heap order, entry 0 unused)."""
+        st = ctypes.c_int(0)
+        _check(lib.mirogpu_photon_download(self._h, int(which), None, 0, ctypes.byref(st)))
+        out = np.zeros(st.value + 1, dtype=PHOTON_DTYPE)
+        if st.value:
+            _check(lib.mirogpu_photon_download(self._h, int(which), _ptr(out), int(st.value), ctypes.byref(st)))
+        return out
 
     def photon_set_exact(self, which, exact):
         """exact=True: the reference's search verbatim, one query per thread (bit-identical); default False: one query per warp."""

@@ -60,9 +60,11 @@ def build_product(force=False, verbose=False, ptxas_v=False):
     _run([GXX] + GXX_FLAGS + ["-c", os.path.join(CSRC, "bvh_build.cpp"), "-o", os.path.join(bdir, "bvh_build.o")], verbose)
     flags = list(NVCC_FLAGS) + (["-Xptxas", "-v"] if ptxas_v else [])
     log = _run([NVCC] + flags + ["-c", os.path.join(CSRC, "mirogpu.cu"), "-o", os.path.join(bdir, "mirogpu.o")], verbose)
+    log2 = _run([NVCC] + flags + ["-c", os.path.join(CSRC, "photon_build.cu"), "-o", os.path.join(bdir, "photon_build.o")], verbose)
     if ptxas_v:
-        print(log)
-    _run([NVCC] + ARCH + ["-ccbin", GXX, "-shared", "-o", LIB, os.path.join(bdir, "mirogpu.o"), os.path.join(bdir, "bvh_build.o"),
+        print(log + log2)
+    _run([NVCC] + ARCH + ["-ccbin", GXX, "-shared", "-o", LIB, os.path.join(bdir, "mirogpu.o"), os.path.join(bdir, "photon_build.o"),
+                          os.path.join(bdir, "bvh_build.o"),
                           "-Xcompiler", "-fopenmp", "-lgomp"], verbose)
     return LIB
 

@@ -1,6 +1,9 @@
 // PhotonMap.h -- Photon_map of the host API layer (reference PhotonMap.h; H. W. Jensen's layout).
-// store / scale_photon_power / balance stay on the host (balance is SURVEY 8f-2, "next"); the balanced,
-// heap-ordered 28-byte Photon array is uploaded once and irradiance_estimate runs on the device.
+// Two ways to fill a map: (1) Scene::tracePhotons / traceCausticPhotons build it on the device in one call
+// (mirogpu_photon_pass: emission, store, scale, balance -- SURVEY 8f-2) and this object adopts it, mirroring the
+// 28-byte Photon array to the host only when data() / store() ask for it; (2) the caller store()s photons here, and
+// balance() sends the array through the device balance (mirogpu_photon_balance: the reference's heap order, ties
+// included) before attach() uploads it for irradiance_estimate.
 #ifndef MIROHOST_PHOTONMAP_H
 #define MIROHOST_PHOTONMAP_H
 #include <vector>
@@ -27,16 +30,17 @@ public:
     void attach(mirogpu_handle h, int which);   // uploads the balanced array to the device as map `which`
     int stored() const { return stored_photons; }
     bool balanced() const { return m_balanced; }
-    const Photon* data() const { return photons; }
+    const Photon* data() const { syncHost(); return photons; }
+    void adoptDevice(mirogpu_handle h, int which, int stored);   // the map mirogpu_photon_pass built as map `which` of h
+    static int balanceDevice;                                     // CUDA device balance() runs on (default 0)
 private:
-    void balance_segment(Photon** pbal, Photon** porg, const int index, const int start, const int end);
-    void balance_segment_box(Photon** pbal, Photon** porg, int index, int start, int end, const float* lo3, const float* hi3);
-    void median_split(Photon** p, const int start, const int end, const int median, const int axis);
+    void syncHost() const;
     Photon* photons;
     int stored_photons, half_stored_photons, max_photons, prev_scale;
     float bbox_min[3], bbox_max[3];
     mirogpu_handle m_handle;
     int m_which;
-    bool m_balanced;
+    bool m_balanced, m_on_device;
+    mutable bool m_host_stale;
 };
 #endif

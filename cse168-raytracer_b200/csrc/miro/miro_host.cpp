@@ -596,39 +596,16 @@ long Scene::tracePhotonPass(Photon_map& map, int which, int target, bool caustic
         if (!map.balanced()) map.balance();                    // (a map the caller filled and balanced by hand stays as it is)
         return 0;
     }
-    long totalPhotons = 0;                                     // emissions consumed
-    int photonsAdded = 0;                                      // photons stored; neither is reset per light (Scene.cpp:360-361)
-    const long kMaxEmissions = 1L << 28;                       // the reference loops forever when nothing can be stored
-    std::vector<uint8_t> counts;
-    std::vector<float> records;
-    for (size_t l = 0; l < m_lights.size(); ++l) {
-        if (dynamic_cast<DirectionalAreaLight*>(m_lights[l]) == 0) continue;
-        uint64_t next = 0;                                     // emission index of this light = its random stream
-        uint32_t batch = 65536;
-        while (photonsAdded < target && totalPhotons < kMaxEmissions) {
-            counts.resize(batch); records.resize((size_t)batch * 45);
-            if (mirogpu_photon_trace(m_bvh.handle(), (int)l, caustic ? 1 : 0, renderSeed + (caustic ? 1u : 0u), ((uint64_t)l << 40) | next, batch,
-                                     counts.data(), records.data()) != MIROGPU_OK) die("Scene::tracePhotons");
-            const int before = photonsAdded;
-            uint32_t used = 0;
-            for (uint32_t i = 0; i < batch && photonsAdded < target; ++i, ++used) {   // "if (photonsAdded < PhotonsPerLightSource)", in emission order
-                const float* r = records.data() + (size_t)i * 45;
-                for (int j = 0; j < counts[i]; ++j) map.store(r + 9 * j, r + 9 * j + 3, r + 9 * j + 6);
-                photonsAdded += counts[i];
-                totalPhotons++;
-            }
-            next += used;
-            // size the next batch from the observed yield (photons per emission), with some slack
-            const double yield = std::max(1e-4, (double)(photonsAdded - before) / (double)std::max<uint32_t>(used, 1));
-            const double want = (double)(target - photonsAdded) / yield * 1.05 + 1024.0;
-            batch = (uint32_t)std::min(4194304.0, std::max(4096.0, want));
-        }
-    }
-    if (totalPhotons >= kMaxEmissions) fprintf(stderr, "Scene::tracePhotons: gave up after %ld emissions (%d of %d photons stored)\n", totalPhotons, photonsAdded, target);
-    if (totalPhotons > 0) map.scale_photon_power(1.0f / (float)totalPhotons);
-    map.balance();
-    if (map.stored() > 0) map.attach(m_bvh.handle(), which);
-    return totalPhotons;
+    // The whole pass -- emission loop with the reference's stop rule, store, scale_photon_power, balance -- runs on the
+    // device (mirogpu_photon_pass); the map is attached there and mirrored to this object only when somebody reads it.
+    long long emissions = 0;
+    int stored = 0;
+    const long long kMaxEmissions = 1LL << 28;                 // the reference loops forever when nothing can be stored
+    if (mirogpu_photon_pass(m_bvh.handle(), which, caustic ? 1 : 0, renderSeed + (caustic ? 1u : 0u), target, kMaxEmissions,
+                            &emissions, &stored) != MIROGPU_OK) die("Scene::tracePhotons");
+    if (emissions >= kMaxEmissions) fprintf(stderr, "Scene::tracePhotons: gave up after %lld emissions (%d of %d photons stored)\n", emissions, stored, target);
+    map.adoptDevice(m_bvh.handle(), which, stored);
+    return (long)emissions;
 }
 
 // Scene.cpp:232-266 for UV-lookup materials with zero bump height: the perturbation vanishes, N is normalised.
@@ -688,22 +665,53 @@ void Scene::raytraceImage(Camera* cam, Image* img)
 
 // ================================= Photon_map ================================================================
 Photon_map::Photon_map(int max_phot)
-    : photons(0), stored_photons(0), half_stored_photons(0), max_photons(max_phot), prev_scale(1), m_handle(0), m_which(0), m_balanced(false)
+    : photons(0), stored_photons(0), half_stored_photons(0), max_photons(max_phot), prev_scale(1), m_handle(0), m_which(0), m_balanced(false),
+      m_on_device(false), m_host_stale(false)
 {
     photons = (Photon*)malloc(sizeof(Photon) * ((size_t)std::max(max_photons, 0) + 1));
+    memset(photons, 0, sizeof(Photon));
     bbox_min[0] = bbox_min[1] = bbox_min[2] = 1e8f;
     bbox_max[0] = bbox_max[1] = bbox_max[2] = -1e8f;
 }
 
 Photon_map::~Photon_map() { free(photons); }
 
+int Photon_map::balanceDevice = 0;
+
+// A map the device built (mirogpu_photon_pass): the host array is filled in on first use.
+void Photon_map::adoptDevice(mirogpu_handle h, int which, int stored)
+{
+    m_handle = h; m_which = which;
+    stored_photons = stored; half_stored_photons = stored / 2 - 1; prev_scale = stored;
+    m_balanced = true; m_on_device = stored > 0; m_host_stale = stored > 0;
+}
+
+void Photon_map::syncHost() const
+{
+    if (!m_host_stale) return;
+    Photon_map* self = const_cast<Photon_map*>(this);
+    if (stored_photons > max_photons) {
+        self->max_photons = stored_photons;
+        self->photons = (Photon*)realloc(photons, sizeof(Photon) * ((size_t)max_photons + 1));
+    }
+    int n = 0;
+    if (mirogpu_photon_download(m_handle, m_which, self->photons, max_photons, &n) != MIROGPU_OK || n != stored_photons) die("Photon_map: device map download");
+    for (int i = 1; i <= n; ++i)
+        for (int k = 0; k < 3; ++k) {
+            self->bbox_min[k] = std::min(bbox_min[k], photons[i].pos[k]);
+            self->bbox_max[k] = std::max(bbox_max[k], photons[i].pos[k]);
+        }
+    self->m_host_stale = false;
+}
+
 void Photon_map::store(const float power[3], const float pos[3], const float dir[3])
 {
+    syncHost();
     if (stored_photons >= max_photons) {        // grow instead of the reference's silent drop at capacity
         max_photons = max_photons ? 2 * max_photons : 1024;
         photons = (Photon*)realloc(photons, sizeof(Photon) * ((size_t)max_photons + 1));
     }
-    m_balanced = false;
+    m_balanced = false; m_on_device = false;
     Photon* const node = &photons[++stored_photons];
     for (int i = 0; i < 3; ++i) {
         node->pos[i] = pos[i];
@@ -711,6 +719,7 @@ void Photon_map::store(const float power[3], const float pos[3], const float dir
         bbox_max[i] = std::max(bbox_max[i], node->pos[i]);
         node->power[i] = power[i];
     }
+    node->plane = 0;
     // direction quantised to two bytes (PhotonMap.cpp:275-287)
     const int theta = int(acos(dir[2]) * (256.0 / M_PI));
     node->theta = theta > 255 ? 255 : (unsigned char)theta;
@@ -720,84 +729,21 @@ void Photon_map::store(const float power[3], const float pos[3], const float dir
 
 void Photon_map::scale_photon_power(const float scale)
 {
+    syncHost();
+    m_on_device = false;
     for (int i = prev_scale; i <= stored_photons; ++i)
         for (int k = 0; k < 3; ++k) photons[i].power[k] *= scale;
     prev_scale = stored_photons;
 }
 
-// Quickselect partition about `median` on one axis (PhotonMap.cpp:371-402); the pivot / scan order decides
-// which photon lands where among equal keys, so it follows Jensen's routine step for step.
-void Photon_map::median_split(Photon** p, const int start, const int end, const int median, const int axis)
-{
-    int left = start, right = end;
-    while (right > left) {
-        const float v = p[right]->pos[axis];
-        int i = left - 1, j = right;
-        for (;;) {
-            while (p[++i]->pos[axis] < v) {}
-            while (p[--j]->pos[axis] > v && j > left) {}
-            if (i >= j) break;
-            std::swap(p[i], p[j]);
-        }
-        std::swap(p[i], p[right]);
-        if (i >= median) right = i - 1;
-        if (i <= median) left = i + 1;
-    }
-}
-
-// PhotonMap.cpp:404-466.  The reference narrows the member bounding box around each recursive call and restores it
-// afterwards; here the box travels by value, which makes the two sub-segments independent -- they own disjoint runs of porg
-// and disjoint heap slots of pbal -- so large ones are balanced as parallel tasks.  Same medians, same axes, same array.
-void Photon_map::balance_segment_box(Photon** pbal, Photon** porg, int index, int start, int end, const float* lo3, const float* hi3)
-{
-    float lo[3] = {lo3[0], lo3[1], lo3[2]}, hi[3] = {hi3[0], hi3[1], hi3[2]};
-    // left-balanced median (Jensen, "Realistic Image Synthesis using Photon Mapping", ch. 6)
-    const int count = end - start + 1;
-    int median = 1;
-    while (4 * median <= count) median += median;
-    if (3 * median <= count) median = 2 * median + start - 1; else median = end - median + 1;
-    int axis = 2;
-    const float ex = hi[0] - lo[0], ey = hi[1] - lo[1], ez = hi[2] - lo[2];
-    if (ex > ey && ex > ez) axis = 0; else if (ey > ez) axis = 1;
-    median_split(porg, start, end, median, axis);
-    pbal[index] = porg[median];
-    pbal[index]->plane = (short)axis;
-    const float split = pbal[index]->pos[axis];
-    const bool left_rec = median > start && start < median - 1, right_rec = median < end && median + 1 < end;
-    if (median > start && !left_rec) pbal[2 * index] = porg[start];
-    if (median < end && !right_rec) pbal[2 * index + 1] = porg[end];
-    float lhi[3] = {hi[0], hi[1], hi[2]}, rlo[3] = {lo[0], lo[1], lo[2]};
-    lhi[axis] = split; rlo[axis] = split;
-    if (count > 16384 && left_rec && right_rec) {
-#pragma omp task default(shared) firstprivate(index, start, median, lo, lhi)
-        balance_segment_box(pbal, porg, 2 * index, start, median - 1, lo, lhi);
-#pragma omp task default(shared) firstprivate(index, median, end, rlo, hi)
-        balance_segment_box(pbal, porg, 2 * index + 1, median + 1, end, rlo, hi);
-#pragma omp taskwait
-    } else {
-        if (left_rec) balance_segment_box(pbal, porg, 2 * index, start, median - 1, lo, lhi);
-        if (right_rec) balance_segment_box(pbal, porg, 2 * index + 1, median + 1, end, rlo, hi);
-    }
-}
-
-void Photon_map::balance_segment(Photon** pbal, Photon** porg, const int index, const int start, const int end)
-{
-#pragma omp parallel
-#pragma omp single nowait
-    balance_segment_box(pbal, porg, index, start, end, bbox_min, bbox_max);
-}
-
+// PhotonMap.cpp:314-466 on the device (mirogpu_photon_balance): the array comes back in the reference's heap order --
+// the quickselect of median_split is evaluated round for round there, so equal keys end up where Jensen's code puts them.
 void Photon_map::balance(void)
 {
+    if (m_on_device && m_balanced) return;                     // the device pass balanced it
+    syncHost();
     if (stored_photons > 1) {
-        std::vector<Photon*> pa1((size_t)2 * stored_photons + 4, (Photon*)0), pa2((size_t)stored_photons + 1);
-        for (int i = 0; i <= stored_photons; ++i) pa2[i] = &photons[i];
-        balance_segment(pa1.data(), pa2.data(), 1, 1, stored_photons);
-        // permute the records in place into heap order by following cycles
-        std::vector<Photon> ordered((size_t)stored_photons + 1);
-        ordered[0] = photons[0];
-        for (int i = 1; i <= stored_photons; ++i) ordered[i] = *pa1[i];
-        memcpy(photons, ordered.data(), sizeof(Photon) * ((size_t)stored_photons + 1));
+        if (mirogpu_photon_balance(balanceDevice, photons, stored_photons, bbox_min, bbox_max) != MIROGPU_OK) die("Photon_map::balance");
     }
     half_stored_photons = stored_photons / 2 - 1;
     m_balanced = true;
@@ -805,6 +751,8 @@ void Photon_map::balance(void)
 
 void Photon_map::attach(mirogpu_handle h, int which)
 {
+    if (m_on_device && h == m_handle && which == m_which) return;   // built there already
+    syncHost();
     m_handle = h; m_which = which;
     if (mirogpu_photon_upload(h, which, photons, stored_photons) != MIROGPU_OK) die("Photon_map::attach");
 }

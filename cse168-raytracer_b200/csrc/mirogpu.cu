@@ -1061,15 +1061,15 @@ int mirogpu_tonemap_rows_rgb8_device(mirogpu_handle h, const float* d_rgb, int w
     return MIROGPU_OK;
 }
 
-int mirogpu_photon_trace(mirogpu_handle h, int light_index, int caustic, uint32_t seed, uint64_t first_emission, uint32_t count,
-                         uint8_t* counts, float* records)
+namespace {
+// k_photon_trace for `count` emissions of one DirectionalAreaLight into device buffers (counts: count bytes, records:
+// count * 45 floats; only the first counts[i] records of an emission are written).
+int photon_trace_launch(mirogpu_scene* h, int light_index, int caustic, uint32_t seed, uint64_t first_emission, uint32_t count,
+                        unsigned char* d_counts, float* d_records, cudaStream_t st)
 {
-    if (!h || (count && (!counts || !records))) return fail(MIROGPU_ERR_INVALID_ARG, "NULL argument");
     if (light_index < 0 || (size_t)light_index >= h->h_lights.size()) return fail(MIROGPU_ERR_INVALID_ARG, "light index out of range");
     const mirogpu_light& L = h->h_lights[(size_t)light_index];
     if (L.kind != 1) return fail(MIROGPU_ERR_INVALID_ARG, "photons are emitted from DirectionalAreaLights only (Scene.cpp:368)");
-    if (count == 0) return MIROGPU_OK;
-    CUDA_TRY(cudaSetDevice(h->device));
     PhotonEmitter em; memset(&em, 0, sizeof em);
     // getTangents (Utility.h:25-31), as SquareLight::preCalc calls it on the light normal
     const float n[3] = {L.normal[0], L.normal[1], L.normal[2]};
@@ -1086,35 +1086,137 @@ int mirogpu_photon_trace(mirogpu_handle h, int light_index, int caustic, uint32_
         em.power[k] = L.color[k] * L.wattage * area;
     }
     em.radius = L.radius; em.caustic = caustic ? 1 : 0; em.seed = seed; em.first = first_emission; em.count = count;
-    unsigned char* d_counts = nullptr;
-    float* d_records = nullptr;
-    const size_t rec_bytes = (size_t)count * 9 * MIRO_PHOTON_MAX_RECORDS * sizeof(float);
-    cudaError_t e = cudaMalloc(&d_counts, count);
-    if (e == cudaSuccess) e = cudaMalloc(&d_records, rec_bytes);
-    if (e == cudaSuccess) e = cudaMemsetAsync(d_records, 0, rec_bytes, cudaStreamPerThread);
-    if (e == cudaSuccess) {
-        const unsigned grid = (count + 127) / 128;
-#define MIRO_PT(L)                                                                                                                              \
-    {                                                                                                                                               \
-        if (h->non_triangles) k_photon_trace<L, true><<<grid, 128, 0, cudaStreamPerThread>>>(h->ds, h->d_materials, em, d_counts, d_records);       \
-        else k_photon_trace<L><<<grid, 128, 0, cudaStreamPerThread>>>(h->ds, h->d_materials, em, d_counts, d_records);                              \
+    const unsigned grid = (count + 127) / 128;
+#define MIRO_PT(L)                                                                                                      \
+    {                                                                                                                       \
+        if (h->non_triangles) k_photon_trace<L, true><<<grid, 128, 0, st>>>(h->ds, h->d_materials, em, d_counts, d_records);       \
+        else k_photon_trace<L><<<grid, 128, 0, st>>>(h->ds, h->d_materials, em, d_counts, d_records);                              \
     }
-        if (h->layout == MIROGPU_LAYOUT_BVH2) MIRO_PT(MIROGPU_LAYOUT_BVH2)
-        else if (h->layout == MIROGPU_LAYOUT_BVH4) MIRO_PT(MIROGPU_LAYOUT_BVH4)
-        else if (h->layout == MIROGPU_LAYOUT_QBVH4) MIRO_PT(MIROGPU_LAYOUT_QBVH4)
-        else MIRO_PT(MIROGPU_LAYOUT_CWBVH8)
+    if (h->layout == MIROGPU_LAYOUT_BVH2) MIRO_PT(MIROGPU_LAYOUT_BVH2)
+    else if (h->layout == MIROGPU_LAYOUT_BVH4) MIRO_PT(MIROGPU_LAYOUT_BVH4)
+    else if (h->layout == MIROGPU_LAYOUT_QBVH4) MIRO_PT(MIROGPU_LAYOUT_QBVH4)
+    else MIRO_PT(MIROGPU_LAYOUT_CWBVH8)
 #undef MIRO_PT
-        e = cudaGetLastError();
-    }
-    if (e == cudaSuccess) e = cudaMemcpyAsync(counts, d_counts, count, cudaMemcpyDeviceToHost, cudaStreamPerThread);
-    if (e == cudaSuccess) e = cudaMemcpyAsync(records, d_records, rec_bytes, cudaMemcpyDeviceToHost, cudaStreamPerThread);
+    const cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return fail(MIROGPU_ERR_CUDA, std::string("photon_trace: ") + cudaGetErrorString(e));
+    return MIROGPU_OK;
+}
+}  // namespace
+
+int mirogpu_photon_trace(mirogpu_handle h, int light_index, int caustic, uint32_t seed, uint64_t first_emission, uint32_t count,
+                         uint8_t* counts, float* records)
+{
+    if (!h || (count && (!counts || !records))) return fail(MIROGPU_ERR_INVALID_ARG, "NULL argument");
+    if (light_index < 0 || (size_t)light_index >= h->h_lights.size()) return fail(MIROGPU_ERR_INVALID_ARG, "light index out of range");
+    if (h->h_lights[(size_t)light_index].kind != 1) return fail(MIROGPU_ERR_INVALID_ARG, "photons are emitted from DirectionalAreaLights only (Scene.cpp:368)");
+    if (count == 0) return MIROGPU_OK;
+    CUDA_TRY(cudaSetDevice(h->device));
+    DevBuf bc, br;
+    const size_t rec_bytes = (size_t)count * 9 * MIRO_PHOTON_MAX_RECORDS * sizeof(float);
+    cudaError_t e = bc.alloc(count);
+    if (e == cudaSuccess) e = br.alloc(rec_bytes);
+    if (e == cudaSuccess) e = cudaMemsetAsync(br.p, 0, rec_bytes, cudaStreamPerThread);
+    if (e != cudaSuccess) { (void)cudaGetLastError(); return fail(cuda_code(e), std::string("photon_trace staging: ") + cudaGetErrorString(e)); }
+    const int rc = photon_trace_launch(h, light_index, caustic, seed, first_emission, count, bc.as<unsigned char>(), br.as<float>(), cudaStreamPerThread);
+    if (rc != MIROGPU_OK) return rc;
+    e = cudaMemcpyAsync(counts, bc.p, count, cudaMemcpyDeviceToHost, cudaStreamPerThread);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(records, br.p, rec_bytes, cudaMemcpyDeviceToHost, cudaStreamPerThread);
     if (e == cudaSuccess) e = cudaStreamSynchronize(cudaStreamPerThread);
-    cudaFree(d_counts); cudaFree(d_records);
     if (e != cudaSuccess) return fail(MIROGPU_ERR_CUDA, std::string("photon_trace: ") + cudaGetErrorString(e));
     {
         std::lock_guard<std::mutex> lk(h->mtx);
         h->last_rays = 0; h->last_launches = 1; h->stats_batches = 0;
     }
+    return MIROGPU_OK;
+}
+
+// Scene::tracePhotons / traceCausticPhotons (Scene.cpp:351-472) without leaving the device: emit in batches, store in
+// emission order under the reference's stop rule, scale by 1 / emissions, balance, lay out the gather records.
+int mirogpu_photon_pass(mirogpu_handle h, int which, int caustic, uint32_t seed, int target, long long max_emissions,
+                        long long* emissions_out, int* stored_out)
+{
+    if (!h || which < 0 || which > 1 || target < 0) return fail(MIROGPU_ERR_INVALID_ARG, "bad argument");
+    if (max_emissions <= 0) max_emissions = 1ll << 28;
+    CUDA_TRY(cudaSetDevice(h->device));
+    cudaStream_t st = cudaStreamPerThread;
+    long long total = 0;
+    int stored = 0;
+    const bool timing = getenv("MIROGPU_TIMING") != nullptr;
+    const double t_begin = now_s();
+    double t_trace_store = 0.0, t_alloc = 0.0;
+    PhotonBuild b;
+    CUDA_TRY(b.alloc(target + 8));
+    DevBuf bc, br;
+    uint32_t buf_cap = 0;
+    for (size_t l = 0; l < h->h_lights.size() && target > 0; ++l) {
+        if (h->h_lights[l].kind != 1) continue;                // "Temporary hack" of the reference: only directional area lights emit
+        uint64_t next = 0;                                     // emission index of this light = its random stream
+        uint32_t batch = 65536;
+        while (stored < target && total < max_emissions) {
+            if (batch > buf_cap) {
+                const double t0 = now_s();
+                cudaFree(bc.p); cudaFree(br.p); bc.p = br.p = nullptr;
+                CUDA_TRY(bc.alloc(batch));
+                CUDA_TRY(br.alloc((size_t)batch * 9 * MIRO_PHOTON_MAX_RECORDS * sizeof(float)));
+                buf_cap = batch;
+                t_alloc += now_s() - t0;
+            }
+            const double t1 = now_s();
+            const int rc = photon_trace_launch(h, (int)l, caustic, seed, ((uint64_t)l << 40) | next, batch, bc.as<unsigned char>(), br.as<float>(), st);
+            if (rc != MIROGPU_OK) return rc;
+            int used = 0, after = stored;
+            CUDA_TRY(b.store_batch(bc.as<unsigned char>(), br.as<float>(), batch, stored, target, st, &used, &after));
+            const int before = stored;
+            stored = after; total += used; next += (uint64_t)used;
+            t_trace_store += now_s() - t1;
+            if (timing) fprintf(stderr, "mirogpu_photon_pass: light %zu batch %u used %d stored %d\n", l, batch, used, stored);
+            // size the next batch from the observed yield (photons per emission), with some slack
+            const double yield = std::max(1e-4, (double)(stored - before) / (double)std::max(used, 1));
+            const double want = (double)(target - stored) / yield * 1.05 + 1024.0;
+            batch = (uint32_t)std::min(4194304.0, std::max(4096.0, want));
+        }
+    }
+    if (total > 0) CUDA_TRY(b.scale(1, stored, 1.0f / (float)total, st));   // Scene.cpp:400
+    std::string err;
+    int rc;
+    {
+        std::lock_guard<std::mutex> lk(h->mtx);
+        rc = h->pm[which].build_from_store(b, stored, true, st, err);
+        h->last_rays = 0; h->last_launches = 1; h->stats_batches = 0;
+    }
+    if (rc != MIROGPU_OK) return fail(rc, err);
+    if (timing) fprintf(stderr, "mirogpu_photon_pass: total %.2f ms (buffers %.2f, trace + store %.2f, scale + balance + records %.2f)\n",
+                        (now_s() - t_begin) * 1e3, t_alloc * 1e3, t_trace_store * 1e3, (now_s() - t_begin - t_alloc - t_trace_store) * 1e3);
+    for (mirogpu_scene* r : h->replicas) {
+        CUDA_TRY(cudaSetDevice(r->device));
+        std::lock_guard<std::mutex> lk(r->mtx);
+        rc = r->pm[which].clone_from(h->pm[which], h->device, r->device, err);
+        if (rc != MIROGPU_OK) { cudaSetDevice(h->device); return fail(rc, err); }
+    }
+    CUDA_TRY(cudaSetDevice(h->device));
+    if (emissions_out) *emissions_out = total;
+    if (stored_out) *stored_out = stored;
+    return MIROGPU_OK;
+}
+
+int mirogpu_photon_download(mirogpu_handle h, int which, void* photons, int capacity, int* stored)
+{
+    if (!h || which < 0 || which > 1) return fail(MIROGPU_ERR_INVALID_ARG, "bad argument");
+    CUDA_TRY(cudaSetDevice(h->device));
+    std::lock_guard<std::mutex> lk(h->mtx);
+    const int n = h->pm[which].stored;
+    if (stored) *stored = n;
+    if (!photons) return MIROGPU_OK;                           // size query
+    if (capacity < n) return fail(MIROGPU_ERR_INVALID_ARG, "photon_download: capacity below the stored count");
+    CUDA_TRY(h->pm[which].export28(photons, cudaStreamPerThread));
+    return MIROGPU_OK;
+}
+
+int mirogpu_photon_balance(int device, void* photons, int stored, const float bbox_min[3], const float bbox_max[3])
+{
+    if (stored < 0 || (stored && (!photons || !bbox_min || !bbox_max))) return fail(MIROGPU_ERR_INVALID_ARG, "bad argument");
+    CUDA_TRY(cudaSetDevice(device));
+    CUDA_TRY(photon_balance_host_array(photons, stored, bbox_min, bbox_max, cudaStreamPerThread));
     return MIROGPU_OK;
 }
 

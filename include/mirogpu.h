@@ -18,6 +18,10 @@
  *   mirogpu_photon_gather       <- Photon_map::irradiance_estimate / locate_photons   PhotonMap.cpp:81-243
  *   mirogpu_photon_trace        <- Scene::tracePhoton over the emissions of Scene::tracePhotons /
  *                                  traceCausticPhotons                                     Scene.cpp:351-472, 526-641
+ *   mirogpu_photon_pass         <- Scene::tracePhotons / traceCausticPhotons as a whole: emission loop with its stop
+ *                                  rule, Photon_map::store, scale_photon_power, balance      Scene.cpp:351-472, PhotonMap.cpp:246-466
+ *   mirogpu_photon_balance      <- Photon_map::balance on a caller-filled array              PhotonMap.cpp:314-466
+ *   mirogpu_photon_download     <- the Photon array a balanced Photon_map holds              PhotonMap.h:16-22, 81-83
  *
  * Conventions: every function returns an int status (MIROGPU_OK = 0), never throws, keeps no global
  * state besides the per-thread last-error string, and works on an opaque scene handle.  The caller owns
@@ -328,6 +332,25 @@ int mirogpu_photon_upload(mirogpu_handle h, int which, const void* photons, int 
  * The walk is a pure function of (seed, emission index): any split of the range into calls / GPUs gives the same map. */
 int mirogpu_photon_trace(mirogpu_handle h, int light_index, int caustic, uint32_t seed, uint64_t first_emission, uint32_t count,
                          uint8_t* counts, float* records);
+/* Scene::tracePhotons (caustic = 0) / traceCausticPhotons (caustic = 1) as one call that never leaves the device
+ * (Scene.cpp:351-472): for every DirectionalAreaLight, in order, emissions are walked in batches (mirogpu_photon_trace's
+ * kernel, emission index = random stream, first index (light << 40)), their records stored in emission order while fewer
+ * than `target` photons are stored -- the reference's sequential "if (photonsAdded < PhotonsPerLightSource)" rule,
+ * evaluated with a prefix sum over the per-emission record counts -- with Photon_map::store's direction quantisation and
+ * bounding box (PhotonMap.cpp:246-288); powers are scaled by 1 / emissions (Scene.cpp:400, PhotonMap.cpp:297-306); the
+ * map is balanced into the reference's left-balanced heap order (PhotonMap.cpp:314-466: Jensen's median_split is
+ * evaluated round for round, each Hoare partition in parallel, so the array equals Photon_map::balance's also among equal
+ * keys) and becomes map `which` of the handle (all devices of a multi-device handle).  max_emissions <= 0: 2^28 (the
+ * reference loops forever when nothing can be stored).  emissions_out / stored_out may be NULL. */
+int mirogpu_photon_pass(mirogpu_handle h, int which, int caustic, uint32_t seed, int target, long long max_emissions,
+                        long long* emissions_out, int* stored_out);
+/* Map `which` as (stored + 1) records of the reference's 28-byte Photon in heap order (entry 0 unused); photons == NULL
+ * only reports the count.  capacity = records the buffer holds beyond entry 0. */
+int mirogpu_photon_download(mirogpu_handle h, int which, void* photons, int capacity, int* stored);
+/* Photon_map::balance (PhotonMap.cpp:314-466) on device `device` for a caller-filled array of (stored + 1) 28-byte Photon
+ * records (entry 0 unused), in place: same heap order, `plane` set on the inner nodes.  bbox_min / bbox_max: the box
+ * Photon_map::store accumulated (the split axes derive from it, PhotonMap.cpp:431-436).  Needs no scene handle. */
+int mirogpu_photon_balance(int device, void* photons, int stored, const float bbox_min[3], const float bbox_max[3]);
 /* Gather search of map `which`.  exact = 0 (default): one query per warp -- a shared stack of kd nodes and a shared
  * candidate buffer, 32 nodes tested per step, the k-th distance found by bisection when the buffer fills; it ends with the
  * same k nearest photons as the reference's search, summed in another order (estimates agree to ~1e-6 relative; k <= 512).
