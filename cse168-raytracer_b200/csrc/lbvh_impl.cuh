@@ -518,7 +518,7 @@ inline cudaError_t build_lbvh_device(const float* tri_vertices, uint32_t ntris, 
             if (const char* ev = getenv("MIROGPU_PLOC_RADIUS")) radius = std::min(std::max(atoi(ev), 1), MIRO_PLOC_MAX_RADIUS);
             const bool dbg = getenv("MIROGPU_DEBUG_BUILD") != nullptr;
             const auto tp0 = std::chrono::steady_clock::now();
-            int rounds = 0;
+            int rounds = 0, slow = 0;
             for (int round = 0; m > 1 && round < 4096; ++round) {
                 ++rounds;
                 if (dbg && (round < 40 || round % 50 == 0)) fprintf(stderr, "ploc round %d m %d t %.3f ms\n", round, m, 1e3 * std::chrono::duration<double>(std::chrono::steady_clock::now() - tp0).count());
@@ -531,7 +531,11 @@ inline cudaError_t build_lbvh_device(const float* tri_vertices, uint32_t ntris, 
                 LB(cudaMemcpyAsync(&new_m, d_m, 4, cudaMemcpyDeviceToHost, st));
                 LB(cudaStreamSynchronize(st));
                 if (new_m >= m || new_m < 1) { cleanup(); cudaFree(o.d_geom); o.d_geom = nullptr; return cudaErrorNotSupported; }   // cannot happen: a mutual pair always exists
+                // thousands of coincident boxes merge one pair per round: give up after 24 rounds in a row that merged less
+                // than a thousandth of the clusters instead of grinding on to the round cap (the caller falls back to the host build)
+                slow = (long long)(m - new_m) * 1024 < m ? slow + 1 : 0;
                 m = new_m; cur ^= 1;
+                if (slow >= 24) break;
             }
             k_ploc_ranges<<<(unsigned)((2 * n - 1 + 255) / 256), 256, 0, st>>>((int)(2 * n - 1), child, parent, size, range, pc + 1);
             uint32_t h_pc[2] = {0, 0};

@@ -76,3 +76,63 @@ def reduce_max(value, group=None):
         return value
     dist.all_reduce(value, op=dist.ReduceOp.MAX, group=group)
     return value
+
+
+class FramePipeline:
+    """Frames of a sequence kept in flight across ranks: while this rank renders frame i + 1, frame i's exchange -- the
+    all_reduce(max) of the tone map's one frame-wide constant (Scene.cpp:157-164), the tone map of this rank's rows, the
+    NCCL all_gather of the 8-bit row shards and rank 0's copy into page-locked host memory -- runs on a side stream.
+    Each slot owns its float frame, 8-bit frame, gather buffers and host frame, so a frame's data is never touched by
+    its successor; a slot is reused only after its previous exchange finished (stream-ordered, no host sync).
+
+        pipe = FramePipeline(scene, height, width, world, rank, device)
+        for cam, params in sequence:
+            slot = pipe.submit(cam, params)          # params carry this rank's rows (rows_of_rank)
+            rays += pipe.rays_traced(slot)           # waits for the RENDER of this frame only
+        pipe.drain()                                 # all exchanges done; pipe.host_frame(slot) on rank 0 is complete
+    """
+
+    def __init__(self, scene, height, width, world, rank, device, depth=2, group=None):
+        self.S, self.world, self.rank, self.group = scene, world, rank, group
+        self.rows, _ = rows_of_rank(height, world, rank)
+        self.side = torch.cuda.Stream(device)
+        self.slots = []
+        for _ in range(depth):
+            self.slots.append({
+                "rgb": torch.zeros((height, width, 3), dtype=torch.float32, device=device),
+                "u8": torch.zeros((height, width, 3), dtype=torch.uint8, device=device),
+                "max": torch.empty(1, dtype=torch.float32, device=device),
+                "gather": RowGather(height, width, 3, torch.uint8, device, world, rank, group),
+                "host": torch.empty((height, width, 3), dtype=torch.uint8).pin_memory() if rank == 0 else None,
+                "rendered": torch.cuda.Event(), "exchanged": torch.cuda.Event(),
+            })
+        self.count = 0
+
+    def submit(self, cam, params):
+        s = self.slots[self.count % len(self.slots)]
+        self.count += 1
+        main = torch.cuda.current_stream()
+        main.wait_event(s["exchanged"])                    # the slot's previous frame has left it
+        self.S.render_device(cam, params, s["rgb"])        # this rank's rows, float radiance
+        s["rendered"].record(main)
+        with torch.cuda.stream(self.side):
+            self.side.wait_event(s["rendered"])
+            self.S.frame_max_device(s["rgb"], self.rows, s["max"])
+            if self.world > 1:
+                dist.all_reduce(s["max"], op=dist.ReduceOp.MAX, group=self.group)
+            self.S.tonemap_rows_rgb8_device(s["rgb"], self.rows, s["max"], s["u8"])
+            full = s["gather"](s["u8"])
+            if self.rank == 0:
+                s["host"].copy_(full, non_blocking=True)
+            s["exchanged"].record(self.side)
+        return s
+
+    def rays_traced(self, slot):
+        slot["rendered"].synchronize()
+        return self.S.last_call_stats()[0]
+
+    def host_frame(self, slot):
+        return slot["host"]
+
+    def drain(self):
+        self.side.synchronize()

@@ -114,6 +114,22 @@ def test_edge_cases_of_the_device_builder(pkg, builder):
         pkg.MiroScene(V, layout=pkg.LAYOUT_BVH2, builder=builder)
 
 
+def test_ploc_gives_up_early_on_coincident_boxes(pkg):
+    """5000 copies of one triangle: every cluster's nearest neighbour is the same box, one mutual pair merges per round.  The
+    PLOC builder must notice (24 rounds in a row merging < 0.1 % of the clusters) and hand over to the host SAH builder instead
+    of grinding to its round cap; the scene still answers with the smallest id."""
+    import time
+    V = np.array([[0, 0, 0, 1, 0, 0, 0, 1, 0]], np.float32)
+    t0 = time.perf_counter()
+    S = pkg.MiroScene(np.repeat(V, 5000, axis=0), layout=pkg.LAYOUT_QBVH4, builder=pkg.BUILDER_PLOC_DEVICE)
+    dt = time.perf_counter() - t0
+    assert S.info.builder in (pkg.BUILDER_SAH_HOST, pkg.BUILDER_PLOC_DEVICE)
+    r = np.zeros((4, 8), np.float32); r[:, 0:3] = [0.25, 0.25, 1.0]; r[:, 4:7] = [0, 0, -1]; r[:, 7] = 1e12
+    h = S.intersect(r)
+    assert (h["prim_id"] == 0).all() and np.allclose(h["t"], 1.0)
+    assert dt < 2.0, dt
+
+
 def test_device_build_of_the_bench_scene(pkg, scenes):
     """1.39 M triangles through the host layer (BVH::setBuilder): same hits as the host-built SAH tree.  Measured on a B200:
     19 ms on the device (incl. the 50 MB vertex upload and one sync per level of the wide tree) against 420 ms of binned
