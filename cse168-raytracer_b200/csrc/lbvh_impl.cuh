@@ -537,14 +537,16 @@ inline cudaError_t build_lbvh_device(const float* tri_vertices, uint32_t ntris, 
                 m = new_m; cur ^= 1;
                 if (slow >= 24) break;
             }
+            // cudaErrorNotSupported = "this builder gives up on this input": the caller falls back to the host builder.  An unfinished
+            // agglomeration (round cap, or the early exit above) leaves child[] / parent[] partly unwritten: nothing may walk it.
+            if (m != 1) { cleanup(); cudaFree(o.d_geom); o.d_geom = nullptr; return cudaErrorNotSupported; }
             k_ploc_ranges<<<(unsigned)((2 * n - 1 + 255) / 256), 256, 0, st>>>((int)(2 * n - 1), child, parent, size, range, pc + 1);
             uint32_t h_pc[2] = {0, 0};
             LB(cudaMemcpyAsync(h_pc, pc, 8, cudaMemcpyDeviceToHost, st));
             LB(cudaStreamSynchronize(st));
             if (dbg) fprintf(stderr, "ploc rounds %d, clustering + ranges %.3f ms\n", rounds, 1e3 * std::chrono::duration<double>(std::chrono::steady_clock::now() - tp0).count());
-            // cudaErrorNotSupported = "this builder gives up on this input" (thousands of coincident boxes merge one pair per round and run
-            // into the round cap; a chain deeper than the walk cap): the caller falls back to the host builder
-            if (m != 1 || h_pc[0] != n - 1 || h_pc[1] != 0) { cleanup(); cudaFree(o.d_geom); o.d_geom = nullptr; return cudaErrorNotSupported; }
+            // (a chain deeper than the walk cap gives up the same way)
+            if (h_pc[0] != n - 1 || h_pc[1] != 0) { cleanup(); cudaFree(o.d_geom); o.d_geom = nullptr; return cudaErrorNotSupported; }
             // triangles in the depth-first order of the agglomerated tree: every subtree is a contiguous run again
             k_ploc_order<<<g256, 256, 0, st>>>((int)n, idx, range, idx2);
             std::swap(idx, idx2);

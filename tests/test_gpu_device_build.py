@@ -123,7 +123,7 @@ def test_ploc_gives_up_early_on_coincident_boxes(pkg):
     t0 = time.perf_counter()
     S = pkg.MiroScene(np.repeat(V, 5000, axis=0), layout=pkg.LAYOUT_QBVH4, builder=pkg.BUILDER_PLOC_DEVICE)
     dt = time.perf_counter() - t0
-    assert S.info.builder in (pkg.BUILDER_SAH_HOST, pkg.BUILDER_PLOC_DEVICE)
+    assert S.info.builder == pkg.BUILDER_SAH_HOST      # equal boxes: every cluster's nearest is its lowest-indexed neighbour, one mutual pair per round
     r = np.zeros((4, 8), np.float32); r[:, 0:3] = [0.25, 0.25, 1.0]; r[:, 4:7] = [0, 0, -1]; r[:, 7] = 1e12
     h = S.intersect(r)
     assert (h["prim_id"] == 0).all() and np.allclose(h["t"], 1.0)
