@@ -36,9 +36,11 @@ WIDTH, HEIGHT = 1920, 1080
 SPP = 16   # samples per step: sized so that one rank's share of a step is still milliseconds of device work at N = 8
 SEED = 168
 # SURVEY 8d yardstick: bytes/ray = 32*V + 36*T + 48 with V, T the scalar reference's node entries / triangle
-# tests per ray.  Measured live with the oracle on a subsample; these are the fall-back figures (SURVEY 8d,
-# bunny x20 bounce rays) if the oracle is unavailable.
-FALLBACK_VT = {"primary": (18.48, 3.37), "bounce": (22.43, 4.70)}
+# tests per ray.  Measured live with the oracle on a subsample of the step's own rays; when the oracle is not run
+# (--no-cpu, or the oracle library missing) the figures it measured on this very workload are used (profiles/
+# r02g_bench_full.json: the bench's rays hit mostly the floor triangle; SURVEY 8d's 18.48 / 22.43 node entries are for a
+# 512 x 512 view and would overstate the roofline fraction 1.35x).
+FALLBACK_VT = {"primary": (13.489, 2.515), "bounce": (16.234, 3.508)}
 
 
 NTRIS = 1389021   # makeBunny20Scene: 20 x 69 451 bunny triangles + the floor triangle (checked against the built scene)
@@ -327,6 +329,9 @@ def run_ours(args):
     info = S.info
     rows = (0, HEIGHT, world, rank)
     nrows = len(range(rank, HEIGHT, world))
+    if args.emulate_shard > 1 and world == 1:
+        rows = (0, HEIGHT, args.emulate_shard, 0)
+        nrows = len(range(0, HEIGHT, args.emulate_shard))
     npix = nrows * WIDTH
     n = npix * SPP
     dev = torch.device("cuda", local)
@@ -337,7 +342,7 @@ def run_ours(args):
     d_live = torch.zeros(1, dtype=torch.int64, device=dev)
     index_base = (rank * 0x01000000) & 0xFFFFFFFF
 
-    def step(it, ev=None):
+    def step_sequential(it, ev=None):
         if ev: ev[4].record()
         S.generate_primary(cam, WIDTH, HEIGHT, d_rays, rows=rows, jitter=1, seed=SEED, sample=it * SPP, samples=SPP)
         if ev: ev[0].record()
@@ -348,11 +353,46 @@ def run_ours(args):
         S.intersect_device(d_b, d_h2)
         if ev: ev[3].record()
 
+    # The timed step: the same work as step_sequential -- same rays, same buffers, same results -- issued as two half-batches
+    # (samples 0-7 and 8-15 of the step) on two streams.  Each half is its own dependent chain (eye rays -> trace -> bounce rays
+    # -> trace); the persistent trace kernels fill the GPU, so the other stream's kernel gets its CTAs exactly while the first
+    # one's last warps finish their longest rays: the ragged end of every launch (~0.1 ms, a quarter of a rank's launch at
+    # N = 8) is covered by the other half's work instead of idling the chip.
+    chunks = int(os.environ.get("MIRO_BENCH_CHUNKS", "2"))
+    nstreams = int(os.environ.get("MIRO_BENCH_STREAMS", "2"))
+    half_spp = SPP // chunks
+    nh = npix * half_spp
+    sides = [torch.cuda.Stream(dev) for _ in range(nstreams - 1)]
+
+    def half_step(it, h):
+        lo, hi = h * nh, (h + 1) * nh
+        S.generate_primary(cam, WIDTH, HEIGHT, d_rays[lo:hi], rows=rows, jitter=1, seed=SEED, sample=it * SPP + h * half_spp, samples=half_spp)
+        S.intersect_device(d_rays[lo:hi], d_hits[lo:hi], mode=pkg.CLOSEST_HIT | pkg.HINT_COHERENT)
+        S.generate_bounce(d_rays[lo:hi], d_hits[lo:hi], d_b[lo:hi], seed=SEED, sample=it, index_base=(index_base + lo) & 0xFFFFFFFF, d_live_count=d_live)
+        S.intersect_device(d_b[lo:hi], d_h2[lo:hi])
+
+    def step(it):
+        for c in range(chunks):
+            k = c % nstreams
+            if k == 0:
+                half_step(it, c)
+            else:
+                with torch.cuda.stream(sides[k - 1]):
+                    half_step(it, c)
+
+    def join_streams():
+        for side in sides:
+            done = torch.cuda.Event()
+            done.record(side)
+            torch.cuda.current_stream().wait_event(done)
+
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
+    if args.sequential:
+        step = step_sequential
     for it in range(args.warmup):
         step(it)
     barrier()
@@ -360,18 +400,32 @@ def run_ours(args):
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
-    evs = [[torch.cuda.Event(enable_timing=True) for _ in range(5)] for _ in range(args.steps)]
     t_begin, t_end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
     t_begin.record()
+    for side in sides:
+        side.wait_event(t_begin)
     for it in range(args.steps):
-        step(args.warmup + it, evs[it])
+        step(args.warmup + it)
+    join_streams()
     t_end.record()
     barrier()
     ms_local = t_begin.elapsed_time(t_end)
-    # keep the GPU busy a little longer so the clock sampler sees the load even for short runs
-    clocks = None
     live_local = int(d_live.item())
+    # Per-kernel durations (and with them roofline.achieved): the same steps once more, one launch after the other on one stream,
+    # CUDA events around each kernel -- under two streams an event interval would include the other stream's kernel.
+    evs = [[torch.cuda.Event(enable_timing=True) for _ in range(5)] for _ in range(args.steps)]
+    t_sb, t_se = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    for it in range(min(3, args.warmup)):
+        step_sequential(it)
+    barrier()
+    t_sb.record()
+    for it in range(args.steps):
+        step_sequential(args.warmup + it, evs[it])
+    t_se.record()
+    barrier()
+    ms_sequential = t_sb.elapsed_time(t_se)
+    clocks = None
     prim_ms = float(np.mean([e[0].elapsed_time(e[1]) for e in evs]))
     bounce_ms = float(np.mean([e[2].elapsed_time(e[3]) for e in evs]))
     genb_ms = float(np.mean([e[1].elapsed_time(e[2]) for e in evs]))
@@ -417,12 +471,12 @@ def run_ours(args):
         clocks = sampler.stop()
 
     # ---- aggregate over ranks: max time, summed rays ------------------------------------------------------------
-    stats = torch.tensor([ms_local, e2e_s_local, prim_ms, bounce_ms, genb_ms, genp_ms], dtype=torch.float64, device=dev)
+    stats = torch.tensor([ms_local, e2e_s_local, prim_ms, bounce_ms, genb_ms, genp_ms, ms_sequential], dtype=torch.float64, device=dev)
     sums = torch.tensor([float(n * args.steps), float(live_local), float(e2e_rays)], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(stats, op=dist.ReduceOp.MAX)
         dist.all_reduce(sums, op=dist.ReduceOp.SUM)
-    ms_total, e2e_s, prim_ms, bounce_ms, genb_ms, genp_ms = [float(x) for x in stats.tolist()]
+    ms_total, e2e_s, prim_ms, bounce_ms, genb_ms, genp_ms, ms_sequential = [float(x) for x in stats.tolist()]
     prim_total, live_total, e2e_total = [float(x) for x in sums.tolist()]
     rays_total = prim_total + live_total
     value = rays_total / (ms_total * 1e-3) / 1e6
@@ -433,7 +487,7 @@ def run_ours(args):
     if rank == 0:
         peak, peak_src = peaks()
         cpu, vt, ref_nodes, parity = None, dict(FALLBACK_VT), None, None
-        vt_src = "SURVEY 8d figures (oracle not run)"
+        vt_src = "oracle not run: V, T as measured on this workload in profiles/r02g_bench_full.json"
         threads = os.cpu_count() or 1
         # the rays of the last timed step, exactly as the GPU generated them (all SPP samples of this rank's rows)
         rp = d_rays.cpu().numpy()
@@ -448,7 +502,7 @@ def run_ours(args):
                 vt, ref_nodes = measure_vt(rp[::16], rb[::16], threads)
                 vt_src = "scalar reference counters (oracle restatement, bit-exact with -DSTATS) on every 16th of rank 0's rays of the last timed step"
             except Exception as exc:
-                vt_src = "SURVEY 8d figures (oracle failed: %r)" % (exc,)
+                vt_src = "oracle failed (%r): V, T as measured on this workload in profiles/r02g_bench_full.json" % (exc,)
         if world == 1 and not args.no_cpu:
             try:
                 leg = cpu_leg(rp, rb)
@@ -483,8 +537,13 @@ def run_ours(args):
                 "layout": args.layout, "kernel_variant": args.variant, "nodes": info.num_nodes, "node_mb": info.node_bytes / 1e6,
                 "triangle_mb": info.triangle_bytes / 1e6, "build_s": info.build_seconds + info.flatten_seconds,
                 "sharding": f"image rows interleaved over {world} rank(s), BVH replicated",
+                "schedule": ("one launch after the other on one stream (--sequential)" if args.sequential else
+                             "two half-batches (8 samples each) per step on two streams: each launch's ragged end overlaps the other half's kernels"),
+                "ms_per_step_sequential": ms_sequential / args.steps,
                 "per_gpu_ms": {"primary_trace": prim_ms, "gen_bounce": genb_ms, "bounce_trace": bounce_ms, "gen_primary": genp_ms,
-                               "note": "max over ranks of each rank's mean over the timed steps (CUDA events on the launching stream)"},
+                               "note": "max over ranks of each rank's mean over a sequential replay of the timed steps right after the timed region "
+                                       "(same rays, whole-step launches one after the other on one stream, CUDA events around each kernel on that stream); "
+                                       "ms_per_step_sequential is that replay's step time"},
                 "primary_mrays_s": (prim_total / args.steps / world) / (prim_ms * 1e-3) / 1e6 * world,
                 "bounce_mrays_s": (live_total / args.steps / world) / (bounce_ms * 1e-3) / 1e6 * world,
                 "bytes_per_ray": {"primary": bpr_p, "bounce": bpr_b, "V_T": vt, "source": vt_src},
@@ -498,7 +557,7 @@ def run_ours(args):
             "cpu_baseline": cpu,
             "e2e": {"value": e2e_value, "unit": "Mrays/s", "h2d_bytes_per_step": 40 + 17 * 4, "d2h_bytes_per_step": WIDTH * HEIGHT * 3,
                     "call": e2e_call},
-            "gpu_launches": int(4 * args.steps * world),
+            "gpu_launches": int((4 if args.sequential else 8) * args.steps * world),
             "clocks": clocks,
         }
         if world == 1 and not args.no_extras:
@@ -540,6 +599,8 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--layout", default=os.environ.get("MIROGPU_LAYOUT", "qbvh4"), choices=["bvh2", "cwbvh8", "bvh4", "qbvh4"])
     ap.add_argument("--variant", type=int, default=int(os.environ.get("MIROGPU_VARIANT", "-1")))
+    ap.add_argument("--sequential", action="store_true", help="time the step as four whole-batch launches on one stream (round-1 schedule)")
+    ap.add_argument("--emulate-shard", type=int, default=0, help="development: trace rank 0's rows of an N-rank run on one GPU")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline / parity legs (faster iteration)")
     ap.add_argument("--no-extras", action="store_true", help="skip the untimed extra measurements (other configs, gather, builders)")
     args = ap.parse_args()

@@ -9,8 +9,19 @@ namespace mirogpu {
 
 // Device buffers reused across render calls on one handle (grown on demand, never shrunk).
 struct RenderScratch {
-    void* buf[16] = {};
-    size_t cap[16] = {};
+    void* buf[20] = {};
+    size_t cap[20] = {};
+    // the fused diffuse-bounce path runs the two halves of a 16-sample batch on two streams (render_impl.cuh)
+    cudaStream_t side = nullptr;
+    cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+    cudaError_t ensure_side()
+    {
+        if (side) return cudaSuccess;
+        cudaError_t e = cudaStreamCreateWithFlags(&side, cudaStreamNonBlocking);
+        if (e == cudaSuccess) e = cudaEventCreateWithFlags(&ev_fork, cudaEventDisableTiming);
+        if (e == cudaSuccess) e = cudaEventCreateWithFlags(&ev_join, cudaEventDisableTiming);
+        return e;
+    }
     cudaError_t ensure(int i, size_t bytes)
     {
         if (cap[i] >= bytes) return cudaSuccess;
@@ -21,7 +32,11 @@ struct RenderScratch {
     }
     void release()
     {
-        for (int i = 0; i < 16; ++i) { cudaFree(buf[i]); buf[i] = nullptr; cap[i] = 0; }
+        for (int i = 0; i < 20; ++i) { cudaFree(buf[i]); buf[i] = nullptr; cap[i] = 0; }
+        if (side) cudaStreamDestroy(side);
+        if (ev_fork) cudaEventDestroy(ev_fork);
+        if (ev_join) cudaEventDestroy(ev_join);
+        side = nullptr; ev_fork = ev_join = nullptr;
     }
 };
 

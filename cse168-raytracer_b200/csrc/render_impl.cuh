@@ -692,16 +692,25 @@ int render_device_once(mirogpu_scene* h, const mirogpu_camera& cam, const mirogp
         const uint32_t fb = (uint32_t)std::min(rp.spp, 16);
         const size_t fitems0 = npix * fb;
         if (fitems0 >= (1ull << 31)) { err = "frame too large"; return MIROGPU_ERR_UNSUPPORTED; }
-        RT(sc.ensure(0, fitems0 * sizeof(mirogpu_ray))); RT(sc.ensure(2, fitems0 * sizeof(mirogpu_hit)));
-        RT(sc.ensure(3, fitems0 * 4)); RT(sc.ensure(12, fitems0 * 12));
+        // A batch of up to 16 samples is rendered as two halves on two streams (the caller's and a side stream of the handle): each
+        // half is its own chain eye rays -> trace -> wave 0 -> trace -> wave 1 with its own ray / hit / parent-material buffers, so
+        // one half's DRAM-bound wave kernels and the ragged end of its persistent trace launches overlap the other half's
+        // issue-bound traversal.  Every sample owns its plane, and the planes are folded into the frame in sample order after both
+        // halves are in -- the same additions in the same order as a single-stream batch: bit-identical frames.
+        static const int two_streams = getenv("MIROGPU_RENDER_STREAMS") ? atoi(getenv("MIROGPU_RENDER_STREAMS")) : 2;
+        const bool split = two_streams >= 2 && fb >= 2;
+        const uint32_t fbA = split ? (fb + 1) / 2 : fb, fbB = fb - fbA;
+        RT(sc.ensure(0, npix * fbA * sizeof(mirogpu_ray))); RT(sc.ensure(2, npix * fbA * sizeof(mirogpu_hit)));
+        RT(sc.ensure(3, npix * fbA * 4)); RT(sc.ensure(12, fitems0 * 12));
+        if (split) {
+            RT(sc.ensure(16, npix * fbB * sizeof(mirogpu_ray))); RT(sc.ensure(17, npix * fbB * sizeof(mirogpu_hit))); RT(sc.ensure(18, npix * fbB * 4));
+            RT(sc.ensure_side());
+        }
         const size_t fbytes = (npix * 12 + 15) / 16 * 16;
         RT(sc.ensure(10, fbytes + 256));
         float* frame = reinterpret_cast<float*>(sc.buf[10]);
         uint32_t* counters = reinterpret_cast<uint32_t*>(reinterpret_cast<char*>(sc.buf[10]) + fbytes);
         unsigned long long* d_total = reinterpret_cast<unsigned long long*>(counters + 20);
-        mirogpu_ray* rays = reinterpret_cast<mirogpu_ray*>(sc.buf[0]);
-        mirogpu_hit* hits = reinterpret_cast<mirogpu_hit*>(sc.buf[2]);
-        uint32_t* pmat = reinterpret_cast<uint32_t*>(sc.buf[3]);
         float* planes = reinterpret_cast<float*>(sc.buf[12]);
         WaveParams wp;
         wp.ds = h->ds; wp.mats = h->d_materials; wp.lights = h->d_lights; wp.nlights = h->nlights;
@@ -719,24 +728,45 @@ int render_device_once(mirogpu_scene* h, const mirogpu_camera& cam, const mirogp
         static const int bw_items = getenv("MIROGPU_BW_ITEMS") ? atoi(getenv("MIROGPU_BW_ITEMS")) : 2;
         static const int bw_readd = getenv("MIROGPU_BW_READD") ? atoi(getenv("MIROGPU_BW_READD")) : 1;
         const int BW = bw_items == 1 ? 1 : bw_items == 2 ? 2 : 4;
-        for (uint32_t s0 = 0; s0 < (uint32_t)rp.spp; s0 += fb) {
-            const uint32_t nb = std::min<uint32_t>(fb, (uint32_t)rp.spp - s0);
-            const size_t items = npix * nb;
-            wp.sample_base = s0;
-            k_gen_primary<<<dim3((unsigned)((npix + 255) / 256), nb), 256, 0, st>>>(cb, rp.width, rp.height, first_row, rp.row_stride, nrows, rp.jitter, rp.seed, s0, nb, rays);
-            RT(dispatch_trace(h, rays, items, hits, MIROGPU_CLOSEST_HIT | MIROGPU_HINT_COHERENT, st));
+        // one half: samples [sb0, sb0 + nbh) of the frame into planes [plane0, plane0 + nbh), on stream s with its own buffers
+        auto half = [&](cudaStream_t s, uint32_t sb0, uint32_t nbh, uint32_t plane0, mirogpu_ray* rays, mirogpu_hit* hits, uint32_t* pmat) -> int {
+            const size_t items = npix * nbh;
+            WaveParams w = wp;
+            w.sample_base = sb0;
+            float* pl = planes + (size_t)plane0 * npix * 3;
+            k_gen_primary<<<dim3((unsigned)((npix + 255) / 256), nbh), 256, 0, s>>>(cb, rp.width, rp.height, first_row, rp.row_stride, nrows, rp.jitter, rp.seed, sb0, nbh, rays);
+            RT(dispatch_trace(h, rays, items, hits, MIROGPU_CLOSEST_HIT | MIROGPU_HINT_COHERENT, s));
             const unsigned grid = (unsigned)((items + MIRO_BW_THREADS * BW - 1) / (MIRO_BW_THREADS * BW));
-#define MIRO_W0(K, R) k_bounce_wave0<K, R><<<grid, MIRO_BW_THREADS, 0, st>>>(wp, cb, rp.height, nrows, rp.jitter, (uint32_t)items, hits, rays, pmat, planes, counters + MIRO_LIVE_SLOT0)
+#define MIRO_W0(K, R) k_bounce_wave0<K, R><<<grid, MIRO_BW_THREADS, 0, s>>>(w, cb, rp.height, nrows, rp.jitter, (uint32_t)items, hits, rays, pmat, pl, counters + MIRO_LIVE_SLOT0)
             if (bw_readd) { if (BW == 1) MIRO_W0(1, true); else if (BW == 2) MIRO_W0(2, true); else MIRO_W0(4, true); }
             else { if (BW == 1) MIRO_W0(1, false); else if (BW == 2) MIRO_W0(2, false); else MIRO_W0(4, false); }
 #undef MIRO_W0
-            RT(dispatch_trace(h, rays, items, hits, MIROGPU_CLOSEST_HIT, st));
-            if (BW == 1) k_bounce_wave1<1><<<grid, MIRO_BW_THREADS, 0, st>>>(wp, (uint32_t)items, hits, rays, pmat, planes);
-            else if (BW == 2) k_bounce_wave1<2><<<grid, MIRO_BW_THREADS, 0, st>>>(wp, (uint32_t)items, hits, rays, pmat, planes);
-            else k_bounce_wave1<4><<<grid, MIRO_BW_THREADS, 0, st>>>(wp, (uint32_t)items, hits, rays, pmat, planes);
-            k_fold_planes<<<(unsigned)((npix * 3 + 255) / 256), 256, 0, st>>>(planes, nb, npix * 3, frame);
-            launches += 6;
+            RT(dispatch_trace(h, rays, items, hits, MIROGPU_CLOSEST_HIT, s));
+            if (BW == 1) k_bounce_wave1<1><<<grid, MIRO_BW_THREADS, 0, s>>>(w, (uint32_t)items, hits, rays, pmat, pl);
+            else if (BW == 2) k_bounce_wave1<2><<<grid, MIRO_BW_THREADS, 0, s>>>(w, (uint32_t)items, hits, rays, pmat, pl);
+            else k_bounce_wave1<4><<<grid, MIRO_BW_THREADS, 0, s>>>(w, (uint32_t)items, hits, rays, pmat, pl);
+            launches += 5;
             host_rays += items;
+            return MIROGPU_OK;
+        };
+        for (uint32_t s0 = 0; s0 < (uint32_t)rp.spp; s0 += fb) {
+            const uint32_t nb = std::min<uint32_t>(fb, (uint32_t)rp.spp - s0);
+            const uint32_t nA = (split && nb >= 2) ? (nb + 1) / 2 : nb, nB = nb - nA;
+            if (nB) {
+                // the side stream starts after everything queued so far on st (frame clear, the previous batch's fold of the planes)
+                RT(cudaEventRecord(sc.ev_fork, st));
+                RT(cudaStreamWaitEvent(sc.side, sc.ev_fork, 0));
+            }
+            int rc = half(st, s0, nA, 0, reinterpret_cast<mirogpu_ray*>(sc.buf[0]), reinterpret_cast<mirogpu_hit*>(sc.buf[2]), reinterpret_cast<uint32_t*>(sc.buf[3]));
+            if (rc != MIROGPU_OK) return rc;
+            if (nB) {
+                rc = half(sc.side, s0 + nA, nB, nA, reinterpret_cast<mirogpu_ray*>(sc.buf[16]), reinterpret_cast<mirogpu_hit*>(sc.buf[17]), reinterpret_cast<uint32_t*>(sc.buf[18]));
+                if (rc != MIROGPU_OK) return rc;
+                RT(cudaEventRecord(sc.ev_join, sc.side));
+                RT(cudaStreamWaitEvent(st, sc.ev_join, 0));
+            }
+            k_fold_planes<<<(unsigned)((npix * 3 + 255) / 256), 256, 0, st>>>(planes, nb, npix * 3, frame);
+            launches += 1;
         }
         k_sum_wave_counters<<<1, 1, 0, st>>>(counters, d_total, 1);   // live bounce rays of all batches (the slots are never reset within a frame)
         float* gmax = reinterpret_cast<float*>(counters + 18);
