@@ -574,11 +574,14 @@ def run_ours(args):
 def run_extras():
     """The other BASELINE configs and entry points, measured outside the timed region by the tools/ scripts (one subprocess each,
     one JSON object each): frame times of configs 1 / 2 / 4 / 5 with the fraction of pixels within 2/255 of the REAL reference's
-    image, photon gather rate on config 5 against its yardstick, BVH::build seconds per builder, the host-buffer batch API."""
+    image, photon gather rate on config 5 against its yardstick, BVH::build seconds per builder, the host-buffer batch API, the
+    photon pass on the device, and the same step as the timed one on a deep-traversal scene (56 node entries per camera ray, like
+    sponza's published 54.8) with its own V, T and roofline fraction."""
     out = {}
     env = dict(os.environ, MIRO_REF_ALL="1")
     for key, script, tmo in (("configs", "bench_configs.py", 240), ("photon_gather", "bench_gather.py", 120), ("bvh_build", "bench_build.py", 120),
-                             ("host_batch_api", "bench_host_batch.py", 120)):
+                             ("host_batch_api", "bench_host_batch.py", 120), ("photon_pass", "bench_photon_pass.py", 120),
+                             ("deep_traversal", "bench_deep.py", 180)):
         path = os.path.join(ROOT, "tools", script)
         if not os.path.exists(path):
             continue

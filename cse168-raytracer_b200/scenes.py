@@ -118,7 +118,42 @@ def _spiral():
                 camera=dict(eye=(0, 0, -5), lookat=(0, 0, 0), up=(0, 1, 0), fov=45), size=(512, 512))
 
 
+def _meadow():
+    """Deep-traversal stand-in for sponza (54.8 node entries per camera ray; makeBunny20Scene's camera mostly sees the
+    floor: 13.5).  6 x 6 of the reference's flower models (Petals2 + Stem + Leaf + WaterDrops, assignment3.cpp:88-106) at a
+    pitch narrower than a corolla, each turned about the vertical axis and lifted by its own amount, over a two-triangle ground;
+    the camera sits inside the field at petal height and looks along the diagonal, so every ray grazes many overlapping
+    corollas before it hits something -- an enclosed, cluttered view like sponza's.  Data only; fixed table of angles / lifts."""
+    meshes, k = [], 0
+    for i in range(6):
+        for j in range(6):
+            ang = (37 * k + 11 * i) % 360
+            lift = ((7 * k + 3 * j) % 13 - 6) * 0.22
+            t = _chain(translate(9.0 * i, lift, 9.0 * j), rotate(ang, 0, 1, 0))
+            meshes += [("Petals2", t, 0), ("Stem", t, 1), ("Leaf", t, 2), ("WaterDrops", t, 3)]
+            k += 1
+    # the field stands in a closed room, so every ray ends on a surface, as in sponza: floor, ceiling and four walls are ONE large
+    # triangle each (like the reference's own floor triangles, assignment2.cpp:101-109) that covers its face of the box
+    # [-40, 90] x [-9, 14] x [-40, 90] -- no coplanar shared edges in view, whose epsilon bands would turn into equal-t ties
+    B = 400.0
+    ground = [(dict(v=[-B, -9, -B, 25, -9, 2 * B, 2 * B, -9, -B], n=[0, 1, 0] * 3), 1),        # floor   y = -9
+              (dict(v=[-B, 14, -B, 2 * B, 14, -B, 25, 14, 2 * B], n=[0, -1, 0] * 3), 1),       # ceiling y = 14
+              (dict(v=[-40, -B, -B, -40, 2 * B, 25, -40, -B, 2 * B], n=[1, 0, 0] * 3), 1),     # wall    x = -40
+              (dict(v=[90, -B, -B, 90, -B, 2 * B, 90, 2 * B, 25], n=[-1, 0, 0] * 3), 1),       # wall    x = 90
+              (dict(v=[-B, -B, -40, 2 * B, -B, -40, 25, 2 * B, -40], n=[0, 0, 1] * 3), 1),     # wall    z = -40
+              (dict(v=[-B, -B, 90, 25, 2 * B, 90, 2 * B, -B, 90], n=[0, 0, -1] * 3), 1)]       # wall    z = 90
+    return dict(meshes=meshes, triangles=ground,
+                materials=[dict(kd=(0.9, 0.35, 0.55), ks=(0, 0, 0), kt=(0, 0, 0), shininess=1.0, refr=1.0),
+                           dict(kd=(0.25, 0.6, 0.2), ks=(0, 0, 0), kt=(0, 0, 0), shininess=1.0, refr=1.0),
+                           dict(kd=(0.1, 0.5, 0.15), ks=(0, 0, 0), kt=(0, 0, 0), shininess=1.0, refr=1.0),
+                           dict(kd=(0.8, 0.8, 0.9), ks=(0, 0, 0), kt=(0, 0, 0), shininess=1.0, refr=1.0)],
+                lights=[dict(kind=0, pos=(22, 12, 22), color=(1, 1, 1), wattage=4000)], bg=(0.6, 0.7, 1.0),
+                camera=dict(eye=(22.5, 1.0, 22.5), lookat=(0, -3, 0), up=(0, 1, 0), fov=70), size=(1920, 1080))
+
+
 SCENES = {
+    # deep-traversal second workload of the bench (tools/bench_deep.py)
+    "meadow": _meadow(),
     # makeSpiralScene (assignment1.cpp:8-76): spheres in the tree, a plane outside it
     "spiral": _spiral(),
     # two glass / mirror spheres over a plane with the teapot: non-triangle primitives under the recursive tracer
