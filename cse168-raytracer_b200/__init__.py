@@ -31,6 +31,7 @@ RENDER_WHITTED, RENDER_DIFFUSE_BOUNCE, RENDER_PRIMARY_ONLY = 0, 1, 2
 
 RAY_DTYPE = np.dtype([("o", np.float32, 3), ("tmin", np.float32), ("d", np.float32, 3), ("tmax", np.float32)])
 HIT_DTYPE = np.dtype([("t", np.float32), ("prim_id", np.uint32), ("beta", np.float32), ("gamma", np.float32)])
+TEX_NONE, TEX_CHECKER, TEX_STONE, TEX_STEM, TEX_PETAL, TEX_LEAF, TEX_FLOWER_CENTER = range(7)   # MIROGPU_TEX_*
 PHOTON_DTYPE = np.dtype([("pos", np.float32, 3), ("plane", np.int16), ("theta", np.uint8), ("phi", np.uint8), ("power", np.float32, 3)])
 assert RAY_DTYPE.itemsize == 32 and HIT_DTYPE.itemsize == 16 and PHOTON_DTYPE.itemsize == 28
 
@@ -54,7 +55,7 @@ class SceneInfo(ctypes.Structure):
 
 class Material(ctypes.Structure):
     _fields_ = [("kd", ctypes.c_float * 3), ("ks", ctypes.c_float * 3), ("kt", ctypes.c_float * 3),
-                ("shininess", ctypes.c_float), ("refract_index", ctypes.c_float), ("_pad", ctypes.c_float)]
+                ("shininess", ctypes.c_float), ("refract_index", ctypes.c_float), ("texture", ctypes.c_int32), ("tex", ctypes.c_float * 12)]
 
 
 class Light(ctypes.Structure):
@@ -87,7 +88,7 @@ EXPORTS = [
     "mirogpu_photon_gather_device", "mirogpu_photon_trace", "mirogpu_photon_set_exact", "mirogpu_host_alloc", "mirogpu_host_free",
     "mirogpu_frame_max_device", "mirogpu_tonemap_rows_rgb8_device", "mirogpu_release_build_scratch",
     "mirogpu_scene_create_ex", "mirogpu_scene_devices", "mirogpu_resolve_hits_rays_device",
-    "mirogpu_photon_pass", "mirogpu_photon_download", "mirogpu_photon_balance",
+    "mirogpu_photon_pass", "mirogpu_photon_download", "mirogpu_photon_balance", "mirogpu_texture_lookup", "mirogpu_texture_bump",
 ]
 
 
@@ -158,6 +159,31 @@ def phong(kd=(1, 1, 1), ks=(0, 0, 0), kt=(0, 0, 0), shininess=1.0, refract_index
     m.shininess = float(shininess) if shininess >= 0 else float("inf")
     m.refract_index = float(refract_index)
     return m
+
+
+def texture_lookup(kind, params, coords):
+    """Texture::lookup2D / lookup3D of a procedural texture at coords (n, 2) or (n, 3) -> (n, 3) colours (host evaluation of the
+    device code, for checkers)."""
+    coords = np.ascontiguousarray(coords, np.float32)
+    tp = (ctypes.c_float * 12)(*([float(x) for x in params] + [0.0] * (12 - len(params))))
+    out = np.zeros((coords.shape[0], 3), np.float32)
+    rgb = (ctypes.c_float * 3)()
+    for i in range(coords.shape[0]):
+        w = float(coords[i, 2]) if coords.shape[1] > 2 else 0.0
+        _check(lib.mirogpu_texture_lookup(int(kind), tp, ctypes.c_float(coords[i, 0]), ctypes.c_float(coords[i, 1]), ctypes.c_float(w), rgb))
+        out[i] = rgb[:]
+    return out
+
+
+def texture_bump(kind, params, coords):
+    coords = np.ascontiguousarray(coords, np.float32)
+    tp = (ctypes.c_float * 12)(*([float(x) for x in params] + [0.0] * (12 - len(params))))
+    out = np.zeros(coords.shape[0], np.float32)
+    h = ctypes.c_float(0)
+    for i in range(coords.shape[0]):
+        _check(lib.mirogpu_texture_bump(int(kind), tp, ctypes.c_float(coords[i, 0]), ctypes.c_float(coords[i, 1]), ctypes.byref(h)))
+        out[i] = h.value
+    return out
 
 
 def photon_balance(photons, bbox_min, bbox_max, device=0):
@@ -435,6 +461,11 @@ class HostScene:
 
     def new_material(self, kd=(1, 1, 1), ks=(0, 0, 0), kt=(0, 0, 0), shininess=1.0, refr=1.0):
         return self.h.mh_new_material(_f3(kd), _f3(ks), _f3(kt), ctypes.c_float(shininess), ctypes.c_float(refr))
+
+    def new_textured_material(self, kind, params, ks=(0, 0, 0), kt=(0, 0, 0), shininess=1.0, refr=1.0):
+        """TexturedPhong over a procedural texture: kind = TEX_*, params = the texture's constructor arguments (mirogpu.h)."""
+        tp = (ctypes.c_float * 12)(*([float(x) for x in params] + [0.0] * (12 - len(params))))
+        return self.h.mh_new_textured_material(int(kind), tp, _f3(ks), _f3(kt), ctypes.c_float(shininess), ctypes.c_float(refr))
 
     def add_obj(self, path, ctm=None, material=0):
         c = None

@@ -13,6 +13,7 @@
 
 #include "traverse.cuh"
 #include "rng.cuh"
+#include "texture.cuh"
 
 namespace mirogpu {
 
@@ -23,6 +24,10 @@ struct DeviceScene {
     const float4* planes;  // 2 float4 per plane: (normal, prim id bits) (origin, 0) -- the unbounded objects of Scene::trace (Scene.cpp:219-230)
     uint32_t num_tris;     // all primitives (triangles, spheres, planes): the range of prim ids
     uint32_t num_planes;
+    // scenes with TexturedPhong materials (texture.cuh): hit points are finished by resolve_hit_textured
+    const mirogpu_material* mats;
+    const float* uvs;      // 6 floats per triangle (tA, tB, tC of TriangleMesh::texCoords) or NULL: meshes without texture coordinates
+    uint32_t textured;
 };
 
 struct CameraBasis {       // what Camera::eyeRay caches in its statics (Camera.cpp:106-125)
@@ -384,6 +389,90 @@ __device__ __forceinline__ SurfacePoint resolve_hit(const ShadeRecord& rec, cons
     return resolve_hit_analytic(rec, h, r.ox, r.oy, r.oz, r.dx, r.dy, r.dz);
 }
 
+// ---- scenes with textured materials ----------------------------------------------------------------------------------------
+// Scene::trace's treatment of a hit (Scene.cpp:232-262) in full, and the diffuse colour Phong::shade / Scene::tracePhoton look up:
+//   * the normal as the primitive left it -- a triangle's interpolated normal un-normalised (Triangle.cpp:162), a sphere's
+//     normalised (Sphere.cpp:63-64), a plane's as given (Plane.cpp:44);
+//   * materials with UV lookup coordinates (plain Phong, 2-D textures): Object::toUVCoordinates, central differences of the bump
+//     height (non-zero for StoneTexture only), the tangent construction, N.normalize();
+//   * materials with UVW lookup coordinates (3-D textures): the normal stays as it is;
+//   * diffuse colour: Material::diffuse2D(uv) / diffuse3D(P).
+// Out of line and by value: untextured scenes (every kernel's fast path) do not pay registers for the noise code.
+struct TexturedPoint { SurfacePoint sp; float dc[3]; };
+
+__device__ __forceinline__ void object_uv(const ShadeRecord& rec, const mirogpu_hit& h, const float P[3], const float* uvs, float uv[2])
+{
+    const uint32_t kind = record_kind(rec);
+    if (kind == 2u) { uv[0] = P[0]; uv[1] = P[2]; return; }                 // Plane::toUVCoordinates, Plane.cpp:50-60
+    if (kind == 1u) {                                                       // Sphere::toUVCoordinates, Sphere.cpp:83-95
+        float d[3] = {xsub(P[0], rec.r0.lo.x), xsub(P[1], rec.r0.lo.y), xsub(P[2], rec.r0.lo.z)};
+        const float inv = xdiv(1.0f, xsqrt(xdot(d[0], d[1], d[2], d[0], d[1], d[2])));
+        d[0] = xmul(d[0], inv); d[1] = xmul(d[1], inv); d[2] = xmul(d[2], inv);
+        uv[0] = (float)dadd((double)xdiv(atan2f(d[0], d[2]), xmul(2.0f, MIRO_PI)), 0.5);
+        uv[1] = (float)dadd((double)xdiv(fmaxf(-1.0f, fminf(1.0f, asinf(d[1]))), MIRO_PI), 0.5);
+        return;
+    }
+    uv[0] = uv[1] = 0.f;                                                    // a mesh without texture coordinates: tex_coord2d_t() (Triangle.cpp:174-175)
+    if (!uvs) return;
+    // Triangle::toUVCoordinates (Triangle.cpp:172-222): barycentrics by Cramer's rule in the plane that drops one axis
+    const float* t = uvs + 6 * (size_t)h.prim_id;
+    const float4 A = rec.r0.lo, e1 = rec.r0.hi, e2 = rec.r1.lo;
+    const float B[3] = {e1.x, e1.y, e1.z}, C[3] = {e2.x, e2.y, e2.z};
+    const float nx = xsub(xmul(B[1], C[2]), xmul(B[2], C[1])), ny = xsub(xmul(B[2], C[0]), xmul(B[0], C[2])), nz = xsub(xmul(B[0], C[1]), xmul(B[1], C[0]));
+    int i = 0, j = 1;
+    if (nx > nz) i = 2; else if (ny > nz) j = 2;
+    const float p[3] = {xsub(P[0], A.x), xsub(P[1], A.y), xsub(P[2], A.z)};
+    auto det = [](float a, float b, float c, float d) { return xsub(xmul(a, d), xmul(b, c)); };   // Det(a, b, c, d) = a d - b c (Utility.h)
+    const float detPC = det(p[i], C[i], p[j], C[j]), detBP = det(B[i], p[i], B[j], p[j]), detBC = det(B[i], C[i], B[j], C[j]);
+    const float beta = fmaxf(xdiv(detPC, detBC), 0.f), gamma = fmaxf(xdiv(detBP, detBC), 0.f);
+    const float alpha = fmaxf(xsub(1.0f, xadd(beta, gamma)), 0.f);
+    uv[0] = xadd(xadd(xmul(alpha, t[0]), xmul(beta, t[2])), xmul(gamma, t[4]));
+    uv[1] = xadd(xadd(xmul(alpha, t[1]), xmul(beta, t[3])), xmul(gamma, t[5]));
+}
+
+__device__ __noinline__ TexturedPoint resolve_hit_textured(const ShadeRecord rec, const mirogpu_hit h, const float ox, const float oy, const float oz,
+                                                            const float dx, const float dy, const float dz, const mirogpu_material* __restrict__ mats,
+                                                            const float* __restrict__ uvs)
+{
+    TexturedPoint tp;
+    SurfacePoint& sp = tp.sp;
+    const uint32_t kind = record_kind(rec);
+    float n[3];
+    if (kind == 0u) {
+        const float4 A = rec.r0.lo, e1 = rec.r0.hi, e2 = rec.r1.lo, nA = rec.r1.hi, nB = rec.r2.lo, nC = rec.r2.hi;
+        sp.P[0] = xadd(xadd(A.x, xmul(e1.x, h.beta)), xmul(e2.x, h.gamma));
+        sp.P[1] = xadd(xadd(A.y, xmul(e1.y, h.beta)), xmul(e2.y, h.gamma));
+        sp.P[2] = xadd(xadd(A.z, xmul(e1.z, h.beta)), xmul(e2.z, h.gamma));
+        const float alpha = xsub(xsub(1.0f, h.beta), h.gamma);
+        n[0] = xadd(xadd(xmul(nA.x, alpha), xmul(nB.x, h.beta)), xmul(nC.x, h.gamma));
+        n[1] = xadd(xadd(xmul(nA.y, alpha), xmul(nB.y, h.beta)), xmul(nC.y, h.gamma));
+        n[2] = xadd(xadd(xmul(nA.z, alpha), xmul(nB.z, h.beta)), xmul(nC.z, h.gamma));
+        sp.material = __float_as_uint(A.w);
+    } else {
+        sp.P[0] = xadd(ox, xmul(dx, h.t)); sp.P[1] = xadd(oy, xmul(dy, h.t)); sp.P[2] = xadd(oz, xmul(dz, h.t));
+        if (kind == 1u) {
+            n[0] = xsub(sp.P[0], rec.r0.lo.x); n[1] = xsub(sp.P[1], rec.r0.lo.y); n[2] = xsub(sp.P[2], rec.r0.lo.z);
+            const float i0 = xdiv(1.0f, xsqrt(xdot(n[0], n[1], n[2], n[0], n[1], n[2])));
+            n[0] = xmul(n[0], i0); n[1] = xmul(n[1], i0); n[2] = xmul(n[2], i0);
+        } else { n[0] = rec.r1.hi.x; n[1] = rec.r1.hi.y; n[2] = rec.r1.hi.z; }
+        sp.material = __float_as_uint(rec.r0.lo.w);
+    }
+    const mirogpu_material m = mats[sp.material];
+    float uv[2];
+    object_uv(rec, h, sp.P, uvs, uv);
+    const bool uvw = m.texture == MIROGPU_TEX_PETAL || m.texture == MIROGPU_TEX_LEAF || m.texture == MIROGPU_TEX_FLOWER_CENTER;
+    if (!uvw) {
+        if (m.texture == MIROGPU_TEX_STONE) material_bump_normal(m, uv[0], uv[1], n);
+        else {
+            const float inv = xdiv(1.0f, xsqrt(xdot(n[0], n[1], n[2], n[0], n[1], n[2])));
+            n[0] = xmul(n[0], inv); n[1] = xmul(n[1], inv); n[2] = xmul(n[2], inv);
+        }
+    }
+    sp.N[0] = n[0]; sp.N[1] = n[1]; sp.N[2] = n[2];
+    material_diffuse_color(m, uv, sp.P, tp.dc);
+    return tp;
+}
+
 __global__ void __launch_bounds__(256) k_resolve_hits(DeviceScene s, const mirogpu_ray* __restrict__ rays, const mirogpu_hit* __restrict__ hits, size_t n,
                                                        float* __restrict__ P, float* __restrict__ N, uint32_t* __restrict__ mat)
 {
@@ -396,7 +485,11 @@ __global__ void __launch_bounds__(256) k_resolve_hits(DeviceScene s, const mirog
         sp.P[0] = sp.P[1] = sp.P[2] = 0.f; sp.N[0] = sp.N[1] = sp.N[2] = 0.f; sp.material = MIROGPU_MISS;
     } else {
         const ShadeRecord rec = load_shade_record(s, h.prim_id);
-        sp = rays ? resolve_hit(rec, h, rays + i) : resolve_hit(rec, h);
+        if (s.textured) {
+            float4 a = make_float4(0.f, 0.f, 0.f, 0.f), b = a;
+            if (rays) { const float4* q = reinterpret_cast<const float4*>(rays + i); a = q[0]; b = q[1]; }
+            sp = resolve_hit_textured(rec, h, a.x, a.y, a.z, b.x, b.y, b.z, s.mats, s.uvs).sp;
+        } else sp = rays ? resolve_hit(rec, h, rays + i) : resolve_hit(rec, h);
     }
     if (P) { P[3 * i] = sp.P[0]; P[3 * i + 1] = sp.P[1]; P[3 * i + 2] = sp.P[2]; }
     if (N) { N[3 * i] = sp.N[0]; N[3 * i + 1] = sp.N[1]; N[3 * i + 2] = sp.N[2]; }
@@ -435,7 +528,7 @@ __device__ __forceinline__ void align_hemisphere(const float v[3], float theta, 
 // MIRO_GENB_ITEMS hits per thread (i, i + 128, ... of a tile; 4 by default): the kernel is a chain of two dependent fetches (the
 // hit, then the 96-byte shading record it names) in front of ~300 instructions, so it runs at the latency of those fetches; all
 // hits and then all records of the thread are requested before anything is computed.
-template <int MIRO_GENB_ITEMS>
+template <int MIRO_GENB_ITEMS, bool TEXTURED = false>
 __global__ void __launch_bounds__(MIRO_GENB_THREADS) k_gen_bounce(DeviceScene s, const mirogpu_ray* __restrict__ rays,
                                                                    const mirogpu_hit* __restrict__ hits, size_t n, uint32_t seed, uint32_t sample,
                                                                    uint32_t index_base, mirogpu_ray* __restrict__ out, unsigned long long* live_count)
@@ -469,7 +562,9 @@ __global__ void __launch_bounds__(MIRO_GENB_THREADS) k_gen_bounce(DeviceScene s,
         if (h[k].prim_id == MIROGPU_MISS) {
             a = make_float4(0.f, 0.f, 0.f, 0.f); b = make_float4(0.f, 0.f, 1.f, -1.0f);  // tmax < tmin: never hits
         } else {
-            const SurfacePoint sp = resolve_hit(rec[k], h[k], rays + i);
+            const SurfacePoint sp = TEXTURED ? resolve_hit_textured(rec[k], h[k], __ldg(&rays[i].ox), __ldg(&rays[i].oy), __ldg(&rays[i].oz), __ldg(&rays[i].dx), __ldg(&rays[i].dy),
+                                                                      __ldg(&rays[i].dz), s.mats, s.uvs).sp
+                                                : resolve_hit(rec[k], h[k], rays + i);
             float u1, u2;
             uniform2(seed, index_base + (uint32_t)i, sample, RNG_DIM_BOUNCE, u1, u2);
             const float phi = asinf(sqrtf(u1));

@@ -7,10 +7,22 @@
 #include "Miro.h"
 #include "Vector3.h"
 
+struct mirogpu_material;
+
+// Material.h:7-15: how the shader queries the material for its colour
+enum LookupCoordinates { UV = 0, UVW = 1 };
+
 class Material {
 public:
     Material() : m_specular(0.f), m_transmission(0.f), m_refractIndex(1.f), m_shininess(infinity) {}
     virtual ~Material() {}
+    virtual LookupCoordinates GetLookupCoordinates() const { return UV; }
+    virtual Vector3 diffuse2D(const tex_coord2d_t&) const { return Vector3(0); }
+    virtual Vector3 diffuse3D(const tex_coord3d_t&) const { return Vector3(0); }
+    virtual float bumpHeight2D(const tex_coord2d_t&) const { return 0; }
+    virtual float bumpHeight3D(const tex_coord3d_t&) const { return 0; }
+    // the texture part of this material's device description (TexturedPhong fills it in; Texture.h)
+    virtual void describeTexture(mirogpu_material&) const {}
     bool isReflective() const { return m_specular.x > 0.f || m_specular.y > 0.f || m_specular.z > 0.f; }
     bool isRefractive() const { return m_transmission.x > 0.f || m_transmission.y > 0.f || m_transmission.z > 0.f; }
     virtual bool isDiffuse() const { return true; }
@@ -38,6 +50,8 @@ public:
         for (int i = 0; i < 3; ++i) m_diffuse[i] = std::max(std::min(m_diffuse[i], 1.0f - m_specular[i] - m_transmission[i]), 0.f);
     }
     virtual bool isDiffuse() const { return m_diffuse.x > 0.f || m_diffuse.y > 0.f || m_diffuse.z > 0.f; }
+    virtual Vector3 diffuse2D(const tex_coord2d_t&) const { return m_diffuse; }   // Phong.h:20-21
+    virtual Vector3 diffuse3D(const tex_coord3d_t&) const { return m_diffuse; }
     virtual Vector3 getDiffuse() const { return m_diffuse; }
     void setDiffuse(const Vector3& kd) { m_diffuse = kd; }
 protected:

@@ -17,6 +17,8 @@ public:
     virtual Vector3 coordsMax() const = 0;
     virtual Vector3 center() const = 0;
     virtual bool isBounded() const { return true; }
+    // the texture mapping function of 2-D lookups (Object.h:37); Plane keeps this default (Plane.cpp:50-60)
+    virtual tex_coord2d_t toUVCoordinates(const Vector3& xyz) const { return tex_coord2d_t(xyz.x, xyz.z); }
     virtual bool intersect(HitInfo& result, const Ray& ray, float tMin = 0.0f, float tMax = MIRO_TMAX) = 0;
 protected:
     const Material* m_material;

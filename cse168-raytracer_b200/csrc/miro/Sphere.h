@@ -17,6 +17,7 @@ public:
     virtual Vector3 coordsMax() const { return m_center + Vector3(m_radius); }
     virtual Vector3 center() const { return m_center; }
     virtual bool intersect(HitInfo& result, const Ray& ray, float tMin = 0.0f, float tMax = MIRO_TMAX);
+    virtual tex_coord2d_t toUVCoordinates(const Vector3& xyz) const;   // Sphere.cpp:83-95
     // P = o + t d, N = (P - c).normalize(), material (Sphere.cpp:62-66), for a hit the device found at distance t
     void fillHit(HitInfo& result, const Ray& ray, float t) const;
 protected:

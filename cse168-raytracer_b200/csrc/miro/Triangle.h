@@ -17,6 +17,7 @@ public:
     void setMesh(TriangleMesh* m) { m_mesh = m; }
     TriangleMesh* getMesh() { return m_mesh; }
     virtual bool intersect(HitInfo& result, const Ray& ray, float tMin = 0.0f, float tMax = MIRO_TMAX);
+    virtual tex_coord2d_t toUVCoordinates(const Vector3& xyz) const;   // Triangle.cpp:172-222
     // Fills result.P / N / material from barycentrics exactly as Triangle.cpp:160-166 does.
     void fillHit(HitInfo& result, float t, float beta, float gamma) const;
 protected:

@@ -21,17 +21,23 @@ public:
     void setN2(const Vector3& n) { m_normals[1] = n; }
     void setN3(const Vector3& n) { m_normals[2] = n; }
     struct TupleI3 { unsigned int v[3]; };
+    struct VectorR2 { float x, y; };
     Vector3* vertices() { return m_vertices; }
     Vector3* normals() { return m_normals; }
     TupleI3* vIndices() { return m_vertexIndices; }
     TupleI3* nIndices() { return m_normalIndices; }
+    VectorR2* texCoords() { return m_texCoords; }
+    TupleI3* tIndices() { return m_texCoordIndices; }
     int numTris() { return m_numTris; }
+    int numTextCoords() { return m_numTextCoords; }
 protected:
     void loadObj(FILE* fp, const Matrix4x4& ctm);
     Vector3* m_normals;
     Vector3* m_vertices;
     TupleI3* m_normalIndices;
     TupleI3* m_vertexIndices;
-    unsigned int m_numVertices, m_numTris;
+    VectorR2* m_texCoords;
+    TupleI3* m_texCoordIndices;
+    unsigned int m_numVertices, m_numTris, m_numTextCoords;
 };
 #endif

@@ -49,11 +49,12 @@ double wall()
 }  // namespace
 
 // ================================= TriangleMesh ===========================================================
-TriangleMesh::TriangleMesh() : m_normals(0), m_vertices(0), m_normalIndices(0), m_vertexIndices(0), m_numVertices(0), m_numTris(0) {}
+TriangleMesh::TriangleMesh() : m_normals(0), m_vertices(0), m_normalIndices(0), m_vertexIndices(0), m_texCoords(0), m_texCoordIndices(0),
+                               m_numVertices(0), m_numTris(0), m_numTextCoords(0) {}
 
 TriangleMesh::~TriangleMesh()
 {
-    delete[] m_normals; delete[] m_vertices; delete[] m_normalIndices; delete[] m_vertexIndices;
+    delete[] m_normals; delete[] m_vertices; delete[] m_normalIndices; delete[] m_vertexIndices; delete[] m_texCoords; delete[] m_texCoordIndices;
 }
 
 void TriangleMesh::createSingleTriangle()
@@ -62,9 +63,14 @@ void TriangleMesh::createSingleTriangle()
     m_vertices = new Vector3[3];
     m_normalIndices = new TupleI3[1];
     m_vertexIndices = new TupleI3[1];
-    for (unsigned k = 0; k < 3; ++k) m_vertexIndices[0].v[k] = m_normalIndices[0].v[k] = k;
+    // TriangleMeshLoad.cpp:20-42: the single triangle carries the texture coordinates (0,0) (1,0) (0,1)
+    m_texCoords = new VectorR2[3];
+    m_texCoords[0].x = 0.0f; m_texCoords[0].y = 0.0f; m_texCoords[1].x = 1.0f; m_texCoords[1].y = 0.0f; m_texCoords[2].x = 0.0f; m_texCoords[2].y = 1.0f;
+    m_texCoordIndices = new TupleI3[1];
+    for (unsigned k = 0; k < 3; ++k) m_vertexIndices[0].v[k] = m_normalIndices[0].v[k] = m_texCoordIndices[0].v[k] = k;
     m_numVertices = 3;
     m_numTris = 1;
+    m_numTextCoords = 3;
 }
 
 bool TriangleMesh::load(const char* file, const Matrix4x4& ctm)
@@ -94,16 +100,16 @@ void splitFaceToken(char* tok, int& v, int& t, int& n)
 namespace {
 struct ObjPiece {
     const char* p; int len;
-    char kind;            // 'v' vertex, 'n' normal, 'f' face, 0 anything else
+    char kind;            // 'v' vertex, 'n' normal, 't' texture coordinate, 'f' face, 0 anything else
     float f[3];
-    int v[3], n[3];
+    int v[3], n[3], t[3];
 };
 inline void parsePiece(ObjPiece& q)
 {
     char line[81];
     memcpy(line, q.p, (size_t)q.len); line[q.len] = 0;
-    if (q.kind == 'v' || q.kind == 'n') {
-        char* c = line + (q.kind == 'n' ? 2 : 1);
+    if (q.kind == 'v' || q.kind == 'n' || q.kind == 't') {
+        char* c = line + (q.kind == 'v' ? 1 : 2);
         q.f[0] = q.f[1] = q.f[2] = 0.f;
         for (int k = 0; k < 3; ++k) { char* e = 0; const float x = strtof(c, &e); if (e == c) break; q.f[k] = x; c = e; }
     } else if (q.kind == 'f') {
@@ -113,8 +119,7 @@ inline void parsePiece(ObjPiece& q)
             char* tok = c;
             while (*c && !(*c == ' ' || *c == '\t' || *c == '\n' || *c == '\r' || *c == '\v' || *c == '\f')) ++c;
             if (*c) *c++ = 0;
-            int t = 0;
-            splitFaceToken(tok, q.v[k], t, q.n[k]);
+            splitFaceToken(tok, q.v[k], q.t[k], q.n[k]);
         }
     }
 }
@@ -131,7 +136,7 @@ void TriangleMesh::loadObj(FILE* fp, const Matrix4x4& ctm)
     // the pieces fgets(line, 80, fp) would return: up to 79 bytes, ending after a newline if one comes first
     std::vector<ObjPiece> pieces;
     pieces.reserve(got / 24 + 16);
-    int nv = 0, nf = 0;
+    int nv = 0, nf = 0, nt = 0;
     for (size_t s0 = 0; s0 < got;) {
         const size_t lim = std::min(got - s0, (size_t)79);
         const void* nl = memchr(text.data() + s0, '\n', lim);
@@ -139,9 +144,9 @@ void TriangleMesh::loadObj(FILE* fp, const Matrix4x4& ctm)
         ObjPiece q;
         q.p = text.data() + s0; q.len = (int)len; q.kind = 0;
         const char c0 = q.p[0], c1 = len > 1 ? q.p[1] : 0;
-        if (c0 == 'v') { if (c1 == 'n') q.kind = 'n'; else if (c1 != 't') { q.kind = 'v'; nv++; } }
+        if (c0 == 'v') { if (c1 == 'n') q.kind = 'n'; else if (c1 == 't') { q.kind = 't'; nt++; } else { q.kind = 'v'; nv++; } }
         else if (c0 == 'f') { q.kind = 'f'; nf++; }
-        q.v[0] = q.v[1] = q.v[2] = q.n[0] = q.n[1] = q.n[2] = 0;
+        q.v[0] = q.v[1] = q.v[2] = q.n[0] = q.n[1] = q.n[2] = q.t[0] = q.t[1] = q.t[2] = 0;
         pieces.push_back(q);
         s0 += len;
     }
@@ -155,6 +160,13 @@ void TriangleMesh::loadObj(FILE* fp, const Matrix4x4& ctm)
     m_numVertices = nv;
     m_normalIndices = new TupleI3[nf];
     m_vertexIndices = new TupleI3[nf];
+    if (nt) {   // TriangleMeshLoad.cpp:152-157
+        m_texCoords = new VectorR2[nt];
+        m_texCoordIndices = new TupleI3[nf];
+        memset(m_texCoordIndices, 0, sizeof(TupleI3) * (size_t)nf);
+    }
+    m_numTextCoords = nt;
+    int ntextures = 0;
     std::vector<char> synthesised(ncap, 0);
     Matrix4x4 nctm = ctm;
     nctm.invert();
@@ -172,6 +184,9 @@ void TriangleMesh::loadObj(FILE* fp, const Matrix4x4& ctm)
             nnormals++;
         } else if (q.kind == 'v') {
             m_vertices[nverts++] = ctm * Vector3(q.f[0], q.f[1], q.f[2]);
+        } else if (q.kind == 't') {
+            m_texCoords[ntextures].x = q.f[0]; m_texCoords[ntextures].y = q.f[1];
+            ntextures++;
         } else if (q.kind == 'f') {
             TupleI3& vi = m_vertexIndices[m_numTris];
             TupleI3& ni = m_normalIndices[m_numTris];
@@ -180,6 +195,7 @@ void TriangleMesh::loadObj(FILE* fp, const Matrix4x4& ctm)
                 n = q.n[k];
                 vi.v[k] = q.v[k] - 1;
                 if (n) { ni.v[k] = n - 1; touch.push_back(std::make_pair(q.v[k] - 1, n - 1)); }
+                if (q.t[k] && nt) m_texCoordIndices[m_numTris].v[k] = q.t[k] - 1;
             }
             if (!n) {   // the LAST token decides, as in the reference
                 const Vector3 e1 = m_vertices[vi.v[1]] - m_vertices[vi.v[0]];
@@ -338,6 +354,7 @@ uint32_t materialIndex(const Material* mat, std::map<const Material*, uint32_t>&
         for (int k = 0; k < 3; ++k) { mm.kd[k] = kd[k]; mm.ks[k] = ks[k]; mm.kt[k] = kt[k]; }
         mm.shininess = mat ? mat->getShininess() : 1.f;
         mm.refract_index = mat ? mat->getRefractionIndex() : 1.f;
+        if (mat) mat->describeTexture(mm);                     // TexturedPhong: texture kind + constructor arguments
         it = matIndex.insert(std::make_pair(mat, (uint32_t)mats.size())).first;
         mats.push_back(mm);
     }
@@ -355,7 +372,8 @@ void BVH::build(Objects* objs, int)
     m_prims.clear(); m_other.clear();
     std::map<const Material*, uint32_t> matIndex;
     std::vector<mirogpu_material> mats;
-    std::vector<float> verts, norms;
+    std::vector<float> verts, norms, uvs;
+    bool anyUv = false;
     std::vector<uint32_t> matIds;
     std::vector<Object*> sphereObjs, planeObjs;
     std::vector<mirogpu_sphere> spheres;
@@ -383,6 +401,15 @@ void BVH::build(Objects* objs, int)
             const Vector3& q = m->normals()[ni.v[k]];
             norms.push_back(q.x); norms.push_back(q.y); norms.push_back(q.z);
         }
+        // Triangle::toUVCoordinates interpolates the corners' texture coordinates; a mesh without them answers (0, 0)
+        if (m->numTextCoords() > 0 && m->tIndices()) {
+            const TriangleMesh::TupleI3 ti = m->tIndices()[t->getIndex()];
+            for (int k = 0; k < 3; ++k) {
+                const unsigned idx = ti.v[k] < (unsigned)m->numTextCoords() ? ti.v[k] : 0u;
+                uvs.push_back(m->texCoords()[idx].x); uvs.push_back(m->texCoords()[idx].y);
+            }
+            anyUv = true;
+        } else uvs.insert(uvs.end(), 6, 0.f);
         matIds.push_back(materialIndex(t->getMaterial(), matIndex, mats));
         m_prims.push_back(t);
     }
@@ -412,6 +439,7 @@ void BVH::build(Objects* objs, int)
     d.planes = planes.empty() ? 0 : planes.data(); d.nplanes = (uint32_t)planes.size();
     d.materials = mats.empty() ? 0 : mats.data(); d.nmaterials = (uint32_t)mats.size();
     d.devices = devs.empty() ? 0 : devs.data(); d.ndevices = (uint32_t)devs.size();
+    d.tri_texcoords = (anyUv && m_ntris) ? uvs.data() : 0;
     const int rc = mirogpu_scene_create_ex(&d, &opt, &m_handle);
     if (rc != MIROGPU_OK) die("BVH::build");
 }
@@ -609,7 +637,63 @@ long Scene::tracePhotonPass(Photon_map& map, int which, int target, bool caustic
 }
 
 // Scene.cpp:232-266 for UV-lookup materials with zero bump height: the perturbation vanishes, N is normalised.
-void Scene::postProcess(HitInfo& minHit) const { minHit.N.normalize(); }
+// Scene.cpp:232-262: materials with UV lookup coordinates (plain Phong, 2-D textures) get the bump-mapped, normalised normal --
+// the perturbation vanishes for every texture but StoneTexture --, materials with UVW coordinates keep the normal as the object
+// computed it.  (The device applies the same rule to every hit it shades: resolve_hit_textured, csrc/kernels.cuh.)
+void Scene::postProcess(HitInfo& minHit) const
+{
+    if (minHit.material && minHit.material->GetLookupCoordinates() != UV) return;
+    const float delta = 0.0001f;
+    float dx = 0.f, dy = 0.f;
+    if (minHit.material && minHit.object) {
+        const tex_coord2d_t c = minHit.object->toUVCoordinates(minHit.P);
+        const float u1 = minHit.material->bumpHeight2D(tex_coord2d_t(c.u - delta, c.v)), u2 = minHit.material->bumpHeight2D(tex_coord2d_t(c.u + delta, c.v));
+        const float v1 = minHit.material->bumpHeight2D(tex_coord2d_t(c.u, c.v - delta)), v2 = minHit.material->bumpHeight2D(tex_coord2d_t(c.u, c.v + delta));
+        dx = (u2 - u1) / (2 * delta); dy = (v2 - v1) / (2 * delta);
+    }
+    if (dx != 0.f || dy != 0.f) {
+        const float n[3] = {minHit.N.x, minHit.N.y, minHit.N.z};
+        int m = 0;
+        if (n[1] > n[0]) m = 1;
+        if (n[2] > n[m]) m = 2;
+        const Vector3 randomVec(m == 2 ? -n[2] : 0, m == 0 ? -n[0] : 0, m == 1 ? -n[1] : 0);
+        const Vector3 t1 = cross(minHit.N, randomVec);
+        minHit.N += dx * (cross(minHit.N, t1)) - dy * (cross(minHit.N, cross(minHit.N, t1)));
+    }
+    minHit.N.normalize();
+}
+
+tex_coord2d_t Sphere::toUVCoordinates(const Vector3& xyz) const
+{
+    Vector3 dir = xyz - m_center;
+    dir.normalize();
+    tex_coord2d_t coords;
+    coords.u = (atan2f(dir.x, dir.z)) / (2.0f * PI) + 0.5;
+    coords.v = (std::max(-1.0f, std::min(1.0f, asinf(dir.y)))) / PI + 0.5;
+    return coords;
+}
+
+tex_coord2d_t Triangle::toUVCoordinates(const Vector3& xyz) const
+{
+    if (m_mesh->numTextCoords() == 0 || !m_mesh->tIndices()) return tex_coord2d_t();
+    const TriangleMesh::TupleI3 vi3 = m_mesh->vIndices()[m_index], ti3 = m_mesh->tIndices()[m_index];
+    const Vector3 &vA = m_mesh->vertices()[vi3.v[0]], &vB = m_mesh->vertices()[vi3.v[1]], &vC = m_mesh->vertices()[vi3.v[2]];
+    const TriangleMesh::VectorR2 &tA = m_mesh->texCoords()[ti3.v[0]], &tB = m_mesh->texCoords()[ti3.v[1]], &tC = m_mesh->texCoords()[ti3.v[2]];
+    // barycentrics in the plane that drops one axis, by Cramer's rule
+    const Vector3 BmA = vB - vA, CmA = vC - vA;
+    const Vector3 normal = cross(BmA, CmA);
+    int i = 0, j = 1;
+    if (normal.x > normal.z) i = 2;
+    else if (normal.y > normal.z) j = 2;
+    const float p[3] = {xyz.x - vA.x, xyz.y - vA.y, xyz.z - vA.z}, B[3] = {BmA.x, BmA.y, BmA.z}, C[3] = {CmA.x, CmA.y, CmA.z};
+    const float detPC = p[i] * C[j] - C[i] * p[j], detBP = B[i] * p[j] - p[i] * B[j], detBC = B[i] * C[j] - C[i] * B[j];
+    const float beta = std::max(detPC / detBC, 0.f), gamma = std::max(detBP / detBC, 0.f);
+    const float alpha = std::max(1 - (beta + gamma), 0.f);
+    tex_coord2d_t UV;
+    UV.u = alpha * tA.x + beta * tB.x + gamma * tC.x;
+    UV.v = alpha * tA.y + beta * tB.y + gamma * tC.y;
+    return UV;
+}
 
 bool Scene::trace(HitInfo& minHit, const Ray& ray, float tMin, float tMax) const
 {

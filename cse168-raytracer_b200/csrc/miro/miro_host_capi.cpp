@@ -8,6 +8,7 @@
 
 #include "Miro.h"
 #include "Scene.h"
+#include "Texture.h"
 #include "Camera.h"
 #include "Image.h"
 #include "Triangle.h"
@@ -41,6 +42,25 @@ int mh_new_material(const float* kd, const float* ks, const float* kt, float shi
 {
     if (shininess < 0) shininess = infinity;
     g_materials.push_back(new Phong(Vector3(kd[0], kd[1], kd[2]), Vector3(ks[0], ks[1], ks[2]), Vector3(kt[0], kt[1], kt[2]), shininess, refr_index));
+    return (int)g_materials.size() - 1;
+}
+
+// TexturedPhong(texture, ks, kt, shininess, refractIndex) over one of the procedural textures; tp: the texture's constructor
+// arguments in mirogpu_material::tex order (include/mirogpu.h)
+int mh_new_textured_material(int kind, const float* tp, const float* ks, const float* kt, float shininess, float refr_index)
+{
+    if (shininess < 0) shininess = infinity;
+    Texture* t = 0;
+    switch (kind) {
+    case MIROGPU_TEX_CHECKER: t = new CheckerBoardTexture(Vector3(tp[0], tp[1], tp[2]), Vector3(tp[3], tp[4], tp[5]), tp[6]); break;
+    case MIROGPU_TEX_STONE: t = new StoneTexture(tp[0]); break;
+    case MIROGPU_TEX_STEM: t = new StemTexture(tp[0]); break;
+    case MIROGPU_TEX_PETAL: t = new PetalTexture(Vector3(tp[0], tp[1], tp[2]), tp[3]); break;
+    case MIROGPU_TEX_LEAF: t = new LeafTexture(Vector3(0, 0, 0), Vector3(1, 0, 0), tp[0]); break;
+    case MIROGPU_TEX_FLOWER_CENTER: t = new FlowerCenterTexture(Vector3(tp[0], tp[1], tp[2]), tp[3]); break;
+    default: return -1;
+    }
+    g_materials.push_back(new TexturedPhong(t, Vector3(ks[0], ks[1], ks[2]), Vector3(kt[0], kt[1], kt[2]), shininess, refr_index));
     return (int)g_materials.size() - 1;
 }
 

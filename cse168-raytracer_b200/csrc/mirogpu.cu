@@ -124,6 +124,7 @@ struct mirogpu_scene {
     cudaStream_t mstream = nullptr;        // multi-device render: this replica's stream and its "rows are in place" event
     cudaEvent_t mevent = nullptr;
     mirogpu_material* d_materials = nullptr;
+    float* d_uvs = nullptr;
     uint32_t nmaterials = 0;
     mirogpu_light* d_lights = nullptr;
     uint32_t nlights = 0;
@@ -368,6 +369,8 @@ struct HostBuild {
     std::unique_ptr<float4[]> shade; size_t shade_count = 0;
     std::vector<mirogpu_material> mats;
     std::vector<float4> planes;   // 2 per plane: (normal, prim id bits) (origin, 0)
+    std::vector<float> uvs;       // 6 per triangle, prim-id order (empty: no texture coordinates)
+    bool textured = false;        // a material carries a procedural texture
     BinaryBvh bin; FlatBvh flat;
     uint32_t nprims = 0, ntris = 0, nspheres = 0, nplanes = 0;
     mirogpu_scene_info info{};
@@ -435,6 +438,10 @@ int upload_replica(const HostBuild& hb, int dev, const LbvhOut* lb, mirogpu_scen
     if (shade_bytes && (e = cudaMemcpy(h->d_shade, hb.shade.get(), shade_bytes, cudaMemcpyHostToDevice)) != cudaSuccess) return bail(e, "upload shading records");
     if ((e = cudaMemcpy(h->d_materials, hb.mats.data(), hb.mats.size() * sizeof(mirogpu_material), cudaMemcpyHostToDevice)) != cudaSuccess) return bail(e, "upload materials");
     if (!hb.planes.empty() && (e = cudaMemcpy(h->d_planes, hb.planes.data(), hb.planes.size() * sizeof(float4), cudaMemcpyHostToDevice)) != cudaSuccess) return bail(e, "upload planes");
+    if (hb.textured && !hb.uvs.empty()) {
+        if ((e = cudaMalloc(&h->d_uvs, hb.uvs.size() * sizeof(float))) != cudaSuccess) return bail(e, "cudaMalloc texture coordinates");
+        if ((e = cudaMemcpy(h->d_uvs, hb.uvs.data(), hb.uvs.size() * sizeof(float), cudaMemcpyHostToDevice)) != cudaSuccess) return bail(e, "upload texture coordinates");
+    }
     if ((e = cudaMemset(h->d_ticket, 0, 64 * sizeof(unsigned long long))) != cudaSuccess) return bail(e, "memset tickets");
     h->nmaterials = (uint32_t)hb.mats.size();
     h->any_refractive = hb.any_refractive; h->any_specular = hb.any_specular;
@@ -446,6 +453,7 @@ int upload_replica(const HostBuild& hb, int dev, const LbvhOut* lb, mirogpu_scen
     h->ds.planes = reinterpret_cast<const float4*>(h->d_planes);
     h->ds.num_tris = hb.nprims;
     h->ds.num_planes = hb.nplanes;
+    h->ds.mats = h->d_materials; h->ds.uvs = h->d_uvs; h->ds.textured = hb.textured ? 1u : 0u;
     h->non_triangles = hb.nspheres + hb.nplanes;
     h->info = hb.info;
     *out = h;
@@ -628,7 +636,13 @@ int scene_create_impl(const mirogpu_scene_desc& d, const mirogpu_build_options* 
     for (const mirogpu_material& m : hb.mats) {
         hb.any_refractive |= m.kt[0] > 0.f || m.kt[1] > 0.f || m.kt[2] > 0.f;
         hb.any_specular |= m.ks[0] > 0.f || m.ks[1] > 0.f || m.ks[2] > 0.f;
+        if (m.texture < MIROGPU_TEX_NONE || m.texture > MIROGPU_TEX_FLOWER_CENTER) {
+            if (device_built && lb.d_geom) cudaFree(lb.d_geom);
+            return fail(MIROGPU_ERR_INVALID_ARG, "unknown texture kind");
+        }
+        hb.textured |= m.texture != MIROGPU_TEX_NONE;
     }
+    if (hb.textured && d.tri_texcoords && ntris) hb.uvs.assign(d.tri_texcoords, d.tri_texcoords + (size_t)ntris * 6);
 
     mirogpu_scene_info& in = hb.info;
     in.num_triangles = ntris;
@@ -712,7 +726,7 @@ int mirogpu_scene_destroy(mirogpu_handle h)
     for (mirogpu_scene* r : h->replicas) mirogpu_scene_destroy(r);
     h->replicas.clear();
     cudaSetDevice(h->device);
-    cudaFree(h->d_nodes); cudaFree(h->d_shade); cudaFree(h->d_materials);   // d_tris lives inside d_nodes's allocation
+    cudaFree(h->d_nodes); cudaFree(h->d_shade); cudaFree(h->d_materials); cudaFree(h->d_uvs);   // d_tris lives inside d_nodes's allocation
     cudaFree(h->d_lights); cudaFree(h->d_ticket); cudaFree(h->d_planes);
     if (h->h_stats) cudaFreeHost(h->h_stats);
     for (int i = 0; i < 2; ++i) h->pm[i].release();
@@ -938,8 +952,10 @@ int mirogpu_generate_bounce_device(mirogpu_handle h, const mirogpu_ray* d_rays, 
 #define MIRO_GENB(K)                                                                                                              \
     {                                                                                                                             \
         const size_t tile = (size_t)MIRO_GENB_THREADS * K;                                                                        \
-        k_gen_bounce<K><<<(unsigned)((n + tile - 1) / tile), MIRO_GENB_THREADS, 0, st>>>(h->ds, d_rays, d_hits, n, seed, sample, \
-                                                                                         index_base, d_out, d_live_count);      \
+        if (h->ds.textured) k_gen_bounce<K, true><<<(unsigned)((n + tile - 1) / tile), MIRO_GENB_THREADS, 0, st>>>(h->ds, d_rays, d_hits, n, seed, sample, \
+                                                                                                              index_base, d_out, d_live_count); \
+        else k_gen_bounce<K><<<(unsigned)((n + tile - 1) / tile), MIRO_GENB_THREADS, 0, st>>>(h->ds, d_rays, d_hits, n, seed, sample, \
+                                                                                              index_base, d_out, d_live_count);      \
     }
     if (items == 1) MIRO_GENB(1) else if (items == 2) MIRO_GENB(2) else if (items == 3) MIRO_GENB(3) else MIRO_GENB(4)
 #undef MIRO_GENB
@@ -1229,6 +1245,25 @@ int mirogpu_photon_upload(mirogpu_handle h, int which, const void* photons, int 
     std::string err;
     const int rc = h->pm[which].upload(photons, stored, err);
     return rc == MIROGPU_OK ? rc : fail(rc, err);
+}
+
+int mirogpu_texture_lookup(int kind, const float* tex, float u, float v, float w, float* rgb3)
+{
+    if (!tex || !rgb3 || kind <= MIROGPU_TEX_NONE || kind > MIROGPU_TEX_FLOWER_CENTER) return fail(MIROGPU_ERR_INVALID_ARG, "bad texture query");
+    mirogpu_material m; memset(&m, 0, sizeof m);
+    m.texture = kind; memcpy(m.tex, tex, sizeof m.tex);
+    const float uv[2] = {u, v}, P[3] = {u, v, w};
+    material_diffuse_color(m, uv, P, rgb3);
+    return MIROGPU_OK;
+}
+
+int mirogpu_texture_bump(int kind, const float* tex, float u, float v, float* height)
+{
+    if (!tex || !height || kind <= MIROGPU_TEX_NONE || kind > MIROGPU_TEX_FLOWER_CENTER) return fail(MIROGPU_ERR_INVALID_ARG, "bad texture query");
+    mirogpu_material m; memset(&m, 0, sizeof m);
+    m.texture = kind; memcpy(m.tex, tex, sizeof m.tex);
+    *height = material_bump_height(m, u, v);
+    return MIROGPU_OK;
 }
 
 int mirogpu_photon_set_exact(mirogpu_handle h, int which, int exact)

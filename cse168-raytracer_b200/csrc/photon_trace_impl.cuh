@@ -74,12 +74,19 @@ __global__ void __launch_bounds__(128) k_photon_trace(DeviceScene s, const mirog
         trace_one<LAYOUT, false, false, NT>(s, r, best, nullptr);
         if (best.prim == MIROGPU_MISS) break;
         mirogpu_hit h; h.t = best.t; h.prim_id = best.prim; h.beta = best.beta; h.gamma = best.gamma;
-        const SurfacePoint sp = resolve_hit(load_shade_record(s, h.prim_id), h, r);
+        const ShadeRecord prec = load_shade_record(s, h.prim_id);
+        SurfacePoint sp;
+        float dc[3];
+        if (s.textured) {
+            const TexturedPoint tp = resolve_hit_textured(prec, h, r.ox, r.oy, r.oz, r.dx, r.dy, r.dz, mats, s.uvs);
+            sp = tp.sp; dc[0] = tp.dc[0]; dc[1] = tp.dc[1]; dc[2] = tp.dc[2];
+        } else sp = resolve_hit(prec, h, r);
         const mirogpu_material m = mats[sp.material];
+        if (!s.textured) { dc[0] = m.kd[0]; dc[1] = m.kd[1]; dc[2] = m.kd[2]; }   // the diffuse colour looked up at the hit (Scene.cpp:546-551)
         float u[4];
         uniform4(em.seed, e, (uint32_t)depth, 3, u);
         const float rnd = u[0];
-        const float p0 = average3(m.kd), p1 = xadd(p0, average3(m.ks)), p2 = xadd(p1, average3(m.kt));
+        const float p0 = average3(dc), p1 = xadd(p0, average3(m.ks)), p2 = xadd(p1, average3(m.kt));
         if (rnd > p2) break;                                   // absorbed
         if (rnd < p0) {
             if (depth > 1) {                                   // only indirect light is stored (Scene.cpp:567)
@@ -97,7 +104,7 @@ __global__ void __launch_bounds__(128) k_photon_trace(DeviceScene s, const mirog
             for (int k = 0; k < 3; ++k) {
                 pos[k] = xadd(sp.P[k], xmul(d[k], MIRO_EPS));
                 dir[k] = d[k];
-                power[k] = xmul(xmul(m.kd[k], power[k]), inv);
+                power[k] = xmul(xmul(dc[k], power[k]), inv);
             }
         } else {
             const bool mirror = rnd < p1;

@@ -126,7 +126,7 @@ __device__ __forceinline__ float powi_ref(float x, int m)
 // reference's x86 build): unit vector to the light, its distance, the diffuse term colour * ((max(0, N.l * falloff * W) * kd) * kd)
 // (Phong::diffuse2D returns m_diffuse, so kd enters twice, Phong.cpp:146, Phong.h:20) and the highlight (exponent fixed at 500,
 // Phong.cpp:152).  false: the point lies outside a DirectionalAreaLight's beam.
-__device__ __forceinline__ bool light_terms(const mirogpu_light L, const SurfacePoint& sp, const mirogpu_material& m, const float rd[3],
+__device__ __forceinline__ bool light_terms(const mirogpu_light L, const SurfacePoint& sp, const mirogpu_material& m, const float dc[3], const float rd[3],
                                             float l[3], float& dist, float cd[3], float& hl)
 {
     if (L.kind == 1) { l[0] = -L.normal[0]; l[1] = -L.normal[1]; l[2] = -L.normal[2]; }
@@ -148,9 +148,10 @@ __device__ __forceinline__ bool light_terms(const mirogpu_light L, const Surface
         falloff = xdiv(1.0f, xmul(xmul(xmul(falloff, 4.0f), MIRO_PI), MIRO_PI));
     }
     const float dterm = fmaxf(0.0f, xmul(xmul(nDotL, falloff), L.wattage));
-    cd[0] = xmul(L.color[0], xmul(xmul(m.kd[0], dterm), m.kd[0]));
-    cd[1] = xmul(L.color[1], xmul(xmul(m.kd[1], dterm), m.kd[1]));
-    cd[2] = xmul(L.color[2], xmul(xmul(m.kd[2], dterm), m.kd[2]));
+    // dc: the diffuse colour looked up for this point (Phong.cpp:50-55) -- m.kd itself for an untextured Phong
+    cd[0] = xmul(L.color[0], xmul(xmul(dc[0], dterm), m.kd[0]));
+    cd[1] = xmul(L.color[1], xmul(xmul(dc[1], dterm), m.kd[1]));
+    cd[2] = xmul(L.color[2], xmul(xmul(dc[2], dterm), m.kd[2]));
     hl = 0.f;
     if (m.shininess < INFINITY) {
         const float ldn = xmul(2.0f, xdot(l[0], l[1], l[2], sp.N[0], sp.N[1], sp.N[2]));
@@ -183,15 +184,21 @@ __device__ __forceinline__ bool shade_item(const WaveParams& p, const Queue& cur
         return false;
     }
     mirogpu_hit h; h.t = hv.x; h.prim_id = __float_as_uint(hv.y); h.beta = hv.z; h.gamma = hv.w;
-    const SurfacePoint sp = resolve_hit(rec, h, ray);
+    SurfacePoint sp;
+    float dc[3];
+    if (p.ds.textured) {
+        const TexturedPoint tp = resolve_hit_textured(rec, h, ray.ox, ray.oy, ray.oz, ray.dx, ray.dy, ray.dz, p.mats, p.ds.uvs);
+        sp = tp.sp; dc[0] = tp.dc[0]; dc[1] = tp.dc[1]; dc[2] = tp.dc[2];
+    } else sp = resolve_hit(rec, h, ray);
     const mirogpu_material m = p.mats[sp.material];
+    if (!p.ds.textured) { dc[0] = m.kd[0]; dc[1] = m.kd[1]; dc[2] = m.kd[2]; }
     const float rd[3] = {ray.dx, ray.dy, ray.dz};
     float direct[3] = {0.f, 0.f, 0.f};
 
     // ---- Phong::shade light loop -------------------------------------------------------------------
     for (uint32_t li = 0; li < p.nlights; ++li) {
         float l[3], cd[3], dist, hl;
-        if (!light_terms(p.lights[li], sp, m, rd, l, dist, cd, hl)) continue;
+        if (!light_terms(p.lights[li], sp, m, dc, rd, l, dist, cd, hl)) continue;
         if (p.shadows) {
             if (cd[0] > 0.f || cd[1] > 0.f || cd[2] > 0.f || hl > 0.f) {
                 const size_t s = (size_t)i * p.nlights + li;
@@ -351,7 +358,8 @@ __global__ void __launch_bounds__(256) k_shadow_accumulate(WaveParams p, const m
     float intensity = 1.f;
     if (__float_as_uint(hv.y) != MIROGPU_MISS) {
         mirogpu_hit h; h.t = hv.x; h.prim_id = __float_as_uint(hv.y); h.beta = hv.z; h.gamma = hv.w;
-        const SurfacePoint sp = resolve_hit(load_shade_record(p.ds, h.prim_id), h, r);
+        const ShadeRecord orec = load_shade_record(p.ds, h.prim_id);
+        const SurfacePoint sp = p.ds.textured ? resolve_hit_textured(orec, h, r.ox, r.oy, r.oz, r.dx, r.dy, r.dz, p.mats, p.ds.uvs).sp : resolve_hit(orec, h, r);
         const mirogpu_material m = p.mats[sp.material];
         if (!(m.kt[0] > 0.f || m.kt[1] > 0.f || m.kt[2] > 0.f)) return;      // opaque occluder
         const float l[3] = {r.dx, r.dy, r.dz};
@@ -557,7 +565,7 @@ __global__ void __launch_bounds__(MIRO_BW_THREADS) k_bounce_wave0(WaveParams p, 
                 float direct[3] = {0.f, 0.f, 0.f};
                 for (uint32_t li = 0; li < p.nlights; ++li) {
                     float l[3], cd[3], dist, hl;
-                    if (!light_terms(p.lights[li], sp, m, rd, l, dist, cd, hl)) continue;
+                    if (!light_terms(p.lights[li], sp, m, m.kd, rd, l, dist, cd, hl)) continue;
                     direct[0] = xadd(xadd(direct[0], cd[0]), hl); direct[1] = xadd(xadd(direct[1], cd[1]), hl); direct[2] = xadd(xadd(direct[2], cd[2]), hl);   // L = L + diffuse; L = L + highlights (Phong.cpp:146-156)
                 }
                 out[0] = 1.f * direct[0]; out[1] = 1.f * direct[1]; out[2] = 1.f * direct[2];
@@ -621,7 +629,7 @@ __global__ void __launch_bounds__(MIRO_BW_THREADS) k_bounce_wave1(WaveParams p, 
             float direct[3] = {0.f, 0.f, 0.f};
             for (uint32_t li = 0; li < p.nlights; ++li) {
                 float l[3], cd[3], dist, hl;
-                if (!light_terms(p.lights[li], sp, m, rd, l, dist, cd, hl)) continue;
+                if (!light_terms(p.lights[li], sp, m, m.kd, rd, l, dist, cd, hl)) continue;
                 direct[0] = xadd(xadd(direct[0], cd[0]), hl); direct[1] = xadd(xadd(direct[1], cd[1]), hl); direct[2] = xadd(xadd(direct[2], cd[2]), hl);   // L = L + diffuse; L = L + highlights (Phong.cpp:146-156)
             }
             if (direct[0] == 0.f && direct[1] == 0.f && direct[2] == 0.f) continue;
@@ -687,7 +695,7 @@ int render_device_once(mirogpu_scene* h, const mirogpu_camera& cam, const mirogp
     const bool use_pm = rp.use_photon_maps && (h->pm[0].stored > 0 || h->pm[1].stored > 0);
 
     RenderScratch& sc = h->scratch;
-    if (rp.mode == MIROGPU_RENDER_DIFFUSE_BOUNCE && !shadows && !use_pm && rp.max_depth >= 1 && !getenv("MIROGPU_GENERAL_WAVEFRONT")) {
+    if (rp.mode == MIROGPU_RENDER_DIFFUSE_BOUNCE && !shadows && !use_pm && rp.max_depth >= 1 && !h->ds.textured && !getenv("MIROGPU_GENERAL_WAVEFRONT")) {
         // ---- two fused waves (see k_bounce_wave0) ------------------------------------------------------------------------
         const uint32_t fb = (uint32_t)std::min(rp.spp, 16);
         const size_t fitems0 = npix * fb;

@@ -151,7 +151,38 @@ def _meadow():
                 camera=dict(eye=(22.5, 1.0, 22.5), lookat=(0, -3, 0), up=(0, 1, 0), fov=70), size=(1920, 1080))
 
 
+# MIROGPU_TEX_* (include/mirogpu.h); a material entry with "tex": (kind, constructor arguments) is a TexturedPhong
+TEX_CHECKER, TEX_STONE, TEX_STEM, TEX_PETAL, TEX_LEAF, TEX_FLOWER_CENTER = 1, 2, 3, 4, 5, 6
+
+
+def _tex(kind, params, ks=(0, 0, 0), kt=(0, 0, 0), shininess=1.0, refr=1.0):
+    return dict(tex=(kind, list(params)), kd=(1, 1, 1), ks=ks, kt=kt, shininess=shininess, refr=refr)
+
+
 SCENES = {
+    # every procedural texture of Texture.h on the primitive kinds it meets in the reference's scenes -- the stone
+    # floor plane of assignment1.cpp:229-232 (the one texture with a bump height), a checkerboard sphere (Sphere::toUVCoordinates),
+    # the flower centre's radial colour on a sphere, petal and leaf textures (3-D lookups) on the teapot and a triangle,
+    # and StemTexture on Stem.obj through its own texture coordinates (Triangle::toUVCoordinates); a mirror sphere reflects it all
+    "textured": dict(
+        meshes=[("teapot", None, 2), ("Stem", _chain(translate(3.2, 3.0, -1.0), scale(0.45, 0.45, 0.45)), 5)],
+        triangles=[(dict(v=[-6, 0.2, -3, -2.5, 0.2, -3, -4, 3.5, -3.5], n=[0, 0, 1] * 3), 4)],
+        materials=[_tex(TEX_STONE, [3.0]), _tex(TEX_CHECKER, [1, 0.9, 0.2, 0.1, 0.1, 0.6, 8.0]), _tex(TEX_PETAL, [0, 0, 0, 3.0], shininess=500.0, refr=1.5),
+                   _tex(TEX_FLOWER_CENTER, [2.4, 0.8, 1.0, 0.8]), _tex(TEX_LEAF, [1.0]), _tex(TEX_STEM, [30.0]),
+                   dict(kd=(0.1, 0.1, 0.1), ks=(0.8, 0.8, 0.8), kt=(0, 0, 0), shininess=50.0, refr=1.0)],
+        spheres=[dict(c=(-2.2, 1.0, 0.5), r=1.0, mat=1), dict(c=(2.4, 0.8, 1.0), r=0.8, mat=3), dict(c=(0.2, 0.9, -2.6), r=0.9, mat=6)],
+        planes=[dict(n=(0, 1, 0), o=(0, 0, 0), mat=0)],
+        lights=[dict(kind=0, pos=(6, 10, 8), color=(1, 1, 1), wattage=5000)], bg=(0.2, 0.3, 0.5),
+        camera=dict(eye=(0, 3, 8), lookat=(0, 0.8, 0), up=(0, 1, 0), fov=45), size=(256, 256)),
+    # config 4 with the materials assignment3.cpp:93-105 gives the flower: PetalTexture(Vector3(0), 7) with shininess 500 and
+    # index 1.5, StemTexture(30), LeafTexture, water drops (FlowerCenter.obj and the HDR environment are absent from the tree)
+    "flower_textured": dict(
+        meshes=[("Petals2", None, 0), ("Stem", None, 1), ("Leaf", None, 2), ("WaterDrops", None, 3)], triangles=[],
+        materials=[_tex(TEX_PETAL, [0, 0, 0, 7.0], shininess=500.0, refr=1.5), _tex(TEX_STEM, [30.0]), _tex(TEX_LEAF, [1.0]),
+                   dict(kd=(1, 1, 1), ks=(0, 0, 0), kt=(1, 1, 1), shininess=250.0, refr=1.33)],
+        lights=[dict(kind=0, pos=(50, 50, 40), color=(1, 1, 1), wattage=60000)],
+        bg=(1, 1, 1),
+        camera=dict(eye=(2, 4.4, 16.8), lookat=(3, 0, 4), up=(0, 1, 0), fov=30), size=(2048, 1365)),
     # deep-traversal second workload of the bench (tools/bench_deep.py)
     "meadow": _meadow(),
     # makeSpiralScene (assignment1.cpp:8-76): spheres in the tree, a plane outside it
@@ -231,7 +262,10 @@ def realise(builder, name, obj_path_of):
     sc = SCENES[name]
     builder.new_scene()
     for m in sc["materials"]:
-        builder.new_material(m["kd"], m["ks"], m["kt"], m["shininess"], m["refr"])
+        if "tex" in m:      # TexturedPhong(texture, ks, kt, shininess, refractIndex): (kind, constructor arguments)
+            builder.new_textured_material(m["tex"][0], m["tex"][1], m["ks"], m["kt"], m["shininess"], m["refr"])
+        else:
+            builder.new_material(m["kd"], m["ks"], m["kt"], m["shininess"], m["refr"])
     for model, ctm, mat in sc["meshes"]:
         builder.add_obj(obj_path_of(model), ctm, mat)
     for tri, mat in sc["triangles"]:

@@ -22,6 +22,7 @@
  *                                  rule, Photon_map::store, scale_photon_power, balance      Scene.cpp:351-472, PhotonMap.cpp:246-466
  *   mirogpu_photon_balance      <- Photon_map::balance on a caller-filled array              PhotonMap.cpp:314-466
  *   mirogpu_photon_download     <- the Photon array a balanced Photon_map holds              PhotonMap.h:16-22, 81-83
+ *   mirogpu_texture_lookup/_bump <- Texture::lookup2D / lookup3D / bumpHeight2D                Texture.h:62-72, Texture.cpp:358-510
  *
  * Conventions: every function returns an int status (MIROGPU_OK = 0), never throws, keeps no global
  * state besides the per-thread last-error string, and works on an opaque scene handle.  The caller owns
@@ -72,14 +73,37 @@ typedef struct mirogpu_hit {
     float beta, gamma;
 } mirogpu_hit;
 
-/* Phong(kd, ks, kt, shininess, refractIndex) AFTER the constructor's energy clamp (Phong.cpp:13-32). */
+/* Procedural textures behind TexturedPhong (Texture.h:108-277, Texture.cpp:358-510): what Phong::shade and Scene::tracePhoton
+ * look up as the diffuse colour (Phong.cpp:50-55, Scene.cpp:546-551) and Scene::trace as the bump height (Scene.cpp:232-262).
+ * tex[] holds the constructor arguments:
+ *   CHECKER        color1[3], color2[3], scale          CheckerBoardTexture (2-D lookup: Object::toUVCoordinates)
+ *   STONE          scale                                StoneTexture        (2-D lookup, the one texture with a bump height)
+ *   STEM           scale                                StemTexture         (2-D lookup)
+ *   PETAL          pivot[3], radius                     PetalTexture        (3-D lookup at the hit point)
+ *   LEAF           scale                                LeafTexture         (3-D lookup; pivot and direction are not used by it)
+ *   FLOWER_CENTER  pivot[3], radius                     FlowerCenterTexture (3-D lookup)
+ * A material with a 3-D texture reports UVW lookup coordinates, so Scene::trace leaves its hit normal as the primitive computed
+ * it (a triangle's interpolated normal stays un-normalised, Scene.cpp:237-262) -- reproduced. */
+enum {
+    MIROGPU_TEX_NONE = 0,
+    MIROGPU_TEX_CHECKER = 1,
+    MIROGPU_TEX_STONE = 2,
+    MIROGPU_TEX_STEM = 3,
+    MIROGPU_TEX_PETAL = 4,
+    MIROGPU_TEX_LEAF = 5,
+    MIROGPU_TEX_FLOWER_CENTER = 6
+};
+
+/* Phong(kd, ks, kt, shininess, refractIndex) AFTER the constructor's energy clamp (Phong.cpp:13-32); texture != NONE:
+ * TexturedPhong(texture, ks, kt, shininess, refractIndex), whose kd is Vector3(1) before the clamp (Texture.cpp:513-517). */
 typedef struct mirogpu_material {
     float kd[3];
     float ks[3];
     float kt[3];
     float shininess; /* +inf disables the highlight (Phong.cpp:149) */
     float refract_index;
-    float _pad;
+    int32_t texture; /* MIROGPU_TEX_* */
+    float tex[12];
 } mirogpu_material;
 
 /* PointLight (kind 0, PointLight.h) or DirectionalAreaLight (kind 1, DirectionalAreaLight.h). */
@@ -214,6 +238,8 @@ typedef struct mirogpu_scene_desc {
     const int32_t* devices;
     uint32_t ndevices;
     uint32_t _pad;
+    const float* tri_texcoords;        /* ntris x 6 floats (tA, tB, tC: TriangleMesh::texCoords of the triangle's corners) or NULL =
+                                          meshes without texture coordinates (Triangle::toUVCoordinates then answers (0, 0)) */
 } mirogpu_scene_desc;
 
 typedef struct mirogpu_scene* mirogpu_handle;
@@ -351,6 +377,13 @@ int mirogpu_photon_download(mirogpu_handle h, int which, void* photons, int capa
  * records (entry 0 unused), in place: same heap order, `plane` set on the inner nodes.  bbox_min / bbox_max: the box
  * Photon_map::store accumulated (the split axes derive from it, PhotonMap.cpp:431-436).  Needs no scene handle. */
 int mirogpu_photon_balance(int device, void* photons, int stored, const float bbox_min[3], const float bbox_max[3]);
+/* ---- procedural textures, single queries on the host ------------------------------------------------------------- */
+/* Texture::lookup2D / lookup3D (Texture.h:66-72) and bumpHeight2D for the kinds above, evaluated by the same code the device
+ * shading kernels run (csrc/texture.cuh, compiled for the host): what the host layer's Texture classes answer with.  kind:
+ * MIROGPU_TEX_*; tex: the 12 parameters of mirogpu_material::tex; (u, v) for the 2-D kinds, (u, v, w) = the point for the 3-D
+ * kinds.  Not a rendering path -- frames evaluate textures on the device. */
+int mirogpu_texture_lookup(int kind, const float* tex, float u, float v, float w, float* rgb3);
+int mirogpu_texture_bump(int kind, const float* tex, float u, float v, float* height);
 /* Gather search of map `which`.  exact = 0 (default): one query per warp -- a shared stack of kd nodes and a shared
  * candidate buffer, 32 nodes tested per step, the k-th distance found by bisection when the buffer fills; it ends with the
  * same k nearest photons as the reference's search, summed in another order (estimates agree to ~1e-6 relative; k <= 512).

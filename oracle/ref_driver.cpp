@@ -36,6 +36,7 @@
 #define private public
 #include "Miro.h"
 #include "Scene.h"
+#include "Texture.h"
 #include "Camera.h"
 #include "Image.h"
 #include "Triangle.h"
@@ -113,6 +114,41 @@ int ref_new_material(const float* kd, const float* ks, const float* kt, float sh
                             Vector3(kt[0], kt[1], kt[2]), shininess, refr_index);
     g_materials.push_back(m);
     return (int)g_materials.size() - 1;
+}
+
+// The reference's own texture classes (Texture.h) by kind number (include/mirogpu.h: MIROGPU_TEX_*), constructor arguments in tp.
+static Texture* make_texture(int kind, const float* tp)
+{
+    switch (kind) {
+    case 1: return new CheckerBoardTexture(Vector3(tp[0], tp[1], tp[2]), Vector3(tp[3], tp[4], tp[5]), tp[6]);
+    case 2: return new StoneTexture(tp[0]);
+    case 3: return new StemTexture(tp[0]);
+    case 4: return new PetalTexture(Vector3(tp[0], tp[1], tp[2]), tp[3]);
+    case 5: return new LeafTexture(Vector3(0, 0, 0), Vector3(1, 0, 0), tp[0]);
+    case 6: return new FlowerCenterTexture(Vector3(tp[0], tp[1], tp[2]), tp[3]);
+    }
+    return 0;
+}
+
+int ref_new_textured_material(int kind, const float* tp, const float* ks, const float* kt, float shininess, float refr_index)
+{
+    if (shininess < 0) shininess = infinity;
+    Texture* t = make_texture(kind, tp);
+    if (!t) return -1;
+    g_materials.push_back(new TexturedPhong(t, Vector3(ks[0], ks[1], ks[2]), Vector3(kt[0], kt[1], kt[2]), shininess, refr_index));
+    return (int)g_materials.size() - 1;
+}
+
+// Texture::lookup2D / lookup3D and bumpHeight2D of the reference's classes at n coordinates (3 floats each: u, v, w)
+void ref_texture_lookup(int kind, const float* tp, const float* coords3, long n, float* rgb3, float* bump)
+{
+    Texture* t = make_texture(kind, tp);
+    for (long i = 0; i < n; ++i) {
+        const float* c = coords3 + 3 * i;
+        Vector3 col = t->GetLookupCoordinates() == UV ? t->lookup2D(tex_coord2d_t(c[0], c[1])) : t->lookup3D(tex_coord3d_t(c[0], c[1], c[2]));
+        rgb3[3 * i] = col.x; rgb3[3 * i + 1] = col.y; rgb3[3 * i + 2] = col.z;
+        if (bump) bump[i] = t->bumpHeight2D(tex_coord2d_t(c[0], c[1]));
+    }
 }
 
 // ctm: 16 floats m11..m44 in ROW order (the member order of Matrix4x4.h:21-24), or NULL for identity.

@@ -54,6 +54,19 @@ class Driver:
         """Phong(kd, ks, kt, shininess, refractIndex); shininess < 0 means infinity."""
         return self._f("new_material")(_f3(kd), _f3(ks), _f3(kt), ctypes.c_float(shininess), ctypes.c_float(refr))
 
+    def new_textured_material(self, kind, params, ks=(0, 0, 0), kt=(0, 0, 0), shininess=1.0, refr=1.0):
+        """reference only: TexturedPhong over one of its procedural textures (kind numbers of include/mirogpu.h)."""
+        tp = (ctypes.c_float * 12)(*([float(x) for x in params] + [0.0] * (12 - len(params))))
+        return self._f("new_textured_material")(int(kind), tp, _f3(ks), _f3(kt), ctypes.c_float(shininess), ctypes.c_float(refr))
+
+    def texture_lookup(self, kind, params, coords, bump=False):
+        """reference only: the real Texture classes' lookup2D / lookup3D (and bumpHeight2D) at coords (n, 3)."""
+        coords = np.ascontiguousarray(coords, np.float32).reshape(-1, 3)
+        tp = (ctypes.c_float * 12)(*([float(x) for x in params] + [0.0] * (12 - len(params))))
+        rgb = np.zeros((coords.shape[0], 3), np.float32); b = np.zeros(coords.shape[0], np.float32)
+        self._f("texture_lookup")(int(kind), tp, _fp(coords), ctypes.c_long(coords.shape[0]), _fp(rgb), _fp(b) if bump else None)
+        return (rgb, b) if bump else rgb
+
     def add_obj(self, path, ctm=None, material=0):
         c = None
         if ctm is not None:

@@ -41,11 +41,35 @@ def parse_obj(path):
                 fn=np.asarray(fn, np.int32).reshape(-1, 3))
 
 
+TEXCOORDS_NPZ = os.path.join(GOLDEN_DIR, "texcoords.npz")
+
+
+def parse_texcoords(path):
+    """The vt records and the texture index of the first three face tokens (0 = none), in file order."""
+    vt, ft = [], []
+    with open(path, "rb") as fh:
+        for raw in fh:
+            line = raw.decode("latin-1").strip()
+            if line.startswith("vt"):
+                x = line[2:].split()
+                vt.append([float(x[0]), float(x[1])])
+            elif line.startswith("f"):
+                toks = line[1:].split()[:3]
+                ft.append([int(t.split("/")[1]) if len(t.split("/")) > 1 and t.split("/")[1] else 0 for t in toks])
+    return dict(vt=np.asarray(vt, np.float32).reshape(-1, 2), ft=np.asarray(ft, np.int32).reshape(-1, 3))
+
+
 def write_obj(path, mesh):
-    """Regenerates OBJ text (lines < 80 chars, the reference's fgets limit) in the original record order."""
+    """Regenerates OBJ text (lines < 80 chars, the reference's fgets limit) in the original record order; texture coordinates
+    (models listed in texcoords.npz) come first -- the loader only appends them to a table, their place among the other
+    records does not matter."""
     iv = ivn = iff = 0
     out = []
     v, vn, fv, fn = mesh["v"], mesh["vn"], mesh["fv"], mesh["fn"]
+    ft = mesh.get("ft")
+    if ft is not None:
+        for t in mesh["vt"]:
+            out.append("vt %.9g %.9g\n" % (float(t[0]), float(t[1])))
     for k in mesh["kinds"]:
         if k == 0:
             out.append("v %.9g %.9g %.9g\n" % tuple(float(x) for x in v[iv])); iv += 1
@@ -53,7 +77,10 @@ def write_obj(path, mesh):
             out.append("vn %.9g %.9g %.9g\n" % tuple(float(x) for x in vn[ivn])); ivn += 1
         else:
             a, b = fv[iff], fn[iff]
-            if b[2] != 0 or b[0] != 0 or b[1] != 0:
+            if ft is not None:
+                c = ft[iff]
+                out.append("f " + " ".join("%d/%s/%s" % (a[k], c[k] if c[k] else "", b[k] if b[k] else "") for k in range(3)) + "\n")
+            elif b[2] != 0 or b[0] != 0 or b[1] != 0:
                 out.append("f %d//%d %d//%d %d//%d\n" % (a[0], b[0], a[1], b[1], a[2], b[2]))
             else:
                 out.append("f %d %d %d\n" % (a[0], a[1], a[2]))
@@ -65,7 +92,12 @@ def write_obj(path, mesh):
 def load_meshes():
     z = np.load(MESHES_NPZ)
     names = sorted({k.split("__")[0] for k in z.files})
-    return {n: {f: z[f"{n}__{f}"] for f in ("kinds", "v", "vn", "fv", "fn")} for n in names}
+    out = {n: {f: z[f"{n}__{f}"] for f in ("kinds", "v", "vn", "fv", "fn")} for n in names}
+    if os.path.exists(TEXCOORDS_NPZ):
+        t = np.load(TEXCOORDS_NPZ)
+        for n in sorted({k.split("__")[0] for k in t.files}):
+            out[n]["vt"] = t[f"{n}__vt"]; out[n]["ft"] = t[f"{n}__ft"]
+    return out
 
 
 _cache = {}

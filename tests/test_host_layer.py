@@ -34,7 +34,7 @@ def test_abi_exports_every_declared_symbol(pkg):
 
 
 def test_struct_sizes_match_header(pkg):
-    assert ctypes.sizeof(pkg.Material) == 48 and ctypes.sizeof(pkg.Light) == 48 and ctypes.sizeof(pkg.Camera) == 40
+    assert ctypes.sizeof(pkg.Material) == 96 and ctypes.sizeof(pkg.Light) == 48 and ctypes.sizeof(pkg.Camera) == 40
     assert ctypes.sizeof(pkg.RenderParams) == 17 * 4 and ctypes.sizeof(pkg.Counters) == 48
     assert pkg.RAY_DTYPE.itemsize == 32 and pkg.HIT_DTYPE.itemsize == 16
 
