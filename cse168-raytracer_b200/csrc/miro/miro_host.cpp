@@ -10,6 +10,7 @@
 #include <cstdarg>
 #include <cstring>
 #include <map>
+#include <omp.h>
 #include <vector>
 
 #include "Miro.h"
@@ -127,35 +128,73 @@ inline void parsePiece(ObjPiece& q)
 
 void TriangleMesh::loadObj(FILE* fp, const Matrix4x4& ctm)
 {
+    static const bool timing = getenv("MIROHOST_TIMING") != 0;
+    const double tt0 = wall();
     fseek(fp, 0, SEEK_END);
     const long fsize = ftell(fp);
     fseek(fp, 0, SEEK_SET);
     std::vector<char> text((size_t)std::max(fsize, 0L) + 1);
     const size_t got = fsize > 0 ? fread(text.data(), 1, (size_t)fsize, fp) : 0;
     text[got] = 0;
-    // the pieces fgets(line, 80, fp) would return: up to 79 bytes, ending after a newline if one comes first
-    std::vector<ObjPiece> pieces;
-    pieces.reserve(got / 24 + 16);
-    int nv = 0, nf = 0, nt = 0;
-    for (size_t s0 = 0; s0 < got;) {
-        const size_t lim = std::min(got - s0, (size_t)79);
-        const void* nl = memchr(text.data() + s0, '\n', lim);
-        const size_t len = nl ? (size_t)((const char*)nl - (text.data() + s0)) + 1 : lim;
-        ObjPiece q;
-        q.p = text.data() + s0; q.len = (int)len; q.kind = 0;
-        const char c0 = q.p[0], c1 = len > 1 ? q.p[1] : 0;
-        if (c0 == 'v') { if (c1 == 'n') q.kind = 'n'; else if (c1 == 't') { q.kind = 't'; nt++; } else { q.kind = 'v'; nv++; } }
-        else if (c0 == 'f') { q.kind = 'f'; nf++; }
-        q.v[0] = q.v[1] = q.v[2] = q.n[0] = q.n[1] = q.n[2] = q.t[0] = q.t[1] = q.t[2] = 0;
-        pieces.push_back(q);
-        s0 += len;
+    // The pieces fgets(line, 80, fp) would return: up to 79 bytes, ending after a newline if one comes first.  A physical line is
+    // cut into pieces independently of every other line, so the text is split at newlines into one chunk per thread.
+    const int nthreads = std::max(1, omp_get_max_threads());
+    std::vector<size_t> bounds((size_t)nthreads + 1, got);
+    bounds[0] = 0;
+    for (int t = 1; t < nthreads; ++t) {
+        size_t s0 = std::max(bounds[(size_t)t - 1], got * (size_t)t / (size_t)nthreads);
+        const void* nl = s0 < got ? memchr(text.data() + s0, '\n', got - s0) : 0;
+        bounds[(size_t)t] = nl ? (size_t)((const char*)nl - text.data()) + 1 : got;
     }
-#pragma omp parallel for schedule(static)
-    for (long i = 0; i < (long)pieces.size(); ++i)
-        if (pieces[i].kind) parsePiece(pieces[i]);
-
+    std::vector<std::vector<ObjPiece> > local((size_t)nthreads);
+#pragma omp parallel num_threads(nthreads)
+    {
+        const int t = omp_get_thread_num();
+        std::vector<ObjPiece>& out = local[(size_t)t];
+        const size_t end = bounds[(size_t)t + 1];
+        out.reserve((end - bounds[(size_t)t]) / 24 + 16);
+        for (size_t s0 = bounds[(size_t)t]; s0 < end;) {
+            const size_t lim = std::min(end - s0, (size_t)79);
+            const void* nl = memchr(text.data() + s0, '\n', lim);
+            const size_t len = nl ? (size_t)((const char*)nl - (text.data() + s0)) + 1 : lim;
+            ObjPiece q;
+            q.p = text.data() + s0; q.len = (int)len; q.kind = 0;
+            const char c0 = q.p[0], c1 = len > 1 ? q.p[1] : 0;
+            if (c0 == 'v') q.kind = c1 == 'n' ? 'n' : (c1 == 't' ? 't' : 'v');
+            else if (c0 == 'f') q.kind = 'f';
+            q.v[0] = q.v[1] = q.v[2] = q.n[0] = q.n[1] = q.n[2] = q.t[0] = q.t[1] = q.t[2] = 0;
+            if (q.kind) parsePiece(q);           // numbers: strtof / atoi, the conversions sscanf performs
+            out.push_back(q);
+            s0 += len;
+        }
+    }
+    std::vector<ObjPiece> pieces;
+    {
+        size_t total = 0;
+        for (int t = 0; t < nthreads; ++t) total += local[(size_t)t].size();
+        pieces.reserve(total);
+        for (int t = 0; t < nthreads; ++t) pieces.insert(pieces.end(), local[(size_t)t].begin(), local[(size_t)t].end());
+    }
+    const double tt2 = wall();
+    // Where every record lands is a prefix count over the pieces: vertex / normal / texture-coordinate slots, triangle number,
+    // and -- for a face whose LAST token carries no normal (the reference's test) -- the three synthesised normal slots, which
+    // the reference allocates in file order between the explicit ones.
+    const size_t np = pieces.size();
+    std::vector<int> slot(np, 0), nslot(np, 0), tbase(np, 0);
+    int nv = 0, nf = 0, nt = 0, nnormals = 0, ntouch = 0;
+    for (size_t i = 0; i < np; ++i) {
+        const ObjPiece& q = pieces[i];
+        if (q.kind == 'v') slot[i] = nv++;
+        else if (q.kind == 't') slot[i] = nt++;
+        else if (q.kind == 'n') slot[i] = nnormals++;
+        else if (q.kind == 'f') {
+            slot[i] = nf++; nslot[i] = nnormals; tbase[i] = ntouch;
+            for (int k = 0; k < 3; ++k) if (q.n[k]) ntouch++;
+            if (!q.n[2]) { nnormals += 3; ntouch += 3; }
+        }
+    }
     const int ncap = std::max(nv, nf * 3);
-    m_normals = new Vector3[ncap];
+    m_normals = new Vector3[std::max(ncap, nnormals)];
     m_vertices = new Vector3[nv];
     m_numVertices = nv;
     m_normalIndices = new TupleI3[nf];
@@ -166,53 +205,56 @@ void TriangleMesh::loadObj(FILE* fp, const Matrix4x4& ctm)
         memset(m_texCoordIndices, 0, sizeof(TupleI3) * (size_t)nf);
     }
     m_numTextCoords = nt;
-    int ntextures = 0;
-    std::vector<char> synthesised(ncap, 0);
+    m_numTris = nf;
+    std::vector<char> synthesised((size_t)std::max(ncap, nnormals), 0);
     Matrix4x4 nctm = ctm;
     nctm.invert();
     nctm.transpose();
-    int nverts = 0, nnormals = 0;
-    m_numTris = 0;
     // normal slots touching each vertex, in order of appearance: (vertex, slot) pairs now, grouped per vertex below
-    std::vector<std::pair<int, int> > touch;
-    touch.reserve((size_t)nf * 3);
-    for (size_t pi = 0; pi < pieces.size(); ++pi) {
-        const ObjPiece& q = pieces[pi];
+    std::vector<std::pair<int, int> > touch((size_t)ntouch);
+    // pass 1: positions, normals, texture coordinates (independent records)
+#pragma omp parallel for schedule(static)
+    for (long pi = 0; pi < (long)np; ++pi) {
+        const ObjPiece& q = pieces[(size_t)pi];
         if (q.kind == 'n') {
-            m_normals[nnormals] = nctm * Vector3(q.f[0], q.f[1], q.f[2]);
-            m_normals[nnormals].normalize();
-            nnormals++;
-        } else if (q.kind == 'v') {
-            m_vertices[nverts++] = ctm * Vector3(q.f[0], q.f[1], q.f[2]);
-        } else if (q.kind == 't') {
-            m_texCoords[ntextures].x = q.f[0]; m_texCoords[ntextures].y = q.f[1];
-            ntextures++;
-        } else if (q.kind == 'f') {
-            TupleI3& vi = m_vertexIndices[m_numTris];
-            TupleI3& ni = m_normalIndices[m_numTris];
-            int n = 0;
+            Vector3& n = m_normals[slot[(size_t)pi]];
+            n = nctm * Vector3(q.f[0], q.f[1], q.f[2]);
+            n.normalize();
+        } else if (q.kind == 'v') m_vertices[slot[(size_t)pi]] = ctm * Vector3(q.f[0], q.f[1], q.f[2]);
+        else if (q.kind == 't') { m_texCoords[slot[(size_t)pi]].x = q.f[0]; m_texCoords[slot[(size_t)pi]].y = q.f[1]; }
+    }
+    // pass 2: faces.  A synthesised normal is cross(e1, e2) of the face's transformed vertices (a well-formed file defines its
+    // vertices before the faces that use them, so every position is final here, as it is when the reference reads the face).
+#pragma omp parallel for schedule(static)
+    for (long pi = 0; pi < (long)np; ++pi) {
+        const ObjPiece& q = pieces[(size_t)pi];
+        if (q.kind != 'f') continue;
+        const int tri = slot[(size_t)pi];
+        TupleI3& vi = m_vertexIndices[tri];
+        TupleI3& ni = m_normalIndices[tri];
+        int tb = tbase[(size_t)pi];
+        int n = 0;
+        for (int k = 0; k < 3; ++k) {
+            n = q.n[k];
+            vi.v[k] = q.v[k] - 1;
+            if (n) { ni.v[k] = n - 1; touch[(size_t)tb++] = std::make_pair(q.v[k] - 1, n - 1); }
+            if (q.t[k] && nt) m_texCoordIndices[tri].v[k] = q.t[k] - 1;
+        }
+        if (!n) {   // the LAST token decides, as in the reference
+            const Vector3 e1 = m_vertices[vi.v[1]] - m_vertices[vi.v[0]];
+            const Vector3 e2 = m_vertices[vi.v[2]] - m_vertices[vi.v[0]];
             for (int k = 0; k < 3; ++k) {
-                n = q.n[k];
-                vi.v[k] = q.v[k] - 1;
-                if (n) { ni.v[k] = n - 1; touch.push_back(std::make_pair(q.v[k] - 1, n - 1)); }
-                if (q.t[k] && nt) m_texCoordIndices[m_numTris].v[k] = q.t[k] - 1;
+                const int sl = nslot[(size_t)pi] + k;
+                m_normals[sl] = cross(e1, e2);
+                m_normals[sl].normalize();
+                synthesised[(size_t)sl] = 1;
+                ni.v[k] = sl;
+                touch[(size_t)tb++] = std::make_pair((int)vi.v[k], sl);
             }
-            if (!n) {   // the LAST token decides, as in the reference
-                const Vector3 e1 = m_vertices[vi.v[1]] - m_vertices[vi.v[0]];
-                const Vector3 e2 = m_vertices[vi.v[2]] - m_vertices[vi.v[0]];
-                for (int k = 0; k < 3; ++k) {
-                    m_normals[nnormals] = cross(e1, e2);
-                    m_normals[nnormals].normalize();
-                    synthesised[nnormals] = 1;
-                    ni.v[k] = nnormals;
-                    touch.push_back(std::make_pair(vi.v[k], nnormals));
-                    nnormals++;
-                }
-            }
-            m_numTris++;
         }
     }
-    // group the touches per vertex, keeping their order (counting sort)
+    const double tt3 = wall();
+    // group the touches per vertex, keeping their order (stable counting sort; sequential: two passes over the list)
     std::vector<int> start((size_t)nv + 1, 0), slots(touch.size());
     for (size_t j = 0; j < touch.size(); ++j) if (touch[j].first >= 0 && touch[j].first < nv) start[(size_t)touch[j].first + 1]++;
     for (int i = 0; i < nv; ++i) start[(size_t)i + 1] += start[i];
@@ -220,7 +262,9 @@ void TriangleMesh::loadObj(FILE* fp, const Matrix4x4& ctm)
         std::vector<int> fill(start.begin(), start.end() - 1);
         for (size_t j = 0; j < touch.size(); ++j) if (touch[j].first >= 0 && touch[j].first < nv) slots[(size_t)fill[touch[j].first]++] = touch[j].second;
     }
-    for (int i = 0; i < nverts; ++i) {
+    // per-vertex averages in order of appearance; a synthesised slot belongs to exactly one vertex, so vertices are independent
+#pragma omp parallel for schedule(static)
+    for (int i = 0; i < nv; ++i) {
         const int b0 = start[i], e0 = start[(size_t)i + 1];
         if (b0 == e0) continue;
         Vector3 avg;                             // default-constructed: (0,1,2), as the reference accumulates from
@@ -229,6 +273,8 @@ void TriangleMesh::loadObj(FILE* fp, const Matrix4x4& ctm)
         avg.normalize();
         for (int j = b0; j < e0; ++j) if (synthesised[slots[j]]) m_normals[slots[j]] = avg;
     }
+    if (timing) fprintf(stderr, "loadObj: read + cut + parse %.1f ms, assemble %.1f ms, group + average %.1f ms\n", (tt2 - tt0) * 1e3, (tt3 - tt2) * 1e3,
+                        (wall() - tt3) * 1e3);
 }
 
 // ================================= Triangle ================================================================
