@@ -62,7 +62,8 @@ def test_layouts_and_call_splits_give_the_same_walks(pkg, scenes, drops):
 
 @pytest.mark.parametrize("which,name", [(0, "global"), (1, "caustic")])
 def test_scene_trace_photons_against_the_reference(pkg, scenes, drops, which, name):
-    H, S, O = drops
+    H, _, O = drops
+    S = H.scene()      # the handle of the CURRENT BVH (the test above rebuilt the global scene: the fixture's wrapper is stale)
     target = 200000                                                     # Scene.h:67-68
     H.set_photon_counts(target if which == 0 else 0, target if which == 1 else 0)
     emissions = H.trace_photons(which)

@@ -10,7 +10,9 @@ python -c "import __graft_entry__ as g; g.smoke()" > gpurun_out/${T}_smoke.log 2
 python bench.py > gpurun_out/${T}_bench_full.json 2> gpurun_out/${T}_bench_full.err; echo "bench rc=$?"; cut -c1-300 gpurun_out/${T}_bench_full.json
 python bench.py --impl reference > gpurun_out/${T}_bench_reference.json 2> gpurun_out/${T}_bench_reference.err; echo "bench reference rc=$?"; cut -c1-300 gpurun_out/${T}_bench_reference.json
 for v in 0 1; do python bench.py --variant $v --no-cpu --no-extras --steps 10 > gpurun_out/${T}_bench_v$v.json 2> gpurun_out/${T}_bench_v$v.err; echo "bench variant $v rc=$?"; done
-BENCH="python bench.py --steps 2 --warmup 3 --no-cpu --no-extras"
+# --sequential: whole-batch launches one after the other -- the launches roofline.achieved is measured on (bench.py replays the
+# timed steps that way for its per-kernel events); the default timed region issues the same work as half-batches on two streams
+BENCH="python bench.py --steps 2 --warmup 3 --no-cpu --no-extras --sequential"
 $BENCH > gpurun_out/${T}_plain.log 2>&1 &&
 ncu --metrics gpu__time_duration.sum --clock-control none -c 120 --csv --log-file gpurun_out/${T}_launches.csv $BENCH > gpurun_out/${T}_ncu_launches.log 2>&1
 echo "ncu launches rc=$?"

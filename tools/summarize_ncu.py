@@ -31,7 +31,7 @@ for r in rows[2:]:
     d = dict(zip(hdr, r)); u = dict(zip(hdr, units))
     launches.append({"kernel": d["Kernel Name"], **{k: {"value": d[k], "unit": u[k]} for k in KEEP if k in d}})
 cmd = open(src("ncu_full.log")).read()
-out = {"command": "ncu --set full --clock-control none --import-source on -k regex:k_trace -s 7 -c 2 python bench.py --steps 2 --warmup 3 --no-cpu",
+out = {"command": "ncu --set full --clock-control none --import-source on -k regex:k_trace -s 7 -c 2 python bench.py --steps 2 --warmup 3 --no-cpu --no-extras --sequential",
        "launches": launches}
 json.dump(out, open(os.path.join(P, f"{tag}_ncu_full.json"), "w"), indent=1)
 def num(x): return float(x["value"].replace(",", ""))
@@ -39,7 +39,7 @@ def to_bytes(m):
     v = num(m); u = m["unit"].lower()
     return v * {"byte": 1, "kbyte": 1e3, "mbyte": 1e6, "gbyte": 1e9}[u]
 b = max(launches, key=lambda l: num(l["gpu__time_duration.sum"]))   # of a step's two trace launches the bounce-ray one is the longer
-summary = {"source": f"profiles/{tag}_ncu_full.json (ncu --set full --clock-control none, bench.py --steps 2 --warmup 3 --no-cpu; the bounce-ray launch of a timed step)",
+summary = {"source": f"profiles/{tag}_ncu_full.json (ncu --set full --clock-control none, bench.py --steps 2 --warmup 3 --no-cpu --no-extras --sequential; the whole-batch bounce-ray launch of a step)",
            "kernel": b["kernel"].split("(")[0],
            "bounce_trace_dram_bytes_per_launch": int(to_bytes(b["dram__bytes_read.sum"]) + to_bytes(b["dram__bytes_write.sum"])),
            "dram_read_bytes": int(to_bytes(b["dram__bytes_read.sum"])), "dram_write_bytes": int(to_bytes(b["dram__bytes_write.sum"])),
