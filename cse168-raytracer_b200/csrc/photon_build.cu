@@ -478,12 +478,15 @@ cudaError_t photon_balance_device(const float4* d_pos, int n, const uint32_t* d_
                                                            small_list, small_count);
     int height = 0;
     while (((1ll << height) - 1) < n) ++height;                 // levels of the left-balanced tree
-    for (int level = 0; level < height && ((1ll << (height - level)) - 1) > PB_SMALL; ++level)
+    // a segment of level L holds at most 2^(height - L) - 1 photons: levels are processed by k_pb_level while that exceeds PB_SMALL
+    int levels_run = 0;
+    for (int level = 0; level < height && ((1ll << (height - level)) - 1) > PB_SMALL; ++level, ++levels_run)
         k_pb_level<<<1u << level, 1024, 0, st>>>(level, n, d_pos, static_cast<uint32_t*>(ids.p), static_cast<float*>(keys.p),
                                                  static_cast<uint32_t*>(pg.p), static_cast<uint32_t*>(ps.p), static_cast<PbSeg*>(segs.p), d_heap,
                                                  small_list, small_count);
-    // at most one open small segment per PB_SMALL / 2 photons... bounded by n / 2 + 1 tasks; the kernel reads the real count
-    const unsigned max_tasks = (unsigned)std::min<size_t>((size_t)n, (size_t)2 * ((size_t)n / (PB_SMALL / 4) + 2));
+    // small segments are opened by the (fewer than 2^levels_run) nodes of the levels above, two each at most, or are the root itself;
+    // the kernel reads the real count
+    const unsigned max_tasks = (unsigned)std::min<size_t>((size_t)n, (size_t)2 << levels_run);
     k_pb_small<<<(max_tasks + PB_WARPS - 1) / PB_WARPS, 32 * PB_WARPS, 0, st>>>(d_pos, static_cast<uint32_t*>(ids.p), static_cast<PbSeg*>(segs.p), d_heap,
                                                                                small_list, small_count);
     e = cudaGetLastError();
