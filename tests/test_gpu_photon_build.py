@@ -85,3 +85,23 @@ def test_device_pass_equals_store_scale_balance_of_its_own_records(drops, which,
     assert np.array_equal(S.photon_gather(which, q, qn, 1e10, k).view(np.uint32), O.pm_irradiance(which, q, qn, 1e10, k).view(np.uint32))
     S.photon_set_exact(which, False)
     O.lib.orc_pm_reset(which, 1)
+
+
+def test_device_built_maps_are_replicated_over_a_device_list(pkg, scenes):
+    """mirogpu_photon_pass builds the map on the first device of a multi-device handle and clones it to the others with peer
+    copies: a photon-mapped frame rendered over two devices equals the one-device frame."""
+    if pkg.device_count() < 2:
+        pytest.skip("needs at least two GPUs")
+    frames = []
+    for ndev in (1, 2):
+        H = pkg.HostScene(pkg.LAYOUT_QBVH4)
+        scenes.realise(H, "cornell_drops", objio.obj_path)
+        H.set_device_count(ndev)
+        H.set_photon_counts(20000, 5000)
+        H.precalc()
+        S = H.scene()
+        assert S.devices() == list(range(ndev))
+        p = S.render_params(96, 96, mode=pkg.RENDER_WHITTED, shadows=1, use_photon_maps=1, seed=5)
+        frames.append(S.render(H.camera(), p))
+    assert frames[0].std() > 0
+    assert np.allclose(frames[0], frames[1], rtol=2e-5, atol=1e-7)
