@@ -579,7 +579,7 @@ def run_extras():
     sponza's published 54.8) with its own V, T and roofline fraction."""
     out = {}
     env = dict(os.environ, MIRO_REF_ALL="1")
-    for key, script, tmo in (("configs", "bench_configs.py", 240), ("photon_gather", "bench_gather.py", 120), ("bvh_build", "bench_build.py", 120),
+    for key, script, tmo in (("configs", "bench_configs.py", 420), ("photon_gather", "bench_gather.py", 120), ("bvh_build", "bench_build.py", 120),
                              ("host_batch_api", "bench_host_batch.py", 120), ("photon_pass", "bench_photon_pass.py", 120),
                              ("deep_traversal", "bench_deep.py", 180)):
         path = os.path.join(ROOT, "tools", script)

@@ -256,6 +256,11 @@ SCENES = {
 }
 
 
+# BASELINE config 4 as assignment3.cpp builds it: the flower scene's geometry and light with the script's own TexturedPhong
+# materials (assignment3.cpp:93-105) instead of the flat colours of "flower" (which the oracle, textureless, can render too)
+SCENES["flower_a3"] = dict(SCENES["flower"], materials=SCENES["flower_textured"]["materials"])
+
+
 def realise(builder, name, obj_path_of):
     """Drives `builder` (an object with new_scene/new_material/add_obj/add_triangle/add_point_light/
     add_directional_light/set_camera/precalc) through scene `name`.  obj_path_of(model) -> .obj path."""
