@@ -8,10 +8,12 @@ reference's makeBunny20Scene geometry, 1 389 021 triangles, with its own camera)
 
 A step is one pass of the hot path over one batch of synthetic rays: SPP jittered samples of the frame --
 device-side Camera::eyeRay -> closest-hit -> device-side Ray::diffuse at every hit -> closest-hit.
-`value` = (primary + live bounce rays of all ranks) / max-over-ranks device time, inputs resident in HBM.
+`value` = (primary + live bounce rays of all ranks) / max-over-ranks device time, inputs resident in HBM; the timed region issues
+          every step as two half-batches (8 samples each) on two streams, and the same steps are replayed one launch after the
+          other right afterwards for the per-kernel durations and the roofline (--sequential times that schedule instead).
 `e2e`   = the same metric through the reference-facing call with HOST buffers: Scene::raytraceImage ->
           mirogpu_render (diffuse-bounce mode, no shadow rays so the ray work equals a step's), framebuffer
-          gathered over NCCL/NVLink for N > 1 and copied to pinned host memory, every step.
+          gathered over NCCL/NVLink for N > 1 (two frames in flight) and copied to pinned host memory, every step.
 Image rows are interleaved across ranks (row % N == rank); the BVH is replicated; fixed frame => strong scaling.
 """
 import argparse
