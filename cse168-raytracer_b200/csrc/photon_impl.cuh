@@ -173,8 +173,12 @@ __global__ void __launch_bounds__(128) k_photon_gather(const float4* __restrict_
 // shrinks to that distance.  Per visited node this costs ~2 warp instructions instead of a divergent per-thread stack
 // machine with a 4 KB heap in local memory.  The result holds the k nearest photons that pass the direction filter --
 // what the reference's heap ends with -- summed in another order: estimates agree to ~1e-6 relative (1e-4).
+#ifndef MIRO_GW_STACK
 #define MIRO_GW_STACK 1024      /* pending nodes per warp (32 x tree depth is the pseudo-DFS worst case; see the throttle below) */
+#endif
+#ifndef MIRO_GW_CAND
 #define MIRO_GW_CAND 768        /* candidate buffer per warp; must be >= k + 128 */
+#endif
 #define MIRO_GW_WARPS 4
 
 struct GatherWarpShared {
