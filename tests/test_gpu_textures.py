@@ -22,22 +22,56 @@ pytestmark = pytest.mark.gpu
 torch = pytest.importorskip("torch")
 
 
-def _build(pkg, scenes, name):
+# The reference answers from a FRESH process: test_dropin_scripts loads the host layer's classes with RTLD_GLOBAL, after which the
+# reference library's own Scene / TriangleMesh symbols would bind to them in this process; a fresh process also gives
+# Camera::eyeRay's function statics (Camera.cpp:106-125) the right camera for the 8-bit frame.
+_REF_JOB = r"""
+import ctypes, importlib, os, sys
+import numpy as np
+here, root, name, rays_path, out, w, h = sys.argv[1], sys.argv[2], sys.argv[3], sys.argv[4], sys.argv[5], int(sys.argv[6]), int(sys.argv[7])
+sys.path.insert(0, here); sys.path.insert(0, root)
+import miro_driver as md, objio
+spec = importlib.util.spec_from_file_location("scenes", os.path.join(root, "cse168-raytracer_b200", "scenes.py"))
+scenes = importlib.util.module_from_spec(spec); spec.loader.exec_module(scenes)
+R = md.reference("scalar")
+scenes.realise(R, name, objio.obj_path)
+R.precalc()
+rays = np.load(rays_path)
+t, ids, P, N = R.trace(rays, 0)
+rgb = R.trace_scene(rays, depth=10)
+img = np.zeros((h, w, 3), np.uint8)
+R.lib.ref_render(w, h, img.ctypes.data_as(ctypes.c_void_p))
+np.savez(out, t=t, ids=ids, P=P, N=N, rgb=rgb, img=img)
+"""
+
+
+def _reference_answers(name, rays, w, h):
+    import subprocess, sys, tempfile
     if not os.path.exists(md.REF_SO):
         pytest.skip("oracle/_ref not built")
-    R = md.reference("scalar")
+    here = os.path.dirname(os.path.abspath(__file__))
+    with tempfile.TemporaryDirectory() as tmp:
+        rp, out = os.path.join(tmp, "rays.npy"), os.path.join(tmp, "ref.npz")
+        np.save(rp, np.ascontiguousarray(rays, np.float32))
+        subprocess.run([sys.executable, "-c", _REF_JOB, here, os.path.dirname(here), name, rp, out, str(w), str(h)], check=True,
+                       stdout=subprocess.DEVNULL)
+        z = np.load(out)
+        return {k: z[k] for k in z.files}
+
+
+def _build(pkg, scenes, name):
     H = pkg.HostScene(pkg.LAYOUT_QBVH4)
-    for d in (R, H):
-        scenes.realise(d, name, objio.obj_path)
-        d.precalc()
-    return H, H.scene(), R
+    scenes.realise(H, name, objio.obj_path)
+    H.precalc()
+    return H, H.scene()
 
 
 def test_hit_normals_follow_the_reference_rules(pkg, scenes):
-    H, S, R = _build(pkg, scenes, "textured")
+    H, S = _build(pkg, scenes, "textured")
     w = h = 160
-    rays = H.eye_rays(w, h)      # Camera::eyeRay of the host layer (bit-identical to the reference's, whose statics keep the first camera of a process)
-    t, ids, P, N = R.trace(rays, 0)
+    rays = H.eye_rays(w, h)      # Camera::eyeRay of the host layer (bit-identical to the reference's)
+    ref = _reference_answers("textured", rays, w, h)
+    ids, P, N = ref["ids"], ref["P"], ref["N"]
     dev = torch.device("cuda", 0)
     d_rays = torch.from_numpy(rays).to(dev); d_hits = torch.empty((rays.shape[0], 4), dtype=torch.float32, device=dev)
     S.intersect_device(d_rays, d_hits)
@@ -49,7 +83,7 @@ def test_hit_normals_follow_the_reference_rules(pkg, scenes):
     assert np.allclose(gP[hit], P[hit], rtol=1e-5, atol=1e-5)
     close = np.isclose(gN[hit], N[hit], rtol=1e-4, atol=1e-4).all(axis=1)
     assert close.mean() > 0.998, close.mean()
-    # the rules are really exercised: bump-mapped floor normals are not (0, 1, 0), 3-D textured triangles' normals are not unit length
+    # the rules are really exercised: bump-mapped floor normals are not (0, 1, 0)
     floor = hit & (np.abs(P[:, 1]) < 1e-4)
     assert floor.sum() > 1000 and (np.abs(N[floor][:, 1] - 1.0) > 1e-3).mean() > 0.5
     # and the host layer's Scene::trace agrees (bump mapping through the Texture classes' own bumpHeight2D)
@@ -60,12 +94,13 @@ def test_hit_normals_follow_the_reference_rules(pkg, scenes):
 
 @pytest.mark.parametrize("name,size,frac", [("textured", (224, 224), 0.99), ("flower_textured", (384, 256), 0.985)])
 def test_textured_frames_against_the_reference(pkg, scenes, name, size, frac):
-    H, S, R = _build(pkg, scenes, name)
+    H, S = _build(pkg, scenes, name)
     w, h = size
     sc = scenes.SCENES[name]
     p = S.render_params(w, h, mode=pkg.RENDER_WHITTED, tonemap=0, bg=sc.get("bg", (0, 0, 0)), shadows=1)
     img = S.render(H.camera(), p)
-    ref = R.trace_scene(H.eye_rays(w, h), depth=10).reshape(h, w, 3)
+    answers = _reference_answers(name, H.eye_rays(w, h), w, h)
+    ref = answers["rgb"].reshape(h, w, 3)
     assert np.isfinite(img).all()
     # PetalTexture sums 25 octaves of noise up to a frequency of 1e12 on coordinates that come out of acosf: a last-ulp difference
     # between CUDA's and glibc's acosf re-rolls the top ten octaves (17 % of the amplitude), so ~5 % of petal pixels move by 1-3 %
@@ -73,14 +108,10 @@ def test_textured_frames_against_the_reference(pkg, scenes, name, size, frac):
     assert close.mean() > frac, close.mean()
     assert (np.abs(img - ref) <= 0.03 * np.abs(ref) + 2e-3).all(axis=2).mean() > 0.998
     assert img.std() > 0.02                                   # a textured image, not a flat one
-    if name == "textured":
-        # 8-bit frame through Scene::raytraceImage of the host layer against the reference's own image (the reference's camera
-        # statics belong to the first camera of the process: only valid for the scene this module builds first)
-        a = H.render(w, h)
-        b = np.zeros((h, w, 3), np.uint8)
-        R.lib.ref_render(int(w), int(h), b.ctypes.data_as(__import__("ctypes").c_void_p))
-        within = (np.abs(a.astype(np.int32) - b.astype(np.int32)) <= 2).all(axis=2)
-        assert within.mean() > frac, within.mean()
+    # 8-bit frame through Scene::raytraceImage of the host layer against the reference's own image
+    a = H.render(w, h)
+    within = (np.abs(a.astype(np.int32) - answers["img"].astype(np.int32)) <= 2).all(axis=2)
+    assert within.mean() > frac, within.mean()
 
 
 def test_photon_pass_looks_up_textured_diffuse_colours(pkg, scenes):
