@@ -580,7 +580,9 @@ def run_extras():
     photon pass on the device, and the same step as the timed one on a deep-traversal scene (56 node entries per camera ray, like
     sponza's published 54.8) with its own V, T and roofline fraction."""
     out = {}
-    env = dict(os.environ, MIRO_REF_ALL="1")
+    # the reference renders configs 1, 2 and 5 next to the GPU inside this run; config 4's reference frame needs 140 s of its own
+    # preCalc (both photon passes) + 13.5 s, so it is only run with MIRO_REF_ALL=1 (recorded: profiles/r02p_configs.json)
+    env = dict(os.environ, MIRO_REF_CONFIG5="1")
     for key, script, tmo in (("configs", "bench_configs.py", 420), ("photon_gather", "bench_gather.py", 120), ("bvh_build", "bench_build.py", 120),
                              ("host_batch_api", "bench_host_batch.py", 120), ("photon_pass", "bench_photon_pass.py", 120),
                              ("deep_traversal", "bench_deep.py", 180)):
