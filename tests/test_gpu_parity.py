@@ -351,3 +351,38 @@ def test_headline_config_vs_reference_traversal(host_scenes, oracle_scene, pkg):
         assert rel.max() <= 1e-5
         assert np.array_equal(bits(hits["t"][~mism]), bits(t_ref[~mism]))   # in fact bit-identical
     assert total >= 2_000_000
+
+
+def test_half_batches_equal_the_whole_batch(host_scenes, pkg):
+    """bench.py issues a step as two half-batches on two streams: the halves must be the whole batch -- same eye rays (sample
+    offsets), same bounce rays (random-number index offsets), same hits -- so the timed schedule and its sequential replay do
+    identical work."""
+    H, S = host_scenes("bunny_teapot", 3)
+    cam = H.camera()
+    w, h, spp = 320, 180, 4
+    npix = w * h
+    n = npix * spp
+    dev = "cuda"
+    def bufs():
+        return [torch.empty((n, 8), dtype=torch.float32, device=dev), torch.empty((n, 4), dtype=torch.float32, device=dev),
+                torch.empty((n, 8), dtype=torch.float32, device=dev), torch.empty((n, 4), dtype=torch.float32, device=dev)]
+    r0, h0, b0, g0 = bufs()
+    S.generate_primary(cam, w, h, r0, jitter=1, seed=168, sample=3 * spp, samples=spp)
+    S.intersect_device(r0, h0, mode=pkg.CLOSEST_HIT | pkg.HINT_COHERENT)
+    S.generate_bounce(r0, h0, b0, seed=168, sample=3, index_base=0x01000000)
+    S.intersect_device(b0, g0)
+    r1, h1, b1, g1 = bufs()
+    side = torch.cuda.Stream()
+    half = spp // 2
+    nh = npix * half
+    torch.cuda.synchronize()
+    for k, stream in ((0, torch.cuda.current_stream()), (1, side)):
+        lo, hi = k * nh, (k + 1) * nh
+        with torch.cuda.stream(stream):
+            S.generate_primary(cam, w, h, r1[lo:hi], jitter=1, seed=168, sample=3 * spp + k * half, samples=half)
+            S.intersect_device(r1[lo:hi], h1[lo:hi], mode=pkg.CLOSEST_HIT | pkg.HINT_COHERENT)
+            S.generate_bounce(r1[lo:hi], h1[lo:hi], b1[lo:hi], seed=168, sample=3, index_base=0x01000000 + lo)
+            S.intersect_device(b1[lo:hi], g1[lo:hi])
+    torch.cuda.synchronize()
+    for a, b in ((r0, r1), (h0, h1), (b0, b1), (g0, g1)):
+        assert torch.equal(a.view(torch.int32), b.view(torch.int32))
