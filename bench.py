@@ -149,9 +149,9 @@ class ClockSampler:
         return out
 
 
-def build_host_scene(pkg, scenes, layout):
+def build_host_scene(pkg, scenes, layout, builder=None):
     import objio
-    H = pkg.HostScene(layout)
+    H = pkg.HostScene(layout) if builder is None else pkg.HostScene(layout, builder=builder)
     scenes.realise(H, SCENE, objio.obj_path)
     H.precalc()
     return H
@@ -324,7 +324,8 @@ def run_ours(args):
     pkg = importlib.import_module("cse168-raytracer_b200")
     scenes = importlib.import_module("cse168-raytracer_b200.scenes")
     layout = {"bvh2": pkg.LAYOUT_BVH2, "cwbvh8": pkg.LAYOUT_CWBVH8, "bvh4": pkg.LAYOUT_BVH4, "qbvh4": pkg.LAYOUT_QBVH4}[args.layout]
-    H = build_host_scene(pkg, scenes, layout)       # BVH replicated on every GPU
+    builder = {"sah": None, "lbvh": pkg.BUILDER_LBVH_DEVICE, "ploc": pkg.BUILDER_PLOC_DEVICE}[args.builder]
+    H = build_host_scene(pkg, scenes, layout, builder)       # BVH replicated on every GPU
     S = H.scene()
     S.set_kernel_variant(args.variant)
     cam = H.camera()
@@ -536,7 +537,7 @@ def run_ours(args):
             "config": shared_config(),
             "detail": {
                 "rays_per_step": rays_total / args.steps, "primary_rays_per_step": prim_total / args.steps, "bounce_rays_per_step": live_total / args.steps,
-                "layout": args.layout, "kernel_variant": args.variant, "nodes": info.num_nodes, "node_mb": info.node_bytes / 1e6,
+                "layout": args.layout, "builder": args.builder, "kernel_variant": args.variant, "nodes": info.num_nodes, "node_mb": info.node_bytes / 1e6,
                 "triangle_mb": info.triangle_bytes / 1e6, "build_s": info.build_seconds + info.flatten_seconds,
                 "sharding": f"image rows interleaved over {world} rank(s), BVH replicated",
                 "schedule": ("one launch after the other on one stream (--sequential)" if args.sequential else
@@ -606,6 +607,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--layout", default=os.environ.get("MIROGPU_LAYOUT", "qbvh4"), choices=["bvh2", "cwbvh8", "bvh4", "qbvh4"])
     ap.add_argument("--variant", type=int, default=int(os.environ.get("MIROGPU_VARIANT", "-1")))
+    ap.add_argument("--builder", default="sah", choices=["sah", "lbvh", "ploc"], help="BVH::build: host binned SAH (default) or a device builder")
     ap.add_argument("--sequential", action="store_true", help="time the step as four whole-batch launches on one stream (round-1 schedule)")
     ap.add_argument("--emulate-shard", type=int, default=0, help="development: trace rank 0's rows of an N-rank run on one GPU")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline / parity legs (faster iteration)")

@@ -415,7 +415,10 @@ inline cudaError_t build_lbvh_device(const float* tri_vertices, uint32_t ntris, 
     cudaError_t e = cudaSuccess;
     // all temporaries come out of ONE allocation (cudaMalloc / cudaFree of two dozen 20-90 MB buffers cost more than the build)
     const size_t per_tri = 36 + 32 + 16 + 8 + 8 + 16 + 8 + 64 + 4 + 64 + 16 + 16 /* sort scratch */ + (ploc ? 8 + 64 + 12 + 8 : 0);
-    const size_t pool_bytes = (size_t)n * per_tri + ((size_t)n / 2 + 2) * (sizeof(Bvh4Node) + 2 * 16) + (8u << 20);
+    // wide nodes: a node has at least two children, so with leaves of up to max_leaf >= 2 triangles the bottom nodes cover three
+    // triangles or more (n / 2 + 2 nodes is safe); with single-triangle leaves a bottom node may cover just two (up to ~2n / 3)
+    const size_t wide_capacity = max_leaf == 1 ? (size_t)n + 2 : (size_t)n / 2 + 2;
+    const size_t pool_bytes = (size_t)n * per_tri + wide_capacity * (sizeof(Bvh4Node) + 2 * 16) + (8u << 20);
     BuildScratch& scratch = build_scratch();
     std::lock_guard<std::mutex> scratch_lock(scratch.mtx);   // one device build at a time per process
     char* pool = nullptr;
@@ -454,8 +457,8 @@ inline cudaError_t build_lbvh_device(const float* tri_vertices, uint32_t ntris, 
     const uint32_t init[6] = {0xffffffffu, 0xffffffffu, 0xffffffffu, 0u, 0u, 0u};
     LB(cudaMemcpyAsync(scene, init, sizeof init, cudaMemcpyHostToDevice, st));
     const unsigned g256 = (n + 255) / 256;
-    // the final geometry allocation: worst case one wide node per two triangles + 1
-    const uint32_t capacity = n / 2 + 2;
+    // the final geometry allocation is sized for that worst case
+    const uint32_t capacity = (uint32_t)wide_capacity;
     o.node_span = (((size_t)capacity * sizeof(Qbvh4Node)) + 255) & ~(size_t)255;
     o.tri_bytes = (size_t)n * sizeof(TriRecord);
     LB(cudaMalloc(&o.d_geom, o.node_span + std::max<size_t>(o.tri_bytes, 16)));

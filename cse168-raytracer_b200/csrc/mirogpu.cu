@@ -482,6 +482,11 @@ int scene_create_impl(const mirogpu_scene_desc& d, const mirogpu_build_options* 
     if (o.layout != MIROGPU_LAYOUT_BVH2 && o.layout != MIROGPU_LAYOUT_CWBVH8 && o.layout != MIROGPU_LAYOUT_BVH4 && o.layout != MIROGPU_LAYOUT_QBVH4)
         return fail(MIROGPU_ERR_INVALID_ARG, "unknown layout");
     if (o.max_leaf <= 0) if (const char* e = getenv("MIROGPU_MAX_LEAF")) o.max_leaf = atoi(e);   // tuning knob
+    // The device builders make every subtree of <= max_leaf triangles a leaf.  Unless the caller asks otherwise they build
+    // single-triangle leaves: the agglomerated tree has no leaf cost model, and four-triangle leaves cost the hybrid kernel (one
+    // triangle per lane and leaf phase) 13 % of its camera-ray rate on the bench scene -- 5.75 / 6.34 / 6.34 / 6.57 Grays/s for
+    // 4 / 3 / 2 / 1 triangles per leaf, against 6.9 for the host SAH tree, whose builder decides leaf sizes by cost.
+    const int device_max_leaf = o.max_leaf > 0 ? std::min(o.max_leaf, 4) : 1;
     if (o.max_leaf <= 0) o.max_leaf = (o.layout == MIROGPU_LAYOUT_CWBVH8) ? 3 : 4;
     if (o.layout == MIROGPU_LAYOUT_CWBVH8 && o.max_leaf > 3) o.max_leaf = 3;
     if (o.layout != MIROGPU_LAYOUT_CWBVH8 && o.max_leaf > 8) o.max_leaf = 8;
@@ -532,7 +537,7 @@ int scene_create_impl(const mirogpu_scene_desc& d, const mirogpu_build_options* 
     LbvhOut lb;
     bool device_built = false;
     if (device_builder) {
-        const cudaError_t be = build_lbvh_device(verts, ntris, std::min(o.max_leaf, 4), lb, o.builder == MIROGPU_BUILDER_PLOC_DEVICE);
+        const cudaError_t be = build_lbvh_device(verts, ntris, device_max_leaf, lb, o.builder == MIROGPU_BUILDER_PLOC_DEVICE);
         if (be == cudaErrorNotSupported) lb.d_geom = nullptr;   // the device builder gave up on this input (see lbvh_impl.cuh): use the host builder
         else if (be != cudaSuccess) return fail(be == cudaErrorMemoryAllocation ? MIROGPU_ERR_OOM : MIROGPU_ERR_CUDA, std::string("device BVH build: ") + cudaGetErrorString(be));
         else if (lb.max_stack <= MIRO_STACK4) device_built = true;

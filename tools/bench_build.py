@@ -24,7 +24,7 @@ for name, b in (("sah_host", pkg.BUILDER_SAH_HOST), ("lbvh_device", pkg.BUILDER_
     res = {"build_s": [], "wall_s": []}
     for rep in range(3):
         t0 = time.perf_counter()
-        S = pkg.MiroScene(V, layout=pkg.LAYOUT_QBVH4, builder=b)
+        S = pkg.MiroScene(V, layout=pkg.LAYOUT_QBVH4, builder=b, max_leaf=int(os.environ.get("MIRO_BUILD_MAX_LEAF", "0")))
         res["wall_s"].append(time.perf_counter() - t0)            # mirogpu_scene_create: build + flatten / collapse + uploads
         res["build_s"].append(S.info.build_seconds)
     res["nodes"] = int(S.info.num_nodes)
