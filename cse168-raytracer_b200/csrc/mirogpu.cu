@@ -70,6 +70,7 @@ struct BatchSlot {
     cudaStream_t st = nullptr;
     mirogpu_ray* d_r = nullptr; mirogpu_hit* d_h = nullptr; size_t cap = 0;
     mirogpu_ray* h_r = nullptr; mirogpu_hit* h_h = nullptr;   // page-locked, MIRO_SMALL_BATCH entries, device-visible (UVA)
+    mirogpu_ray* pin_r = nullptr; mirogpu_hit* pin_h = nullptr; size_t pin_cap = 0;   // page-locked staging of one chunk, for callers with pageable buffers
     unsigned long long* d_c = nullptr;                          // 4 counters of the instrumented kernel
     bool busy = false;
     cudaError_t init()
@@ -89,8 +90,22 @@ struct BatchSlot {
         if (e == cudaSuccess) cap = n;
         return e;
     }
+    cudaError_t ensure_pinned(size_t n)
+    {
+        if (n <= pin_cap) return cudaSuccess;
+        if (pin_r) cudaFreeHost(pin_r);
+        if (pin_h) cudaFreeHost(pin_h);
+        pin_r = nullptr; pin_h = nullptr; pin_cap = 0;
+        cudaError_t e = cudaHostAlloc(&pin_r, n * sizeof(mirogpu_ray), cudaHostAllocDefault);
+        if (e == cudaSuccess) e = cudaHostAlloc(&pin_h, n * sizeof(mirogpu_hit), cudaHostAllocDefault);
+        if (e == cudaSuccess) pin_cap = n;
+        return e;
+    }
     void release()
     {
+        if (pin_r) cudaFreeHost(pin_r);
+        if (pin_h) cudaFreeHost(pin_h);
+        pin_r = nullptr; pin_h = nullptr; pin_cap = 0;
         cudaFree(d_r); cudaFree(d_h); cudaFree(d_c);
         if (h_r) cudaFreeHost(h_r);
         if (h_h) cudaFreeHost(h_h);
@@ -838,27 +853,62 @@ int mirogpu_intersect_batch(mirogpu_handle h, const mirogpu_ray* rays, size_t n,
         memcpy(hits, g0.s->h_h, n * sizeof(mirogpu_hit));
         launches = 1;
     } else {
-        const size_t chunk = std::min<size_t>(n, (size_t)4 << 20);
+        // Pageable caller buffers (the usual case for a C++ caller's std::vector): cudaMemcpyAsync would stage them through the
+        // driver's own bounce buffer on this thread (measured: 0.23 Grays/s against 1.2 from page-locked memory).  Instead the
+        // chunks go through page-locked staging of the slots, filled and drained by all host threads, two chunks in flight.
+        cudaPointerAttributes pa_r, pa_h;
+        const bool pageable = (cudaPointerGetAttributes(&pa_r, rays) != cudaSuccess || pa_r.type == cudaMemoryTypeUnregistered) ||
+                              (cudaPointerGetAttributes(&pa_h, hits) != cudaSuccess || pa_h.type == cudaMemoryTypeUnregistered);
+        (void)cudaGetLastError();
+        const size_t chunk = std::min<size_t>(n, pageable ? (size_t)1 << 20 : (size_t)4 << 20);
         const int nbuf = n > chunk ? 2 : 1;
         SlotGuard g1{h, nbuf == 2 ? slot_acquire(h, e) : nullptr};
         if (nbuf == 2 && !g1.s) return fail(cuda_code(e), std::string("intersect_batch staging: ") + cudaGetErrorString(e));
         BatchSlot* sl[2] = {g0.s, g1.s};
-        for (int b = 0; b < nbuf; ++b)
-            if ((e = sl[b]->ensure(chunk)) != cudaSuccess) { (void)cudaGetLastError(); return fail(cuda_code(e), std::string("intersect_batch staging: ") + cudaGetErrorString(e)); }
+        for (int b = 0; b < nbuf; ++b) {
+            e = sl[b]->ensure(chunk);
+            if (e == cudaSuccess && pageable) e = sl[b]->ensure_pinned(chunk);
+            if (e != cudaSuccess) { (void)cudaGetLastError(); return fail(cuda_code(e), std::string("intersect_batch staging: ") + cudaGetErrorString(e)); }
+        }
+        auto par_copy = [](void* dst, const void* src, size_t bytes) {
+            const size_t piece = (size_t)1 << 20;
+            const long pieces = (long)((bytes + piece - 1) / piece);
+#pragma omp parallel for schedule(static)
+            for (long p = 0; p < pieces; ++p) {
+                const size_t o = (size_t)p * piece;
+                memcpy(static_cast<char*>(dst) + o, static_cast<const char*>(src) + o, std::min(piece, bytes - o));
+            }
+        };
         int rc = MIROGPU_OK;
         size_t k = 0;
+        size_t pend_off[2] = {0, 0}, pend_m[2] = {0, 0};   // chunk whose hits still sit in the slot's staging buffer
         for (size_t off = 0; off < n && rc == MIROGPU_OK; off += chunk, ++k) {
             BatchSlot* s = sl[k % nbuf];
             const size_t m = std::min(chunk, n - off);
-            e = cudaMemcpyAsync(s->d_r, rays + off, m * sizeof(mirogpu_ray), cudaMemcpyHostToDevice, s->st);
-            if (e == cudaSuccess) e = dispatch_trace(h, s->d_r, m, s->d_h, mode, s->st);
-            if (e == cudaSuccess) e = cudaMemcpyAsync(hits + off, s->d_h, m * sizeof(mirogpu_hit), cudaMemcpyDeviceToHost, s->st);
+            if (pageable) {
+                if (pend_m[k % nbuf]) {   // the slot's previous chunk: wait for it, hand its hits to the caller
+                    e = cudaStreamSynchronize(s->st);
+                    if (e != cudaSuccess) { rc = fail(MIROGPU_ERR_CUDA, std::string("intersect_batch: ") + cudaGetErrorString(e)); break; }
+                    par_copy(hits + pend_off[k % nbuf], s->pin_h, pend_m[k % nbuf] * sizeof(mirogpu_hit));
+                    pend_m[k % nbuf] = 0;
+                }
+                par_copy(s->pin_r, rays + off, m * sizeof(mirogpu_ray));
+                e = cudaMemcpyAsync(s->d_r, s->pin_r, m * sizeof(mirogpu_ray), cudaMemcpyHostToDevice, s->st);
+                if (e == cudaSuccess) e = dispatch_trace(h, s->d_r, m, s->d_h, mode, s->st);
+                if (e == cudaSuccess) e = cudaMemcpyAsync(s->pin_h, s->d_h, m * sizeof(mirogpu_hit), cudaMemcpyDeviceToHost, s->st);
+                pend_off[k % nbuf] = off; pend_m[k % nbuf] = m;
+            } else {
+                e = cudaMemcpyAsync(s->d_r, rays + off, m * sizeof(mirogpu_ray), cudaMemcpyHostToDevice, s->st);
+                if (e == cudaSuccess) e = dispatch_trace(h, s->d_r, m, s->d_h, mode, s->st);
+                if (e == cudaSuccess) e = cudaMemcpyAsync(hits + off, s->d_h, m * sizeof(mirogpu_hit), cudaMemcpyDeviceToHost, s->st);
+            }
             if (e != cudaSuccess) rc = fail(MIROGPU_ERR_CUDA, std::string("intersect_batch: ") + cudaGetErrorString(e));
             launches++;
         }
         for (int b = 0; b < nbuf; ++b) {
             e = cudaStreamSynchronize(sl[b]->st);
             if (e != cudaSuccess && rc == MIROGPU_OK) rc = fail(MIROGPU_ERR_CUDA, std::string("intersect_batch sync: ") + cudaGetErrorString(e));
+            if (rc == MIROGPU_OK && pageable && pend_m[b]) par_copy(hits + pend_off[b], sl[b]->pin_h, pend_m[b] * sizeof(mirogpu_hit));
         }
         if (rc != MIROGPU_OK) return rc;
     }
