@@ -1348,6 +1348,23 @@ int mirogpu_photon_gather(mirogpu_handle h, int which, const float* pos3, const 
     if (k < 1 || k > MIRO_PHOTON_KMAX) return fail(MIROGPU_ERR_INVALID_ARG, "k out of range (1..512)");
     if (n == 0) return MIROGPU_OK;
     CUDA_TRY(cudaSetDevice(h->device));
+    if (n <= MIRO_SMALL_BATCH) {
+        // The reference's own call pattern is ONE query per irradiance_estimate call (Scene.cpp:292-293): no allocation and no
+        // staging copies on that path -- the queries sit in the slot's page-locked, device-visible buffers and the kernel reads
+        // them over the bus (32 KB hold 1024 positions + normals, 16 KB the irradiances).
+        cudaError_t es;
+        SlotGuard g{h, slot_acquire(h, es)};
+        if (!g.s) return fail(cuda_code(es), std::string("photon_gather staging: ") + cudaGetErrorString(es));
+        float* hp = reinterpret_cast<float*>(g.s->h_r);
+        float* hn = hp + 3 * MIRO_SMALL_BATCH;
+        float* hi = reinterpret_cast<float*>(g.s->h_h);
+        memcpy(hp, pos3, n * 12); memcpy(hn, normal3, n * 12);
+        es = photon_gather_launch(h->pm[which], hp, hn, n, max_dist, k, hi, g.s->st);
+        if (es == cudaSuccess) es = cudaStreamSynchronize(g.s->st);
+        if (es != cudaSuccess) return fail(MIROGPU_ERR_CUDA, std::string("photon_gather: ") + cudaGetErrorString(es));
+        memcpy(irrad3, hi, n * 12);
+        return MIROGPU_OK;
+    }
     DevBuf bp, bn, bi;
     cudaError_t e = bp.alloc(n * 12);
     if (e == cudaSuccess) e = bn.alloc(n * 12);
