@@ -480,6 +480,7 @@ void flatten_qbvh4(const BinaryBvh& b, FlatBvh& out)
             q.e[a] = (uint8_t)(e + 127);
         }
         for (int c = 0; c < 4; ++c) q.link[c] = w.link[c];
+        qbvh4_cell_words(q);
         out.nodesq[(size_t)i] = q;
     }
 }

@@ -75,7 +75,7 @@ static_assert(sizeof(Bvh4Node) == 128, "Bvh4Node must be 128 bytes");
 // origin = the node's min corner (binary32), one power-of-two cell size per axis (biased exponent byte), planes =
 // origin + q * cell with q rounded outward (plus a safety margin that covers the decode's rounding).  Half the
 // sectors per visit of BVH4 / the same as BVH2 at half the visits -- the traversal is bound by L1 wavefronts per ray.
-//   origin[3] | ex,ey,ez,0 | qlo.x[4] qhi.x[4] qlo.y[4] qhi.y[4] || qlo.z[4] qhi.z[4] | link[4] | pad[2]
+//   origin[3] | ex,ey,ez,0 | qlo.x[4] qhi.x[4] qlo.y[4] qhi.y[4] || qlo.z[4] qhi.z[4] | link[4] | cell[2]
 // Empty slot: qlo = 255, qhi = 0 on every axis (an inverted interval never passes the slab test).
 struct Qbvh4Node {
     float origin[3];
@@ -83,9 +83,22 @@ struct Qbvh4Node {
     uint8_t qlox[4], qhix[4], qloy[4], qhiy[4];
     uint8_t qloz[4], qhiz[4];
     int32_t link[4];
-    int32_t pad[2];
+    uint32_t cell[2];   // the three cell sizes times 2^24 as the traversal multiplies them (qbvh4_cell_words), derived from e[]
 };
 static_assert(sizeof(Qbvh4Node) == 64, "Qbvh4Node must be 64 bytes");
+
+// The traversal needs 2^24 * cell per axis as a binary32 (qbvh4_node_step: the planes arrive as q * 2^-24).  A power of two is
+// its exponent field alone, so the upper 16 bits of the binary32 are enough: x and y share cell[0] (low / high half), z is
+// cell[1] whole -- one shift and one mask per node instead of three shift / mask / add chains on the exponent bytes.
+// e[] <= 227 (the builders clamp the exponent), so e + 24 is a finite exponent.
+#if defined(__CUDACC__)
+__host__ __device__
+#endif
+inline void qbvh4_cell_words(Qbvh4Node& q)
+{
+    q.cell[0] = (((uint32_t)q.e[0] + 24u) << 7) | (((uint32_t)q.e[1] + 24u) << 23);
+    q.cell[1] = ((uint32_t)q.e[2] + 24u) << 23;
+}
 
 // ---- CWBVH8 flat layout (80 B / node) ----------------------------------------------------------------
 struct Cwbvh8Node {

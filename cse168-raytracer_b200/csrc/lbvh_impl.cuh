@@ -363,6 +363,7 @@ __global__ void __launch_bounds__(256) k_lbvh_quantise(uint32_t nn, const Bvh4No
         q.e[a] = (uint8_t)(e + 127);
     }
     for (int c = 0; c < 4; ++c) q.link[c] = w.link[c];
+    qbvh4_cell_words(q);
     out[i] = q;
 }
 

@@ -510,6 +510,21 @@ MIRO_HD void unpack_planes(uint32_t w, float f[4])
 #endif
 }
 
+#ifndef MIRO_FFMA2
+#define MIRO_FFMA2 1
+#endif
+#ifndef MIRO_QCELL
+#define MIRO_QCELL 1
+#endif
+#ifdef __CUDA_ARCH__
+// (a, b) = (a, b) * s + c, each half rounded once (fma.rn.f32x2 -> FFMA2 with s and c as broadcast scalar operands).
+__device__ __forceinline__ void fma2(float& a, float& b, const float s, const float c)
+{
+    asm("{\n\t.reg .b64 ra, rs, rc;\n\tmov.b64 ra, {%0, %1};\n\tmov.b64 rs, {%2, %2};\n\tmov.b64 rc, {%3, %3};\n\t"
+        "fma.rn.f32x2 ra, ra, rs, rc;\n\tmov.b64 {%0, %1}, ra;\n\t}" : "+f"(a), "+f"(b) : "f"(s), "f"(c));
+}
+#endif
+
 // ---- BVH4 (128-byte nodes, four full-precision child boxes per fetch) ---------------------------------------------
 // Node = 8 x float4: (lo.x[4]) (hi.x[4]) (lo.y[4]) (hi.y[4]) (lo.z[4]) (hi.z[4]) (link[4]) (pad) -- four 256-bit loads, one
 // cache line.  Same walk state and leaf step as BVH2.  Child order: a three-comparator tournament finds the nearest
@@ -561,7 +576,7 @@ MIRO_HD void trace_bvh4(const float4* __restrict__ nodes, const float4* __restri
 
 // ---- QBVH4 (64-byte nodes, four child boxes quantised to 8 bits per plane on a per-node grid) ------------------------
 // Node = 4 x float4: (origin.xyz, ex|ey<<8|ez<<16) (qlo.x[4], qhi.x[4], qlo.y[4], qhi.y[4]) (qlo.z[4], qhi.z[4], link0, link1)
-// (link2, link3, -, -): two 256-bit loads.  A plane is origin + q * cell with cell = 2^(e-127); along the ray
+// (link2, link3, cell words: 2^24 cell of x | y as binary32 upper halves, of z whole): two 256-bit loads.  A plane is origin + q * cell with cell = 2^(e-127); along the ray
 //   t = (origin + q cell - o) / d = (q 2^-24) * (2^24 cell / d) + (origin - o) / d,
 // one FMA per plane once the two per-axis constants are formed.  The near / far plane words are picked by the sign of
 // the direction (two selects per axis), so no per-plane min / max is needed.  The builder rounds q outward with a
@@ -580,10 +595,16 @@ MIRO_HD void qbvh4_node_step(const float4* __restrict__ nodes, const float4* __r
     } else {
         A = ld256(p); B = ld256(p + 2);
     }
+    // cell * 2^24 (the planes arrive as q * 2^-24): the builders leave the three powers of two ready-made in the node's last two
+    // words (bvh_build.h, qbvh4_cell_words) -- x and y as the upper halves of their binary32, z whole
+#if MIRO_QCELL
+    const uint32_t cw = f2u(B.hi.z);
+    const float cx = u2f(cw << 16) * w.idx, cy = u2f(cw & 0xffff0000u) * w.idy, cz = B.hi.w * w.idz;
+#else
     const uint32_t ew = f2u(A.lo.w);
-    // cell * 2^24 (the planes arrive as q * 2^-24): the exponent bytes are at most 227, so + 24 stays a finite exponent
     const float cx = u2f(((ew & 0xffu) + 24u) << 23) * w.idx, cy = u2f((((ew >> 8) & 0xffu) + 24u) << 23) * w.idy,
                 cz = u2f((((ew >> 16) & 0xffu) + 24u) << 23) * w.idz;
+#endif
     const float bx = fmaf(A.lo.x, w.idx, -w.oodx), by = fmaf(A.lo.y, w.idy, -w.oody), bz = fmaf(A.lo.z, w.idz, -w.oodz);
     const bool px = w.idx >= 0.f, py = w.idy >= 0.f, pz = w.idz >= 0.f;
     const uint32_t qlx = f2u(A.hi.x), qhx = f2u(A.hi.y), qly = f2u(A.hi.z), qhy = f2u(A.hi.w), qlz = f2u(B.lo.x), qhz = f2u(B.lo.y);
@@ -594,12 +615,27 @@ MIRO_HD void qbvh4_node_step(const float4* __restrict__ nodes, const float4* __r
     const int32_t lk[4] = {(int32_t)f2u(B.lo.z), (int32_t)f2u(B.lo.w), (int32_t)f2u(B.hi.x), (int32_t)f2u(B.hi.y)};
     const float kFar = u2f(0x7f800000u);
     float d[4];
+#if defined(__CUDA_ARCH__) && MIRO_FFMA2
+    // Plane distances two children at a time: sm_100's packed binary32 FMA (FFMA2, the per-axis constants as broadcast scalar
+    // operands) rounds each half like fmaf, so the distances -- and every box decision -- are the bits of the scalar form at
+    // half the issue slots (24 FFMA -> 12 FFMA2 per node; the kernel is bound by issue slots, not by the FMA pipe).
+    fma2(nx[0], nx[1], cx, bx); fma2(nx[2], nx[3], cx, bx); fma2(fx[0], fx[1], cx, bx); fma2(fx[2], fx[3], cx, bx);
+    fma2(ny[0], ny[1], cy, by); fma2(ny[2], ny[3], cy, by); fma2(fy[0], fy[1], cy, by); fma2(fy[2], fy[3], cy, by);
+    fma2(nz[0], nz[1], cz, bz); fma2(nz[2], nz[3], cz, bz); fma2(fz[0], fz[1], cz, bz); fma2(fz[2], fz[3], cz, bz);
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+        const float tn = fmaxf(fmaxf(nx[c], ny[c]), fmaxf(nz[c], r.tmin));
+        const float tf = fminf(fminf(fx[c], fy[c]), fminf(fz[c], best.t));
+        d[c] = tn <= tf ? tn : kFar;
+    }
+#else
 #pragma unroll
     for (int c = 0; c < 4; ++c) {
         const float tn = fmaxf(fmaxf(fmaf(nx[c], cx, bx), fmaf(ny[c], cy, by)), fmaxf(fmaf(nz[c], cz, bz), r.tmin));
         const float tf = fminf(fminf(fmaf(fx[c], cx, bx), fmaf(fy[c], cy, by)), fminf(fmaf(fz[c], cz, bz), best.t));
         d[c] = tn <= tf ? tn : kFar;
     }
+#endif
     wide4_descend<PF>(d, lk, tris, w, stack);
 }
 
