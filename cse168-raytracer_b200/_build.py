@@ -57,8 +57,9 @@ def build_product(force=False, verbose=False, ptxas_v=False):
         return LIB
     bdir = os.path.join(ROOT, "build")
     os.makedirs(bdir, exist_ok=True)
-    _run([GXX] + GXX_FLAGS + ["-c", os.path.join(CSRC, "bvh_build.cpp"), "-o", os.path.join(bdir, "bvh_build.o")], verbose)
-    flags = list(NVCC_FLAGS) + (["-Xptxas", "-v"] if ptxas_v else []) + os.environ.get("MIROGPU_NVCC_DEFS", "").split()   # tuning builds: -DNAME=value
+    defs = os.environ.get("MIROGPU_NVCC_DEFS", "").split()   # tuning builds: -DNAME=value (the host builder sees them too: qbvh4_config.h)
+    _run([GXX] + GXX_FLAGS + defs + ["-c", os.path.join(CSRC, "bvh_build.cpp"), "-o", os.path.join(bdir, "bvh_build.o")], verbose)
+    flags = list(NVCC_FLAGS) + (["-Xptxas", "-v"] if ptxas_v else []) + defs
     log = _run([NVCC] + flags + ["-c", os.path.join(CSRC, "mirogpu.cu"), "-o", os.path.join(bdir, "mirogpu.o")], verbose)
     log2 = _run([NVCC] + flags + ["-c", os.path.join(CSRC, "photon_build.cu"), "-o", os.path.join(bdir, "photon_build.o")], verbose)
     if ptxas_v:

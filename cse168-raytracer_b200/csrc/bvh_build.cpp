@@ -458,18 +458,19 @@ void flatten_qbvh4(const BinaryBvh& b, FlatBvh& out)
             float mn = kInf, mx = -kInf;
             for (int c = 0; c < 4; ++c) if (used[c]) { mn = std::min(mn, lo[a][c]); mx = std::max(mx, hi[a][c]); }
             if (!(mn <= mx)) { mn = 0.f; mx = 0.f; }
-            q.origin[a] = mn;
             // smallest power-of-two cell with origin + (255 - margin) * cell >= max; retried one notch coarser if a plane
             // still lands above 255 after outward rounding
             int e = (int)std::ceil(std::log2(std::max((double)mx - (double)mn, 1e-30) / (255.0 - 2.0 * kMargin)));
             e = std::max(-100, std::min(100, e));
             for (;;) {
                 const double cell = std::ldexp(1.0, e);
+                q.origin[a] = qbvh4_stored_origin(mn, e);
+                const double g = qbvh4_grid_origin(q.origin[a], e);   // the grid the traversal decodes (<= mn)
                 bool ok = true;
                 for (int c = 0; c < 4 && ok; ++c) {
                     if (!used[c]) { qlo[a][c] = 255; qhi[a][c] = 0; continue; }
-                    const double l = std::floor(((double)lo[a][c] - (double)mn) / cell - kMargin);
-                    const double h = std::ceil(((double)hi[a][c] - (double)mn) / cell + kMargin);
+                    const double l = std::floor(((double)lo[a][c] - g) / cell - kMargin);
+                    const double h = std::ceil(((double)hi[a][c] - g) / cell + kMargin);
                     if (h > 255.0) { ok = false; break; }
                     qlo[a][c] = (uint8_t)std::max(0.0, l);
                     qhi[a][c] = (uint8_t)h;

@@ -18,7 +18,9 @@
 #define MIROGPU_BVH_BUILD_H
 
 #include <cstdint>
+#include <cmath>
 #include <vector>
+#include "qbvh4_config.h"
 
 // four-wide layouts: the first MIRO_TOP_NODES nodes are the top levels in breadth-first order (1 + 4 + 16 + 64)
 #define MIRO_TOP_NODES 85
@@ -72,8 +74,8 @@ static_assert(sizeof(Bvh4Node) == 128, "Bvh4Node must be 128 bytes");
 
 // ---- QBVH4 flat layout (64 B / node = two 32-byte sectors) ---------------------------------------------------------
 // The same four-wide collapse as BVH4 with the child boxes quantised to 8 bits per plane on a per-node grid: grid
-// origin = the node's min corner (binary32), one power-of-two cell size per axis (biased exponent byte), planes =
-// origin + q * cell with q rounded outward (plus a safety margin that covers the decode's rounding).  Half the
+// origin = the node's min corner (binary32; the MIRO_QDIRECT variant stores it 2^15 cells low, qbvh4_stored_origin), one
+// power-of-two cell size per axis (biased exponent byte), planes = origin + q * cell with q rounded outward (plus a safety margin that covers the decode's rounding).  Half the
 // sectors per visit of BVH4 / the same as BVH2 at half the visits -- the traversal is bound by L1 wavefronts per ray.
 //   origin[3] | ex,ey,ez,0 | qlo.x[4] qhi.x[4] qlo.y[4] qhi.y[4] || qlo.z[4] qhi.z[4] | link[4] | cell[2]
 // Empty slot: qlo = 255, qhi = 0 on every axis (an inverted interval never passes the slab test).
@@ -96,8 +98,42 @@ __host__ __device__
 #endif
 inline void qbvh4_cell_words(Qbvh4Node& q)
 {
-    q.cell[0] = (((uint32_t)q.e[0] + 24u) << 7) | (((uint32_t)q.e[1] + 24u) << 23);
-    q.cell[1] = ((uint32_t)q.e[2] + 24u) << 23;
+    q.cell[0] = (((uint32_t)q.e[0] + (uint32_t)MIRO_QSHIFT) << 7) | (((uint32_t)q.e[1] + (uint32_t)MIRO_QSHIFT) << 23);
+    q.cell[1] = ((uint32_t)q.e[2] + (uint32_t)MIRO_QSHIFT) << 23;
+}
+
+// MIRO_QDIRECT (qbvh4_config.h; a measured, slower variant, off by default): the traversal reads a plane byte as the binary32 1 + q 2^-15 and multiplies by 2^15 cell, i.e. it evaluates
+// (2^15 + q) cell above the stored origin -- so the node stores origin' = the largest binary32 with origin' + 2^15 cell <= mn, and
+// the builders quantise against the grid that origin' really gives, qbvh4_grid_origin(origin', e) = origin' + 2^15 cell (exact in
+// binary64), never above mn.  Where 2^15 cell exceeds |mn| the grid moves down by up to 2^-9 cell, which the outward rounding of q
+// absorbs like any other offset; the traversal's own rounding of (origin' - o) / d is then at most 2^-9 cell too, inside the
+// builders' 0.02-cell margin.
+#if defined(__CUDACC__)
+__host__ __device__
+#endif
+inline float qbvh4_stored_origin(float mn, int e)
+{
+#if MIRO_QDIRECT
+    const double off = ldexp(1.0, e + 15);
+    float o = (float)((double)mn - off);
+    while ((double)o + off > (double)mn) o = nextafterf(o, -INFINITY);
+    return o;
+#else
+    (void)e;
+    return mn;
+#endif
+}
+#if defined(__CUDACC__)
+__host__ __device__
+#endif
+inline double qbvh4_grid_origin(float stored, int e)
+{
+#if MIRO_QDIRECT
+    return (double)stored + ldexp(1.0, e + 15);
+#else
+    (void)e;
+    return (double)stored;
+#endif
 }
 
 // ---- CWBVH8 flat layout (80 B / node) ----------------------------------------------------------------

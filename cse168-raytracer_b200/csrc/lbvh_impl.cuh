@@ -343,16 +343,17 @@ __global__ void __launch_bounds__(256) k_lbvh_quantise(uint32_t nn, const Bvh4No
         float mn = INFINITY, mx = -INFINITY;
         for (int c = 0; c < 4; ++c) if (isfinite(w.lox[c])) { mn = fminf(mn, lo[a][c]); mx = fmaxf(mx, hi[a][c]); }
         if (!(mn <= mx)) { mn = 0.f; mx = 0.f; }
-        q.origin[a] = mn;
         int e = (int)ceil(log2(fmax((double)mx - (double)mn, 1e-30) / (255.0 - 2.0 * kMargin)));
         e = max(-100, min(100, e));
         for (;;) {
             const double cell = ldexp(1.0, e);
+            q.origin[a] = qbvh4_stored_origin(mn, e);
+            const double g = qbvh4_grid_origin(q.origin[a], e);   // the grid the traversal decodes (<= mn)
             bool ok = true;
             for (int c = 0; c < 4 && ok; ++c) {
                 if (!isfinite(w.lox[c])) { qlo[a][c] = 255; qhi[a][c] = 0; continue; }
-                const double l = floor(((double)lo[a][c] - (double)mn) / cell - kMargin);
-                const double h = ceil(((double)hi[a][c] - (double)mn) / cell + kMargin);
+                const double l = floor(((double)lo[a][c] - g) / cell - kMargin);
+                const double h = ceil(((double)hi[a][c] - g) / cell + kMargin);
                 if (h > 255.0) { ok = false; break; }
                 qlo[a][c] = (uint8_t)fmax(0.0, l);
                 qhi[a][c] = (uint8_t)h;

@@ -16,6 +16,7 @@
 #include <cuda_fp16.h>
 
 #include "../../include/mirogpu.h"
+#include "qbvh4_config.h"
 
 #define MIRO_HD __host__ __device__ __forceinline__
 
@@ -158,6 +159,27 @@ struct BestHit {
     float beta, gamma;
 };
 
+#ifdef __CUDACC__
+// The hybrid kernel's copy of BestHit for triangle-only scenes: only t is consulted by the walk (every box test), prim / beta /
+// gamma are written when a triangle is accepted (once or twice per ray) and read when the ray is answered.  They live in the
+// CTA's shared memory ([field][thread], conflict-free) instead of three registers per lane -- the kernel runs at a 48-register
+// budget (10 CTAs of 128 threads per SM), and with them resident the node step spills.  Slot 3 is the lane's ray index.
+#define MIRO_BEST_SM_THREADS 128
+__shared__ uint32_t g_best_sm[4 * MIRO_BEST_SM_THREADS];
+template <int K, typename T>
+struct BestSmSlot {
+    __device__ __forceinline__ operator T() const { const uint32_t v = g_best_sm[K * MIRO_BEST_SM_THREADS + threadIdx.x]; return *reinterpret_cast<const T*>(&v); }
+    __device__ __forceinline__ BestSmSlot& operator=(T x) { g_best_sm[K * MIRO_BEST_SM_THREADS + threadIdx.x] = *reinterpret_cast<const uint32_t*>(&x); return *this; }
+    __device__ __forceinline__ BestSmSlot& operator=(const BestSmSlot& o) { return *this = (T)o; }
+};
+struct BestHitSm {
+    float t;
+    BestSmSlot<0, uint32_t> prim;
+    BestSmSlot<1, float> beta;
+    BestSmSlot<2, float> gamma;
+};
+#endif
+
 // Sphere::intersect, Sphere.cpp:28-69, on a sphere slot of the leaf array: v0 = (centre, prim id bits), radius separately.  Same
 // operations in the same order (a = |d|^2, b = (2 d) . (o - c), c = |o - c|^2 - r r, discriminant b b - 4 a c, the two roots
 // divided by 2 a), no FMA.  The reference takes the nearer root if it lies strictly inside (tMin, tMax) -- tMax being the best
@@ -198,8 +220,8 @@ MIRO_RARE float sphere_hit_t(const float4 v0, const float radius, const mirogpu_
 // Acceptance on top of the reference's own reject line: the leaf keeps a hit only if it is strictly closer
 // than the best so far (BVH.cpp:498-500); equal t goes to the smaller primitive id so the result does not
 // depend on traversal order.  NaN t fails every comparison and is dropped, as in the reference.
-template <bool NT>
-MIRO_HD bool tri_test(const float4 v0, const float4 v1, const float4 v2, const float4 v3, const mirogpu_ray& r, BestHit& best, const float4* __restrict__ rec)
+template <bool NT, typename BEST>
+MIRO_HD bool tri_test(const float4 v0, const float4 v1, const float4 v2, const float4 v3, const mirogpu_ray& r, BEST& best, const float4* __restrict__ rec)
 {
     const float nx = v1.w, ny = v2.w, nz = v3.x;   // normal = cross(BmA, CmA)
     const float ndx = -r.dx, ndy = -r.dy, ndz = -r.dz;
@@ -335,7 +357,8 @@ MIRO_HD float fast_safe_rcp(float d)
 #endif
 }
 
-MIRO_HD void bvh2_begin(const mirogpu_ray& r, Bvh2Walk& w, BestHit& best)
+template <typename BEST>
+MIRO_HD void bvh2_begin(const mirogpu_ray& r, Bvh2Walk& w, BEST& best)
 {
     w.idx = fast_safe_rcp(r.dx); w.idy = fast_safe_rcp(r.dy); w.idz = fast_safe_rcp(r.dz);
     w.oodx = r.ox * w.idx; w.oody = r.oy * w.idy; w.oodz = r.oz * w.idz;
@@ -373,9 +396,9 @@ MIRO_HD void bvh2_pop(Bvh2Walk& w, const STK& stack)
 
 // PF bit 0: prefetch the pushed far child (node or first triangle line) into L2; bit 1: into L1 instead;
 // bit 2: prefetch the triangles of a leaf reached by descent (the lane usually waits for the warp's leaf phase).
-template <int PF, typename STK>
+template <int PF, typename STK, typename BEST>
 MIRO_HD void bvh2_node_step(const float4* __restrict__ nodes, const float4* __restrict__ tris, const mirogpu_ray& r, Bvh2Walk& w,
-                            STK& stack, const BestHit& best)
+                            STK& stack, const BEST& best)
 {
     const F8 na = ld256(nodes + 4 * (size_t)w.node), nb = ld256(nodes + 4 * (size_t)w.node + 2);
     const float4 n0 = na.lo, n1 = na.hi, nz = nb.lo, lk = nb.hi;
@@ -413,9 +436,9 @@ MIRO_HD void bvh2_node_step(const float4* __restrict__ nodes, const float4* __re
     }
 }
 
-template <bool ANY, bool NT = false, typename STK>
+template <bool ANY, bool NT = false, typename STK, typename BEST>
 MIRO_HD void bvh2_leaf_step(const float4* __restrict__ tris, const mirogpu_ray& r, Bvh2Walk& w, const STK& stack,
-                            BestHit& best)
+                            BEST& best)
 {
     const uint32_t ref = (uint32_t)~w.node;
     const uint32_t first = ref >> 3, count = (ref & 7u) + 1u;
@@ -429,9 +452,9 @@ MIRO_HD void bvh2_leaf_step(const float4* __restrict__ tris, const mirogpu_ray& 
 
 // One triangle of the leaf per call; a leaf with more stays the lane's node (first + 1, count - 1), so the warp's next vote
 // decides again between node steps and another leaf phase and a leaf phase never loops over the longest leaf of the warp.
-template <bool ANY, bool NT = false, typename STK>
+template <bool ANY, bool NT = false, typename STK, typename BEST>
 MIRO_HD void bvh2_leaf_step_one(const float4* __restrict__ tris, const mirogpu_ray& r, Bvh2Walk& w, const STK& stack,
-                                BestHit& best)
+                                BEST& best)
 {
     const uint32_t ref = (uint32_t)~w.node;
     const uint32_t first = ref >> 3;
@@ -444,8 +467,8 @@ MIRO_HD void bvh2_leaf_step_one(const float4* __restrict__ tris, const mirogpu_r
 
 // Up to two triangles of the leaf per call (PF bit 5): fewer leaf phases -- and votes -- per ray than one at a time, at the
 // price of lanes with a single triangle idling through the second test.
-template <bool ANY, bool NT = false, typename STK>
-MIRO_HD void bvh2_leaf_step_two(const float4* __restrict__ tris, const mirogpu_ray& r, Bvh2Walk& w, const STK& stack, BestHit& best)
+template <bool ANY, bool NT = false, typename STK, typename BEST>
+MIRO_HD void bvh2_leaf_step_two(const float4* __restrict__ tris, const mirogpu_ray& r, Bvh2Walk& w, const STK& stack, BEST& best)
 {
     const uint32_t ref = (uint32_t)~w.node;
     const uint32_t first = ref >> 3, left = ref & 7u;   // left = count - 1
@@ -461,8 +484,8 @@ MIRO_HD void bvh2_leaf_step_two(const float4* __restrict__ tris, const mirogpu_r
 
 // One triangle of a postponed leaf reference (PF bit 6, see k_trace_hybrid); returns the reference of what is left of the leaf
 // (MIRO_BVH2_DONE = nothing).  hit: a triangle was accepted.
-template <bool NT = false>
-MIRO_HD int32_t leaf_ref_test_one(const float4* __restrict__ tris, const mirogpu_ray& r, int32_t leaf, BestHit& best, bool& hit)
+template <bool NT = false, typename BEST>
+MIRO_HD int32_t leaf_ref_test_one(const float4* __restrict__ tris, const mirogpu_ray& r, int32_t leaf, BEST& best, bool& hit)
 {
     const uint32_t ref = (uint32_t)~leaf;
     const uint32_t first = ref >> 3;
@@ -501,7 +524,16 @@ MIRO_HD void wide4_descend(const float d[4], const int32_t lk[4], const float4* 
 // idle.  The 2^24 is folded into the per-axis cell constant (a power of two, so exactly).
 MIRO_HD void unpack_planes(uint32_t w, float f[4])
 {
+#if MIRO_QDIRECT
+    // f[i] = 1 + 2^-15 * byte i of w: the byte dropped into bits 8..15 of the binary32 1.0 -- one PRMT per plane and no
+    // conversion.  The builder shifts the grid origin down by 2^15 cells to match (bvh_build.h, qbvh4_cell_words).
 #ifdef __CUDA_ARCH__
+    f[0] = u2f(__byte_perm(w, 0x3f800000u, 0x7604)); f[1] = u2f(__byte_perm(w, 0x3f800000u, 0x7614));
+    f[2] = u2f(__byte_perm(w, 0x3f800000u, 0x7624)); f[3] = u2f(__byte_perm(w, 0x3f800000u, 0x7634));
+#else
+    for (int i = 0; i < 4; ++i) f[i] = u2f(0x3f800000u | (((w >> (8 * i)) & 0xffu) << 8));
+#endif
+#elif defined(__CUDA_ARCH__)
     const uint32_t p01 = __byte_perm(w, 0u, 0x4140), p23 = __byte_perm(w, 0u, 0x4342);
     const __half2 h01 = *reinterpret_cast<const __half2*>(&p01), h23 = *reinterpret_cast<const __half2*>(&p23);
     f[0] = __low2float(h01); f[1] = __high2float(h01); f[2] = __low2float(h23); f[3] = __high2float(h23);
@@ -510,12 +542,7 @@ MIRO_HD void unpack_planes(uint32_t w, float f[4])
 #endif
 }
 
-#ifndef MIRO_FFMA2
-#define MIRO_FFMA2 1
-#endif
-#ifndef MIRO_QCELL
-#define MIRO_QCELL 1
-#endif
+
 #ifdef __CUDA_ARCH__
 // (a, b) = (a, b) * s + c, each half rounded once (fma.rn.f32x2 -> FFMA2 with s and c as broadcast scalar operands).
 __device__ __forceinline__ void fma2(float& a, float& b, const float s, const float c)
@@ -530,9 +557,9 @@ __device__ __forceinline__ void fma2(float& a, float& b, const float s, const fl
 // cache line.  Same walk state and leaf step as BVH2.  Child order: a three-comparator tournament finds the nearest
 // hit child (descended next); the two first-round losers are pushed first, the runner-up of the final last, so the
 // nearer of the remaining children tends to be popped earlier.  Misses carry distance +inf and are never pushed.
-template <int PF, typename STK>
+template <int PF, typename STK, typename BEST>
 MIRO_HD void bvh4_node_step(const float4* __restrict__ nodes, const float4* __restrict__ tris, const mirogpu_ray& r, Bvh2Walk& w,
-                            STK& stack, const BestHit& best)
+                            STK& stack, const BEST& best)
 {
     const float4* p = nodes + 8 * (size_t)w.node;
     const F8 X = ld256(p), Y = ld256(p + 2), Z = ld256(p + 4), L = ld256(p + 6);
@@ -583,9 +610,9 @@ MIRO_HD void trace_bvh4(const float4* __restrict__ nodes, const float4* __restri
 // margin of 0.02 cell, far above the rounding of this decode (a few ulp of the plane distance).
 // STAGE > 0 (device, hybrid kernel): nodes [0, STAGE) -- the top levels, numbered breadth-first by the flattener -- are read from
 // the CTA's copy in shared memory (`staged`, 4 float4 per node) instead of through L1.
-template <int PF, typename STK, int STAGE = 0>
+template <int PF, typename STK, int STAGE = 0, typename BEST = BestHit>
 MIRO_HD void qbvh4_node_step(const float4* __restrict__ nodes, const float4* __restrict__ tris, const mirogpu_ray& r, Bvh2Walk& w,
-                             STK& stack, const BestHit& best, const float4* staged = nullptr)
+                             STK& stack, const BEST& best, const float4* staged = nullptr)
 {
     const float4* p = nodes + 4 * (size_t)w.node;
     F8 A, B;
@@ -595,8 +622,9 @@ MIRO_HD void qbvh4_node_step(const float4* __restrict__ nodes, const float4* __r
     } else {
         A = ld256(p); B = ld256(p + 2);
     }
-    // cell * 2^24 (the planes arrive as q * 2^-24): the builders leave the three powers of two ready-made in the node's last two
-    // words (bvh_build.h, qbvh4_cell_words) -- x and y as the upper halves of their binary32, z whole
+    // cell * 2^MIRO_QSHIFT (the planes arrive as 1 + q * 2^-15 above an origin stored 2^15 cells low -- or, MIRO_QDIRECT 0, as
+    // q * 2^-24): the builders leave the three powers of two ready-made in the node's last two words (bvh_build.h,
+    // qbvh4_cell_words) -- x and y as the upper halves of their binary32, z whole
 #if MIRO_QCELL
     const uint32_t cw = f2u(B.hi.z);
     const float cx = u2f(cw << 16) * w.idx, cy = u2f(cw & 0xffff0000u) * w.idy, cz = B.hi.w * w.idz;

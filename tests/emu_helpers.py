@@ -11,7 +11,7 @@ CW_NODE = np.dtype([("p", np.float32, 3), ("e", np.uint8, 3), ("imask", np.uint8
 BVH4_NODE = np.dtype([("lox", np.float32, 4), ("hix", np.float32, 4), ("loy", np.float32, 4), ("hiy", np.float32, 4), ("loz", np.float32, 4), ("hiz", np.float32, 4),
                       ("link", np.int32, 4), ("pad", np.int32, 4)])
 QBVH4_NODE = np.dtype([("origin", np.float32, 3), ("e", np.uint8, 3), ("pad0", np.uint8), ("qlox", np.uint8, 4), ("qhix", np.uint8, 4), ("qloy", np.uint8, 4),
-                       ("qhiy", np.uint8, 4), ("qloz", np.uint8, 4), ("qhiz", np.uint8, 4), ("link", np.int32, 4), ("pad", np.int32, 2)])
+                       ("qhiy", np.uint8, 4), ("qloz", np.uint8, 4), ("qhiz", np.uint8, 4), ("link", np.int32, 4), ("cell", np.uint32, 2)])
 TRI_REC = np.dtype([("a", np.float32, 3), ("prim_id", np.uint32), ("e1", np.float32, 3), ("nx", np.float32), ("e2", np.float32, 3), ("ny", np.float32),
                     ("nz", np.float32), ("pad", np.float32, 3)])
 assert BVH2_NODE.itemsize == 64 and CW_NODE.itemsize == 80 and TRI_REC.itemsize == 64 and BVH4_NODE.itemsize == 128 and QBVH4_NODE.itemsize == 64

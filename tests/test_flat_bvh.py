@@ -158,17 +158,24 @@ def test_bvh4_boxes_contain_reference_bounds(emu, oracle, scenes, name):
 @pytest.mark.parametrize("name", ["testobj", "cornell", "teapot", "bunny_teapot"])
 def test_qbvh4_decoded_boxes_contain_the_full_precision_boxes(emu, oracle, scenes, name):
     """QBVH4 = the BVH4 tree with child boxes quantised to 8 bits per plane: same topology and links, and every decoded
-    box (origin + q * 2^(e-127)) contains the full-precision BVH4 box it encodes, with the builder's margin to spare."""
+    box (grid origin + q * 2^(e-127)) contains the full-precision BVH4 box it encodes, with the builder's margin to spare."""
     V = _verts(oracle, scenes, name)
     wide, order, _, _ = emu_build(emu, V, 3)
     quant, order_q, _, _ = emu_build(emu, V, 4)
     assert np.array_equal(order, order_q) and len(wide) == len(quant)
     assert np.array_equal(wide["link"], quant["link"])
     cell = np.ldexp(1.0, quant["e"].astype(np.int64) - 127)                 # (n, 3)
+    # the last two words hold 2^24 cell per axis ready-made for the traversal (bvh_build.h, qbvh4_cell_words: x and y as the upper
+    # halves of their binary32, z whole)
+    grid = quant["origin"].astype(np.float64)
+    cw = quant["cell"].astype(np.uint64)
+    assert np.array_equal((cw[:, 0] & 0xffff) << 16, (quant["e"][:, 0].astype(np.uint64) + 24) << 23)
+    assert np.array_equal(cw[:, 0] & 0xffff0000, (quant["e"][:, 1].astype(np.uint64) + 24) << 23)
+    assert np.array_equal(cw[:, 1], (quant["e"][:, 2].astype(np.uint64) + 24) << 23)
     for a, (lo, hi, qlo, qhi) in enumerate((("lox", "hix", "qlox", "qhix"), ("loy", "hiy", "qloy", "qhiy"), ("loz", "hiz", "qloz", "qhiz"))):
         used = np.isfinite(wide[lo])
-        dlo = quant["origin"][:, a:a + 1].astype(np.float64) + quant[qlo].astype(np.float64) * cell[:, a:a + 1]
-        dhi = quant["origin"][:, a:a + 1].astype(np.float64) + quant[qhi].astype(np.float64) * cell[:, a:a + 1]
+        dlo = grid[:, a:a + 1] + quant[qlo].astype(np.float64) * cell[:, a:a + 1]
+        dhi = grid[:, a:a + 1] + quant[qhi].astype(np.float64) * cell[:, a:a + 1]
         assert (dlo[used] <= wide[lo][used]).all() and (dhi[used] >= wide[hi][used]).all()
         assert (quant[qlo][~used] == 255).all() and (quant[qhi][~used] == 0).all()      # empty slots: inverted interval
         # not needlessly loose: within two cells of the box it encodes

@@ -84,8 +84,9 @@ def test_device_built_tree_structure(pkg, scenes, oracle, name, builder):
             for c in range(4):
                 if nd["qlox"][c] == 255 and nd["qhix"][c] == 0:
                     continue   # empty slot
-                clo = nd["origin"].astype(np.float64) + np.array([nd["qlox"][c], nd["qloy"][c], nd["qloz"][c]]) * cell[ref]
-                chi = nd["origin"].astype(np.float64) + np.array([nd["qhix"][c], nd["qhiy"][c], nd["qhiz"][c]]) * cell[ref]
+                grid = nd["origin"].astype(np.float64)
+                clo = grid + np.array([nd["qlox"][c], nd["qloy"][c], nd["qloz"][c]]) * cell[ref]
+                chi = grid + np.array([nd["qhix"][c], nd["qhiy"][c], nd["qhiz"][c]]) * cell[ref]
                 parts.append(check(int(nd["link"][c]), clo, chi))
             assert parts
             slo, shi = np.min([p[0] for p in parts], 0), np.max([p[1] for p in parts], 0)
