@@ -8,9 +8,11 @@ reference's makeBunny20Scene geometry, 1 389 021 triangles, with its own camera)
 
 A step is one pass of the hot path over one batch of synthetic rays: SPP jittered samples of the frame --
 device-side Camera::eyeRay -> closest-hit -> device-side Ray::diffuse at every hit -> closest-hit.
-`value` = (primary + live bounce rays of all ranks) / max-over-ranks device time, inputs resident in HBM; the timed region issues
-          every step as two half-batches (8 samples each) on two streams, and the same steps are replayed one launch after the
-          other right afterwards for the per-kernel durations and the roofline (--sequential times that schedule instead).
+`value` = (primary + live bounce rays of all ranks) / max-over-ranks device time, inputs resident in HBM; the timed region keeps
+          three steps in flight (consecutive steps go round-robin over three streams, each with its own ray / hit buffers, all K
+          steps finished inside the timed region), and the same steps are replayed one launch after the other right afterwards
+          for the per-kernel durations and the roofline (--sequential times that schedule instead; MIRO_BENCH_INFLIGHT=0 the
+          round-2 schedule of two half-batches per step on two streams).
 `e2e`   = the same metric through the reference-facing call with HOST buffers: Scene::raytraceImage ->
           mirogpu_render (diffuse-bounce mode, no shadow rays so the ray work equals a step's), framebuffer
           gathered over NCCL/NVLink for N > 1 (two frames in flight) and copied to pinned host memory, every step.
@@ -383,6 +385,32 @@ def run_ours(args):
                 with torch.cuda.stream(sides[k - 1]):
                     half_step(it, c)
 
+    # Default schedule (MIRO_BENCH_INFLIGHT = k, default 3; 0 or 1 = the half-batch schedule above): whole steps go round-robin over
+    # k streams, each with its own ray / hit buffers, so consecutive steps cover each other's ragged ends with launches twice the
+    # size of the half-batches' (a persistent launch pays a fixed ramp and tail whatever its size).  Measured on one B200 for one
+    # rank's share of an N-rank run (--emulate-shard N; profiles/r02v_inflight.txt): N = 8: 7.44 Grays/s with half-batches, 8.16 with
+    # two steps in flight, 8.35 with three; N = 4: 8.13 -> 8.62 (two); N = 1: 8.97 -> 9.11 -> 9.13.
+    inflight = int(os.environ.get("MIRO_BENCH_INFLIGHT", "3"))
+    if inflight > 1 and not args.sequential:
+        bufs = [(d_rays, d_hits, d_b, d_h2)] + [tuple(torch.empty_like(t) for t in (d_rays, d_hits, d_b, d_h2)) for _ in range(inflight - 1)]
+        while len(sides) < inflight - 1:
+            sides.append(torch.cuda.Stream(dev))
+
+        def whole_step(it, B):
+            r, h, b, h2 = B
+            S.generate_primary(cam, WIDTH, HEIGHT, r, rows=rows, jitter=1, seed=SEED, sample=it * SPP, samples=SPP)
+            S.intersect_device(r, h, mode=pkg.CLOSEST_HIT | pkg.HINT_COHERENT)
+            S.generate_bounce(r, h, b, seed=SEED, sample=it, index_base=index_base, d_live_count=d_live)
+            S.intersect_device(b, h2)
+
+        def step(it):
+            k = it % inflight
+            if k == 0:
+                whole_step(it, bufs[0])
+            else:
+                with torch.cuda.stream(sides[k - 1]):
+                    whole_step(it, bufs[k])
+
     def join_streams():
         for side in sides:
             done = torch.cuda.Event()
@@ -441,9 +469,16 @@ def run_ours(args):
     host_fb = torch.empty((HEIGHT, WIDTH, 3), dtype=torch.uint8).pin_memory()   # the reference's Image: 3 bytes per pixel
     e2e_rays = 0
     e2e_call = "mirogpu_render_rgb8 (Scene::raytraceImage -> 8-bit Image), diffuse-bounce mode, pinned host framebuffer; rays = primary + LIVE bounce rays"
-    if world > 1:
-        e2e_call += " per rank -> all_reduce(max) of the tone-map constant, 8-bit rows, NCCL all_gather of the row shards, rank 0 copies the frame to the host; two frames in flight (the exchange of frame i overlaps the render of frame i + 1, all frames delivered inside the timed region)"
-    if world == 1:
+    # development: MIRO_BENCH_FORCE_PIPE=1 takes the multi-rank e2e path (frames in flight, NCCL exchange) on a single rank
+    piped = world > 1 or os.environ.get("MIRO_BENCH_FORCE_PIPE") == "1"
+    if piped and world == 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1"); os.environ.setdefault("MASTER_PORT", "29533")
+        dist.init_process_group("nccl", rank=0, world_size=1, device_id=torch.device("cuda", local))
+    if piped:
+        e2e_call += (" per rank -> all_reduce(max) of the tone-map constant, 8-bit rows, NCCL all_gather of the row shards, rank 0 copies the frame to the host; "
+                     "frames in flight (the exchange of frame i overlaps the render of frame i + 1; the host queues the timed frames without waiting on any -- "
+                     "their live-ray counts, a function of the seed alone, are read from an untimed pass over the same seeds -- and all frames are delivered inside the timed region)")
+    if not piped:
         def e2e_step(it):
             p.seed = SEED + it
             S.render_rgb8(cam, p, out=host_fb.numpy())
@@ -453,20 +488,38 @@ def run_ours(args):
         # frames in flight (sharding.FramePipeline): rank r renders frame i + 1 while frame i's exchange -- all_reduce(max) of the
         # tone map's frame-wide constant (Scene.cpp:157-202), 8-bit rows, NCCL all_gather, rank 0's copy to the host -- runs on a
         # side stream; every frame is still delivered to host memory inside the timed region (drained before the clock stops)
-        pipe = sharding.FramePipeline(S, HEIGHT, WIDTH, world, rank, dev)
+        # MIRO_BENCH_E2E_HANDLES = k (default 3): k handles of the scene per rank (0.25 GB each), k consecutive frames rendering
+        # concurrently on k streams -- a handle renders one frame at a time
+        n_handles = max(1, int(os.environ.get("MIRO_BENCH_E2E_HANDLES", "3")))
+        replicas = [scenes.handle_replica(pkg, H, SCENE, layout) for _ in range(n_handles - 1)]
+        for Sx in replicas:
+            Sx.set_kernel_variant(args.variant)
+        pipe = sharding.FramePipeline(S, HEIGHT, WIDTH, world, rank, dev, replicas=replicas)
+        e2e_call += f"; {n_handles} handles of the scene per rank, {n_handles} consecutive frames rendering concurrently"
+
+        # Untimed pass over the seeds of the timed frames: rays traced per frame (primary + LIVE bounce rays -- the device counter
+        # mirogpu_last_call_stats reads is valid once the frame's render has finished, so reading it costs a host wait per frame;
+        # the counts depend on the seed alone).  The timed loop then queues its frames without waiting on any of them.
+        rays_of_seed = {}
 
         def e2e_step(it):
             p.seed = SEED + it
-            return pipe.rays_traced(pipe.submit(cam, p))
+            if it in rays_of_seed:
+                pipe.submit(cam, p)
+                return rays_of_seed[it]
+            rays_of_seed[it] = pipe.rays_traced(pipe.submit(cam, p))
+            return rays_of_seed[it]
     for it in range(min(3, args.warmup)):
         e2e_step(it)
-    if world > 1:
+    if piped:
+        for it in range(e2e_steps):
+            e2e_step(100 + it)
         pipe.drain()
     barrier()
     t0 = time.perf_counter()
     for it in range(e2e_steps):
         e2e_rays += e2e_step(100 + it)
-    if world > 1:
+    if piped:
         pipe.drain()
     barrier()
     e2e_s_local = time.perf_counter() - t0
@@ -541,6 +594,9 @@ def run_ours(args):
                 "triangle_mb": info.triangle_bytes / 1e6, "build_s": info.build_seconds + info.flatten_seconds,
                 "sharding": f"image rows interleaved over {world} rank(s), BVH replicated",
                 "schedule": ("one launch after the other on one stream (--sequential)" if args.sequential else
+                             f"{inflight} steps in flight: consecutive steps round-robin over {inflight} streams, each with its own ray / hit buffers, "
+                             "so each persistent launch's ragged end overlaps the neighbouring steps' kernels; all steps end inside the timed region"
+                             if inflight > 1 else
                              "two half-batches (8 samples each) per step on two streams: each launch's ragged end overlaps the other half's kernels"),
                 "ms_per_step_sequential": ms_sequential / args.steps,
                 "per_gpu_ms": {"primary_trace": prim_ms, "gen_bounce": genb_ms, "bounce_trace": bounce_ms, "gen_primary": genp_ms,
@@ -560,7 +616,7 @@ def run_ours(args):
             "cpu_baseline": cpu,
             "e2e": {"value": e2e_value, "unit": "Mrays/s", "h2d_bytes_per_step": 40 + 17 * 4, "d2h_bytes_per_step": WIDTH * HEIGHT * 3,
                     "call": e2e_call},
-            "gpu_launches": int((4 if args.sequential else 8) * args.steps * world),
+            "gpu_launches": int((4 if (args.sequential or inflight > 1) else 4 * chunks) * args.steps * world),
             "clocks": clocks,
         }
         if world == 1 and not args.no_extras:
@@ -568,6 +624,7 @@ def run_ours(args):
         emit(line)
     if world > 1:
         dist.barrier()
+    if dist.is_initialized():
         dist.destroy_process_group()
     if rc:
         raise SystemExit(rc)

@@ -114,6 +114,7 @@ struct BatchSlot {
     }
 };
 
+#define MIRO_TICKETS 1024u
 struct mirogpu_scene {
     std::vector<std::unique_ptr<BatchSlot>> slots;   // guarded by slot_mtx
     std::mutex slot_mtx;
@@ -144,7 +145,7 @@ struct mirogpu_scene {
     mirogpu_light* d_lights = nullptr;
     uint32_t nlights = 0;
     std::vector<mirogpu_light> h_lights;   // host copy (photon emission parameters are derived on the host)
-    unsigned long long* d_ticket = nullptr;  // persistent-kernel ticket counters (ring of 64)
+    unsigned long long* d_ticket = nullptr;  // persistent-kernel ticket counters (ring of MIRO_TICKETS: a slot is reused that many launches later -- callers that queue launches on several streams far ahead of the device must not wrap onto a launch still running)
     std::atomic<uint32_t> ticket_slot{0};
     mirogpu_scene_info info{};
     std::vector<uint8_t> h_nodes;     // host copies kept for mirogpu_debug_copy_*
@@ -219,7 +220,7 @@ cudaError_t launch_trace(mirogpu_scene* h, const mirogpu_ray* d_rays, size_t n, 
         else k_trace_simple<LAYOUT, ANY, false><<<grid, 128, 0, st>>>(h->ds, d_rays, n, d_hits, nullptr, d_n, mult);
         return cudaGetLastError();
     }
-    unsigned long long* ticket = h->d_ticket + (h->ticket_slot.fetch_add(1) & 63u);
+    unsigned long long* ticket = h->d_ticket + (h->ticket_slot.fetch_add(1) & (MIRO_TICKETS - 1u));
     cudaError_t e = cudaMemsetAsync(ticket, 0, sizeof(unsigned long long), st);
     if (e != cudaSuccess) return e;
     if (h->non_triangles) {
@@ -446,7 +447,7 @@ int upload_replica(const HostBuild& hb, int dev, const LbvhOut* lb, mirogpu_scen
     h->node_bytes_dev = node_bytes; h->tri_bytes_dev = tri_bytes;
     if ((e = cudaMalloc(&h->d_shade, std::max<size_t>(shade_bytes, 16))) != cudaSuccess) return bail(e, "cudaMalloc shading records");
     if ((e = cudaMalloc(&h->d_materials, hb.mats.size() * sizeof(mirogpu_material))) != cudaSuccess) return bail(e, "cudaMalloc materials");
-    if ((e = cudaMalloc(&h->d_ticket, 64 * sizeof(unsigned long long))) != cudaSuccess) return bail(e, "cudaMalloc tickets");
+    if ((e = cudaMalloc(&h->d_ticket, MIRO_TICKETS * sizeof(unsigned long long))) != cudaSuccess) return bail(e, "cudaMalloc tickets");
     if (!hb.planes.empty() && (e = cudaMalloc(&h->d_planes, hb.planes.size() * sizeof(float4))) != cudaSuccess) return bail(e, "cudaMalloc planes");
     if (!device_built && node_bytes && (e = cudaMemcpy(h->d_nodes, hb.node_src, node_bytes, cudaMemcpyHostToDevice)) != cudaSuccess) return bail(e, "upload nodes");
     if (!device_built && tri_bytes && (e = cudaMemcpy(h->d_tris, hb.tris.data(), tri_bytes, cudaMemcpyHostToDevice)) != cudaSuccess) return bail(e, "upload triangles");
@@ -457,7 +458,7 @@ int upload_replica(const HostBuild& hb, int dev, const LbvhOut* lb, mirogpu_scen
         if ((e = cudaMalloc(&h->d_uvs, hb.uvs.size() * sizeof(float))) != cudaSuccess) return bail(e, "cudaMalloc texture coordinates");
         if ((e = cudaMemcpy(h->d_uvs, hb.uvs.data(), hb.uvs.size() * sizeof(float), cudaMemcpyHostToDevice)) != cudaSuccess) return bail(e, "upload texture coordinates");
     }
-    if ((e = cudaMemset(h->d_ticket, 0, 64 * sizeof(unsigned long long))) != cudaSuccess) return bail(e, "memset tickets");
+    if ((e = cudaMemset(h->d_ticket, 0, MIRO_TICKETS * sizeof(unsigned long long))) != cudaSuccess) return bail(e, "memset tickets");
     h->nmaterials = (uint32_t)hb.mats.size();
     h->any_refractive = hb.any_refractive; h->any_specular = hb.any_specular;
     if ((e = cudaHostAlloc(&h->h_stats, 64 * sizeof(uint32_t), cudaHostAllocDefault)) != cudaSuccess) return bail(e, "cudaHostAlloc stats");

@@ -289,3 +289,28 @@ def realise(builder, name, obj_path_of):
     c = sc["camera"]
     builder.set_camera(c["eye"], c["lookat"], c["up"], c["fov"])
     return sc
+
+
+def handle_replica(pkg, host_scene, name, layout):
+    """A second device handle of scene `name` as `host_scene` (a HostScene that realised it) holds it: the same triangles in the
+    same order (so the same primitive ids), material table and lights, through the C ABI (mirogpu_scene_create).  The host layer
+    owns one global scene like the reference's g_scene, so further handles -- a handle renders one frame at a time, several
+    render frames concurrently (sharding.FramePipeline) -- are made this way.  Single-material triangle scenes only."""
+    sc = SCENES[name]
+    assert len(sc["materials"]) == 1 and "tex" not in sc["materials"][0] and not sc.get("spheres") and not sc.get("planes")
+    m = sc["materials"][0]
+    tri = host_scene.dump_triangles()
+    R = pkg.MiroScene(tri[:, :9], tri[:, 9:], np.zeros(tri.shape[0], np.uint32),
+                      [pkg.phong(m["kd"], m["ks"], m["kt"], m["shininess"], m["refr"])], layout=layout)
+    lights = []
+    for l in sc["lights"]:
+        L = pkg.Light()
+        L.kind = int(l["kind"])
+        L.position[:] = [float(x) for x in l["pos"]]; L.color[:] = [float(x) for x in l["color"]]
+        L.wattage = float(l["wattage"])
+        if l["kind"] != 0:
+            L.normal[:] = [float(x) for x in l["normal"]]; L.radius = float(l["radius"])
+        lights.append(L)
+    R.set_lights(lights)
+    return R
+

@@ -92,8 +92,15 @@ class FramePipeline:
         pipe.drain()                                 # all exchanges done; pipe.host_frame(slot) on rank 0 is complete
     """
 
-    def __init__(self, scene, height, width, world, rank, device, depth=2, group=None):
+    def __init__(self, scene, height, width, world, rank, device, depth=2, group=None, replicas=()):
+        """replicas: further handles of the same scene (a handle renders one frame at a time -- its wave buffers are its own).
+        With k handles, k consecutive frames render concurrently, each on its own stream, so the ragged end of one frame's
+        persistent launches is covered by its neighbours' kernels (the same effect as bench.py's steps in flight); the
+        exchanges still run in frame order on the one side stream, so every rank issues its collectives in the same order."""
         self.S, self.world, self.rank, self.group = scene, world, rank, group
+        self.scenes = [scene] + list(replicas)
+        self.render_streams = [None] + [torch.cuda.Stream(device) for _ in replicas]   # None: the caller's current stream
+        depth = max(depth, len(self.scenes) + 1)
         self.rows, _ = rows_of_rank(height, world, rank)
         self.side = torch.cuda.Stream(device)
         self.slots = []
@@ -110,11 +117,19 @@ class FramePipeline:
 
     def submit(self, cam, params):
         s = self.slots[self.count % len(self.slots)]
+        k = self.count % len(self.scenes)
         self.count += 1
+        s["scene"] = self.scenes[k]
         main = torch.cuda.current_stream()
-        main.wait_event(s["exchanged"])                    # the slot's previous frame has left it
-        self.S.render_device(cam, params, s["rgb"])        # this rank's rows, float radiance
-        s["rendered"].record(main)
+        rs = self.render_streams[k] or main
+        if rs is not main:
+            fork = torch.cuda.Event()
+            fork.record(main)
+            rs.wait_event(fork)                            # whatever the caller queued before this frame
+        with torch.cuda.stream(rs):
+            rs.wait_event(s["exchanged"])                  # the slot's previous frame has left it
+            s["scene"].render_device(cam, params, s["rgb"])   # this rank's rows, float radiance
+            s["rendered"].record(rs)
         with torch.cuda.stream(self.side):
             self.side.wait_event(s["rendered"])
             self.S.frame_max_device(s["rgb"], self.rows, s["max"])
@@ -129,10 +144,13 @@ class FramePipeline:
 
     def rays_traced(self, slot):
         slot["rendered"].synchronize()
-        return self.S.last_call_stats()[0]
+        return slot.get("scene", self.S).last_call_stats()[0]
 
     def host_frame(self, slot):
         return slot["host"]
 
     def drain(self):
+        for rs in self.render_streams:
+            if rs is not None:
+                rs.synchronize()
         self.side.synchronize()

@@ -418,3 +418,47 @@ def test_page_locked_host_buffers_and_image_reuse(pkg, scenes, oracle):
     assert H.last_render_seconds > 0
     c = H.render(w // 2, h // 2)      # a different size reallocates
     assert c.shape == (h // 2, w // 2, 3) and c.max() > 0
+
+
+def test_frame_pipeline_with_several_handles_delivers_the_single_call_frames(pkg, scenes, oracle):
+    """sharding.FramePipeline (bench.py's multi-rank e2e path) with three handles of the scene -- three consecutive frames
+    rendering concurrently on three streams, exchanges in frame order on the side stream: every delivered host frame equals
+    the frame of one synchronous mirogpu_render_rgb8 call with the same seed, and the ray counts agree.  One-rank NCCL group."""
+    import importlib
+    import os
+    import torch.distributed as dist
+    sharding = importlib.import_module(pkg.__name__ + ".sharding")
+    H, S = build_pair(pkg, scenes, oracle, "teapot", layout=pkg.LAYOUT_QBVH4)
+    extra = [scenes.handle_replica(pkg, H, "teapot", pkg.LAYOUT_QBVH4) for _ in range(2)]   # the host layer holds ONE scene
+    w, h = 192, 128
+    dev = torch.device("cuda", 0)
+    created = False
+    if not dist.is_initialized():
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        os.environ.setdefault("MASTER_PORT", "29541")
+        dist.init_process_group("nccl", rank=0, world_size=1, device_id=dev)
+        created = True
+
+    def params(it):
+        return S.render_params(w, h, spp=4, jitter=1, max_depth=10, mode=pkg.RENDER_DIFFUSE_BOUNCE, seed=40 + it, tonemap=0, shadows=0)
+    try:
+        pipe = sharding.FramePipeline(S, h, w, 1, 0, dev, replicas=extra)
+        assert len(pipe.slots) == 4 and len(pipe.scenes) == 3
+        cam = H.camera()
+        nframes = 7
+        slots = [pipe.submit(cam, params(it)) for it in range(nframes)]      # queued without waiting on any frame
+        pipe.drain()
+        # the four slots now hold the last four frames
+        for it in range(nframes - 4, nframes):
+            ref = np.zeros((h, w, 3), np.uint8)
+            S.render_rgb8(cam, params(it), out=ref)
+            assert np.array_equal(pipe.host_frame(slots[it]).numpy(), ref), it
+        # ray counts: read per frame (waits for that frame's render)
+        for it in range(3):
+            got = pipe.rays_traced(pipe.submit(cam, params(it)))
+            S.render_rgb8(cam, params(it), out=np.zeros((h, w, 3), np.uint8))
+            assert got == S.last_call_stats()[0] and got > w * h * 4
+        pipe.drain()
+    finally:
+        if created:
+            dist.destroy_process_group()
