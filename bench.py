@@ -491,11 +491,16 @@ def run_ours(args):
         # MIRO_BENCH_E2E_HANDLES = k (default 3): k handles of the scene per rank (0.25 GB each), k consecutive frames rendering
         # concurrently on k streams -- a handle renders one frame at a time
         n_handles = max(1, int(os.environ.get("MIRO_BENCH_E2E_HANDLES", "3")))
+        if n_handles > 1:
+            # with several frames in flight the library's own split of a frame into two half-batches on two streams only makes the
+            # launches smaller (one rank's share of an N = 8 run on one GPU: 1.229 -> 1.177 ms per frame without it; read once, at
+            # the process's first render, which is the one below)
+            os.environ.setdefault("MIROGPU_RENDER_STREAMS", "1")
         replicas = [scenes.handle_replica(pkg, H, SCENE, layout) for _ in range(n_handles - 1)]
         for Sx in replicas:
             Sx.set_kernel_variant(args.variant)
         pipe = sharding.FramePipeline(S, HEIGHT, WIDTH, world, rank, dev, replicas=replicas)
-        e2e_call += f"; {n_handles} handles of the scene per rank, {n_handles} consecutive frames rendering concurrently"
+        e2e_call += f"; {n_handles} handles of the scene per rank, {n_handles} consecutive frames rendering concurrently, each as whole 16-sample batches"
 
         # Untimed pass over the seeds of the timed frames: rays traced per frame (primary + LIVE bounce rays -- the device counter
         # mirogpu_last_call_stats reads is valid once the frame's render has finished, so reading it costs a host wait per frame;
