@@ -528,16 +528,17 @@ def run_ours(args):
         pipe.drain()
     barrier()
     e2e_s_local = time.perf_counter() - t0
+    exchange_ms = pipe.exchange_ms(last=e2e_steps) if piped else 0.0
     if rank == 0:
         clocks = sampler.stop()
 
     # ---- aggregate over ranks: max time, summed rays ------------------------------------------------------------
-    stats = torch.tensor([ms_local, e2e_s_local, prim_ms, bounce_ms, genb_ms, genp_ms, ms_sequential], dtype=torch.float64, device=dev)
+    stats = torch.tensor([ms_local, e2e_s_local, prim_ms, bounce_ms, genb_ms, genp_ms, ms_sequential, exchange_ms], dtype=torch.float64, device=dev)
     sums = torch.tensor([float(n * args.steps), float(live_local), float(e2e_rays)], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(stats, op=dist.ReduceOp.MAX)
         dist.all_reduce(sums, op=dist.ReduceOp.SUM)
-    ms_total, e2e_s, prim_ms, bounce_ms, genb_ms, genp_ms, ms_sequential = [float(x) for x in stats.tolist()]
+    ms_total, e2e_s, prim_ms, bounce_ms, genb_ms, genp_ms, ms_sequential, exchange_ms = [float(x) for x in stats.tolist()]
     prim_total, live_total, e2e_total = [float(x) for x in sums.tolist()]
     rays_total = prim_total + live_total
     value = rays_total / (ms_total * 1e-3) / 1e6
@@ -605,6 +606,7 @@ def run_ours(args):
                              "two half-batches (8 samples each) per step on two streams: each launch's ragged end overlaps the other half's kernels"),
                 "ms_per_step_sequential": ms_sequential / args.steps,
                 "per_gpu_ms": {"primary_trace": prim_ms, "gen_bounce": genb_ms, "bounce_trace": bounce_ms, "gen_primary": genp_ms,
+                               "e2e_frame_exchange_elapsed": exchange_ms,   # N > 1: elapsed device time of a frame's exchange on the side stream, first to last operation -- it runs underneath the following frames' persistent trace kernels and waits for SM slots between them, so this is a latency (what the slots of the frame pipeline have to cover), not a cost added to the frame
                                "note": "max over ranks of each rank's mean over a sequential replay of the timed steps right after the timed region "
                                        "(same rays, whole-step launches one after the other on one stream, CUDA events around each kernel on that stream); "
                                        "ms_per_step_sequential is that replay's step time"},

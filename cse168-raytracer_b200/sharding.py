@@ -114,6 +114,7 @@ class FramePipeline:
                 "rendered": torch.cuda.Event(), "exchanged": torch.cuda.Event(),
             })
         self.count = 0
+        self.timings = []     # per submitted frame: (exchange begin, exchange end) events on the side stream, see exchange_ms()
 
     def submit(self, cam, params):
         s = self.slots[self.count % len(self.slots)]
@@ -132,6 +133,8 @@ class FramePipeline:
             s["rendered"].record(rs)
         with torch.cuda.stream(self.side):
             self.side.wait_event(s["rendered"])
+            t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            t0.record(self.side)
             self.S.frame_max_device(s["rgb"], self.rows, s["max"])
             if self.world > 1:
                 dist.all_reduce(s["max"], op=dist.ReduceOp.MAX, group=self.group)
@@ -139,7 +142,9 @@ class FramePipeline:
             full = s["gather"](s["u8"])
             if self.rank == 0:
                 s["host"].copy_(full, non_blocking=True)
+            t1.record(self.side)
             s["exchanged"].record(self.side)
+            self.timings.append((t0, t1))
         return s
 
     def rays_traced(self, slot):
@@ -148,6 +153,12 @@ class FramePipeline:
 
     def host_frame(self, slot):
         return slot["host"]
+
+    def exchange_ms(self, last=None):
+        """Mean device time of a frame's exchange (frame maximum, all_reduce, tone map, all_gather, reorder, rank 0's copy to the
+        host) on the side stream, over the last `last` submitted frames (all if None).  Call after drain()."""
+        ev = self.timings if last is None else self.timings[-last:]
+        return sum(a.elapsed_time(b) for a, b in ev) / max(1, len(ev))
 
     def drain(self):
         for rs in self.render_streams:
