@@ -145,6 +145,8 @@ class FramePipeline:
             t1.record(self.side)
             s["exchanged"].record(self.side)
             self.timings.append((t0, t1))
+            if len(self.timings) > 1024:       # long sequences: keep the recent frames only
+                del self.timings[:512]
         return s
 
     def rays_traced(self, slot):
