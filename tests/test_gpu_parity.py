@@ -354,9 +354,9 @@ def test_headline_config_vs_reference_traversal(host_scenes, oracle_scene, pkg):
 
 
 def test_half_batches_equal_the_whole_batch(host_scenes, pkg):
-    """bench.py issues a step as two half-batches on two streams: the halves must be the whole batch -- same eye rays (sample
-    offsets), same bounce rays (random-number index offsets), same hits -- so the timed schedule and its sequential replay do
-    identical work."""
+    """bench.py's half-batch schedule (MIRO_BENCH_INFLIGHT=0; the default keeps whole steps in flight on several streams) issues
+    a step as two half-batches on two streams: the halves must be the whole batch -- same eye rays (sample offsets), same bounce
+    rays (random-number index offsets), same hits -- so the timed schedule and its sequential replay do identical work."""
     H, S = host_scenes("bunny_teapot", 3)
     cam = H.camera()
     w, h, spp = 320, 180, 4
