@@ -386,3 +386,43 @@ def test_half_batches_equal_the_whole_batch(host_scenes, pkg):
     torch.cuda.synchronize()
     for a, b in ((r0, r1), (h0, h1), (b0, b1), (g0, g1)):
         assert torch.equal(a.view(torch.int32), b.view(torch.int32))
+
+
+def test_steps_in_flight_equal_sequential_steps(host_scenes, pkg):
+    """bench.py's default schedule keeps three whole steps in flight: consecutive steps on three streams, each with its own ray
+    and hit buffers, all through ONE handle (the persistent kernels of concurrent launches draw tickets from different slots of
+    the handle's ring).  Every step's rays and hits must be the bits of the same step run alone."""
+    H, S = host_scenes("bunny_teapot", 3)
+    cam = H.camera()
+    w, h, spp = 320, 180, 4
+    n = w * h * spp
+    dev = "cuda"
+
+    def bufs():
+        return [torch.empty((n, 8), dtype=torch.float32, device=dev), torch.empty((n, 4), dtype=torch.float32, device=dev),
+                torch.empty((n, 8), dtype=torch.float32, device=dev), torch.empty((n, 4), dtype=torch.float32, device=dev)]
+
+    def whole_step(it, B):
+        r, hh, b, g = B
+        S.generate_primary(cam, w, h, r, jitter=1, seed=168, sample=it * spp, samples=spp)
+        S.intersect_device(r, hh, mode=pkg.CLOSEST_HIT | pkg.HINT_COHERENT)
+        S.generate_bounce(r, hh, b, seed=168, sample=it, index_base=0x01000000)
+        S.intersect_device(b, g)
+
+    nsteps, k = 7, 3
+    streams = [torch.cuda.current_stream()] + [torch.cuda.Stream() for _ in range(k - 1)]
+    flight = [bufs() for _ in range(k)]
+    kept = {}
+    torch.cuda.synchronize()
+    for it in range(nsteps):
+        with torch.cuda.stream(streams[it % k]):
+            whole_step(it, flight[it % k])
+            if it >= nsteps - k:      # the last k steps stay in their buffers
+                kept[it] = flight[it % k]
+    torch.cuda.synchronize()
+    alone = bufs()
+    for it, B in kept.items():
+        whole_step(it, alone)
+        torch.cuda.synchronize()
+        for a, b in zip(alone, B):
+            assert torch.equal(a.view(torch.int32), b.view(torch.int32)), it
