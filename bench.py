@@ -475,7 +475,8 @@ def run_ours(args):
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1"); os.environ.setdefault("MASTER_PORT", "29533")
         dist.init_process_group("nccl", rank=0, world_size=1, device_id=torch.device("cuda", local))
     if piped:
-        e2e_call += (" per rank -> all_reduce(max) of the tone-map constant, 8-bit rows, NCCL all_gather of the row shards, rank 0 copies the frame to the host; "
+        e2e_call = ("mirogpu_render_device (Scene::raytraceImage of this rank's rows, diffuse-bounce mode, float radiance in HBM; rays = primary + LIVE bounce rays)"
+                    " per rank -> mirogpu_frame_max_device, all_reduce(max) of the tone-map constant, mirogpu_tonemap_rows_rgb8_device, NCCL all_gather of the 8-bit row shards, rank 0 copies the frame to pinned host memory; "
                      "frames in flight (the exchange of frame i overlaps the render of frame i + 1; the host queues the timed frames without waiting on any -- "
                      "their live-ray counts, a function of the seed alone, are read from an untimed pass over the same seeds -- and all frames are delivered inside the timed region)")
     if not piped:
